@@ -1,0 +1,250 @@
+// common.cuh -- shared internals of libhordeb200: the device-resident array
+// type (the Concrete-equivalent carrier of CarriersConcrete.hs:150-155,293:
+// shape + strides + offset over reference-counted storage), the caching
+// allocator, error plumbing and launch helpers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/hordeb200.h"
+
+#define HB_R HB_MAX_RANK
+
+// ----------------------------------------------------------------- storage
+struct hb_storage {
+  void *ptr;
+  size_t bytes;      // size-class size handed out by the allocator
+  std::atomic<int> rc;
+};
+
+struct hb_array {
+  std::atomic<int> rc;
+  hb_storage *st;    // may be nullptr for zero-sized arrays
+  hb_dtype dt;
+  int rank;
+  int64_t shape[HB_R];
+  int64_t strides[HB_R];  // in elements; 0 = broadcast, <0 = reversed
+  int64_t offset;         // in elements from st->ptr
+};
+
+// ------------------------------------------------------------ global state
+struct hb_global {
+  bool inited = false;
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  std::atomic<uint64_t> launches{0};
+  std::atomic<uint64_t> live_bytes{0};
+  std::atomic<uint64_t> reserved_bytes{0};
+  // scratch for two-pass reductions / scatter bookkeeping (grown on demand)
+  void *scratch = nullptr;
+  size_t scratch_bytes = 0;
+  bool capturing = false;
+  cudaEvent_t events[64] = {};
+};
+extern hb_global g_hb;
+
+// ------------------------------------------------------------------ errors
+void hb_set_error(const char *fmt, ...);
+#define HB_FAIL(code, ...)        \
+  do {                            \
+    hb_set_error(__VA_ARGS__);    \
+    return (code);                \
+  } while (0)
+#define HB_REQUIRE(cond, ...)                     \
+  do {                                            \
+    if (!(cond)) HB_FAIL(HB_ERR_INVALID, __VA_ARGS__); \
+  } while (0)
+#define HB_CUDA(call)                                                     \
+  do {                                                                    \
+    cudaError_t e_ = (call);                                              \
+    if (e_ != cudaSuccess)                                                \
+      HB_FAIL(HB_ERR_CUDA, "%s failed: %s (%s:%d)", #call,                \
+              cudaGetErrorString(e_), __FILE__, __LINE__);                \
+  } while (0)
+#define HB_TRY(call)            \
+  do {                          \
+    int s_ = (call);            \
+    if (s_ != HB_OK) return s_; \
+  } while (0)
+#define HB_CHECK_INIT() HB_REQUIRE(g_hb.inited, "hb_init has not been called")
+
+// count + check a kernel launch
+#define HB_LAUNCHED()                                                  \
+  do {                                                                 \
+    g_hb.launches.fetch_add(1, std::memory_order_relaxed);             \
+    cudaError_t e_ = cudaPeekAtLastError();                            \
+    if (e_ != cudaSuccess) {                                           \
+      cudaGetLastError();                                              \
+      HB_FAIL(HB_ERR_CUDA, "kernel launch failed: %s (%s:%d)",         \
+              cudaGetErrorString(e_), __FILE__, __LINE__);             \
+    }                                                                  \
+  } while (0)
+
+// ---------------------------------------------------------------- helpers
+static inline size_t hb_dtype_size(hb_dtype dt) {
+  switch (dt) {
+    case HB_F64: case HB_I64: return 8;
+    case HB_F32: case HB_I32: return 4;
+    case HB_I16: return 2;
+    default: return 1;
+  }
+}
+static inline bool hb_is_float(hb_dtype dt) { return dt == HB_F64 || dt == HB_F32; }
+static inline const char *hb_dtype_name(hb_dtype dt) {
+  static const char *n[] = {"f64", "f32", "i64", "i32", "i16", "i8", "bool"};
+  return (int)dt >= 0 && (int)dt <= 6 ? n[dt] : "?";
+}
+static inline int64_t hb_numel(const hb_array *a) {
+  int64_t n = 1;
+  for (int i = 0; i < a->rank; i++) n *= a->shape[i];
+  return n;
+}
+static inline bool hb_contig(const hb_array *a) {
+  int64_t s = 1;
+  for (int i = a->rank - 1; i >= 0; i--) {
+    if (a->shape[i] != 1 && a->strides[i] != s) return false;
+    s *= a->shape[i];
+  }
+  return true;
+}
+static inline void *hb_data(const hb_array *a) {
+  return a->st ? (char *)a->st->ptr + a->offset * (int64_t)hb_dtype_size(a->dt) : nullptr;
+}
+static inline bool hb_same_shape(const hb_array *a, const hb_array *b) {
+  if (a->rank != b->rank) return false;
+  for (int i = 0; i < a->rank; i++)
+    if (a->shape[i] != b->shape[i]) return false;
+  return true;
+}
+std::string hb_shape_str(const hb_array *a);
+
+// allocator (alloc.cu)
+int hb_alloc_storage(size_t bytes, hb_storage **out);
+void hb_storage_release(hb_storage *st);
+int hb_scratch(size_t bytes, void **ptr);  // persistent scratch, >= bytes
+
+// array construction (array.cu)
+int hb_new_array(hb_dtype dt, int rank, const int64_t *shape, hb_array **out);  // fresh contiguous
+hb_array *hb_new_view(const hb_array *parent);  // same storage, copies metadata
+int hb_zeros(hb_dtype dt, int rank, const int64_t *shape, hb_array **out);
+// write one scalar of dtype dt (read from host memory `value`) to device `dst`
+int hb_fill_scalar(void *dst, hb_dtype dt, const void *value);
+
+// ------------------------------------------------- strided iteration space
+// Collapsed description of up to 3 operands over a common logical shape.
+#define HB_MAXOPS 4
+struct hb_iter {
+  int rank;
+  int64_t shape[HB_R];
+  int64_t stride[HB_MAXOPS][HB_R];
+};
+// Build a collapsed iteration space for `nops` arrays of identical logical
+// shape: size-1 axes dropped, adjacent axes merged when every operand allows.
+void hb_make_iter(int nops, const hb_array *const *ops, hb_iter *it);
+
+// Generic: collapse arbitrary (shape, strides[nops]) lists in place.
+void hb_collapse(int *rank, int64_t *shape, int nops, int64_t (*strides)[HB_R]);
+
+static inline int hb_blocks_for(int64_t n, int per_block, int max_blocks = 1 << 30) {
+  int64_t b = (n + per_block - 1) / per_block;
+  if (b < 1) b = 1;
+  if (b > max_blocks) b = max_blocks;
+  return (int)b;
+}
+
+// dtype dispatch ---------------------------------------------------------
+#define HB_DISPATCH_ALL(dt, T, ...)                                  \
+  switch (dt) {                                                      \
+    case HB_F64: { typedef double T; __VA_ARGS__; } break;           \
+    case HB_F32: { typedef float T; __VA_ARGS__; } break;            \
+    case HB_I64: { typedef int64_t T; __VA_ARGS__; } break;          \
+    case HB_I32: { typedef int32_t T; __VA_ARGS__; } break;          \
+    case HB_I16: { typedef int16_t T; __VA_ARGS__; } break;          \
+    case HB_I8: { typedef int8_t T; __VA_ARGS__; } break;            \
+    case HB_BOOL: { typedef uint8_t T; __VA_ARGS__; } break;         \
+    default: HB_FAIL(HB_ERR_INVALID, "bad dtype %d", (int)(dt));     \
+  }
+#define HB_DISPATCH_FLOAT(dt, T, ...)                                \
+  switch (dt) {                                                      \
+    case HB_F64: { typedef double T; __VA_ARGS__; } break;           \
+    case HB_F32: { typedef float T; __VA_ARGS__; } break;            \
+    default: HB_FAIL(HB_ERR_INVALID, "floating dtype required, got %s", hb_dtype_name(dt)); \
+  }
+#define HB_DISPATCH_NUM(dt, T, ...)                                  \
+  switch (dt) {                                                      \
+    case HB_F64: { typedef double T; __VA_ARGS__; } break;           \
+    case HB_F32: { typedef float T; __VA_ARGS__; } break;            \
+    case HB_I64: { typedef int64_t T; __VA_ARGS__; } break;          \
+    case HB_I32: { typedef int32_t T; __VA_ARGS__; } break;          \
+    case HB_I16: { typedef int16_t T; __VA_ARGS__; } break;          \
+    case HB_I8: { typedef int8_t T; __VA_ARGS__; } break;            \
+    default: HB_FAIL(HB_ERR_INVALID, "numeric dtype required, got %s", hb_dtype_name(dt)); \
+  }
+// byte-size dispatch for pure data movement (bit-exact for every dtype)
+#define HB_DISPATCH_BYTES(dt, T, ...)                                \
+  switch (hb_dtype_size(dt)) {                                       \
+    case 8: { typedef uint64_t T; __VA_ARGS__; } break;              \
+    case 4: { typedef uint32_t T; __VA_ARGS__; } break;              \
+    case 2: { typedef uint16_t T; __VA_ARGS__; } break;              \
+    default: { typedef uint8_t T; __VA_ARGS__; } break;              \
+  }
+
+// ---------------------------------------------------- device-side helpers
+#ifdef __CUDACC__
+struct hb_dims {  // by-value kernel parameter
+  int rank;
+  int64_t shape[HB_R];
+  int64_t stride[HB_R];
+};
+// linear index (row-major over d.shape) -> element offset with d.stride
+__device__ __forceinline__ int64_t hb_offset_of(const hb_dims &d, int64_t lin) {
+  int64_t off = 0;
+#pragma unroll 1
+  for (int i = d.rank - 1; i >= 0; i--) {
+    int64_t q = lin / d.shape[i];
+    int64_t r = lin - q * d.shape[i];
+    off += r * d.stride[i];
+    lin = q;
+  }
+  return off;
+}
+// xor-shuffle for any trivially copyable type of 1, 2, 4 or 8 bytes
+template <typename T>
+__device__ __forceinline__ T hb_shfl_xor(T v, int o) {
+  if constexpr (sizeof(T) == 8) {
+    unsigned long long u;
+    memcpy(&u, &v, 8);
+    unsigned lo = __shfl_xor_sync(0xffffffffu, (unsigned)u, o);
+    unsigned hi = __shfl_xor_sync(0xffffffffu, (unsigned)(u >> 32), o);
+    u = ((unsigned long long)hi << 32) | lo;
+    T r;
+    memcpy(&r, &u, 8);
+    return r;
+  } else if constexpr (sizeof(T) == 4) {
+    unsigned u;
+    memcpy(&u, &v, 4);
+    u = __shfl_xor_sync(0xffffffffu, u, o);
+    T r;
+    memcpy(&r, &u, 4);
+    return r;
+  } else {
+    int u = (int)v;
+    u = __shfl_xor_sync(0xffffffffu, u, o);
+    return (T)u;
+  }
+}
+template <typename T>
+__device__ __forceinline__ T hb_warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += hb_shfl_xor(v, o);
+  return v;
+}
+#endif

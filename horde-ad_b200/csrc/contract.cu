@@ -1,0 +1,357 @@
+// contract.cu -- dense contractions: tsdot1In, tsmatmul2, tsmatvecmul
+// (OpsConcrete.hs:234-242) and the fused `ssumN . sdot1In` contraction the
+// simplified artifacts contain (TestMnistPP.hs:735: `ssumN @[3,4] (sdot1In ..)`).
+//
+// The reference expresses matmul -- and, after contraction, convolution -- as
+// sdot1In over stride-0 (sreplicate) and permuted (stranspose) VIEWS, which are
+// free on the CPU.  Here the views are never materialised either: the axes of
+// the two equal-shape operands are classified from their strides into
+//   M axes (b has stride 0), N axes (a has stride 0), batch axes (both move),
+//   K axes (the reduced ones),
+// and one strided batched GEMM engine walks the operands in place through
+// per-tile offset tables in shared memory (overlapping im2col views from
+// affine gathers included).
+//
+// Engine: 64x64 output tile, K chunk 16, 256 threads, FP64 DMMA (mma.sync
+// m8n8k4 -> SASS DMMA.8x8x4, the only FP64 tensor shape on sm_100a; tcgen05
+// has no FP64 kind) for doubles, FFMA register tiles for floats.  Tensor-pipe
+// roofline: 2*M*N*K flops against the measured FP64 peak (hb_microbench).
+#include "common.cuh"
+
+#define TM 64
+#define TN 64
+#define TK 16
+
+struct hb_cgroup {
+  int rank;
+  int64_t n;  // product of extents
+  int64_t shape[HB_R];
+  int64_t sa[HB_R], sb[HB_R], sc[HB_R];
+};
+
+struct hb_contractp {
+  hb_cgroup M, N, B, K;
+};
+
+__device__ __forceinline__ void hb_cg_offsets(const hb_cgroup &g, int64_t lin, int64_t &oa, int64_t &ob,
+                                              int64_t &oc) {
+  oa = ob = oc = 0;
+#pragma unroll 1
+  for (int d = g.rank - 1; d >= 0; d--) {
+    int64_t q = lin / g.shape[d], r = lin - q * g.shape[d];
+    oa += r * g.sa[d];
+    ob += r * g.sb[d];
+    oc += r * g.sc[d];
+    lin = q;
+  }
+}
+
+// ---- FP64 tensor-core tile product: warp computes 32(m) x 16(n) of the tile
+__device__ __forceinline__ void hb_dmma(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+#define AS_LD (TM + 8)  // k-major tiles; row stride == 8 (mod 16) doubles: conflict-free fragments
+#define BS_LD (TN + 8)
+
+template <typename T, bool A_KFAST, bool B_KFAST>
+__global__ void __launch_bounds__(256)
+    hb_contract_kernel(const __grid_constant__ hb_contractp P, const T *__restrict__ A,
+                       const T *__restrict__ Bm, T *__restrict__ C) {
+  __shared__ T As[2][TK][AS_LD];
+  __shared__ T Bs[2][TK][BS_LD];
+  __shared__ int64_t offAm[TM], offBn[TN], offCm[TM], offCn[TN];
+  __shared__ int64_t offAk[2][TK], offBk[2][TK];
+
+  const int tid = threadIdx.x;
+  const int64_t m0 = (int64_t)blockIdx.x * TM;
+  const int64_t n0 = (int64_t)blockIdx.y * TN;
+  int64_t ba, bb, bc;
+  hb_cg_offsets(P.B, blockIdx.z, ba, bb, bc);
+  if (tid < TM) {
+    int64_t m = m0 + tid, oa = 0, ob = 0, oc = 0;
+    if (m < P.M.n) hb_cg_offsets(P.M, m, oa, ob, oc);
+    offAm[tid] = oa;
+    offCm[tid] = oc;
+  } else if (tid < TM + TN) {
+    int t = tid - TM;
+    int64_t n = n0 + t, oa = 0, ob = 0, oc = 0;
+    if (n < P.N.n) hb_cg_offsets(P.N, n, oa, ob, oc);
+    offBn[t] = ob;
+    offCn[t] = oc;
+  }
+  const int64_t Ktot = P.K.n;
+  const int nk = (int)((Ktot + TK - 1) / TK);
+
+  auto load_koffs = [&](int buf, int kc) {
+    if (tid < TK) {
+      int64_t k = (int64_t)kc * TK + tid, oa = 0, ob = 0, oc = 0;
+      if (k < Ktot) hb_cg_offsets(P.K, k, oa, ob, oc);
+      offAk[buf][tid] = oa;
+      offBk[buf][tid] = ob;
+    }
+  };
+  // each thread stages 4 elements of A and 4 of B per chunk
+  T ra[4], rb[4];
+  auto fetch = [&](int buf, int kc) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      int e = tid + i * 256;
+      int am, ak, bn, bk;
+      if (A_KFAST) { ak = e % TK; am = e / TK; } else { am = e % TM; ak = e / TM; }
+      if (B_KFAST) { bk = e % TK; bn = e / TK; } else { bn = e % TN; bk = e / TN; }
+      int64_t kA = (int64_t)kc * TK + ak, kB = (int64_t)kc * TK + bk;
+      ra[i] = (m0 + am < P.M.n && kA < Ktot) ? A[ba + offAm[am] + offAk[buf][ak]] : T(0);
+      rb[i] = (n0 + bn < P.N.n && kB < Ktot) ? Bm[bb + offBn[bn] + offBk[buf][bk]] : T(0);
+    }
+  };
+  auto stash = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      int e = tid + i * 256;
+      int am, ak, bn, bk;
+      if (A_KFAST) { ak = e % TK; am = e / TK; } else { am = e % TM; ak = e / TM; }
+      if (B_KFAST) { bk = e % TK; bn = e / TK; } else { bn = e % TN; bk = e / TN; }
+      As[buf][ak][am] = ra[i];
+      Bs[buf][bk][bn] = rb[i];
+    }
+  };
+
+  load_koffs(0, 0);
+  __syncthreads();
+  fetch(0, 0);
+  stash(0);
+  if (nk > 1) load_koffs(1, 1);
+  __syncthreads();
+
+  const int warp = tid >> 5, lane = tid & 31;
+  if constexpr (std::is_same<T, double>::value) {
+    // 8 warps: warp (wm, wn) = (warp % 2, warp / 2) owns rows [32*wm, +32) x cols [16*wn, +16)
+    const int wm = (warp & 1) * 32, wn = (warp >> 1) * 16;
+    const int fr = lane >> 2, fk = lane & 3;  // fragment row/col (A: row fr, k fk; B: k fk, col fr)
+    double acc[4][2][2];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int j = 0; j < 2; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int kc = 0; kc < nk; kc++) {
+      int buf = kc & 1;
+      if (kc + 1 < nk) fetch(buf ^ 1, kc + 1);
+#pragma unroll
+      for (int k4 = 0; k4 < TK; k4 += 4) {
+        double af[4], bf[2];
+#pragma unroll
+        for (int i = 0; i < 4; i++) af[i] = As[buf][k4 + fk][wm + 8 * i + fr];
+#pragma unroll
+        for (int j = 0; j < 2; j++) bf[j] = Bs[buf][k4 + fk][wn + 8 * j + fr];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+          for (int j = 0; j < 2; j++) hb_dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+      }
+      if (kc + 1 < nk) {
+        stash(buf ^ 1);
+        if (kc + 2 < nk) load_koffs(buf, kc + 2);
+      }
+      __syncthreads();
+    }
+    // C fragment: row = lane/4, cols = (lane%4)*2 + {0,1}
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int j = 0; j < 2; j++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          int ml = wm + 8 * i + fr, nl = wn + 8 * j + fk * 2 + e;
+          if (m0 + ml < P.M.n && n0 + nl < P.N.n) C[bc + offCm[ml] + offCn[nl]] = acc[i][j][e];
+        }
+  } else {
+    // FP32: 4x4 register tile per thread, thread (tx, ty) = (tid % 16, tid / 16)
+    const int tx = tid & 15, ty = tid >> 4;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
+    for (int kc = 0; kc < nk; kc++) {
+      int buf = kc & 1;
+      if (kc + 1 < nk) fetch(buf ^ 1, kc + 1);
+#pragma unroll
+      for (int k = 0; k < TK; k++) {
+        float av[4], bv[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) av[i] = As[buf][k][ty + 16 * i];
+#pragma unroll
+        for (int j = 0; j < 4; j++) bv[j] = Bs[buf][k][tx + 16 * j];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+          for (int j = 0; j < 4; j++) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      }
+      if (kc + 1 < nk) {
+        stash(buf ^ 1);
+        if (kc + 2 < nk) load_koffs(buf, kc + 2);
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        int ml = ty + 16 * i, nl = tx + 16 * j;
+        if (m0 + ml < P.M.n && n0 + nl < P.N.n) C[bc + offCm[ml] + offCn[nl]] = acc[i][j];
+      }
+  }
+}
+
+static void cg_finish(hb_cgroup *g) {
+  // collapse adjacent axes jointly over (sa, sb, sc)
+  int64_t s[3][HB_R];
+  for (int i = 0; i < g->rank; i++) { s[0][i] = g->sa[i]; s[1][i] = g->sb[i]; s[2][i] = g->sc[i]; }
+  hb_collapse(&g->rank, g->shape, 3, s);
+  g->n = 1;
+  for (int i = 0; i < g->rank; i++) {
+    g->sa[i] = s[0][i]; g->sb[i] = s[1][i]; g->sc[i] = s[2][i];
+    g->n *= g->shape[i];
+  }
+}
+
+static int64_t min_abs_stride(const hb_cgroup &g, const int64_t *s) {
+  int64_t m = INT64_MAX;
+  for (int i = 0; i < g.rank; i++) {
+    int64_t x = s[i] < 0 ? -s[i] : s[i];
+    if (x && x < m) m = x;
+  }
+  return m;
+}
+
+template <typename T>
+static int launch_contract(hb_contractp &P, const hb_array *a, const hb_array *b, hb_array *o) {
+  cg_finish(&P.M); cg_finish(&P.N); cg_finish(&P.B); cg_finish(&P.K);
+  if (P.M.n == 0 || P.N.n == 0 || P.B.n == 0) return HB_OK;
+  HB_REQUIRE(P.B.n < 65536 && (P.N.n + TN - 1) / TN < 65536, "contract: grid too large");
+  bool a_kfast = min_abs_stride(P.K, P.K.sa) <= min_abs_stride(P.M, P.M.sa);
+  bool b_kfast = min_abs_stride(P.K, P.K.sb) <= min_abs_stride(P.N, P.N.sb);
+  dim3 grid((unsigned)((P.M.n + TM - 1) / TM), (unsigned)((P.N.n + TN - 1) / TN), (unsigned)P.B.n);
+  const T *pa = (const T *)hb_data(a);
+  const T *pb = (const T *)hb_data(b);
+  T *pc = (T *)hb_data(o);
+  if (a_kfast && b_kfast) hb_contract_kernel<T, true, true><<<grid, 256, 0, g_hb.stream>>>(P, pa, pb, pc);
+  else if (a_kfast) hb_contract_kernel<T, true, false><<<grid, 256, 0, g_hb.stream>>>(P, pa, pb, pc);
+  else if (b_kfast) hb_contract_kernel<T, false, true><<<grid, 256, 0, g_hb.stream>>>(P, pa, pb, pc);
+  else hb_contract_kernel<T, false, false><<<grid, 256, 0, g_hb.stream>>>(P, pa, pb, pc);
+  HB_LAUNCHED();
+  return HB_OK;
+}
+
+int hb_reduce_generic(const hb_array *a, const hb_array *b, int nk, const int *kax, int nr,
+                      const int *rax, hb_array *out);
+
+// a, b: equal shapes.  Axes [0, n_lead) and the last axis are contracted; the
+// axes in between index the result.
+static int contract_impl(const hb_array *a, const hb_array *b, int n_lead, hb_array **out) {
+  HB_CHECK_INIT();
+  HB_REQUIRE(a && b && out, "null argument");
+  HB_REQUIRE(a->dt == b->dt && hb_same_shape(a, b), "sdot1In: %s %s vs %s %s", hb_dtype_name(a->dt),
+             hb_shape_str(a).c_str(), hb_dtype_name(b->dt), hb_shape_str(b).c_str());
+  HB_REQUIRE(a->rank >= 1 && n_lead >= 0 && n_lead <= a->rank - 1, "sdot1In: bad rank");
+  HB_REQUIRE(a->dt != HB_BOOL, "sdot1In: numeric dtype required");
+  int r = a->rank;
+  hb_array *o;
+  HB_TRY(hb_new_array(a->dt, r - 1 - n_lead, a->shape + n_lead, &o));
+  int st = HB_OK;
+  int64_t K = a->shape[r - 1];
+  for (int i = 0; i < n_lead; i++) K *= a->shape[i];
+  int64_t outn = hb_numel(o);
+  // classify the kept axes
+  hb_contractp P;
+  memset(&P, 0, sizeof P);
+  bool gemm = hb_is_float(a->dt) && outn > 0 && K > 0;
+  int64_t nM = 1, nN = 1;
+  for (int i = n_lead; i < r - 1 && gemm; i++) {
+    if (a->shape[i] == 1) continue;
+    int64_t oc = o->strides[i - n_lead];
+    hb_cgroup *g;
+    if (a->strides[i] != 0 && b->strides[i] == 0) { g = &P.M; nM *= a->shape[i]; }
+    else if (a->strides[i] == 0 && b->strides[i] != 0) { g = &P.N; nN *= a->shape[i]; }
+    else g = &P.B;  // both move (batch) or both broadcast
+    int k = g->rank++;
+    g->shape[k] = a->shape[i];
+    g->sa[k] = a->strides[i];
+    g->sb[k] = b->strides[i];
+    g->sc[k] = oc;
+  }
+  // worth a GEMM only when there is reuse on both sides
+  if (gemm && (nM < 16 || nN < 16 || K < 4)) gemm = false;
+  if (gemm) {
+    for (int i = 0; i <= n_lead; i++) {
+      int ax = i < n_lead ? i : r - 1;
+      if (a->shape[ax] == 1) continue;
+      int k = P.K.rank++;
+      P.K.shape[k] = a->shape[ax];
+      P.K.sa[k] = a->strides[ax];
+      P.K.sb[k] = b->strides[ax];
+      P.K.sc[k] = 0;
+    }
+    if (a->dt == HB_F64) st = launch_contract<double>(P, a, b, o);
+    else st = launch_contract<float>(P, a, b, o);
+  } else {
+    int kax[HB_R], rax[HB_R];
+    int nk = 0, nr = 0;
+    for (int i = 0; i < n_lead; i++) rax[nr++] = i;
+    for (int i = n_lead; i < r - 1; i++) kax[nk++] = i;
+    rax[nr++] = r - 1;
+    st = hb_reduce_generic(a, b, nk, kax, nr, rax, o);
+  }
+  if (st != HB_OK) {
+    hb_release(o);
+    return st;
+  }
+  *out = o;
+  return HB_OK;
+}
+
+extern "C" int hb_dot_inner(const hb_array *a, const hb_array *b, hb_array **out) {
+  return contract_impl(a, b, 0, out);
+}
+
+extern "C" int hb_dot_inner_sum_leading(const hb_array *a, const hb_array *b, int n_axes, hb_array **out) {
+  return contract_impl(a, b, n_axes, out);
+}
+
+// tsmatmul2 m1 m2 = sdot1In (tr [1,0] (replicate m1)) (tr [0,2,1] (replicate m2))
+// (OpsConcrete.hs:237-242): built here directly as the two broadcast views.
+extern "C" int hb_matmul2(const hb_array *a, const hb_array *b, hb_array **out) {
+  HB_REQUIRE(a && b && out, "null argument");
+  HB_REQUIRE(a->rank == 2 && b->rank == 2 && a->shape[1] == b->shape[0], "smatmul2: %s x %s",
+             hb_shape_str(a).c_str(), hb_shape_str(b).c_str());
+  hb_array *av = hb_new_view(a), *bv = hb_new_view(b);
+  // av[m, p, n] = a[m, n] ; bv[m, p, n] = b[n, p]
+  av->rank = bv->rank = 3;
+  av->shape[0] = a->shape[0]; av->strides[0] = a->strides[0];
+  av->shape[1] = b->shape[1]; av->strides[1] = 0;
+  av->shape[2] = a->shape[1]; av->strides[2] = a->strides[1];
+  bv->shape[0] = a->shape[0]; bv->strides[0] = 0;
+  bv->shape[1] = b->shape[1]; bv->strides[1] = b->strides[1];
+  bv->shape[2] = b->shape[0]; bv->strides[2] = b->strides[0];
+  int st = contract_impl(av, bv, 0, out);
+  hb_release(av);
+  hb_release(bv);
+  return st;
+}
+
+// tsmatvecmul m v = sdot1In m (sreplicate v)  (OpsConcrete.hs:236)
+extern "C" int hb_matvecmul(const hb_array *m, const hb_array *v, hb_array **out) {
+  HB_REQUIRE(m && v && out, "null argument");
+  HB_REQUIRE(m->rank == 2 && v->rank == 1 && m->shape[1] == v->shape[0], "smatvecmul: %s x %s",
+             hb_shape_str(m).c_str(), hb_shape_str(v).c_str());
+  hb_array *vv = hb_new_view(v);
+  vv->rank = 2;
+  vv->shape[0] = m->shape[0]; vv->strides[0] = 0;
+  vv->shape[1] = v->shape[0]; vv->strides[1] = v->strides[0];
+  int st = contract_impl(m, vv, 0, out);
+  hb_release(vv);
+  return st;
+}

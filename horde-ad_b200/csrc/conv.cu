@@ -1,0 +1,156 @@
+// conv.cu -- im2col-free convolution forward and VJPs.
+//
+// Reference semantics: conv2dPreservingS (CommonShapedOps.hs:136-157, zero
+// padding on the HIGH side only via slicezS :225-237) and the handwritten
+// adjoints conv2dPreserving_dInp / _dKrn (TestConvQuickCheck.hs:290-349).
+//
+// No patch tensor is ever built.  The input is copied once into a zero-padded
+// buffer; the im2col operand is then a pure strided VIEW of that buffer
+// (overlapping windows, for dInp with negative kernel strides) and the
+// contraction runs on the strided batched GEMM engine of contract.cu (FP64
+// DMMA), which walks views through per-tile offset tables:
+//   fwd : M=(n,h,w)  N=o          K=(c,kh,kw)
+//   dK  : M=o        N=(c,kh,kw)  K=(n_in,h,w)  batched over image groups,
+//         partials reduced in fixed order (deterministic split-K)
+//   dA  : M=(n,h,w)  N=c          K=(o,kh,kw)   on the low-side padded dB
+// Algorithmic bytes per pass at ConvVjpBench: 205.8 MB,
+// 14.80 GFLOP -> FP64 tensor pipe bound.
+#include "common.cuh"
+
+int hb_copy_into(hb_array *dst, const hb_array *src);  // elementwise.cu
+extern "C" int hb_dot_inner_sum_leading(const hb_array *a, const hb_array *b, int n_axes, hb_array **out);
+
+// zero-padded copy of x[N,C,H,W]: lo rows/cols before, hi after
+static int pad2d(const hb_array *x, int64_t lo_h, int64_t hi_h, int64_t lo_w, int64_t hi_w, hb_array **out) {
+  int64_t sh[4] = {x->shape[0], x->shape[1], x->shape[2] + lo_h + hi_h, x->shape[3] + lo_w + hi_w};
+  hb_array *p;
+  if (lo_h + hi_h + lo_w + hi_w == 0 && hb_contig(x)) {
+    hb_retain((hb_array *)x);
+    *out = (hb_array *)x;
+    return HB_OK;
+  }
+  HB_TRY(hb_zeros(x->dt, 4, sh, &p));
+  hb_array *v = hb_new_view(p);
+  v->shape[2] = x->shape[2];
+  v->shape[3] = x->shape[3];
+  v->offset += lo_h * p->strides[2] + lo_w * p->strides[3];
+  int st = hb_copy_into(v, x);
+  hb_release(v);
+  if (st != HB_OK) {
+    hb_release(p);
+    return st;
+  }
+  *out = p;
+  return HB_OK;
+}
+
+static hb_array *view6(const hb_array *base, int64_t off, const int64_t *shape, const int64_t *strides, int rank) {
+  hb_array *v = hb_new_view(base);
+  v->rank = rank;
+  v->offset += off;
+  for (int i = 0; i < rank; i++) {
+    v->shape[i] = shape[i];
+    v->strides[i] = strides[i];
+  }
+  return v;
+}
+
+extern "C" int hb_conv2d_preserving(const hb_array *K, const hb_array *A, hb_array **out) {
+  HB_CHECK_INIT();
+  HB_REQUIRE(K && A && out, "null argument");
+  HB_REQUIRE(K->rank == 4 && A->rank == 4 && K->dt == A->dt && hb_is_float(A->dt),
+             "conv2dPreserving: rank-4 floating operands required");
+  HB_REQUIRE(K->shape[1] == A->shape[1], "conv2dPreserving: kernel %s vs input %s", hb_shape_str(K).c_str(),
+             hb_shape_str(A).c_str());
+  int64_t N = A->shape[0], Ci = A->shape[1], H = A->shape[2], W = A->shape[3];
+  int64_t Co = K->shape[0], KH = K->shape[2], KW = K->shape[3];
+  if (N * Co * H * W == 0 || Ci * KH * KW == 0) {
+    int64_t sh[4] = {N, Co, H, W};
+    return hb_zeros(A->dt, 4, sh, out);
+  }
+  hb_array *Ap;
+  HB_TRY(pad2d(A, 0, KH - 1, 0, KW - 1, &Ap));
+  // operands over the index space [kept: n, o, h, w | reduced(last... ) ]
+  // layout for hb_dot_inner_sum_leading: leading reduced axes (c, kh), kept
+  // (n, o, h, w), last reduced axis kw.
+  int64_t shp[7] = {Ci, KH, N, Co, H, W, KW};
+  int64_t sa[7] = {Ap->strides[1], Ap->strides[2], Ap->strides[0], 0, Ap->strides[2], Ap->strides[3], Ap->strides[3]};
+  int64_t sk[7] = {K->strides[1], K->strides[2], 0, K->strides[0], 0, 0, K->strides[3]};
+  hb_array *va = view6(Ap, 0, shp, sa, 7);
+  hb_array *vk = view6(K, 0, shp, sk, 7);
+  int st = hb_dot_inner_sum_leading(va, vk, 2, out);
+  hb_release(va);
+  hb_release(vk);
+  hb_release(Ap);
+  return st;
+}
+
+extern "C" int hb_conv2d_preserving_dkrn(const hb_array *A, const hb_array *dB, int KH, int KW,
+                                         hb_array **out) {
+  HB_CHECK_INIT();
+  HB_REQUIRE(A && dB && out, "null argument");
+  HB_REQUIRE(A->rank == 4 && dB->rank == 4 && A->dt == dB->dt && hb_is_float(A->dt),
+             "conv2dPreserving_dKrn: rank-4 floating operands required");
+  HB_REQUIRE(A->shape[0] == dB->shape[0] && A->shape[2] == dB->shape[2] && A->shape[3] == dB->shape[3],
+             "conv2dPreserving_dKrn: input %s vs cotangent %s", hb_shape_str(A).c_str(), hb_shape_str(dB).c_str());
+  HB_REQUIRE(KH >= 0 && KW >= 0, "conv2dPreserving_dKrn: bad kernel size");
+  int64_t N = A->shape[0], Ci = A->shape[1], H = A->shape[2], W = A->shape[3], Co = dB->shape[1];
+  int64_t ksh[4] = {Co, Ci, KH, KW};
+  if (N * H * W == 0 || Co * Ci * KH * KW == 0) return hb_zeros(A->dt, 4, ksh, out);
+  hb_array *Ap;
+  HB_TRY(pad2d(A, 0, KH - 1, 0, KW - 1, &Ap));
+  // deterministic split-K over image groups: G partial kernels, summed in order
+  int64_t tiles = ((Co + 63) / 64) * ((Ci * KH * KW + 63) / 64);
+  int64_t G = 1;
+  while (G * 2 <= N && N % (G * 2) == 0 && tiles * G < 2 * (int64_t)g_hb.sm_count) G *= 2;
+  int64_t Nin = N / G;
+  // index space: leading reduced (n_in, h), kept (g, o, c, kh, kw), last reduced w
+  int64_t shp[8] = {Nin, H, G, Co, Ci, KH, KW, W};
+  int64_t sa[8] = {Ap->strides[0], Ap->strides[2], Ap->strides[0] * Nin, 0, Ap->strides[1], Ap->strides[2], Ap->strides[3], Ap->strides[3]};
+  int64_t sb[8] = {dB->strides[0], dB->strides[2], dB->strides[0] * Nin, dB->strides[1], 0, 0, 0, dB->strides[3]};
+  hb_array *va = view6(Ap, 0, shp, sa, 8);
+  hb_array *vb = view6(dB, 0, shp, sb, 8);
+  hb_array *part = nullptr;
+  // a := dB view (M = o), b := A view (N = c,kh,kw)
+  int st = hb_dot_inner_sum_leading(vb, va, 2, &part);
+  hb_release(va);
+  hb_release(vb);
+  hb_release(Ap);
+  if (st != HB_OK) return st;
+  if (G == 1) {
+    int64_t zero = 0;
+    st = hb_index_prefix(part, 1, &zero, out);
+  } else {
+    st = hb_sum_leading(part, 1, out);
+  }
+  hb_release(part);
+  return st;
+}
+
+extern "C" int hb_conv2d_preserving_dinp(const hb_array *K, const hb_array *dB, hb_array **out) {
+  HB_CHECK_INIT();
+  HB_REQUIRE(K && dB && out, "null argument");
+  HB_REQUIRE(K->rank == 4 && dB->rank == 4 && K->dt == dB->dt && hb_is_float(K->dt),
+             "conv2dPreserving_dInp: rank-4 floating operands required");
+  HB_REQUIRE(K->shape[0] == dB->shape[1], "conv2dPreserving_dInp: kernel %s vs cotangent %s",
+             hb_shape_str(K).c_str(), hb_shape_str(dB).c_str());
+  int64_t N = dB->shape[0], Co = dB->shape[1], H = dB->shape[2], W = dB->shape[3];
+  int64_t Ci = K->shape[1], KH = K->shape[2], KW = K->shape[3];
+  int64_t ash[4] = {N, Ci, H, W};
+  if (N * Ci * H * W == 0 || Co * KH * KW == 0) return hb_zeros(K->dt, 4, ash, out);
+  hb_array *Bp;
+  HB_TRY(pad2d(dB, KH - 1, 0, KW - 1, 0, &Bp));
+  // dA[n,c,h,w] = sum_{o,kh,kw} Bp[n,o,h+(KH-1)-kh, w+(KW-1)-kw] K[o,c,kh,kw]
+  // index space: leading reduced (o, kh), kept (n, c, h, w), last reduced kw
+  int64_t shp[7] = {Co, KH, N, Ci, H, W, KW};
+  int64_t sb[7] = {Bp->strides[1], -Bp->strides[2], Bp->strides[0], 0, Bp->strides[2], Bp->strides[3], -Bp->strides[3]};
+  int64_t sk[7] = {K->strides[0], K->strides[2], 0, K->strides[1], 0, 0, K->strides[3]};
+  int64_t off = (KH - 1) * Bp->strides[2] + (KW - 1) * Bp->strides[3];
+  hb_array *vb = view6(Bp, off, shp, sb, 7);
+  hb_array *vk = view6(K, 0, shp, sk, 7);
+  int st = hb_dot_inner_sum_leading(vb, vk, 2, out);
+  hb_release(vb);
+  hb_release(vk);
+  hb_release(Bp);
+  return st;
+}

@@ -1,0 +1,749 @@
+// ixprog.cu -- index-function programs and the kernels driven by them:
+// tsgather (OpsConcrete.hs:321-323,1621-1665), tsscatter (:318-320,
+// 1529-1619), tsoneHot (:1516-1525) and fused elementwise maps.
+//
+// Kernel selection ("kernel generator for index functions"):
+//   * affine program, provably in bounds  -> the gather IS a strided view of
+//     the source (overlapping windows allowed): zero bytes moved, no launch.
+//   * affine program with out-of-bounds    -> masked strided copy, the index
+//     arithmetic folded into per-axis strides + per-component bound checks.
+//   * general program (table lookups, kargMax, ifH on tensor data ...)
+//     -> the VM evaluates the program once per shm position into an offset
+//     table, then a pure bandwidth copy moves the shn slices; positions of
+//     rank-0 slices are fused into one pass.
+// Scatter is deterministic and reproduces the reference's accumulation order
+// (row-major over the source positions, OpsConcrete.hs:1594-1601): counting
+// pass -> exclusive scan -> fill -> per-destination sort by source position
+// -> sequential sum; when no destination is hit twice the sort/sum stages
+// exit immediately and a direct store kernel does the work.
+// HBM roofline: 2*sizeof(T) bytes per moved element (+ index tables).
+#include "iter.cuh"
+#include "vm.cuh"
+
+// ------------------------------------------------------------------ build
+extern "C" int hb_ixprog_build(const hb_insn *code, int n_insns, int n_vars, int n_out,
+                               hb_array *const *tensors, int n_tensors, int f32, hb_ixprog **out) {
+  HB_REQUIRE(code && out, "null argument");
+  HB_REQUIRE(n_insns >= 0 && n_insns <= HB_VM_MAX_INSNS, "index program too long: %d instructions (max %d)",
+             n_insns, HB_VM_MAX_INSNS);
+  HB_REQUIRE(n_vars >= 0 && n_vars <= HB_R, "index program: %d variables", n_vars);
+  HB_REQUIRE(n_out >= 0 && n_out <= HB_VM_MAX_OUT, "index program: %d outputs", n_out);
+  HB_REQUIRE(n_tensors >= 0 && n_tensors <= HB_VM_MAX_TENSORS, "index program: %d tensor operands (max %d)",
+             n_tensors, HB_VM_MAX_TENSORS);
+  hb_ixprog *p = new hb_ixprog;
+  memset(&p->vm, 0, sizeof p->vm);
+  p->vm.n_insns = n_insns;
+  p->vm.n_vars = n_vars;
+  p->vm.n_out = n_out;
+  p->vm.f32 = f32;
+  p->n_tensors = n_tensors;
+  bool seen_out[HB_VM_MAX_OUT] = {};
+  for (int i = 0; i < n_insns; i++) {
+    const hb_insn &I = code[i];
+    bool ok = I.op < HB_VM_OP_COUNT && I.dst < HB_VM_MAX_REGS && I.a < HB_VM_MAX_REGS;
+    if (I.op == HB_VM_IVAR) ok = ok && I.a < n_vars;
+    if (I.op == HB_VM_TBL || I.op == HB_VM_ARGMAX || I.op == HB_VM_ARGMIN) {
+      ok = ok && I.a < n_tensors && I.n <= 8;
+      if (ok) {
+        int need = I.n + (I.op == HB_VM_TBL ? 0 : 1);
+        ok = tensors[I.a] && tensors[I.a]->rank == need && need <= HB_VM_TRANK;
+      }
+    }
+    if (I.op == HB_VM_OUT) {
+      ok = ok && I.b < n_out;
+      if (ok) seen_out[I.b] = true;
+    }
+    if (!ok) {
+      delete p;
+      HB_FAIL(HB_ERR_INVALID, "index program: malformed instruction %d (op %d)", i, (int)I.op);
+    }
+    p->vm.code[i] = I;
+  }
+  for (int c = 0; c < n_out; c++)
+    if (!seen_out[c]) {
+      delete p;
+      HB_FAIL(HB_ERR_INVALID, "index program: output component %d is never written", c);
+    }
+  for (int t = 0; t < n_tensors; t++) {
+    hb_array *a = tensors[t];
+    hb_retain(a);
+    p->held[t] = a;
+    hb_vm_tensor &vt = p->vm.tensors[t];
+    vt.ptr = hb_data(a);
+    vt.dtype = a->dt;
+    vt.rank = a->rank;
+    for (int i = 0; i < a->rank && i < HB_VM_TRANK; i++) {
+      vt.shape[i] = a->shape[i];
+      vt.stride[i] = a->strides[i];
+    }
+  }
+  // affine classification by abstract interpretation over (c0, coef[])
+  struct Aff { bool ok; int64_t c0; int64_t k[HB_R]; };
+  Aff regs[HB_VM_MAX_REGS];
+  for (auto &r : regs) { r.ok = false; r.c0 = 0; memset(r.k, 0, sizeof r.k); }
+  p->affine = true;
+  for (int i = 0; i < n_insns; i++) {
+    const hb_insn &I = code[i];
+    Aff r; r.ok = false; r.c0 = 0; memset(r.k, 0, sizeof r.k);
+    switch (I.op) {
+      case HB_VM_IVAR: r.ok = true; r.k[I.a] = 1; break;
+      case HB_VM_ICONST: r.ok = true; r.c0 = I.imm.i; break;
+      case HB_VM_IADD: case HB_VM_ISUB: {
+        const Aff &x = regs[I.a], &y = regs[I.b];
+        if (x.ok && y.ok) {
+          r.ok = true;
+          int64_t s = I.op == HB_VM_IADD ? 1 : -1;
+          r.c0 = x.c0 + s * y.c0;
+          for (int k = 0; k < HB_R; k++) r.k[k] = x.k[k] + s * y.k[k];
+        }
+      } break;
+      case HB_VM_INEG: {
+        const Aff &x = regs[I.a];
+        if (x.ok) { r.ok = true; r.c0 = -x.c0; for (int k = 0; k < HB_R; k++) r.k[k] = -x.k[k]; }
+      } break;
+      case HB_VM_IMUL: {
+        const Aff &x = regs[I.a], &y = regs[I.b];
+        auto isconst = [](const Aff &a) { if (!a.ok) return false; for (int k = 0; k < HB_R; k++) if (a.k[k]) return false; return true; };
+        if (x.ok && y.ok && (isconst(x) || isconst(y))) {
+          const Aff &c = isconst(x) ? x : y; const Aff &v = isconst(x) ? y : x;
+          r.ok = true; r.c0 = c.c0 * v.c0;
+          for (int k = 0; k < HB_R; k++) r.k[k] = c.c0 * v.k[k];
+        }
+      } break;
+      case HB_VM_OUT: {
+        const Aff &x = regs[I.a];
+        if (x.ok) { p->c0[I.b] = x.c0; for (int k = 0; k < HB_R; k++) p->coef[I.b][k] = x.k[k]; }
+        else p->affine = false;
+      } continue;
+      default: break;
+    }
+    regs[I.dst] = r;
+  }
+  *out = p;
+  return HB_OK;
+}
+
+extern "C" int hb_ixprog_free(hb_ixprog *p) {
+  if (!p) return HB_OK;
+  for (int t = 0; t < p->n_tensors; t++) hb_release(p->held[t]);
+  delete p;
+  return HB_OK;
+}
+
+extern "C" int hb_ixprog_is_affine(const hb_ixprog *p, int *flag) {
+  HB_REQUIRE(p && flag, "null argument");
+  *flag = p->affine ? 1 : 0;
+  return HB_OK;
+}
+
+// ------------------------------------------------------------- VM kernels
+struct hb_shm {  // the shm index space and the target (shp) bounds/strides
+  int mrank, prank;
+  int64_t mshape[HB_R];
+  int64_t pshape[HB_VM_MAX_OUT];
+  int64_t pstride[HB_VM_MAX_OUT];
+};
+
+__device__ __forceinline__ int64_t hb_vm_target(const hb_vm_prog &P, const hb_shm &S, int64_t m) {
+  int64_t vars[HB_R];
+  int64_t rem = m;
+#pragma unroll 1
+  for (int d = S.mrank - 1; d >= 0; d--) {
+    int64_t q = rem / S.mshape[d];
+    vars[d] = rem - q * S.mshape[d];
+    rem = q;
+  }
+  uint64_t outs[HB_VM_MAX_OUT];
+  hb_vm_run(P, vars, hb_vm_noin(), outs);
+  int64_t off = 0;
+  bool inb = true;
+  for (int c = 0; c < S.prank; c++) {
+    int64_t ix = (int64_t)outs[c];
+    inb = inb && ix >= 0 && ix < S.pshape[c];
+    off += ix * S.pstride[c];
+  }
+  return inb ? off : INT64_MIN;  // INT64_MIN = out of bounds
+}
+
+// offsets[m] = strided offset of prog(m) in the target, or INT64_MIN
+__global__ void __launch_bounds__(128)
+    hb_vm_offsets_kernel(const __grid_constant__ hb_vm_prog P, const __grid_constant__ hb_shm S,
+                         int64_t M, int64_t *__restrict__ offsets) {
+  int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m < M) offsets[m] = hb_vm_target(P, S, m);
+}
+
+// fused gather for rank-0 slices: out[m] = src[prog(m)]
+template <typename T>
+__global__ void __launch_bounds__(128)
+    hb_vm_gather0_kernel(const __grid_constant__ hb_vm_prog P, const __grid_constant__ hb_shm S,
+                         int64_t M, const T *__restrict__ src, T *__restrict__ out) {
+  int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  int64_t off = hb_vm_target(P, S, m);
+  out[m] = off == INT64_MIN ? T(0) : src[off];
+}
+
+// out[m, j] = offsets[m] valid ? src[offsets[m] + noff(j)] : 0
+template <typename T>
+__global__ void __launch_bounds__(256)
+    hb_gather_copy_kernel(const int64_t *__restrict__ offsets, hb_dims nd, int64_t Nn, int64_t total,
+                          const T *__restrict__ src, T *__restrict__ out) {
+  int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t gs = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t lin = gid; lin < total; lin += gs) {
+    int64_t m = lin / Nn, j = lin - m * Nn;
+    int64_t base = offsets[m];
+    T v = T(0);
+    if (base != INT64_MIN) v = src[base + hb_offset_of(nd, j)];
+    out[lin] = v;
+  }
+}
+
+// affine gather with bound checks: lin over (shm ++ shn)
+struct hb_affp {
+  int mrank, prank;
+  int64_t c0[HB_VM_MAX_OUT], pshape[HB_VM_MAX_OUT];
+  int64_t coef[HB_VM_MAX_OUT][HB_R];
+};
+template <typename T>
+__global__ void __launch_bounds__(256)
+    hb_gather_affine_kernel(const __grid_constant__ hb_affp A, hb_dims d /* shm++shn with folded strides */,
+                            int64_t base, int64_t total, const T *__restrict__ src, T *__restrict__ out) {
+  int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t gs = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t lin = gid; lin < total; lin += gs) {
+    int64_t rem = lin, off = base;
+    int64_t p[HB_VM_MAX_OUT];
+#pragma unroll
+    for (int c = 0; c < HB_VM_MAX_OUT; c++) p[c] = c < A.prank ? A.c0[c] : 0;
+#pragma unroll 1
+    for (int k = d.rank - 1; k >= 0; k--) {
+      int64_t q = rem / d.shape[k], r = rem - q * d.shape[k];
+      off += r * d.stride[k];
+      if (k < A.mrank) {
+#pragma unroll
+        for (int c = 0; c < HB_VM_MAX_OUT; c++)
+          if (c < A.prank) p[c] += r * A.coef[c][k];
+      }
+      rem = q;
+    }
+    bool inb = true;
+#pragma unroll
+    for (int c = 0; c < HB_VM_MAX_OUT; c++)
+      if (c < A.prank) inb = inb && p[c] >= 0 && p[c] < A.pshape[c];
+    out[lin] = inb ? src[off] : T(0);
+  }
+}
+
+static void fill_shm(hb_shm *S, int shm_rank, const int64_t *shm, int shp_rank, const int64_t *pshape,
+                     const int64_t *pstride) {
+  memset(S, 0, sizeof *S);
+  S->mrank = shm_rank;
+  S->prank = shp_rank;
+  for (int i = 0; i < shm_rank; i++) S->mshape[i] = shm[i];
+  for (int i = 0; i < shp_rank; i++) {
+    S->pshape[i] = pshape[i];
+    S->pstride[i] = pstride[i];
+  }
+}
+
+extern "C" int hb_gather(const hb_array *src, int shm_rank, const int64_t *shm, int shp_rank,
+                         const hb_ixprog *prog, hb_array **out) {
+  HB_CHECK_INIT();
+  HB_REQUIRE(src && prog && out, "null argument");
+  HB_REQUIRE(shm_rank >= 0 && shm_rank <= HB_R && (shm_rank == 0 || shm), "gather: bad shm");
+  HB_REQUIRE(shp_rank >= 0 && shp_rank <= src->rank, "gather: |shp| = %d exceeds source rank %d", shp_rank,
+             src->rank);
+  HB_REQUIRE(prog->vm.n_vars == shm_rank && prog->vm.n_out == shp_rank,
+             "gather: program maps %d -> %d indices, expected %d -> %d", prog->vm.n_vars, prog->vm.n_out,
+             shm_rank, shp_rank);
+  int nrank = src->rank - shp_rank;
+  HB_REQUIRE(shm_rank + nrank <= HB_R, "gather: result rank too large");
+  int64_t osh[HB_R];
+  int64_t M = 1, Nn = 1;
+  for (int i = 0; i < shm_rank; i++) { osh[i] = shm[i]; M *= shm[i]; }
+  for (int i = 0; i < nrank; i++) { osh[shm_rank + i] = src->shape[shp_rank + i]; Nn *= src->shape[shp_rank + i]; }
+  int orank = shm_rank + nrank;
+
+  if (prog->affine) {
+    // folded strides: stride of shm axis k = sum_c coef[c][k] * src.stride[c]
+    int64_t fs[HB_R];
+    int64_t base = 0;
+    bool inb = true;
+    for (int c = 0; c < shp_rank; c++) base += prog->c0[c] * src->strides[c];
+    for (int k = 0; k < shm_rank; k++) {
+      fs[k] = 0;
+      for (int c = 0; c < shp_rank; c++) fs[k] += prog->coef[c][k] * src->strides[c];
+    }
+    for (int c = 0; c < shp_rank; c++) {  // range of component c over the shm box
+      int64_t lo = prog->c0[c], hi = prog->c0[c];
+      for (int k = 0; k < shm_rank; k++) {
+        int64_t e = prog->coef[c][k] * (shm[k] - 1);
+        if (shm[k] == 0) e = 0;
+        if (e < 0) lo += e; else hi += e;
+      }
+      if (lo < 0 || hi >= src->shape[c]) inb = false;
+    }
+    if (inb || M * Nn == 0) {
+      // pure view: zero-copy gather (possibly overlapping windows)
+      hb_array *v = hb_new_view(src);
+      v->rank = orank;
+      v->offset += (M * Nn == 0) ? 0 : base;
+      for (int k = 0; k < shm_rank; k++) { v->shape[k] = shm[k]; v->strides[k] = fs[k]; }
+      for (int i = 0; i < nrank; i++) {
+        v->shape[shm_rank + i] = src->shape[shp_rank + i];
+        v->strides[shm_rank + i] = src->strides[shp_rank + i];
+      }
+      *out = v;
+      return HB_OK;
+    }
+    hb_array *o;
+    HB_TRY(hb_new_array(src->dt, orank, osh, &o));
+    hb_affp A;
+    memset(&A, 0, sizeof A);
+    A.mrank = shm_rank;
+    A.prank = shp_rank;
+    for (int c = 0; c < shp_rank; c++) {
+      A.c0[c] = prog->c0[c];
+      A.pshape[c] = src->shape[c];
+      for (int k = 0; k < shm_rank; k++) A.coef[c][k] = prog->coef[c][k];
+    }
+    hb_dims d;
+    d.rank = orank;
+    for (int i = 0; i < HB_R; i++) {
+      d.shape[i] = i < orank ? osh[i] : 1;
+      d.stride[i] = i < shm_rank ? fs[i] : (i < orank ? src->strides[shp_rank + (i - shm_rank)] : 0);
+    }
+    int64_t total = M * Nn;
+    int blocks = hb_blocks_for(total, 256, g_hb.sm_count * 32);
+    HB_DISPATCH_BYTES(src->dt, T,
+                      (hb_gather_affine_kernel<T><<<blocks, 256, 0, g_hb.stream>>>(
+                          A, d, base, total, (const T *)hb_data(src), (T *)hb_data(o))));
+    HB_LAUNCHED();
+    *out = o;
+    return HB_OK;
+  }
+
+  hb_array *o;
+  HB_TRY(hb_new_array(src->dt, orank, osh, &o));
+  int64_t total = M * Nn;
+  if (total == 0) { *out = o; return HB_OK; }
+  hb_shm S;
+  fill_shm(&S, shm_rank, shm, shp_rank, src->shape, src->strides);
+  if (Nn == 1) {
+    int64_t tail = 0;  // offset of the (all size-1) shn axes is 0
+    (void)tail;
+    int blocks = hb_blocks_for(M, 128);
+    HB_DISPATCH_BYTES(src->dt, T,
+                      (hb_vm_gather0_kernel<T><<<blocks, 128, 0, g_hb.stream>>>(
+                          prog->vm, S, M, (const T *)hb_data(src), (T *)hb_data(o))));
+    HB_LAUNCHED();
+  } else {
+    void *scr;
+    int st = hb_scratch((size_t)M * 8, &scr);
+    if (st != HB_OK) { hb_release(o); return st; }
+    hb_vm_offsets_kernel<<<hb_blocks_for(M, 128), 128, 0, g_hb.stream>>>(prog->vm, S, M, (int64_t *)scr);
+    HB_LAUNCHED();
+    hb_dims nd;
+    nd.rank = nrank;
+    for (int i = 0; i < HB_R; i++) {
+      nd.shape[i] = i < nrank ? src->shape[shp_rank + i] : 1;
+      nd.stride[i] = i < nrank ? src->strides[shp_rank + i] : 0;
+    }
+    int blocks = hb_blocks_for(total, 256, g_hb.sm_count * 32);
+    HB_DISPATCH_BYTES(src->dt, T,
+                      (hb_gather_copy_kernel<T><<<blocks, 256, 0, g_hb.stream>>>(
+                          (const int64_t *)scr, nd, Nn, total, (const T *)hb_data(src), (T *)hb_data(o))));
+    HB_LAUNCHED();
+  }
+  *out = o;
+  return HB_OK;
+}
+
+// ------------------------------------------------------------------- scan
+// exclusive scan of int32 counts, tiles of 1024 (256 threads x 4)
+__global__ void __launch_bounds__(256)
+    hb_scan_tiles_kernel(const int *__restrict__ in, int *__restrict__ out, int *__restrict__ tile_sums,
+                         int64_t n) {
+  __shared__ int warp_sums[8];
+  int64_t base = (int64_t)blockIdx.x * 1024 + threadIdx.x * 4;
+  int v[4];
+  int s = 0;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    v[i] = base + i < n ? in[base + i] : 0;
+    s += v[i];
+  }
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int incl = s;
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) warp_sums[w] = incl;
+  __syncthreads();
+  if (w == 0) {
+    int ws = lane < 8 ? warp_sums[lane] : 0;
+    int wi = ws;
+    for (int o = 1; o < 8; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += t;
+    }
+    if (lane < 8) warp_sums[lane] = wi - ws;  // exclusive warp offsets
+    if (lane == 7 && tile_sums) tile_sums[blockIdx.x] = wi;
+  }
+  __syncthreads();
+  int excl = incl - s + warp_sums[w];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    if (base + i < n) out[base + i] = excl;
+    excl += v[i];
+  }
+}
+__global__ void hb_scan_add_kernel(int *__restrict__ out, const int *__restrict__ tile_offs, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * 1024 + threadIdx.x;
+  int add = tile_offs[blockIdx.x];
+  for (int k = 0; k < 4; k++, i += 256)
+    if (i < n) out[i] += add;
+}
+
+// out may alias in.  tmp: scratch of >= (n/1024 + 2) * 2 ints
+static int exclusive_scan_i32(const int *in, int *out, int64_t n, int *tmp) {
+  if (n <= 0) return HB_OK;
+  int64_t tiles = (n + 1023) / 1024;
+  hb_scan_tiles_kernel<<<(unsigned)tiles, 256, 0, g_hb.stream>>>(in, out, tiles > 1 ? tmp : nullptr, n);
+  HB_LAUNCHED();
+  if (tiles > 1) {
+    HB_TRY(exclusive_scan_i32(tmp, tmp, tiles, tmp + tiles + 1));
+    hb_scan_add_kernel<<<(unsigned)tiles, 256, 0, g_hb.stream>>>(out, tmp, n);
+    HB_LAUNCHED();
+  }
+  return HB_OK;
+}
+
+// ---------------------------------------------------------------- scatter
+// pass 1: dest[m] (linear index in shp, or -1), counts[dest]++, collision flag
+__global__ void __launch_bounds__(128)
+    hb_scatter_dest_kernel(const __grid_constant__ hb_vm_prog P, const __grid_constant__ hb_shm S,
+                           int64_t M, int *__restrict__ dest, int *__restrict__ counts,
+                           int *__restrict__ collision) {
+  int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  int64_t off = hb_vm_target(P, S, m);
+  int d = off == INT64_MIN ? -1 : (int)off;
+  dest[m] = d;
+  if (d >= 0) {
+    int old = atomicAdd(&counts[d], 1);
+    if (old > 0) *collision = 1;
+  }
+}
+
+// no destination hit twice: out[dest[m], j] = src[m, j]
+template <typename T>
+__global__ void __launch_bounds__(256)
+    hb_scatter_direct_kernel(const int *__restrict__ dest, const int *__restrict__ collision, hb_dims sd,
+                             int64_t Nn, int64_t total, const T *__restrict__ src, T *__restrict__ out) {
+  if (*collision) return;
+  int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t gs = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t lin = gid; lin < total; lin += gs) {
+    int64_t m = lin / Nn, j = lin - m * Nn;
+    int d = dest[m];
+    if (d >= 0) out[(int64_t)d * Nn + j] = src[hb_offset_of(sd, lin)];
+  }
+}
+
+__global__ void __launch_bounds__(128)
+    hb_scatter_fill_kernel(const int *__restrict__ dest, const int *__restrict__ collision,
+                           const int *__restrict__ starts, int *__restrict__ cursor, int *__restrict__ seg,
+                           int64_t M) {
+  if (!*collision) return;
+  int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  int d = dest[m];
+  if (d >= 0) {
+    int slot = atomicAdd(&cursor[d], 1);
+    seg[starts[d] + slot] = (int)m;
+  }
+}
+
+// sort each destination's source list ascending (restores row-major source
+// order regardless of the order the atomics resolved in)
+__global__ void __launch_bounds__(128)
+    hb_scatter_sort_kernel(const int *__restrict__ collision, const int *__restrict__ starts,
+                           const int *__restrict__ counts, int *__restrict__ seg, int64_t Pn) {
+  if (!*collision) return;
+  int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= Pn) return;
+  int c = counts[d];
+  if (c < 2 || c > 64) return;  // long segments: hb_scatter_sort_long_kernel
+  int *s = seg + starts[d];
+  for (int i = 1; i < c; i++) {
+    int key = s[i], j = i - 1;
+    while (j >= 0 && s[j] > key) { s[j + 1] = s[j]; j--; }
+    s[j + 1] = key;
+  }
+}
+
+// one block per destination with a long list: same-direction bitonic network
+// with virtual +inf padding
+__global__ void __launch_bounds__(256)
+    hb_scatter_sort_long_kernel(const int *__restrict__ collision, const int *__restrict__ starts,
+                                const int *__restrict__ counts, int *__restrict__ seg, int64_t Pn) {
+  if (!*collision) return;
+  for (int64_t d = blockIdx.x; d < Pn; d += gridDim.x) {
+    int c = counts[d];
+    if (c <= 64) continue;
+    int *s = seg + starts[d];
+    int n = 1;
+    while (n < c) n <<= 1;
+    for (int k = 2; k <= n; k <<= 1) {
+      // first step: mirrored compare
+      for (int t = threadIdx.x; t < n / 2; t += blockDim.x) {
+        int blk = t / (k / 2), o = t % (k / 2);
+        int i = blk * k + o, j = blk * k + k - 1 - o;
+        if (j < c && s[i] > s[j]) { int x = s[i]; s[i] = s[j]; s[j] = x; }
+      }
+      __syncthreads();
+      for (int h = k / 4; h > 0; h >>= 1) {
+        for (int t = threadIdx.x; t < n / 2; t += blockDim.x) {
+          int blk = t / h, o = t % h;
+          int i = blk * 2 * h + o, j = i + h;
+          if (j < c && s[i] > s[j]) { int x = s[i]; s[i] = s[j]; s[j] = x; }
+        }
+        __syncthreads();
+      }
+    }
+  }
+}
+
+// out[d, j] = sum over the sorted source list (sequential, reference order)
+template <typename T>
+__global__ void __launch_bounds__(256)
+    hb_scatter_sum_kernel(const int *__restrict__ collision, const int *__restrict__ starts,
+                          const int *__restrict__ counts, const int *__restrict__ seg, hb_dims md,
+                          hb_dims nd, int64_t Nn, int64_t total, const T *__restrict__ src,
+                          T *__restrict__ out) {
+  if (!*collision) return;
+  int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t gs = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t lin = gid; lin < total; lin += gs) {
+    int64_t d = lin / Nn, j = lin - d * Nn;
+    int c = counts[d];
+    if (c == 0) continue;  // stays zero
+    const int *s = seg + starts[d];
+    int64_t joff = hb_offset_of(nd, j);
+    T acc;
+    if (Nn == 1) {
+      // rank-0 slices: vec starts at 0 and adds u + u2 (OpsConcrete.hs:1594-1601)
+      acc = T(0);
+      for (int i = 0; i < c; i++) acc = src[hb_offset_of(md, s[i]) + joff] + acc;
+    } else {
+      // IntMap.insertWith (+): first slice stored as is, later ones new + old
+      acc = src[hb_offset_of(md, s[0]) + joff];
+      for (int i = 1; i < c; i++) acc = src[hb_offset_of(md, s[i]) + joff] + acc;
+    }
+    out[lin] = acc;
+  }
+}
+
+extern "C" int hb_scatter_add(const hb_array *src, int shm_rank, int shp_rank, const int64_t *shp,
+                              const hb_ixprog *prog, hb_array **out) {
+  HB_CHECK_INIT();
+  HB_REQUIRE(src && prog && out, "null argument");
+  HB_REQUIRE(shm_rank >= 0 && shm_rank <= src->rank, "scatter: |shm| = %d exceeds source rank %d", shm_rank,
+             src->rank);
+  HB_REQUIRE(shp_rank >= 0 && shp_rank <= HB_VM_MAX_OUT && (shp_rank == 0 || shp), "scatter: bad shp");
+  HB_REQUIRE(prog->vm.n_vars == shm_rank && prog->vm.n_out == shp_rank,
+             "scatter: program maps %d -> %d indices, expected %d -> %d", prog->vm.n_vars, prog->vm.n_out,
+             shm_rank, shp_rank);
+  HB_REQUIRE(src->dt != HB_BOOL, "scatter: numeric dtype required");
+  int nrank = src->rank - shm_rank;
+  HB_REQUIRE(shp_rank + nrank <= HB_R, "scatter: result rank too large");
+  int64_t osh[HB_R];
+  int64_t M = 1, Nn = 1, Pn = 1;
+  for (int i = 0; i < shm_rank; i++) M *= src->shape[i];
+  for (int i = 0; i < shp_rank; i++) { osh[i] = shp[i]; Pn *= shp[i]; }
+  for (int i = 0; i < nrank; i++) { osh[shp_rank + i] = src->shape[shm_rank + i]; Nn *= src->shape[shm_rank + i]; }
+  hb_array *o;
+  HB_TRY(hb_zeros(src->dt, shp_rank + nrank, osh, &o));
+  if (M * Nn == 0 || Pn == 0) { *out = o; return HB_OK; }
+  if (M >= (1ll << 31) - 1 || Pn >= (1ll << 31) - 1) {
+    hb_release(o);
+    HB_FAIL(HB_ERR_UNSUPPORTED, "scatter: index spaces of 2^31 positions or more are not supported");
+  }
+  // contiguous strides of the shp space
+  int64_t pstr[HB_VM_MAX_OUT];
+  { int64_t s = 1; for (int i = shp_rank - 1; i >= 0; i--) { pstr[i] = s; s *= shp[i]; } }
+  hb_shm S;
+  fill_shm(&S, shm_rank, src->shape, shp_rank, shp, pstr);
+  // scratch layout (ints): dest[M] | counts[Pn] | starts[Pn] | cursor[Pn] | seg[M] | flag | scan tmp
+  int64_t tiles = (Pn + 1023) / 1024;
+  size_t ints = (size_t)M * 2 + (size_t)Pn * 3 + 16 + (size_t)(tiles + 2) * 4;
+  void *scr;
+  int st = hb_scratch(ints * 4, &scr);
+  if (st != HB_OK) { hb_release(o); return st; }
+  int *dest = (int *)scr;
+  int *counts = dest + M;
+  int *starts = counts + Pn;
+  int *cursor = starts + Pn;
+  int *flag = cursor + Pn;  // 16 ints reserved
+  int *seg = flag + 16;
+  int *tmp = seg + M;
+  // zero counts, starts, cursor, flag in one memset
+  cudaError_t e = cudaMemsetAsync(counts, 0, ((size_t)Pn * 3 + 16) * 4, g_hb.stream);
+  if (e != cudaSuccess) { hb_release(o); HB_CUDA(e); }
+  hb_scatter_dest_kernel<<<hb_blocks_for(M, 128), 128, 0, g_hb.stream>>>(prog->vm, S, M, dest, counts, flag);
+  HB_LAUNCHED();
+  hb_dims sd;  // full source dims (shm ++ shn) for the direct kernel
+  sd.rank = src->rank;
+  hb_dims md;  // source offset of an shm position
+  md.rank = shm_rank;
+  hb_dims nd;  // source offset within a slice
+  nd.rank = nrank;
+  for (int i = 0; i < HB_R; i++) {
+    sd.shape[i] = i < src->rank ? src->shape[i] : 1;
+    sd.stride[i] = i < src->rank ? src->strides[i] : 0;
+    md.shape[i] = i < shm_rank ? src->shape[i] : 1;
+    md.stride[i] = i < shm_rank ? src->strides[i] : 0;
+    nd.shape[i] = i < nrank ? src->shape[shm_rank + i] : 1;
+    nd.stride[i] = i < nrank ? src->strides[shm_rank + i] : 0;
+  }
+  int64_t total_src = M * Nn, total_dst = Pn * Nn;
+  int bsrc = hb_blocks_for(total_src, 256, g_hb.sm_count * 32);
+  int bdst = hb_blocks_for(total_dst, 256, g_hb.sm_count * 32);
+  st = exclusive_scan_i32(counts, starts, Pn, tmp);
+  if (st != HB_OK) { hb_release(o); return st; }
+  HB_DISPATCH_NUM(src->dt, T, {
+    hb_scatter_direct_kernel<T><<<bsrc, 256, 0, g_hb.stream>>>(dest, flag, sd, Nn, total_src,
+                                                               (const T *)hb_data(src), (T *)hb_data(o));
+    HB_LAUNCHED();
+    hb_scatter_fill_kernel<<<hb_blocks_for(M, 128), 128, 0, g_hb.stream>>>(dest, flag, starts, cursor, seg, M);
+    HB_LAUNCHED();
+    hb_scatter_sort_kernel<<<hb_blocks_for(Pn, 128), 128, 0, g_hb.stream>>>(flag, starts, counts, seg, Pn);
+    HB_LAUNCHED();
+    hb_scatter_sort_long_kernel<<<hb_blocks_for(Pn, 1, g_hb.sm_count * 4), 256, 0, g_hb.stream>>>(flag, starts, counts, seg, Pn);
+    HB_LAUNCHED();
+    hb_scatter_sum_kernel<T><<<bdst, 256, 0, g_hb.stream>>>(flag, starts, counts, seg, md, nd, Nn, total_dst,
+                                                            (const T *)hb_data(src), (T *)hb_data(o));
+    HB_LAUNCHED();
+  });
+  *out = o;
+  return HB_OK;
+}
+
+extern "C" int hb_onehot(const hb_array *v, int shp_rank, const int64_t *shp, const int64_t *ix,
+                         hb_array **out) {
+  HB_CHECK_INIT();
+  HB_REQUIRE(v && out, "null argument");
+  HB_REQUIRE(shp_rank >= 0 && shp_rank + v->rank <= HB_R, "oneHot: rank too large");
+  int64_t osh[HB_R];
+  for (int i = 0; i < shp_rank; i++) osh[i] = shp[i];
+  for (int i = 0; i < v->rank; i++) osh[shp_rank + i] = v->shape[i];
+  hb_array *o;
+  HB_TRY(hb_zeros(v->dt, shp_rank + v->rank, osh, &o));
+  bool inb = true;
+  for (int i = 0; i < shp_rank; i++) inb = inb && ix[i] >= 0 && ix[i] < shp[i];
+  if (inb && hb_numel(v) > 0) {
+    hb_array *slot = nullptr;
+    int st = hb_index_prefix(o, shp_rank, ix, &slot);
+    if (st == HB_OK) {
+      // copy v into the slot: reuse the generic strided copy through hb_iter
+      const hb_array *ops[2] = {slot, v};
+      hb_iter it;
+      hb_make_iter(2, ops, &it);
+      HB_DISPATCH_BYTES(v->dt, T, {
+        T *po = (T *)hb_data(slot);
+        const T *pi = (const T *)hb_data(v);
+        st = hb_launch_iter<2>(it, [=] __device__(int64_t, const int64_t *off) { po[off[0]] = pi[off[1]]; });
+      });
+    }
+    hb_release(slot);
+    if (st != HB_OK) { hb_release(o); return st; }
+  }
+  *out = o;
+  return HB_OK;
+}
+
+// -------------------------------------------------------------- fused map
+#define HB_MAP_MAXIN 6
+struct hb_mapp {
+  int rank, n_in;
+  int64_t shape[HB_R];
+  int64_t stride[HB_MAP_MAXIN][HB_R];
+  const void *ptr[HB_MAP_MAXIN];
+  int dtype[HB_MAP_MAXIN];
+};
+
+struct hb_map_in {
+  const hb_mapp *mp;
+  const int64_t *off;
+  __device__ __forceinline__ uint64_t operator()(int k) const {
+    return hb_vm_load(mp->ptr[k], mp->dtype[k], off[k]);
+  }
+};
+
+template <typename TO>
+__global__ void __launch_bounds__(128)
+    hb_fused_map_kernel(const __grid_constant__ hb_vm_prog P, const __grid_constant__ hb_mapp mp, int64_t n,
+                        TO *__restrict__ out) {
+  int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t gs = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t lin = gid; lin < n; lin += gs) {
+    int64_t off[HB_MAP_MAXIN];
+#pragma unroll
+    for (int k = 0; k < HB_MAP_MAXIN; k++) off[k] = 0;
+    int64_t rem = lin;
+#pragma unroll 1
+    for (int d = mp.rank - 1; d >= 0; d--) {
+      int64_t q = rem / mp.shape[d], r = rem - q * mp.shape[d];
+#pragma unroll
+      for (int k = 0; k < HB_MAP_MAXIN; k++)
+        if (k < mp.n_in) off[k] += r * mp.stride[k][d];
+      rem = q;
+    }
+    uint64_t outs[HB_VM_MAX_OUT];
+    hb_map_in in{&mp, off};
+    int64_t novars[1] = {lin};
+    hb_vm_run(P, novars, in, outs);
+    if constexpr (std::is_same<TO, double>::value) out[lin] = hb_bits_f(outs[0]);
+    else if constexpr (std::is_same<TO, float>::value) out[lin] = (float)hb_bits_f(outs[0]);
+    else out[lin] = (TO)(int64_t)outs[0];
+  }
+}
+
+extern "C" int hb_fused_map(const hb_ixprog *prog, int n_in, hb_array *const *ins, hb_dtype dt,
+                            hb_array **out) {
+  HB_CHECK_INIT();
+  HB_REQUIRE(prog && out && ins, "null argument");
+  HB_REQUIRE(n_in >= 1 && n_in <= HB_MAP_MAXIN, "fused map: %d inputs (max %d)", n_in, HB_MAP_MAXIN);
+  HB_REQUIRE(prog->vm.n_out == 1, "fused map: program must have exactly one output");
+  for (int i = 1; i < n_in; i++)
+    HB_REQUIRE(hb_same_shape(ins[0], ins[i]), "fused map: input %d has shape %s, expected %s", i,
+               hb_shape_str(ins[i]).c_str(), hb_shape_str(ins[0]).c_str());
+  hb_array *o;
+  HB_TRY(hb_new_array(dt, ins[0]->rank, ins[0]->shape, &o));
+  int64_t n = hb_numel(o);
+  if (n > 0) {
+    hb_mapp mp;
+    memset(&mp, 0, sizeof mp);
+    mp.n_in = n_in;
+    mp.rank = ins[0]->rank;
+    int64_t str[HB_MAP_MAXIN][HB_R];
+    for (int d = 0; d < mp.rank; d++) mp.shape[d] = ins[0]->shape[d];
+    for (int k = 0; k < n_in; k++) {
+      for (int d = 0; d < mp.rank; d++) str[k][d] = ins[k]->strides[d];
+      mp.ptr[k] = hb_data(ins[k]);
+      mp.dtype[k] = ins[k]->dt;
+    }
+    hb_collapse(&mp.rank, mp.shape, n_in, str);
+    for (int k = 0; k < n_in; k++)
+      for (int d = 0; d < mp.rank; d++) mp.stride[k][d] = str[k][d];
+    int blocks = hb_blocks_for(n, 128, g_hb.sm_count * 32);
+    HB_DISPATCH_ALL(dt, T, (hb_fused_map_kernel<T><<<blocks, 128, 0, g_hb.stream>>>(prog->vm, mp, n, (T *)hb_data(o))));
+    HB_LAUNCHED();
+  }
+  *out = o;
+  return HB_OK;
+}

@@ -1,0 +1,224 @@
+// nn.cu -- fused NN blocks emitted by the device contraction pass in place of
+// the gather chains of the vectorised artifacts: max-pooling with its adjoint
+// (maxPool2dUnpaddedS, CommonShapedOps.hs:241-260; smaximum :33-36; the
+// gather/scatter form is at TestMnistPP.hs:735) and the fused
+// softmax-cross-entropy loss (lossSoftMaxCrossEntropyS, :89-111).
+// All kernels are HBM-bound single passes.
+#include "common.cuh"
+
+// one thread per output window; value at the FIRST maximum of the row-major
+// flattened window (kargMax of the flattened slice); positions outside the
+// input read as 0 (slicezS, CommonShapedOps.hs:225-237).
+template <typename T>
+__global__ void __launch_bounds__(256)
+    hb_maxpool_kernel(const T *__restrict__ x, hb_dims xd, int ks, int stride, int64_t H, int64_t W,
+                      int64_t Ho, int64_t Wo, int64_t total, T *__restrict__ y, int64_t *__restrict__ am) {
+  int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t gs = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t o = gid; o < total; o += gs) {
+    int64_t j = o % Wo, t = o / Wo;
+    int64_t i = t % Ho;
+    t /= Ho;
+    int64_t c = t % xd.shape[1], n = t / xd.shape[1];
+    int64_t base = n * xd.stride[0] + c * xd.stride[1];
+    T best = T(0);
+    int64_t bi = 0;
+    bool first = true;
+    for (int a = 0; a < ks; a++)
+      for (int b = 0; b < ks; b++) {
+        int64_t yy = i * stride + a, xx = j * stride + b;
+        T v = (yy < H && xx < W) ? x[base + yy * xd.stride[2] + xx * xd.stride[3]] : T(0);
+        if (first || v > best) {
+          best = v;
+          bi = a * ks + b;
+          first = false;
+        }
+      }
+    y[o] = best;
+    if (am) am[o] = bi;
+  }
+}
+
+extern "C" int hb_maxpool2d(const hb_array *x, int ksize, int stride, hb_array **out, hb_array **argmax_out) {
+  HB_CHECK_INIT();
+  HB_REQUIRE(x && out, "null argument");
+  HB_REQUIRE(x->rank == 4 && hb_is_float(x->dt), "maxPool2d: rank-4 floating input required");
+  HB_REQUIRE(ksize >= 1 && stride >= 1, "maxPool2d: bad window");
+  int64_t H = x->shape[2], W = x->shape[3];
+  int64_t osh[4] = {x->shape[0], x->shape[1], H / stride, W / stride};
+  hb_array *y, *am = nullptr;
+  HB_TRY(hb_new_array(x->dt, 4, osh, &y));
+  if (argmax_out) {
+    int st = hb_new_array(HB_I64, 4, osh, &am);
+    if (st != HB_OK) { hb_release(y); return st; }
+  }
+  int64_t total = hb_numel(y);
+  if (total > 0) {
+    hb_dims xd;
+    xd.rank = 4;
+    for (int i = 0; i < HB_R; i++) { xd.shape[i] = i < 4 ? x->shape[i] : 1; xd.stride[i] = i < 4 ? x->strides[i] : 0; }
+    int blocks = hb_blocks_for(total, 256, g_hb.sm_count * 32);
+    HB_DISPATCH_FLOAT(x->dt, T,
+                      (hb_maxpool_kernel<T><<<blocks, 256, 0, g_hb.stream>>>(
+                          (const T *)hb_data(x), xd, ksize, stride, H, W, osh[2], osh[3], total, (T *)hb_data(y),
+                          am ? (int64_t *)hb_data(am) : nullptr)));
+    HB_LAUNCHED();
+  }
+  *out = y;
+  if (argmax_out) *argmax_out = am;
+  return HB_OK;
+}
+
+// adjoint in gather form: one thread per INPUT position sums, in row-major
+// window order, the cotangents of the windows whose argmax selected it.
+template <typename T>
+__global__ void __launch_bounds__(256)
+    hb_maxpool_bwd_kernel(const T *__restrict__ dy, const int64_t *__restrict__ am, int ks, int stride,
+                          int64_t C, int64_t H, int64_t W, int64_t Ho, int64_t Wo, int64_t total,
+                          T *__restrict__ dx) {
+  int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t gs = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t p = gid; p < total; p += gs) {
+    int64_t xx = p % W, t = p / W;
+    int64_t yy = t % H;
+    int64_t nc = t / H;
+    T acc = T(0);
+    // windows (i, j) with i*stride <= yy < i*stride + ks
+    int64_t i_hi = yy / stride, j_hi = xx / stride;
+    int64_t i_lo = yy - ks + 1 <= 0 ? 0 : (yy - ks + 1 + stride - 1) / stride;
+    int64_t j_lo = xx - ks + 1 <= 0 ? 0 : (xx - ks + 1 + stride - 1) / stride;
+    for (int64_t i = i_lo; i <= i_hi && i < Ho; i++)
+      for (int64_t j = j_lo; j <= j_hi && j < Wo; j++) {
+        int64_t a = yy - i * stride, b = xx - j * stride;
+        int64_t o = (nc * Ho + i) * Wo + j;
+        if (am[o] == a * ks + b) acc = dy[o] + acc;
+      }
+    dx[p] = acc;
+  }
+}
+
+extern "C" int hb_maxpool2d_bwd(const hb_array *dy, const hb_array *argmax, int ksize, int stride, int64_t H,
+                                int64_t W, hb_array **out) {
+  HB_CHECK_INIT();
+  HB_REQUIRE(dy && argmax && out, "null argument");
+  HB_REQUIRE(dy->rank == 4 && hb_is_float(dy->dt) && argmax->dt == HB_I64 && hb_same_shape(dy, argmax),
+             "maxPool2d_bwd: bad operands");
+  HB_REQUIRE(dy->shape[2] == H / stride && dy->shape[3] == W / stride, "maxPool2d_bwd: output extents do not match");
+  const hb_array *dyc = dy, *amc = argmax;
+  hb_array *t1 = nullptr, *t2 = nullptr;
+  if (!hb_contig(dy)) { HB_TRY(hb_contiguous(dy, &t1)); dyc = t1; }
+  if (!hb_contig(argmax)) {
+    int st = hb_contiguous(argmax, &t2);
+    if (st != HB_OK) { hb_release(t1); return st; }
+    amc = t2;
+  }
+  int64_t xsh[4] = {dy->shape[0], dy->shape[1], H, W};
+  hb_array *dx;
+  int st = hb_new_array(dy->dt, 4, xsh, &dx);
+  if (st == HB_OK) {
+    int64_t total = hb_numel(dx);
+    if (total > 0) {
+      int blocks = hb_blocks_for(total, 256, g_hb.sm_count * 32);
+      if (dy->dt == HB_F64)
+        hb_maxpool_bwd_kernel<double><<<blocks, 256, 0, g_hb.stream>>>(
+            (const double *)hb_data(dyc), (const int64_t *)hb_data(amc), ksize, stride, dy->shape[1], H, W,
+            dy->shape[2], dy->shape[3], total, (double *)hb_data(dx));
+      else
+        hb_maxpool_bwd_kernel<float><<<blocks, 256, 0, g_hb.stream>>>(
+            (const float *)hb_data(dyc), (const int64_t *)hb_data(amc), ksize, stride, dy->shape[1], H, W,
+            dy->shape[2], dy->shape[3], total, (float *)hb_data(dx));
+      g_hb.launches.fetch_add(1);
+      cudaError_t e = cudaPeekAtLastError();
+      if (e != cudaSuccess) { cudaGetLastError(); hb_set_error("maxpool bwd launch: %s", cudaGetErrorString(e)); st = HB_ERR_CUDA; }
+    }
+  }
+  hb_release(t1);
+  hb_release(t2);
+  if (st != HB_OK) { if (dx) hb_release(dx); return st; }
+  *out = dx;
+  return HB_OK;
+}
+
+// ---------------------------------------------------------- softmax-xent
+// lossSoftMaxCrossEntropyS (CommonShapedOps.hs:89-111), normalising over the
+// WHOLE tensor exactly as the reference does:
+//   expU = exp (u - minimum u); softMax = recip (sum expU) * expU
+//   loss = negate (log softMax `dot` expected); dual = (softMax - expected) * du
+// One block (the logits of a minibatch are a few 10^4 elements); three
+// block-wide deterministic tree reductions.
+template <typename T>
+__device__ T hb_block_reduce(T v, T *smem, bool is_min) {
+  for (int o = 16; o > 0; o >>= 1) {
+    T u = hb_shfl_xor(v, o);
+    v = is_min ? (u < v ? u : v) : v + u;
+  }
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (l == 0) smem[w] = v;
+  __syncthreads();
+  v = smem[0];
+  for (int i = 1; i < nw; i++) v = is_min ? (smem[i] < v ? smem[i] : v) : v + smem[i];
+  return v;  // every thread
+}
+
+template <typename T>
+__global__ void __launch_bounds__(1024)
+    hb_softmax_xent_kernel(const T *__restrict__ u, hb_dims ud, const T *__restrict__ ex, hb_dims ed,
+                           int64_t n, T scale, T *__restrict__ loss, T *__restrict__ dl) {
+  __shared__ T smem[32];
+  T mn = u[hb_offset_of(ud, 0)];
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    T v = u[hb_offset_of(ud, i)];
+    mn = v < mn ? v : mn;
+  }
+  mn = hb_block_reduce<T>(mn, smem, true);
+  T s = T(0);
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += exp(u[hb_offset_of(ud, i)] - mn);
+  s = hb_block_reduce<T>(s, smem, false);
+  T rs = T(1) / s;
+  T l = T(0);
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    T sm = rs * exp(u[hb_offset_of(ud, i)] - mn);
+    T e = ex[hb_offset_of(ed, i)];
+    l += log(sm) * e;
+    if (dl) dl[i] = scale * (sm - e);
+  }
+  l = hb_block_reduce<T>(l, smem, false);
+  if (threadIdx.x == 0) *loss = scale * (-l);
+}
+
+extern "C" int hb_softmax_xent(const hb_array *logits, const hb_array *expected, double scale,
+                               hb_array **loss_out, hb_array **dlogits_out) {
+  HB_CHECK_INIT();
+  HB_REQUIRE(logits && expected && loss_out, "null argument");
+  HB_REQUIRE(hb_is_float(logits->dt) && logits->dt == expected->dt && hb_same_shape(logits, expected),
+             "softmax-xent: logits %s vs expected %s", hb_shape_str(logits).c_str(), hb_shape_str(expected).c_str());
+  int64_t n = hb_numel(logits);
+  HB_REQUIRE(n > 0, "softmax-xent: empty logits");
+  hb_array *loss, *dl = nullptr;
+  int64_t one = 1;
+  HB_TRY(hb_new_array(logits->dt, 0, &one, &loss));
+  if (dlogits_out) {
+    int st = hb_new_array(logits->dt, logits->rank, logits->shape, &dl);
+    if (st != HB_OK) { hb_release(loss); return st; }
+  }
+  hb_dims ud, ed;
+  ud.rank = ed.rank = logits->rank;
+  for (int i = 0; i < HB_R; i++) {
+    ud.shape[i] = ed.shape[i] = i < logits->rank ? logits->shape[i] : 1;
+    ud.stride[i] = i < logits->rank ? logits->strides[i] : 0;
+    ed.stride[i] = i < logits->rank ? expected->strides[i] : 0;
+  }
+  if (logits->dt == HB_F64)
+    hb_softmax_xent_kernel<double><<<1, 1024, 0, g_hb.stream>>>(
+        (const double *)hb_data(logits), ud, (const double *)hb_data(expected), ed, n, scale,
+        (double *)hb_data(loss), dl ? (double *)hb_data(dl) : nullptr);
+  else
+    hb_softmax_xent_kernel<float><<<1, 1024, 0, g_hb.stream>>>(
+        (const float *)hb_data(logits), ud, (const float *)hb_data(expected), ed, n, (float)scale,
+        (float *)hb_data(loss), dl ? (float *)hb_data(dl) : nullptr);
+  HB_LAUNCHED();
+  *loss_out = loss;
+  if (dlogits_out) *dlogits_out = dl;
+  return HB_OK;
+}
