@@ -1,0 +1,410 @@
+"""Host-side mirror of horde-ad's dual-number AD over an arbitrary carrier:
+`ADVal target` (CarriersADVal.hs:47, OpsADVal.hs:164-548) and the delta
+evaluator `gradientFromDelta` / `evalRev` (DeltaEval.hs:64-77,274-730).
+
+In the real drop-in this layer is horde-ad itself, unchanged Haskell running
+over the new `Device` carrier; it is restated here only so that the reference's
+gradient golden vectors and the `cgrad` call sequence can be
+replayed through the C ABI without GHC.  It is target-generic: the same code
+drives the CPU oracle in tests and the device backend in the product path, and
+it touches tensors only through backend methods -- just like DeltaEval uses
+only BaseTensor methods of `target`.
+
+Every differentiable op records a node (a fresh id from a global counter, as
+DeltaFreshId.hs:56-68) with a pullback implementing the transposition rule of
+the corresponding Delta constructor; `grad` walks the nodes in DESCENDING id
+order accumulating cotangents with taddTarget (evalRevFromnMap,
+DeltaEval.hs:720-730; accumulation :139-148,317-332).
+"""
+from __future__ import annotations
+
+import heapq
+import itertools
+from typing import Callable, Sequence
+
+import numpy as np
+
+_ids = itertools.count(1)
+
+
+class Node:
+    __slots__ = ("id", "parents", "pullback")
+
+    def __init__(self, parents, pullback):
+        self.id = next(_ids)
+        self.parents = parents      # list[Node | None]
+        self.pullback = pullback    # c -> list of cotangents (None = zero)
+
+
+class ADVal:
+    """A dual number: primal tensor + delta node (None = constant)."""
+    __slots__ = ("p", "d")
+
+    def __init__(self, p, d=None):
+        self.p = p
+        self.d = d
+
+    @property
+    def shape(self):
+        return tuple(self.p.shape)
+
+
+def _inv_perm(perm):
+    inv = [0] * len(perm)
+    for i, p in enumerate(perm):
+        inv[p] = i
+    return inv
+
+
+class ADBackend:
+    """`target = ADVal base`: same method surface as a carrier backend."""
+
+    def __init__(self, base):
+        self.B = base
+        self.name = "adval(" + base.name + ")"
+
+    # ----------------------------------------------------------- plumbing
+    def lift(self, x) -> ADVal:
+        return x if isinstance(x, ADVal) else ADVal(x)
+
+    def primal(self, x):
+        return x.p if isinstance(x, ADVal) else x
+
+    def _node(self, p, parents: Sequence[ADVal], pullback) -> ADVal:
+        ds = [a.d for a in parents]
+        if all(d is None for d in ds):
+            return ADVal(p)
+        return ADVal(p, Node(ds, pullback))
+
+    def shape(self, t): return tuple(self.primal(t).shape)
+    def dtype(self, t): return self.B.dtype(self.primal(t))
+    def sconcrete(self, a): return ADVal(self.B.sconcrete(a))
+    def srepl(self, shape, value, dtype=np.float64): return ADVal(self.B.srepl(shape, value, dtype))
+    def sscalar(self, value, dtype=np.float64): return ADVal(self.B.sscalar(value, dtype))
+    def to_numpy(self, t): return self.B.to_numpy(self.primal(t))
+    def kfromS(self, t): return self.B.kfromS(self.primal(t))
+    def siota(self, n, dtype=np.int64): return ADVal(self.B.siota(n, dtype))
+    def sfromPrimal(self, t): return ADVal(self.primal(t))
+    def sprimalPart(self, t): return self.primal(t)
+
+    # index-expression references read primal (plain) parts
+    def ix_tbl(self, t, ixs): return self.B.ix_tbl(self.primal(t), ixs)
+    def ix_argmax(self, t, ixs): return self.B.ix_argmax(self.primal(t), ixs)
+    def ix_argmin(self, t, ixs): return self.B.ix_argmin(self.primal(t), ixs)
+
+    # --------------------------------------------------------- arithmetic
+    def binary(self, op, a, b):
+        B = self.B
+        a, b = self.lift(a), self.lift(b)
+        p = B.binary(op, a.p, b.p)
+        if op == "add":
+            return self._node(p, [a, b], lambda c: [c, c])
+        if op == "sub":
+            return self._node(p, [a, b], lambda c: [c, B.unary("negate", c)])
+        if op == "mul":  # DeltaScale (DeltaEval.hs:392-396)
+            return self._node(p, [a, b], lambda c: [B.binary("mul", b.p, c), B.binary("mul", a.p, c)])
+        if op == "divide":
+            def pb(c):
+                ca = B.binary("divide", c, b.p)
+                cb = B.unary("negate", B.binary("divide", B.binary("mul", c, p), b.p))
+                return [ca, cb]
+            return self._node(p, [a, b], pb)
+        if op == "power":
+            def pb(c):
+                one = B.srepl(B.shape(p), 1, B.dtype(p))
+                ca = B.binary("mul", c, B.binary("mul", b.p, B.binary("power", a.p, B.binary("sub", b.p, one))))
+                cb = B.binary("mul", c, B.binary("mul", p, B.unary("log", a.p)))
+                return [ca, cb]
+            return self._node(p, [a, b], pb)
+        if op == "atan2":  # atan2H y x: d/dy = x/(x^2+y^2), d/dx = -y/(x^2+y^2)
+            def pb(c):
+                r2 = B.binary("add", B.binary("mul", a.p, a.p), B.binary("mul", b.p, b.p))
+                ca = B.binary("mul", c, B.binary("divide", b.p, r2))
+                cb = B.binary("mul", c, B.unary("negate", B.binary("divide", a.p, r2)))
+                return [ca, cb]
+            return self._node(p, [a, b], pb)
+        if op in ("max", "min", "quot", "rem", "logbase"):
+            if a.d is None and b.d is None:
+                return ADVal(p)
+            raise NotImplementedError(f"derivative of {op}")
+        raise ValueError(op)
+
+    def unary(self, op, a):
+        B = self.B
+        a = self.lift(a)
+        p = B.unary(op, a.p)
+        if a.d is None:
+            return ADVal(p)
+        sh, dt = B.shape(p), B.dtype(p)
+        one = lambda: B.srepl(sh, 1, dt)
+
+        def scale(k):  # DeltaScale k d
+            return self._node(p, [a], lambda c: [B.binary("mul", k(), c)])
+        if op == "negate":
+            return self._node(p, [a], lambda c: [B.unary("negate", c)])
+        if op == "abs":
+            return scale(lambda: B.unary("signum", a.p))
+        if op == "signum":
+            return ADVal(p)
+        if op == "recip":
+            return scale(lambda: B.unary("negate", B.binary("mul", p, p)))
+        if op == "exp":
+            return scale(lambda: p)
+        if op == "log":
+            return scale(lambda: B.unary("recip", a.p))
+        if op == "sqrt":
+            return scale(lambda: B.unary("recip", B.binary("add", p, p)))
+        if op == "sin":
+            return scale(lambda: B.unary("cos", a.p))
+        if op == "cos":
+            return scale(lambda: B.unary("negate", B.unary("sin", a.p)))
+        if op == "tan":
+            return scale(lambda: B.binary("add", one(), B.binary("mul", p, p)))
+        if op == "tanh":
+            return scale(lambda: B.binary("sub", one(), B.binary("mul", p, p)))
+        if op == "sinh":
+            return scale(lambda: B.unary("cosh", a.p))
+        if op == "cosh":
+            return scale(lambda: B.unary("sinh", a.p))
+        if op == "asin":
+            return scale(lambda: B.unary("recip", B.unary("sqrt", B.binary("sub", one(), B.binary("mul", a.p, a.p)))))
+        if op == "acos":
+            return scale(lambda: B.unary("negate", B.unary("recip", B.unary("sqrt", B.binary("sub", one(), B.binary("mul", a.p, a.p))))))
+        if op == "atan":
+            return scale(lambda: B.unary("recip", B.binary("add", one(), B.binary("mul", a.p, a.p))))
+        if op == "asinh":
+            return scale(lambda: B.unary("recip", B.unary("sqrt", B.binary("add", one(), B.binary("mul", a.p, a.p)))))
+        if op == "acosh":
+            return scale(lambda: B.unary("recip", B.unary("sqrt", B.binary("sub", B.binary("mul", a.p, a.p), one()))))
+        if op == "atanh":
+            return scale(lambda: B.unary("recip", B.binary("sub", one(), B.binary("mul", a.p, a.p))))
+        raise ValueError(op)
+
+    def scast(self, t, dtype):
+        B = self.B
+        t = self.lift(t)
+        src = B.dtype(t.p)
+        if not (np.issubdtype(np.dtype(dtype), np.floating) and np.issubdtype(src, np.floating)):
+            return ADVal(B.scast(t.p, dtype))
+        return self._node(B.scast(t.p, dtype), [t], lambda c: [B.scast(c, src)])
+
+    def sfromIntegral(self, t, dtype): return ADVal(self.B.sfromIntegral(self.primal(t), dtype))
+    def sfloor(self, t, dtype=np.int64): return ADVal(self.B.sfloor(self.primal(t), dtype))
+    def sargMax(self, t): return ADVal(self.B.sargMax(self.primal(t)))
+    def sargMin(self, t): return ADVal(self.B.sargMin(self.primal(t)))
+
+    # ---------------------------------------------------------- structure
+    def stranspose(self, perm, t):
+        B = self.B
+        t = self.lift(t)
+        perm = list(perm)
+        return self._node(B.stranspose(perm, t.p), [t], lambda c: [B.stranspose(_inv_perm(perm), c)])
+
+    def sreshape(self, sh, t):
+        B = self.B
+        t = self.lift(t)
+        old = B.shape(t.p)
+        return self._node(B.sreshape(sh, t.p), [t], lambda c: [B.sreshape(old, c)])
+
+    # DeltaReplicateS -> tssumN (DeltaEval.hs:534-555)
+    def sreplicateN(self, shm, t):
+        B = self.B
+        t = self.lift(t)
+        n = len(shm)
+        return self._node(B.sreplicateN(shm, t.p), [t], lambda c: [B.ssumN(c, n)])
+
+    def sreplicate(self, k, t): return self.sreplicateN([k], t)
+    def sreplicate0N(self, shm, t0): return self.sreplicateN(shm, t0)
+
+    # DeltaSumS -> tsreplicateN
+    def ssumN(self, t, n_axes):
+        B = self.B
+        t = self.lift(t)
+        shm = list(B.shape(t.p)[:n_axes])
+        return self._node(B.ssumN(t.p, n_axes), [t], lambda c: [B.sreplicateN(shm, c)])
+
+    def ssum(self, t): return self.ssumN(t, 1)
+    def ssum0(self, t): return self.ssumN(t, len(self.shape(t)))
+
+    def sslice(self, i, n, t):
+        B = self.B
+        t = self.lift(t)
+        sh = B.shape(t.p)
+        total, rest, dt = sh[0], list(sh[1:]), B.dtype(t.p)
+
+        def pb(c):
+            parts = c
+            if i > 0:
+                parts = B.sappend(B.srepl([i] + rest, 0, dt), parts)
+            if total - i - n > 0:
+                parts = B.sappend(parts, B.srepl([total - i - n] + rest, 0, dt))
+            return [parts]
+        return self._node(B.sslice(i, n, t.p), [t], pb)
+
+    def sappend(self, a, b):
+        B = self.B
+        a, b = self.lift(a), self.lift(b)
+        m, n = B.shape(a.p)[0], B.shape(b.p)[0]
+        return self._node(B.sappend(a.p, b.p), [a, b], lambda c: [B.sslice(0, m, c), B.sslice(m, n, c)])
+
+    def sreverse(self, t):
+        B = self.B
+        t = self.lift(t)
+        return self._node(B.sreverse(t.p), [t], lambda c: [B.sreverse(c)])
+
+    def sfromVector(self, ts):
+        B = self.B
+        ts = [self.lift(t) for t in ts]
+        return self._node(B.sfromVector([t.p for t in ts]), ts, lambda c: B.sunravelToList(c))
+
+    def sunravelToList(self, t):
+        return [self.sindex(t, [i]) for i in range(self.shape(t)[0])]
+
+    # DeltaIndexS -> tsoneHot
+    def sindex(self, t, ixs):
+        B = self.B
+        t = self.lift(t)
+        ixs = [int(i) for i in ixs]
+        shp = list(B.shape(t.p)[:len(ixs)])
+        return self._node(B.sindex(t.p, ixs), [t], lambda c: [B.soneHot(shp, c, ixs)])
+
+    # DeltaGatherS -> tsscatter ; DeltaScatterS -> tsgather (DeltaEval.hs:538-562)
+    def sgather(self, shm, t, f, shp_rank, prog=None):
+        B = self.B
+        t = self.lift(t)
+        shp = list(B.shape(t.p)[:shp_rank])
+        shm = list(shm)
+        return self._node(B.sgather(shm, t.p, f, shp_rank, prog), [t],
+                          lambda c: [B.sscatter(shp, c, f, len(shm), prog)])
+
+    def sscatter(self, shp, t, f, shm_rank, prog=None):
+        B = self.B
+        t = self.lift(t)
+        shm = list(B.shape(t.p)[:shm_rank])
+        shp = list(shp)
+        return self._node(B.sscatter(shp, t.p, f, shm_rank, prog), [t],
+                          lambda c: [B.sgather(shm, c, f, len(shp), prog)])
+
+    # ---------------------------------------------------------- contraction
+    # DeltaDot0S v d -> v * replicate c (DeltaEval.hs:496-501)
+    def sdot0(self, a, b):
+        B = self.B
+        a, b = self.lift(a), self.lift(b)
+        sh = list(B.shape(a.p))
+        return self._node(B.sdot0(a.p, b.p), [a, b],
+                          lambda c: [B.binary("mul", b.p, B.sreplicate0N(sh, c)),
+                                     B.binary("mul", a.p, B.sreplicate0N(sh, c))])
+
+    def _bcast_last(self, c, n):
+        B = self.B
+        r = len(B.shape(c))
+        rep = B.sreplicate(n, c)                    # [n, sh...]
+        return B.stranspose(list(range(1, r + 1)) + [0], rep)  # [sh..., n]
+
+    def sdot1In(self, a, b):
+        B = self.B
+        a, b = self.lift(a), self.lift(b)
+        n = B.shape(a.p)[-1]
+        return self._node(B.sdot1In(a.p, b.p), [a, b],
+                          lambda c: [B.binary("mul", b.p, self._bcast_last(c, n)),
+                                     B.binary("mul", a.p, self._bcast_last(c, n))])
+
+    def smatmul2(self, a, b):
+        B = self.B
+        a, b = self.lift(a), self.lift(b)
+        return self._node(B.smatmul2(a.p, b.p), [a, b],
+                          lambda c: [B.smatmul2(c, B.stranspose([1, 0], b.p)),
+                                     B.smatmul2(B.stranspose([1, 0], a.p), c)])
+
+    def smatvecmul(self, m, v):
+        B = self.B
+        m, v = self.lift(m), self.lift(v)
+        rows = B.shape(m.p)[0]
+        cols = B.shape(m.p)[1]
+        return self._node(B.smatvecmul(m.p, v.p), [m, v],
+                          lambda c: [B.binary("mul", B.stranspose([1, 0], B.sreplicate(cols, c)), B.sreplicate(rows, v.p)),
+                                     B.smatvecmul(B.stranspose([1, 0], m.p), c)])
+
+    # --------------------------------------- fused blocks (custom derivatives)
+    def conv2dPreserving(self, K, A):
+        B = self.B
+        K, A = self.lift(K), self.lift(A)
+        KH, KW = B.shape(K.p)[2], B.shape(K.p)[3]
+        return self._node(B.conv2dPreserving(K.p, A.p), [K, A],
+                          lambda c: [B.conv2d_dkrn(A.p, c, KH, KW) if K.d is not None else None,
+                                     B.conv2d_dinp(K.p, c) if A.d is not None else None])
+
+    def relu(self, t):
+        B = self.B
+        t = self.lift(t)
+        sh, dt = B.shape(t.p), B.dtype(t.p)
+
+        def pb(c):  # oneIfGtZero * c, with oneIfGtZero = relu(x) > 0 mask
+            mask = B.unary("signum", B.relu(t.p))
+            return [B.binary("mul", mask, c)]
+        return self._node(B.relu(t.p), [t], pb)
+
+    def maxpool2d(self, x, ksize, stride):
+        B = self.B
+        x = self.lift(x)
+        H, W = B.shape(x.p)[2], B.shape(x.p)[3]
+        y, am = B.maxpool2d(x.p, ksize, stride)
+        return self._node(y, [x], lambda c: [B.maxpool2d_bwd(c, am, ksize, stride, H, W)])
+
+    # lossSoftMaxCrossEntropyS: tD primal (dual via (softMax - expected) * du)
+    def softmax_xent(self, logits, expected, scale=1.0, want_grad=True):
+        B = self.B
+        logits = self.lift(logits)
+        loss, dl = B.softmax_xent(logits.p, self.primal(expected), scale, want_grad=logits.d is not None)
+        sh = list(B.shape(logits.p))
+        return self._node(loss, [logits], lambda c: [B.binary("mul", dl, B.sreplicate0N(sh, c))]), None
+
+    def prod_fold(self, x):
+        """sfold (*) 1 x with the DeltaMapAccumL transposition (DeltaEval.hs:351-389)."""
+        B = self.B
+        x = self.lift(x)
+        prod, _ = B.prod_fold_grad(x.p, 1.0, want_grad=False)
+        return self._node(prod, [x], lambda c: [B.prod_fold_grad(x.p, float(B.kfromS(c)))[1]])
+
+
+def grad(base, f: Callable, inputs: Sequence, dt=None):
+    """cgrad / cvjp (ADEngine.hs:544-555): returns (value, [gradients]).
+
+    `f` receives the ADBackend and the inputs as ADVals.  dt=None means a
+    cotangent of ones (crevOnParams Nothing, OpsADVal.hs:62-73).  Gradients of
+    untouched inputs are explicit zeros (rebuildInputs, DeltaEval.hs:151-184).
+    """
+    T = ADBackend(base)
+    in_nodes = [Node([], None) for _ in inputs]
+    advals = [ADVal(x, n) for x, n in zip(inputs, in_nodes)]
+    out = f(T, *advals)
+    out = T.lift(out)
+    if dt is None:
+        dt = base.srepl(base.shape(out.p), 1, base.dtype(out.p))
+    grads = [None] * len(inputs)
+    if out.d is not None:
+        input_ix = {n.id: i for i, n in enumerate(in_nodes)}
+        cot = {out.d.id: dt}
+        nodes = {out.d.id: out.d}
+        heap = [-out.d.id]
+        while heap:
+            nid = -heapq.heappop(heap)
+            node = nodes.pop(nid)
+            c = cot.pop(nid)
+            if nid in input_ix:
+                grads[input_ix[nid]] = c
+                continue
+            cs = node.pullback(c)
+            for parent, pc in zip(node.parents, cs):
+                if parent is None or pc is None:
+                    continue
+                if parent.id in cot:
+                    cot[parent.id] = base.add_accumulate(cot[parent.id], pc)
+                else:
+                    cot[parent.id] = pc
+                    nodes[parent.id] = parent
+                    heapq.heappush(heap, -parent.id)
+    for i, x in enumerate(inputs):
+        if grads[i] is None:
+            grads[i] = base.srepl(base.shape(x), 0, base.dtype(x))
+    return out.p, grads

@@ -36,8 +36,14 @@ std::string hb_shape_str(const hb_array *a) {
 // driver before hb_shutdown; frees coming from foreign threads (GHC
 // finalisers) are queued and recycled by the next allocation.
 static std::mutex g_alloc_mu;
-static std::multimap<size_t, void *> g_free_blocks;
+// pool 0 = general; pool k > 0 = private pool of the k-th captured graph:
+// blocks allocated while capturing stay with the graph (its kernels have the
+// addresses baked in) and are recycled only among that graph's own captures,
+// so an eager allocation can never be handed a block a replay will overwrite.
+static std::map<int, std::multimap<size_t, void *>> g_pools;
 static std::vector<void *> g_all_blocks;
+static int g_capture_pool = 0;  // pool new allocations are charged to
+static int g_next_pool = 1;
 
 static size_t size_class(size_t bytes) {
   if (bytes < 512) return 512;
@@ -50,32 +56,41 @@ static size_t size_class(size_t bytes) {
   return (bytes + q - 1) / q * q;
 }
 
+static void *pool_take(int pool, size_t sz) {
+  auto &fl = g_pools[pool];
+  auto it = fl.find(sz);
+  if (it == fl.end()) return nullptr;
+  void *p = it->second;
+  fl.erase(it);
+  return p;
+}
+
 int hb_alloc_storage(size_t bytes, hb_storage **out) {
   size_t sz = size_class(bytes);
   void *p = nullptr;
+  int pool;
   {
     std::lock_guard<std::mutex> lk(g_alloc_mu);
-    auto it = g_free_blocks.find(sz);
-    if (it != g_free_blocks.end()) {
-      p = it->second;
-      g_free_blocks.erase(it);
-    }
+    pool = g_capture_pool;
+    p = pool_take(pool, sz);
+    // a capture may adopt idle blocks of the general pool (they leave it for good)
+    if (!p && pool != 0) p = pool_take(0, sz);
   }
   if (!p) {
     cudaError_t e = cudaMalloc(&p, sz);
     if (e != cudaSuccess) {
       cudaGetLastError();
-      // release the cache and retry once
-      {
+      // release the general cache and retry once
+      if (!g_hb.capturing) {
         std::lock_guard<std::mutex> lk(g_alloc_mu);
         cudaStreamSynchronize(g_hb.stream);
-        for (auto &kv : g_free_blocks) {
+        for (auto &kv : g_pools[0]) {
           cudaFree(kv.second);
           g_hb.reserved_bytes -= kv.first;
           for (auto &b : g_all_blocks)
             if (b == kv.second) b = nullptr;
         }
-        g_free_blocks.clear();
+        g_pools[0].clear();
       }
       e = cudaMalloc(&p, sz);
       if (e != cudaSuccess) {
@@ -90,6 +105,7 @@ int hb_alloc_storage(size_t bytes, hb_storage **out) {
   hb_storage *st = new hb_storage;
   st->ptr = p;
   st->bytes = sz;
+  st->pool = pool;
   st->rc.store(1);
   g_hb.live_bytes += sz;
   *out = st;
@@ -105,7 +121,7 @@ void hb_storage_release(hb_storage *st) {
       // single library stream before this point, and every later producer is
       // enqueued after it, so the block can be recycled immediately.
       std::lock_guard<std::mutex> lk(g_alloc_mu);
-      g_free_blocks.insert({st->bytes, st->ptr});
+      g_pools[st->pool].insert({st->bytes, st->ptr});
     }
     delete st;
   }
@@ -161,7 +177,7 @@ extern "C" int hb_shutdown(void) {
     for (void *p : g_all_blocks)
       if (p) cudaFree(p);
     g_all_blocks.clear();
-    g_free_blocks.clear();
+    g_pools.clear();
   }
   if (g_hb.scratch) cudaFree(g_hb.scratch);
   g_hb.scratch = nullptr;
@@ -334,8 +350,10 @@ extern "C" int hb_upload_into(hb_array *dst, const void *host) {
   HB_REQUIRE(hb_contig(dst), "hb_upload_into: destination must be contiguous");
   int64_t n = hb_numel(dst);
   if (n > 0)
+    // cudaMemcpyDefault: the source may be pinned host memory or a device
+    // pointer (a resident batch), resolved through unified addressing
     HB_CUDA(cudaMemcpyAsync(hb_data(dst), host, (size_t)n * hb_dtype_size(dst->dt),
-                            cudaMemcpyHostToDevice, g_hb.stream));
+                            cudaMemcpyDefault, g_hb.stream));
   return HB_OK;
 }
 
@@ -635,6 +653,7 @@ struct hb_graph {
   cudaGraph_t graph;
   cudaGraphExec_t exec;
   uint64_t n_kernels;  // kernels recorded during capture (per replay)
+  int pool;            // private allocator pool
 };
 static uint64_t g_capture_start = 0;
 
@@ -644,12 +663,22 @@ extern "C" int hb_graph_begin(void) {
   HB_CUDA(cudaStreamBeginCapture(g_hb.stream, cudaStreamCaptureModeRelaxed));
   g_hb.capturing = true;
   g_capture_start = g_hb.launches.load();
+  {
+    std::lock_guard<std::mutex> lk(g_alloc_mu);
+    g_capture_pool = g_next_pool++;
+  }
   return HB_OK;
 }
 extern "C" int hb_graph_end(hb_graph **out) {
   HB_CHECK_INIT();
   HB_REQUIRE(g_hb.capturing, "hb_graph_end: not capturing");
   g_hb.capturing = false;
+  int pool;
+  {
+    std::lock_guard<std::mutex> lk(g_alloc_mu);
+    pool = g_capture_pool;
+    g_capture_pool = 0;
+  }
   cudaGraph_t gr;
   HB_CUDA(cudaStreamEndCapture(g_hb.stream, &gr));
   cudaGraphExec_t ex;
@@ -658,7 +687,7 @@ extern "C" int hb_graph_end(hb_graph **out) {
     cudaGraphDestroy(gr);
     HB_CUDA(e);
   }
-  hb_graph *g = new hb_graph{gr, ex, g_hb.launches.load() - g_capture_start};
+  hb_graph *g = new hb_graph{gr, ex, g_hb.launches.load() - g_capture_start, pool};
   g_hb.launches = g_capture_start;  // capture enqueued nothing
   *out = g;
   return HB_OK;
@@ -674,6 +703,16 @@ extern "C" int hb_graph_free(hb_graph *g) {
   if (!g) return HB_OK;
   cudaGraphExecDestroy(g->exec);
   cudaGraphDestroy(g->graph);
+  {
+    // idle blocks of the private pool rejoin the general pool; blocks still
+    // referenced by live arrays follow when those arrays are released
+    std::lock_guard<std::mutex> lk(g_alloc_mu);
+    auto it = g_pools.find(g->pool);
+    if (it != g_pools.end()) {
+      for (auto &kv : it->second) g_pools[0].insert(kv);
+      g_pools.erase(it);
+    }
+  }
   delete g;
   return HB_OK;
 }

@@ -21,6 +21,7 @@
 struct hb_storage {
   void *ptr;
   size_t bytes;      // size-class size handed out by the allocator
+  int pool;          // allocator pool the block returns to (0 = general)
   std::atomic<int> rc;
 };
 

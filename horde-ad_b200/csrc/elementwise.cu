@@ -136,6 +136,43 @@ extern "C" int hb_stack(int k, hb_array *const *arrs, hb_array **out) {
   return HB_OK;
 }
 
+// Flatten k arrays (row-major) and concatenate them into one vector: the
+// contiguous gradient bucket of the data-parallel loop.
+extern "C" int hb_flatten_concat(int k, hb_array *const *arrs, hb_array **out) {
+  HB_CHECK_INIT();
+  HB_REQUIRE(out && k > 0 && arrs, "flatten_concat: empty list");
+  int64_t total = 0;
+  for (int i = 0; i < k; i++) {
+    HB_REQUIRE(arrs[i] && arrs[i]->dt == arrs[0]->dt, "flatten_concat: dtype mismatch at %d", i);
+    total += hb_numel(arrs[i]);
+  }
+  hb_array *o;
+  HB_TRY(hb_new_array(arrs[0]->dt, 1, &total, &o));
+  int64_t pos = 0;
+  for (int i = 0; i < k; i++) {
+    int64_t n = hb_numel(arrs[i]);
+    if (n == 0) continue;
+    hb_array *v = hb_new_view(o);
+    v->offset += pos;
+    v->rank = arrs[i]->rank;
+    int64_t st = 1;
+    for (int d = arrs[i]->rank - 1; d >= 0; d--) {
+      v->shape[d] = arrs[i]->shape[d];
+      v->strides[d] = st;
+      st *= arrs[i]->shape[d];
+    }
+    int s = copy_into(v, arrs[i]);
+    hb_release(v);
+    if (s != HB_OK) {
+      hb_release(o);
+      return s;
+    }
+    pos += n;
+  }
+  *out = o;
+  return HB_OK;
+}
+
 template <typename T>
 __global__ void hb_iota_kernel(T *o, int64_t n) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

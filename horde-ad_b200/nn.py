@@ -1,0 +1,122 @@
+"""Target-generic NN blocks: mirror of src/HordeAd/External/CommonShapedOps.hs.
+
+Each block exists in two forms, both written against the carrier method
+surface (so they run over the device carrier, the CPU oracle, or either wrapped
+in ADBackend):
+
+* `*_vectorised`: the op sequence horde-ad's vectoriser + simplifier produce
+  from the reference definitions (`kbuild` over `slicezS`/`sdot0`/`smaximum`),
+  i.e. what `interpretAst` actually sends to a backend: chained affine
+  `sgather`s (im2col), stride-0 `sreplicate`/`stranspose` views, `sdot1In`,
+  `ssumN`, data-dependent gathers with `kargMax` and `ifH`
+  (TestMnistPP.hs:735; bench/ConvVjpBench.hs:428-555).
+* fused: the nodes a device-specific contraction pass (sibling of
+  `contractAst`, AstTraverse.hs:290-699) would emit instead:
+  one C-ABI call per block.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import ix as ixm
+
+
+def _mul(T, a, b): return T.binary("mul", a, b)
+def _add(T, a, b): return T.binary("add", a, b)
+def _sub(T, a, b): return T.binary("sub", a, b)
+
+
+# ------------------------------------------------------------------ relu
+def reluS(T, v):
+    """reluS (CommonShapedOps.hs:38-44), fused."""
+    return T.relu(v)
+
+
+def reluS_vectorised(T, v):
+    """oneIfGtZero * v with the mask as the artifact builds it: a gather from
+    the constant [0.0, 1.0] with a data-dependent index
+    `ifH (0.0 <=. negate (v sindex0 ix)) 0 1` (TestMnistPP.hs:735)."""
+    sh = list(T.shape(v))
+    dt = T.dtype(v)
+    table = T.sconcrete(np.array([0.0, 1.0], dtype=dt))
+    plain = T.sprimalPart(v) if hasattr(T, "sprimalPart") else v
+
+    def f(ix):
+        x = T.ix_tbl(plain, ix)
+        return [ixm.ifH(ixm.Ix.lift(0.0) <= -x, 0, 1)]
+    mask = T.sgather(sh, table, f, 1)
+    return _mul(T, mask, v)
+
+
+# ------------------------------------------------------------------ conv
+def conv2dPreservingS(T, K, A):
+    """conv2dPreservingS (CommonShapedOps.hs:136-157), fused."""
+    return T.conv2dPreserving(K, A)
+
+
+def conv2dPreservingS_vectorised(T, K, A):
+    """The vectorised form: two chained affine gathers `[i + j]` build the
+    patch tensor (zeros beyond the high edge come from the gather's
+    out-of-bounds rule), then `ssumN . sdot1In` over broadcast views contracts
+    (c, kh, kw) (bench/ConvVjpBench.hs:428-555; TestMnistPP.hs:735)."""
+    Co, Ci, KH, KW = T.shape(K)
+    N, _, H, W = T.shape(A)
+    # rows: [H, KH, N, Ci, W] from A transposed to [H, N, Ci, W]
+    a_h = T.stranspose([2, 0, 1, 3], A)
+    g1 = T.sgather([H, KH], a_h, lambda ix: [ix[0] + ix[1]], 1)
+    # cols: bring W to the front: [W, H, KH, N, Ci] -> gather -> [W, KW, H, KH, N, Ci]
+    g1t = T.stranspose([4, 0, 1, 2, 3], g1)
+    g2 = T.sgather([W, KW], g1t, lambda ix: [ix[0] + ix[1]], 1)
+    # patches as [Ci, KH, N, Co, H, W, KW] (Co by replication)
+    p = T.stranspose([5, 3, 4, 2, 0, 1], g2)          # [Ci, KH, N, H, W, KW]
+    p = T.stranspose([1, 2, 3, 0], T.sreplicate(Co, p))  # [Ci, KH, N, Co, H, W, KW]
+    k = T.stranspose([1, 2, 0, 3], K)                 # [Ci, KH, Co, KW]
+    k = T.sreplicateN([N, H, W], k)                   # [N, H, W, Ci, KH, Co, KW]
+    k = T.stranspose([3, 4, 0, 5, 1, 2], k)           # [Ci, KH, N, Co, H, W, KW]
+    return T.sdot1InSumN(p, k, 2) if hasattr(T, "sdot1InSumN") else T.ssumN(T.sdot1In(p, k), 2)
+
+
+# --------------------------------------------------------------- maxpool
+def maxPool2dUnpaddedS(T, ksize, stride, x):
+    """maxPool2dUnpaddedS (CommonShapedOps.hs:241-260), fused."""
+    return T.maxpool2d(x, ksize, stride)
+
+
+def maxPool2dUnpaddedS_vectorised(T, ksize, stride, x):
+    """Windows by a gather with table lookups `[tblH[i, a], tblW[j, b]]`
+    (tbl = stride*i + a as a constant Int tensor, as the simplifier prints it),
+    then `smaximum` = gather at `kargMax` of the flattened window."""
+    N, Cc, H, W = T.shape(x)
+    Ho, Wo = H // stride, W // stride
+    th = T.sconcrete((stride * np.arange(Ho)[:, None] + np.arange(ksize)[None, :]).astype(np.int64))
+    tw = T.sconcrete((stride * np.arange(Wo)[:, None] + np.arange(ksize)[None, :]).astype(np.int64))
+    xt = T.stranspose([2, 3, 0, 1], x)                # [H, W, N, C]
+    win = T.sgather([Ho, Wo, ksize, ksize], xt,
+                    lambda ix: [T.ix_tbl(th, [ix[0], ix[2]]), T.ix_tbl(tw, [ix[1], ix[3]])], 2)
+    win = T.stranspose([4, 5, 0, 1, 2, 3], win)       # [N, C, Ho, Wo, ks, ks]
+    u = T.sreshape([N, Cc, Ho, Wo, ksize * ksize], win)
+    plain = T.sprimalPart(u) if hasattr(T, "sprimalPart") else u
+    return T.sgather([N, Cc, Ho, Wo], u,
+                     lambda ix: [ix[0], ix[1], ix[2], ix[3], T.ix_argmax(plain, ix)], 5)
+
+
+# ------------------------------------------------------------------ loss
+def lossSoftMaxCrossEntropyS(T, expected, d, scale=1.0):
+    """lossSoftMaxCrossEntropyS (CommonShapedOps.hs:89-111), fused with its
+    custom dual; `scale` folds the `recip batch_size *` of the callers
+    (MnistCnnShaped2.hs:136)."""
+    return T.softmax_xent(d, expected, scale)[0]
+
+
+def lossSoftMaxCrossEntropyS_vectorised(T, expected, d, scale=1.0):
+    """The same loss op by op (primal only; the reference attaches the dual
+    with tD, so differentiation goes through the fused form)."""
+    u = d
+    sh = list(T.shape(u))
+    flat = T.sreshape([int(np.prod(sh))], u)
+    umin = T.sindex(flat, [int(T.kfromS(T.sargMin(flat)))])       # sminimum (:28-31)
+    expU = T.unary("exp", _sub(T, u, T.sreplicate0N(sh, umin)))
+    recip_sum = T.unary("recip", T.ssum0(expU))
+    soft = _mul(T, T.sreplicate0N(sh, recip_sum), expU)
+    loss = T.unary("negate", T.sdot0(T.unary("log", soft), expected))
+    return _mul(T, T.sscalar(scale, T.dtype(u)), loss)

@@ -1,0 +1,159 @@
+"""Batch-sharded MNIST CNN training loop over the device carrier (SURVEY.md 8e;
+BASELINE.json config 4): every rank owns batch/world samples, interprets the
+same gradient program (the fused nodes of the device contraction pass) over
+its shard, and ONE all-reduce of the flattened gradient bucket (plus the loss
+in its last slot) over NVLink precedes the identical Adam step on every rank.
+
+The whole step (gradient program + bucket + all-reduce + optimizer) is
+recorded once into a CUDA graph; a training step is then
+  hb_upload_into (glyphs, labels from pinned host memory)  ->  hb_graph_launch
+  ->  one scalar read-back.
+Parameters, Adam moments and the bucket are leaves/views of flat device
+buffers so the optimizer is a single fused pass (OptimizerTools.hs:134-232).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import ad, ffi, mnist_cnn
+from .device import DeviceArray, DeviceBackend
+from .ffi import call
+
+
+class PinnedBuffer:
+    """Pinned host staging memory exposed as a numpy array."""
+
+    def __init__(self, shape, dtype):
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        call("hb_host_alloc", self.nbytes, C.byref(p))
+        self.ptr = p
+        buf = (C.c_char * self.nbytes).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def free(self):
+        if self.ptr is not None:
+            self.array = None
+            ffi.lib().hb_host_free(self.ptr)
+            self.ptr = None
+
+
+class CnnTrainer:
+    def __init__(self, dev: DeviceBackend, local_batch: int, kh=4, kw=4, c_out=16, n_hidden=64,
+                 dtype=np.float64, world=1, seed=44, use_graph=True, optimizer="adam", gamma=0.02):
+        self.dev, self.B, self.world, self.dtype = dev, local_batch, world, np.dtype(dtype)
+        self.optimizer, self.gamma = optimizer, gamma
+        self.hyper = (kh, kw, c_out, n_hidden)
+        host_params = mnist_cnn.init_params(kh, kw, c_out, n_hidden, seed=seed, dtype=dtype)
+        self.shapes = [p.shape for p in host_params]
+        self.sizes = [int(p.size) for p in host_params]
+        self.n_params = sum(self.sizes)
+        flat = np.concatenate([p.reshape(-1) for p in host_params])
+        self.flat_p = dev.sconcrete(flat)
+        self.flat_m = dev.sconcrete(np.zeros_like(flat))
+        self.flat_v = dev.sconcrete(np.zeros_like(flat))
+        self.params = self._leaves(self.flat_p)
+        self.glyphs = dev.sconcrete(np.zeros((local_batch, 28, 28), dtype))
+        self.labels = dev.sconcrete(np.zeros((local_batch, 10), dtype))
+        self.t = 0
+        self.graph = None
+        # the graph holds the gradient program + bucket + all-reduce; Adam's
+        # bias-corrected step size depends on t, so it is one eager launch after it
+        self.use_graph = use_graph
+        self.loss_arr = None
+        self.bucket = None
+
+    def _leaves(self, flat: DeviceArray):
+        out, pos = [], 0
+        for sh, n in zip(self.shapes, self.sizes):
+            out.append(self.dev.sreshape(list(sh), self.dev.sslice(pos, n, flat)))
+            pos += n
+        return out
+
+    # ---- one step, enqueued op by op -------------------------------------
+    def _gradient_program(self):
+        dev = self.dev
+        loss, grads = ad.grad(
+            dev, lambda T, *ps: mnist_cnn.convMnistLossFusedS(T, self.glyphs, self.labels, list(ps), fused=True),
+            self.params)
+        bucket = dev.flatten_concat(list(grads) + [loss])
+        call("hb_allreduce_sum", bucket.h, 1.0 / self.world)
+        return bucket
+
+    def _apply(self, bucket):
+        dev = self.dev
+        g = dev.sslice(0, self.n_params, bucket)
+        if self.optimizer == "adam":
+            self.t += 1
+            dev.adam_step(self.flat_p, self.flat_m, self.flat_v, g, self.t)
+        else:
+            dev.sgd_step(self.flat_p, g, self.gamma)
+
+    def step_enqueue(self):
+        """Enqueue one training step on the inputs currently in self.glyphs /
+        self.labels; returns the bucket whose last element is the mean loss."""
+        if self.use_graph:
+            if self.graph is None:
+                self._capture()
+            call("hb_graph_launch", self.graph)
+            if self.optimizer == "adam":
+                self._apply(self.bucket)
+            return self.bucket
+        bucket = self._gradient_program()
+        self._apply(bucket)
+        self.bucket = bucket
+        return bucket
+
+    def _capture(self):
+        # run once eagerly so every size class and the scratch buffer exist
+        b = self._gradient_program()
+        self.dev.sync()
+        del b
+        call("hb_graph_begin")
+        try:
+            self.bucket = self._gradient_program()
+            if self.optimizer != "adam":
+                self._apply(self.bucket)
+        finally:
+            g = C.c_void_p()
+            call("hb_graph_end", C.byref(g))
+        self.graph = g
+
+    # ---- public API --------------------------------------------------------
+    def upload(self, glyphs_ptr, labels_ptr):
+        self.dev.upload_into(self.glyphs, glyphs_ptr)
+        self.dev.upload_into(self.labels, labels_ptr)
+
+    def train_step(self, glyphs_ptr, labels_ptr) -> float:
+        """The end-to-end user call: H2D of the minibatch, step, loss D2H."""
+        self.upload(glyphs_ptr, labels_ptr)
+        bucket = self.step_enqueue()
+        return float(self.dev.kfromS(self.dev.sslice(self.n_params, 1, bucket)))
+
+    def loss_of(self, bucket) -> float:
+        return float(self.dev.kfromS(self.dev.sslice(self.n_params, 1, bucket)))
+
+    def get_params(self):
+        return [self.dev.to_numpy(p) for p in self.params]
+
+    def close(self):
+        if self.graph is not None:
+            call("hb_graph_free", self.graph)
+            self.graph = None
+
+
+def comm_init(rank: int, world: int, broadcast_bytes) -> None:
+    """hb_comm_init with the NCCL unique id created on rank 0 and shipped by
+    `broadcast_bytes(bytes_or_None) -> bytes` (the host process' own control
+    plane, e.g. torch.distributed over gloo)."""
+    if world == 1:
+        call("hb_comm_init", 0, 1, None)
+        return
+    buf = C.create_string_buffer(ffi.HB_UNIQUE_ID_BYTES)
+    if rank == 0:
+        call("hb_comm_unique_id", buf)
+    raw = broadcast_bytes(bytes(buf.raw) if rank == 0 else None)
+    idb = C.create_string_buffer(raw, ffi.HB_UNIQUE_ID_BYTES)
+    call("hb_comm_init", rank, world, idb)

@@ -155,6 +155,10 @@ int hb_append(const hb_array *a, const hb_array *b, hb_array **out);
  * shape arrays along a new leading axis.  k = 0 is an error ("empty vector",
  * OpsConcrete.hs:129). */
 int hb_stack(int k, hb_array *const *arrs, hb_array **out);
+/* Flatten k arrays (row-major) into one contiguous vector: the gradient
+ * bucket of the data-parallel loop (leaves of the TKProduct gradient,
+ * MnistCnnShaped2.hs:30-40, in order). */
+int hb_flatten_concat(int k, hb_array *const *arrs, hb_array **out);
 /* tsiota (OpsConcrete.hs:536): [0..n-1] in dtype dt. */
 int hb_iota(hb_dtype dt, int64_t n, hb_array **out);
 

@@ -1,0 +1,149 @@
+"""Objective functions transcribed from the reference's own test-suite, written
+against the carrier method surface so the same program runs on the oracle
+(CPU tests) and on the device backend (GPU tests).
+
+Sources (relative to the horde-ad tree):
+  test/simplified/TestGatherSimplified.hs:142-398   gather programs
+  test/simplified/TestGatherSimplified.hs:961-1232  scatter programs
+  test/simplified/TestGatherSimplified.hs:1262-1288 barRelu
+  test/simplified/TestConvSimplified.hs:183-297     conv gradients
+  test/tool/CrossTesting.hs:457-473                 fixtures t16b, t128, t128b, t128c
+"""
+import numpy as np
+
+from horde_ad_b200 import ix as ixm
+
+minH = ixm.minH
+
+T16B = np.array([5, 2, 6, 1, -2, 0, 0.1, -0.2, 13.1, 9, 8, -4, 582934, 2.99432, -335, 26],
+                dtype=np.float64).reshape(2, 2, 2, 2)
+T128 = np.array([29.1,32.1,40.1,29.0,53.99432,97.1,58.8943200001,18.1,29.1,32.1,40.1,32.0,53.99432,97.1,25.8943200001, 5, 2, 6, 1, -2, 97.1,58.8943200001,97.1,55.8943200001,97.1,58.8943200001,18.1,29.1,32.1,40.1,32.1,32.1,40.1,53.0,53.99432, -0.00001, 0.1, -0.2, 13.1, 9, 8, -4, 29, 2.99432, -335, 26, 2, 2, 2, 2, -0.2,-0.2,-0.2,-0.2,25.0003,25.0003,25.0003,25.0003,-0.2,-0.2,-0.2,-0.2,25.0003,25.0003,25.0003,25.0003,40.1,8.0,11.0,-3.0,25.89432,28.79432,-39.09999999999997,25.8,40.1,8.0,11.0,-3.0,25.89432,28.79432,-19.09999999999997,25.8, 8.1,29.1,32.1,40.1,32.1,40.1,292.0,53.99432,97.1,55.8943200001,97.1,85.8943200001,97.1,85.8943200001,18.1,29.1,32.1,40.1,32.1,40.1,32.1,40.1,22.0,53.99432,97.1,82.8943200001,97.1,22.8943200001,97.1,58.8943200001,18.1,29.1,32.1,40.1,32.1,40.1,32.1,40.1,89.0,53.99432,97.1,56.8943200001,97.1,52.8943200001,97.1,55.8943200001],
+                dtype=np.float64).reshape(1, 2, 2, 1, 2, 2, 2, 2, 2, 1)
+T128B = T128.reshape(4, 2, 4, 4)
+T128C = T128.reshape(2, 2, 8, 4)
+
+# rreplicate 7 $ ringestData [2] [0, 1]
+IN72 = np.tile(np.array([0.0, 1.0]), (7, 1))
+# vals of the interpreter-consistency tests (TestGatherSimplified.hs:212)
+VALS72 = np.array([-1, 0, 2.0, 5.0, 11.0, -17.0, 23.0, 29.0, -35.0, 41.0, 47.0, 33.0, 0.1, 0.007]).reshape(7, 2)
+
+
+# ---- gathers (TestGatherSimplified.hs:142-398) ---------------------------
+def gatherNested1(T, t):
+    inner = T.sgather([4], t, lambda i: [i[0]], 1)
+    return T.sgather([2], inner, lambda i: [i[0] + i[0], i[0]], 2)
+
+
+def gather1(T, t):
+    return T.sgather([2], T.sslice(0, 4, t), lambda i: [i[0] + i[0], i[0]], 2)
+
+
+def gatherNested02(T, t):
+    inner = T.sgather([2], t, lambda k: [k[0] + k[0]], 1)
+    return T.sgather([1], inner, lambda i: [i[0] + i[0] + i[0]], 1)
+
+
+def gatherNested2(T, t):
+    inner = T.sgather([2, 3, 4], t, lambda k: [k[0] + k[1] + k[2]], 1)
+    return T.sgather([2, 3], inner, lambda i: [i[0], i[1], i[0] + i[1], i[0]], 4)
+
+
+def gather2(T, t):
+    return T.sgather([2, 3], t, lambda i: [i[0] + i[1] + i[0] + i[1], i[0]], 2)
+
+
+def gatherNested12(T, t):
+    inner = T.sgather([2, 3, 4], t, lambda k: [k[0] + k[1] + k[2], k[0]], 2)
+    return T.sgather([2], inner, lambda i: [i[0], i[0] + i[0]], 2)
+
+
+def gather12(T, t):
+    return T.sgather([2, 4], t, lambda i: [i[0] + i[0] + i[0] + i[1], i[0]], 2)
+
+
+# ---- scatters (TestGatherSimplified.hs:961-1232) -------------------------
+def scatterNested1(T, t):
+    inner = T.sscatter([7], t, lambda k: [k[0]], 1)
+    return T.sscatter([2], inner, lambda i: [i[1].quotH(1 + i[0])], 2)
+
+
+def scatter1(T, t):
+    return T.sscatter([2], t, lambda i: [minH(i[1] + 2 * i[0], 1)], 2)
+
+
+def scatterNested2(T, t):
+    inner = T.sscatter([2, 3, 4], t, lambda k: [minH(k[0], 1), minH(k[0], 2), minH(k[0], 3)], 1)
+    return T.sscatter([2, 3], inner, lambda i: [minH(i[0] + i[1], 1), minH(i[3] + i[0], 2)], 4)
+
+
+def scatter2(T, t):
+    return T.sscatter([2, 3], t, lambda i: [minH(i[0] + i[1] + i[0] + i[1], 1), minH(i[0], 2)], 2)
+
+
+def scatterNested12(T, t):
+    inner = T.sscatter([2, 3, 4], t, lambda k: [minH(k[0], 1), minH(k[1] + k[0], 2), minH(k[0], 3)], 2)
+    return T.sscatter([2], inner, lambda i: [minH(i[0] + i[0], 1)], 2)
+
+
+def scatter12(T, t):
+    return T.sscatter([2, 4], t, lambda i: [minH(i[0] + i[0] + i[0] + i[1], 1), minH(i[0], 3)], 2)
+
+
+ONES72 = [1.0] * 14
+GATHER_GOLDEN = [
+    # (name, program, input, expected gradient wrt the input, dt = ones)
+    ("gatherNested1", gatherNested1, IN72, [1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0]),
+    ("gather1", gather1, IN72, [1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0]),
+    ("gatherNested02", gatherNested02, np.full(4, 0.1), [1, 0, 0, 0]),
+    ("gatherNested2", gatherNested2, IN72, [1, 0, 0, 0, 1, 1, 0, 0, 1, 1, 0, 0, 0, 1]),
+    ("gather2", gather2, IN72, [1, 0, 0, 0, 1, 1, 0, 0, 1, 1, 0, 0, 0, 1]),
+    ("gatherNested12", gatherNested12, IN72, [1, 0, 1, 0, 1, 0, 1, 1, 0, 1, 0, 1, 0, 1]),
+    ("gather12", gather12, IN72, [1, 0, 1, 0, 1, 0, 1, 1, 0, 1, 0, 1, 0, 1]),
+    ("scatterNested1", scatterNested1, IN72, ONES72),
+    ("scatter1", scatter1, IN72, ONES72),
+    ("scatterNested2", scatterNested2, IN72, ONES72),
+    ("scatter2", scatter2, IN72, ONES72),
+    ("scatterNested12", scatterNested12, IN72, ONES72),
+    ("scatter12", scatter12, IN72, ONES72),
+]
+
+# pairs the reference asserts to be @?=-equal (bit-exact) on VALS72
+# (TestGatherSimplified.hs:208-235, 302-345): nested == fused-by-hand
+GATHER_EQUAL_PAIRS = [(gatherNested1, gather1), (gatherNested2, gather2), (gatherNested12, gather12)]
+
+
+# ---- barRelu (TestGatherSimplified.hs:1262-1288) -------------------------
+def _foo(T, x, y, z):
+    w = T.binary("mul", x, T.unary("sin", y))
+    return T.binary("add", T.binary("atan2", z, w), T.binary("mul", z, w))
+
+
+def _bar(T, x, y):
+    w = T.binary("mul", _foo(T, x, y, x), T.unary("sin", y))
+    return T.binary("add", T.binary("atan2", x, w), T.binary("mul", y, w))
+
+
+def barRelu(T, x):
+    from horde_ad_b200 import nn
+    sh = list(T.shape(x))
+    t = T.binary("mul", T.srepl(sh, 0.001), x)
+    return nn.reluS(T, _bar(T, t, nn.reluS(T, t)))
+
+
+BARRELU_GOLDEN = np.array([2.885038541771792e-4,2.885145151321922e-4,2.8854294397024206e-4,2.885034988157713e-4,2.885923176600045e-4,2.887454843457817e-4,2.886097295122454e-4,2.8846476339094805e-4,2.885038541771792e-4,2.885145151321922e-4,2.8854294397024206e-4,2.8851415976532735e-4,2.885923176600045e-4,2.887454843457817e-4,2.8849246223035154e-4,2.884182085399516e-4,2.884075468755327e-4,2.8842176240868867e-4,2.8840399312321096e-4,0.0,2.887454843457817e-4,2.886097295122454e-4,2.887454843457817e-4,2.88599069218435e-4,2.887454843457817e-4,2.886097295122454e-4,2.8846476339094805e-4,2.885038541771792e-4,2.885145151321922e-4,2.8854294397024206e-4,2.885145151321922e-4,2.885145151321922e-4,2.8854294397024206e-4,2.8858878438222746e-4,2.885923176600045e-4,0.0,2.884007943794131e-4,0.0,2.884469945274759e-4,2.8843242392031246e-4,2.884288700806792e-4,0.0,2.885034988157713e-4,2.884110805753153e-4,0.0,2.8849283778617973e-4,2.884075468755327e-4,2.884075468755327e-4,2.884075468755327e-4,2.884075468755327e-4,0.0,0.0,0.0,0.0,2.884892851579934e-4,2.884892851579934e-4,2.884892851579934e-4,2.884892851579934e-4,0.0,0.0,0.0,0.0,2.884892851579934e-4,2.884892851579934e-4,2.884892851579934e-4,2.884892851579934e-4,2.8854294397024206e-4,2.884288700806792e-4,2.884395315486472e-4,0.0,2.8849246223035154e-4,2.8850276789489724e-4,0.0,2.8849212704517413e-4,2.8854294397024206e-4,2.884288700806792e-4,2.884395315486472e-4,0.0,2.8849246223035154e-4,2.8850276789489724e-4,0.0,2.8849212704517413e-4,2.8842922547482884e-4,2.885038541771792e-4,2.885145151321922e-4,2.8854294397024206e-4,2.885145151321922e-4,2.8854294397024206e-4,2.894378297730782e-4,2.885923176600045e-4,2.887454843457817e-4,2.88599069218435e-4,2.887454843457817e-4,2.887056688523444e-4,2.887454843457817e-4,2.887056688523444e-4,2.8846476339094805e-4,2.885038541771792e-4,2.885145151321922e-4,2.8854294397024206e-4,2.885145151321922e-4,2.8854294397024206e-4,2.885145151321922e-4,2.8854294397024206e-4,2.884786229769816e-4,2.885923176600045e-4,2.887454843457817e-4,2.886950092188272e-4,2.887454843457817e-4,2.884818011261814e-4,2.887454843457817e-4,2.886097295122454e-4,2.8846476339094805e-4,2.885038541771792e-4,2.885145151321922e-4,2.8854294397024206e-4,2.885145151321922e-4,2.8854294397024206e-4,2.885145151321922e-4,2.8854294397024206e-4,2.887167039107226e-4,2.885923176600045e-4,2.887454843457817e-4,2.8860262265516213e-4,2.887454843457817e-4,2.885884088500461e-4,2.887454843457817e-4,2.88599069218435e-4])
+
+# ---- conv gradients (TestConvSimplified.hs:183-297) -----------------------
+# (name, kernel K or None, input A or None, differentiate wrt, expected, eps)
+CONV_GOLDEN = [
+    ("KonstG0Rev", T16B, np.zeros((2, 2, 2, 2)), "A",
+     [18.1,29.1,32.1,40.1,582932.0,582934.99432,582597.1,582625.8943200001,18.1,29.1,32.1,40.1,582932.0,582934.99432,582597.1,582625.8943200001], 1e-4),
+    ("KonstG0Tiny1", np.array([-0.2]).reshape(1, 1, 1, 1), np.zeros((1, 1, 1, 1)), "A", [-0.2], 1e-10),
+    ("KonstG0TinyS", np.full((1, 1, 1, 1), T16B.sum()), np.zeros((1, 1, 1, 1)), "A", [582665.99432], 1e-10),
+    ("KonstG0TinyA", np.array([-0.2, 25.0003]).reshape(1, 2, 1, 1), np.zeros((1, 2, 1, 1)), "A", [-0.2, 25.0003], 1e-10),
+    ("KonstG0LittleA", np.array([-0.2, 25.0003]).reshape(1, 2, 1, 1), np.zeros((2, 2, 2, 2)), "A",
+     [-0.2,-0.2,-0.2,-0.2,25.0003,25.0003,25.0003,25.0003,-0.2,-0.2,-0.2,-0.2,25.0003,25.0003,25.0003,25.0003], 1e-10),
+    ("Konst5LittleB", T16B, np.full((2, 2, 2, 2), 5.0), "A",
+     [18.1,29.1,32.1,40.1,582932.0,582934.99432,582597.1,582625.8943200001,18.1,29.1,32.1,40.1,582932.0,582934.99432,582597.1,582625.8943200001], 1e-8),
+    ("Konst5LittleC", np.full((2, 2, 2, 2), 5.0), T16B, "K",
+     [40.1,8.0,11.0,-3.0,582625.89432,28.79432,-309.09999999999997,25.8,40.1,8.0,11.0,-3.0,582625.89432,28.79432,-309.09999999999997,25.8], 1e-8),
+]

@@ -1,0 +1,479 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle.
+
+Bar (BASELINE.json north_star): bit-exact for data movement, indexing and
+integer work; 1e-12 relative for Double, 1e-5 for Float floating point.
+Every test here needs a B200 (`-m gpu`); the library has no CPU fallback.
+"""
+import numpy as np
+import pytest
+
+from horde_ad_b200 import ad, ffi, ix as ixm, nn, mnist_cnn
+from tests import programs as P
+
+pytestmark = pytest.mark.gpu
+
+RTOL = {np.dtype(np.float64): 1e-12, np.dtype(np.float32): 1e-5}
+ALL_DTYPES = [np.float64, np.float32, np.int64, np.int32, np.int16, np.int8, np.bool_]
+
+
+def rnd(rng, shape, dtype=np.float64, lo=-0.5, hi=0.5):
+    dtype = np.dtype(dtype)
+    if dtype == np.bool_:
+        return rng.integers(0, 2, shape).astype(np.bool_)
+    if np.issubdtype(dtype, np.integer):
+        return rng.integers(-100, 100, shape).astype(dtype)
+    return rng.uniform(lo, hi, shape).astype(dtype)
+
+
+def close(dev_arr, ref, dtype=None, scale=1.0):
+    dtype = np.dtype(dtype or ref.dtype)
+    got = dev_arr if isinstance(dev_arr, np.ndarray) else None
+    assert got is not None
+    assert got.shape == tuple(ref.shape), (got.shape, ref.shape)
+    if np.issubdtype(dtype, np.floating):
+        tol = RTOL[dtype] * scale
+        np.testing.assert_allclose(got, ref, rtol=tol, atol=tol * max(1.0, float(np.max(np.abs(ref))) if ref.size else 1.0))
+    else:
+        np.testing.assert_array_equal(got, ref)
+
+
+def exact(got, ref):
+    assert got.shape == tuple(ref.shape) and got.dtype == ref.dtype, (got.shape, ref.shape, got.dtype, ref.dtype)
+    assert np.array_equal(got.view(np.uint8) if got.dtype != np.bool_ else got,
+                          np.ascontiguousarray(ref).view(np.uint8) if ref.dtype != np.bool_ else ref), "not bit-exact"
+
+
+# ------------------------------------------------------------------ plumbing
+@pytest.mark.parametrize("dtype", ALL_DTYPES)
+def test_roundtrip_and_views(dev, oracle, dtype):
+    rng = np.random.default_rng(0)
+    a = rnd(rng, (3, 4, 5), dtype)
+    d = dev.sconcrete(a)
+    exact(dev.to_numpy(d), a)
+    for perm in ([1, 0], [2, 0, 1], [0, 2, 1]):
+        exact(dev.to_numpy(dev.stranspose(perm, d)), np.ascontiguousarray(oracle.stranspose(perm, a)))
+    exact(dev.to_numpy(dev.sreplicateN([2, 3], d)), np.ascontiguousarray(oracle.sreplicateN([2, 3], a)))
+    exact(dev.to_numpy(dev.sslice(1, 2, d)), a[1:3])
+    exact(dev.to_numpy(dev.sreverse(d)), np.ascontiguousarray(a[::-1]))
+    exact(dev.to_numpy(dev.sreshape([4, 15], d)), a.reshape(4, 15))
+    exact(dev.to_numpy(dev.sreshape([5, 12], dev.stranspose([2, 1, 0], d))), np.transpose(a, (2, 1, 0)).reshape(5, 12))
+    exact(dev.to_numpy(dev.sindex(d, [2, 1])), a[2, 1])
+    exact(dev.to_numpy(dev.sindex(d, [3, 1])), np.zeros(5, dtype))      # OOB -> zeros
+    exact(dev.to_numpy(dev.sindex(d, [-1])), np.zeros((4, 5), dtype))
+    exact(dev.to_numpy(dev.sappend(d, dev.sreverse(d))), np.concatenate([a, a[::-1]]))
+    exact(dev.to_numpy(dev.sfromVector([d, dev.sreverse(d)])), np.stack([a, a[::-1]]))
+    exact(dev.to_numpy(dev.srepl([2, 3], a.reshape(-1)[0], dtype)), np.full((2, 3), a.reshape(-1)[0], dtype))
+    exact(dev.to_numpy(dev.soneHot([2, 3], dev.sindex(d, [0, 0]), [1, 2])), oracle.soneHot([2, 3], a[0, 0], [1, 2]))
+    exact(dev.to_numpy(dev.soneHot([2, 3], dev.sindex(d, [0, 0]), [2, 0])), np.zeros((2, 3, 5), dtype))
+    assert dev.kfromS(dev.sindex(d, [1, 2, 3])) == a[1, 2, 3]
+
+
+def test_empty_and_errors(dev):
+    e = dev.sconcrete(np.zeros((0, 3)))
+    assert dev.to_numpy(e).shape == (0, 3)
+    assert dev.to_numpy(dev.ssum(e)).tolist() == [0, 0, 0]
+    assert dev.to_numpy(dev.binary("add", e, e)).shape == (0, 3)
+    with pytest.raises(ffi.HordeError, match="empty vector"):
+        dev.sfromVector([])
+    with pytest.raises(ffi.HordeError):
+        dev.binary("add", dev.sconcrete(np.zeros(3)), dev.sconcrete(np.zeros(4)))
+    with pytest.raises(ffi.HordeError):
+        dev.binary("add", dev.sconcrete(np.zeros(3)), dev.sconcrete(np.zeros(3, np.float32)))
+    with pytest.raises(ffi.HordeError):
+        dev.unary("exp", dev.sconcrete(np.zeros(3, np.int64)))
+    with pytest.raises(ffi.HordeError):
+        dev.sreshape([7], dev.sconcrete(np.zeros(6)))
+
+
+# --------------------------------------------------------------- elementwise
+EXACT_UN = ["negate", "abs", "signum"]
+DOMAIN = {"log": (0.1, 3), "sqrt": (0, 3), "asin": (-.9, .9), "acos": (-.9, .9), "acosh": (1.1, 4), "atanh": (-.9, .9)}
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("op", ffi.UNOPS)
+def test_unary_float(dev, oracle, op, dtype):
+    rng = np.random.default_rng(1)
+    lo, hi = DOMAIN.get(op, (-2, 2))
+    a = rnd(rng, (7, 33, 5), dtype, lo, hi)
+    for view in (lambda T, t: t, lambda T, t: T.stranspose([2, 0, 1], t), lambda T, t: T.sreplicate(2, T.sindex(t, [1]))):
+        got = dev.to_numpy(dev.unary(op, view(dev, dev.sconcrete(a))))
+        ref = oracle.unary(op, view(oracle, a))
+        if op in EXACT_UN or op in ("recip", "sqrt"):
+            exact(got, np.ascontiguousarray(ref))   # IEEE-exact operations
+        else:
+            close(got, ref, dtype, scale=4)
+
+
+@pytest.mark.parametrize("dtype", [np.int64, np.int32, np.int16, np.int8])
+def test_int_arith(dev, oracle, dtype):
+    rng = np.random.default_rng(2)
+    a, b = rnd(rng, (5, 9), dtype), rnd(rng, (5, 9), dtype)
+    b[0, :3] = 0  # zero divisors: array quotH/remH replace them by 1
+    da, db = dev.sconcrete(a), dev.sconcrete(b)
+    for op in EXACT_UN:
+        exact(dev.to_numpy(dev.unary(op, da)), oracle.unary(op, a).astype(dtype))
+    for op in ("add", "sub", "mul", "quot", "rem", "max", "min"):
+        exact(dev.to_numpy(dev.binary(op, da, db)), oracle.binary(op, a, b).astype(dtype))
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_binary_float(dev, oracle, dtype):
+    rng = np.random.default_rng(3)
+    a, b = rnd(rng, (6, 130), dtype, 0.1, 2), rnd(rng, (6, 130), dtype, 0.1, 2)
+    da, db = dev.sconcrete(a), dev.sconcrete(b)
+    for op in ("add", "sub", "mul", "divide", "max", "min"):
+        exact(dev.to_numpy(dev.binary(op, da, db)), oracle.binary(op, a, b))
+    for op in ("power", "logbase", "atan2"):
+        close(dev.to_numpy(dev.binary(op, da, db)), oracle.binary(op, a, b), dtype, scale=8)
+    # broadcast (stride-0) and transposed operands, long inner axis (rows kernel)
+    big = rnd(rng, (4, 3, 700), dtype)
+    bias = rnd(rng, (3,), dtype)
+    dv = dev.stranspose([1, 2, 0], dev.sreplicateN([4, 700], dev.sconcrete(bias)))
+    rv = oracle.stranspose([1, 2, 0], oracle.sreplicateN([4, 700], bias))
+    exact(dev.to_numpy(dev.binary("add", dev.sconcrete(big), dv)), big + rv)
+    s = dev.srepl([4, 3, 700], 0.25, dtype)
+    exact(dev.to_numpy(dev.binary("mul", s, dev.sconcrete(big))), (np.array(0.25, dtype) * big))
+
+
+def test_large_vector_path(dev):
+    rng = np.random.default_rng(4)
+    n = (1 << 22) + 3
+    a, b = rng.standard_normal(n), rng.standard_normal(n)
+    exact(dev.to_numpy(dev.binary("add", dev.sconcrete(a), dev.sconcrete(b))), a + b)
+    off = dev.sslice(1, n - 1, dev.sconcrete(a))     # misaligned view -> scalar fallback
+    exact(dev.to_numpy(dev.unary("negate", off)), -a[1:])
+
+
+def test_casts_iota_compare(dev, oracle):
+    rng = np.random.default_rng(5)
+    for src in ALL_DTYPES:
+        a = rnd(rng, (4, 6), src, -3, 3)
+        for dst in ALL_DTYPES:
+            exact(dev.to_numpy(dev.scast(dev.sconcrete(a), dst)), oracle.scast(a, dst))
+    f = rng.uniform(-5, 5, (3, 8))
+    for dst in (np.int64, np.int32, np.int16, np.int8):
+        exact(dev.to_numpy(dev.sfloor(dev.sconcrete(f), dst)), oracle.sfloor(f, dst))
+    for dt in (np.int64, np.float64, np.float32, np.int8):
+        exact(dev.to_numpy(dev.siota(11, dt)), oracle.siota(11, dt))
+    a = rng.integers(0, 3, (4, 5)).astype(np.float64)
+    for b in (a.copy(), a + np.eye(4, 5), a - np.eye(4, 5)[::-1]):
+        da, db = dev.sconcrete(a), dev.sconcrete(b)
+        assert dev.all_eq(da, db) == oracle.all_eq(a, b)
+        assert dev.all_leq(da, db) == oracle.all_leq(a, b)
+        assert dev.all_lt(da, db) == oracle.all_lt(a, b)
+
+
+def test_fused_map(dev, oracle):
+    rng = np.random.default_rng(6)
+    for dtype in (np.float64, np.float32):
+        x, y = rnd(rng, (5, 77), dtype), rnd(rng, (5, 77), dtype)
+        a, b = ixm.map_input(0, True), ixm.map_input(1, True)
+        expr = ixm.ifH(a <= 0.0, ixm.Ix.lift(0.0), a) * ixm.fun1("tanh", b) + a * b
+        got = dev.to_numpy(dev.fused_map(expr, [dev.stranspose([1, 0], dev.sconcrete(x.T.copy())), dev.sconcrete(y)], dtype))
+        ref = oracle.fused_map(expr, [x, y], dtype)
+        close(got, ref, dtype, scale=4)
+
+
+def test_add_accumulate_in_place(dev):
+    a = np.arange(12.0).reshape(3, 4)
+    acc = dev.sconcrete(a)
+    keep = dev.stranspose([1, 0], acc)      # second reference to the storage -> must not mutate
+    r = dev.add_accumulate(acc, dev.sconcrete(a))
+    assert r is not acc
+    exact(dev.to_numpy(acc), a)
+    del keep
+    r2 = dev.add_accumulate(acc, dev.sconcrete(a))
+    assert r2 is acc                        # uniquely referenced -> in place
+    exact(dev.to_numpy(acc), 2 * a)
+
+
+# ---------------------------------------------------------------- reductions
+@pytest.mark.parametrize("dtype", [np.float64, np.float32, np.int64, np.int32])
+def test_sums_and_dots(dev, oracle, dtype):
+    rng = np.random.default_rng(7)
+    a = rnd(rng, (6, 5, 40, 7), dtype)
+    b = rnd(rng, (6, 5, 40, 7), dtype)
+    da, db = dev.sconcrete(a), dev.sconcrete(b)
+    views = [lambda T, t: t, lambda T, t: T.stranspose([3, 2, 1, 0], t), lambda T, t: T.stranspose([1, 3, 0, 2], t)]
+    for v in views:
+        for n in range(0, 5):
+            close(dev.to_numpy(dev.ssumN(v(dev, da), n)), oracle.ssumN(v(oracle, a), n), dtype, scale=10)
+        close(dev.to_numpy(dev.sdot0(v(dev, da), v(dev, db))), np.asarray(oracle.sdot0(v(oracle, a), v(oracle, b))), dtype, scale=10)
+        close(dev.to_numpy(dev.sdot1In(v(dev, da), v(dev, db))), oracle.sdot1In(v(oracle, a), v(oracle, b)), dtype, scale=10)
+    close(dev.to_numpy(dev.ssum0(da)).reshape(()), np.asarray(oracle.ssum0(a)), dtype, scale=10)
+
+
+def test_bias_gradient_shapes(dev, oracle):
+    # ssumN @[N,H,W] over a [N,H,W,C] view of [N,C,H,W] (TestMnistPP.hs:735)
+    rng = np.random.default_rng(8)
+    t = rng.uniform(-.5, .5, (33, 16, 14, 14))
+    v = lambda T, x: T.stranspose([0, 2, 3, 1], x)
+    close(dev.to_numpy(dev.ssumN(v(dev, dev.sconcrete(t)), 3)), oracle.ssumN(v(oracle, t), 3), scale=10)
+    big = rng.uniform(-.5, .5, (3_000_017,))
+    close(dev.to_numpy(dev.ssum0(dev.sconcrete(big))).reshape(()), np.asarray(big.sum()), scale=100)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_matmul_family(dev, oracle, dtype):
+    rng = np.random.default_rng(9)
+    for (m, k, n) in [(64, 784, 70), (10, 64, 33), (1, 5, 1), (130, 17, 129), (3, 1, 4)]:
+        a, b = rnd(rng, (m, k), dtype), rnd(rng, (k, n), dtype)
+        ref = (a.astype(np.float64) @ b.astype(np.float64)).astype(dtype)
+        close(dev.to_numpy(dev.smatmul2(dev.sconcrete(a), dev.sconcrete(b))), ref, dtype, scale=50)
+        close(dev.to_numpy(dev.smatmul2(dev.stranspose([1, 0], dev.sconcrete(a.T.copy())), dev.sconcrete(b))), ref, dtype, scale=50)
+        v = rnd(rng, (k,), dtype)
+        close(dev.to_numpy(dev.smatvecmul(dev.sconcrete(a), dev.sconcrete(v))),
+              (a.astype(np.float64) @ v.astype(np.float64)).astype(dtype), dtype, scale=50)
+    # the reference's literal formulation through broadcast views (OpsConcrete.hs:237-242)
+    a, b = rnd(rng, (40, 50), dtype), rnd(rng, (50, 30), dtype)
+    lit = lambda T, x, y: T.sdot1In(T.stranspose([1, 0], T.sreplicate(30, x)), T.stranspose([0, 2, 1], T.sreplicate(40, y)))
+    close(dev.to_numpy(lit(dev, dev.sconcrete(a), dev.sconcrete(b))), lit(oracle, a, b), dtype, scale=50)
+
+
+def test_argmax_argmin(dev, oracle):
+    rng = np.random.default_rng(10)
+    a = rng.integers(0, 4, (5, 6, 9)).astype(np.float64)     # many ties: first extremum wins
+    exact(dev.to_numpy(dev.sargMax(dev.sconcrete(a))), oracle.sargMax(a))
+    exact(dev.to_numpy(dev.sargMin(dev.sconcrete(a))), oracle.sargMin(a))
+    v = lambda T, x: T.stranspose([2, 0, 1], x)
+    exact(dev.to_numpy(dev.sargMax(v(dev, dev.sconcrete(a)))), oracle.sargMax(v(oracle, a)))
+
+
+# ---------------------------------------------------------- gather / scatter
+@pytest.mark.parametrize("name,prog,inp,expected", P.GATHER_GOLDEN, ids=[g[0] for g in P.GATHER_GOLDEN])
+def test_reference_gather_scatter_programs(dev, oracle, name, prog, inp, expected):
+    # values on VALS72-like data: bit-exact vs oracle; gradients: the reference's goldens
+    data = P.VALS72 if inp.shape == (7, 2) else np.array([0.1, -3.0, 7.5, 2.25])
+    exact(dev.to_numpy(prog(dev, dev.sconcrete(data))), np.ascontiguousarray(prog(oracle, data)))
+    _, (g,) = ad.grad(dev, lambda T, t: prog(T, t), [dev.sconcrete(inp)])
+    np.testing.assert_allclose(dev.to_numpy(g).reshape(-1), np.array(expected, dtype=float), atol=1e-10, rtol=0)
+
+
+@pytest.mark.parametrize("dtype", ALL_DTYPES)
+def test_gather_kinds_bit_exact(dev, oracle, dtype):
+    rng = np.random.default_rng(11)
+    src = rnd(rng, (9, 7, 5), dtype)
+    d = dev.sconcrete(src)
+    tbl = rng.integers(-2, 11, (6, 4)).astype(np.int64)
+    cases = [
+        ([4, 3], 1, lambda T: (lambda i: [i[0] + i[1]])),                       # affine in bounds -> view
+        ([9, 4], 1, lambda T: (lambda i: [i[0] + i[1]])),                       # affine, high-side OOB
+        ([5, 5], 2, lambda T: (lambda i: [2 * i[0] - 1, i[1] + i[0] - 2])),     # affine, both-side OOB
+        ([6, 4], 2, lambda T: (lambda i: [T.ix_tbl(T.sconcrete(tbl), [i[0], i[1]]), i[1].remH(3) + i[0].quotH(2)])),
+        ([6, 4], 3, lambda T: (lambda i: [ixm.ifH((i[0] <= 2) & ~(i[1].eq(1)), i[0], 8 - i[0]), abs(i[1] - 2), ixm.maxH(i[0] - i[1], 0)])),
+        ([3], 0, lambda T: (lambda i: [])),                                     # replicate-like
+    ]
+    for shm, p, mk in cases:
+        got = dev.to_numpy(dev.sgather(shm, d, mk(dev), p))
+        ref = oracle.sgather(shm, src, mk(oracle), p)
+        exact(got, np.ascontiguousarray(ref))
+    # strided (transposed) source
+    got = dev.to_numpy(dev.sgather([5, 2], dev.stranspose([2, 0, 1], d), lambda i: [i[0] - i[1]], 1))
+    exact(got, oracle.sgather([5, 2], np.transpose(src, (2, 0, 1)), lambda i: [i[0] - i[1]], 1))
+
+
+def test_gather_data_dependent(dev, oracle):
+    rng = np.random.default_rng(12)
+    u = rng.integers(0, 3, (4, 5, 6)).astype(np.float64)   # ties
+    prog = lambda T, x: T.sgather([4, 5], x, lambda i: [i[0], i[1], T.ix_argmax(x, i)], 3)
+    exact(dev.to_numpy(prog(dev, dev.sconcrete(u))), prog(oracle, u))
+    x = rng.uniform(-.5, .5, (3, 2, 6, 8))
+    exact(dev.to_numpy(nn.reluS_vectorised(dev, dev.sconcrete(x))), nn.reluS_vectorised(oracle, x))
+    exact(dev.to_numpy(nn.maxPool2dUnpaddedS_vectorised(dev, 2, 2, dev.sconcrete(x))), nn.maxPool2dUnpaddedS_vectorised(oracle, 2, 2, x))
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32, np.int64, np.int32, np.int16, np.int8])
+def test_scatter_bit_exact_order(dev, oracle, dtype):
+    rng = np.random.default_rng(13)
+    src = rnd(rng, (12, 10, 3), dtype)
+    d = dev.sconcrete(src)
+    cases = [
+        ([12, 10], 2, lambda i: [i[0], i[1]]),                          # injective -> direct path
+        ([5], 2, lambda i: [(i[0] + i[1]).remH(7) - 1]),                # collisions + drops
+        ([3, 2], 2, lambda i: [i[0].quotH(5), i[1].remH(2)]),           # heavier collisions
+        ([4], 1, lambda i: [ixm.minH(i[0], 3)]),                        # slices of rank 2
+        ([2], 3, lambda i: [ixm.minH(i[0] + i[1] + i[2], 1)]),          # rank-0 slices, long lists
+    ]
+    for shp, m, f in cases:
+        got = dev.to_numpy(dev.sscatter(shp, d, f, m))
+        ref = oracle.sscatter(shp, src, f, m)
+        exact(got, ref)   # same accumulation order as the reference => identical bits
+    # transposed source
+    got = dev.to_numpy(dev.sscatter([6], dev.stranspose([1, 0], d), lambda i: [i[0].quotH(2) + i[1].remH(2)], 2))
+    exact(got, oracle.sscatter([6], np.transpose(src, (1, 0, 2)), lambda i: [i[0].quotH(2) + i[1].remH(2)], 2))
+
+
+def test_scatter_long_segments(dev, oracle):
+    rng = np.random.default_rng(14)
+    src = rng.uniform(-.5, .5, (5000,))
+    f = lambda i: [ixm.ifH(i[0] <= 4000, 0, i[0].remH(3) + 1)]     # 4001 contributions to slot 0
+    exact(dev.to_numpy(dev.sscatter([4], dev.sconcrete(src), f, 1)), oracle.sscatter([4], src, f, 1))
+    src2 = rng.uniform(-.5, .5, (300, 4))
+    f2 = lambda i: [i[0].remH(2)]                                    # 150 slices per destination
+    exact(dev.to_numpy(dev.sscatter([2], dev.sconcrete(src2), f2, 1)), oracle.sscatter([2], src2, f2, 1))
+
+
+def test_gather_scatter_adjoint(dev):
+    # checkAdjoint (bench/ConvVjpBench.hs:564-584) at the gather48 shapes (:428-439)
+    rng = np.random.default_rng(15)
+    x = dev.sconcrete(rng.uniform(-.5, .5, (50, 3, 3, 50)))
+    f = lambda i: [i[0] + i[1]]
+    g = dev.sgather([48, 3], x, f, 1)
+    y = dev.sconcrete(rng.uniform(-.5, .5, dev.shape(g)))
+    lhs = dev.kfromS(dev.sdot0(g, y))
+    rhs = dev.kfromS(dev.sdot0(x, dev.sscatter([50], y, f, 2)))
+    assert abs(lhs - rhs) <= 1e-12 * max(1.0, abs(lhs))
+
+
+# -------------------------------------------------------------------- conv
+@pytest.mark.parametrize("name,K,A,wrt,expected,eps", P.CONV_GOLDEN, ids=[c[0] for c in P.CONV_GOLDEN])
+@pytest.mark.parametrize("form", ["fused", "vectorised"])
+def test_conv_reference_goldens(dev, form, name, K, A, wrt, expected, eps):
+    conv = nn.conv2dPreservingS if form == "fused" else nn.conv2dPreservingS_vectorised
+    Kt, At = dev.sconcrete(K), dev.sconcrete(A)
+    if wrt == "A":
+        _, (g,) = ad.grad(dev, lambda T, a: conv(T, Kt, a), [At])
+    else:
+        _, (g,) = ad.grad(dev, lambda T, k: conv(T, k, At), [Kt])
+    np.testing.assert_allclose(dev.to_numpy(g).reshape(-1), np.array(expected), atol=eps, rtol=0)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("shape", [(3, 3, 3, 6, 6, 3, 3), (2, 5, 7, 9, 4, 2, 4), (5, 1, 16, 12, 12, 5, 5), (1, 1, 1, 1, 1, 1, 1),
+                                   (4, 16, 16, 14, 14, 5, 5), (2, 3, 2, 5, 0, 3, 3), (3, 2, 2, 3, 3, 4, 5)])
+def test_conv_fwd_vjp_vs_oracle(dev, oracle, dtype, shape):
+    N, Ci, Co, H, W, KH, KW = shape
+    rng = np.random.default_rng(16)
+    K, A, dB = rnd(rng, (Co, Ci, KH, KW), dtype), rnd(rng, (N, Ci, H, W), dtype), rnd(rng, (N, Co, H, W), dtype)
+    dK_, dA_, dB_ = dev.sconcrete(K), dev.sconcrete(A), dev.sconcrete(dB)
+    close(dev.to_numpy(dev.conv2dPreserving(dK_, dA_)), oracle.conv2dPreserving(K, A), dtype, scale=100)
+    close(dev.to_numpy(dev.conv2d_dkrn(dA_, dB_, KH, KW)), oracle.conv2d_dkrn(A, dB, KH, KW), dtype, scale=200)
+    close(dev.to_numpy(dev.conv2d_dinp(dK_, dB_)), oracle.conv2d_dinp(K, dB), dtype, scale=100)
+    if N * H * W and dtype == np.float64:
+        close(dev.to_numpy(nn.conv2dPreservingS_vectorised(dev, dK_, dA_)), oracle.conv2dPreserving(K, A), dtype, scale=100)
+
+
+def test_conv_full_size_adjoint_property(dev):
+    """ConvVjpBench at BASELINE's size: size-independent checks (adjointness,
+    linearity) instead of an oracle run."""
+    rng = np.random.Generator(np.random.Philox(42))
+    N, C, H, W, KH, KW = 256, 64, 28, 28, 3, 3
+    K = dev.sconcrete(rng.uniform(-.5, .5, (C, C, KH, KW)))
+    A = dev.sconcrete(rng.uniform(-.5, .5, (N, C, H, W)))
+    Y = dev.sconcrete(rng.uniform(-.5, .5, (N, C, H, W)))
+    B = dev.conv2dPreserving(K, A)
+    lhs = dev.kfromS(dev.sdot0(B, Y))
+    r1 = dev.kfromS(dev.sdot0(A, dev.conv2d_dinp(K, Y)))
+    r2 = dev.kfromS(dev.sdot0(K, dev.conv2d_dkrn(A, Y, KH, KW)))
+    assert abs(lhs - r1) <= 1e-10 * abs(lhs) and abs(lhs - r2) <= 1e-10 * abs(lhs)
+    B2 = dev.conv2dPreserving(K, dev.binary("add", A, A))
+    assert dev.all_eq(B2, dev.binary("add", B, B))      # exact: scaling by 2 commutes with rounding
+
+
+# ---------------------------------------------------------------- NN blocks
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_nn_blocks(dev, oracle, dtype):
+    rng = np.random.default_rng(17)
+    x = rnd(rng, (5, 3, 9, 10), dtype)
+    x[0, 0, :2, :2] = 0.25     # ties inside a window
+    exact(dev.to_numpy(dev.relu(dev.sconcrete(x))), oracle.relu(x))
+    for ks, st in [(2, 2), (3, 2), (2, 3), (3, 3)]:
+        y, am = dev.maxpool2d(dev.sconcrete(x), ks, st)
+        ry, ram = oracle.maxpool2d(x, ks, st)
+        exact(dev.to_numpy(y), ry)
+        exact(dev.to_numpy(am), ram)
+        dy = rnd(rng, ry.shape, dtype)
+        got = dev.to_numpy(dev.maxpool2d_bwd(dev.sconcrete(dy), am, ks, st, 9, 10))
+        ref = oracle.maxpool2d_bwd(dy, ram, ks, st, 9, 10)
+        if ks <= st:
+            exact(got, ref)
+        else:
+            close(got, ref, dtype)
+    lg, ex = rnd(rng, (10, 37), dtype, -2, 2), np.eye(10, dtype=dtype)[:, rng.integers(0, 10, 37)]
+    l, dl = dev.softmax_xent(dev.sconcrete(lg), dev.sconcrete(ex), 1 / 37)
+    rl, rdl = oracle.softmax_xent(lg, ex, 1 / 37)
+    close(dev.to_numpy(l).reshape(()), np.asarray(rl), dtype, scale=100)
+    close(dev.to_numpy(dl), rdl, dtype, scale=100)
+    if dtype == np.float64:
+        close(dev.to_numpy(nn.lossSoftMaxCrossEntropyS_vectorised(dev, dev.sconcrete(ex), dev.sconcrete(lg), 1 / 37)).reshape(()),
+              np.asarray(rl), dtype, scale=100)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_optimizers(dev, oracle, dtype):
+    rng = np.random.default_rng(18)
+    p, g = rnd(rng, (1000,), dtype), rnd(rng, (1000,), dtype)
+    m, v = np.zeros(1000, dtype), np.zeros(1000, dtype)
+    dp, dm, dv = dev.sconcrete(p), dev.sconcrete(m), dev.sconcrete(v)
+    for t in range(1, 4):
+        g = rnd(rng, (1000,), dtype)
+        dev.adam_step(dp, dm, dv, dev.sconcrete(g), t)
+        oracle.adam_step(p, m, v, g, t)
+    close(dev.to_numpy(dp), p, dtype, scale=10)
+    close(dev.to_numpy(dm), m, dtype, scale=10)
+    close(dev.to_numpy(dv), v, dtype, scale=10)
+    dev.sgd_step(dp, dev.sconcrete(g), 0.02)
+    oracle.sgd_step(p, g, 0.02)
+    close(dev.to_numpy(dp), p, dtype, scale=10)
+
+
+def test_prod_fold(dev, oracle):
+    # testListProd golden (TestAdaptorSimplified.hs:1043-1053)
+    val, (g,) = ad.grad(dev, lambda T, t: T.prod_fold(t), [dev.sconcrete(np.array([1.0, 2.0, 3.0, 4.0]))])
+    assert float(dev.kfromS(val)) == 24.0
+    np.testing.assert_allclose(dev.to_numpy(g), [24, 12, 8, 6], atol=1e-10)
+    rng = np.random.default_rng(19)
+    for n in (1, 7, 2048, 2049, 10_000, 123_457):
+        # the reference's LongProdBench distribution 0.55 + U[0,1) overflows past ~9e4;
+        # exp(U[-a,a]) keeps the product finite
+        x = np.exp(rng.uniform(-1e-3, 1e-3, n)) if n > 10_000 else 0.55 + rng.uniform(0, 1, n)
+        pr, gr = dev.prod_fold_grad(dev.sconcrete(x), 1.5)
+        rp, rg = oracle.prod_fold_grad(x, 1.5)
+        tol = 4e-16 * (n + 10)
+        np.testing.assert_allclose(dev.kfromS(pr), rp, rtol=tol)
+        np.testing.assert_allclose(dev.to_numpy(gr), rg, rtol=tol)
+    z = np.array([2.0, 0.0, 3.0, 5.0])     # exact zeros: no division anywhere
+    _, gz = dev.prod_fold_grad(dev.sconcrete(z), 1.0)
+    assert dev.to_numpy(gz).tolist() == [0.0, 30.0, 0.0, 0.0]
+
+
+# ------------------------------------------------------------- whole model
+@pytest.mark.parametrize("fused", [True, False])
+def test_mnist_cnn_gradient_vs_oracle(dev, oracle, fused):
+    """MnistCnnShaped2 loss and all 8 gradient leaves, device vs oracle, both
+    through the same dual-number pipeline (cgrad)."""
+    rng = np.random.Generator(np.random.Philox(42))
+    batch, kh, kw, c_out, n_hidden = 6, 2, 2, 4, 8
+    params = mnist_cnn.init_params(kh, kw, c_out, n_hidden)
+    glyphs = rng.uniform(0, 1, (batch, 28, 28))
+    labels = np.eye(10)[rng.integers(0, 10, batch)]
+
+    def run(B):
+        ins = [B.sconcrete(p) for p in params]
+        g, l = B.sconcrete(glyphs), B.sconcrete(labels)
+        val, grads = ad.grad(B, lambda T, *ps: mnist_cnn.convMnistLossFusedS(T, g, l, list(ps), fused=fused), ins)
+        return float(B.kfromS(val)), [B.to_numpy(x) for x in grads]
+    dl, dg = run(dev)
+    ol, og = run(oracle)
+    np.testing.assert_allclose(dl, ol, rtol=1e-12)
+    for a, b in zip(dg, og):
+        np.testing.assert_allclose(a, b, rtol=1e-10, atol=1e-13)
+
+
+def test_graph_capture_replay(dev):
+    rng = np.random.default_rng(20)
+    x = dev.sconcrete(rng.uniform(-.5, .5, (64, 32)))
+    w = dev.sconcrete(rng.uniform(-.5, .5, (32, 16)))
+    import ctypes as C
+    def step():
+        return dev.ssum0(dev.unary("tanh", dev.smatmul2(x, w)))
+    eager = dev.kfromS(step())
+    ffi.call("hb_graph_begin")
+    out = step()
+    g = C.c_void_p()
+    ffi.call("hb_graph_end", C.byref(g))
+    for _ in range(3):
+        ffi.call("hb_graph_launch", g)
+    assert dev.kfromS(out) == eager
+    ffi.call("hb_graph_free", g)
