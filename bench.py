@@ -1,0 +1,458 @@
+#!/usr/bin/env python
+"""bench.py -- the headline measurement (BASELINE.json: "MNIST CNN train
+samples/s at 1/2/4/8 B200; conv VJP achieved HBM GB/s").
+
+  python bench.py [--gpus N --steps K --warmup W] [--impl reference]
+
+A "step" is one pass of the hot path over one batch of synthetic MNIST-shaped
+input: the MnistCnnShaped2 gradient program (example/MnistCnnShaped2.hs:111-136)
+interpreted over the device carrier + one all-reduce of the gradient bucket +
+the Adam step (OptimizerTools.hs:134-232).  Per-GPU batch 4096 (BASELINE
+config 4); with N GPUs every rank owns 4096 samples (weak scaling; `--scaling
+strong` shards ONE batch of 4096 instead).  One JSON line on stdout (rank 0).
+
+`value`  : samples/s with the minibatch already resident in HBM.
+`e2e`    : the same through the public call `CnnTrainer.train_step(host ptrs)`:
+           H2D of glyphs+labels from pinned host memory and the loss D2H are
+           inside the timed region, every step.
+`roofline`: the dominant kernel of the step, timed live with CUDA events on the
+           library stream (hb_prof_*), against MEASURED_PEAKS.json.
+`conv_vjp`: ConvVjpBench at BASELINE config 3 (batch 256, 64 ch, 3x3, 28x28,
+           Double): fwd / dKrn / dInp achieved HBM GB/s and FP64 TFLOP/s.
+`cpu_baseline`: the oracle (CPU restatement of the reference's Concrete
+           backend) on a bounded sample of the same workload, on this box's
+           host cores.
+
+--impl reference: only the CPU oracle leg (the reference itself is Haskell and
+cannot be built here: no GHC), same metric/config.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import re
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+L2_BYTES = 126e6
+PER_GPU_BATCH = 4096
+HYPER = dict(kh=4, kw=4, c_out=16, n_hidden=64)     # 5x5 kernels: TestMnistCNNS.hs:422-424
+METRIC = "mnist_cnn_train_samples_per_s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)", d
+    return 6650.0, "fallback (B200_PROFILING.md)", {}
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.rows = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------ algorithmic work
+def _shapes(tag: str):
+    m = re.match(r"(\w+)\{(\w+)\[([\d,]*)\](?:;\[([\d,]*)\])?\}", tag)
+    if not m:
+        return tag, None, None, None
+    f = lambda s: [int(x) for x in s.split(",") if x] if s is not None else None
+    return m.group(1), m.group(2), f(m.group(3)), f(m.group(4))
+
+
+def alg_work(tag: str, kh1: int, kw1: int):
+    """(algorithmic bytes, flops) of one call of the C-ABI entry `tag`
+    (per-unit figures x units per launch)."""
+    name, dt, a, b = _shapes(tag)
+    if a is None:
+        return None
+    s = {"f64": 8, "f32": 4, "i64": 8, "i32": 4, "i16": 2, "i8": 1, "bool": 1}[dt]
+    n = lambda sh: int(np.prod(sh)) if sh is not None else 0
+    if name == "conv2d_preserving":          # K ; A  -> B
+        Co, Ci, KH, KW = a; N, _, H, W = b
+        return (n(a) + n(b) + N * Co * H * W) * s, 2 * N * Co * H * W * Ci * KH * KW
+    if name == "conv2d_preserving_dkrn":     # A ; dB -> dK
+        N, Ci, H, W = a; Co = b[1]
+        return (n(a) + n(b) + Co * Ci * kh1 * kw1) * s, 2 * N * Co * H * W * Ci * kh1 * kw1
+    if name == "conv2d_preserving_dinp":     # K ; dB -> dA
+        Co, Ci, KH, KW = a; N, _, H, W = b
+        return (n(a) + n(b) + N * Ci * H * W) * s, 2 * N * Co * H * W * Ci * KH * KW
+    if name == "matmul2":
+        return (n(a) + n(b) + a[0] * b[1]) * s, 2 * a[0] * a[1] * b[1]
+    if name in ("binary", "add_inplace_or_new"):
+        return 3 * n(a) * s, n(a)
+    if name in ("unary", "relu", "cast", "contiguous"):
+        return 2 * n(a) * s, n(a)
+    if name == "maxpool2d":                  # x -> y (1/4) + argmax i64 (1/4)
+        return n(a) * s + n(a) // 4 * (s + 8), n(a)
+    if name == "maxpool2d_bwd":              # dy + argmax -> dx (4x)
+        return n(a) * (s + 8) + 4 * n(a) * s, n(a)
+    if name in ("sum_leading", "sum_all"):
+        return n(a) * s, n(a)
+    if name == "adam_step":                  # p, m, v read+write, g read
+        return 7 * n(a) * s, 12 * n(a)
+    return None
+
+
+# ---------------------------------------------------------------- reference arm
+def run_reference(args, rank, world):
+    """The reference's own CPU path: the oracle restatement of the Concrete
+    backend (numpy; the Haskell reference cannot be built here), same program
+    (dual-number gradient of convMnistLossFusedS + Adam), bounded sample."""
+    if rank != 0:
+        return
+    from horde_ad_b200 import ad, mnist_cnn
+    from oracle.concrete import ConcreteBackend
+    orc = ConcreteBackend()
+    sample = args.cpu_sample
+    rng = np.random.Generator(np.random.Philox(42))
+    gl = rng.uniform(0, 1, (sample, 28, 28))
+    lb = np.eye(10)[rng.integers(0, 10, sample)]
+    hy = (HYPER["kh"], HYPER["kw"], HYPER["c_out"], HYPER["n_hidden"])
+    ps = mnist_cnn.init_params(*hy)
+    ms = [np.zeros_like(p) for p in ps]
+    vs = [np.zeros_like(p) for p in ps]
+
+    def step(t):
+        val, grads = ad.grad(orc, lambda T, *p: mnist_cnn.convMnistLossFusedS(T, gl, lb, list(p), fused=True), ps)
+        for p, m, v, g in zip(ps, ms, vs, grads):
+            orc.adam_step(p, m, v, np.asarray(g), t)
+        return float(val)
+
+    steps, warm = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
+    for i in range(warm):
+        step(i + 1)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        step(warm + i + 1)
+    dt = (time.perf_counter() - t0) / steps
+    val = sample / dt
+    out = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": args.scaling,
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_dict(args, world),
+        "cpu_baseline": {"value": val, "unit": "samples/s", "cores": 1, "kind": "port",
+                         "sample": f"{steps} steps of batch {sample} (of {PER_GPU_BATCH}); numpy oracle, single thread"},
+        "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "host": {"nproc": os.cpu_count()},
+    }
+    print(json.dumps(out), flush=True)
+
+
+def config_dict(args, world):
+    local = PER_GPU_BATCH if args.scaling == "weak" else PER_GPU_BATCH // world
+    return {"workload": "MnistCnnShaped2 training step (convMnistLossFusedS gradient + Adam), synthetic MNIST 28x28",
+            "per_gpu_batch": local, "global_batch": local * world,
+            "hyper": "kh=kw=4 (5x5 kernels), c_out=16, n_hidden=64",
+            "parallelism": f"dp{world}", "optimizer": "adam",
+            "l2": "per-step working set (activations ~1.6 GB at batch 4096) >> 126 MB L2; no explicit flush"}
+
+
+# -------------------------------------------------------------------- our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--cpu-sample", type=int, default=512, help="batch of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-conv-vjp", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            # convenience: relaunch under torchrun
+            port = os.environ.get("MASTER_PORT", "29517")
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                   "--master-addr", "127.0.0.1", "--master-port", port, __file__] + sys.argv[1:]
+            sys.exit(subprocess.call(cmd))
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group(backend="gloo", rank=rank, world_size=world)   # control plane only
+
+    from horde_ad_b200 import ffi
+    from horde_ad_b200.device import DeviceBackend
+    from horde_ad_b200.train import CnnTrainer, PinnedBuffer, comm_init
+
+    dev = DeviceBackend(local_rank)      # raises without a GPU / without the built library
+
+    def bcast(b):
+        objs = [b]
+        dist.broadcast_object_list(objs, src=0)
+        return objs[0]
+    comm_init(rank, world, bcast if world > 1 else None)
+
+    def barrier():
+        dev.sync()
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    local_batch = PER_GPU_BATCH if args.scaling == "weak" else PER_GPU_BATCH // world
+    global_batch = local_batch * world
+    tr = CnnTrainer(dev, local_batch, **HYPER, world=world, use_graph=not args.no_graph)
+    rng = np.random.Generator(np.random.Philox(42, key=rank))
+    gl = PinnedBuffer((local_batch, 28, 28), np.float64)
+    lb = PinnedBuffer((local_batch, 10), np.float64)
+    gl.array[...] = rng.uniform(0, 1, gl.array.shape)
+    lb.array[...] = np.eye(10)[rng.integers(0, 10, local_batch)]
+    h2d = gl.nbytes + lb.nbytes
+
+    K, W = args.steps, max(3, args.warmup)
+    n0 = C.c_uint64()
+
+    # ---- device-resident: inputs uploaded once, K steps timed with CUDA events
+    tr.upload(gl.ptr, lb.ptr)
+    for _ in range(W):
+        tr.step_enqueue()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    ffi.call("hb_launch_count", C.byref(n0))
+    ffi.call("hb_event_record", 0)
+    for _ in range(K):
+        bucket = tr.step_enqueue()
+    ffi.call("hb_event_record", 1)
+    ms = C.c_float()
+    ffi.call("hb_event_elapsed_ms", 0, 1, C.byref(ms))
+    n1 = C.c_uint64()
+    ffi.call("hb_launch_count", C.byref(n1))
+    barrier()
+    loss_resident = tr.loss_of(bucket)
+    dev_ms = max_over_ranks(float(ms.value))
+    value = global_batch * K / (dev_ms * 1e-3)
+
+    # ---- end to end through the public call: H2D + step + loss D2H per step
+    for _ in range(2):
+        tr.train_step(gl.ptr, lb.ptr)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        loss = tr.train_step(gl.ptr, lb.ptr)
+    dev.sync()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    clk = clocks.stop()
+    e2e_value = global_batch * K / e2e_s
+
+    if rank != 0:
+        tr.close()
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- live per-kernel timing of the same step (eager, events per launch)
+    hbm_peak, peak_src, _ = peaks()
+    prof = profile_step(dev, ffi, CnnTrainer, local_batch, gl, lb, world)
+    fp64_dmma, fp64_fma = C.c_double(), C.c_double()
+    ffi.call("hb_microbench", 1, C.byref(fp64_dmma))
+    ffi.call("hb_microbench", 0, C.byref(fp64_fma))
+    fp64_peak = max(fp64_dmma.value, fp64_fma.value)
+    roof, breakdown = roofline_of(prof, hbm_peak, peak_src, fp64_peak)
+
+    out = {
+        "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": config_dict(args, world),
+        "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d * world,
+                "d2h_bytes_per_step": 8 * world, "ms_per_step": e2e_s / K * 1e3},
+        "gpu_launches": int(n1.value - n0.value),
+        "clocks": clk, "loss": loss, "loss_resident": loss_resident,
+        "roofline": roof, "breakdown": breakdown,
+        "fp64_peak_tflops": {"dmma": fp64_dmma.value, "dfma": fp64_fma.value, "how": "hb_microbench, this run"},
+    }
+    if not args.no_conv_vjp:
+        out["conv_vjp"] = conv_vjp_bench(dev, ffi, hbm_peak, fp64_peak)
+    if not args.no_cpu_baseline and world == 1:
+        out["cpu_baseline"] = cpu_baseline(args.cpu_sample)
+    print(json.dumps(out), flush=True)
+    tr.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def profile_step(dev, ffi, CnnTrainer, local_batch, gl, lb, world, steps=3):
+    """Per-launch CUDA-event timing of the eager (non-graph) step."""
+    tr = CnnTrainer(dev, local_batch, **HYPER, world=1, use_graph=False)
+    tr.upload(gl.ptr, lb.ptr)
+    for _ in range(2):
+        tr.step_enqueue()
+    dev.sync()
+    ffi.call("hb_prof_begin")
+    for _ in range(steps):
+        tr.step_enqueue()
+    ffi.call("hb_prof_end")
+    buf = C.create_string_buffer(1 << 16)
+    ffi.call("hb_prof_report", buf, len(buf))
+    rows = []
+    for line in buf.value.decode().splitlines():
+        tag, site, cnt, tot = line.rsplit(" ", 3)
+        rows.append({"entry": tag, "site": site, "launches_per_step": int(cnt) / steps, "ms_per_step": float(tot) / steps})
+    return rows
+
+
+def roofline_of(rows, hbm_peak, peak_src, fp64_peak):
+    kh1 = kw1 = HYPER["kh"] + 1
+    total = sum(r["ms_per_step"] for r in rows)
+    for r in rows:
+        r["share"] = r["ms_per_step"] / total if total else 0.0
+    # group by entry (an entry may launch a pad/copy kernel besides its main kernel)
+    top = rows[0]
+    w = alg_work(top["entry"], kh1, kw1)
+    per_launch_ms = top["ms_per_step"] / max(1.0, top["launches_per_step"])
+    roof = {"kernel": f'{top["entry"]} @ {top["site"]}', "share_of_step": top["share"],
+            "launch_ms": per_launch_ms}
+    if w is not None:
+        by, fl = w
+        gbs = by / (per_launch_ms * 1e-3) / 1e9
+        tfs = fl / (per_launch_ms * 1e-3) / 1e12
+        ai = fl / by
+        ridge = fp64_peak * 1e12 / (hbm_peak * 1e9)
+        if ai > ridge:
+            roof.update({"bound": "tensor", "achieved": tfs, "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": tfs / fp64_peak, "peak_source": "hb_microbench FP64 (DMMA/DFMA) this run; "
+                         "MEASURED_PEAKS.json has no FP64 figure", "algorithmic_flops": fl,
+                         "hbm_view": {"achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                                      "algorithmic_bytes": by, "peak_source": peak_src}})
+        else:
+            roof.update({"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                         "peak_source": peak_src, "algorithmic_bytes": by})
+        roof["traffic"] = None
+    breakdown = [{"entry": r["entry"], "site": r["site"], "ms": round(r["ms_per_step"], 4),
+                  "share": round(r["share"], 4), "n": r["launches_per_step"]} for r in rows[:12]]
+    return roof, breakdown
+
+
+def conv_vjp_bench(dev, ffi, hbm_peak, fp64_peak, reps=10):
+    """ConvVjpBench at BASELINE config 3: K[64,64,3,3], A,dB[256,64,28,28] Double."""
+    rng = np.random.Generator(np.random.Philox(42))
+    K = dev.sconcrete(rng.uniform(-.5, .5, (64, 64, 3, 3)))
+    A = dev.sconcrete(rng.uniform(-.5, .5, (256, 64, 28, 28)))
+    dB = dev.sconcrete(rng.uniform(-.5, .5, (256, 64, 28, 28)))
+    by = (2 * 256 * 64 * 28 * 28 + 64 * 64 * 9) * 8
+    fl = 2 * 256 * 64 * 28 * 28 * 64 * 9
+    out = {"config": "K[64,64,3,3], A,dB[256,64,28,28] f64", "algorithmic_bytes_per_pass": by,
+           "algorithmic_flops_per_pass": fl}
+    ms = C.c_float()
+    for name, f in (("fwd", lambda: dev.conv2dPreserving(K, A)), ("dkrn", lambda: dev.conv2d_dkrn(A, dB, 3, 3)),
+                    ("dinp", lambda: dev.conv2d_dinp(K, dB))):
+        for _ in range(3):
+            f()
+        dev.sync()
+        ffi.call("hb_event_record", 2)
+        for _ in range(reps):
+            f()
+        ffi.call("hb_event_record", 3)
+        ffi.call("hb_event_elapsed_ms", 2, 3, C.byref(ms))
+        t = ms.value / reps * 1e-3
+        out[name] = {"ms": t * 1e3, "hbm_gbs": by / t / 1e9, "hbm_frac": by / t / 1e9 / hbm_peak,
+                     "tflops": fl / t / 1e12, "fp64_frac": fl / t / 1e12 / fp64_peak}
+    return out
+
+
+def cpu_baseline(sample: int):
+    """The oracle on the box's host cores, bounded sample (same program)."""
+    from horde_ad_b200 import ad, mnist_cnn
+    from oracle.concrete import ConcreteBackend
+    orc = ConcreteBackend()
+    rng = np.random.Generator(np.random.Philox(42))
+    gl = rng.uniform(0, 1, (sample, 28, 28))
+    lb = np.eye(10)[rng.integers(0, 10, sample)]
+    ps = mnist_cnn.init_params(HYPER["kh"], HYPER["kw"], HYPER["c_out"], HYPER["n_hidden"])
+    ms = [np.zeros_like(p) for p in ps]
+    vs = [np.zeros_like(p) for p in ps]
+    reps = 2
+    t0 = time.perf_counter()
+    for t in range(reps):
+        _, grads = ad.grad(orc, lambda T, *p: mnist_cnn.convMnistLossFusedS(T, gl, lb, list(p), fused=True), ps)
+        for p, m, v, g in zip(ps, ms, vs, grads):
+            orc.adam_step(p, m, v, np.asarray(g), t + 1)
+    dt = (time.perf_counter() - t0) / reps
+    return {"value": sample / dt, "unit": "samples/s", "cores": 1, "kind": "port",
+            "sample": f"{reps} steps of batch {sample} (of {PER_GPU_BATCH}); numpy oracle, single thread",
+            "host_nproc": os.cpu_count()}
+
+
+if __name__ == "__main__":
+    main()

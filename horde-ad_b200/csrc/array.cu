@@ -6,6 +6,7 @@
 // :638-652 (slice/reverse/transpose/reshape), :1451-1490 (tindexZS).
 #include <stdarg.h>
 
+#include <algorithm>
 #include <map>
 
 #include "common.cuh"
@@ -246,6 +247,91 @@ extern "C" int hb_event_elapsed_ms(int a, int b, float *ms) {
   HB_REQUIRE(a >= 0 && a < 64 && b >= 0 && b < 64, "event slot out of range");
   HB_CUDA(cudaEventSynchronize(g_hb.events[b]));
   HB_CUDA(cudaEventElapsedTime(ms, g_hb.events[a], g_hb.events[b]));
+  return HB_OK;
+}
+
+// ----------------------------------------------------- per-launch profiler
+// While enabled every HB_LAUNCHED() records an event on the library stream;
+// the device time between consecutive events is attributed to the launch site
+// (host function:line).  The stream is serial, so as long as the host runs
+// ahead of the GPU the difference is the kernel's own duration.  bench.py uses
+// it for the live per-kernel roofline; never enabled on the product path.
+struct hb_prof_rec {
+  cudaEvent_t ev;
+  std::string key;
+};
+static std::string g_prof_tag;
+
+hb_prof_scope::hb_prof_scope(const char *name, const hb_array *a, const hb_array *b) {
+  if (!g_hb.profiling || !g_prof_tag.empty()) return;
+  owner = true;
+  g_prof_tag = name;
+  if (a) g_prof_tag += std::string("{") + hb_dtype_name(a->dt) + hb_shape_str(a) + (b ? ";" + hb_shape_str(b) : "") + "}";
+}
+hb_prof_scope::~hb_prof_scope() {
+  if (owner) g_prof_tag.clear();
+}
+static std::vector<hb_prof_rec> g_prof;
+static std::vector<cudaEvent_t> g_prof_free;
+
+static cudaEvent_t prof_event() {
+  cudaEvent_t e;
+  if (!g_prof_free.empty()) {
+    e = g_prof_free.back();
+    g_prof_free.pop_back();
+  } else {
+    cudaEventCreate(&e);
+  }
+  return e;
+}
+
+void hb_prof_mark(const char *func, int line) {
+  if (g_hb.capturing) return;
+  cudaEvent_t e = prof_event();
+  cudaEventRecord(e, g_hb.stream);
+  g_prof.push_back({e, (g_prof_tag.empty() ? std::string("-") : g_prof_tag) + " " + func + ":" + std::to_string(line)});
+}
+
+extern "C" int hb_prof_begin(void) {
+  HB_CHECK_INIT();
+  for (auto &r : g_prof) g_prof_free.push_back(r.ev);
+  g_prof.clear();
+  g_hb.profiling = true;
+  hb_prof_mark("<begin>", 0);
+  return HB_OK;
+}
+
+extern "C" int hb_prof_end(void) {
+  HB_CHECK_INIT();
+  g_hb.profiling = false;
+  HB_CUDA(cudaStreamSynchronize(g_hb.stream));
+  return HB_OK;
+}
+
+// One line per (entry point{shapes}, launch site), sorted by total time:
+// "entry{dtype[shape];[shape]} func:line count total_ms".
+extern "C" int hb_prof_report(char *buf, size_t len) {
+  HB_CHECK_INIT();
+  HB_REQUIRE(buf && len > 0, "null buffer");
+  std::map<std::string, std::pair<int64_t, double>> agg;
+  for (size_t i = 1; i < g_prof.size(); i++) {
+    float ms = 0.f;
+    HB_CUDA(cudaEventElapsedTime(&ms, g_prof[i - 1].ev, g_prof[i].ev));
+    auto &a = agg[g_prof[i].key];
+    a.first++;
+    a.second += ms;
+  }
+  std::vector<std::pair<double, std::string>> rows;
+  for (auto &kv : agg) {
+    char line[256];
+    snprintf(line, sizeof line, "%s %lld %.6f\n", kv.first.c_str(), (long long)kv.second.first, kv.second.second);
+    rows.push_back({-kv.second.second, line});
+  }
+  std::sort(rows.begin(), rows.end());
+  std::string out;
+  for (auto &r : rows) out += r.second;
+  strncpy(buf, out.c_str(), len - 1);
+  buf[len - 1] = 0;
   return HB_OK;
 }
 

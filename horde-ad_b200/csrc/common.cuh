@@ -48,6 +48,7 @@ struct hb_global {
   void *scratch = nullptr;
   size_t scratch_bytes = 0;
   bool capturing = false;
+  bool profiling = false;  // hb_prof_begin .. hb_prof_end: one event per launch
   cudaEvent_t events[64] = {};
 };
 extern hb_global g_hb;
@@ -77,10 +78,20 @@ void hb_set_error(const char *fmt, ...);
   } while (0)
 #define HB_CHECK_INIT() HB_REQUIRE(g_hb.inited, "hb_init has not been called")
 
+// per-launch profiler (array.cu): an event after every launch while enabled
+void hb_prof_mark(const char *func, int line);
+// Names the C-ABI entry point (with operand shapes) the launches belong to;
+// the outermost scope wins.  Free when profiling is off.
+struct hb_prof_scope {
+  bool owner = false;
+  hb_prof_scope(const char *name, const struct hb_array *a = nullptr, const struct hb_array *b = nullptr);
+  ~hb_prof_scope();
+};
 // count + check a kernel launch
 #define HB_LAUNCHED()                                                  \
   do {                                                                 \
     g_hb.launches.fetch_add(1, std::memory_order_relaxed);             \
+    if (g_hb.profiling) hb_prof_mark(__func__, __LINE__);              \
     cudaError_t e_ = cudaPeekAtLastError();                            \
     if (e_ != cudaSuccess) {                                           \
       cudaGetLastError();                                              \

@@ -314,16 +314,19 @@ static int contract_impl(const hb_array *a, const hb_array *b, int n_lead, hb_ar
 }
 
 extern "C" int hb_dot_inner(const hb_array *a, const hb_array *b, hb_array **out) {
+  hb_prof_scope prof_("dot_inner", a, b);
   return contract_impl(a, b, 0, out);
 }
 
 extern "C" int hb_dot_inner_sum_leading(const hb_array *a, const hb_array *b, int n_axes, hb_array **out) {
+  hb_prof_scope prof_("dot_inner_sum_leading", a, b);
   return contract_impl(a, b, n_axes, out);
 }
 
 // tsmatmul2 m1 m2 = sdot1In (tr [1,0] (replicate m1)) (tr [0,2,1] (replicate m2))
 // (OpsConcrete.hs:237-242): built here directly as the two broadcast views.
 extern "C" int hb_matmul2(const hb_array *a, const hb_array *b, hb_array **out) {
+  hb_prof_scope prof_("matmul2", a, b);
   HB_REQUIRE(a && b && out, "null argument");
   HB_REQUIRE(a->rank == 2 && b->rank == 2 && a->shape[1] == b->shape[0], "smatmul2: %s x %s",
              hb_shape_str(a).c_str(), hb_shape_str(b).c_str());
@@ -344,6 +347,7 @@ extern "C" int hb_matmul2(const hb_array *a, const hb_array *b, hb_array **out) 
 
 // tsmatvecmul m v = sdot1In m (sreplicate v)  (OpsConcrete.hs:236)
 extern "C" int hb_matvecmul(const hb_array *m, const hb_array *v, hb_array **out) {
+  hb_prof_scope prof_("matvecmul", m, v);
   HB_REQUIRE(m && v && out, "null argument");
   HB_REQUIRE(m->rank == 2 && v->rank == 1 && m->shape[1] == v->shape[0], "smatvecmul: %s x %s",
              hb_shape_str(m).c_str(), hb_shape_str(v).c_str());

@@ -56,6 +56,7 @@ static hb_array *view6(const hb_array *base, int64_t off, const int64_t *shape, 
 }
 
 extern "C" int hb_conv2d_preserving(const hb_array *K, const hb_array *A, hb_array **out) {
+  hb_prof_scope prof_("conv2d_preserving", K, A);
   HB_CHECK_INIT();
   HB_REQUIRE(K && A && out, "null argument");
   HB_REQUIRE(K->rank == 4 && A->rank == 4 && K->dt == A->dt && hb_is_float(A->dt),
@@ -87,6 +88,7 @@ extern "C" int hb_conv2d_preserving(const hb_array *K, const hb_array *A, hb_arr
 
 extern "C" int hb_conv2d_preserving_dkrn(const hb_array *A, const hb_array *dB, int KH, int KW,
                                          hb_array **out) {
+  hb_prof_scope prof_("conv2d_preserving_dkrn", A, dB);
   HB_CHECK_INIT();
   HB_REQUIRE(A && dB && out, "null argument");
   HB_REQUIRE(A->rank == 4 && dB->rank == 4 && A->dt == dB->dt && hb_is_float(A->dt),
@@ -128,6 +130,7 @@ extern "C" int hb_conv2d_preserving_dkrn(const hb_array *A, const hb_array *dB, 
 }
 
 extern "C" int hb_conv2d_preserving_dinp(const hb_array *K, const hb_array *dB, hb_array **out) {
+  hb_prof_scope prof_("conv2d_preserving_dinp", K, dB);
   HB_CHECK_INIT();
   HB_REQUIRE(K && dB && out, "null argument");
   HB_REQUIRE(K->rank == 4 && dB->rank == 4 && K->dt == dB->dt && hb_is_float(K->dt),

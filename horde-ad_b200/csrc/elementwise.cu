@@ -67,6 +67,7 @@ static int copy_into(hb_array *dst, const hb_array *src) {
 int hb_copy_into(hb_array *dst, const hb_array *src) { return copy_into(dst, src); }
 
 extern "C" int hb_contiguous(const hb_array *a, hb_array **out) {
+  hb_prof_scope prof_("contiguous", a);
   HB_CHECK_INIT();
   HB_REQUIRE(a && out, "null argument");
   hb_array *o;
@@ -81,6 +82,7 @@ extern "C" int hb_contiguous(const hb_array *a, hb_array **out) {
 }
 
 extern "C" int hb_append(const hb_array *a, const hb_array *b, hb_array **out) {
+  hb_prof_scope prof_("append", a, b);
   HB_CHECK_INIT();
   HB_REQUIRE(a && b && out, "null argument");
   HB_REQUIRE(a->rank >= 1 && a->rank == b->rank && a->dt == b->dt, "append: rank/dtype mismatch");
@@ -108,6 +110,7 @@ extern "C" int hb_append(const hb_array *a, const hb_array *b, hb_array **out) {
 }
 
 extern "C" int hb_stack(int k, hb_array *const *arrs, hb_array **out) {
+  hb_prof_scope prof_("stack");
   HB_CHECK_INIT();
   HB_REQUIRE(out, "null argument");
   HB_REQUIRE(k > 0 && arrs, "sfromVector: empty vector");  // OpsConcrete.hs:129
@@ -139,6 +142,7 @@ extern "C" int hb_stack(int k, hb_array *const *arrs, hb_array **out) {
 // Flatten k arrays (row-major) and concatenate them into one vector: the
 // contiguous gradient bucket of the data-parallel loop.
 extern "C" int hb_flatten_concat(int k, hb_array *const *arrs, hb_array **out) {
+  hb_prof_scope prof_("flatten_concat");
   HB_CHECK_INIT();
   HB_REQUIRE(out && k > 0 && arrs, "flatten_concat: empty list");
   int64_t total = 0;
@@ -222,6 +226,7 @@ static int unary_dispatch(hb_unop op, hb_array *o, const hb_array *a) {
 }
 
 extern "C" int hb_unary(hb_unop op, const hb_array *a, hb_array **out) {
+  hb_prof_scope prof_("unary", a);
   HB_CHECK_INIT();
   HB_REQUIRE(a && out, "null argument");
   hb_array *o;
@@ -284,6 +289,7 @@ static int binary_into(hb_binop op, hb_array *o, const hb_array *a, const hb_arr
 }
 
 extern "C" int hb_binary(hb_binop op, const hb_array *a, const hb_array *b, hb_array **out) {
+  hb_prof_scope prof_("binary", a, b);
   HB_CHECK_INIT();
   HB_REQUIRE(a && b && out, "null argument");
   HB_REQUIRE(a->dt == b->dt, "binary op: dtype %s vs %s", hb_dtype_name(a->dt), hb_dtype_name(b->dt));
@@ -301,6 +307,7 @@ extern "C" int hb_binary(hb_binop op, const hb_array *a, const hb_array *b, hb_a
 }
 
 extern "C" int hb_add_inplace_or_new(hb_array *acc, const hb_array *c, hb_array **out) {
+  hb_prof_scope prof_("add_inplace_or_new", acc, c);
   HB_CHECK_INIT();
   HB_REQUIRE(acc && c && out, "null argument");
   HB_REQUIRE(acc->dt == c->dt && hb_same_shape(acc, c), "taddTarget: %s %s vs %s %s",
@@ -341,6 +348,7 @@ static int cast_from(hb_array *o, const hb_array *a) {
 }
 
 extern "C" int hb_cast(const hb_array *a, hb_dtype dt, hb_array **out) {
+  hb_prof_scope prof_("cast", a);
   HB_CHECK_INIT();
   HB_REQUIRE(a && out, "null argument");
   hb_array *o;
@@ -475,6 +483,7 @@ extern "C" int hb_compare_all(int op, const hb_array *a, const hb_array *b, int 
 // reluS (CommonShapedOps.hs:38-44): oneIfGtZero * v with
 // oneIfGtZero = ifH (x <=. 0) 0 1.
 extern "C" int hb_relu(const hb_array *x, hb_array **out) {
+  hb_prof_scope prof_("relu", x);
   HB_CHECK_INIT();
   HB_REQUIRE(x && out, "null argument");
   hb_array *o;
@@ -499,6 +508,7 @@ __global__ void hb_sgd_kernel(T *p, const T *g, T gamma, int64_t n) {
 }
 
 extern "C" int hb_sgd_step(hb_array *p, const hb_array *g, double gamma) {
+  hb_prof_scope prof_("sgd_step", p);
   HB_CHECK_INIT();
   HB_REQUIRE(p && g, "null argument");
   HB_REQUIRE(p->dt == g->dt && hb_same_shape(p, g), "sgd: parameter/gradient mismatch");
@@ -545,6 +555,7 @@ __global__ void hb_adam_kernel(T *p, T *m, T *v, const T *g, T alphat, T b1, T b
 
 extern "C" int hb_adam_step(hb_array *p, hb_array *m, hb_array *v, const hb_array *g, double alpha,
                             double beta1, double beta2, double epsilon, int64_t t) {
+  hb_prof_scope prof_("adam_step", p);
   HB_CHECK_INIT();
   HB_REQUIRE(p && m && v && g, "null argument");
   HB_REQUIRE(p->dt == g->dt && p->dt == m->dt && p->dt == v->dt, "adam: dtype mismatch");

@@ -250,6 +250,7 @@ static void fill_shm(hb_shm *S, int shm_rank, const int64_t *shm, int shp_rank, 
 
 extern "C" int hb_gather(const hb_array *src, int shm_rank, const int64_t *shm, int shp_rank,
                          const hb_ixprog *prog, hb_array **out) {
+  hb_prof_scope prof_("gather", src);
   HB_CHECK_INIT();
   HB_REQUIRE(src && prog && out, "null argument");
   HB_REQUIRE(shm_rank >= 0 && shm_rank <= HB_R && (shm_rank == 0 || shm), "gather: bad shm");
@@ -550,6 +551,7 @@ __global__ void __launch_bounds__(256)
 
 extern "C" int hb_scatter_add(const hb_array *src, int shm_rank, int shp_rank, const int64_t *shp,
                               const hb_ixprog *prog, hb_array **out) {
+  hb_prof_scope prof_("scatter_add", src);
   HB_CHECK_INIT();
   HB_REQUIRE(src && prog && out, "null argument");
   HB_REQUIRE(shm_rank >= 0 && shm_rank <= src->rank, "scatter: |shm| = %d exceeds source rank %d", shm_rank,
@@ -635,6 +637,7 @@ extern "C" int hb_scatter_add(const hb_array *src, int shm_rank, int shp_rank, c
 
 extern "C" int hb_onehot(const hb_array *v, int shp_rank, const int64_t *shp, const int64_t *ix,
                          hb_array **out) {
+  hb_prof_scope prof_("onehot", v);
   HB_CHECK_INIT();
   HB_REQUIRE(v && out, "null argument");
   HB_REQUIRE(shp_rank >= 0 && shp_rank + v->rank <= HB_R, "oneHot: rank too large");
@@ -715,6 +718,7 @@ __global__ void __launch_bounds__(128)
 
 extern "C" int hb_fused_map(const hb_ixprog *prog, int n_in, hb_array *const *ins, hb_dtype dt,
                             hb_array **out) {
+  hb_prof_scope prof_("fused_map");
   HB_CHECK_INIT();
   HB_REQUIRE(prog && out && ins, "null argument");
   HB_REQUIRE(n_in >= 1 && n_in <= HB_MAP_MAXIN, "fused map: %d inputs (max %d)", n_in, HB_MAP_MAXIN);

@@ -40,6 +40,7 @@ __global__ void __launch_bounds__(256)
 }
 
 extern "C" int hb_maxpool2d(const hb_array *x, int ksize, int stride, hb_array **out, hb_array **argmax_out) {
+  hb_prof_scope prof_("maxpool2d", x);
   HB_CHECK_INIT();
   HB_REQUIRE(x && out, "null argument");
   HB_REQUIRE(x->rank == 4 && hb_is_float(x->dt), "maxPool2d: rank-4 floating input required");
@@ -99,6 +100,7 @@ __global__ void __launch_bounds__(256)
 
 extern "C" int hb_maxpool2d_bwd(const hb_array *dy, const hb_array *argmax, int ksize, int stride, int64_t H,
                                 int64_t W, hb_array **out) {
+  hb_prof_scope prof_("maxpool2d_bwd", dy);
   HB_CHECK_INIT();
   HB_REQUIRE(dy && argmax && out, "null argument");
   HB_REQUIRE(dy->rank == 4 && hb_is_float(dy->dt) && argmax->dt == HB_I64 && hb_same_shape(dy, argmax),
@@ -189,6 +191,7 @@ __global__ void __launch_bounds__(1024)
 
 extern "C" int hb_softmax_xent(const hb_array *logits, const hb_array *expected, double scale,
                                hb_array **loss_out, hb_array **dlogits_out) {
+  hb_prof_scope prof_("softmax_xent", logits);
   HB_CHECK_INIT();
   HB_REQUIRE(logits && expected && loss_out, "null argument");
   HB_REQUIRE(hb_is_float(logits->dt) && logits->dt == expected->dt && hb_same_shape(logits, expected),

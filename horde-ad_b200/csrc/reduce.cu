@@ -269,6 +269,7 @@ int hb_reduce_generic(const hb_array *a, const hb_array *b, int nk, const int *k
 }
 
 extern "C" int hb_sum_leading(const hb_array *a, int n_axes, hb_array **out) {
+  hb_prof_scope prof_("sum_leading", a);
   HB_CHECK_INIT();
   HB_REQUIRE(a && out, "null argument");
   HB_REQUIRE(n_axes >= 0 && n_axes <= a->rank, "ssumN: %d axes of rank %d", n_axes, a->rank);
@@ -288,11 +289,13 @@ extern "C" int hb_sum_leading(const hb_array *a, int n_axes, hb_array **out) {
 }
 
 extern "C" int hb_sum_all(const hb_array *a, hb_array **out) {
+  hb_prof_scope prof_("sum_all", a);
   HB_REQUIRE(a, "null argument");
   return hb_sum_leading(a, a->rank, out);
 }
 
 extern "C" int hb_dot_all(const hb_array *a, const hb_array *b, hb_array **out) {
+  hb_prof_scope prof_("dot_all", a, b);
   HB_CHECK_INIT();
   HB_REQUIRE(a && b && out, "null argument");
   HB_REQUIRE(a->dt == b->dt && hb_same_shape(a, b), "sdot0: %s %s vs %s %s", hb_dtype_name(a->dt),

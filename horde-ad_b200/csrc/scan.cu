@@ -107,6 +107,7 @@ __global__ void __launch_bounds__(256)
 }
 
 extern "C" int hb_prod_fold_grad(const hb_array *x, double dt, hb_array **prod_out, hb_array **grad_out) {
+  hb_prof_scope prof_("prod_fold_grad", x);
   HB_CHECK_INIT();
   HB_REQUIRE(x && prod_out, "null argument");
   HB_REQUIRE(x->rank == 1 && hb_is_float(x->dt), "prod fold: rank-1 floating vector required");

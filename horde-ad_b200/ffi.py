@@ -59,6 +59,7 @@ PROTOTYPES = {
     "hb_launch_count": [C.POINTER(C.c_uint64)], "hb_reset_launch_count": [],
     "hb_stream": [PP], "hb_event_record": [C.c_int],
     "hb_event_elapsed_ms": [C.c_int, C.c_int, C.POINTER(C.c_float)],
+    "hb_prof_begin": [], "hb_prof_end": [], "hb_prof_report": [C.c_char_p, C.c_size_t],
     "hb_retain": [P], "hb_release": [P],
     "hb_from_host": [C.c_int, C.c_int, I64P, P, PP], "hb_upload_into": [P, P],
     "hb_to_host": [P, P], "hb_scalar_to_host": [P, P],

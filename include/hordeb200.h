@@ -85,6 +85,14 @@ int hb_stream(void **cuda_stream);
 int hb_event_record(int slot);
 int hb_event_elapsed_ms(int slot_a, int slot_b, float *ms);
 
+/* Per-launch profiler for bench.py's live roofline: between begin and end every
+ * kernel launch is bracketed by events on the library stream; the report has
+ * one line per launch site, "hostfunction:line count total_ms", sorted by
+ * total device time.  Not used on the product path. */
+int hb_prof_begin(void);
+int hb_prof_end(void);
+int hb_prof_report(char *buf, size_t len);
+
 int hb_retain(hb_array *a);
 /* ForeignPtr finaliser; stream-ordered free; callable from any thread. */
 int hb_release(hb_array *a);

@@ -129,8 +129,8 @@ def test_binary_float(dev, oracle, dtype):
     # broadcast (stride-0) and transposed operands, long inner axis (rows kernel)
     big = rnd(rng, (4, 3, 700), dtype)
     bias = rnd(rng, (3,), dtype)
-    dv = dev.stranspose([1, 2, 0], dev.sreplicateN([4, 700], dev.sconcrete(bias)))
-    rv = oracle.stranspose([1, 2, 0], oracle.sreplicateN([4, 700], bias))
+    dv = dev.stranspose([0, 2, 1], dev.sreplicateN([4, 700], dev.sconcrete(bias)))
+    rv = oracle.stranspose([0, 2, 1], oracle.sreplicateN([4, 700], bias))
     exact(dev.to_numpy(dev.binary("add", dev.sconcrete(big), dv)), big + rv)
     s = dev.srepl([4, 3, 700], 0.25, dtype)
     exact(dev.to_numpy(dev.binary("mul", s, dev.sconcrete(big))), (np.array(0.25, dtype) * big))
