@@ -270,7 +270,7 @@ def main():
     local_batch = PER_GPU_BATCH if args.scaling == "weak" else PER_GPU_BATCH // world
     global_batch = local_batch * world
     tr = CnnTrainer(dev, local_batch, **HYPER, world=world, use_graph=not args.no_graph)
-    rng = np.random.Generator(np.random.Philox(42, key=rank))
+    rng = np.random.Generator(np.random.Philox(42 + 1000 * rank))
     gl = PinnedBuffer((local_batch, 28, 28), np.float64)
     lb = PinnedBuffer((local_batch, 10), np.float64)
     gl.array[...] = rng.uniform(0, 1, gl.array.shape)
