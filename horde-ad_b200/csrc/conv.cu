@@ -18,6 +18,24 @@
 #include "common.cuh"
 
 int hb_copy_into(hb_array *dst, const hb_array *src);  // elementwise.cu
+// conv_dmma.cu: shared-memory-staged DMMA kernels (contiguous f64 operands)
+int hb_conv_sp_dmma(const hb_array *K, const hb_array *in, hb_array *out, int flip, int *done);
+int hb_conv_dk_dmma(const hb_array *A, const hb_array *dB, hb_array *out, int KH, int KW, int *done);
+
+// Runs the DMMA fast path into a fresh [n0,n1,n2,n3] array when it applies.
+static int try_sp(const hb_array *K, const hb_array *in, const int64_t *osh, int flip, hb_array **out, int *done) {
+  *done = 0;
+  if (in->dt != HB_F64 || !hb_contig(in)) return HB_OK;
+  hb_array *o;
+  HB_TRY(hb_new_array(HB_F64, 4, osh, &o));
+  int st = hb_conv_sp_dmma(K, in, o, flip, done);
+  if (st != HB_OK || !*done) {
+    hb_release(o);
+    return st;
+  }
+  *out = o;
+  return HB_OK;
+}
 extern "C" int hb_dot_inner_sum_leading(const hb_array *a, const hb_array *b, int n_axes, hb_array **out);
 
 // zero-padded copy of x[N,C,H,W]: lo rows/cols before, hi after
@@ -69,6 +87,12 @@ extern "C" int hb_conv2d_preserving(const hb_array *K, const hb_array *A, hb_arr
     int64_t sh[4] = {N, Co, H, W};
     return hb_zeros(A->dt, 4, sh, out);
   }
+  {
+    int64_t osh[4] = {N, Co, H, W};
+    int done = 0;
+    HB_TRY(try_sp(K, A, osh, 0, out, &done));
+    if (done) return HB_OK;
+  }
   hb_array *Ap;
   HB_TRY(pad2d(A, 0, KH - 1, 0, KW - 1, &Ap));
   // operands over the index space [kept: n, o, h, w | reduced(last... ) ]
@@ -99,6 +123,18 @@ extern "C" int hb_conv2d_preserving_dkrn(const hb_array *A, const hb_array *dB, 
   int64_t N = A->shape[0], Ci = A->shape[1], H = A->shape[2], W = A->shape[3], Co = dB->shape[1];
   int64_t ksh[4] = {Co, Ci, KH, KW};
   if (N * H * W == 0 || Co * Ci * KH * KW == 0) return hb_zeros(A->dt, 4, ksh, out);
+  if (A->dt == HB_F64 && hb_contig(A) && hb_contig(dB)) {
+    hb_array *o;
+    int done = 0;
+    HB_TRY(hb_new_array(HB_F64, 4, ksh, &o));
+    int st = hb_conv_dk_dmma(A, dB, o, KH, KW, &done);
+    if (st == HB_OK && done) {
+      *out = o;
+      return HB_OK;
+    }
+    hb_release(o);
+    if (st != HB_OK) return st;
+  }
   hb_array *Ap;
   HB_TRY(pad2d(A, 0, KH - 1, 0, KW - 1, &Ap));
   // deterministic split-K over image groups: G partial kernels, summed in order
@@ -141,6 +177,11 @@ extern "C" int hb_conv2d_preserving_dinp(const hb_array *K, const hb_array *dB, 
   int64_t Ci = K->shape[1], KH = K->shape[2], KW = K->shape[3];
   int64_t ash[4] = {N, Ci, H, W};
   if (N * Ci * H * W == 0 || Co * KH * KW == 0) return hb_zeros(K->dt, 4, ash, out);
+  {
+    int done = 0;
+    HB_TRY(try_sp(K, dB, ash, 1, out, &done));
+    if (done) return HB_OK;
+  }
   hb_array *Bp;
   HB_TRY(pad2d(dB, KH - 1, 0, KW - 1, 0, &Bp));
   // dA[n,c,h,w] = sum_{o,kh,kw} Bp[n,o,h+(KH-1)-kh, w+(KW-1)-kw] K[o,c,kh,kw]

@@ -1,0 +1,683 @@
+// conv_dmma.cu -- shared-memory-staged, im2col-free FP64 convolution kernels
+// on the DMMA tensor pipe (mma.sync m8n8k4 f64 -> SASS DMMA; tcgen05 has no
+// FP64 kind, so this is the FP64 tensor path of sm_100a).
+//
+// Reference semantics: conv2dPreservingS (CommonShapedOps.hs:136-157) and its
+// handwritten adjoints conv2dPreserving_dInp / _dKrn
+// (TestConvQuickCheck.hs:290-349).
+//
+// Why not the generic strided-GEMM engine (contract.cu): ncu showed it LSU/L1
+// bound (l1tex 88 %, FP64 pipe 34 %), because every operand element is
+// gathered through offset tables.  Here the INPUT TILE ITSELF (with its halo,
+// zero-filled at the image border) is staged in shared memory with cp.async
+// and the DMMA fragments are read from SHIFTED addresses of that tile -- the
+// (kh, kw) taps are address offsets, no patch matrix exists anywhere:
+//
+//   spatial kernel (forward and dInp):
+//     out[n,q,y,x] = sum_{p,i,j} in[n,p,y+i+oy,x+j+ox] * Wt[p,(i,j),q]
+//     M = 8 consecutive output positions, N = 8 output channels,
+//     K = 4 input channels (or 4 kw taps when there are < 4 input channels)
+//   dKrn kernel:
+//     dK[o,c,kh,kw] = sum_{n,y,x} dB[n,o,y,x] * A[n,c,y+kh,x+kw]
+//     M = 8 output channels, N = 8 input channels (or 8 kw taps),
+//     K = 4 positions; split-K over CTAs with a fixed-order second pass
+//     (deterministic).
+//
+// Shared-memory strides are chosen = 4 (mod 8) doubles so that every 64-bit
+// fragment load of a half-warp hits 16 distinct bank pairs.  CTAs are
+// persistent (grid = #SMs), two cp.async stages, one CTA per SM (up to 227 KB).
+#include "common.cuh"
+
+namespace {
+
+constexpr int kSmemMax = 227 * 1024;
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp16(void *s, const void *g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(s)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp8(void *s, const void *g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(smem_u32(s)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+// Geometry of one staged input tile: NI images x TR rows x RS columns per
+// channel (channel stride CS), holding output rows [y0, y0+R) and their halo.
+struct TileGeo {
+  int H, W, KH, KW;
+  int R, NI;
+  int TR, RS, IS, CS;
+  int oy, ox;  // tile row t holds input row y0+oy+t; input col x sits at tile col x-ox
+  int bands;   // ceil(H / R)
+  int vec;     // rows may be moved in 16-byte pieces
+};
+
+// channels [c0, c0+CC) of images [n0, n0+NI), input rows of band y0 -> dst
+__device__ __forceinline__ void load_in_tile(double *dst, const double *__restrict__ in, const TileGeo &g, int CC,
+                                             int c0, int P, int n0, int N, int y0, int64_t sn, int64_t sp,
+                                             int tid) {
+  const int cpr = g.vec ? (g.W >> 1) : g.W;
+  const int rpc = g.NI * g.TR;
+  const int total = CC * rpc * cpr;
+  for (int idx = tid; idx < total; idx += kThreads) {
+    int row = idx / cpr, ch = idx - row * cpr;
+    int c = row / rpc, r2 = row - c * rpc;
+    int img = r2 / g.TR, t = r2 - img * g.TR;
+    int y = y0 + g.oy + t, n = n0 + img, cg = c0 + c;
+    double *d = dst + c * g.CS + img * g.IS + t * g.RS - g.ox;
+    bool ok = cg < P && n < N && y >= 0 && y < g.H;
+    const double *s = in + n * sn + cg * sp + (int64_t)y * g.W;
+    if (g.vec) {
+      if (ok) cp16(d + 2 * ch, s + 2 * ch);
+      else *reinterpret_cast<double2 *>(d + 2 * ch) = make_double2(0.0, 0.0);
+    } else {
+      if (ok) cp8(d + ch, s + ch);
+      else d[ch] = 0.0;
+    }
+  }
+}
+
+// contiguous n doubles (n even, both 16-byte aligned)
+__device__ __forceinline__ void load_linear(double *dst, const double *__restrict__ src, int n, int tid) {
+  for (int i = tid * 2; i < n; i += kThreads * 2) cp16(dst + i, src + i);
+}
+
+// ===================================================== spatial (fwd / dInp)
+struct SpP {
+  const double *in, *wp;
+  double *out;
+  TileGeo g;
+  int N, P, Q;
+  int CC, NCH;       // input channels per stage, number of stages per item
+  int QT, TS, WCS;   // output-channel tile, tap stride, channel stride of the packed weights
+  int Ppad;          // NCH * CC
+  int items;         // ceil(N / NI) * bands
+  int in_doubles, stage_doubles;
+  int64_t sn, sp;
+  int KWP;           // KW rounded up to 4 (TAPK)
+};
+
+// Packs K into Wt[qt][p][tap][q] (tap stride TS, channel stride WCS), zero
+// padded in p, q and (TAPK) kw.  flip: dInp (Wt[p=o][i',j'][q=c] =
+// K[o,c,KH-1-i',KW-1-j']); else forward (Wt[p=c][i,j][q=o] = K[o,c,i,j]).
+__global__ void pack_sp_weights(const double *__restrict__ K, double *__restrict__ wp, int Co, int Ci, int KH, int KW,
+                                int KWe, int P, int Q, int Ppad, int QT, int TS, int WCS, int nqt, int flip,
+                                int64_t k_so, int64_t k_sc, int64_t k_si, int64_t k_sj) {
+  int64_t total = (int64_t)nqt * Ppad * WCS;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    int w = (int)(idx % WCS);
+    int64_t r = idx / WCS;
+    int p = (int)(r % Ppad), qt = (int)(r / Ppad);
+    int tap = w / TS, ql = w - tap * TS;
+    int i = tap / KWe, j = tap - i * KWe;
+    int q = qt * QT + ql;
+    double v = 0.0;
+    if (i < KH && j < KW && ql < QT && p < P && q < Q) {
+      if (flip) v = K[p * k_so + q * k_sc + (KH - 1 - i) * k_si + (KW - 1 - j) * k_sj];
+      else v = K[q * k_so + p * k_sc + i * k_si + j * k_sj];
+    }
+    wp[idx] = v;
+  }
+}
+
+template <int WM, int WN, int MF, int NQ, bool TAPK>
+__global__ void __launch_bounds__(kThreads, 1) conv_sp_kernel(const __grid_constant__ SpP p) {
+  extern __shared__ __align__(16) double smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wm = warp % WM, wn = warp / WM;
+  const int fr = lane >> 2, fk = lane & 3;
+  const TileGeo &g = p.g;
+
+  for (int i = tid; i < 2 * p.stage_doubles; i += kThreads) smem[i] = 0.0;
+  __syncthreads();
+
+  const int RW = g.R * g.W, npos = g.NI * RW;
+  const int F = (npos + 7) >> 3;
+  // fragment f = i * WM + wm (strided over the warps of a column: balanced)
+  int nf = (F - wm + WM - 1) / WM;
+  nf = nf < 0 ? 0 : (nf > MF ? MF : nf);
+  int mbase[MF];
+#pragma unroll
+  for (int i = 0; i < MF; i++) {
+    int pidx = (i * WM + wm) * 8 + fr;
+    int off = 0;
+    if (pidx < npos) {
+      int img = pidx / RW, rem = pidx - img * RW;
+      int y = rem / g.W, x = rem - y * g.W;
+      off = img * g.IS + y * g.RS + x;
+    }
+    mbase[i] = off;
+  }
+  double acc[MF][NQ][2];
+#pragma unroll
+  for (int i = 0; i < MF; i++)
+#pragma unroll
+    for (int j = 0; j < NQ; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  const int qt = blockIdx.y;
+  const int my_items = (p.items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int T = my_items * p.NCH;
+  const double *wbase = p.wp + (int64_t)qt * p.Ppad * p.WCS;
+
+  auto issue = [&](int t) {
+    int it = blockIdx.x + (t / p.NCH) * gridDim.x, ch = t % p.NCH;
+    int nblk = it / g.bands, band = it - nblk * g.bands;
+    double *st = smem + (t & 1) * p.stage_doubles;
+    load_in_tile(st, p.in, g, p.CC, ch * p.CC, p.P, nblk * g.NI, p.N, band * g.R, p.sn, p.sp, tid);
+    load_linear(st + p.in_doubles, wbase + (int64_t)ch * p.CC * p.WCS, p.CC * p.WCS, tid);
+    cp_commit();
+  };
+
+  if (T > 0) issue(0);
+  for (int t = 0; t < T; t++) {
+    if (t + 1 < T) {
+      issue(t + 1);
+      cp_wait<1>();
+    } else {
+      cp_wait<0>();
+    }
+    __syncthreads();
+    const double *Is = smem + (t & 1) * p.stage_doubles;
+    const double *Ws = Is + p.in_doubles + wn * NQ * 8 + fr;
+    if (TAPK) {
+      const int ng = p.KWP >> 2;
+      for (int c = 0; c < p.CC; c++) {
+        for (int kh = 0; kh < g.KH; kh++) {
+          for (int g4 = 0; g4 < ng; g4++) {
+            const double *ia = Is + c * g.CS + kh * g.RS + g4 * 4 + fk;
+            const double *wb = Ws + c * p.WCS + (kh * p.KWP + g4 * 4 + fk) * p.TS;
+            double b[NQ];
+#pragma unroll
+            for (int j = 0; j < NQ; j++) b[j] = wb[j * 8];
+#pragma unroll
+            for (int i = 0; i < MF; i++) {
+              if (i < nf) {
+                double a = ia[mbase[i]];
+#pragma unroll
+                for (int j = 0; j < NQ; j++) dmma884(acc[i][j][0], acc[i][j][1], a, b[j]);
+              }
+            }
+          }
+        }
+      }
+    } else {
+      for (int c4 = 0; c4 < p.CC; c4 += 4) {
+        const double *ic = Is + (c4 + fk) * g.CS;
+        const double *wc = Ws + (c4 + fk) * p.WCS;
+        for (int kh = 0; kh < g.KH; kh++) {
+          for (int kw = 0; kw < g.KW; kw++) {
+            const double *ia = ic + kh * g.RS + kw;
+            const double *wb = wc + (kh * g.KW + kw) * p.TS;
+            double b[NQ];
+#pragma unroll
+            for (int j = 0; j < NQ; j++) b[j] = wb[j * 8];
+#pragma unroll
+            for (int i = 0; i < MF; i++) {
+              if (i < nf) {
+                double a = ia[mbase[i]];
+#pragma unroll
+                for (int j = 0; j < NQ; j++) dmma884(acc[i][j][0], acc[i][j][1], a, b[j]);
+              }
+            }
+          }
+        }
+      }
+    }
+    if ((t + 1) % p.NCH == 0) {
+      // epilogue of this item: C fragment row = position, cols = 2 output channels
+      int it = blockIdx.x + (t / p.NCH) * gridDim.x;
+      int nblk = it / g.bands, band = it - nblk * g.bands;
+      int y0 = band * g.R;
+#pragma unroll
+      for (int i = 0; i < MF; i++) {
+        if (i < nf) {
+          int pidx = (i * WM + wm) * 8 + fr;
+          int img = pidx / RW, rem = pidx - img * RW;
+          int y = rem / g.W, x = rem - y * g.W;
+          int n = nblk * g.NI + img, yy = y0 + y;
+          bool okp = pidx < npos && n < p.N && yy < g.H;
+#pragma unroll
+          for (int j = 0; j < NQ; j++) {
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+              int q = qt * p.QT + wn * NQ * 8 + j * 8 + fk * 2 + e;
+              if (okp && q < p.Q) p.out[(((int64_t)n * p.Q + q) * g.H + yy) * g.W + x] = acc[i][j][e];
+              acc[i][j][e] = 0.0;
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ================================================================== dKrn
+struct DkP {
+  const double *A, *dB;
+  double *part;  // [split * WK + wk][Co][Ci][KH][KW]
+  TileGeo g;
+  int N, Ci, Co;
+  int CC;          // input channels per CTA (gridDim.y chunks)
+  int NCF;         // CHAN: CC / 8 column fragments; TAPW: kw groups of 8
+  int npairs;      // (tap, cf) pairs (CHAN) or (c, kh, kwg) triples (TAPW) per CTA
+  int WN, WK, NPW; // warps along pairs / along K; pairs per warp
+  int PS, npos4;   // dB tile row stride; positions rounded up to 4
+  int items;
+  int a_doubles, stage_doubles;
+  int lut_off;     // ints, after the two stages
+  int64_t a_sn, a_sc, b_sn, b_so;
+  int dbvec;
+};
+
+constexpr int kNP = 9;  // max column pairs per warp
+
+template <int WM, int MO, bool TAPW>
+__global__ void __launch_bounds__(kThreads, 1) conv_dk_kernel(const __grid_constant__ DkP p) {
+  extern __shared__ __align__(16) double smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wm = warp % WM, wn = (warp / WM) % p.WN, wk = warp / (WM * p.WN);
+  const int fr = lane >> 2, fk = lane & 3;
+  const TileGeo &g = p.g;
+  int *lut = reinterpret_cast<int *>(smem + 2 * p.stage_doubles);
+
+  for (int i = tid; i < 2 * p.stage_doubles; i += kThreads) smem[i] = 0.0;
+  const int RW = g.R * g.W, npos = g.NI * RW;
+  for (int i = tid; i < p.npos4; i += kThreads) {
+    int off = 0;
+    if (i < npos) {
+      int img = i / RW, rem = i - img * RW;
+      int y = rem / g.W, x = rem - y * g.W;
+      off = img * g.IS + y * g.RS + x;
+    }
+    lut[i] = off;
+  }
+  __syncthreads();
+
+  // column pairs of this warp
+  const int c0 = blockIdx.y * p.CC;
+  int pair_off[kNP];
+  int npw = p.npairs - wn * p.NPW;
+  npw = npw < 0 ? 0 : (npw > p.NPW ? p.NPW : npw);
+#pragma unroll
+  for (int j = 0; j < kNP; j++) {
+    int pr = wn * p.NPW + j, off = 0;
+    if (j < npw) {
+      if (TAPW) {  // pr = (c * KH + kh) * NCF + kwg ; column = kw
+        int kwg = pr % p.NCF, r = pr / p.NCF;
+        int kh = r % g.KH, c = r / g.KH;
+        off = c * g.CS + kh * g.RS + kwg * 8 + fr;
+      } else {     // pr = tap * NCF + cf ; column = channel
+        int cf = pr % p.NCF, tap = pr / p.NCF;
+        int kh = tap / g.KW, kw = tap - kh * g.KW;
+        off = (cf * 8 + fr) * g.CS + kh * g.RS + kw;
+      }
+    }
+    pair_off[j] = off;
+  }
+  double acc[MO][kNP][2];
+#pragma unroll
+  for (int m = 0; m < MO; m++)
+#pragma unroll
+    for (int j = 0; j < kNP; j++) acc[m][j][0] = acc[m][j][1] = 0.0;
+
+  const int o_tile = blockIdx.z * (WM * MO * 8);
+  const int T = (p.items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  auto issue = [&](int t) {
+    int it = blockIdx.x + t * gridDim.x;
+    int nblk = it / g.bands, band = it - nblk * g.bands;
+    int n0 = nblk * g.NI, y0 = band * g.R;
+    double *st = smem + (t & 1) * p.stage_doubles;
+    load_in_tile(st, p.A, g, p.CC, c0, p.Ci, n0, p.N, y0, p.a_sn, p.a_sc, tid);
+    // dB tile: [o][img * RW + y * W + x], rows beyond the image zero
+    double *db = st + p.a_doubles;
+    int rows_ok = g.H - y0 < g.R ? g.H - y0 : g.R;
+    int nval = rows_ok * g.W;
+    int co = p.Co - o_tile < WM * MO * 8 ? p.Co - o_tile : WM * MO * 8;
+    if (p.dbvec) {
+      int cpr = RW >> 1, total = co * g.NI * cpr;
+      for (int idx = tid; idx < total; idx += kThreads) {
+        int r = idx / cpr, ch = idx - r * cpr;
+        int o = r / g.NI, img = r - o * g.NI;
+        double *d = db + o * p.PS + img * RW + 2 * ch;
+        if (n0 + img < p.N && 2 * ch < nval)
+          cp16(d, p.dB + (n0 + img) * p.b_sn + (o_tile + o) * p.b_so + (int64_t)y0 * g.W + 2 * ch);
+        else *reinterpret_cast<double2 *>(d) = make_double2(0.0, 0.0);
+      }
+    } else {
+      int total = co * g.NI * RW;
+      for (int idx = tid; idx < total; idx += kThreads) {
+        int r = idx / RW, ch = idx - r * RW;
+        int o = r / g.NI, img = r - o * g.NI;
+        double *d = db + o * p.PS + img * RW + ch;
+        if (n0 + img < p.N && ch < nval)
+          cp8(d, p.dB + (n0 + img) * p.b_sn + (o_tile + o) * p.b_so + (int64_t)y0 * g.W + ch);
+        else *d = 0.0;
+      }
+    }
+    cp_commit();
+  };
+
+  if (T > 0) issue(0);
+  for (int t = 0; t < T; t++) {
+    if (t + 1 < T) {
+      issue(t + 1);
+      cp_wait<1>();
+    } else {
+      cp_wait<0>();
+    }
+    __syncthreads();
+    const double *As = smem + (t & 1) * p.stage_doubles;
+    const double *Bs = As + p.a_doubles + (wm * MO * 8 + fr) * p.PS + fk;
+    for (int k0 = wk * 4; k0 < p.npos4; k0 += 4 * p.WK) {
+      const double *ap = As + lut[k0 + fk];
+      double a[MO];
+#pragma unroll
+      for (int m = 0; m < MO; m++) a[m] = Bs[m * 8 * p.PS + k0];
+#pragma unroll
+      for (int j = 0; j < kNP; j++) {
+        if (j < npw) {
+          double b = ap[pair_off[j]];
+#pragma unroll
+          for (int m = 0; m < MO; m++) dmma884(acc[m][j][0], acc[m][j][1], a[m], b);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // partial result of this (CTA, wk): C fragment row = o, cols = 2 columns
+  const int KK = g.KH * g.KW;
+  double *part = p.part + ((int64_t)blockIdx.x * p.WK + wk) * ((int64_t)p.Co * p.Ci * KK);
+#pragma unroll
+  for (int j = 0; j < kNP; j++) {
+    if (j < npw) {
+      int pr = wn * p.NPW + j;
+#pragma unroll
+      for (int m = 0; m < MO; m++) {
+        int o = o_tile + wm * MO * 8 + m * 8 + fr;
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          int col = fk * 2 + e, c, kh, kw;
+          if (TAPW) {
+            int kwg = pr % p.NCF, r = pr / p.NCF;
+            kh = r % g.KH;
+            c = c0 + r / g.KH;
+            kw = kwg * 8 + col;
+          } else {
+            int cf = pr % p.NCF, tap = pr / p.NCF;
+            kh = tap / g.KW;
+            kw = tap - kh * g.KW;
+            c = c0 + cf * 8 + col;
+          }
+          if (o < p.Co && c < p.Ci && kw < g.KW) part[((int64_t)o * p.Ci + c) * KK + kh * g.KW + kw] = acc[m][j][e];
+        }
+      }
+    }
+  }
+}
+
+// dK[i] = sum_s part[s][i], s ascending (fixed order -> deterministic)
+__global__ void dk_reduce_kernel(const double *__restrict__ part, double *__restrict__ out, int n, int splits) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s = 0.0;
+  for (int k = 0; k < splits; k++) s += part[(int64_t)k * n + i];
+  out[i] = s;
+}
+
+static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+// smallest s >= n with s = 4 (mod 8)
+static inline int stride4mod8(int n) {
+  int s = round_up(n, 8) + 4;
+  if (s - 8 >= n) s -= 8;
+  return s;
+}
+
+template <typename K>
+static int set_smem(K kernel, int bytes) {
+  HB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  return HB_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ hosts
+// Returns HB_OK and sets *done = 1 when the fast path ran.
+// flip = 0: forward (in = A[N,P,H,W], K[Q,P,KH,KW]); flip = 1: dInp
+// (in = dB[N,P,H,W], K[P,Q,KH,KW]).  `in` contiguous f64, out contiguous.
+int hb_conv_sp_dmma(const hb_array *K, const hb_array *in, hb_array *out, int flip, int *done) {
+  *done = 0;
+  if (in->dt != HB_F64 || !hb_contig(in) || !hb_contig(out)) return HB_OK;
+  int N = (int)in->shape[0], P = (int)in->shape[1], H = (int)in->shape[2], W = (int)in->shape[3];
+  int Q = (int)out->shape[1];
+  int KH = (int)K->shape[2], KW = (int)K->shape[3];
+  if ((int64_t)N * P * H * W >= (1ll << 31) || (int64_t)N * Q * H * W >= (1ll << 31)) return HB_OK;
+  if (W > 224 || KH > 16 || KW > 16) return HB_OK;
+  SpP p;
+  memset(&p, 0, sizeof p);
+  // k mode
+  double eff_chan = (double)P / round_up(P, 4), eff_tap = (double)KW / round_up(KW, 4);
+  bool tapk = eff_tap > eff_chan;
+  p.KWP = round_up(KW, 4);
+  int KWe = tapk ? p.KWP : KW;
+  // output-channel tile and warp grid
+  int WN, NQ;
+  if (Q <= 8) { WN = 1; NQ = 1; }
+  else if (Q <= 16) { WN = 1; NQ = 2; }
+  else if (Q <= 32) { WN = 2; NQ = 2; }
+  else { WN = 2; NQ = 4; }
+  int WM = 8 / WN, MF = 7;
+  p.QT = WN * NQ * 8;
+  int nqt = (Q + p.QT - 1) / p.QT;
+  p.TS = tapk ? p.QT + 4 : p.QT;
+  p.WCS = stride4mod8(KH * KWe * p.TS);
+  int slots = WM * MF * 8;
+  TileGeo &g = p.g;
+  g.H = H; g.W = W; g.KH = KH; g.KW = KW;
+  g.oy = flip ? -(KH - 1) : 0;
+  g.ox = flip ? -(KW - 1) : 0;
+  int halo_w = tapk ? p.KWP - 1 : KW - 1;
+  if (flip && tapk) halo_w = (KW - 1) + (p.KWP - 1);  // low-side halo plus the padded taps' overrun
+  g.RS = round_up(W + halo_w, 2);
+  int NI, R;
+  if (H * W <= slots) { R = H; NI = slots / (H * W); if (NI > N) NI = N; }
+  else { NI = 1; R = slots / W; if (R < 1) return HB_OK; int nb = (H + R - 1) / R; R = (H + nb - 1) / nb; }
+  int Pq = tapk ? P : round_up(P, 4);
+  int CC = 0;
+  for (;;) {
+    g.R = R; g.NI = NI; g.TR = R + KH - 1; g.IS = g.TR * g.RS;
+    g.CS = stride4mod8(NI * g.IS + (tapk ? 4 : 0));
+    // largest channel chunk whose two stages fit
+    int per_c = g.CS + p.WCS;
+    int maxc = (kSmemMax / 8 / 2) / per_c;
+    if (!tapk) maxc = maxc / 4 * 4;
+    if (maxc >= (tapk ? 1 : 4)) { CC = maxc < Pq ? maxc : Pq; break; }
+    if (NI > 1) NI = (NI + 1) / 2;
+    else if (R > 1) R = (R + 1) / 2;
+    else return HB_OK;
+  }
+  // balance chunks
+  p.NCH = (Pq + CC - 1) / CC;
+  CC = (Pq + p.NCH - 1) / p.NCH;
+  if (!tapk) CC = round_up(CC, 4);
+  p.CC = CC;
+  p.Ppad = p.NCH * CC;
+  g.bands = (H + g.R - 1) / g.R;
+  p.items = ((N + g.NI - 1) / g.NI) * g.bands;
+  p.in_doubles = CC * g.CS;
+  p.stage_doubles = round_up(p.in_doubles + CC * p.WCS, 2);
+  p.N = N; p.P = P; p.Q = Q;
+  p.sn = in->strides[0]; p.sp = in->strides[1];
+  p.in = (const double *)hb_data(in);
+  p.out = (double *)hb_data(out);
+  g.vec = (W % 2 == 0) && (g.ox % 2 == 0) && (((uintptr_t)p.in & 15) == 0) && (p.sn % 2 == 0) && (p.sp % 2 == 0);
+  int smem_bytes = 2 * p.stage_doubles * 8;
+  if (smem_bytes > kSmemMax) return HB_OK;
+  // packed weights in scratch
+  int64_t wn = (int64_t)nqt * p.Ppad * p.WCS;
+  void *scr;
+  HB_TRY(hb_scratch((size_t)wn * 8, &scr));
+  p.wp = (const double *)scr;
+  {
+    int blocks = hb_blocks_for(wn, 256, g_hb.sm_count * 8);
+    pack_sp_weights<<<blocks, 256, 0, g_hb.stream>>>((const double *)hb_data(K), (double *)scr, 0, 0, KH, KW, KWe, P,
+                                                     Q, p.Ppad, p.QT, p.TS, p.WCS, nqt, flip, K->strides[0],
+                                                     K->strides[1], K->strides[2], K->strides[3]);
+    HB_LAUNCHED();
+  }
+  dim3 grid((unsigned)(p.items < g_hb.sm_count ? p.items : g_hb.sm_count), (unsigned)nqt);
+#define SP_LAUNCH(WM_, WN_, NQ_)                                                                   \
+  do {                                                                                             \
+    if (tapk) {                                                                                    \
+      HB_TRY(set_smem(conv_sp_kernel<WM_, WN_, 7, NQ_, true>, smem_bytes));                        \
+      conv_sp_kernel<WM_, WN_, 7, NQ_, true><<<grid, kThreads, smem_bytes, g_hb.stream>>>(p);      \
+    } else {                                                                                       \
+      HB_TRY(set_smem(conv_sp_kernel<WM_, WN_, 7, NQ_, false>, smem_bytes));                       \
+      conv_sp_kernel<WM_, WN_, 7, NQ_, false><<<grid, kThreads, smem_bytes, g_hb.stream>>>(p);     \
+    }                                                                                              \
+  } while (0)
+  if (WN == 1 && NQ == 1) SP_LAUNCH(8, 1, 1);
+  else if (WN == 1 && NQ == 2) SP_LAUNCH(8, 1, 2);
+  else if (WN == 2 && NQ == 2) SP_LAUNCH(4, 2, 2);
+  else SP_LAUNCH(4, 2, 4);
+#undef SP_LAUNCH
+  HB_LAUNCHED();
+  (void)MF;
+  *done = 1;
+  return HB_OK;
+}
+
+// dK[Co,Ci,KH,KW] from A[N,Ci,H,W], dB[N,Co,H,W] (contiguous f64).
+int hb_conv_dk_dmma(const hb_array *A, const hb_array *dB, hb_array *out, int KH, int KW, int *done) {
+  *done = 0;
+  if (A->dt != HB_F64 || !hb_contig(A) || !hb_contig(dB) || !hb_contig(out)) return HB_OK;
+  int N = (int)A->shape[0], Ci = (int)A->shape[1], H = (int)A->shape[2], W = (int)A->shape[3];
+  int Co = (int)dB->shape[1];
+  if ((int64_t)N * Ci * H * W >= (1ll << 31) || (int64_t)N * Co * H * W >= (1ll << 31)) return HB_OK;
+  if (W > 256 || KH > 16 || KW > 16) return HB_OK;
+  DkP p;
+  memset(&p, 0, sizeof p);
+  double eff_chan = (double)Ci / round_up(Ci, 8), eff_tap = (double)KW / round_up(KW, 8);
+  bool tapw = eff_tap > eff_chan;
+  int WM, MO;
+  if (Co <= 8) { WM = 1; MO = 1; }
+  else if (Co <= 16) { WM = 1; MO = 2; }
+  else if (Co <= 32) { WM = 2; MO = 2; }
+  else { WM = 4; MO = 2; }
+  int otile = WM * MO * 8, not_ = (Co + otile - 1) / otile;
+  int wrest = 8 / WM;  // warps left for pairs x K
+  int KK = KH * KW;
+  int maxpairs = wrest * kNP;
+  // channels per CTA
+  int CC, NCF, npairs;
+  if (tapw) {
+    NCF = (KW + 7) / 8;
+    int per_c = KH * NCF;
+    if (per_c > maxpairs) return HB_OK;
+    CC = maxpairs / per_c;
+    if (CC > Ci) CC = Ci;
+    npairs = CC * per_c;
+  } else {
+    if (KK > maxpairs) return HB_OK;
+    int ncf = maxpairs / KK;  // column fragments of 8 channels
+    int need = (Ci + 7) / 8;
+    if (ncf > need) ncf = need;
+    // balance the chunks
+    int chunks = (need + ncf - 1) / ncf;
+    ncf = (need + chunks - 1) / chunks;
+    NCF = ncf;
+    CC = ncf * 8;
+    npairs = KK * ncf;
+  }
+  int ncc = (Ci + CC - 1) / CC;
+  int WN = 1;
+  while (WN < wrest && WN * kNP < npairs) WN *= 2;
+  if (WN * kNP < npairs) return HB_OK;
+  p.WN = WN;
+  p.WK = wrest / WN;
+  p.NPW = (npairs + WN - 1) / WN;
+  p.CC = CC; p.NCF = NCF; p.npairs = npairs;
+  TileGeo &g = p.g;
+  g.H = H; g.W = W; g.KH = KH; g.KW = KW; g.oy = 0; g.ox = 0;
+  int halo_w = tapw ? NCF * 8 - 1 : KW - 1;
+  g.RS = round_up(W + halo_w, 2);
+  // positions per stage: as many rows as two stages allow
+  int NI = 1, R = H;
+  for (;;) {
+    g.R = R; g.NI = NI; g.TR = R + KH - 1; g.IS = g.TR * g.RS;
+    g.CS = stride4mod8(NI * g.IS + (tapw ? 8 : 0));
+    int npos = NI * R * W;
+    p.npos4 = round_up(npos, 4);
+    p.PS = stride4mod8(p.npos4);
+    p.a_doubles = round_up(CC * g.CS, 2);
+    p.stage_doubles = p.a_doubles + otile * p.PS;
+    int bytes = 2 * p.stage_doubles * 8 + p.npos4 * 4 + 16;
+    if (bytes <= kSmemMax) break;
+    if (R > 1) R = (R + 1) / 2;
+    else return HB_OK;
+  }
+  {
+    int nb = (H + g.R - 1) / g.R;
+    g.R = (H + nb - 1) / nb;
+    g.TR = g.R + KH - 1; g.IS = g.TR * g.RS;
+    g.CS = stride4mod8(NI * g.IS + (tapw ? 8 : 0));
+    p.npos4 = round_up(NI * g.R * W, 4);
+    p.PS = stride4mod8(p.npos4);
+    p.a_doubles = round_up(CC * g.CS, 2);
+    p.stage_doubles = p.a_doubles + otile * p.PS;
+  }
+  g.bands = (H + g.R - 1) / g.R;
+  p.items = ((N + NI - 1) / NI) * g.bands;
+  p.N = N; p.Ci = Ci; p.Co = Co;
+  p.A = (const double *)hb_data(A);
+  p.dB = (const double *)hb_data(dB);
+  p.a_sn = A->strides[0]; p.a_sc = A->strides[1];
+  p.b_sn = dB->strides[0]; p.b_so = dB->strides[1];
+  g.vec = (W % 2 == 0) && (((uintptr_t)p.A & 15) == 0) && (p.a_sn % 2 == 0) && (p.a_sc % 2 == 0);
+  p.dbvec = ((g.R * W) % 2 == 0) && (W % 2 == 0) && (((uintptr_t)p.dB & 15) == 0) && (p.b_sn % 2 == 0) &&
+            (p.b_so % 2 == 0);
+  int smem_bytes = 2 * p.stage_doubles * 8 + p.npos4 * 4 + 16;
+  int splits = g_hb.sm_count / (ncc * not_);
+  if (splits < 1) splits = 1;
+  if (splits > p.items) splits = p.items;
+  int nparts = splits * p.WK;
+  int64_t nout = (int64_t)Co * Ci * KK;
+  void *scr;
+  HB_TRY(hb_scratch((size_t)nparts * nout * 8, &scr));
+  p.part = (double *)scr;
+  // every (split, wk) writes every element it owns; columns beyond npairs never exist
+  dim3 grid((unsigned)splits, (unsigned)ncc, (unsigned)not_);
+#define DK_LAUNCH(WM_, MO_)                                                                  \
+  do {                                                                                       \
+    if (tapw) {                                                                              \
+      HB_TRY(set_smem(conv_dk_kernel<WM_, MO_, true>, smem_bytes));                          \
+      conv_dk_kernel<WM_, MO_, true><<<grid, kThreads, smem_bytes, g_hb.stream>>>(p);        \
+    } else {                                                                                 \
+      HB_TRY(set_smem(conv_dk_kernel<WM_, MO_, false>, smem_bytes));                         \
+      conv_dk_kernel<WM_, MO_, false><<<grid, kThreads, smem_bytes, g_hb.stream>>>(p);       \
+    }                                                                                        \
+  } while (0)
+  if (WM == 1 && MO == 1) DK_LAUNCH(1, 1);
+  else if (WM == 1) DK_LAUNCH(1, 2);
+  else if (WM == 2) DK_LAUNCH(2, 2);
+  else DK_LAUNCH(4, 2);
+#undef DK_LAUNCH
+  HB_LAUNCHED();
+  dk_reduce_kernel<<<(unsigned)((nout + 255) / 256), 256, 0, g_hb.stream>>>(p.part, (double *)hb_data(out), (int)nout,
+                                                                           nparts);
+  HB_LAUNCHED();
+  *done = 1;
+  return HB_OK;
+}

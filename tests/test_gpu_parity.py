@@ -341,7 +341,12 @@ def test_conv_reference_goldens(dev, form, name, K, A, wrt, expected, eps):
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 @pytest.mark.parametrize("shape", [(3, 3, 3, 6, 6, 3, 3), (2, 5, 7, 9, 4, 2, 4), (5, 1, 16, 12, 12, 5, 5), (1, 1, 1, 1, 1, 1, 1),
-                                   (4, 16, 16, 14, 14, 5, 5), (2, 3, 2, 5, 0, 3, 3), (3, 2, 2, 3, 3, 4, 5)])
+                                   (4, 16, 16, 14, 14, 5, 5), (2, 3, 2, 5, 0, 3, 3), (3, 2, 2, 3, 3, 4, 5),
+                                   # DMMA kernels: row bands + channel chunks, several output-channel tiles,
+                                   # odd widths (8-byte cp.async path), ragged last band, tap-k / tap-column modes
+                                   (3, 64, 64, 28, 28, 3, 3), (2, 20, 72, 9, 7, 2, 3), (2, 8, 40, 30, 30, 3, 3),
+                                   (9, 1, 16, 28, 28, 5, 5), (301, 16, 16, 14, 14, 5, 5), (3, 2, 9, 31, 17, 3, 6),
+                                   (2, 12, 24, 50, 20, 1, 1), (1, 4, 4, 40, 230, 3, 3)])
 def test_conv_fwd_vjp_vs_oracle(dev, oracle, dtype, shape):
     N, Ci, Co, H, W, KH, KW = shape
     rng = np.random.default_rng(16)
