@@ -218,6 +218,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-conv-vjp", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--breakdown-file", default=None, help="write the full per-launch-site table of one step here")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -246,13 +247,19 @@ def main():
     from horde_ad_b200.device import DeviceBackend
     from horde_ad_b200.train import CnnTrainer, PinnedBuffer, comm_init
 
+    def dbg(msg):
+        if os.environ.get("HB_BENCH_DEBUG"):
+            print(f"[rank {rank}] {time.strftime('%H:%M:%S')} {msg}", file=sys.stderr, flush=True)
+
     dev = DeviceBackend(local_rank)      # raises without a GPU / without the built library
+    dbg("device up")
 
     def bcast(b):
         objs = [b]
         dist.broadcast_object_list(objs, src=0)
         return objs[0]
     comm_init(rank, world, bcast if world > 1 else None)
+    dbg("comm up")
 
     def barrier():
         dev.sync()
@@ -282,9 +289,13 @@ def main():
 
     # ---- device-resident: inputs uploaded once, K steps timed with CUDA events
     tr.upload(gl.ptr, lb.ptr)
-    for _ in range(W):
+    for i in range(W):
         tr.step_enqueue()
+        if i == 0:
+            dev.sync()
+            dbg("first step done")
     barrier()
+    dbg("warm-up done")
     clocks = ClockSampler(local_rank)
     clocks.start()
     ffi.call("hb_launch_count", C.byref(n0))
@@ -297,6 +308,7 @@ def main():
     n1 = C.c_uint64()
     ffi.call("hb_launch_count", C.byref(n1))
     barrier()
+    dbg("resident timing done")
     loss_resident = tr.loss_of(bucket)
     dev_ms = max_over_ranks(float(ms.value))
     value = global_batch * K / (dev_ms * 1e-3)
@@ -311,9 +323,15 @@ def main():
     dev.sync()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
+    dbg("e2e timing done")
     clk = clocks.stop()
     e2e_value = global_batch * K / e2e_s
 
+    # ---- live per-kernel timing of the same step (eager, events per launch);
+    # every rank runs it (the step contains the all-reduce), rank 0 reports
+    prof = profile_step(dev, ffi, CnnTrainer, local_batch, gl, lb, world)
+    barrier()
+    dbg("profile done")
     if rank != 0:
         tr.close()
         if dist is not None:
@@ -321,14 +339,16 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- live per-kernel timing of the same step (eager, events per launch)
     hbm_peak, peak_src, _ = peaks()
-    prof = profile_step(dev, ffi, CnnTrainer, local_batch, gl, lb, world)
     fp64_dmma, fp64_fma = C.c_double(), C.c_double()
     ffi.call("hb_microbench", 1, C.byref(fp64_dmma))
     ffi.call("hb_microbench", 0, C.byref(fp64_fma))
     fp64_peak = max(fp64_dmma.value, fp64_fma.value)
     roof, breakdown = roofline_of(prof, hbm_peak, peak_src, fp64_peak)
+    if args.breakdown_file:
+        with open(args.breakdown_file, "w") as f:
+            for r in prof:
+                f.write(f'{r["ms_per_step"]:9.4f} ms {100 * r["share"]:5.1f}% n={r["launches_per_step"]:4.1f} {r["entry"]} @ {r["site"]}\n')
 
     out = {
         "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -354,7 +374,7 @@ def main():
 
 def profile_step(dev, ffi, CnnTrainer, local_batch, gl, lb, world, steps=3):
     """Per-launch CUDA-event timing of the eager (non-graph) step."""
-    tr = CnnTrainer(dev, local_batch, **HYPER, world=1, use_graph=False)
+    tr = CnnTrainer(dev, local_batch, **HYPER, world=world, use_graph=False)
     tr.upload(gl.ptr, lb.ptr)
     for _ in range(2):
         tr.step_enqueue()

@@ -334,6 +334,22 @@ class ADBackend:
                           lambda c: [B.conv2d_dkrn(A.p, c, KH, KW) if K.d is not None else None,
                                      B.conv2d_dinp(K.p, c) if A.d is not None else None])
 
+    def conv_relu_pool(self, K, bias, A, ksize):
+        """convMnistLayerS as one node (MnistCnnShaped2.hs:42-62): conv, then the
+        fused bias + relu + max-pool pass; the adjoint needs only the pooled
+        cotangent and one code byte per pooled element."""
+        B = self.B
+        K, bias, A = self.lift(K), self.lift(bias), self.lift(A)
+        KH, KW = B.shape(K.p)[2], B.shape(K.p)[3]
+        H, W = B.shape(A.p)[2], B.shape(A.p)[3]
+        y, code = B.relu_pool_fwd(B.conv2dPreserving(K.p, A.p), bias.p, ksize)
+
+        def pb(c):
+            dpre, dbias = B.relu_pool_bwd(c, code, ksize, H, W, want_bias=bias.d is not None)
+            return [B.conv2d_dkrn(A.p, dpre, KH, KW) if K.d is not None else None, dbias,
+                    B.conv2d_dinp(K.p, dpre) if A.d is not None else None]
+        return self._node(y, [K, bias, A], pb)
+
     def relu(self, t):
         B = self.B
         t = self.lift(t)

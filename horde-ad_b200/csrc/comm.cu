@@ -81,6 +81,7 @@ __global__ void hb_scale_kernel(T *p, T s, int64_t n) {
 }
 
 extern "C" int hb_allreduce_sum(hb_array *bucket, double scale) {
+  hb_prof_scope prof_("allreduce_sum", bucket);
   HB_CHECK_INIT();
   HB_REQUIRE(bucket, "null argument");
   HB_REQUIRE(hb_contig(bucket), "allreduce: bucket must be contiguous");
@@ -92,6 +93,7 @@ extern "C" int hb_allreduce_sum(hb_array *bucket, double scale) {
     HB_NCCL(g_nccl.AllReduce(hb_data(bucket), hb_data(bucket), (size_t)n,
                              bucket->dt == HB_F64 ? hbNcclFloat64 : hbNcclFloat32, hbNcclSum, g_nccl.comm,
                              g_hb.stream));
+    if (g_hb.profiling) hb_prof_mark("ncclAllReduce", 0);
   }
   if (scale != 1.0) {
     int blocks = hb_blocks_for(n, 256, g_hb.sm_count * 8);

@@ -246,6 +246,9 @@ static int launch_contract(hb_contractp &P, const hb_array *a, const hb_array *b
   return HB_OK;
 }
 
+// gemm_dmma.cu
+int hb_gemm_dmma(const double *A, int64_t a_sm, int64_t a_sk, const double *B, int64_t b_sk, int64_t b_sn, double *C,
+                 int64_t M, int64_t N, int64_t K, int *done);
 int hb_reduce_generic(const hb_array *a, const hb_array *b, int nk, const int *kax, int nr,
                       const int *rax, hb_array *out);
 
@@ -295,8 +298,23 @@ static int contract_impl(const hb_array *a, const hb_array *b, int n_lead, hb_ar
       P.K.sb[k] = b->strides[ax];
       P.K.sc[k] = 0;
     }
-    if (a->dt == HB_F64) st = launch_contract<double>(P, a, b, o);
-    else st = launch_contract<float>(P, a, b, o);
+    int done = 0;
+    if (a->dt == HB_F64) {
+      // plain 2-D (possibly transposed) operands -> the cp.async-staged DMMA GEMM
+      cg_finish(&P.M); cg_finish(&P.N); cg_finish(&P.B); cg_finish(&P.K);
+      if (P.M.rank == 1 && P.N.rank == 1 && P.K.rank == 1 && P.B.n == 1) {
+        const double *pa = (const double *)hb_data(a), *pb = (const double *)hb_data(b);
+        double *pc = (double *)hb_data(o);
+        if (P.N.sc[0] == 1 && P.M.sc[0] == P.N.n)
+          st = hb_gemm_dmma(pa, P.M.sa[0], P.K.sa[0], pb, P.K.sb[0], P.N.sb[0], pc, P.M.n, P.N.n, P.K.n, &done);
+        else if (P.M.sc[0] == 1 && P.N.sc[0] == P.M.n)  // output is [N, M]: C^T = B^T A^T
+          st = hb_gemm_dmma(pb, P.N.sb[0], P.K.sb[0], pa, P.K.sa[0], P.M.sa[0], pc, P.N.n, P.M.n, P.K.n, &done);
+      }
+    }
+    if (st == HB_OK && !done) {
+      if (a->dt == HB_F64) st = launch_contract<double>(P, a, b, o);
+      else st = launch_contract<float>(P, a, b, o);
+    }
   } else {
     int kax[HB_R], rax[HB_R];
     int nk = 0, nr = 0;

@@ -1,0 +1,223 @@
+// gemm_dmma.cu -- dense FP64 GEMM on the DMMA tensor pipe for the plain
+// matrix contractions of the hot path: tsmatmul2 / tsmatvecmul-like sdot1In
+// over 2-D (possibly transposed) operands (OpsConcrete.hs:234-242), i.e. the
+// dense layers of MnistCnnShaped2 / MnistFcnnRanked2 and the recurrence of
+// MnistRnnShaped2.
+//
+//   C[m, n] = sum_k A[m, k] * B[k, n]        (any row/column strides with one
+//                                             unit stride per operand)
+//
+// 64x64 CTA tile, 4 warps (32x32 each = 4x4 DMMA m8n8k4 fragments), K chunks
+// of 16 staged by 16-byte cp.async through a 3-stage ring; shared-memory rows
+// padded to a stride = 4 (mod 8) doubles so fragment loads are conflict-free
+// in either operand orientation.  Small output grids are split along K across
+// CTAs (grid.z) with partials reduced in a fixed order (deterministic).
+// Anything else (batch axes, non-unit strides) stays on the generic strided
+// engine in contract.cu.
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 64, BN = 64, BK = 16, STAGES = 3, NT = 128;
+constexpr int LDK = BK + 4;   // [row][k] layout (k contiguous in memory)
+constexpr int LDM = BM + 4;   // [k][row] layout (row contiguous in memory)
+constexpr int TILE = 64 * LDK > BK * LDM ? 64 * LDK : BK * LDM;  // doubles per operand per stage
+
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp16(void *s, const void *g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(s)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+struct GemmP {
+  const double *A, *B;
+  double *C;            // C or the split-K partial buffer [split][M][N]
+  int M, N, K;
+  int64_t a_sm, a_sk;   // strides of A[m,k]
+  int64_t b_sk, b_sn;   // strides of B[k,n]
+  int64_t c_sm;         // row stride of C (columns contiguous)
+  int kchunks;          // BK-chunks per split
+  int a_vec, b_vec;     // 16-byte cp.async allowed
+};
+
+// Stage one operand tile: `rows` x BK where the operand's (row, k) element is
+// at base[row * s_row + k * s_k]; out-of-range elements are zero.  KFAST:
+// s_k == 1, shared layout [row][LDK]; else s_row == 1, layout [k][LDM].
+template <bool KFAST>
+__device__ __forceinline__ void stage_tile(double *dst, const double *__restrict__ base, int64_t s_row, int64_t s_k,
+                                           int row0, int nrows, int k0, int K, int vec, int tid) {
+  if (KFAST) {
+    // 64 rows x 16 k: 8 x 16-byte pieces per row
+    for (int idx = tid; idx < 64 * 8; idx += NT) {
+      int r = idx >> 3, kk = (idx & 7) * 2;
+      double *d = dst + r * LDK + kk;
+      int row = row0 + r, k = k0 + kk;
+      const double *s = base + (int64_t)row * s_row + k;
+      if (row < nrows && k + 1 < K && vec) cp16(d, s);
+      else {
+        d[0] = (row < nrows && k < K) ? s[0] : 0.0;
+        d[1] = (row < nrows && k + 1 < K) ? s[1] : 0.0;
+      }
+    }
+  } else {
+    // 16 k x 64 rows: 32 x 16-byte pieces per k
+    for (int idx = tid; idx < 16 * 32; idx += NT) {
+      int kk = idx >> 5, r = (idx & 31) * 2;
+      double *d = dst + kk * LDM + r;
+      int row = row0 + r, k = k0 + kk;
+      const double *s = base + (int64_t)k * s_k + row;
+      if (k < K && row + 1 < nrows && vec) cp16(d, s);
+      else {
+        d[0] = (k < K && row < nrows) ? s[0] : 0.0;
+        d[1] = (k < K && row + 1 < nrows) ? s[1] : 0.0;
+      }
+    }
+  }
+}
+
+template <bool A_KFAST, bool B_KFAST>
+__global__ void __launch_bounds__(NT) gemm_dmma_kernel(const __grid_constant__ GemmP p) {
+  extern __shared__ __align__(16) double smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wm = (warp & 1) * 32, wn = (warp >> 1) * 32;
+  const int fr = lane >> 2, fk = lane & 3;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int kbeg = blockIdx.z * p.kchunks * BK;
+  int kend = kbeg + p.kchunks * BK;
+  if (kend > p.K) kend = p.K;
+  const int nk = kend > kbeg ? (kend - kbeg + BK - 1) / BK : 0;
+
+  auto issue = [&](int c) {
+    double *as = smem + (c % STAGES) * 2 * TILE, *bs = as + TILE;
+    stage_tile<A_KFAST>(as, p.A, p.a_sm, p.a_sk, m0, p.M, kbeg + c * BK, kend, p.a_vec, tid);
+    stage_tile<B_KFAST>(bs, p.B, p.b_sn, p.b_sk, n0, p.N, kbeg + c * BK, kend, p.b_vec, tid);
+    cp_commit();
+  };
+  double acc[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  for (int c = 0; c < STAGES - 1; c++) {
+    if (c < nk) issue(c);
+    else cp_commit();
+  }
+  for (int c = 0; c < nk; c++) {
+    cp_wait<STAGES - 2>();
+    __syncthreads();
+    if (c + STAGES - 1 < nk) issue(c + STAGES - 1);
+    else cp_commit();
+    const double *as = smem + (c % STAGES) * 2 * TILE, *bs = as + TILE;
+#pragma unroll
+    for (int k4 = 0; k4 < BK; k4 += 4) {
+      double a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+        a[i] = A_KFAST ? as[(wm + i * 8 + fr) * LDK + k4 + fk] : as[(k4 + fk) * LDM + wm + i * 8 + fr];
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+        b[j] = B_KFAST ? bs[(wn + j * 8 + fr) * LDK + k4 + fk] : bs[(k4 + fk) * LDM + wn + j * 8 + fr];
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+  }
+  double *C = p.C + (int64_t)blockIdx.z * p.M * p.c_sm;
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      int m = m0 + wm + i * 8 + fr, n = n0 + wn + j * 8 + fk * 2;
+      if (m < p.M) {
+        double *c = C + (int64_t)m * p.c_sm + n;
+        if (n + 1 < p.N && (p.c_sm & 1) == 0 && ((uintptr_t)C & 15) == 0)
+          *reinterpret_cast<double2 *>(c) = make_double2(acc[i][j][0], acc[i][j][1]);
+        else {
+          if (n < p.N) c[0] = acc[i][j][0];
+          if (n + 1 < p.N) c[1] = acc[i][j][1];
+        }
+      }
+    }
+}
+
+__global__ void gemm_reduce_kernel(const double *__restrict__ part, double *__restrict__ out, int64_t n, int splits) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s = 0.0;
+  for (int k = 0; k < splits; k++) s += part[(int64_t)k * n + i];
+  out[i] = s;
+}
+
+}  // namespace
+
+// C (contiguous [M,N] f64) = A x B with element strides; *done = 1 if handled.
+int hb_gemm_dmma(const double *A, int64_t a_sm, int64_t a_sk, const double *B, int64_t b_sk, int64_t b_sn, double *C,
+                 int64_t M, int64_t N, int64_t K, int *done) {
+  *done = 0;
+  if (M <= 0 || N <= 0 || K <= 0) return HB_OK;
+  if (M >= (1ll << 31) || N >= (1ll << 31) || K >= (1ll << 31)) return HB_OK;
+  bool a_kfast = a_sk == 1, b_kfast = b_sk == 1;
+  if (!a_kfast && a_sm != 1) return HB_OK;
+  if (!b_kfast && b_sn != 1) return HB_OK;
+  // a size-1 axis may report any stride: prefer the k-fast reading when both are 1
+  GemmP p;
+  memset(&p, 0, sizeof p);
+  p.A = A; p.B = B;
+  p.M = (int)M; p.N = (int)N; p.K = (int)K;
+  p.a_sm = a_sm; p.a_sk = a_sk; p.b_sk = b_sk; p.b_sn = b_sn;
+  p.c_sm = N;
+  p.a_vec = ((uintptr_t)A & 15) == 0 && ((a_kfast ? a_sm : a_sk) % 2 == 0);
+  p.b_vec = ((uintptr_t)B & 15) == 0 && ((b_kfast ? b_sn : b_sk) % 2 == 0);
+  int gm = (int)((M + BM - 1) / BM), gn = (int)((N + BN - 1) / BN);
+  if (gn > 65535) return HB_OK;
+  int chunks = (int)((K + BK - 1) / BK);
+  int splits = 1;
+  int64_t tiles = (int64_t)gm * gn;
+  if (tiles < 2 * g_hb.sm_count) {
+    splits = (int)((3 * (int64_t)g_hb.sm_count + tiles - 1) / tiles);
+    if (splits > chunks / 4) splits = chunks / 4;   // at least 4 chunks (64 k) per split
+    if (splits < 1) splits = 1;
+    if (splits > 64) splits = 64;
+  }
+  p.kchunks = (chunks + splits - 1) / splits;
+  splits = (chunks + p.kchunks - 1) / p.kchunks;
+  if (splits > 1) {
+    void *scr;
+    HB_TRY(hb_scratch((size_t)splits * M * N * 8, &scr));
+    p.C = (double *)scr;
+  } else {
+    p.C = C;
+  }
+  dim3 grid((unsigned)gm, (unsigned)gn, (unsigned)splits);
+  size_t smem = (size_t)STAGES * 2 * TILE * 8;
+#define GEMM_LAUNCH(AK, BKF)                                                                              \
+  do {                                                                                                    \
+    HB_CUDA(cudaFuncSetAttribute(gemm_dmma_kernel<AK, BKF>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                 (int)smem));                                                             \
+    gemm_dmma_kernel<AK, BKF><<<grid, NT, smem, g_hb.stream>>>(p);                                        \
+  } while (0)
+  if (a_kfast && b_kfast) GEMM_LAUNCH(true, true);
+  else if (a_kfast) GEMM_LAUNCH(true, false);
+  else if (b_kfast) GEMM_LAUNCH(false, true);
+  else GEMM_LAUNCH(false, false);
+#undef GEMM_LAUNCH
+  HB_LAUNCHED();
+  if (splits > 1) {
+    int64_t n = M * N;
+    gemm_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, g_hb.stream>>>(p.C, C, n, splits);
+    HB_LAUNCHED();
+  }
+  *done = 1;
+  return HB_OK;
+}

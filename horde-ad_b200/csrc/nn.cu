@@ -5,6 +5,7 @@
 // softmax-cross-entropy loss (lossSoftMaxCrossEntropyS, :89-111).
 // All kernels are HBM-bound single passes.
 #include "common.cuh"
+#include "iter.cuh"
 
 // one thread per output window; value at the FIRST maximum of the row-major
 // flattened window (kargMax of the flattened slice); positions outside the
@@ -138,6 +139,225 @@ extern "C" int hb_maxpool2d_bwd(const hb_array *dy, const hb_array *argmax, int 
   hb_release(t2);
   if (st != HB_OK) { if (dx) hb_release(dx); return st; }
   *out = dx;
+  return HB_OK;
+}
+
+// ------------------------------------------- fused bias + relu + max-pool
+// The tail of convMnistLayerS (MnistCnnShaped2.hs:42-62) as ONE pass:
+//   yRelu = reluS (yConv + biasStretched);  yPool = maxPool2dUnpaddedS @k @k yRelu
+// for non-overlapping windows (ksize == stride, the CNN's 2x2/2).  The full-size
+// pre-activation is read once and never written back; what the adjoint needs
+// is one byte per pooled element:
+//   code = argmax within the window (row-major, first maximum, as kargMax)
+//          | 0x80 if the selected pre-activation is > 0 (the relu mask there).
+// relu is (x <= 0 ? 0 : 1) * x exactly as CommonShapedOps.hs:38-44 (so
+// negative inputs give -0.0 and ties resolve as in the unfused chain).
+template <typename T, bool VEC2>
+__global__ void __launch_bounds__(256)
+    hb_relu_pool_fwd_kernel(const T *__restrict__ pre, const T *__restrict__ bias, int C, int H, int W, int ks,
+                            int Ho, int Wo, int64_t total, T *__restrict__ y, uint8_t *__restrict__ code) {
+  int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t gs = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t o = gid; o < total; o += gs) {
+    int j = (int)(o % Wo);
+    int64_t t = o / Wo;
+    int i = (int)(t % Ho);
+    int64_t nc = t / Ho;
+    T b = bias ? bias[nc % C] : T(0);
+    const T *p = pre + (nc * H + (int64_t)i * ks) * W + (int64_t)j * ks;
+    T best = T(0), bestpre = T(0);
+    int bi = 0;
+    if (VEC2) {  // ks == 2, W even, 2-element aligned
+      typedef hb_vec<T, 2> V;
+      V r0 = *reinterpret_cast<const V *>(p), r1 = *reinterpret_cast<const V *>(p + W);
+      T v[4] = {r0.v[0] + b, r0.v[1] + b, r1.v[0] + b, r1.v[1] + b};
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        T r = (v[k] <= T(0) ? T(0) : T(1)) * v[k];
+        if (k == 0 || r > best) { best = r; bestpre = v[k]; bi = k; }
+      }
+    } else {
+      for (int a = 0; a < ks; a++)
+        for (int c = 0; c < ks; c++) {
+          T v = p[(int64_t)a * W + c] + b;
+          T r = (v <= T(0) ? T(0) : T(1)) * v;
+          if ((a == 0 && c == 0) || r > best) { best = r; bestpre = v; bi = a * ks + c; }
+        }
+    }
+    y[o] = best;
+    code[o] = (uint8_t)(bi | (bestpre > T(0) ? 0x80 : 0));
+  }
+}
+
+extern "C" int hb_relu_pool_fwd(const hb_array *pre, const hb_array *bias, int ksize, hb_array **out,
+                                hb_array **code_out) {
+  hb_prof_scope prof_("relu_pool_fwd", pre);
+  HB_CHECK_INIT();
+  HB_REQUIRE(pre && out && code_out, "null argument");
+  HB_REQUIRE(pre->rank == 4 && hb_is_float(pre->dt), "relu_pool: rank-4 floating input required");
+  HB_REQUIRE(ksize >= 1 && ksize <= 11, "relu_pool: window must be 1..11");
+  HB_REQUIRE(!bias || (bias->rank == 1 && bias->dt == pre->dt && bias->shape[0] == pre->shape[1]),
+             "relu_pool: bias must be [%lld]", (long long)pre->shape[1]);
+  const hb_array *pc = pre, *bc = bias;
+  hb_array *t1 = nullptr, *t2 = nullptr;
+  if (!hb_contig(pre)) { HB_TRY(hb_contiguous(pre, &t1)); pc = t1; }
+  if (bias && !hb_contig(bias)) {
+    int st = hb_contiguous(bias, &t2);
+    if (st != HB_OK) { hb_release(t1); return st; }
+    bc = t2;
+  }
+  int64_t H = pre->shape[2], W = pre->shape[3];
+  int64_t osh[4] = {pre->shape[0], pre->shape[1], H / ksize, W / ksize};
+  hb_array *y = nullptr, *code = nullptr;
+  int st = hb_new_array(pre->dt, 4, osh, &y);
+  if (st == HB_OK) st = hb_new_array(HB_I8, 4, osh, &code);
+  if (st == HB_OK) {
+    int64_t total = hb_numel(y);
+    if (total > 0) {
+      int blocks = hb_blocks_for(total, 256, g_hb.sm_count * 32);
+      size_t es = hb_dtype_size(pre->dt);
+      bool vec = ksize == 2 && W % 2 == 0 && ((uintptr_t)hb_data(pc) % (2 * es)) == 0;
+#define RP_LAUNCH(T, V)                                                                                           \
+  hb_relu_pool_fwd_kernel<T, V><<<blocks, 256, 0, g_hb.stream>>>(                                                 \
+      (const T *)hb_data(pc), bc ? (const T *)hb_data(bc) : nullptr, (int)pre->shape[1], (int)H, (int)W, ksize,    \
+      (int)osh[2], (int)osh[3], total, (T *)hb_data(y), (uint8_t *)hb_data(code))
+      if (pre->dt == HB_F64) { if (vec) RP_LAUNCH(double, true); else RP_LAUNCH(double, false); }
+      else { if (vec) RP_LAUNCH(float, true); else RP_LAUNCH(float, false); }
+#undef RP_LAUNCH
+      g_hb.launches.fetch_add(1);
+      if (g_hb.profiling) hb_prof_mark(__func__, __LINE__);
+      cudaError_t e = cudaPeekAtLastError();
+      if (e != cudaSuccess) { cudaGetLastError(); hb_set_error("relu_pool launch: %s", cudaGetErrorString(e)); st = HB_ERR_CUDA; }
+    }
+  }
+  hb_release(t1);
+  hb_release(t2);
+  if (st != HB_OK) { hb_release(y); hb_release(code); return st; }
+  *out = y;
+  *code_out = code;
+  return HB_OK;
+}
+
+// Adjoint: d_pre[window position] = dy if (position == argmax and relu active)
+// else 0 (maxpool scatter then mask, DeltaEval.hs:538-562 / :392-396), and the
+// bias cotangent  dbias[c] = sum_{n,i,j} of the same values, reduced per
+// (channel, image chunk) block in a fixed tree order, then over chunks in
+// order by hb_bias_finish_kernel: deterministic.
+template <typename T, bool VEC2>
+__global__ void __launch_bounds__(256)
+    hb_relu_pool_bwd_kernel(const T *__restrict__ dy, const uint8_t *__restrict__ code, int N, int C, int H, int W,
+                            int ks, int Ho, int Wo, int npc, T *__restrict__ dpre, T *__restrict__ part) {
+  __shared__ T sm[8];
+  const int c = blockIdx.x, chunk = blockIdx.y;
+  const int n0 = chunk * npc, n1 = n0 + npc < N ? n0 + npc : N;
+  const int HW = Ho * Wo;
+  const int64_t cnt = (int64_t)(n1 - n0) * HW;
+  T acc = T(0);
+  for (int64_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+    int n = n0 + (int)(i / HW), w = (int)(i % HW);
+    int wi = w / Wo, wj = w - wi * Wo;
+    int64_t o = ((int64_t)n * C + c) * HW + w;
+    uint8_t cd = code[o];
+    T g = (cd & 0x80) ? dy[o] : T(0);
+    acc += g;
+    int bi = cd & 0x7f;
+    T *p = dpre + (((int64_t)n * C + c) * H + (int64_t)wi * ks) * W + (int64_t)wj * ks;
+    if (VEC2) {
+      typedef hb_vec<T, 2> V;
+      V r0, r1;
+      r0.v[0] = bi == 0 ? g : T(0); r0.v[1] = bi == 1 ? g : T(0);
+      r1.v[0] = bi == 2 ? g : T(0); r1.v[1] = bi == 3 ? g : T(0);
+      *reinterpret_cast<V *>(p) = r0;
+      *reinterpret_cast<V *>(p + W) = r1;
+    } else {
+      for (int a = 0; a < ks; a++)
+        for (int b = 0; b < ks; b++) p[(int64_t)a * W + b] = (a * ks + b == bi) ? g : T(0);
+    }
+  }
+  acc = hb_warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    T s = sm[0];
+    for (int i = 1; i < (int)(blockDim.x >> 5); i++) s += sm[i];
+    part[(int64_t)c * gridDim.y + chunk] = s;
+  }
+}
+
+template <typename T>
+__global__ void hb_bias_finish_kernel(const T *__restrict__ part, int C, int nchunks, T *__restrict__ out) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  T s = T(0);
+  for (int k = 0; k < nchunks; k++) s += part[(int64_t)c * nchunks + k];
+  out[c] = s;
+}
+
+extern "C" int hb_relu_pool_bwd(const hb_array *dy, const hb_array *code, int ksize, int64_t H, int64_t W,
+                                hb_array **dpre_out, hb_array **dbias_out) {
+  hb_prof_scope prof_("relu_pool_bwd", dy);
+  HB_CHECK_INIT();
+  HB_REQUIRE(dy && code && dpre_out, "null argument");
+  HB_REQUIRE(dy->rank == 4 && hb_is_float(dy->dt) && code->dt == HB_I8 && hb_same_shape(dy, code),
+             "relu_pool_bwd: bad operands");
+  HB_REQUIRE(ksize >= 1 && ksize <= 11 && dy->shape[2] == H / ksize && dy->shape[3] == W / ksize,
+             "relu_pool_bwd: extents do not match");
+  const hb_array *dyc = dy, *cc = code;
+  hb_array *t1 = nullptr, *t2 = nullptr;
+  if (!hb_contig(dy)) { HB_TRY(hb_contiguous(dy, &t1)); dyc = t1; }
+  if (!hb_contig(code)) {
+    int st = hb_contiguous(code, &t2);
+    if (st != HB_OK) { hb_release(t1); return st; }
+    cc = t2;
+  }
+  int64_t N = dy->shape[0], C = dy->shape[1];
+  int64_t xsh[4] = {N, C, H, W};
+  hb_array *dx = nullptr, *db = nullptr;
+  int st = hb_new_array(dy->dt, 4, xsh, &dx);
+  if (st == HB_OK) st = hb_new_array(dy->dt, 1, &C, &db);
+  if (st == HB_OK && hb_numel(dx) > 0) {
+    size_t es = hb_dtype_size(dy->dt);
+    bool leftover = (H % ksize) || (W % ksize);
+    if (leftover) {
+      cudaError_t e = cudaMemsetAsync(hb_data(dx), 0, (size_t)hb_numel(dx) * es, g_hb.stream);
+      if (e != cudaSuccess) { hb_set_error("memset: %s", cudaGetErrorString(e)); st = HB_ERR_CUDA; }
+    }
+    int nchunks = (int)((4 * (int64_t)g_hb.sm_count + C - 1) / C);
+    if (nchunks > N) nchunks = (int)N;
+    if (nchunks < 1) nchunks = 1;
+    int npc = (int)((N + nchunks - 1) / nchunks);
+    nchunks = (int)((N + npc - 1) / npc);
+    void *scr = nullptr;
+    if (st == HB_OK) st = hb_scratch((size_t)C * nchunks * es, &scr);
+    if (st == HB_OK && hb_numel(dy) > 0) {
+      bool vec = ksize == 2 && W % 2 == 0 && ((uintptr_t)hb_data(dx) % (2 * es)) == 0;
+      dim3 grid((unsigned)C, (unsigned)nchunks);
+#define RPB_LAUNCH(T, V)                                                                                    \
+  hb_relu_pool_bwd_kernel<T, V><<<grid, 256, 0, g_hb.stream>>>(                                             \
+      (const T *)hb_data(dyc), (const uint8_t *)hb_data(cc), (int)N, (int)C, (int)H, (int)W, ksize,         \
+      (int)dy->shape[2], (int)dy->shape[3], npc, (T *)hb_data(dx), (T *)scr)
+      if (dy->dt == HB_F64) { if (vec) RPB_LAUNCH(double, true); else RPB_LAUNCH(double, false); }
+      else { if (vec) RPB_LAUNCH(float, true); else RPB_LAUNCH(float, false); }
+#undef RPB_LAUNCH
+      g_hb.launches.fetch_add(1);
+      if (g_hb.profiling) hb_prof_mark(__func__, __LINE__);
+      if (dy->dt == HB_F64)
+        hb_bias_finish_kernel<double><<<(unsigned)((C + 127) / 128), 128, 0, g_hb.stream>>>((const double *)scr, (int)C, nchunks, (double *)hb_data(db));
+      else
+        hb_bias_finish_kernel<float><<<(unsigned)((C + 127) / 128), 128, 0, g_hb.stream>>>((const float *)scr, (int)C, nchunks, (float *)hb_data(db));
+      g_hb.launches.fetch_add(1);
+      if (g_hb.profiling) hb_prof_mark(__func__, __LINE__);
+      cudaError_t e = cudaPeekAtLastError();
+      if (e != cudaSuccess) { cudaGetLastError(); hb_set_error("relu_pool_bwd launch: %s", cudaGetErrorString(e)); st = HB_ERR_CUDA; }
+    } else if (st == HB_OK && C > 0) {
+      cudaMemsetAsync(hb_data(db), 0, (size_t)C * es, g_hb.stream);
+    }
+  }
+  hb_release(t1);
+  hb_release(t2);
+  if (st != HB_OK) { hb_release(dx); hb_release(db); return st; }
+  *dpre_out = dx;
+  if (dbias_out) *dbias_out = db; else hb_release(db);
   return HB_OK;
 }
 

@@ -378,6 +378,16 @@ class DeviceBackend:
         call("hb_maxpool2d_bwd", dy.h, am.h, ksize, stride, H, W, C.byref(p))
         return _wrap(p)
 
+    def relu_pool_fwd(self, pre, bias, ksize):
+        y, code = _out(), _out()
+        call("hb_relu_pool_fwd", pre.h, bias.h if bias is not None else None, ksize, C.byref(y), C.byref(code))
+        return _wrap(y), _wrap(code)
+
+    def relu_pool_bwd(self, dy, code, ksize, H, W, want_bias=True):
+        dp, db = _out(), _out()
+        call("hb_relu_pool_bwd", dy.h, code.h, ksize, H, W, C.byref(dp), C.byref(db) if want_bias else None)
+        return _wrap(dp), (_wrap(db) if want_bias else None)
+
     def softmax_xent(self, logits, expected, scale=1.0, want_grad=True):
         l, d = _out(), _out()
         call("hb_softmax_xent", logits.h, expected.h, float(scale), C.byref(l),

@@ -2,9 +2,11 @@
 method surface, plus the training step the benches time.
 
 `convMnistTwoS` / `convMnistLossFusedS` follow the reference definitions line
-by line (MnistCnnShaped2.hs:42-136).  `fused=True` selects the nodes a device
-contraction pass emits (conv / relu / maxpool as single C-ABI calls),
-`fused=False` the vectorised gather programs the stock pipeline produces.
+by line (MnistCnnShaped2.hs:42-136).  `fused=True` ("layer") selects the coarsest
+nodes a device contraction pass emits (a whole conv layer: conv, then one
+fused bias + relu + max-pool pass), `fused="nodes"` conv / relu / maxpool as
+single C-ABI calls each, `fused=False` the vectorised gather programs the
+stock pipeline produces.
 """
 from __future__ import annotations
 
@@ -39,6 +41,8 @@ def init_params(kh, kw, c_out, n_hidden, seed=44, rng_range=0.4, dtype=np.float6
 def convMnistLayerS(T, ker, x, bias, fused=True):
     """convMnistLayerS (MnistCnnShaped2.hs:42-62)."""
     N, _, H, W = T.shape(x)
+    if fused is True or fused == "layer":     # the whole layer as one contraction-pass node
+        return nn.convReluPoolS(T, ker, bias, x, 2)
     yConv = (nn.conv2dPreservingS if fused else nn.conv2dPreservingS_vectorised)(T, ker, x)
     biasStretched = T.stranspose([0, 3, 1, 2], T.sreplicateN([N, H, W], bias))
     pre = T.binary("add", yConv, biasStretched)

@@ -76,6 +76,14 @@ def conv2dPreservingS_vectorised(T, K, A):
     return T.sdot1InSumN(p, k, 2) if hasattr(T, "sdot1InSumN") else T.ssumN(T.sdot1In(p, k), 2)
 
 
+def convReluPoolS(T, K, bias, A, ksize):
+    """convMnistLayerS (MnistCnnShaped2.hs:42-62) as one node: maxPool (relu
+    (conv2dPreserving K A + bias)) with ksize == stride."""
+    if hasattr(T, "conv_relu_pool"):
+        return T.conv_relu_pool(K, bias, A, ksize)
+    return T.relu_pool_fwd(T.conv2dPreserving(K, A), bias, ksize)[0]
+
+
 # --------------------------------------------------------------- maxpool
 def maxPool2dUnpaddedS(T, ksize, stride, x):
     """maxPool2dUnpaddedS (CommonShapedOps.hs:241-260), fused."""

@@ -108,6 +108,7 @@ class CnnTrainer:
 
     def _capture(self):
         # run once eagerly so every size class and the scratch buffer exist
+        # (and NCCL has set up its channels before the all-reduce is captured)
         b = self._gradient_program()
         self.dev.sync()
         del b

@@ -359,6 +359,20 @@ int hb_maxpool2d(const hb_array *x, int ksize, int stride, hb_array **out,
  * accumulating deterministically where windows overlap. */
 int hb_maxpool2d_bwd(const hb_array *dy, const hb_array *argmax, int ksize,
                      int stride, int64_t H, int64_t W, hb_array **out);
+/* The tail of convMnistLayerS (MnistCnnShaped2.hs:42-62) in one pass, for
+ * non-overlapping windows (ksize == stride):
+ *   out = maxPool2dUnpaddedS @k @k (reluS (pre + bias stretched over [N,.,H,W]))
+ * `code` (I8, shape of out) is what the adjoint needs: argmax within the window
+ * (row-major, first maximum) | 0x80 when the selected pre-activation is > 0.
+ * bias may be NULL. */
+int hb_relu_pool_fwd(const hb_array *pre, const hb_array *bias, int ksize,
+                     hb_array **out, hb_array **code_out);
+/* Its adjoint: d_pre [N,C,H,W] (dy routed to the argmax where relu is active,
+ * zero elsewhere) and, optionally, dbias[c] = sum over n, h, w of d_pre
+ * (deterministic two-stage reduction). */
+int hb_relu_pool_bwd(const hb_array *dy, const hb_array *code, int ksize,
+                     int64_t H, int64_t W, hb_array **dpre_out,
+                     hb_array **dbias_out /* may be NULL */);
 /* lossSoftMaxCrossEntropyS (CommonShapedOps.hs:89-111) over the WHOLE tensor
  * (the reference normalises over all elements), scaled by `scale`:
  *   loss = scale * -(log softmax . expected);  dlogits = scale*(softmax-expected).

@@ -394,6 +394,26 @@ class ConcreteBackend:
                 np.add.at(dx, (n_idx, c_idx, yy[ok], xx[ok]), dy[:, :, i, j][ok])
         return dx
 
+    # the tail of convMnistLayerS (MnistCnnShaped2.hs:42-62) for ksize == stride,
+    # composed from the oracle's own bias add, reluS and maxPool2dUnpaddedS
+    def relu_pool_fwd(self, pre, bias, ksize):
+        pre = np.asarray(pre)
+        v = pre if bias is None else pre + np.asarray(bias).reshape(1, -1, 1, 1)
+        y, am = self.maxpool2d(self.relu(v), ksize, ksize)
+        N, Cc, Ho, Wo = y.shape
+        win = np.stack([v[:, :, a:a + Ho * ksize:ksize, b:b + Wo * ksize:ksize][:, :, :Ho, :Wo]
+                        for a in range(ksize) for b in range(ksize)], axis=-1)
+        sel = np.take_along_axis(win, am[..., None], axis=-1)[..., 0]
+        code = (am | np.where(sel > 0, 0x80, 0)).astype(np.uint8).view(np.int8)
+        return y, code
+
+    def relu_pool_bwd(self, dy, code, ksize, H, W, want_bias=True):
+        code = np.asarray(code).view(np.uint8)
+        am = (code & 0x7f).astype(np.int64)
+        g = np.where(code & 0x80, dy, np.zeros_like(dy))
+        dpre = self.maxpool2d_bwd(g, am, ksize, ksize, H, W)
+        return dpre, (np.sum(dpre, axis=(0, 2, 3)) if want_bias else None)
+
     # lossSoftMaxCrossEntropyS (CommonShapedOps.hs:89-111): normalises over the
     # WHOLE tensor; dual = (softMax - expected) * du
     def softmax_xent(self, logits, expected, scale=1.0, want_grad=True):

@@ -217,11 +217,18 @@ def test_bias_gradient_shapes(dev, oracle):
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 def test_matmul_family(dev, oracle, dtype):
     rng = np.random.default_rng(9)
-    for (m, k, n) in [(64, 784, 70), (10, 64, 33), (1, 5, 1), (130, 17, 129), (3, 1, 4)]:
+    for (m, k, n) in [(64, 784, 70), (10, 64, 33), (1, 5, 1), (130, 17, 129), (3, 1, 4), (64, 4099, 784),
+                      (512, 512, 300), (65, 333, 63), (17, 2000, 19)]:
         a, b = rnd(rng, (m, k), dtype), rnd(rng, (k, n), dtype)
         ref = (a.astype(np.float64) @ b.astype(np.float64)).astype(dtype)
         close(dev.to_numpy(dev.smatmul2(dev.sconcrete(a), dev.sconcrete(b))), ref, dtype, scale=50)
         close(dev.to_numpy(dev.smatmul2(dev.stranspose([1, 0], dev.sconcrete(a.T.copy())), dev.sconcrete(b))), ref, dtype, scale=50)
+        # every operand orientation (the four cp.async staging layouts of the DMMA GEMM) and odd offsets
+        bt = dev.stranspose([1, 0], dev.sconcrete(b.T.copy()))
+        close(dev.to_numpy(dev.smatmul2(dev.sconcrete(a), bt)), ref, dtype, scale=50)
+        close(dev.to_numpy(dev.smatmul2(dev.stranspose([1, 0], dev.sconcrete(a.T.copy())), bt)), ref, dtype, scale=50)
+        if m > 2:
+            close(dev.to_numpy(dev.smatmul2(dev.sslice(1, m - 1, dev.sconcrete(a)), dev.sconcrete(b))), ref[1:], dtype, scale=50)
         v = rnd(rng, (k,), dtype)
         close(dev.to_numpy(dev.smatvecmul(dev.sconcrete(a), dev.sconcrete(v))),
               (a.astype(np.float64) @ v.astype(np.float64)).astype(dtype), dtype, scale=50)
@@ -406,6 +413,35 @@ def test_nn_blocks(dev, oracle, dtype):
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("shape,ks", [((5, 3, 10, 12), 2), ((3, 4, 9, 11), 2), ((2, 2, 9, 10), 3), ((130, 16, 28, 28), 2),
+                                      ((2, 3, 4, 4), 1)])
+def test_fused_relu_pool(dev, oracle, dtype, shape, ks):
+    """hb_relu_pool_fwd/bwd == reluS . (+bias) then maxPool2dUnpaddedS and their
+    adjoints (bit-exact forward incl. ties and -0.0; cotangents exact, bias
+    cotangent to reduction tolerance)."""
+    rng = np.random.default_rng(21)
+    pre, bias = rnd(rng, shape, dtype), rnd(rng, (shape[1],), dtype)
+    pre[0, 0, :2, :2] = 0.25 - bias[0]
+    pre[0, 1, :2, :2] = -1.0          # an all-inactive window
+    y, code = dev.relu_pool_fwd(dev.sconcrete(pre), dev.sconcrete(bias), ks)
+    ry, rcode = oracle.relu_pool_fwd(pre, bias, ks)
+    exact(dev.to_numpy(y), ry.astype(dtype))
+    exact(dev.to_numpy(code), rcode)
+    # the same through the unfused device chain
+    N, Cc, H, W = shape
+    stretched = dev.stranspose([0, 3, 1, 2], dev.sreplicateN([N, H, W], dev.sconcrete(bias)))
+    chain, _ = dev.maxpool2d(dev.relu(dev.binary("add", dev.sconcrete(pre), stretched)), ks, ks)
+    exact(dev.to_numpy(y), dev.to_numpy(chain))
+    dy = rnd(rng, ry.shape, dtype)
+    dp, db = dev.relu_pool_bwd(dev.sconcrete(dy), code, ks, H, W)
+    rdp, rdb = oracle.relu_pool_bwd(dy, rcode, ks, H, W)
+    exact(dev.to_numpy(dp), rdp.astype(dtype))
+    close(dev.to_numpy(db), rdb.astype(dtype), dtype, scale=100)
+    y2, _ = dev.relu_pool_fwd(dev.sconcrete(pre), None, ks)
+    exact(dev.to_numpy(y2), oracle.relu_pool_fwd(pre, None, ks)[0].astype(dtype))
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
 def test_optimizers(dev, oracle, dtype):
     rng = np.random.default_rng(18)
     p, g = rnd(rng, (1000,), dtype), rnd(rng, (1000,), dtype)
@@ -444,7 +480,7 @@ def test_prod_fold(dev, oracle):
 
 
 # ------------------------------------------------------------- whole model
-@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("fused", [True, "nodes", False])
 def test_mnist_cnn_gradient_vs_oracle(dev, oracle, fused):
     """MnistCnnShaped2 loss and all 8 gradient leaves, device vs oracle, both
     through the same dual-number pipeline (cgrad)."""

@@ -83,3 +83,22 @@ def test_vectorised_blocks_match_fused(oracle):
     lg, ex = rng.uniform(-1, 1, (10, 5)), np.eye(10)[:, :5]
     np.testing.assert_allclose(nn.lossSoftMaxCrossEntropyS_vectorised(oracle, ex, lg, 0.2),
                                nn.lossSoftMaxCrossEntropyS(oracle, ex, lg, 0.2), rtol=1e-14)
+
+
+@pytest.mark.parametrize("fused", [True, "nodes"])
+def test_cnn_fusion_levels_agree_on_the_oracle(oracle, fused):
+    """The layer-level node, the per-op nodes and the vectorised gather program
+    are the same function (loss and all 8 gradient leaves)."""
+    from horde_ad_b200 import mnist_cnn
+    rng = np.random.Generator(np.random.Philox(5))
+    batch, hyper = 3, (1, 2, 3, 4)
+    params = mnist_cnn.init_params(*hyper)
+    glyphs, labels = rng.uniform(0, 1, (batch, 28, 28)), np.eye(10)[rng.integers(0, 10, batch)]
+
+    def run(f):
+        return ad.grad(oracle, lambda T, *ps: mnist_cnn.convMnistLossFusedS(T, glyphs, labels, list(ps), fused=f), params)
+    v0, g0 = run(False)
+    v1, g1 = run(fused)
+    np.testing.assert_allclose(float(v1), float(v0), rtol=1e-13)
+    for a, b in zip(g1, g0):
+        np.testing.assert_allclose(np.asarray(a), np.asarray(b), rtol=1e-10, atol=1e-14)
