@@ -34,9 +34,9 @@ constexpr int kSmemMax = 227 * 1024;
 constexpr int kThreads = 256;
 
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-               : "+d"(c0), "+d"(c1)
-               : "d"(a), "d"(b));
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+      : "+d"(c0), "+d"(c1)
+      : "d"(a), "d"(b));
 }
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cp16(void *s, const void *g) {
@@ -60,29 +60,39 @@ struct TileGeo {
   int oy, ox;  // tile row t holds input row y0+oy+t; input col x sits at tile col x-ox
   int bands;   // ceil(H / R)
   int vec;     // rows may be moved in 16-byte pieces
+  int cpr, cshift;  // pieces per row and log2 of its power-of-two padding
 };
 
-// channels [c0, c0+CC) of images [n0, n0+NI), input rows of band y0 -> dst
+// channels [c0, c0+CC) of images [n0, n0+NI), input rows of band y0 -> dst.
+// A warp owns whole (channel, image) planes; its lanes cover (row, piece) with
+// the pieces per row padded to a power of two, so the hot loop has no integer
+// division (one per plane).
 __device__ __forceinline__ void load_in_tile(double *dst, const double *__restrict__ in, const TileGeo &g, int CC,
                                              int c0, int P, int n0, int N, int y0, int64_t sn, int64_t sp,
                                              int tid) {
-  const int cpr = g.vec ? (g.W >> 1) : g.W;
-  const int rpc = g.NI * g.TR;
-  const int total = CC * rpc * cpr;
-  for (int idx = tid; idx < total; idx += kThreads) {
-    int row = idx / cpr, ch = idx - row * cpr;
-    int c = row / rpc, r2 = row - c * rpc;
-    int img = r2 / g.TR, t = r2 - img * g.TR;
-    int y = y0 + g.oy + t, n = n0 + img, cg = c0 + c;
-    double *d = dst + c * g.CS + img * g.IS + t * g.RS - g.ox;
-    bool ok = cg < P && n < N && y >= 0 && y < g.H;
-    const double *s = in + n * sn + cg * sp + (int64_t)y * g.W;
-    if (g.vec) {
-      if (ok) cp16(d + 2 * ch, s + 2 * ch);
-      else *reinterpret_cast<double2 *>(d + 2 * ch) = make_double2(0.0, 0.0);
-    } else {
-      if (ok) cp8(d + ch, s + ch);
-      else d[ch] = 0.0;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int planes = CC * g.NI;
+  const int slots = g.TR << g.cshift, cmask = (1 << g.cshift) - 1;
+  for (int pl = warp; pl < planes; pl += kThreads / 32) {
+    int c = pl / g.NI, img = pl - c * g.NI;
+    int n = n0 + img, cg = c0 + c;
+    bool okp = cg < P && n < N;
+    double *d0 = dst + c * g.CS + img * g.IS - g.ox;
+    const double *s0 = in + n * sn + cg * sp + (int64_t)(y0 + g.oy) * g.W;
+    for (int sl = lane; sl < slots; sl += 32) {
+      int t = sl >> g.cshift, ch = sl & cmask;
+      if (ch >= g.cpr) continue;
+      int y = y0 + g.oy + t;
+      bool ok = okp && y >= 0 && y < g.H;
+      if (g.vec) {
+        double *d = d0 + t * g.RS + 2 * ch;
+        if (ok) cp16(d, s0 + t * g.W + 2 * ch);
+        else *reinterpret_cast<double2 *>(d) = make_double2(0.0, 0.0);
+      } else {
+        double *d = d0 + t * g.RS + ch;
+        if (ok) cp8(d, s0 + t * g.W + ch);
+        else *d = 0.0;
+      }
     }
   }
 }
@@ -110,9 +120,9 @@ struct SpP {
 // Packs K into Wt[qt][p][tap][q] (tap stride TS, channel stride WCS), zero
 // padded in p, q and (TAPK) kw.  flip: dInp (Wt[p=o][i',j'][q=c] =
 // K[o,c,KH-1-i',KW-1-j']); else forward (Wt[p=c][i,j][q=o] = K[o,c,i,j]).
-__global__ void pack_sp_weights(const double *__restrict__ K, double *__restrict__ wp, int Co, int Ci, int KH, int KW,
-                                int KWe, int P, int Q, int Ppad, int QT, int TS, int WCS, int nqt, int flip,
-                                int64_t k_so, int64_t k_sc, int64_t k_si, int64_t k_sj) {
+__global__ void pack_sp_weights(const double *__restrict__ K, double *__restrict__ wp, int KH, int KW, int KWe, int P,
+                                int Q, int Ppad, int QT, int TS, int WCS, int nqt, int flip, int64_t k_so,
+                                int64_t k_sc, int64_t k_si, int64_t k_sj) {
   int64_t total = (int64_t)nqt * Ppad * WCS;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
@@ -131,8 +141,8 @@ __global__ void pack_sp_weights(const double *__restrict__ K, double *__restrict
   }
 }
 
-template <int WM, int WN, int MF, int NQ, bool TAPK>
-__global__ void __launch_bounds__(kThreads, 1) conv_sp_kernel(const __grid_constant__ SpP p) {
+template <int WM, int WN, int MF, int NQ, bool TAPK, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) conv_sp_kernel(const __grid_constant__ SpP p) {
   extern __shared__ __align__(16) double smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wm = warp % WM, wn = warp / WM;
@@ -142,22 +152,28 @@ __global__ void __launch_bounds__(kThreads, 1) conv_sp_kernel(const __grid_const
   for (int i = tid; i < 2 * p.stage_doubles; i += kThreads) smem[i] = 0.0;
   __syncthreads();
 
-  const int RW = g.R * g.W, npos = g.NI * RW;
+  const int RW = g.R * g.W, npos = g.NI * RW, HW = g.H * g.W;
   const int F = (npos + 7) >> 3;
   // fragment f = i * WM + wm (strided over the warps of a column: balanced)
   int nf = (F - wm + WM - 1) / WM;
   nf = nf < 0 ? 0 : (nf > MF ? MF : nf);
-  int mbase[MF];
+  // per fragment: byte offset of this lane's A element inside a stage (k part
+  // included), the output offset relative to the item's base, and (img, y)
+  int aoff[MF], orel[MF], pimy[MF];
 #pragma unroll
   for (int i = 0; i < MF; i++) {
     int pidx = (i * WM + wm) * 8 + fr;
-    int off = 0;
+    int off = 0, o = 0, iy = 0x7fff0000;
     if (pidx < npos) {
       int img = pidx / RW, rem = pidx - img * RW;
       int y = rem / g.W, x = rem - y * g.W;
       off = img * g.IS + y * g.RS + x;
+      o = img * p.Q * HW + y * g.W + x;
+      iy = (img << 16) | y;
     }
-    mbase[i] = off;
+    aoff[i] = (off + (TAPK ? fk : fk * g.CS)) * 8;
+    orel[i] = o;
+    pimy[i] = iy;
   }
   double acc[MF][NQ][2];
 #pragma unroll
@@ -169,6 +185,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_sp_kernel(const __grid_const
   const int my_items = (p.items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int T = my_items * p.NCH;
   const double *wbase = p.wp + (int64_t)qt * p.Ppad * p.WCS;
+  // this lane's B element inside a stage's weight block (k part included), bytes
+  const int woff = (p.in_doubles + wn * NQ * 8 + fr + (TAPK ? fk * p.TS : fk * p.WCS)) * 8;
 
   auto issue = [&](int t) {
     int it = blockIdx.x + (t / p.NCH) * gridDim.x, ch = t % p.NCH;
@@ -188,48 +206,51 @@ __global__ void __launch_bounds__(kThreads, 1) conv_sp_kernel(const __grid_const
       cp_wait<0>();
     }
     __syncthreads();
-    const double *Is = smem + (t & 1) * p.stage_doubles;
-    const double *Ws = Is + p.in_doubles + wn * NQ * 8 + fr;
+    const char *Sb = reinterpret_cast<const char *>(smem + (t & 1) * p.stage_doubles);
+    const char *Wb = Sb + woff;
     if (TAPK) {
       const int ng = p.KWP >> 2;
       for (int c = 0; c < p.CC; c++) {
         for (int kh = 0; kh < g.KH; kh++) {
+          const char *ia = Sb + (c * g.CS + kh * g.RS) * 8;
+          const char *wb = Wb + (c * p.WCS + kh * p.KWP * p.TS) * 8;
           for (int g4 = 0; g4 < ng; g4++) {
-            const double *ia = Is + c * g.CS + kh * g.RS + g4 * 4 + fk;
-            const double *wb = Ws + c * p.WCS + (kh * p.KWP + g4 * 4 + fk) * p.TS;
             double b[NQ];
 #pragma unroll
-            for (int j = 0; j < NQ; j++) b[j] = wb[j * 8];
+            for (int j = 0; j < NQ; j++) b[j] = *reinterpret_cast<const double *>(wb + j * 64);
 #pragma unroll
             for (int i = 0; i < MF; i++) {
               if (i < nf) {
-                double a = ia[mbase[i]];
+                double a = *reinterpret_cast<const double *>(ia + aoff[i]);
 #pragma unroll
                 for (int j = 0; j < NQ; j++) dmma884(acc[i][j][0], acc[i][j][1], a, b[j]);
               }
             }
+            ia += 32;
+            wb += 4 * p.TS * 8;
           }
         }
       }
     } else {
+      const int tsb = p.TS * 8;
       for (int c4 = 0; c4 < p.CC; c4 += 4) {
-        const double *ic = Is + (c4 + fk) * g.CS;
-        const double *wc = Ws + (c4 + fk) * p.WCS;
+        const char *wb = Wb + c4 * p.WCS * 8;
         for (int kh = 0; kh < g.KH; kh++) {
+          const char *ia = Sb + (c4 * g.CS + kh * g.RS) * 8;
           for (int kw = 0; kw < g.KW; kw++) {
-            const double *ia = ic + kh * g.RS + kw;
-            const double *wb = wc + (kh * g.KW + kw) * p.TS;
             double b[NQ];
 #pragma unroll
-            for (int j = 0; j < NQ; j++) b[j] = wb[j * 8];
+            for (int j = 0; j < NQ; j++) b[j] = *reinterpret_cast<const double *>(wb + j * 64);
 #pragma unroll
             for (int i = 0; i < MF; i++) {
               if (i < nf) {
-                double a = ia[mbase[i]];
+                double a = *reinterpret_cast<const double *>(ia + aoff[i]);
 #pragma unroll
                 for (int j = 0; j < NQ; j++) dmma884(acc[i][j][0], acc[i][j][1], a, b[j]);
               }
             }
+            ia += 8;
+            wb += tsb;
           }
         }
       }
@@ -238,21 +259,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_sp_kernel(const __grid_const
       // epilogue of this item: C fragment row = position, cols = 2 output channels
       int it = blockIdx.x + (t / p.NCH) * gridDim.x;
       int nblk = it / g.bands, band = it - nblk * g.bands;
-      int y0 = band * g.R;
+      int n0 = nblk * g.NI, y0 = band * g.R;
+      double *ob = p.out + ((int64_t)n0 * p.Q + qt * p.QT + wn * NQ * 8 + fk * 2) * HW + (int64_t)y0 * g.W;
+      const int q0 = qt * p.QT + wn * NQ * 8 + fk * 2;
 #pragma unroll
       for (int i = 0; i < MF; i++) {
         if (i < nf) {
-          int pidx = (i * WM + wm) * 8 + fr;
-          int img = pidx / RW, rem = pidx - img * RW;
-          int y = rem / g.W, x = rem - y * g.W;
-          int n = nblk * g.NI + img, yy = y0 + y;
-          bool okp = pidx < npos && n < p.N && yy < g.H;
+          int img = pimy[i] >> 16, y = pimy[i] & 0xffff;
+          bool okp = n0 + img < p.N && y0 + y < g.H;
 #pragma unroll
           for (int j = 0; j < NQ; j++) {
 #pragma unroll
             for (int e = 0; e < 2; e++) {
-              int q = qt * p.QT + wn * NQ * 8 + j * 8 + fk * 2 + e;
-              if (okp && q < p.Q) p.out[(((int64_t)n * p.Q + q) * g.H + yy) * g.W + x] = acc[i][j][e];
+              if (okp && q0 + j * 8 + e < p.Q) ob[orel[i] + (int64_t)(j * 8 + e) * HW] = acc[i][j][e];
               acc[i][j][e] = 0.0;
             }
           }
@@ -266,7 +285,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_sp_kernel(const __grid_const
 // ================================================================== dKrn
 struct DkP {
   const double *A, *dB;
-  double *part;  // [split * WK + wk][Co][Ci][KH][KW]
+  double *part;  // [split][Co][Ci][KH][KW]
   TileGeo g;
   int N, Ci, Co;
   int CC;          // input channels per CTA (gridDim.y chunks)
@@ -276,7 +295,6 @@ struct DkP {
   int PS, npos4;   // dB tile row stride; positions rounded up to 4
   int items;
   int a_doubles, stage_doubles;
-  int lut_off;     // ints, after the two stages
   int64_t a_sn, a_sc, b_sn, b_so;
   int dbvec;
 };
@@ -284,7 +302,7 @@ struct DkP {
 constexpr int kNP = 9;  // max column pairs per warp
 
 template <int WM, int MO, bool TAPW>
-__global__ void __launch_bounds__(kThreads, 1) conv_dk_kernel(const __grid_constant__ DkP p) {
+__global__ void __launch_bounds__(kThreads, 2) conv_dk_kernel(const __grid_constant__ DkP p) {
   extern __shared__ __align__(16) double smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wm = warp % WM, wn = (warp / WM) % p.WN, wk = warp / (WM * p.WN);
@@ -301,11 +319,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_dk_kernel(const __grid_const
       int y = rem / g.W, x = rem - y * g.W;
       off = img * g.IS + y * g.RS + x;
     }
-    lut[i] = off;
+    lut[i] = off * 8;  // bytes
   }
   __syncthreads();
 
-  // column pairs of this warp
+  // column pairs of this warp (byte offsets into the A tile)
   const int c0 = blockIdx.y * p.CC;
   int pair_off[kNP];
   int npw = p.npairs - wn * p.NPW;
@@ -324,7 +342,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_dk_kernel(const __grid_const
         off = (cf * 8 + fr) * g.CS + kh * g.RS + kw;
       }
     }
-    pair_off[j] = off;
+    pair_off[j] = off * 8;
   }
   double acc[MO][kNP][2];
 #pragma unroll
@@ -334,6 +352,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_dk_kernel(const __grid_const
 
   const int o_tile = blockIdx.z * (WM * MO * 8);
   const int T = (p.items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int co = p.Co - o_tile < WM * MO * 8 ? p.Co - o_tile : WM * MO * 8;
 
   auto issue = [&](int t) {
     int it = blockIdx.x + t * gridDim.x;
@@ -341,30 +360,27 @@ __global__ void __launch_bounds__(kThreads, 1) conv_dk_kernel(const __grid_const
     int n0 = nblk * g.NI, y0 = band * g.R;
     double *st = smem + (t & 1) * p.stage_doubles;
     load_in_tile(st, p.A, g, p.CC, c0, p.Ci, n0, p.N, y0, p.a_sn, p.a_sc, tid);
-    // dB tile: [o][img * RW + y * W + x], rows beyond the image zero
+    // dB tile: [o][img * RW + y * W + x], rows beyond the image zero; a warp
+    // owns whole (o, img) planes, lanes run along the contiguous positions
     double *db = st + p.a_doubles;
     int rows_ok = g.H - y0 < g.R ? g.H - y0 : g.R;
     int nval = rows_ok * g.W;
-    int co = p.Co - o_tile < WM * MO * 8 ? p.Co - o_tile : WM * MO * 8;
-    if (p.dbvec) {
-      int cpr = RW >> 1, total = co * g.NI * cpr;
-      for (int idx = tid; idx < total; idx += kThreads) {
-        int r = idx / cpr, ch = idx - r * cpr;
-        int o = r / g.NI, img = r - o * g.NI;
-        double *d = db + o * p.PS + img * RW + 2 * ch;
-        if (n0 + img < p.N && 2 * ch < nval)
-          cp16(d, p.dB + (n0 + img) * p.b_sn + (o_tile + o) * p.b_so + (int64_t)y0 * g.W + 2 * ch);
-        else *reinterpret_cast<double2 *>(d) = make_double2(0.0, 0.0);
-      }
-    } else {
-      int total = co * g.NI * RW;
-      for (int idx = tid; idx < total; idx += kThreads) {
-        int r = idx / RW, ch = idx - r * RW;
-        int o = r / g.NI, img = r - o * g.NI;
-        double *d = db + o * p.PS + img * RW + ch;
-        if (n0 + img < p.N && ch < nval)
-          cp8(d, p.dB + (n0 + img) * p.b_sn + (o_tile + o) * p.b_so + (int64_t)y0 * g.W + ch);
-        else *d = 0.0;
+    const int planes = co * g.NI;
+    for (int pl = warp; pl < planes; pl += kThreads / 32) {
+      int o = pl / g.NI, img = pl - o * g.NI;
+      double *d0 = db + o * p.PS + img * RW;
+      bool okn = n0 + img < p.N;
+      const double *s0 = p.dB + (n0 + img) * p.b_sn + (o_tile + o) * p.b_so + (int64_t)y0 * g.W;
+      if (p.dbvec) {
+        for (int ch = lane * 2; ch < RW; ch += 64) {
+          if (okn && ch < nval) cp16(d0 + ch, s0 + ch);
+          else *reinterpret_cast<double2 *>(d0 + ch) = make_double2(0.0, 0.0);
+        }
+      } else {
+        for (int ch = lane; ch < RW; ch += 32) {
+          if (okn && ch < nval) cp8(d0 + ch, s0 + ch);
+          else d0[ch] = 0.0;
+        }
       }
     }
     cp_commit();
@@ -379,17 +395,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_dk_kernel(const __grid_const
       cp_wait<0>();
     }
     __syncthreads();
-    const double *As = smem + (t & 1) * p.stage_doubles;
-    const double *Bs = As + p.a_doubles + (wm * MO * 8 + fr) * p.PS + fk;
+    const char *As = reinterpret_cast<const char *>(smem + (t & 1) * p.stage_doubles);
+    const double *Bs = smem + (t & 1) * p.stage_doubles + p.a_doubles + (wm * MO * 8 + fr) * p.PS + fk;
     for (int k0 = wk * 4; k0 < p.npos4; k0 += 4 * p.WK) {
-      const double *ap = As + lut[k0 + fk];
+      const char *ap = As + lut[k0 + fk];
       double a[MO];
 #pragma unroll
       for (int m = 0; m < MO; m++) a[m] = Bs[m * 8 * p.PS + k0];
 #pragma unroll
       for (int j = 0; j < kNP; j++) {
         if (j < npw) {
-          double b = ap[pair_off[j]];
+          double b = *reinterpret_cast<const double *>(ap + pair_off[j]);
 #pragma unroll
           for (int m = 0; m < MO; m++) dmma884(acc[m][j][0], acc[m][j][1], a[m], b);
         }
@@ -397,9 +413,41 @@ __global__ void __launch_bounds__(kThreads, 1) conv_dk_kernel(const __grid_const
     }
     __syncthreads();
   }
-  // partial result of this (CTA, wk): C fragment row = o, cols = 2 columns
+  // K-split warps of this CTA are summed in fixed order through shared memory
+  if (p.WK > 1) {
+    double *red = smem;  // [warp][m][j][lane][2]
+#pragma unroll
+    for (int m = 0; m < MO; m++)
+#pragma unroll
+      for (int j = 0; j < kNP; j++)
+        if (j < npw) {
+          double *r = red + (((warp * MO + m) * kNP + j) * 32 + lane) * 2;
+          r[0] = acc[m][j][0];
+          r[1] = acc[m][j][1];
+        }
+    __syncthreads();
+    if (wk == 0) {
+      const int wstride = WM * p.WN;
+#pragma unroll
+      for (int m = 0; m < MO; m++)
+#pragma unroll
+        for (int j = 0; j < kNP; j++)
+          if (j < npw) {
+            double s0 = acc[m][j][0], s1 = acc[m][j][1];
+            for (int k = 1; k < p.WK; k++) {
+              const double *r = red + ((((warp + k * wstride) * MO + m) * kNP + j) * 32 + lane) * 2;
+              s0 += r[0];
+              s1 += r[1];
+            }
+            acc[m][j][0] = s0;
+            acc[m][j][1] = s1;
+          }
+    }
+  }
+  if (wk != 0) return;
+  // partial result of this CTA: C fragment row = o, cols = 2 columns
   const int KK = g.KH * g.KW;
-  double *part = p.part + ((int64_t)blockIdx.x * p.WK + wk) * ((int64_t)p.Co * p.Ci * KK);
+  double *part = p.part + (int64_t)blockIdx.x * ((int64_t)p.Co * p.Ci * KK);
 #pragma unroll
   for (int j = 0; j < kNP; j++) {
     if (j < npw) {
@@ -428,13 +476,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_dk_kernel(const __grid_const
   }
 }
 
-// dK[i] = sum_s part[s][i], s ascending (fixed order -> deterministic)
-__global__ void dk_reduce_kernel(const double *__restrict__ part, double *__restrict__ out, int n, int splits) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+// dK[i] = sum_s part[s][i], s ascending within each of 32 interleaved groups,
+// groups combined in order (fixed association -> deterministic)
+__global__ void __launch_bounds__(1024) dk_reduce_kernel(const double *__restrict__ part, double *__restrict__ out,
+                                                         int n, int splits) {
+  __shared__ double sm[32][33];
+  int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  int i = blockIdx.x * 32 + lane;
   double s = 0.0;
-  for (int k = 0; k < splits; k++) s += part[(int64_t)k * n + i];
-  out[i] = s;
+  if (i < n)
+    for (int k = grp; k < splits; k += 32) s += part[(int64_t)k * n + i];
+  sm[grp][lane] = s;
+  __syncthreads();
+  if (grp == 0 && i < n) {
+    double t = sm[0][lane];
+    for (int k = 1; k < 32; k++) t += sm[k][lane];
+    out[i] = t;
+  }
 }
 
 static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
@@ -443,6 +501,11 @@ static inline int stride4mod8(int n) {
   int s = round_up(n, 8) + 4;
   if (s - 8 >= n) s -= 8;
   return s;
+}
+static inline void set_pieces(TileGeo &g) {
+  g.cpr = g.vec ? g.W / 2 : g.W;
+  g.cshift = 0;
+  while ((1 << g.cshift) < g.cpr) g.cshift++;
 }
 
 template <typename K>
@@ -464,7 +527,7 @@ int hb_conv_sp_dmma(const hb_array *K, const hb_array *in, hb_array *out, int fl
   int Q = (int)out->shape[1];
   int KH = (int)K->shape[2], KW = (int)K->shape[3];
   if ((int64_t)N * P * H * W >= (1ll << 31) || (int64_t)N * Q * H * W >= (1ll << 31)) return HB_OK;
-  if (W > 224 || KH > 16 || KW > 16) return HB_OK;
+  if (W > 224 || KH > 16 || KW > 16 || H >= 32768) return HB_OK;
   SpP p;
   memset(&p, 0, sizeof p);
   // k mode
@@ -478,7 +541,8 @@ int hb_conv_sp_dmma(const hb_array *K, const hb_array *in, hb_array *out, int fl
   else if (Q <= 16) { WN = 1; NQ = 2; }
   else if (Q <= 32) { WN = 2; NQ = 2; }
   else { WN = 2; NQ = 4; }
-  int WM = 8 / WN, MF = 7;
+  const int WM = 8 / WN, MF = 7;
+  const bool one_cta = (NQ == 4);  // 56 accumulator doubles per thread: 1 CTA / SM
   p.QT = WN * NQ * 8;
   int nqt = (Q + p.QT - 1) / p.QT;
   p.TS = tapk ? p.QT + 4 : p.QT;
@@ -491,23 +555,41 @@ int hb_conv_sp_dmma(const hb_array *K, const hb_array *in, hb_array *out, int fl
   int halo_w = tapk ? p.KWP - 1 : KW - 1;
   if (flip && tapk) halo_w = (KW - 1) + (p.KWP - 1);  // low-side halo plus the padded taps' overrun
   g.RS = round_up(W + halo_w, 2);
-  int NI, R;
-  if (H * W <= slots) { R = H; NI = slots / (H * W); if (NI > N) NI = N; }
-  else { NI = 1; R = slots / W; if (R < 1) return HB_OK; int nb = (H + R - 1) / R; R = (H + nb - 1) / nb; }
   int Pq = tapk ? P : round_up(P, 4);
-  int CC = 0;
-  for (;;) {
-    g.R = R; g.NI = NI; g.TR = R + KH - 1; g.IS = g.TR * g.RS;
-    g.CS = stride4mod8(NI * g.IS + (tapk ? 4 : 0));
-    // largest channel chunk whose two stages fit
-    int per_c = g.CS + p.WCS;
-    int maxc = (kSmemMax / 8 / 2) / per_c;
-    if (!tapk) maxc = maxc / 4 * 4;
-    if (maxc >= (tapk ? 1 : 4)) { CC = maxc < Pq ? maxc : Pq; break; }
-    if (NI > 1) NI = (NI + 1) / 2;
-    else if (R > 1) R = (R + 1) / 2;
-    else return HB_OK;
+  // tile candidates: NI whole images, or bands of R rows of one image; keep the
+  // best-balanced one (fragments per warp) that fits two stages in the budget
+  int budgets[2] = {one_cta ? kSmemMax : (kSmemMax / 2 - 1024), kSmemMax};
+  int bestNI = 0, bestR = 0, bestCC = 0, ctas = 1;
+  for (int bi = 0; bi < 2 && !bestCC; bi++) {
+    double best_eff = 0;
+    for (int cand = 0; cand < 64; cand++) {
+      int NI, R;
+      if (H * W <= slots) { NI = cand + 1; R = H; if (NI > N || NI * H * W > slots) break; }
+      else { NI = 1; R = slots / W - cand; if (R < 1) break; int nb = (H + R - 1) / R; R = (H + nb - 1) / nb; }
+      int TR = R + KH - 1, IS = TR * g.RS;
+      int CS = stride4mod8(NI * IS + (tapk ? 4 : 0));
+      int per_c = CS + p.WCS;
+      int maxc = (budgets[bi] / 8 / 2) / per_c;
+      if (!tapk) maxc = maxc / 4 * 4;
+      if (maxc < (tapk ? 1 : 4)) continue;
+      int CC = maxc < Pq ? maxc : Pq;
+      int F = (NI * R * W + 7) / 8, per_warp = (F + WM - 1) / WM;
+      int nb = (H + R - 1) / R;
+      // balance over warps and bands, times the fragment-reuse factor: a warp
+      // with m fragments issues m + NQ shared loads per m * NQ DMMAs and pays the
+      // per-stage fixed costs over m fragments
+      double eff = (double)F / (WM * per_warp) * ((double)H / (nb * R)) * per_warp / (per_warp + 1.0);
+      // prefer fewer channel chunks when the balance is (nearly) the same
+      int nch = (Pq + CC - 1) / CC;
+      eff -= 0.01 * (nch - 1);
+      if (eff > best_eff + 1e-9) { best_eff = eff; bestNI = NI; bestR = R; bestCC = CC; }
+    }
+    if (bestCC) ctas = (bi == 0 && !one_cta) ? 2 : 1;
   }
+  if (!bestCC) return HB_OK;
+  int CC = bestCC;
+  g.R = bestR; g.NI = bestNI; g.TR = g.R + KH - 1; g.IS = g.TR * g.RS;
+  g.CS = stride4mod8(g.NI * g.IS + (tapk ? 4 : 0));
   // balance chunks
   p.NCH = (Pq + CC - 1) / CC;
   CC = (Pq + p.NCH - 1) / p.NCH;
@@ -523,6 +605,7 @@ int hb_conv_sp_dmma(const hb_array *K, const hb_array *in, hb_array *out, int fl
   p.in = (const double *)hb_data(in);
   p.out = (double *)hb_data(out);
   g.vec = (W % 2 == 0) && (g.ox % 2 == 0) && (((uintptr_t)p.in & 15) == 0) && (p.sn % 2 == 0) && (p.sp % 2 == 0);
+  set_pieces(g);
   int smem_bytes = 2 * p.stage_doubles * 8;
   if (smem_bytes > kSmemMax) return HB_OK;
   // packed weights in scratch
@@ -532,26 +615,27 @@ int hb_conv_sp_dmma(const hb_array *K, const hb_array *in, hb_array *out, int fl
   p.wp = (const double *)scr;
   {
     int blocks = hb_blocks_for(wn, 256, g_hb.sm_count * 8);
-    pack_sp_weights<<<blocks, 256, 0, g_hb.stream>>>((const double *)hb_data(K), (double *)scr, 0, 0, KH, KW, KWe, P,
-                                                     Q, p.Ppad, p.QT, p.TS, p.WCS, nqt, flip, K->strides[0],
+    pack_sp_weights<<<blocks, 256, 0, g_hb.stream>>>((const double *)hb_data(K), (double *)scr, KH, KW, KWe, P, Q,
+                                                     p.Ppad, p.QT, p.TS, p.WCS, nqt, flip, K->strides[0],
                                                      K->strides[1], K->strides[2], K->strides[3]);
     HB_LAUNCHED();
   }
-  dim3 grid((unsigned)(p.items < g_hb.sm_count ? p.items : g_hb.sm_count), (unsigned)nqt);
-#define SP_LAUNCH(WM_, WN_, NQ_)                                                                   \
-  do {                                                                                             \
-    if (tapk) {                                                                                    \
-      HB_TRY(set_smem(conv_sp_kernel<WM_, WN_, 7, NQ_, true>, smem_bytes));                        \
-      conv_sp_kernel<WM_, WN_, 7, NQ_, true><<<grid, kThreads, smem_bytes, g_hb.stream>>>(p);      \
-    } else {                                                                                       \
-      HB_TRY(set_smem(conv_sp_kernel<WM_, WN_, 7, NQ_, false>, smem_bytes));                       \
-      conv_sp_kernel<WM_, WN_, 7, NQ_, false><<<grid, kThreads, smem_bytes, g_hb.stream>>>(p);     \
-    }                                                                                              \
+  int maxg = g_hb.sm_count * ctas;
+  dim3 grid((unsigned)(p.items < maxg ? p.items : maxg), (unsigned)nqt);
+#define SP_LAUNCH(WM_, WN_, NQ_, MINB_)                                                                  \
+  do {                                                                                                   \
+    if (tapk) {                                                                                          \
+      HB_TRY(set_smem(conv_sp_kernel<WM_, WN_, 7, NQ_, true, MINB_>, smem_bytes));                       \
+      conv_sp_kernel<WM_, WN_, 7, NQ_, true, MINB_><<<grid, kThreads, smem_bytes, g_hb.stream>>>(p);     \
+    } else {                                                                                             \
+      HB_TRY(set_smem(conv_sp_kernel<WM_, WN_, 7, NQ_, false, MINB_>, smem_bytes));                      \
+      conv_sp_kernel<WM_, WN_, 7, NQ_, false, MINB_><<<grid, kThreads, smem_bytes, g_hb.stream>>>(p);    \
+    }                                                                                                    \
   } while (0)
-  if (WN == 1 && NQ == 1) SP_LAUNCH(8, 1, 1);
-  else if (WN == 1 && NQ == 2) SP_LAUNCH(8, 1, 2);
-  else if (WN == 2 && NQ == 2) SP_LAUNCH(4, 2, 2);
-  else SP_LAUNCH(4, 2, 4);
+  if (WN == 1 && NQ == 1) SP_LAUNCH(8, 1, 1, 2);
+  else if (WN == 1 && NQ == 2) SP_LAUNCH(8, 1, 2, 2);
+  else if (WN == 2 && NQ == 2) SP_LAUNCH(4, 2, 2, 2);
+  else SP_LAUNCH(4, 2, 4, 1);
 #undef SP_LAUNCH
   HB_LAUNCHED();
   (void)MF;
@@ -613,31 +697,31 @@ int hb_conv_dk_dmma(const hb_array *A, const hb_array *dB, hb_array *out, int KH
   g.H = H; g.W = W; g.KH = KH; g.KW = KW; g.oy = 0; g.ox = 0;
   int halo_w = tapw ? NCF * 8 - 1 : KW - 1;
   g.RS = round_up(W + halo_w, 2);
-  // positions per stage: as many rows as two stages allow
-  int NI = 1, R = H;
-  for (;;) {
+  // positions per stage: as many rows as two stages allow, two CTAs per SM
+  // when that still leaves at least a quarter of the image per stage
+  const int red_bytes = p.WK > 1 ? 8 * MO * kNP * 64 * 8 : 0;  // end-of-kernel K-split reduction area
+  int NI = 1, ctas = 1;
+  auto fits = [&](int R, int budget) {
     g.R = R; g.NI = NI; g.TR = R + KH - 1; g.IS = g.TR * g.RS;
     g.CS = stride4mod8(NI * g.IS + (tapw ? 8 : 0));
-    int npos = NI * R * W;
-    p.npos4 = round_up(npos, 4);
+    p.npos4 = round_up(NI * R * W, 4);
     p.PS = stride4mod8(p.npos4);
     p.a_doubles = round_up(CC * g.CS, 2);
     p.stage_doubles = p.a_doubles + otile * p.PS;
     int bytes = 2 * p.stage_doubles * 8 + p.npos4 * 4 + 16;
-    if (bytes <= kSmemMax) break;
-    if (R > 1) R = (R + 1) / 2;
-    else return HB_OK;
+    return bytes <= budget && red_bytes <= budget;
+  };
+  int R = 0;
+  for (int nb = 1; nb <= H && !R; nb++) {  // fewest bands first
+    int r = (H + nb - 1) / nb;
+    if (nb <= 4 && fits(r, kSmemMax / 2 - 1024)) { R = r; ctas = 2; }
   }
-  {
-    int nb = (H + g.R - 1) / g.R;
-    g.R = (H + nb - 1) / nb;
-    g.TR = g.R + KH - 1; g.IS = g.TR * g.RS;
-    g.CS = stride4mod8(NI * g.IS + (tapw ? 8 : 0));
-    p.npos4 = round_up(NI * g.R * W, 4);
-    p.PS = stride4mod8(p.npos4);
-    p.a_doubles = round_up(CC * g.CS, 2);
-    p.stage_doubles = p.a_doubles + otile * p.PS;
+  for (int nb = 1; nb <= H && !R; nb++) {
+    int r = (H + nb - 1) / nb;
+    if (fits(r, kSmemMax)) { R = r; ctas = 1; }
   }
+  if (!R) return HB_OK;
+  fits(R, kSmemMax);
   g.bands = (H + g.R - 1) / g.R;
   p.items = ((N + NI - 1) / NI) * g.bands;
   p.N = N; p.Ci = Ci; p.Co = Co;
@@ -646,18 +730,18 @@ int hb_conv_dk_dmma(const hb_array *A, const hb_array *dB, hb_array *out, int KH
   p.a_sn = A->strides[0]; p.a_sc = A->strides[1];
   p.b_sn = dB->strides[0]; p.b_so = dB->strides[1];
   g.vec = (W % 2 == 0) && (((uintptr_t)p.A & 15) == 0) && (p.a_sn % 2 == 0) && (p.a_sc % 2 == 0);
+  set_pieces(g);
   p.dbvec = ((g.R * W) % 2 == 0) && (W % 2 == 0) && (((uintptr_t)p.dB & 15) == 0) && (p.b_sn % 2 == 0) &&
             (p.b_so % 2 == 0);
   int smem_bytes = 2 * p.stage_doubles * 8 + p.npos4 * 4 + 16;
-  int splits = g_hb.sm_count / (ncc * not_);
+  if (smem_bytes < red_bytes) smem_bytes = red_bytes;
+  int splits = g_hb.sm_count * ctas / (ncc * not_);
   if (splits < 1) splits = 1;
   if (splits > p.items) splits = p.items;
-  int nparts = splits * p.WK;
   int64_t nout = (int64_t)Co * Ci * KK;
   void *scr;
-  HB_TRY(hb_scratch((size_t)nparts * nout * 8, &scr));
+  HB_TRY(hb_scratch((size_t)splits * nout * 8, &scr));
   p.part = (double *)scr;
-  // every (split, wk) writes every element it owns; columns beyond npairs never exist
   dim3 grid((unsigned)splits, (unsigned)ncc, (unsigned)not_);
 #define DK_LAUNCH(WM_, MO_)                                                                  \
   do {                                                                                       \
@@ -675,8 +759,8 @@ int hb_conv_dk_dmma(const hb_array *A, const hb_array *dB, hb_array *out, int KH
   else DK_LAUNCH(4, 2);
 #undef DK_LAUNCH
   HB_LAUNCHED();
-  dk_reduce_kernel<<<(unsigned)((nout + 255) / 256), 256, 0, g_hb.stream>>>(p.part, (double *)hb_data(out), (int)nout,
-                                                                           nparts);
+  dk_reduce_kernel<<<(unsigned)((nout + 31) / 32), 1024, 0, g_hb.stream>>>(p.part, (double *)hb_data(out), (int)nout,
+                                                                          splits);
   HB_LAUNCHED();
   *done = 1;
   return HB_OK;
