@@ -48,6 +48,14 @@ L2_BYTES = 126e6
 PER_GPU_BATCH = 4096
 HYPER = dict(kh=4, kw=4, c_out=16, n_hidden=64)     # 5x5 kernels: TestMnistCNNS.hs:422-424
 METRIC = "mnist_cnn_train_samples_per_s"
+# The reference's objective (whole-tensor softmax with the custom dual
+# `softMax - expected`, CommonShapedOps.hs:89-111) pushes all labelled logits up
+# without bound on a batch of random labels and overflows exp after ~50 Adam
+# steps -- identically on the CPU oracle.  The bench
+# therefore restores the initial parameters every RESET_EVERY steps (three
+# 0.46 MB device-to-device copies inside the timed region) so reported losses
+# stay finite; the arithmetic per step is unchanged.
+RESET_EVERY = 16
 
 
 def peaks():
@@ -72,7 +80,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -82,6 +90,10 @@ class ClockSampler:
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append(line.strip())
+
+    def mark(self):
+        """Samples taken before this point (warm-up) are dropped."""
+        self.rows = self.rows[-1:]
 
     def stop(self) -> dict:
         if self.proc is None:
@@ -203,6 +215,7 @@ def config_dict(args, world):
             "per_gpu_batch": local, "global_batch": local * world,
             "hyper": "kh=kw=4 (5x5 kernels), c_out=16, n_hidden=64",
             "parallelism": f"dp{world}", "optimizer": "adam",
+            "param_reset_every_steps": RESET_EVERY,
             "l2": "per-step working set (activations ~1.6 GB at batch 4096) >> 126 MB L2; no explicit flush"}
 
 
@@ -210,7 +223,7 @@ def config_dict(args, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
@@ -288,6 +301,8 @@ def main():
     n0 = C.c_uint64()
 
     # ---- device-resident: inputs uploaded once, K steps timed with CUDA events
+    clocks = ClockSampler(local_rank)
+    clocks.start()
     tr.upload(gl.ptr, lb.ptr)
     for i in range(W):
         tr.step_enqueue()
@@ -296,11 +311,12 @@ def main():
             dbg("first step done")
     barrier()
     dbg("warm-up done")
-    clocks = ClockSampler(local_rank)
-    clocks.start()
+    clocks.mark()
     ffi.call("hb_launch_count", C.byref(n0))
     ffi.call("hb_event_record", 0)
-    for _ in range(K):
+    for i in range(K):
+        if i % RESET_EVERY == 0:
+            tr.reset()
         bucket = tr.step_enqueue()
     ffi.call("hb_event_record", 1)
     ms = C.c_float()
@@ -314,12 +330,22 @@ def main():
     value = global_batch * K / (dev_ms * 1e-3)
 
     # ---- end to end through the public call: H2D + step + loss D2H per step
-    for _ in range(2):
-        tr.train_step(gl.ptr, lb.ptr)
+    # two pinned host batches alternate, as a data loader would hand them out;
+    # step k uploads batch k+1 on the copy stream while it computes (every
+    # step still performs one full H2D of a minibatch and one loss D2H)
+    gl2 = PinnedBuffer((local_batch, 28, 28), np.float64)
+    lb2 = PinnedBuffer((local_batch, 10), np.float64)
+    gl2.array[...] = gl.array[::-1]
+    lb2.array[...] = lb.array[::-1]
+    hostb = [(gl.ptr, lb.ptr), (gl2.ptr, lb2.ptr)]
+    for i in range(2):
+        tr.train_step(*hostb[i % 2], *hostb[(i + 1) % 2])
     barrier()
     t0 = time.perf_counter()
-    for _ in range(K):
-        loss = tr.train_step(gl.ptr, lb.ptr)
+    for i in range(K):
+        if i % RESET_EVERY == 0:
+            tr.reset()
+        loss = tr.train_step(*hostb[i % 2], *hostb[(i + 1) % 2])
     dev.sync()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
@@ -357,7 +383,8 @@ def main():
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d * world,
                 "d2h_bytes_per_step": 8 * world, "ms_per_step": e2e_s / K * 1e3},
         "gpu_launches": int(n1.value - n0.value),
-        "clocks": clk, "loss": loss, "loss_resident": loss_resident,
+        "clocks": clk, "loss": loss if np.isfinite(loss) else None,
+        "loss_resident": loss_resident if np.isfinite(loss_resident) else None,
         "roofline": roof, "breakdown": breakdown,
         "fp64_peak_tflops": {"dmma": fp64_dmma.value, "dfma": fp64_fma.value, "how": "hb_microbench, this run"},
     }

@@ -443,6 +443,49 @@ extern "C" int hb_upload_into(hb_array *dst, const void *host) {
   return HB_OK;
 }
 
+// ---- prefetch: H2D on a second stream, overlapped with the compute stream
+static cudaStream_t g_copy_stream = nullptr;
+static cudaEvent_t g_ev_ready = nullptr, g_ev_consumed = nullptr;
+static bool g_consumed_recorded = false;
+
+static int prefetch_init() {
+  if (g_copy_stream) return HB_OK;
+  HB_CUDA(cudaStreamCreateWithFlags(&g_copy_stream, cudaStreamNonBlocking));
+  HB_CUDA(cudaEventCreateWithFlags(&g_ev_ready, cudaEventDisableTiming));
+  HB_CUDA(cudaEventCreateWithFlags(&g_ev_consumed, cudaEventDisableTiming));
+  return HB_OK;
+}
+
+extern "C" int hb_prefetch_into(hb_array *dst, const void *host) {
+  HB_CHECK_INIT();
+  HB_REQUIRE(dst && host, "null argument");
+  HB_REQUIRE(hb_contig(dst), "hb_prefetch_into: destination must be contiguous");
+  HB_REQUIRE(!g_hb.capturing, "hb_prefetch_into: not inside a graph capture");
+  HB_TRY(prefetch_init());
+  if (g_consumed_recorded) HB_CUDA(cudaStreamWaitEvent(g_copy_stream, g_ev_consumed, 0));
+  int64_t n = hb_numel(dst);
+  if (n > 0)
+    HB_CUDA(cudaMemcpyAsync(hb_data(dst), host, (size_t)n * hb_dtype_size(dst->dt), cudaMemcpyHostToDevice,
+                            g_copy_stream));
+  HB_CUDA(cudaEventRecord(g_ev_ready, g_copy_stream));
+  return HB_OK;
+}
+
+extern "C" int hb_prefetch_ready(void) {
+  HB_CHECK_INIT();
+  HB_TRY(prefetch_init());
+  HB_CUDA(cudaStreamWaitEvent(g_hb.stream, g_ev_ready, 0));
+  return HB_OK;
+}
+
+extern "C" int hb_prefetch_consumed(void) {
+  HB_CHECK_INIT();
+  HB_TRY(prefetch_init());
+  HB_CUDA(cudaEventRecord(g_ev_consumed, g_hb.stream));
+  g_consumed_recorded = true;
+  return HB_OK;
+}
+
 extern "C" int hb_to_host(const hb_array *a, void *host) {
   HB_CHECK_INIT();
   HB_REQUIRE(a, "null array");

@@ -141,6 +141,56 @@ __global__ void pack_sp_weights(const double *__restrict__ K, double *__restrict
   }
 }
 
+// One stage of the spatial kernel for a warp that owns exactly NF fragments.
+template <int NF, int MF, int NQ, bool TAPK>
+__device__ __forceinline__ void sp_stage(double (&acc)[MF][NQ][2], const int (&aoff)[MF], const char *Sb,
+                                         const char *Wb, const SpP &p) {
+  const TileGeo &g = p.g;
+  if (TAPK) {
+    const int ng = p.KWP >> 2;
+    for (int c = 0; c < p.CC; c++) {
+      for (int kh = 0; kh < g.KH; kh++) {
+        const char *ia = Sb + (c * g.CS + kh * g.RS) * 8;
+        const char *wb = Wb + (c * p.WCS + kh * p.KWP * p.TS) * 8;
+        for (int g4 = 0; g4 < ng; g4++) {
+          double b[NQ];
+#pragma unroll
+          for (int j = 0; j < NQ; j++) b[j] = *reinterpret_cast<const double *>(wb + j * 64);
+#pragma unroll
+          for (int i = 0; i < NF; i++) {
+            double a = *reinterpret_cast<const double *>(ia + aoff[i]);
+#pragma unroll
+            for (int j = 0; j < NQ; j++) dmma884(acc[i][j][0], acc[i][j][1], a, b[j]);
+          }
+          ia += 32;
+          wb += 4 * p.TS * 8;
+        }
+      }
+    }
+  } else {
+    const int tsb = p.TS * 8;
+    for (int c4 = 0; c4 < p.CC; c4 += 4) {
+      const char *wb = Wb + c4 * p.WCS * 8;
+      for (int kh = 0; kh < g.KH; kh++) {
+        const char *ia = Sb + (c4 * g.CS + kh * g.RS) * 8;
+        for (int kw = 0; kw < g.KW; kw++) {
+          double b[NQ];
+#pragma unroll
+          for (int j = 0; j < NQ; j++) b[j] = *reinterpret_cast<const double *>(wb + j * 64);
+#pragma unroll
+          for (int i = 0; i < NF; i++) {
+            double a = *reinterpret_cast<const double *>(ia + aoff[i]);
+#pragma unroll
+            for (int j = 0; j < NQ; j++) dmma884(acc[i][j][0], acc[i][j][1], a, b[j]);
+          }
+          ia += 8;
+          wb += tsb;
+        }
+      }
+    }
+  }
+}
+
 template <int WM, int WN, int MF, int NQ, bool TAPK, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB) conv_sp_kernel(const __grid_constant__ SpP p) {
   extern __shared__ __align__(16) double smem[];
@@ -207,53 +257,18 @@ __global__ void __launch_bounds__(kThreads, MINB) conv_sp_kernel(const __grid_co
     }
     __syncthreads();
     const char *Sb = reinterpret_cast<const char *>(smem + (t & 1) * p.stage_doubles);
-    const char *Wb = Sb + woff;
-    if (TAPK) {
-      const int ng = p.KWP >> 2;
-      for (int c = 0; c < p.CC; c++) {
-        for (int kh = 0; kh < g.KH; kh++) {
-          const char *ia = Sb + (c * g.CS + kh * g.RS) * 8;
-          const char *wb = Wb + (c * p.WCS + kh * p.KWP * p.TS) * 8;
-          for (int g4 = 0; g4 < ng; g4++) {
-            double b[NQ];
-#pragma unroll
-            for (int j = 0; j < NQ; j++) b[j] = *reinterpret_cast<const double *>(wb + j * 64);
-#pragma unroll
-            for (int i = 0; i < MF; i++) {
-              if (i < nf) {
-                double a = *reinterpret_cast<const double *>(ia + aoff[i]);
-#pragma unroll
-                for (int j = 0; j < NQ; j++) dmma884(acc[i][j][0], acc[i][j][1], a, b[j]);
-              }
-            }
-            ia += 32;
-            wb += 4 * p.TS * 8;
-          }
-        }
-      }
-    } else {
-      const int tsb = p.TS * 8;
-      for (int c4 = 0; c4 < p.CC; c4 += 4) {
-        const char *wb = Wb + c4 * p.WCS * 8;
-        for (int kh = 0; kh < g.KH; kh++) {
-          const char *ia = Sb + (c4 * g.CS + kh * g.RS) * 8;
-          for (int kw = 0; kw < g.KW; kw++) {
-            double b[NQ];
-#pragma unroll
-            for (int j = 0; j < NQ; j++) b[j] = *reinterpret_cast<const double *>(wb + j * 64);
-#pragma unroll
-            for (int i = 0; i < MF; i++) {
-              if (i < nf) {
-                double a = *reinterpret_cast<const double *>(ia + aoff[i]);
-#pragma unroll
-                for (int j = 0; j < NQ; j++) dmma884(acc[i][j][0], acc[i][j][1], a, b[j]);
-              }
-            }
-            ia += 8;
-            wb += tsb;
-          }
-        }
-      }
+    // predicated-off DMMAs still occupy the tensor pipe (ncu: dmma cycles =
+    // issued slots, not useful ones), so the fragment count is a template
+    // parameter selected by a warp-uniform switch, never a predicate
+    switch (nf) {
+      case 7: if (MF >= 7) sp_stage<(MF >= 7 ? 7 : MF), MF, NQ, TAPK>(acc, aoff, Sb, Sb + woff, p); break;
+      case 6: if (MF >= 6) sp_stage<(MF >= 6 ? 6 : MF), MF, NQ, TAPK>(acc, aoff, Sb, Sb + woff, p); break;
+      case 5: if (MF >= 5) sp_stage<(MF >= 5 ? 5 : MF), MF, NQ, TAPK>(acc, aoff, Sb, Sb + woff, p); break;
+      case 4: if (MF >= 4) sp_stage<(MF >= 4 ? 4 : MF), MF, NQ, TAPK>(acc, aoff, Sb, Sb + woff, p); break;
+      case 3: sp_stage<3, MF, NQ, TAPK>(acc, aoff, Sb, Sb + woff, p); break;
+      case 2: sp_stage<2, MF, NQ, TAPK>(acc, aoff, Sb, Sb + woff, p); break;
+      case 1: sp_stage<1, MF, NQ, TAPK>(acc, aoff, Sb, Sb + woff, p); break;
+      default: break;
     }
     if ((t + 1) % p.NCH == 0) {
       // epilogue of this item: C fragment row = position, cols = 2 output channels
@@ -300,6 +315,24 @@ struct DkP {
 };
 
 constexpr int kNP = 9;  // max column pairs per warp
+
+// One stage of the dKrn kernel for a warp that owns exactly NPW column pairs.
+template <int NPW, int MO>
+__device__ __forceinline__ void dk_stage(double (&acc)[MO][kNP][2], const int (&pair_off)[kNP], const char *As,
+                                         const double *Bs, const int *lutk, int kbeg, int kstep, const DkP &p) {
+  for (int k0 = kbeg; k0 < p.npos4; k0 += kstep) {
+    const char *ap = As + lutk[k0];
+    double a[MO];
+#pragma unroll
+    for (int m = 0; m < MO; m++) a[m] = Bs[m * 8 * p.PS + k0];
+#pragma unroll
+    for (int j = 0; j < NPW; j++) {
+      double b = *reinterpret_cast<const double *>(ap + pair_off[j]);
+#pragma unroll
+      for (int m = 0; m < MO; m++) dmma884(acc[m][j][0], acc[m][j][1], a[m], b);
+    }
+  }
+}
 
 template <int WM, int MO, bool TAPW>
 __global__ void __launch_bounds__(kThreads, 2) conv_dk_kernel(const __grid_constant__ DkP p) {
@@ -397,19 +430,18 @@ __global__ void __launch_bounds__(kThreads, 2) conv_dk_kernel(const __grid_const
     __syncthreads();
     const char *As = reinterpret_cast<const char *>(smem + (t & 1) * p.stage_doubles);
     const double *Bs = smem + (t & 1) * p.stage_doubles + p.a_doubles + (wm * MO * 8 + fr) * p.PS + fk;
-    for (int k0 = wk * 4; k0 < p.npos4; k0 += 4 * p.WK) {
-      const char *ap = As + lut[k0 + fk];
-      double a[MO];
-#pragma unroll
-      for (int m = 0; m < MO; m++) a[m] = Bs[m * 8 * p.PS + k0];
-#pragma unroll
-      for (int j = 0; j < kNP; j++) {
-        if (j < npw) {
-          double b = *reinterpret_cast<const double *>(ap + pair_off[j]);
-#pragma unroll
-          for (int m = 0; m < MO; m++) dmma884(acc[m][j][0], acc[m][j][1], a[m], b);
-        }
-      }
+    const int kbeg = wk * 4, kstep = 4 * p.WK;
+    switch (npw) {  // exact pair count: no predicated-off DMMAs (they would still occupy the pipe)
+      case 9: dk_stage<9, MO>(acc, pair_off, As, Bs, lut + fk, kbeg, kstep, p); break;
+      case 8: dk_stage<8, MO>(acc, pair_off, As, Bs, lut + fk, kbeg, kstep, p); break;
+      case 7: dk_stage<7, MO>(acc, pair_off, As, Bs, lut + fk, kbeg, kstep, p); break;
+      case 6: dk_stage<6, MO>(acc, pair_off, As, Bs, lut + fk, kbeg, kstep, p); break;
+      case 5: dk_stage<5, MO>(acc, pair_off, As, Bs, lut + fk, kbeg, kstep, p); break;
+      case 4: dk_stage<4, MO>(acc, pair_off, As, Bs, lut + fk, kbeg, kstep, p); break;
+      case 3: dk_stage<3, MO>(acc, pair_off, As, Bs, lut + fk, kbeg, kstep, p); break;
+      case 2: dk_stage<2, MO>(acc, pair_off, As, Bs, lut + fk, kbeg, kstep, p); break;
+      case 1: dk_stage<1, MO>(acc, pair_off, As, Bs, lut + fk, kbeg, kstep, p); break;
+      default: break;
     }
     __syncthreads();
   }

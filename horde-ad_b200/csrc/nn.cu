@@ -383,30 +383,80 @@ __device__ T hb_block_reduce(T v, T *smem, bool is_min) {
   return v;  // every thread
 }
 
+// Multi-block version (the [10, batch] logits of a 4096-sample minibatch are
+// 40960 elements; one block spent 150 us on them): three grid-wide phases,
+// each a kernel whose blocks first combine the previous phase's per-block
+// partials IN BLOCK ORDER (so every block derives the identical global value
+// and the result is deterministic), then do their share of the next phase.
+//   phase 0: partial minima          phase 1: partial sums of exp(u - min)
+//   phase 2: dl = scale*(softmax - expected), partial sums of log(softmax)*expected
+//   phase 3: loss = scale * -(sum of partials)
 template <typename T>
-__global__ void __launch_bounds__(1024)
-    hb_softmax_xent_kernel(const T *__restrict__ u, hb_dims ud, const T *__restrict__ ex, hb_dims ed,
-                           int64_t n, T scale, T *__restrict__ loss, T *__restrict__ dl) {
+__device__ T hb_combine(const T *part, int n, bool is_min) {
+  T v = part[0];
+  for (int i = 1; i < n; i++) v = is_min ? (part[i] < v ? part[i] : v) : v + part[i];
+  return v;
+}
+
+template <typename T, int PHASE>
+__global__ void __launch_bounds__(256)
+    hb_softmax_xent_phase(const T *__restrict__ u, hb_dims ud, const T *__restrict__ ex, hb_dims ed, int64_t n,
+                          T scale, T *__restrict__ pmin, T *__restrict__ psum, T *__restrict__ ploss,
+                          T *__restrict__ loss, T *__restrict__ dl) {
   __shared__ T smem[32];
-  T mn = u[hb_offset_of(ud, 0)];
-  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
-    T v = u[hb_offset_of(ud, i)];
-    mn = v < mn ? v : mn;
+  const int nb = gridDim.x;
+  const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gs = (int64_t)nb * blockDim.x;
+  if (PHASE == 0) {
+    T mn = u[hb_offset_of(ud, i0 < n ? i0 : 0)];
+    for (int64_t i = i0; i < n; i += gs) {
+      T v = u[hb_offset_of(ud, i)];
+      mn = v < mn ? v : mn;
+    }
+    mn = hb_block_reduce<T>(mn, smem, true);
+    if (threadIdx.x == 0) pmin[blockIdx.x] = mn;
+  } else if (PHASE == 1) {
+    T mn = hb_combine<T>(pmin, nb, true);
+    T s = T(0);
+    for (int64_t i = i0; i < n; i += gs) s += exp(u[hb_offset_of(ud, i)] - mn);
+    s = hb_block_reduce<T>(s, smem, false);
+    if (threadIdx.x == 0) psum[blockIdx.x] = s;
+  } else if (PHASE == 2) {
+    T mn = hb_combine<T>(pmin, nb, true);
+    T rs = T(1) / hb_combine<T>(psum, nb, false);
+    T l = T(0);
+    for (int64_t i = i0; i < n; i += gs) {
+      T sm = rs * exp(u[hb_offset_of(ud, i)] - mn);
+      T e = ex[hb_offset_of(ed, i)];
+      l += log(sm) * e;
+      if (dl) dl[i] = scale * (sm - e);
+    }
+    l = hb_block_reduce<T>(l, smem, false);
+    if (threadIdx.x == 0) ploss[blockIdx.x] = l;
+  } else {
+    if (blockIdx.x == 0 && threadIdx.x == 0) *loss = scale * (-hb_combine<T>(ploss, (int)n, false));
   }
-  mn = hb_block_reduce<T>(mn, smem, true);
-  T s = T(0);
-  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += exp(u[hb_offset_of(ud, i)] - mn);
-  s = hb_block_reduce<T>(s, smem, false);
-  T rs = T(1) / s;
-  T l = T(0);
-  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
-    T sm = rs * exp(u[hb_offset_of(ud, i)] - mn);
-    T e = ex[hb_offset_of(ed, i)];
-    l += log(sm) * e;
-    if (dl) dl[i] = scale * (sm - e);
-  }
-  l = hb_block_reduce<T>(l, smem, false);
-  if (threadIdx.x == 0) *loss = scale * (-l);
+}
+
+template <typename T>
+static int softmax_xent_launch(const hb_array *logits, const hb_array *expected, const hb_dims &ud,
+                               const hb_dims &ed, int64_t n, double scale, hb_array *loss, hb_array *dl) {
+  int nb = (int)((n + 511) / 512);
+  if (nb > 128) nb = 128;
+  if (nb < 1) nb = 1;
+  void *scr;
+  HB_TRY(hb_scratch((size_t)3 * 128 * sizeof(T), &scr));
+  T *pmin = (T *)scr, *psum = pmin + 128, *ploss = psum + 128;
+  const T *u = (const T *)hb_data(logits), *ex = (const T *)hb_data(expected);
+  T *lp = (T *)hb_data(loss), *dp = dl ? (T *)hb_data(dl) : nullptr;
+  hb_softmax_xent_phase<T, 0><<<nb, 256, 0, g_hb.stream>>>(u, ud, ex, ed, n, (T)scale, pmin, psum, ploss, lp, dp);
+  HB_LAUNCHED();
+  hb_softmax_xent_phase<T, 1><<<nb, 256, 0, g_hb.stream>>>(u, ud, ex, ed, n, (T)scale, pmin, psum, ploss, lp, dp);
+  HB_LAUNCHED();
+  hb_softmax_xent_phase<T, 2><<<nb, 256, 0, g_hb.stream>>>(u, ud, ex, ed, n, (T)scale, pmin, psum, ploss, lp, dp);
+  HB_LAUNCHED();
+  hb_softmax_xent_phase<T, 3><<<1, 32, 0, g_hb.stream>>>(u, ud, ex, ed, (int64_t)nb, (T)scale, pmin, psum, ploss, lp, dp);
+  HB_LAUNCHED();
+  return HB_OK;
 }
 
 extern "C" int hb_softmax_xent(const hb_array *logits, const hb_array *expected, double scale,
@@ -432,15 +482,13 @@ extern "C" int hb_softmax_xent(const hb_array *logits, const hb_array *expected,
     ud.stride[i] = i < logits->rank ? logits->strides[i] : 0;
     ed.stride[i] = i < logits->rank ? expected->strides[i] : 0;
   }
-  if (logits->dt == HB_F64)
-    hb_softmax_xent_kernel<double><<<1, 1024, 0, g_hb.stream>>>(
-        (const double *)hb_data(logits), ud, (const double *)hb_data(expected), ed, n, scale,
-        (double *)hb_data(loss), dl ? (double *)hb_data(dl) : nullptr);
-  else
-    hb_softmax_xent_kernel<float><<<1, 1024, 0, g_hb.stream>>>(
-        (const float *)hb_data(logits), ud, (const float *)hb_data(expected), ed, n, (float)scale,
-        (float *)hb_data(loss), dl ? (float *)hb_data(dl) : nullptr);
-  HB_LAUNCHED();
+  int st = logits->dt == HB_F64 ? softmax_xent_launch<double>(logits, expected, ud, ed, n, scale, loss, dl)
+                                : softmax_xent_launch<float>(logits, expected, ud, ed, n, scale, loss, dl);
+  if (st != HB_OK) {
+    hb_release(loss);
+    hb_release(dl);
+    return st;
+  }
   *loss_out = loss;
   if (dlogits_out) *dlogits_out = dl;
   return HB_OK;

@@ -62,6 +62,7 @@ PROTOTYPES = {
     "hb_prof_begin": [], "hb_prof_end": [], "hb_prof_report": [C.c_char_p, C.c_size_t],
     "hb_retain": [P], "hb_release": [P],
     "hb_from_host": [C.c_int, C.c_int, I64P, P, PP], "hb_upload_into": [P, P],
+    "hb_prefetch_into": [P, P], "hb_prefetch_ready": [], "hb_prefetch_consumed": [],
     "hb_to_host": [P, P], "hb_scalar_to_host": [P, P],
     "hb_full": [C.c_int, C.c_int, I64P, P, PP],
     "hb_host_alloc": [C.c_size_t, PP], "hb_host_free": [P],

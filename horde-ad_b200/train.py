@@ -40,6 +40,16 @@ class PinnedBuffer:
             self.ptr = None
 
 
+def _addr(p) -> int:
+    return p.value if isinstance(p, C.c_void_p) else int(p)
+
+
+def _devptr(t: DeviceArray) -> C.c_void_p:
+    p = C.c_void_p()
+    call("hb_device_ptr", t.h, C.byref(p))
+    return p
+
+
 class CnnTrainer:
     def __init__(self, dev: DeviceBackend, local_batch: int, kh=4, kw=4, c_out=16, n_hidden=64,
                  dtype=np.float64, world=1, seed=44, use_graph=True, optimizer="adam", gamma=0.02):
@@ -54,6 +64,8 @@ class CnnTrainer:
         self.flat_p = dev.sconcrete(flat)
         self.flat_m = dev.sconcrete(np.zeros_like(flat))
         self.flat_v = dev.sconcrete(np.zeros_like(flat))
+        self._p0 = dev.sconcrete(flat)                    # initial parameters, for reset()
+        self._z0 = dev.sconcrete(np.zeros_like(flat))
         self.params = self._leaves(self.flat_p)
         self.glyphs = dev.sconcrete(np.zeros((local_batch, 28, 28), dtype))
         self.labels = dev.sconcrete(np.zeros((local_batch, 10), dtype))
@@ -64,6 +76,8 @@ class CnnTrainer:
         self.use_graph = use_graph
         self.loss_arr = None
         self.bucket = None
+        self._prefetched = None
+        self._stage_g = self._stage_l = None
 
     def _leaves(self, flat: DeviceArray):
         out, pos = [], 0
@@ -127,14 +141,42 @@ class CnnTrainer:
         self.dev.upload_into(self.glyphs, glyphs_ptr)
         self.dev.upload_into(self.labels, labels_ptr)
 
-    def train_step(self, glyphs_ptr, labels_ptr) -> float:
-        """The end-to-end user call: H2D of the minibatch, step, loss D2H."""
-        self.upload(glyphs_ptr, labels_ptr)
+    def train_step(self, glyphs_ptr, labels_ptr, next_glyphs_ptr=None, next_labels_ptr=None) -> float:
+        """The end-to-end user call: H2D of the minibatch, step, loss D2H.
+
+        With `next_*` (the host buffers of the FOLLOWING minibatch, as a data
+        loader hands them out) that batch's H2D copy is started on the copy
+        stream into staging buffers and overlaps this step; the next call then
+        finds its inputs already on the device and pays one D2D copy."""
+        key = (_addr(glyphs_ptr), _addr(labels_ptr))
+        if self._prefetched == key:
+            call("hb_prefetch_ready")
+            self.dev.upload_into(self.glyphs, _devptr(self._stage_g))
+            self.dev.upload_into(self.labels, _devptr(self._stage_l))
+            call("hb_prefetch_consumed")
+        else:
+            self.upload(glyphs_ptr, labels_ptr)
+        self._prefetched = None
         bucket = self.step_enqueue()
+        if next_glyphs_ptr is not None:
+            if self._stage_g is None:
+                self._stage_g = self.dev.sconcrete(np.zeros((self.B, 28, 28), self.dtype))
+                self._stage_l = self.dev.sconcrete(np.zeros((self.B, 10), self.dtype))
+            call("hb_prefetch_into", self._stage_g.h, next_glyphs_ptr)
+            call("hb_prefetch_into", self._stage_l.h, next_labels_ptr)
+            self._prefetched = (_addr(next_glyphs_ptr), _addr(next_labels_ptr))
         return float(self.dev.kfromS(self.dev.sslice(self.n_params, 1, bucket)))
 
     def loss_of(self, bucket) -> float:
         return float(self.dev.kfromS(self.dev.sslice(self.n_params, 1, bucket)))
+
+    def reset(self):
+        """Back to the initial parameters and zero Adam state (three small
+        device-to-device copies on the library stream)."""
+        self.dev.upload_into(self.flat_p, _devptr(self._p0))
+        self.dev.upload_into(self.flat_m, _devptr(self._z0))
+        self.dev.upload_into(self.flat_v, _devptr(self._z0))
+        self.t = 0
 
     def get_params(self):
         return [self.dev.to_numpy(p) for p in self.params]

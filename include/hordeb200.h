@@ -107,6 +107,14 @@ int hb_from_host(hb_dtype dt, int rank, const int64_t *shape,
  * memory, asynchronously on the library stream: the per-step upload of a
  * minibatch into a resident buffer (no allocation). */
 int hb_upload_into(hb_array *dst, const void *host);
+/* Prefetch: the same copy on a second (copy-engine) stream so that the upload
+ * of the NEXT minibatch overlaps the current step.  hb_prefetch_ready makes the
+ * compute stream wait for every prefetch issued so far; hb_prefetch_consumed
+ * marks the point of the compute stream after which the prefetch destinations
+ * may be overwritten (later prefetches wait for it). */
+int hb_prefetch_into(hb_array *dst, const void *host);
+int hb_prefetch_ready(void);
+int hb_prefetch_consumed(void);
 /* Download in logical row-major order (materialises views); synchronises. */
 int hb_to_host(const hb_array *a, void *host);
 /* kfromS / sunScalar (OpsConcrete.hs:777-812): 0-d (or 1-element) array ->
