@@ -350,6 +350,14 @@ class ADBackend:
                     B.conv2d_dinp(K.p, dpre) if A.d is not None else None]
         return self._node(y, [K, bias, A], pb)
 
+    def custom_unary(self, t, primal, vjp):
+        """tD with a hand-written dual part (e.g. logistic,
+        CommonRankedOps.hs:55-63): primal(B, x) and vjp(B, x, y, c)."""
+        B = self.B
+        t = self.lift(t)
+        y = primal(B, t.p)
+        return self._node(y, [t], lambda c: [vjp(B, t.p, y, c)])
+
     def relu(self, t):
         B = self.B
         t = self.lift(t)

@@ -1,0 +1,63 @@
+"""MnistRnnShaped2 (example/MnistRnnShaped2.hs:25-139) against the carrier
+method surface: two recurrent tanh layers unrolled over the 28 rows of the
+glyph (`unrollLastS` = a host fold over `sunravelToList`, :45-52), a dense
+read-out, and the fused softmax-cross-entropy loss."""
+from __future__ import annotations
+
+import numpy as np
+
+from . import nn
+
+SIZE_MNIST_LABEL = 10
+
+
+def param_shapes(out_width, h=28):
+    """ADRnnMnistParametersShaped (MnistRnnShaped2.hs:25-36)."""
+    return [(out_width, h), (out_width, out_width), (out_width,),
+            (out_width, out_width), (out_width, out_width), (out_width,),
+            (SIZE_MNIST_LABEL, out_width), (SIZE_MNIST_LABEL,)]
+
+
+def init_params(out_width, seed=44, rng_range=0.4, dtype=np.float64, h=28):
+    rng = np.random.Generator(np.random.Philox(seed))
+    return [(2 * rng_range * (rng.random(s) - 0.5)).astype(dtype) for s in param_shapes(out_width, h)]
+
+
+def rnnMnistLayerS(T, s, x, wX, wS, b):
+    """rnnMnistLayerS (MnistRnnShaped2.hs:55-69): tanh (wX x + wS s + b)."""
+    batch = T.shape(x)[1]
+    y = T.binary("add", T.binary("add", T.smatmul2(wX, x), T.smatmul2(wS, s)),
+                 T.stranspose([1, 0], T.sreplicate(batch, b)))
+    return T.unary("tanh", y)
+
+
+def rnnMnistTwoS(T, s, x, layers):
+    """rnnMnistTwoS (MnistRnnShaped2.hs:73-99): state = sappend vec1 vec2."""
+    (wX, wS, b), (wX2, wS2, b2) = layers
+    out_width = T.shape(wS)[0]
+    s1, s2 = T.sslice(0, out_width, s), T.sslice(out_width, out_width, s)
+    vec1 = rnnMnistLayerS(T, s1, x, wX, wS, b)
+    vec2 = rnnMnistLayerS(T, s2, vec1, wX2, wS2, b2)
+    s3 = T.sappend(vec1, vec2)
+    return T.sslice(out_width, out_width, s3), s3
+
+
+def rnnMnistZeroS(T, xs, params):
+    """rnnMnistZeroS (MnistRnnShaped2.hs:103-117): zero state, unrollLastS."""
+    wX, wS, b, wX2, wS2, b2, w3, b3 = params
+    out_width = T.shape(wS)[0]
+    batch = T.shape(xs)[2]
+    s = T.srepl([2 * out_width, batch], 0, T.dtype(wS))
+    out = None
+    for x in T.sunravelToList(xs):          # foldl' over the rows (:45-52)
+        out, s = rnnMnistTwoS(T, s, x, ((wX, wS, b), (wX2, wS2, b2)))
+    return T.binary("add", T.smatmul2(w3, out), T.stranspose([1, 0], T.sreplicate(batch, b3)))
+
+
+def rnnMnistLossFusedS(T, glyphs, labels, params):
+    """rnnMnistLossFusedS (MnistRnnShaped2.hs:119-139): glyphs [batch, h, w],
+    labels [batch, 10]."""
+    batch = T.shape(glyphs)[0]
+    xs = T.stranspose([2, 1, 0], glyphs)
+    result = rnnMnistZeroS(T, xs, params)
+    return nn.lossSoftMaxCrossEntropyS(T, T.stranspose([1, 0], labels), result, scale=1.0 / batch)

@@ -128,3 +128,81 @@ def lossSoftMaxCrossEntropyS_vectorised(T, expected, d, scale=1.0):
     soft = _mul(T, T.sreplicate0N(sh, recip_sum), expU)
     loss = T.unary("negate", T.sdot0(T.unary("log", soft), expected))
     return _mul(T, T.sscalar(scale, T.dtype(u)), loss)
+
+
+# ------------------------------------------------- dense-network pieces
+def logistic(T, d):
+    """logistic (CommonRankedOps.hs:55-63): y = recip (1 + exp (-d)) with the
+    custom dual y * (1 - y) * dd (not the derivative AD would assemble from
+    the three ops)."""
+    def primal(B, x):
+        one = B.srepl(list(B.shape(x)), 1, B.dtype(x))
+        return B.unary("recip", B.binary("add", one, B.unary("exp", B.unary("negate", x))))
+
+    def vjp(B, x, y, c):
+        one = B.srepl(list(B.shape(y)), 1, B.dtype(y))
+        return B.binary("mul", B.binary("mul", y, B.binary("sub", one, y)), c)
+    if hasattr(T, "custom_unary"):
+        return T.custom_unary(d, primal, vjp)
+    return primal(T, d)
+
+
+def softMax1(T, d):
+    """softMax1 (CommonRankedOps.hs:139-145)."""
+    expU = T.unary("exp", d)
+    return _mul(T, T.sreplicate0N(list(T.shape(d)), T.unary("recip", T.ssum0(expU))), expU)
+
+
+def lossCrossEntropyV(T, targ, res):
+    """lossCrossEntropyV (CommonRankedOps.hs:89-92)."""
+    return T.unary("negate", T.sdot0(T.unary("log", res), targ))
+
+
+# ------------------------------------------------ folds (tmapAccumL family)
+def smapAccumL(T, f, acc0, es):
+    """tmapAccumL (Ops.hs:987-1125) as the Concrete backend runs it
+    (tmapAccumLC, OpsConcrete.hs:990-1019): a host loop over the slices of
+    `es` along its leading axis, left to right; returns (acc, stacked bs).
+    Over an AD backend the unrolled ops record their own delta nodes, which
+    transposes to the same cotangents as the reference's tmapAccumR rule
+    (DeltaEval.hs:351-389)."""
+    acc, bs = acc0, []
+    for e in T.sunravelToList(es):
+        acc, b = f(acc, e)
+        if b is not None:
+            bs.append(b)
+    return acc, (T.sfromVector(bs) if bs else None)
+
+
+def sfold(T, f, acc0, es):
+    """sfold / rfold (Ops.hs:188-210): left fold of f :: acc -> e -> acc."""
+    return smapAccumL(T, lambda a, e: (f(a, e), None), acc0, es)[0]
+
+
+def sscan(T, f, acc0, es):
+    """sscan (Ops.hs:66-90 of the Concrete instance): acc0 followed by every
+    intermediate accumulator, stacked."""
+    accs = [acc0]
+    for e in T.sunravelToList(es):
+        accs.append(f(accs[-1], e))
+    return T.sfromVector(accs)
+
+
+# -------------------------------- per-element builds (non-vectorised code)
+def sbuild1(T, k, f):
+    """tsbuild1 (Ops.hs:910; OpsConcrete.hs:1761-1789): stack f 0 .. f (k-1).
+    Only reached by code the vectoriser did not touch; a host loop by design."""
+    return T.sfromVector([f(i) for i in range(k)])
+
+
+def smap0N(T, f, t):
+    """tsmap0N (Ops.hs:929): per-element host function over 0-d slices."""
+    sh = list(T.shape(t))
+    flat = T.sreshape([int(np.prod(sh))], t)
+    out = T.sfromVector([f(x) for x in T.sunravelToList(flat)])
+    return T.sreshape(sh, out)
+
+
+def scond(T, b: bool, u, v):
+    """scond / tcond (OpsConcrete.hs:113-119): a host `if` on a host Bool."""
+    return u if b else v

@@ -502,6 +502,81 @@ def test_mnist_cnn_gradient_vs_oracle(dev, oracle, fused):
         np.testing.assert_allclose(a, b, rtol=1e-10, atol=1e-13)
 
 
+@pytest.mark.parametrize("q", [np.float32, np.float64])
+def test_mnist_fcnn_gradient_vs_oracle(dev, oracle, q):
+    """MnistFcnnRanked2 (BASELINE config 1): loss and the 6 gradient leaves, with
+    the reference's mixed precision (Double net, Float second hidden layer)."""
+    from horde_ad_b200 import mnist_fcnn
+    rng = np.random.Generator(np.random.Philox(11))
+    datum, target = rng.uniform(0, 1, 784), np.eye(10)[7]
+    params = mnist_fcnn.init_params(30, 10, q=q)
+
+    def run(B):
+        ins = [B.sconcrete(p) for p in params]
+        d, t = B.sconcrete(datum), B.sconcrete(target)
+        val, grads = ad.grad(B, lambda T, *ps: mnist_fcnn.afcnnMnistLoss2(T, d, t, list(ps)), ins)
+        return float(B.kfromS(val)), [B.to_numpy(x) for x in grads]
+    dl, dg = run(dev)
+    ol, og = run(oracle)
+    tol = 1e-12 if q == np.float64 else 2e-5
+    np.testing.assert_allclose(dl, ol, rtol=tol * 10)
+    for a, b in zip(dg, og):
+        assert a.dtype == b.dtype
+        np.testing.assert_allclose(a, b, rtol=tol * 100, atol=tol * 10)
+
+
+def test_mnist_rnn_gradient_vs_oracle(dev, oracle):
+    """MnistRnnShaped2 (BASELINE config 5) at a small width: 28 unrolled steps of
+    two tanh layers (smatmul2 on the DMMA GEMM), loss and the 8 gradient leaves."""
+    from horde_ad_b200 import mnist_rnn
+    rng = np.random.Generator(np.random.Philox(12))
+    batch, width = 9, 24
+    glyphs, labels = rng.uniform(0, 1, (batch, 28, 28)), np.eye(10)[rng.integers(0, 10, batch)]
+    params = mnist_rnn.init_params(width, rng_range=0.2)
+
+    def run(B):
+        ins = [B.sconcrete(p) for p in params]
+        g, l = B.sconcrete(glyphs), B.sconcrete(labels)
+        val, grads = ad.grad(B, lambda T, *ps: mnist_rnn.rnnMnistLossFusedS(T, g, l, list(ps)), ins)
+        return float(B.kfromS(val)), [B.to_numpy(x) for x in grads]
+    dl, dg = run(dev)
+    ol, og = run(oracle)
+    np.testing.assert_allclose(dl, ol, rtol=1e-12)
+    for a, b in zip(dg, og):
+        np.testing.assert_allclose(a, b, rtol=1e-9, atol=1e-13)
+
+
+def test_folds_builds_and_cond(dev, oracle):
+    """tmapAccumL / tfold / tscan as host loops over device slices, tsbuild1,
+    tsmap0N, scond (non-vectorised code paths: they must work, not be fast)."""
+    rng = np.random.default_rng(23)
+    es, a0 = rng.uniform(-1, 1, (6, 3, 4)), rng.uniform(-1, 1, (3, 4))
+
+    def prog(T, acc0, xs):
+        step = lambda a, e: (T.binary("add", T.unary("sin", a), T.binary("mul", a, e)), T.unary("cos", a))
+        acc, bs = nn.smapAccumL(T, step, acc0, xs)
+        sc = nn.sscan(T, lambda a, e: T.binary("mul", a, e), acc0, xs)
+        return T.binary("add", T.ssum0(acc), T.binary("add", T.ssum0(bs), T.ssum0(sc)))
+
+    def run(B):
+        val, grads = ad.grad(B, prog, [B.sconcrete(a0), B.sconcrete(es)])
+        return float(B.kfromS(val)), [B.to_numpy(g) for g in grads]
+    dv, dg = run(dev)
+    ov, og = run(oracle)
+    np.testing.assert_allclose(dv, ov, rtol=1e-12)
+    for a, b in zip(dg, og):
+        np.testing.assert_allclose(a, b, rtol=1e-11, atol=1e-14)
+    # fold golden on the device: testSin0Fold2 (TestRevFwdFold.hs:545-550)
+    _, (g,) = ad.grad(dev, lambda T, x: nn.sfold(T, lambda a, _e: T.unary("sin", a), x, T.srepl([5], 42.0)), [dev.sscalar(1.1)])
+    np.testing.assert_allclose(float(dev.kfromS(g)), 0.12389721944941383, atol=1e-10)
+    t = dev.sconcrete(a0)
+    b1 = nn.sbuild1(dev, 4, lambda i: dev.binary("mul", t, dev.srepl([3, 4], float(i))))
+    exact(dev.to_numpy(b1), np.stack([a0 * i for i in range(4)]))
+    m0 = nn.smap0N(dev, lambda x: dev.unary("negate", x), t)
+    exact(dev.to_numpy(m0), -a0)
+    assert nn.scond(dev, dev.all_leq(t, t), t, m0) is t
+
+
 def test_graph_capture_replay(dev):
     rng = np.random.default_rng(20)
     x = dev.sconcrete(rng.uniform(-.5, .5, (64, 32)))

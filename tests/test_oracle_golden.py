@@ -102,3 +102,76 @@ def test_cnn_fusion_levels_agree_on_the_oracle(oracle, fused):
     np.testing.assert_allclose(float(v1), float(v0), rtol=1e-13)
     for a, b in zip(g1, g0):
         np.testing.assert_allclose(np.asarray(a), np.asarray(b), rtol=1e-10, atol=1e-14)
+
+
+def test_fold_goldens(oracle):
+    """rfold known answers (TestRevFwdFold.hs:516-596): pins tmapAccumL/tfold and
+    its reverse rule; eps 1e-10 as in the reference."""
+    o = oracle
+    x0 = o.sscalar(1.1)
+    sin = lambda T, v: T.unary("sin", v)
+    cases = [
+        # testSin0FoldB3 / B4: constant step functions
+        (lambda T, x: nn.sfold(T, lambda _x, _a: T.sscalar(7.0), T.sscalar(5.0), T.sreplicate(1, x)), 0.0),
+        (lambda T, x: nn.sfold(T, lambda _x, _a: T.sscalar(7.0), x, T.srepl([1], 42.0)), 0.0),
+        # testSin0Fold2: five nested sins of the accumulator
+        (lambda T, x: nn.sfold(T, lambda a, _e: sin(T, a), x, T.srepl([5], 42.0)), 0.12389721944941383),
+        # testSin0Fold3
+        (lambda T, a0: nn.sfold(T, lambda _x, a: sin(T, a), T.sscalar(84.0), T.sreplicate(3, a0)), 0.4535961214255773),
+        # testSin0Fold4
+        (lambda T, a0: nn.sfold(T, lambda x, a: T.binary("atan2", sin(T, x), sin(T, a)),
+                                T.binary("mul", T.sscalar(2.0), a0), T.sreplicate(3, a0)), -0.7053476446727861),
+    ]
+    for f, expected in cases:
+        _, (g,) = ad.grad(o, f, [x0])
+        np.testing.assert_allclose(float(np.asarray(g)), expected, atol=1e-10, rtol=0)
+
+    # testSin0Fold6 (= 6) and testSin0Fold7 (= 250): tensor-valued accumulators
+    def fold6(T, a0):
+        acc0 = T.sreplicate(2, T.sreplicate(1, a0))
+        step = lambda x, a: T.stranspose([1, 0], T.binary("add", T.stranspose([1, 0], x), T.sreplicate(1, T.sreplicate(2, a))))
+        return T.ssum0(nn.sfold(T, step, acc0, T.sreplicate(2, a0)))
+
+    def fold7(T, a0):
+        acc0 = T.sreplicate(2, T.sreplicate(5, a0))
+        step = lambda x, _a: T.stranspose([1, 0], T.sreplicate(5, T.ssum(T.stranspose([1, 0], x))))
+        return T.ssum0(nn.sfold(T, step, acc0, T.sreplicate(2, a0)))
+    for f, expected in ((fold6, 6.0), (fold7, 250.0)):
+        _, (g,) = ad.grad(o, f, [x0])
+        np.testing.assert_allclose(float(np.asarray(g)), expected, atol=1e-10, rtol=0)
+
+
+def test_fcnn_and_rnn_gradients_match_finite_differences(oracle):
+    """MnistFcnnRanked2 (logistic/softMax1/lossCrossEntropyV, Float hidden layer)
+    and MnistRnnShaped2 on the oracle: the dual-number gradient agrees with
+    central differences of the primal (their losses, unlike the CNN's fused
+    whole-tensor softmax with its custom dual, are plain compositions)."""
+    from horde_ad_b200 import mnist_fcnn
+    rng = np.random.Generator(np.random.Philox(3))
+    datum, target = rng.uniform(0, 1, 784), np.eye(10)[3]
+    params = mnist_fcnn.init_params(6, 5, rng_range=0.3, q=np.float64)
+    f = lambda ps: float(np.asarray(ad.grad(oracle, lambda T, *p: mnist_fcnn.afcnnMnistLoss2(T, datum, target, list(p)), ps)[0]))
+    _, grads = ad.grad(oracle, lambda T, *p: mnist_fcnn.afcnnMnistLoss2(T, datum, target, list(p)), params)
+    for k in (0, 2, 5):
+        idx = tuple(rng.integers(0, s) for s in params[k].shape)
+        e = 1e-6
+        pp = [p.copy() for p in params]; pp[k][idx] += e
+        pm = [p.copy() for p in params]; pm[k][idx] -= e
+        np.testing.assert_allclose(np.asarray(grads[k])[idx], (f(pp) - f(pm)) / (2 * e), rtol=1e-6, atol=1e-9)
+
+
+def test_committed_golden_fixture_is_in_sync(oracle):
+    """tests/golden/reference_goldens.json (written by tests/golden/make_golden.py)
+    carries the same literals the programs above are checked against, and the
+    oracle reproduces the conv entries straight from the file."""
+    import json, os
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_goldens.json")))
+    assert [e["name"] for e in g["gather_scatter_gradients"]] == [x[0] for x in P.GATHER_GOLDEN]
+    for e in g["conv_gradients"]:
+        K = np.array(e["K"]).reshape(e["K_shape"])
+        A = np.array(e["A"]).reshape(e["A_shape"])
+        if e["wrt"] == "A":
+            got = oracle.conv2d_dinp(K, np.ones((A.shape[0], K.shape[0], A.shape[2], A.shape[3])))
+        else:
+            got = oracle.conv2d_dkrn(A, np.ones((A.shape[0], K.shape[0], A.shape[2], A.shape[3])), K.shape[2], K.shape[3])
+        np.testing.assert_allclose(got.reshape(-1), e["expected_gradient"], atol=e["eps"], rtol=0)
