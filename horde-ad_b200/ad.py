@@ -340,14 +340,12 @@ class ADBackend:
         cotangent and one code byte per pooled element."""
         B = self.B
         K, bias, A = self.lift(K), self.lift(bias), self.lift(A)
-        KH, KW = B.shape(K.p)[2], B.shape(K.p)[3]
-        H, W = B.shape(A.p)[2], B.shape(A.p)[3]
-        y, code = B.relu_pool_fwd(B.conv2dPreserving(K.p, A.p), bias.p, ksize)
+        y, code = B.conv_relu_pool_fwd(K.p, bias.p, A.p, ksize)
 
         def pb(c):
-            dpre, dbias = B.relu_pool_bwd(c, code, ksize, H, W, want_bias=bias.d is not None)
-            return [B.conv2d_dkrn(A.p, dpre, KH, KW) if K.d is not None else None, dbias,
-                    B.conv2d_dinp(K.p, dpre) if A.d is not None else None]
+            dK, dbias, dA = B.conv_relu_pool_bwd(K.p, A.p, c, code, ksize, want_bias=bias.d is not None,
+                                                 want_dA=A.d is not None)
+            return [dK, dbias, dA]
         return self._node(y, [K, bias, A], pb)
 
     def custom_unary(self, t, primal, vjp):

@@ -286,8 +286,10 @@ static int contract_impl(const hb_array *a, const hb_array *b, int n_lead, hb_ar
     g->sb[k] = b->strides[i];
     g->sc[k] = oc;
   }
-  // worth a GEMM only when there is reuse on both sides
-  if (gemm && (nM < 16 || nN < 16 || K < 4)) gemm = false;
+  // worth a GEMM only when there is reuse on both sides (the cp.async-staged
+  // FP64 DMMA GEMM pads small sides cheaply, so it takes thin matrices too)
+  bool thin_ok = a->dt == HB_F64 && nM >= 4 && nN >= 4 && nM * nN >= 512 && K >= 8;
+  if (gemm && (nM < 16 || nN < 16 || K < 4) && !thin_ok) gemm = false;
   if (gemm) {
     for (int i = 0; i <= n_lead; i++) {
       int ax = i < n_lead ? i : r - 1;

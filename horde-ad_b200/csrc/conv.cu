@@ -19,8 +19,14 @@
 
 int hb_copy_into(hb_array *dst, const hb_array *src);  // elementwise.cu
 // conv_dmma.cu: shared-memory-staged DMMA kernels (contiguous f64 operands)
-int hb_conv_sp_dmma(const hb_array *K, const hb_array *in, hb_array *out, int flip, int *done);
-int hb_conv_dk_dmma(const hb_array *A, const hb_array *dB, hb_array *out, int KH, int KW, int *done);
+struct hb_pool_fuse {
+  const hb_array *bias;
+  hb_array *y, *code;
+};
+int hb_conv_sp_dmma(const hb_array *K, const hb_array *in, hb_array *out, int flip, const hb_pool_fuse *pf,
+                    int *done);
+int hb_conv_dk_dmma(const hb_array *A, const hb_array *dB, const hb_array *code, hb_array *out, int KH, int KW,
+                    int *done);
 
 // Runs the DMMA fast path into a fresh [n0,n1,n2,n3] array when it applies.
 static int try_sp(const hb_array *K, const hb_array *in, const int64_t *osh, int flip, hb_array **out, int *done) {
@@ -28,7 +34,7 @@ static int try_sp(const hb_array *K, const hb_array *in, const int64_t *osh, int
   if (in->dt != HB_F64 || !hb_contig(in)) return HB_OK;
   hb_array *o;
   HB_TRY(hb_new_array(HB_F64, 4, osh, &o));
-  int st = hb_conv_sp_dmma(K, in, o, flip, done);
+  int st = hb_conv_sp_dmma(K, in, o, flip, nullptr, done);
   if (st != HB_OK || !*done) {
     hb_release(o);
     return st;
@@ -127,7 +133,7 @@ extern "C" int hb_conv2d_preserving_dkrn(const hb_array *A, const hb_array *dB, 
     hb_array *o;
     int done = 0;
     HB_TRY(hb_new_array(HB_F64, 4, ksh, &o));
-    int st = hb_conv_dk_dmma(A, dB, o, KH, KW, &done);
+    int st = hb_conv_dk_dmma(A, dB, nullptr, o, KH, KW, &done);
     if (st == HB_OK && done) {
       *out = o;
       return HB_OK;
@@ -197,4 +203,92 @@ extern "C" int hb_conv2d_preserving_dinp(const hb_array *K, const hb_array *dB, 
   hb_release(vk);
   hb_release(Bp);
   return st;
+}
+
+// ------------------------------------------------ a whole convMnistLayerS
+extern "C" int hb_relu_pool_fwd(const hb_array *pre, const hb_array *bias, int ksize, hb_array **out,
+                                hb_array **code_out);
+extern "C" int hb_relu_pool_bwd(const hb_array *dy, const hb_array *code, int ksize, int64_t H, int64_t W,
+                                hb_array **dpre_out, hb_array **dbias_out);
+
+// maxPool k k (relu (conv2dPreserving K A + bias)) (MnistCnnShaped2.hs:42-62).  For
+// 2x2/2 windows on contiguous f64 operands the bias add, relu and pooling run in
+// the epilogue of the DMMA convolution kernel and the pre-activation never
+// reaches HBM; otherwise the two kernels run back to back.
+extern "C" int hb_conv_relu_pool_fwd(const hb_array *K, const hb_array *bias, const hb_array *A, int ksize,
+                                     hb_array **out, hb_array **code_out) {
+  hb_prof_scope prof_("conv_relu_pool_fwd", K, A);
+  HB_CHECK_INIT();
+  HB_REQUIRE(K && A && out && code_out, "null argument");
+  HB_REQUIRE(K->rank == 4 && A->rank == 4 && K->dt == A->dt && hb_is_float(A->dt) && K->shape[1] == A->shape[1],
+             "conv_relu_pool: kernel %s vs input %s", hb_shape_str(K).c_str(), hb_shape_str(A).c_str());
+  HB_REQUIRE(!bias || (bias->rank == 1 && bias->dt == A->dt && bias->shape[0] == K->shape[0]),
+             "conv_relu_pool: bias must be [%lld]", (long long)K->shape[0]);
+  HB_REQUIRE(ksize >= 1 && ksize <= 11, "conv_relu_pool: window must be 1..11");
+  int64_t N = A->shape[0], Co = K->shape[0], H = A->shape[2], W = A->shape[3];
+  if (ksize == 2 && A->dt == HB_F64 && N * Co * (H / 2) * (W / 2) > 0 && K->shape[1] * K->shape[2] * K->shape[3] > 0) {
+    int64_t osh[4] = {N, Co, H / 2, W / 2};
+    hb_pool_fuse pf;
+    pf.bias = bias;
+    pf.y = pf.code = nullptr;
+    int st = hb_new_array(HB_F64, 4, osh, &pf.y);
+    if (st == HB_OK) st = hb_new_array(HB_I8, 4, osh, &pf.code);
+    int done = 0;
+    if (st == HB_OK) st = hb_conv_sp_dmma(K, A, nullptr, 0, &pf, &done);
+    if (st == HB_OK && done) {
+      *out = pf.y;
+      *code_out = pf.code;
+      return HB_OK;
+    }
+    hb_release(pf.y);
+    hb_release(pf.code);
+    if (st != HB_OK) return st;
+  }
+  hb_array *pre;
+  HB_TRY(hb_conv2d_preserving(K, A, &pre));
+  int st = hb_relu_pool_fwd(pre, bias, ksize, out, code_out);
+  hb_release(pre);
+  return st;
+}
+
+// Adjoint of hb_conv_relu_pool_fwd: dK, dbias and (optionally) dA from the
+// pooled cotangent dy and the code bytes.  When dA is not wanted (first layer:
+// the glyphs are not differentiated) the full-size cotangent is never
+// materialised: the dKrn kernel expands (dy, code) inside shared memory.
+extern "C" int hb_conv_relu_pool_bwd(const hb_array *K, const hb_array *A, const hb_array *dy, const hb_array *code,
+                                     int ksize, hb_array **dK_out, hb_array **dbias_out, hb_array **dA_out) {
+  hb_prof_scope prof_("conv_relu_pool_bwd", A, dy);
+  HB_CHECK_INIT();
+  HB_REQUIRE(K && A && dy && code && dK_out, "null argument");
+  HB_REQUIRE(K->rank == 4 && A->rank == 4 && dy->rank == 4 && K->dt == A->dt && dy->dt == A->dt && hb_is_float(A->dt),
+             "conv_relu_pool_bwd: bad operands");
+  int64_t H = A->shape[2], W = A->shape[3];
+  int KH = (int)K->shape[2], KW = (int)K->shape[3];
+  int st = HB_OK;
+  if (!dA_out && ksize == 2 && A->dt == HB_F64 && hb_contig(A) && hb_contig(dy) && hb_numel(dy) > 0 &&
+      K->shape[1] * KH * KW > 0) {
+    hb_array *dk = nullptr;
+    int done = 0;
+    int64_t ksh[4] = {K->shape[0], K->shape[1], KH, KW};
+    HB_TRY(hb_new_array(HB_F64, 4, ksh, &dk));
+    st = hb_conv_dk_dmma(A, dy, code, dk, KH, KW, &done);
+    if (st == HB_OK && done) {
+      if (dbias_out) st = hb_relu_pool_bwd(dy, code, ksize, H, W, nullptr, dbias_out);
+      if (st != HB_OK) { hb_release(dk); return st; }
+      *dK_out = dk;
+      return HB_OK;
+    }
+    hb_release(dk);
+    if (st != HB_OK) return st;
+  }
+  hb_array *dpre = nullptr, *dk = nullptr, *da = nullptr, *db = nullptr;
+  HB_TRY(hb_relu_pool_bwd(dy, code, ksize, H, W, &dpre, dbias_out ? &db : nullptr));
+  st = hb_conv2d_preserving_dkrn(A, dpre, KH, KW, &dk);
+  if (st == HB_OK && dA_out) st = hb_conv2d_preserving_dinp(K, dpre, &da);
+  hb_release(dpre);
+  if (st != HB_OK) { hb_release(dk); hb_release(da); hb_release(db); return st; }
+  *dK_out = dk;
+  if (dbias_out) *dbias_out = db;
+  if (dA_out) *dA_out = da;
+  return HB_OK;
 }

@@ -115,6 +115,13 @@ struct SpP {
   int in_doubles, stage_doubles;
   int64_t sn, sp;
   int KWP;           // KW rounded up to 4 (TAPK)
+  // fused tail of convMnistLayerS: out is never written; instead
+  //   pool_out = maxPool 2x2/2 (relu (conv + bias)),  code_out = adjoint code
+  int pool;
+  const double *bias;
+  double *pool_out;
+  uint8_t *code_out;
+  int qg, OPS;       // channels per pooling round, position stride of the output tile
 };
 
 // Packs K into Wt[qt][p][tap][q] (tap stride TS, channel stride WCS), zero
@@ -191,7 +198,7 @@ __device__ __forceinline__ void sp_stage(double (&acc)[MF][NQ][2], const int (&a
   }
 }
 
-template <int WM, int WN, int MF, int NQ, bool TAPK, int MINB>
+template <int WM, int WN, int MF, int NQ, bool TAPK, int MINB, bool POOL>
 __global__ void __launch_bounds__(kThreads, MINB) conv_sp_kernel(const __grid_constant__ SpP p) {
   extern __shared__ __align__(16) double smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -204,6 +211,16 @@ __global__ void __launch_bounds__(kThreads, MINB) conv_sp_kernel(const __grid_co
 
   const int RW = g.R * g.W, npos = g.NI * RW, HW = g.H * g.W;
   const int F = (npos + 7) >> 3;
+  if (POOL) {  // window table: first position, image, pooled row in the band, pooled output offset
+    int4 *wl = reinterpret_cast<int4 *>(smem + 2 * p.stage_doubles + p.qg * p.OPS);
+    const int Wo = g.W >> 1, Ho = g.H >> 1, wpi = (g.R >> 1) * Wo, nwin = g.NI * wpi;
+    for (int w = tid; w < nwin; w += kThreads) {
+      int img = w / wpi, rem = w - img * wpi;
+      int i = rem / Wo, j = rem - i * Wo;
+      wl[w] = make_int4(img * RW + 2 * i * g.W + 2 * j, img, i, img * p.Q * Ho * Wo + i * Wo + j);
+    }
+    __syncthreads();
+  }
   // fragment f = i * WM + wm (strided over the warps of a column: balanced)
   int nf = (F - wm + WM - 1) / WM;
   nf = nf < 0 ? 0 : (nf > MF ? MF : nf);
@@ -275,22 +292,84 @@ __global__ void __launch_bounds__(kThreads, MINB) conv_sp_kernel(const __grid_co
       int it = blockIdx.x + (t / p.NCH) * gridDim.x;
       int nblk = it / g.bands, band = it - nblk * g.bands;
       int n0 = nblk * g.NI, y0 = band * g.R;
-      double *ob = p.out + ((int64_t)n0 * p.Q + qt * p.QT + wn * NQ * 8 + fk * 2) * HW + (int64_t)y0 * g.W;
       const int q0 = qt * p.QT + wn * NQ * 8 + fk * 2;
+      if (!POOL) {
+        double *ob = p.out + ((int64_t)n0 * p.Q + q0) * HW + (int64_t)y0 * g.W;
 #pragma unroll
-      for (int i = 0; i < MF; i++) {
-        if (i < nf) {
-          int img = pimy[i] >> 16, y = pimy[i] & 0xffff;
-          bool okp = n0 + img < p.N && y0 + y < g.H;
+        for (int i = 0; i < MF; i++) {
+          if (i < nf) {
+            int img = pimy[i] >> 16, y = pimy[i] & 0xffff;
+            bool okp = n0 + img < p.N && y0 + y < g.H;
 #pragma unroll
-          for (int j = 0; j < NQ; j++) {
+            for (int j = 0; j < NQ; j++) {
 #pragma unroll
-            for (int e = 0; e < 2; e++) {
-              if (okp && q0 + j * 8 + e < p.Q) ob[orel[i] + (int64_t)(j * 8 + e) * HW] = acc[i][j][e];
-              acc[i][j][e] = 0.0;
+              for (int e = 0; e < 2; e++) {
+                if (okp && q0 + j * 8 + e < p.Q) ob[orel[i] + (int64_t)(j * 8 + e) * HW] = acc[i][j][e];
+                acc[i][j][e] = 0.0;
+              }
             }
           }
         }
+      } else {
+        // bias + relu + 2x2 max-pool through a shared [channel][position] tile,
+        // qg channels per round; the pre-activation never goes to HBM
+        double *ot = smem + 2 * p.stage_doubles;
+        const int4 *wl = reinterpret_cast<const int4 *>(ot + p.qg * p.OPS);
+        const int Wo = g.W >> 1, Ho = g.H >> 1, nwin = npos >> 2;
+        double bv[NQ][2];
+#pragma unroll
+        for (int j = 0; j < NQ; j++)
+#pragma unroll
+          for (int e = 0; e < 2; e++) bv[j][e] = (p.bias && q0 + j * 8 + e < p.Q) ? p.bias[q0 + j * 8 + e] : 0.0;
+        const int64_t obase = ((int64_t)n0 * p.Q + qt * p.QT) * Ho * Wo + (int64_t)(y0 >> 1) * Wo;
+        for (int r0 = 0; r0 < p.QT; r0 += p.qg) {
+#pragma unroll
+          for (int i = 0; i < MF; i++) {
+            if (i < nf) {
+              int pidx = (i * WM + wm) * 8 + fr;
+#pragma unroll
+              for (int j = 0; j < NQ; j++) {
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                  int ql = wn * NQ * 8 + j * 8 + fk * 2 + e - r0;
+                  if (ql >= 0 && ql < p.qg && pidx < npos) ot[ql * p.OPS + pidx] = acc[i][j][e] + bv[j][e];
+                }
+              }
+            }
+          }
+          __syncthreads();
+          // all threads pool: thread (tid % hw) takes windows, tid / hw picks the channel lane
+          const int hw = nwin <= 64 ? 64 : (nwin <= 128 ? 128 : 256), lanes = kThreads / hw;
+          const int wbeg = tid % hw, qoff = tid / hw;
+          for (int ql = qoff; ql < p.qg; ql += lanes) {
+            int q = qt * p.QT + r0 + ql;
+            if (q >= p.Q) break;
+            const double *oq = ot + ql * p.OPS;
+            for (int w = wbeg; w < nwin; w += hw) {
+              const int4 wv = wl[w];
+              const int p00 = wv.x;
+              if (n0 + wv.y >= p.N || y0 + 2 * wv.z >= g.H) continue;
+              double2 r0v = *reinterpret_cast<const double2 *>(oq + p00);
+              double2 r1v = *reinterpret_cast<const double2 *>(oq + p00 + g.W);
+              double v[4] = {r0v.x, r0v.y, r1v.x, r1v.y};
+              double best = 0.0, bestpre = 0.0;
+              int bi = 0;
+#pragma unroll
+              for (int k = 0; k < 4; k++) {
+                double rl = (v[k] <= 0.0 ? 0.0 : 1.0) * v[k];
+                if (k == 0 || rl > best) { best = rl; bestpre = v[k]; bi = k; }
+              }
+              int64_t o = obase + (int64_t)(r0 + ql) * Ho * Wo + wv.w;
+              p.pool_out[o] = best;
+              p.code_out[o] = (uint8_t)(bi | (bestpre > 0.0 ? 0x80 : 0));
+            }
+          }
+          __syncthreads();
+        }
+#pragma unroll
+        for (int i = 0; i < MF; i++)
+#pragma unroll
+          for (int j = 0; j < NQ; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
       }
     }
     __syncthreads();
@@ -312,6 +391,14 @@ struct DkP {
   int a_doubles, stage_doubles;
   int64_t a_sn, a_sc, b_sn, b_so;
   int dbvec;
+  // pooled cotangent (adjoint of the fused bias + relu + 2x2 max-pool): dB is
+  // never materialised; dy [N,Co,H/2,W/2] and its code bytes are staged and
+  // expanded into the dB tile in shared memory
+  int pooled;
+  const double *dy;
+  const uint8_t *code;
+  int PW, PPS;     // pooled elements per (o, image) plane of a band, and their staging stride
+  int dyvec;
 };
 
 constexpr int kNP = 9;  // max column pairs per warp
@@ -341,10 +428,21 @@ __global__ void __launch_bounds__(kThreads, 2) conv_dk_kernel(const __grid_const
   const int wm = warp % WM, wn = (warp / WM) % p.WN, wk = warp / (WM * p.WN);
   const int fr = lane >> 2, fk = lane & 3;
   const TileGeo &g = p.g;
-  int *lut = reinterpret_cast<int *>(smem + 2 * p.stage_doubles);
+  // pooled mode: stages hold [A tile | pooled dy staging]; one expanded dB tile follows
+  double *dbx = smem + 2 * p.stage_doubles;
+  const int otile_rows = WM * MO * 8;
+  int *lut = reinterpret_cast<int *>(smem + 2 * p.stage_doubles + (p.pooled ? otile_rows * p.PS : 0));
+  int *lutp = lut + p.npos4;  // pooled index -> first position of its window inside one image band
 
-  for (int i = tid; i < 2 * p.stage_doubles; i += kThreads) smem[i] = 0.0;
+  for (int i = tid; i < 2 * p.stage_doubles + (p.pooled ? otile_rows * p.PS : 0); i += kThreads) smem[i] = 0.0;
   const int RW = g.R * g.W, npos = g.NI * RW;
+  if (p.pooled) {
+    const int Wo = g.W >> 1;
+    for (int i = tid; i < p.PW; i += kThreads) {
+      int pi = i / Wo, pj = i - pi * Wo;
+      lutp[i] = 2 * pi * g.W + 2 * pj;
+    }
+  }
   for (int i = tid; i < p.npos4; i += kThreads) {
     int off = 0;
     if (i < npos) {
@@ -393,12 +491,36 @@ __global__ void __launch_bounds__(kThreads, 2) conv_dk_kernel(const __grid_const
     int n0 = nblk * g.NI, y0 = band * g.R;
     double *st = smem + (t & 1) * p.stage_doubles;
     load_in_tile(st, p.A, g, p.CC, c0, p.Ci, n0, p.N, y0, p.a_sn, p.a_sc, tid);
-    // dB tile: [o][img * RW + y * W + x], rows beyond the image zero; a warp
-    // owns whole (o, img) planes, lanes run along the contiguous positions
     double *db = st + p.a_doubles;
     int rows_ok = g.H - y0 < g.R ? g.H - y0 : g.R;
-    int nval = rows_ok * g.W;
     const int planes = co * g.NI;
+    if (p.pooled) {
+      // pooled cotangent of the band: (rows_ok / 2) * (W / 2) contiguous doubles per (o, image)
+      const int Ho = g.H >> 1, Wo = g.W >> 1;
+      const int nvalp = (rows_ok >> 1) * Wo;
+      for (int pl = warp; pl < planes; pl += kThreads / 32) {
+        int o = pl / g.NI, img = pl - o * g.NI;
+        double *d0 = db + pl * p.PPS;
+        bool okn = n0 + img < p.N;
+        const double *s0 = p.dy + (((int64_t)(n0 + img) * p.Co + o_tile + o) * Ho + (y0 >> 1)) * Wo;
+        if (p.dyvec) {
+          for (int ch = lane * 2; ch < p.PW; ch += 64) {
+            if (okn && ch < nvalp) cp16(d0 + ch, s0 + ch);
+            else *reinterpret_cast<double2 *>(d0 + ch) = make_double2(0.0, 0.0);
+          }
+        } else {
+          for (int ch = lane; ch < p.PW; ch += 32) {
+            if (okn && ch < nvalp) cp8(d0 + ch, s0 + ch);
+            else d0[ch] = 0.0;
+          }
+        }
+      }
+      cp_commit();
+      return;
+    }
+    // dB tile: [o][img * RW + y * W + x], rows beyond the image zero; a warp
+    // owns whole (o, img) planes, lanes run along the contiguous positions
+    int nval = rows_ok * g.W;
     for (int pl = warp; pl < planes; pl += kThreads / 32) {
       int o = pl / g.NI, img = pl - o * g.NI;
       double *d0 = db + o * p.PS + img * RW;
@@ -428,8 +550,36 @@ __global__ void __launch_bounds__(kThreads, 2) conv_dk_kernel(const __grid_const
       cp_wait<0>();
     }
     __syncthreads();
+    if (p.pooled) {
+      // expand the staged pooled cotangent of stage t into the dB tile:
+      // window position `code & 0x7f` receives dy where the relu was active
+      // (code & 0x80), the other three positions of the window zero
+      int it = blockIdx.x + t * gridDim.x;
+      int nblk = it / g.bands, band = it - nblk * g.bands;
+      int n0 = nblk * g.NI, y0 = band * g.R;
+      int rows_ok = g.H - y0 < g.R ? g.H - y0 : g.R;
+      const int Ho = g.H >> 1, Wo = g.W >> 1, nvalp = (rows_ok >> 1) * Wo;
+      const double *dyp = smem + (t & 1) * p.stage_doubles + p.a_doubles;
+      const int planes = co * g.NI;
+      for (int pl = warp; pl < planes; pl += kThreads / 32) {
+        int o = pl / g.NI, img = pl - o * g.NI;
+        bool okn = n0 + img < p.N;
+        const uint8_t *c0p = p.code + (((int64_t)(n0 + img) * p.Co + o_tile + o) * Ho + (y0 >> 1)) * Wo;
+        double *x0 = dbx + o * p.PS + img * RW;
+        const double *d0 = dyp + pl * p.PPS;
+        for (int idx = lane; idx < p.PW; idx += 32) {
+          unsigned cd = (okn && idx < nvalp) ? c0p[idx] : 0u;
+          double gv = (cd & 0x80u) ? d0[idx] : 0.0;
+          int bi = cd & 0x7f;
+          double *xp = x0 + lutp[idx];
+          *reinterpret_cast<double2 *>(xp) = make_double2(bi == 0 ? gv : 0.0, bi == 1 ? gv : 0.0);
+          *reinterpret_cast<double2 *>(xp + g.W) = make_double2(bi == 2 ? gv : 0.0, bi == 3 ? gv : 0.0);
+        }
+      }
+      __syncthreads();
+    }
     const char *As = reinterpret_cast<const char *>(smem + (t & 1) * p.stage_doubles);
-    const double *Bs = smem + (t & 1) * p.stage_doubles + p.a_doubles + (wm * MO * 8 + fr) * p.PS + fk;
+    const double *Bs = (p.pooled ? dbx : smem + (t & 1) * p.stage_doubles + p.a_doubles) + (wm * MO * 8 + fr) * p.PS + fk;
     const int kbeg = wk * 4, kstep = 4 * p.WK;
     switch (npw) {  // exact pair count: no predicated-off DMMAs (they would still occupy the pipe)
       case 9: dk_stage<9, MO>(acc, pair_off, As, Bs, lut + fk, kbeg, kstep, p); break;
@@ -534,6 +684,13 @@ static inline int stride4mod8(int n) {
   if (s - 8 >= n) s -= 8;
   return s;
 }
+// position stride of the pooled epilogue's output tile: >= n, = 2 (mod 4), so the
+// fragment stores of a half-warp (4 channel pairs x 4 positions) hit distinct banks
+static inline int pool_stride(int n) {
+  int s = round_up(n, 4) + 2;
+  if (s - 4 >= n) s -= 4;
+  return s;
+}
 static inline void set_pieces(TileGeo &g) {
   g.cpr = g.vec ? g.W / 2 : g.W;
   g.cshift = 0;
@@ -548,15 +705,27 @@ static int set_smem(K kernel, int bytes) {
 
 }  // namespace
 
+struct hb_pool_fuse {
+  const hb_array *bias;  // [Q] or NULL
+  hb_array *y, *code;    // [N,Q,H/2,W/2] f64 / i8
+};
+
 // ------------------------------------------------------------------ hosts
 // Returns HB_OK and sets *done = 1 when the fast path ran.
 // flip = 0: forward (in = A[N,P,H,W], K[Q,P,KH,KW]); flip = 1: dInp
 // (in = dB[N,P,H,W], K[P,Q,KH,KW]).  `in` contiguous f64, out contiguous.
-int hb_conv_sp_dmma(const hb_array *K, const hb_array *in, hb_array *out, int flip, int *done) {
+// pf != NULL: fused bias + relu + 2x2/2 max-pool epilogue (forward only): `out`
+// is ignored, pf->y [N,Q,H/2,W/2] f64 and pf->code (i8) are written instead.
+int hb_conv_sp_dmma(const hb_array *K, const hb_array *in, hb_array *out, int flip, const hb_pool_fuse *pf,
+                    int *done) {
   *done = 0;
-  if (in->dt != HB_F64 || !hb_contig(in) || !hb_contig(out)) return HB_OK;
+  if (in->dt != HB_F64 || !hb_contig(in)) return HB_OK;
+  if (pf ? (flip || !hb_contig(pf->y) || !hb_contig(pf->code) || (pf->bias && !hb_contig(pf->bias)))
+         : !hb_contig(out))
+    return HB_OK;
   int N = (int)in->shape[0], P = (int)in->shape[1], H = (int)in->shape[2], W = (int)in->shape[3];
-  int Q = (int)out->shape[1];
+  int Q = flip ? (int)K->shape[1] : (int)K->shape[0];
+  if (pf && ((H & 1) || (W & 1) || H < 2 || W < 2)) return HB_OK;
   int KH = (int)K->shape[2], KW = (int)K->shape[3];
   if ((int64_t)N * P * H * W >= (1ll << 31) || (int64_t)N * Q * H * W >= (1ll << 31)) return HB_OK;
   if (W > 224 || KH > 16 || KW > 16 || H >= 32768) return HB_OK;
@@ -573,6 +742,7 @@ int hb_conv_sp_dmma(const hb_array *K, const hb_array *in, hb_array *out, int fl
   else if (Q <= 16) { WN = 1; NQ = 2; }
   else if (Q <= 32) { WN = 2; NQ = 2; }
   else { WN = 2; NQ = 4; }
+  if (pf && NQ == 4) return HB_OK;  // 64-channel tile: pooled epilogue not instantiated, unfused path
   const int WM = 8 / WN, MF = 7;
   const bool one_cta = (NQ == 4);  // 56 accumulator doubles per thread: 1 CTA / SM
   p.QT = WN * NQ * 8;
@@ -597,11 +767,22 @@ int hb_conv_sp_dmma(const hb_array *K, const hb_array *in, hb_array *out, int fl
     for (int cand = 0; cand < 64; cand++) {
       int NI, R;
       if (H * W <= slots) { NI = cand + 1; R = H; if (NI > N || NI * H * W > slots) break; }
-      else { NI = 1; R = slots / W - cand; if (R < 1) break; int nb = (H + R - 1) / R; R = (H + nb - 1) / nb; }
+      else {
+        NI = 1; R = slots / W - cand; if (R < 1) break;
+        int nb = (H + R - 1) / R; R = (H + nb - 1) / nb;
+        if (pf && (R & 1)) { R++; if (R * W > slots) continue; }  // bands hold whole pooling windows
+      }
       int TR = R + KH - 1, IS = TR * g.RS;
       int CS = stride4mod8(NI * IS + (tapk ? 4 : 0));
       int per_c = CS + p.WCS;
-      int maxc = (budgets[bi] / 8 / 2) / per_c;
+      // fused pooling: room for an output tile of at least min(QT, 8) channels + the window table
+      int extra = 0;
+      if (pf) {
+        int np = NI * R * W;
+        extra = (p.QT < 8 ? p.QT : 8) * pool_stride(np) * 8 + (np / 4) * 16 + 64;
+      }
+      if (budgets[bi] - extra < 0) continue;
+      int maxc = ((budgets[bi] - extra) / 8 / 2) / per_c;
       if (!tapk) maxc = maxc / 4 * 4;
       if (maxc < (tapk ? 1 : 4)) continue;
       int CC = maxc < Pq ? maxc : Pq;
@@ -635,10 +816,25 @@ int hb_conv_sp_dmma(const hb_array *K, const hb_array *in, hb_array *out, int fl
   p.N = N; p.P = P; p.Q = Q;
   p.sn = in->strides[0]; p.sp = in->strides[1];
   p.in = (const double *)hb_data(in);
-  p.out = (double *)hb_data(out);
   g.vec = (W % 2 == 0) && (g.ox % 2 == 0) && (((uintptr_t)p.in & 15) == 0) && (p.sn % 2 == 0) && (p.sp % 2 == 0);
   set_pieces(g);
   int smem_bytes = 2 * p.stage_doubles * 8;
+  if (pf) {
+    const int np = g.NI * g.R * W;
+    p.pool = 1;
+    p.OPS = pool_stride(np);
+    p.bias = pf->bias ? (const double *)hb_data(pf->bias) : nullptr;
+    p.pool_out = (double *)hb_data(pf->y);
+    p.code_out = (uint8_t *)hb_data(pf->code);
+    int budget = ctas == 2 ? kSmemMax / 2 - 1024 : kSmemMax;
+    int avail = budget - smem_bytes - (np / 4) * 16 - 64;
+    p.qg = p.QT;
+    while (p.qg > 1 && p.qg * p.OPS * 8 > avail) p.qg >>= 1;
+    if (p.qg < 2 || p.qg * p.OPS * 8 > avail) return HB_OK;
+    smem_bytes += p.qg * p.OPS * 8 + (np / 4) * 16 + 64;
+  } else {
+    p.out = (double *)hb_data(out);
+  }
   if (smem_bytes > kSmemMax) return HB_OK;
   // packed weights in scratch
   int64_t wn = (int64_t)nqt * p.Ppad * p.WCS;
@@ -654,33 +850,47 @@ int hb_conv_sp_dmma(const hb_array *K, const hb_array *in, hb_array *out, int fl
   }
   int maxg = g_hb.sm_count * ctas;
   dim3 grid((unsigned)(p.items < maxg ? p.items : maxg), (unsigned)nqt);
-#define SP_LAUNCH(WM_, WN_, NQ_, MINB_)                                                                  \
-  do {                                                                                                   \
-    if (tapk) {                                                                                          \
-      HB_TRY(set_smem(conv_sp_kernel<WM_, WN_, 7, NQ_, true, MINB_>, smem_bytes));                       \
-      conv_sp_kernel<WM_, WN_, 7, NQ_, true, MINB_><<<grid, kThreads, smem_bytes, g_hb.stream>>>(p);     \
-    } else {                                                                                             \
-      HB_TRY(set_smem(conv_sp_kernel<WM_, WN_, 7, NQ_, false, MINB_>, smem_bytes));                      \
-      conv_sp_kernel<WM_, WN_, 7, NQ_, false, MINB_><<<grid, kThreads, smem_bytes, g_hb.stream>>>(p);    \
-    }                                                                                                    \
+#define SP_LAUNCH2(WM_, WN_, NQ_, MINB_, TAPK_, POOL_)                                                            \
+  do {                                                                                                           \
+    HB_TRY(set_smem(conv_sp_kernel<WM_, WN_, 7, NQ_, TAPK_, MINB_, POOL_>, smem_bytes));                         \
+    conv_sp_kernel<WM_, WN_, 7, NQ_, TAPK_, MINB_, POOL_><<<grid, kThreads, smem_bytes, g_hb.stream>>>(p);       \
+  } while (0)
+#define SP_LAUNCH(WM_, WN_, NQ_, MINB_)                                                \
+  do {                                                                                 \
+    if (pf) {                                                                          \
+      if (tapk) SP_LAUNCH2(WM_, WN_, NQ_, MINB_, true, true);                          \
+      else SP_LAUNCH2(WM_, WN_, NQ_, MINB_, false, true);                              \
+    } else {                                                                           \
+      if (tapk) SP_LAUNCH2(WM_, WN_, NQ_, MINB_, true, false);                         \
+      else SP_LAUNCH2(WM_, WN_, NQ_, MINB_, false, false);                             \
+    }                                                                                  \
   } while (0)
   if (WN == 1 && NQ == 1) SP_LAUNCH(8, 1, 1, 2);
   else if (WN == 1 && NQ == 2) SP_LAUNCH(8, 1, 2, 2);
   else if (WN == 2 && NQ == 2) SP_LAUNCH(4, 2, 2, 2);
-  else SP_LAUNCH(4, 2, 4, 1);
+  else {
+    if (tapk) SP_LAUNCH2(4, 2, 4, 1, true, false);
+    else SP_LAUNCH2(4, 2, 4, 1, false, false);
+  }
 #undef SP_LAUNCH
+#undef SP_LAUNCH2
   HB_LAUNCHED();
   (void)MF;
   *done = 1;
   return HB_OK;
 }
 
-// dK[Co,Ci,KH,KW] from A[N,Ci,H,W], dB[N,Co,H,W] (contiguous f64).
-int hb_conv_dk_dmma(const hb_array *A, const hb_array *dB, hb_array *out, int KH, int KW, int *done) {
+// dK[Co,Ci,KH,KW] from A[N,Ci,H,W], dB[N,Co,H,W] (contiguous f64).  With
+// `code` != NULL, dB is instead the POOLED cotangent dy [N,Co,H/2,W/2] of the
+// fused bias + relu + 2x2 max-pool and `code` its adjoint code bytes.
+int hb_conv_dk_dmma(const hb_array *A, const hb_array *dB, const hb_array *code, hb_array *out, int KH, int KW,
+                    int *done) {
   *done = 0;
   if (A->dt != HB_F64 || !hb_contig(A) || !hb_contig(dB) || !hb_contig(out)) return HB_OK;
   int N = (int)A->shape[0], Ci = (int)A->shape[1], H = (int)A->shape[2], W = (int)A->shape[3];
   int Co = (int)dB->shape[1];
+  const bool pooled = code != nullptr;
+  if (pooled && (!hb_contig(code) || (H & 1) || (W & 1) || H < 2 || W < 2)) return HB_OK;
   if ((int64_t)N * Ci * H * W >= (1ll << 31) || (int64_t)N * Co * H * W >= (1ll << 31)) return HB_OK;
   if (W > 256 || KH > 16 || KW > 16) return HB_OK;
   DkP p;
@@ -733,15 +943,26 @@ int hb_conv_dk_dmma(const hb_array *A, const hb_array *dB, hb_array *out, int KH
   // when that still leaves at least a quarter of the image per stage
   const int red_bytes = p.WK > 1 ? 8 * MO * kNP * 64 * 8 : 0;  // end-of-kernel K-split reduction area
   int NI = 1, ctas = 1;
+  auto smem_need = [&]() {
+    int b = 2 * p.stage_doubles * 8 + p.npos4 * 4 + 16;
+    if (pooled) b += otile * p.PS * 8 + p.PW * 4 + 16;
+    return b;
+  };
   auto fits = [&](int R, int budget) {
+    if (pooled && (R & 1)) return false;  // bands hold whole pooling windows
     g.R = R; g.NI = NI; g.TR = R + KH - 1; g.IS = g.TR * g.RS;
     g.CS = stride4mod8(NI * g.IS + (tapw ? 8 : 0));
     p.npos4 = round_up(NI * R * W, 4);
     p.PS = stride4mod8(p.npos4);
     p.a_doubles = round_up(CC * g.CS, 2);
-    p.stage_doubles = p.a_doubles + otile * p.PS;
-    int bytes = 2 * p.stage_doubles * 8 + p.npos4 * 4 + 16;
-    return bytes <= budget && red_bytes <= budget;
+    if (pooled) {
+      p.PW = (R / 2) * (W / 2);
+      p.PPS = round_up(p.PW, 2);
+      p.stage_doubles = p.a_doubles + round_up(otile * NI * p.PPS, 2);
+    } else {
+      p.stage_doubles = p.a_doubles + otile * p.PS;
+    }
+    return smem_need() <= budget && red_bytes <= budget;
   };
   int R = 0;
   for (int nb = 1; nb <= H && !R; nb++) {  // fewest bands first
@@ -765,7 +986,13 @@ int hb_conv_dk_dmma(const hb_array *A, const hb_array *dB, hb_array *out, int KH
   set_pieces(g);
   p.dbvec = ((g.R * W) % 2 == 0) && (W % 2 == 0) && (((uintptr_t)p.dB & 15) == 0) && (p.b_sn % 2 == 0) &&
             (p.b_so % 2 == 0);
-  int smem_bytes = 2 * p.stage_doubles * 8 + p.npos4 * 4 + 16;
+  if (pooled) {
+    p.pooled = 1;
+    p.dy = p.dB;
+    p.code = (const uint8_t *)hb_data(code);
+    p.dyvec = (((H / 2) * (W / 2)) % 2 == 0) && (p.PW % 2 == 0) && (((uintptr_t)p.dy & 15) == 0);
+  }
+  int smem_bytes = smem_need();
   if (smem_bytes < red_bytes) smem_bytes = red_bytes;
   int splits = g_hb.sm_count * ctas / (ncc * not_);
   if (splits < 1) splits = 1;

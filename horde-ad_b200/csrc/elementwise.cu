@@ -141,17 +141,51 @@ extern "C" int hb_stack(int k, hb_array *const *arrs, hb_array **out) {
 
 // Flatten k arrays (row-major) and concatenate them into one vector: the
 // contiguous gradient bucket of the data-parallel loop.
+// all leaves contiguous (the usual case: gradient leaves): ONE launch moves up
+// to 16 of them; blockIdx.y selects the leaf
+struct hb_concat_tab {
+  const void *src[16];
+  int64_t off[16], n[16];
+};
+template <typename T>
+__global__ void __launch_bounds__(256) hb_concat_kernel(const __grid_constant__ hb_concat_tab tab, T *__restrict__ dst) {
+  const int k = blockIdx.y;
+  const T *s = (const T *)tab.src[k];
+  T *d = dst + tab.off[k];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < tab.n[k]; i += (int64_t)gridDim.x * blockDim.x)
+    d[i] = s[i];
+}
+
 extern "C" int hb_flatten_concat(int k, hb_array *const *arrs, hb_array **out) {
   hb_prof_scope prof_("flatten_concat");
   HB_CHECK_INIT();
   HB_REQUIRE(out && k > 0 && arrs, "flatten_concat: empty list");
-  int64_t total = 0;
+  int64_t total = 0, maxn = 0;
+  bool all_contig = k <= 16;
   for (int i = 0; i < k; i++) {
     HB_REQUIRE(arrs[i] && arrs[i]->dt == arrs[0]->dt, "flatten_concat: dtype mismatch at %d", i);
-    total += hb_numel(arrs[i]);
+    int64_t n = hb_numel(arrs[i]);
+    total += n;
+    if (n > maxn) maxn = n;
+    if (!hb_contig(arrs[i])) all_contig = false;
   }
   hb_array *o;
   HB_TRY(hb_new_array(arrs[0]->dt, 1, &total, &o));
+  if (all_contig && total > 0) {
+    hb_concat_tab tab;
+    int64_t p = 0;
+    for (int i = 0; i < 16; i++) {
+      tab.src[i] = i < k ? hb_data(arrs[i]) : nullptr;
+      tab.n[i] = i < k ? hb_numel(arrs[i]) : 0;
+      tab.off[i] = p;
+      p += tab.n[i];
+    }
+    dim3 grid((unsigned)hb_blocks_for(maxn, 256 * 4, g_hb.sm_count * 4), (unsigned)k);
+    HB_DISPATCH_BYTES(arrs[0]->dt, T, (hb_concat_kernel<T><<<grid, 256, 0, g_hb.stream>>>(tab, (T *)hb_data(o))));
+    HB_LAUNCHED();
+    *out = o;
+    return HB_OK;
+  }
   int64_t pos = 0;
   for (int i = 0; i < k; i++) {
     int64_t n = hb_numel(arrs[i]);

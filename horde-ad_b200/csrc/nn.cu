@@ -243,7 +243,7 @@ extern "C" int hb_relu_pool_fwd(const hb_array *pre, const hb_array *bias, int k
 // bias cotangent  dbias[c] = sum_{n,i,j} of the same values, reduced per
 // (channel, image chunk) block in a fixed tree order, then over chunks in
 // order by hb_bias_finish_kernel: deterministic.
-template <typename T, bool VEC2>
+template <typename T, bool VEC2, bool WRITE>
 __global__ void __launch_bounds__(256)
     hb_relu_pool_bwd_kernel(const T *__restrict__ dy, const uint8_t *__restrict__ code, int N, int C, int H, int W,
                             int ks, int Ho, int Wo, int npc, T *__restrict__ dpre, T *__restrict__ part) {
@@ -258,8 +258,10 @@ __global__ void __launch_bounds__(256)
     int wi = w / Wo, wj = w - wi * Wo;
     int64_t o = ((int64_t)n * C + c) * HW + w;
     uint8_t cd = code[o];
-    T g = (cd & 0x80) ? dy[o] : T(0);
+    T dv = dy[o];               // independent of the code load (no serialised latency)
+    T g = (cd & 0x80) ? dv : T(0);
     acc += g;
+    if (!WRITE) continue;
     int bi = cd & 0x7f;
     T *p = dpre + (((int64_t)n * C + c) * H + (int64_t)wi * ks) * W + (int64_t)wj * ks;
     if (VEC2) {
@@ -297,7 +299,8 @@ extern "C" int hb_relu_pool_bwd(const hb_array *dy, const hb_array *code, int ks
                                 hb_array **dpre_out, hb_array **dbias_out) {
   hb_prof_scope prof_("relu_pool_bwd", dy);
   HB_CHECK_INIT();
-  HB_REQUIRE(dy && code && dpre_out, "null argument");
+  HB_REQUIRE(dy && code && (dpre_out || dbias_out), "null argument");
+  const bool write = dpre_out != nullptr;  // NULL: only the bias cotangent is wanted
   HB_REQUIRE(dy->rank == 4 && hb_is_float(dy->dt) && code->dt == HB_I8 && hb_same_shape(dy, code),
              "relu_pool_bwd: bad operands");
   HB_REQUIRE(ksize >= 1 && ksize <= 11 && dy->shape[2] == H / ksize && dy->shape[3] == W / ksize,
@@ -313,11 +316,11 @@ extern "C" int hb_relu_pool_bwd(const hb_array *dy, const hb_array *code, int ks
   int64_t N = dy->shape[0], C = dy->shape[1];
   int64_t xsh[4] = {N, C, H, W};
   hb_array *dx = nullptr, *db = nullptr;
-  int st = hb_new_array(dy->dt, 4, xsh, &dx);
+  int st = write ? hb_new_array(dy->dt, 4, xsh, &dx) : HB_OK;
   if (st == HB_OK) st = hb_new_array(dy->dt, 1, &C, &db);
-  if (st == HB_OK && hb_numel(dx) > 0) {
+  if (st == HB_OK && N * C * H * W > 0) {
     size_t es = hb_dtype_size(dy->dt);
-    bool leftover = (H % ksize) || (W % ksize);
+    bool leftover = write && ((H % ksize) || (W % ksize));
     if (leftover) {
       cudaError_t e = cudaMemsetAsync(hb_data(dx), 0, (size_t)hb_numel(dx) * es, g_hb.stream);
       if (e != cudaSuccess) { hb_set_error("memset: %s", cudaGetErrorString(e)); st = HB_ERR_CUDA; }
@@ -330,14 +333,14 @@ extern "C" int hb_relu_pool_bwd(const hb_array *dy, const hb_array *code, int ks
     void *scr = nullptr;
     if (st == HB_OK) st = hb_scratch((size_t)C * nchunks * es, &scr);
     if (st == HB_OK && hb_numel(dy) > 0) {
-      bool vec = ksize == 2 && W % 2 == 0 && ((uintptr_t)hb_data(dx) % (2 * es)) == 0;
+      bool vec = write && ksize == 2 && W % 2 == 0 && ((uintptr_t)hb_data(dx) % (2 * es)) == 0;
       dim3 grid((unsigned)C, (unsigned)nchunks);
-#define RPB_LAUNCH(T, V)                                                                                    \
-  hb_relu_pool_bwd_kernel<T, V><<<grid, 256, 0, g_hb.stream>>>(                                             \
+#define RPB_LAUNCH(T, V, WR)                                                                                \
+  hb_relu_pool_bwd_kernel<T, V, WR><<<grid, 256, 0, g_hb.stream>>>(                                         \
       (const T *)hb_data(dyc), (const uint8_t *)hb_data(cc), (int)N, (int)C, (int)H, (int)W, ksize,         \
-      (int)dy->shape[2], (int)dy->shape[3], npc, (T *)hb_data(dx), (T *)scr)
-      if (dy->dt == HB_F64) { if (vec) RPB_LAUNCH(double, true); else RPB_LAUNCH(double, false); }
-      else { if (vec) RPB_LAUNCH(float, true); else RPB_LAUNCH(float, false); }
+      (int)dy->shape[2], (int)dy->shape[3], npc, write ? (T *)hb_data(dx) : nullptr, (T *)scr)
+      if (dy->dt == HB_F64) { if (!write) RPB_LAUNCH(double, false, false); else if (vec) RPB_LAUNCH(double, true, true); else RPB_LAUNCH(double, false, true); }
+      else { if (!write) RPB_LAUNCH(float, false, false); else if (vec) RPB_LAUNCH(float, true, true); else RPB_LAUNCH(float, false, true); }
 #undef RPB_LAUNCH
       g_hb.launches.fetch_add(1);
       if (g_hb.profiling) hb_prof_mark(__func__, __LINE__);
@@ -356,7 +359,7 @@ extern "C" int hb_relu_pool_bwd(const hb_array *dy, const hb_array *code, int ks
   hb_release(t1);
   hb_release(t2);
   if (st != HB_OK) { hb_release(dx); hb_release(db); return st; }
-  *dpre_out = dx;
+  if (dpre_out) *dpre_out = dx;
   if (dbias_out) *dbias_out = db; else hb_release(db);
   return HB_OK;
 }

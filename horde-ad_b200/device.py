@@ -388,6 +388,17 @@ class DeviceBackend:
         call("hb_relu_pool_bwd", dy.h, code.h, ksize, H, W, C.byref(dp), C.byref(db) if want_bias else None)
         return _wrap(dp), (_wrap(db) if want_bias else None)
 
+    def conv_relu_pool_fwd(self, K, bias, A, ksize):
+        y, code = _out(), _out()
+        call("hb_conv_relu_pool_fwd", K.h, bias.h if bias is not None else None, A.h, ksize, C.byref(y), C.byref(code))
+        return _wrap(y), _wrap(code)
+
+    def conv_relu_pool_bwd(self, K, A, dy, code, ksize, want_bias=True, want_dA=True):
+        dk, db, da = _out(), _out(), _out()
+        call("hb_conv_relu_pool_bwd", K.h, A.h, dy.h, code.h, ksize, C.byref(dk),
+             C.byref(db) if want_bias else None, C.byref(da) if want_dA else None)
+        return _wrap(dk), (_wrap(db) if want_bias else None), (_wrap(da) if want_dA else None)
+
     def softmax_xent(self, logits, expected, scale=1.0, want_grad=True):
         l, d = _out(), _out()
         call("hb_softmax_xent", logits.h, expected.h, float(scale), C.byref(l),

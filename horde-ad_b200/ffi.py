@@ -94,6 +94,8 @@ PROTOTYPES = {
     "hb_maxpool2d_bwd": [P, P, C.c_int, C.c_int, C.c_int64, C.c_int64, PP],
     "hb_relu_pool_fwd": [P, P, C.c_int, PP, PP],
     "hb_relu_pool_bwd": [P, P, C.c_int, C.c_int64, C.c_int64, PP, PP],
+    "hb_conv_relu_pool_fwd": [P, P, P, C.c_int, PP, PP],
+    "hb_conv_relu_pool_bwd": [P, P, P, P, C.c_int, PP, PP, PP],
     "hb_softmax_xent": [P, P, C.c_double, PP, PP],
     "hb_sgd_step": [P, P, C.c_double],
     "hb_adam_step": [P, P, P, P, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int64],

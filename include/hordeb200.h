@@ -381,6 +381,21 @@ int hb_relu_pool_fwd(const hb_array *pre, const hb_array *bias, int ksize,
 int hb_relu_pool_bwd(const hb_array *dy, const hb_array *code, int ksize,
                      int64_t H, int64_t W, hb_array **dpre_out,
                      hb_array **dbias_out /* may be NULL */);
+/* A whole convMnistLayerS (MnistCnnShaped2.hs:42-62) as one node of the device
+ * contraction pass:  out = maxPool k k (reluS (conv2dPreservingS K A + bias)).
+ * For 2x2/2 windows in Double the bias add, relu and pooling run in the
+ * epilogue of the convolution kernel (the pre-activation never reaches HBM);
+ * `code` as in hb_relu_pool_fwd. */
+int hb_conv_relu_pool_fwd(const hb_array *K, const hb_array *bias,
+                          const hb_array *A, int ksize, hb_array **out,
+                          hb_array **code_out);
+/* Its adjoint: dK, dbias (may be NULL) and dA (NULL when the input is not
+ * differentiated: then the full-size cotangent is never materialised, the dKrn
+ * kernel expands (dy, code) inside shared memory). */
+int hb_conv_relu_pool_bwd(const hb_array *K, const hb_array *A,
+                          const hb_array *dy, const hb_array *code, int ksize,
+                          hb_array **dK_out, hb_array **dbias_out,
+                          hb_array **dA_out);
 /* lossSoftMaxCrossEntropyS (CommonShapedOps.hs:89-111) over the WHOLE tensor
  * (the reference normalises over all elements), scaled by `scale`:
  *   loss = scale * -(log softmax . expected);  dlogits = scale*(softmax-expected).

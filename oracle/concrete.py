@@ -414,6 +414,14 @@ class ConcreteBackend:
         dpre = self.maxpool2d_bwd(g, am, ksize, ksize, H, W)
         return dpre, (np.sum(dpre, axis=(0, 2, 3)) if want_bias else None)
 
+    def conv_relu_pool_fwd(self, K, bias, A, ksize):
+        return self.relu_pool_fwd(self.conv2dPreserving(K, A), bias, ksize)
+
+    def conv_relu_pool_bwd(self, K, A, dy, code, ksize, want_bias=True, want_dA=True):
+        dpre, db = self.relu_pool_bwd(dy, code, ksize, A.shape[2], A.shape[3], want_bias)
+        return (self.conv2d_dkrn(A, dpre, K.shape[2], K.shape[3]), db,
+                self.conv2d_dinp(K, dpre) if want_dA else None)
+
     # lossSoftMaxCrossEntropyS (CommonShapedOps.hs:89-111): normalises over the
     # WHOLE tensor; dual = (softMax - expected) * du
     def softmax_xent(self, logits, expected, scale=1.0, want_grad=True):

@@ -68,6 +68,18 @@ def test_roundtrip_and_views(dev, oracle, dtype):
     assert dev.kfromS(dev.sindex(d, [1, 2, 3])) == a[1, 2, 3]
 
 
+def test_flatten_concat(dev):
+    rng = np.random.default_rng(5)
+    leaves = [rng.uniform(-1, 1, sh) for sh in [(16, 1, 5, 5), (16,), (3, 7), (), (1000,)]]
+    d = [dev.sconcrete(x) for x in leaves]
+    exact(dev.to_numpy(dev.flatten_concat(d)), np.concatenate([x.reshape(-1) for x in leaves]))
+    # a non-contiguous leaf takes the per-leaf copy path
+    d[2] = dev.stranspose([1, 0], dev.sconcrete(leaves[2].T.copy()))
+    exact(dev.to_numpy(dev.flatten_concat(d)), np.concatenate([x.reshape(-1) for x in leaves]))
+    many = [dev.sconcrete(np.full(3, float(i))) for i in range(20)]
+    exact(dev.to_numpy(dev.flatten_concat(many)), np.repeat(np.arange(20.0), 3))
+
+
 def test_empty_and_errors(dev):
     e = dev.sconcrete(np.zeros((0, 3)))
     assert dev.to_numpy(e).shape == (0, 3)
@@ -353,7 +365,9 @@ def test_conv_reference_goldens(dev, form, name, K, A, wrt, expected, eps):
                                    # odd widths (8-byte cp.async path), ragged last band, tap-k / tap-column modes
                                    (3, 64, 64, 28, 28, 3, 3), (2, 20, 72, 9, 7, 2, 3), (2, 8, 40, 30, 30, 3, 3),
                                    (9, 1, 16, 28, 28, 5, 5), (301, 16, 16, 14, 14, 5, 5), (3, 2, 9, 31, 17, 3, 6),
-                                   (2, 12, 24, 50, 20, 1, 1), (1, 4, 4, 40, 230, 3, 3)])
+                                   (2, 12, 24, 50, 20, 1, 1), (1, 4, 4, 40, 230, 3, 3),
+                                   # the reference's own ConvVjpBench sweep (bench/ConvVjpBench.hs:850-859)
+                                   (3, 3, 3, 24, 24, 3, 3), (3, 3, 3, 96, 96, 3, 3), (3, 3, 3, 192, 192, 3, 3)])
 def test_conv_fwd_vjp_vs_oracle(dev, oracle, dtype, shape):
     N, Ci, Co, H, W, KH, KW = shape
     rng = np.random.default_rng(16)
@@ -439,6 +453,43 @@ def test_fused_relu_pool(dev, oracle, dtype, shape, ks):
     close(dev.to_numpy(db), rdb.astype(dtype), dtype, scale=100)
     y2, _ = dev.relu_pool_fwd(dev.sconcrete(pre), None, ks)
     exact(dev.to_numpy(y2), oracle.relu_pool_fwd(pre, None, ks)[0].astype(dtype))
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("shape,ks", [((37, 1, 16, 28, 28, 5, 5), 2), ((9, 16, 16, 14, 14, 5, 5), 2), ((3, 3, 40, 12, 20, 3, 3), 2),
+                                      ((2, 5, 7, 9, 11, 2, 3), 2), ((2, 4, 4, 12, 12, 3, 3), 3), ((5, 8, 64, 28, 28, 3, 3), 2),
+                                      ((4, 2, 9, 30, 6, 3, 2), 2)])
+def test_fused_conv_layer(dev, oracle, dtype, shape, ks):
+    """hb_conv_relu_pool_fwd/bwd (a whole convMnistLayerS as one node): the fused
+    DMMA epilogue / pooled-cotangent dKrn path and its unfused fallbacks agree
+    with conv -> (+bias) -> relu -> maxpool and the adjoints on the oracle."""
+    N, Ci, Co, H, W, KH, KW = shape
+    rng = np.random.default_rng(31)
+    K, A, bias = rnd(rng, (Co, Ci, KH, KW), dtype), rnd(rng, (N, Ci, H, W), dtype), rnd(rng, (Co,), dtype)
+    dK_, dA_, db_ = dev.sconcrete(K), dev.sconcrete(A), dev.sconcrete(bias)
+    y, code = dev.conv_relu_pool_fwd(dK_, db_, dA_, ks)
+    ry, rcode = oracle.conv_relu_pool_fwd(K, bias, A, ks)
+    close(dev.to_numpy(y), ry.astype(dtype), dtype, scale=100)
+    got_code = dev.to_numpy(code)
+    if dtype == np.float64:
+        exact(got_code, rcode)
+    dy = rnd(rng, ry.shape, dtype)
+    for want_dA in (False, True):
+        dk, dbias, da = dev.conv_relu_pool_bwd(dK_, dA_, dev.sconcrete(dy), code, ks, want_bias=True, want_dA=want_dA)
+        rdk, rdb, rda = oracle.conv_relu_pool_bwd(K, A, dy, got_code, ks, True, want_dA)
+        close(dev.to_numpy(dk), rdk.astype(dtype), dtype, scale=400)
+        close(dev.to_numpy(dbias), rdb.astype(dtype), dtype, scale=400)
+        if want_dA:
+            close(dev.to_numpy(da), rda.astype(dtype), dtype, scale=100)
+        else:
+            assert da is None
+    # no bias, no bias cotangent
+    y2, code2 = dev.conv_relu_pool_fwd(dK_, None, dA_, ks)
+    close(dev.to_numpy(y2), oracle.conv_relu_pool_fwd(K, None, A, ks)[0].astype(dtype), dtype, scale=100)
+    dk2, none_b, _ = dev.conv_relu_pool_bwd(dK_, dA_, dev.sconcrete(dy), code2, ks, want_bias=False, want_dA=False)
+    assert none_b is None
+    close(dev.to_numpy(dk2), oracle.conv_relu_pool_bwd(K, A, dy, dev.to_numpy(code2), ks, False, False)[0].astype(dtype),
+          dtype, scale=400)
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
