@@ -271,7 +271,21 @@ def main():
         objs = [b]
         dist.broadcast_object_list(objs, src=0)
         return objs[0]
-    comm_init(rank, world, bcast if world > 1 else None)
+    # NCCL writes its version banner to stdout at communicator creation; stdout
+    # carries exactly one JSON line, so fd 1 points at stderr while NCCL initialises
+    sys.stdout.flush()
+    saved_fd = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        comm_init(rank, world, bcast if world > 1 else None)
+        if world > 1:       # first collective (lazy channel set-up may print too)
+            warm = dev.sconcrete(np.zeros(8))
+            ffi.call("hb_allreduce_sum", warm.h, 1.0)
+            dev.sync()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_fd, 1)
+        os.close(saved_fd)
     dbg("comm up")
 
     def barrier():
