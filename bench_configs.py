@@ -1,0 +1,177 @@
+#!/usr/bin/env python
+"""bench_configs.py -- the OTHER BASELINE.json configs on the device backend
+(the headline config lives in bench.py): one JSON line per config, with the
+achieved fraction of the roofline that bounds its dominant kernel.
+
+  LongProdBench   gradient of the product of an n-vector (n = 1e6 .. 1e8),
+                  sfold (*) 1 + its reverse rule = prefix/suffix product scans
+                  (bench/LongProdBench.hs): HBM bound, 16 n bytes
+  ShortMnistForCI MnistFcnnRanked2 (Double, Float hidden layer), batch 1, SGD
+                  gamma = 0.02, 40 samples (bench/ShortMnistForCI.hs:11-17):
+                  latency bound; eager C-ABI calls vs one CUDA graph per step
+  MnistRnnShaped2 width 512, sequence 28, per-GPU batch 1024 (8192 / 8 GPUs):
+                  FP64 DMMA GEMMs (tensor pipe)
+  GEMM            smatmul2 [512,512] x [512,8192] alone (the RNN's recurrence)
+
+Usage: python bench_configs.py [--quick]
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from horde_ad_b200 import ad, ffi, mnist_fcnn, mnist_rnn  # noqa: E402
+from horde_ad_b200.device import DeviceBackend  # noqa: E402
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    return (float(json.load(open(p))["hbm_gbs"]), "measured") if os.path.exists(p) else (6650.0, "fallback")
+
+
+def timed(dev, f, reps, warm=3):
+    for _ in range(warm):
+        f()
+    dev.sync()
+    ms = C.c_float()
+    ffi.call("hb_event_record", 4)
+    for _ in range(reps):
+        f()
+    ffi.call("hb_event_record", 5)
+    ffi.call("hb_event_elapsed_ms", 4, 5, C.byref(ms))
+    return ms.value / reps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--quick", action="store_true")
+    args = ap.parse_args()
+    dev = DeviceBackend(int(os.environ.get("LOCAL_RANK", "0")))
+    hbm, src = peaks()
+    fp64 = C.c_double()
+    ffi.call("hb_microbench", 1, C.byref(fp64))
+    rng = np.random.Generator(np.random.Philox(42))
+
+    # ---------------------------------------------------------------- LongProd
+    for n in ([10**6, 10**7] if args.quick else [10**6, 10**7, 10**8]):
+        x = dev.sconcrete(np.exp(rng.uniform(-1e-3, 1e-3, n)))      # mean-zero log: the product stays finite
+        ms = timed(dev, lambda: dev.prod_fold_grad(x, 1.0), 10 if n < 10**8 else 5)
+        pr, g = dev.prod_fold_grad(x, 1.0)
+        # size-independent property: g_i * x_i = prod for every i
+        chk = dev.binary("mul", g, x)
+        p = float(dev.kfromS(pr))
+        err = float(np.max(np.abs(dev.to_numpy(chk) / p - 1.0)))
+        gbs = 16.0 * n / (ms * 1e-3) / 1e9
+        print(json.dumps({"config": "LongProdBench", "n": n, "ms": ms, "algorithmic_bytes": 16 * n,
+                          "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
+                                       "peak_source": src},
+                          "max_rel_err_of_g_i_times_x_i_vs_prod": err}), flush=True)
+        del x, pr, g, chk
+
+    # ----------------------------------------------------------- ShortMnistForCI
+    for (h1, h2) in ([(300, 100)] if args.quick else [(30, 10), (300, 100), (500, 150), (1500, 500)]):
+        params = [dev.sconcrete(p) for p in mnist_fcnn.init_params(h1, h2)]
+        datum = dev.sconcrete(rng.uniform(0, 1, 784))
+        target = dev.sconcrete(np.eye(10)[3])
+
+        def step():
+            _, grads = ad.grad(dev, lambda T, *ps: mnist_fcnn.afcnnMnistLoss2(T, datum, target, list(ps)), params)
+            for p, g in zip(params, grads):
+                dev.sgd_step(p, g, 0.02)
+        step()
+        dev.sync()
+        t0 = time.perf_counter()
+        for _ in range(40):
+            step()
+        dev.sync()
+        eager_ms = (time.perf_counter() - t0) / 40 * 1e3
+        # the same step captured once
+        ffi.call("hb_graph_begin")
+        try:
+            step()
+        finally:
+            gph = C.c_void_p()
+            ffi.call("hb_graph_end", C.byref(gph))
+        graph_ms = timed(dev, lambda: ffi.call("hb_graph_launch", gph), 40)
+        ffi.call("hb_graph_free", gph)
+        nparam = sum(int(np.prod(p.shape)) for p in params)
+        by = 3 * sum(int(np.prod(p.shape)) * p.dtype.itemsize for p in params)   # W read fwd + bwd, dW write
+        print(json.dumps({"config": "ShortMnistForCI / MnistFcnnRanked2", "widths": [h1, h2], "batch": 1,
+                          "parameters": nparam, "ms_per_sample_eager": eager_ms, "ms_per_sample_graph": graph_ms,
+                          "samples_per_s_graph": 1e3 / graph_ms,
+                          "roofline": {"bound": "hbm", "achieved": by / (graph_ms * 1e-3) / 1e9, "peak": hbm,
+                                       "unit": "GB/s", "frac": by / (graph_ms * 1e-3) / 1e9 / hbm, "peak_source": src,
+                                       "note": "batch 1: launch-latency bound by construction"}}), flush=True)
+
+    # -------------------------------------------------------------------- GEMM
+    m, k, n = 512, 512, (2048 if args.quick else 8192)
+    a, b = dev.sconcrete(rng.uniform(-.5, .5, (m, k))), dev.sconcrete(rng.uniform(-.5, .5, (k, n)))
+    ms = timed(dev, lambda: dev.smatmul2(a, b), 20)
+    tf = 2.0 * m * k * n / (ms * 1e-3) / 1e12
+    print(json.dumps({"config": "smatmul2", "shape": [m, k, n], "ms": ms,
+                      "roofline": {"bound": "tensor", "achieved": tf, "peak": fp64.value, "unit": "TFLOP/s",
+                                   "frac": tf / fp64.value, "peak_source": "hb_microbench FP64 DMMA, this run"}}), flush=True)
+
+    # --------------------------------------------------------------------- RNN
+    width, batch = 512, (256 if args.quick else 1024)
+    params = [dev.sconcrete(p) for p in mnist_rnn.init_params(width, rng_range=0.05)]
+    glyphs = dev.sconcrete(rng.uniform(0, 1, (batch, 28, 28)))
+    labels = dev.sconcrete(np.eye(10)[rng.integers(0, 10, batch)])
+    moms = [(dev.sconcrete(np.zeros(p.shape)), dev.sconcrete(np.zeros(p.shape))) for p in params]
+    tstep = [0]
+
+    def rnn_grad():
+        return ad.grad(dev, lambda T, *ps: mnist_rnn.rnnMnistLossFusedS(T, glyphs, labels, list(ps)), params)
+
+    def rnn_apply(grads):
+        tstep[0] += 1
+        for p, (mm, vv), g in zip(params, moms, grads):
+            dev.adam_step(p, mm, vv, g, tstep[0])
+    # eager: one C-ABI call per op, as the interpreter would issue them
+    val, grads = rnn_grad()
+    rnn_apply(grads)
+    dev.sync()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        val, grads = rnn_grad()
+        rnn_apply(grads)
+    dev.sync()
+    eager_ms = (time.perf_counter() - t0) / 3 * 1e3
+    # the gradient program captured once into a CUDA graph; Adam stays
+    # outside (its bias-corrected step size depends on t)
+    del val, grads
+    ffi.call("hb_graph_begin")
+    try:
+        val, grads = rnn_grad()
+    finally:
+        gph = C.c_void_p()
+        ffi.call("hb_graph_end", C.byref(gph))
+
+    def rnn_step():
+        ffi.call("hb_graph_launch", gph)
+        rnn_apply(grads)
+    step_ms = timed(dev, rnn_step, 10)
+    loss = float(dev.kfromS(val))
+    # flops: per time step 2 layers x (W_x x + W_s s), fwd + 2x bwd
+    fl = 28 * 3 * 2.0 * batch * (28 * width + 3 * width * width)
+    tf = fl / (step_ms * 1e-3) / 1e12
+    print(json.dumps({"config": "MnistRnnShaped2", "width": width, "seq": 28, "per_gpu_batch": batch, "ms_per_step": step_ms,
+                      "ms_per_step_eager": eager_ms,
+                      "samples_per_s": batch / (step_ms * 1e-3), "loss": loss if np.isfinite(loss) else None,
+                      "roofline": {"bound": "tensor", "achieved": tf, "peak": fp64.value, "unit": "TFLOP/s",
+                                   "frac": tf / fp64.value, "peak_source": "hb_microbench FP64 DMMA, this run",
+                                   "algorithmic_flops": fl}}), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -278,8 +278,8 @@ static int contract_impl(const hb_array *a, const hb_array *b, int n_lead, hb_ar
     int64_t oc = o->strides[i - n_lead];
     hb_cgroup *g;
     if (a->strides[i] != 0 && b->strides[i] == 0) { g = &P.M; nM *= a->shape[i]; }
-    else if (a->strides[i] == 0 && b->strides[i] != 0) { g = &P.N; nN *= a->shape[i]; }
-    else g = &P.B;  // both move (batch) or both broadcast
+    else if (a->strides[i] == 0) { g = &P.N; nN *= a->shape[i]; }  // also when b is broadcast too (a constant operand, e.g. srepl 0)
+    else g = &P.B;  // both move: batch
     int k = g->rank++;
     g->shape[k] = a->shape[i];
     g->sa[k] = a->strides[i];
@@ -307,10 +307,33 @@ static int contract_impl(const hb_array *a, const hb_array *b, int n_lead, hb_ar
       if (P.M.rank == 1 && P.N.rank == 1 && P.K.rank == 1 && P.B.n == 1) {
         const double *pa = (const double *)hb_data(a), *pb = (const double *)hb_data(b);
         double *pc = (double *)hb_data(o);
+        // an operand with no unit stride (e.g. a slice of a transposed batch) is
+        // packed once: O(rows * K) against the O(M * N * K) product
+        hb_array *ta = nullptr, *tb = nullptr;
+        auto pack = [&](const hb_array *src, int64_t rows, int64_t s_row, int64_t s_k, hb_array **tmp) -> int {
+          hb_array *v = hb_new_view(src);
+          v->rank = 2;
+          v->shape[0] = rows; v->strides[0] = s_row;
+          v->shape[1] = P.K.n; v->strides[1] = s_k;
+          int r = hb_contiguous(v, tmp);
+          hb_release(v);
+          return r;
+        };
+        if (st == HB_OK && P.M.sa[0] != 1 && P.K.sa[0] != 1) {
+          st = pack(a, P.M.n, P.M.sa[0], P.K.sa[0], &ta);
+          if (st == HB_OK) { pa = (const double *)hb_data(ta); P.M.sa[0] = P.K.n; P.K.sa[0] = 1; }
+        }
+        if (st == HB_OK && P.N.sb[0] != 1 && P.K.sb[0] != 1) {
+          st = pack(b, P.N.n, P.N.sb[0], P.K.sb[0], &tb);
+          if (st == HB_OK) { pb = (const double *)hb_data(tb); P.N.sb[0] = P.K.n; P.K.sb[0] = 1; }
+        }
+        if (st != HB_OK) { hb_release(ta); hb_release(tb); hb_release(o); return st; }
         if (P.N.sc[0] == 1 && P.M.sc[0] == P.N.n)
           st = hb_gemm_dmma(pa, P.M.sa[0], P.K.sa[0], pb, P.K.sb[0], P.N.sb[0], pc, P.M.n, P.N.n, P.K.n, &done);
         else if (P.M.sc[0] == 1 && P.N.sc[0] == P.M.n)  // output is [N, M]: C^T = B^T A^T
           st = hb_gemm_dmma(pb, P.N.sb[0], P.K.sb[0], pa, P.K.sa[0], P.M.sa[0], pc, P.N.n, P.M.n, P.K.n, &done);
+        hb_release(ta);
+        hb_release(tb);
       }
     }
     if (st == HB_OK && !done) {

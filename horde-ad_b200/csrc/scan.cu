@@ -10,33 +10,69 @@
 //                                  flowing backwards through the steps)
 //   grad_i = cot_i * acc_i        (no division: exact also when some x_j = 0)
 // Three kernels: tile products -> scan of tile products (one block) -> tile
-// rescans producing the gradient.  HBM traffic 24 bytes per element (two
+// rescans producing the gradient; in-tile scans are ordered warp-shuffle scans.  HBM traffic 24 bytes per element (two
 // reads, one write) against the 16-byte minimum.
 #include "common.cuh"
+#include "iter.cuh"
 
 #define PT 2048  // elements per tile (256 threads x 8)
 
+// 8 consecutive elements of this thread: two 128-bit loads per 4 doubles when
+// the vector is contiguous and aligned (VEC), else strided scalar loads
+template <typename T, bool VEC>
+__device__ __forceinline__ void hb_load8(const T *__restrict__ x, int64_t stride, int64_t base, int64_t n, T (&v)[8]) {
+  if (VEC && base + 8 <= n) {
+    typedef hb_vec<T, 16 / sizeof(T)> V;
+    constexpr int PER = 16 / sizeof(T), NV = 8 / PER;
+    const V *p = reinterpret_cast<const V *>(x + base);
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+      V t = p[k];
+#pragma unroll
+      for (int e = 0; e < PER; e++) v[k * PER + e] = t.v[e];
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = base + i < n ? x[(base + i) * stride] : T(1);
+  }
+}
+
+// ordered (left-to-right) inclusive product scan across the block's 256
+// thread values; returns the exclusive prefix of this thread.  `rev` scans
+// from the right (exclusive suffix).  Fixed association -> deterministic.
 template <typename T>
+__device__ __forceinline__ T hb_block_excl_prod(T p, bool rev, T *smem /* 8 */) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  T incl = p;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    T u = rev ? __shfl_down_sync(0xffffffffu, incl, o) : __shfl_up_sync(0xffffffffu, incl, o);
+    bool ok = rev ? (lane + o < 32) : (lane >= o);
+    if (ok) incl = rev ? incl * u : u * incl;
+  }
+  T excl = rev ? __shfl_down_sync(0xffffffffu, incl, 1) : __shfl_up_sync(0xffffffffu, incl, 1);
+  if (rev ? lane == 31 : lane == 0) excl = T(1);
+  __syncthreads();  // smem may still be read by a previous call
+  if (rev ? lane == 0 : lane == 31) smem[w] = incl;
+  __syncthreads();
+  T wp = T(1);  // product of the warps before (after) this one, in order
+  if (!rev) { for (int i = 0; i < w; i++) wp = wp * smem[i]; return wp * excl; }
+  for (int i = 7; i > w; i--) wp = smem[i] * wp;
+  return excl * wp;
+}
+
+template <typename T, bool VEC>
 __global__ void __launch_bounds__(256)
     hb_prod_tiles_kernel(const T *__restrict__ x, int64_t stride, int64_t n, T *__restrict__ tileprod) {
   __shared__ T smem[8];
   int64_t base = (int64_t)blockIdx.x * PT + threadIdx.x * 8;
+  T v[8];
+  hb_load8<T, VEC>(x, stride, base, n, v);
   T p = T(1);
 #pragma unroll
-  for (int i = 0; i < 8; i++)
-    if (base + i < n) p *= x[(base + i) * stride];
-  for (int o = 1; o < 32; o <<= 1) {  // ordered warp product (left to right)
-    T u = hb_shfl_xor(p, o);
-    p = ((threadIdx.x & o) ? u * p : p * u);
-  }
-  int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  if (l == 0) smem[w] = p;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    T r = smem[0];
-    for (int i = 1; i < 8; i++) r *= smem[i];
-    tileprod[blockIdx.x] = r;
-  }
+  for (int i = 0; i < 8; i++) p *= v[i];
+  T before = hb_block_excl_prod<T>(p, false, smem);
+  if (threadIdx.x == 255) tileprod[blockIdx.x] = before * p;
 }
 
 // exclusive prefix (pre) and suffix (suf) products of the tile products;
@@ -69,41 +105,62 @@ __global__ void __launch_bounds__(1024)
 }
 
 // per tile: grad[i] = (suf_tile * prod_{j>i in tile} x_j) * (pre_tile * prod_{j<i in tile} x_j)
-template <typename T>
+template <typename T, bool VEC>
 __global__ void __launch_bounds__(256)
     hb_prod_grad_kernel(const T *__restrict__ x, int64_t stride, int64_t n, const T *__restrict__ pre,
                         const T *__restrict__ suf, T *__restrict__ grad) {
-  __shared__ T tpre[257], tsuf[257];
+  __shared__ T smem[8];
   int64_t base = (int64_t)blockIdx.x * PT + threadIdx.x * 8;
   T v[8];
+  hb_load8<T, VEC>(x, stride, base, n, v);
   T p = T(1);
 #pragma unroll
-  for (int i = 0; i < 8; i++) {
-    v[i] = base + i < n ? x[(base + i) * stride] : T(1);
-    p *= v[i];
-  }
-  tpre[threadIdx.x + 1] = p;  // thread products; scanned serially by two threads
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    T r = pre[blockIdx.x];
-    T prev = r;
-    for (int i = 0; i < 256; i++) { T t = tpre[i + 1]; tpre[i] = prev; prev = prev * t; tsuf[i] = t; }
-    // tsuf currently holds thread products; convert to exclusive suffix
-    T s = suf[blockIdx.x];
-    for (int i = 255; i >= 0; i--) { T t = tsuf[i]; tsuf[i] = s; s = s * t; }
-  }
-  __syncthreads();
-  T a = tpre[threadIdx.x];   // product of everything before this thread's 8
-  T c = tsuf[threadIdx.x];   // dt * product of everything after this thread's 8
-  T sufl[8];
+  for (int i = 0; i < 8; i++) p *= v[i];
+  T a = pre[blockIdx.x] * hb_block_excl_prod<T>(p, false, smem);  // everything before this thread's 8
+  T c = hb_block_excl_prod<T>(p, true, smem) * suf[blockIdx.x];   // dt * everything after them
+  T out[8];
   T r = c;
 #pragma unroll
-  for (int i = 7; i >= 0; i--) { sufl[i] = r; r *= v[i]; }
+  for (int i = 7; i >= 0; i--) { out[i] = r; r *= v[i]; }
 #pragma unroll
   for (int i = 0; i < 8; i++) {
-    if (base + i < n) grad[base + i] = sufl[i] * a;
+    out[i] = out[i] * a;
     a *= v[i];
   }
+  if (VEC && base + 8 <= n) {
+    typedef hb_vec<T, 16 / sizeof(T)> V;
+    constexpr int PER = 16 / sizeof(T), NV = 8 / PER;
+    V *g = reinterpret_cast<V *>(grad + base);
+#pragma unroll
+    for (int k = 0; k < NV; k++) {
+      V t;
+#pragma unroll
+      for (int e = 0; e < PER; e++) t.v[e] = out[k * PER + e];
+      g[k] = t;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+      if (base + i < n) grad[base + i] = out[i];
+  }
+}
+
+template <typename T>
+static int prod_launch(const hb_array *x, int64_t n, int64_t nt, double dt, void *scr, hb_array *prod, hb_array *grad) {
+  T *tp = (T *)scr, *pre = tp + nt, *suf = pre + nt;
+  const T *xp = (const T *)hb_data(x);
+  bool vec = x->strides[0] == 1 && ((uintptr_t)xp & 15) == 0 && (!grad || ((uintptr_t)hb_data(grad) & 15) == 0);
+  if (vec) hb_prod_tiles_kernel<T, true><<<(unsigned)nt, 256, 0, g_hb.stream>>>(xp, 1, n, tp);
+  else hb_prod_tiles_kernel<T, false><<<(unsigned)nt, 256, 0, g_hb.stream>>>(xp, x->strides[0], n, tp);
+  HB_LAUNCHED();
+  hb_prod_tilescan_kernel<T><<<1, 1024, 0, g_hb.stream>>>(tp, nt, (T)dt, pre, suf, (T *)hb_data(prod));
+  HB_LAUNCHED();
+  if (grad) {
+    if (vec) hb_prod_grad_kernel<T, true><<<(unsigned)nt, 256, 0, g_hb.stream>>>(xp, 1, n, pre, suf, (T *)hb_data(grad));
+    else hb_prod_grad_kernel<T, false><<<(unsigned)nt, 256, 0, g_hb.stream>>>(xp, x->strides[0], n, pre, suf, (T *)hb_data(grad));
+    HB_LAUNCHED();
+  }
+  return HB_OK;
 }
 
 extern "C" int hb_prod_fold_grad(const hb_array *x, double dt, hb_array **prod_out, hb_array **grad_out) {
@@ -132,27 +189,9 @@ extern "C" int hb_prod_fold_grad(const hb_array *x, double dt, hb_array **prod_o
   void *scr;
   int st = hb_scratch((size_t)nt * 3 * es + 64, &scr);
   if (st != HB_OK) { hb_release(prod); hb_release(grad); return st; }
-  if (x->dt == HB_F64) {
-    double *tp = (double *)scr, *pre = tp + nt, *suf = pre + nt;
-    hb_prod_tiles_kernel<double><<<(unsigned)nt, 256, 0, g_hb.stream>>>((const double *)hb_data(x), x->strides[0], n, tp);
-    HB_LAUNCHED();
-    hb_prod_tilescan_kernel<double><<<1, 1024, 0, g_hb.stream>>>(tp, nt, dt, pre, suf, (double *)hb_data(prod));
-    HB_LAUNCHED();
-    if (grad) {
-      hb_prod_grad_kernel<double><<<(unsigned)nt, 256, 0, g_hb.stream>>>((const double *)hb_data(x), x->strides[0], n, pre, suf, (double *)hb_data(grad));
-      HB_LAUNCHED();
-    }
-  } else {
-    float *tp = (float *)scr, *pre = tp + nt, *suf = pre + nt;
-    hb_prod_tiles_kernel<float><<<(unsigned)nt, 256, 0, g_hb.stream>>>((const float *)hb_data(x), x->strides[0], n, tp);
-    HB_LAUNCHED();
-    hb_prod_tilescan_kernel<float><<<1, 1024, 0, g_hb.stream>>>(tp, nt, (float)dt, pre, suf, (float *)hb_data(prod));
-    HB_LAUNCHED();
-    if (grad) {
-      hb_prod_grad_kernel<float><<<(unsigned)nt, 256, 0, g_hb.stream>>>((const float *)hb_data(x), x->strides[0], n, pre, suf, (float *)hb_data(grad));
-      HB_LAUNCHED();
-    }
-  }
+  st = x->dt == HB_F64 ? prod_launch<double>(x, n, nt, dt, scr, prod, grad)
+                       : prod_launch<float>(x, n, nt, dt, scr, prod, grad);
+  if (st != HB_OK) { hb_release(prod); hb_release(grad); return st; }
   *prod_out = prod;
   if (grad_out) *grad_out = grad;
   return HB_OK;
