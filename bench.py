@@ -145,6 +145,12 @@ def alg_work(tag: str, kh1: int, kw1: int):
     if name == "conv2d_preserving_dinp":     # K ; dB -> dA
         Co, Ci, KH, KW = a; N, _, H, W = b
         return (n(a) + n(b) + N * Ci * H * W) * s, 2 * N * Co * H * W * Ci * KH * KW
+    if name == "conv_relu_pool_bwd":         # A ; dy (pooled) -> dK (+ dA): tagged launches are the dKrn / dInp kernels
+        N, Ci, H, W = a; Co = b[1]
+        return (n(a) + N * Co * H * W + Co * Ci * kh1 * kw1) * s, 2 * N * Co * H * W * Ci * kh1 * kw1
+    if name == "conv_relu_pool_fwd":         # K ; A -> pooled out
+        Co, Ci, KH, KW = a; N, _, H, W = b
+        return (n(a) + n(b)) * s + N * Co * (H // 2) * (W // 2) * (s + 1), 2 * N * Co * H * W * Ci * KH * KW
     if name == "matmul2":
         return (n(a) + n(b) + a[0] * b[1]) * s, 2 * a[0] * a[1] * b[1]
     if name in ("binary", "add_inplace_or_new"):
@@ -433,6 +439,23 @@ def profile_step(dev, ffi, CnnTrainer, local_batch, gl, lb, world, steps=3):
     return rows
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed
+# `ncu --set full` capture (profiles/r01_conv_dmma_kernels_full_raw.csv), keyed
+# by (launch-site function, operand shapes of the entry)
+NCU_TRAFFIC = {
+    ("hb_conv_dk_dmma", "[4096,16,14,14]"): 205613568 + 5349632,     # conv2 dKrn
+    ("hb_conv_sp_dmma", "[16,16,5,5]"): 102898944 + 59005952,        # conv2 fwd / dInp (rest of the write still in L2)
+    ("hb_conv_dk_dmma", "[4096,1,28,28]"): 436843008 + 4918784,      # conv1 dKrn (unfused capture)
+}
+
+
+def ncu_traffic(entry: str, site: str):
+    for (fn, shape), by in NCU_TRAFFIC.items():
+        if site.startswith(fn) and shape in entry and "[4096," in entry:   # captured at per-GPU batch 4096
+            return by
+    return None
+
+
 def roofline_of(rows, hbm_peak, peak_src, fp64_peak):
     kh1 = kw1 = HYPER["kh"] + 1
     total = sum(r["ms_per_step"] for r in rows)
@@ -459,7 +482,8 @@ def roofline_of(rows, hbm_peak, peak_src, fp64_peak):
         else:
             roof.update({"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
                          "peak_source": peak_src, "algorithmic_bytes": by})
-        roof["traffic"] = None
+        roof["traffic"] = ncu_traffic(top["entry"], top["site"])
+        roof["traffic_source"] = "profiles/r01_conv_dmma_kernels_full_raw.csv (ncu --set full, per launch)"
     breakdown = [{"entry": r["entry"], "site": r["site"], "ms": round(r["ms_per_step"], 4),
                   "share": round(r["share"], 4), "n": r["launches_per_step"]} for r in rows[:12]]
     return roof, breakdown

@@ -128,15 +128,18 @@ void hb_storage_release(hb_storage *st) {
   }
 }
 
+// Outgrown scratch blocks are retired, not freed: captured graphs have their
+// address baked in and may still be replayed (freed at hb_shutdown).
+static std::vector<void *> g_retired_scratch;
+
 int hb_scratch(size_t bytes, void **ptr) {
   if (g_hb.scratch_bytes < bytes) {
     HB_REQUIRE(!g_hb.capturing, "scratch growth (%zu bytes) during graph capture: run the step once eagerly first", bytes);
-    if (g_hb.scratch) {
-      HB_CUDA(cudaStreamSynchronize(g_hb.stream));
-      HB_CUDA(cudaFree(g_hb.scratch));
-    }
     size_t sz = bytes < (64u << 20) ? (64u << 20) : (bytes + (bytes >> 2));
-    HB_CUDA(cudaMalloc(&g_hb.scratch, sz));
+    void *fresh = nullptr;
+    HB_CUDA(cudaMalloc(&fresh, sz));
+    if (g_hb.scratch) g_retired_scratch.push_back(g_hb.scratch);
+    g_hb.scratch = fresh;
     g_hb.scratch_bytes = sz;
   }
   *ptr = g_hb.scratch;
@@ -181,6 +184,8 @@ extern "C" int hb_shutdown(void) {
     g_pools.clear();
   }
   if (g_hb.scratch) cudaFree(g_hb.scratch);
+  for (void *p : g_retired_scratch) cudaFree(p);
+  g_retired_scratch.clear();
   g_hb.scratch = nullptr;
   g_hb.scratch_bytes = 0;
   for (int i = 0; i < 64; i++) cudaEventDestroy(g_hb.events[i]);
