@@ -52,15 +52,92 @@ def timed(dev, f, reps, warm=3):
     return ms.value / reps
 
 
+def families(dev, rng, hbm, src, quick):
+    """Achieved HBM GB/s of the data-parallel kernel families against their
+    algorithmic bytes (SURVEY.md 8d table)."""
+    from horde_ad_b200 import nn
+    n = 1 << (24 if quick else 26)            # 512 MiB of doubles per operand
+    a = dev.sconcrete(rng.uniform(0.5, 1.5, n))
+    b = dev.sconcrete(rng.uniform(0.5, 1.5, n))
+
+    def report(name, ms, by, extra=None):
+        gbs = by / (ms * 1e-3) / 1e9
+        d = {"config": "kernel family", "kernel": name, "ms": ms, "algorithmic_bytes": by,
+             "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm, "peak_source": src}}
+        if extra:
+            d.update(extra)
+        print(json.dumps(d), flush=True)
+
+    report("binary add, contiguous f64 [2^26]", timed(dev, lambda: dev.binary("add", a, b), 10), 3 * 8 * n)
+    report("unary exp, contiguous f64", timed(dev, lambda: dev.unary("exp", a), 10), 2 * 8 * n)
+    report("taddTarget in place (cotangent accumulation)", timed(dev, lambda: dev.add_accumulate(dev.binary("add", a, b), b), 10) -
+           timed(dev, lambda: dev.binary("add", a, b), 10), 3 * 8 * n)
+    report("ssum0 (full reduction)", timed(dev, lambda: dev.ssum0(a), 10), 8 * n)
+    report("sdot0", timed(dev, lambda: dev.sdot0(a, b), 10), 2 * 8 * n)
+    m = dev.sconcrete(np.zeros(n)), dev.sconcrete(np.zeros(n))
+    report("Adam step (p, m, v in place, g read)", timed(dev, lambda: dev.adam_step(a, m[0], m[1], b, 3), 10), 7 * 8 * n)
+    del m
+    # the CNN's bias-gradient reduction: ssumN @[N,H,W] of [N,H,W,C] (a transposed view of [N,C,H,W])
+    N, Cc, H, W = (1024 if quick else 4096), 16, 28, 28
+    x = dev.sconcrete(rng.uniform(-.5, .5, (N, Cc, H, W)))
+    xt = dev.stranspose([0, 2, 3, 1], x)
+    report("ssumN @[N,H,W] over a transposed view [N,H,W,C] (bias gradient)", timed(dev, lambda: dev.ssumN(xt, 3), 10), 8 * N * Cc * H * W)
+    bias = dev.sconcrete(rng.uniform(-.5, .5, (Cc,)))
+    bst = dev.stranspose([0, 3, 1, 2], dev.sreplicateN([N, H, W], bias))
+    report("bias add through a stride-0 broadcast view", timed(dev, lambda: dev.binary("add", x, bst), 10), 2 * 8 * N * Cc * H * W)
+    report("relu_pool_fwd (bias + relu + 2x2 max-pool)", timed(dev, lambda: dev.relu_pool_fwd(x, bias, 2), 10),
+           8 * N * Cc * H * W + 9 * N * Cc * H * W // 4)
+    y, code = dev.relu_pool_fwd(x, bias, 2)
+    report("relu_pool_bwd (cotangent routing + bias cotangent)", timed(dev, lambda: dev.relu_pool_bwd(y, code, 2, H, W), 10),
+           8 * N * Cc * H * W + 9 * N * Cc * H * W // 4)
+    # gathers / scatters compiled from index functions
+    # (a) the vectorised convolution's first im2col gather: rows [H, KH] of A as [H, N, C, W]
+    xh = dev.stranspose([2, 0, 1, 3], x)
+    f = lambda ix: [ix[0] + ix[1]]
+    prog = dev.program(f, 2)
+    KH = 5
+    g1 = dev.sgather([H, KH], xh, f, 1, prog)
+    report("sgather, affine index i+j (im2col rows, KH = 5)", timed(dev, lambda: dev.sgather([H, KH], xh, f, 1, prog), 10),
+           8 * N * Cc * H * W * (KH + 1), {"shape": [H, KH, N, Cc, W]})
+    report("sscatter, affine index i+j (its adjoint, deterministic order)",
+           timed(dev, lambda: dev.sscatter([H], g1, f, 2, prog), 5), 8 * N * Cc * H * W * (KH + 1))
+    del g1
+    # (b) data-dependent gather: max-pool as a gather at kargMax of the window
+    Ho, Wo = H // 2, W // 2
+    win = dev.sconcrete(rng.uniform(-.5, .5, (N, Cc, Ho, Wo, 4)))
+    fa = lambda ix: [ix[0], ix[1], ix[2], ix[3], dev.ix_argmax(win, ix)]
+    proga = dev.program(fa, 4)
+    report("sgather with kargMax in the index (max-pool of the vectorised program)",
+           timed(dev, lambda: dev.sgather([N, Cc, Ho, Wo], win, fa, 5, proga), 10), 8 * N * Cc * Ho * Wo * 5)
+    # (c) the reference's gather48 chain (bench/ConvVjpBench.hs:428-439): [50,3,3,50] -> [48,3,3,48,3,3]
+    t = dev.sconcrete(rng.uniform(-.5, .5, (50, 3, 3, 50)))
+
+    def gather48():
+        q = dev.sgather([48, 3], t, f, 1)                      # [48,3,3,3,50]
+        q = dev.stranspose([4, 0, 1, 2, 3], q)                 # [50,48,3,3,3]
+        return dev.sgather([48, 3], q, f, 1)                   # [48,3,48,3,3,3]
+    report("gather48 chain of the reference (two affine gathers, 1.5 MB)", timed(dev, gather48, 20),
+           2 * 8 * (48 * 3 * 3 * 3 * 50 + 48 * 3 * 48 * 3 * 3 * 3), {"note": "L2-resident, launch-bound"})
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--skip-families", action="store_true")
+    ap.add_argument("--only-families", action="store_true")
     args = ap.parse_args()
     dev = DeviceBackend(int(os.environ.get("LOCAL_RANK", "0")))
     hbm, src = peaks()
     fp64 = C.c_double()
     ffi.call("hb_microbench", 1, C.byref(fp64))
     rng = np.random.Generator(np.random.Philox(42))
+    if args.only_families:
+        families(dev, rng, hbm, src, args.quick)
+        return
+
+    # ------------------------------------------ HBM-bound kernel families (8a rows)
+    if not args.skip_families:
+        families(dev, rng, hbm, src, args.quick)
 
     # ---------------------------------------------------------------- LongProd
     for n in ([10**6, 10**7] if args.quick else [10**6, 10**7, 10**8]):

@@ -236,6 +236,166 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// A run longer than ~2048 elements is cut into equal pieces (a divisor of L) so
+// that the rows outnumber the warps; returns the number of pieces (1 = keep).
+static int64_t hb_run_pieces(int64_t L) {
+  if (L <= 2048) return 1;
+  for (int64_t len = 2048; len >= 256; len--)
+    if (L % len == 0) return L / len;
+  return 1;  // no convenient divisor (e.g. a large prime): one long run per row
+}
+
+// grid for the row kernels: 8 warps per block, 32 rows per warp for short runs, one for long ones
+static int hb_rows_blocks(int64_t rows, int L) {
+  int64_t warps = L <= 32 ? (rows + 31) / 32 : rows;
+  return hb_blocks_for(warps, 8, g_hb.sm_count * 16);
+}
+
+// ------------------------------------------------------- row-structured copy
+// The result of a gather is [shm ++ shn]; its innermost collapsed axis is a
+// run of L elements that share ONE index computation.  A warp takes 32 rows
+// at a time: lane r decomposes row r (so the integer divisions are paid once
+// per row, not once per element), then the warp walks the 32 rows with the
+// offsets broadcast by shuffles and moves each run with coalesced accesses
+// (several short runs per pass when L < 32).
+//   TABLE = false: affine program folded into per-axis strides; the bound
+//                  checks of the index components ride along.
+//   TABLE = true : axis 0 is the whole shm space, its source offset comes from
+//                  the table the VM kernel wrote (INT64_MIN = out of bounds).
+struct hb_rowsp {
+  int rank;               // outer axes (everything except the inner run)
+  int mrank, prank;       // affine: leading shm axes carry index coefficients
+  int64_t rows;
+  int shape[HB_R];
+  int64_t stride[HB_R];   // source stride of each outer axis
+  int64_t c0[HB_VM_MAX_OUT], pshape[HB_VM_MAX_OUT];
+  int64_t coef[HB_VM_MAX_OUT][HB_R];
+  int64_t base;
+  int L, lp, lshift;      // run length, its power-of-two padding (<= 32) and log2
+  int64_t s_in;           // source stride along the run
+};
+
+template <typename T, bool TABLE>
+__global__ void __launch_bounds__(256)
+    hb_gather_rows_kernel(const __grid_constant__ hb_rowsp R, const int64_t *__restrict__ table,
+                          const T *__restrict__ src, T *__restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  // short runs: 32 rows per warp pass (lane r decodes row r); long runs: one row
+  // per warp (every lane decodes it; the cost is amortised over the run)
+  const int rpg = R.L <= 32 ? 32 : 1;
+  for (int64_t r0 = warp * rpg; r0 < R.rows; r0 += nwarps * rpg) {
+    // lane r: source offset of row r0 + r (INT64_MIN when out of bounds)
+    int64_t row = r0 + (rpg == 32 ? lane : 0), off = INT64_MIN;
+    if (row < R.rows) {
+      int64_t rem = row, o = R.base;
+      int64_t pc[HB_VM_MAX_OUT];
+#pragma unroll
+      for (int c = 0; c < HB_VM_MAX_OUT; c++) pc[c] = c < R.prank ? R.c0[c] : 0;
+#pragma unroll 1
+      for (int k = R.rank - 1; k >= (TABLE ? 1 : 0); k--) {
+        int64_t q = rem / R.shape[k];
+        int rr = (int)(rem - q * R.shape[k]);
+        o += rr * R.stride[k];
+        if (!TABLE && k < R.mrank) {
+#pragma unroll
+          for (int c = 0; c < HB_VM_MAX_OUT; c++)
+            if (c < R.prank) pc[c] += rr * R.coef[c][k];
+        }
+        rem = q;
+      }
+      bool inb = true;
+      if (TABLE) {
+        int64_t t = table[rem];
+        inb = t != INT64_MIN;
+        o += inb ? t : 0;
+      } else {
+#pragma unroll
+        for (int c = 0; c < HB_VM_MAX_OUT; c++)
+          if (c < R.prank) inb = inb && pc[c] >= 0 && pc[c] < R.pshape[c];
+      }
+      off = inb ? o : INT64_MIN;
+    }
+    // walk the 32 rows, 32 / lp of them per pass; four passes (or four pieces
+    // of a long run) are loaded before any is stored, for memory-level parallelism
+    const int rpp = 32 >> R.lshift, sub = lane >> R.lshift, j0 = lane & (R.lp - 1);
+    if (R.L <= 32) {
+      for (int rb = 0; rb < 32; rb += 4 * rpp) {
+        T v[4];
+        int64_t dsto[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          int rsel = rb + u * rpp + sub;
+          int64_t o = __shfl_sync(0xffffffffu, off, rsel & 31);
+          int64_t rr = r0 + rsel;
+          bool live = rsel < 32 && rr < R.rows && j0 < R.L;
+          dsto[u] = live ? rr * R.L + j0 : -1;
+          v[u] = (live && o != INT64_MIN) ? src[o + (int64_t)j0 * R.s_in] : T(0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+          if (dsto[u] >= 0) out[dsto[u]] = v[u];
+      }
+    } else {
+      {
+        int64_t o = off;
+        int64_t rr = r0;
+        T *dst = out + rr * R.L;
+        const bool inb = o != INT64_MIN;
+        const T *sp = src + (inb ? o : 0);
+        int j = lane;
+        for (; j + 96 < R.L; j += 128) {
+          T a = T(0), b = T(0), c = T(0), d = T(0);
+          if (inb) {
+            a = sp[(int64_t)j * R.s_in];
+            b = sp[(int64_t)(j + 32) * R.s_in];
+            c = sp[(int64_t)(j + 64) * R.s_in];
+            d = sp[(int64_t)(j + 96) * R.s_in];
+          }
+          dst[j] = a; dst[j + 32] = b; dst[j + 64] = c; dst[j + 96] = d;
+        }
+        for (; j < R.L; j += 32) dst[j] = inb ? sp[(int64_t)j * R.s_in] : T(0);
+      }
+    }
+  }
+}
+
+// Collapses the trailing shn axes (source strides against the contiguous
+// result) and fills the row description; the first `nlead` entries of
+// shape/stride (the shm axes or the single table axis) are given by the caller.
+static void rows_finish(hb_rowsp *R, int nlead, int nrank, const int64_t *nshape, const int64_t *nstride) {
+  int64_t sh[HB_R], st[1][HB_R];
+  int r = nrank;
+  for (int i = 0; i < nrank; i++) { sh[i] = nshape[i]; st[0][i] = nstride[i]; }
+  // merge adjacent shn axes that are contiguous in the source (the result is contiguous anyway)
+  int w = 0;
+  for (int i = 0; i < r; i++) {
+    if (sh[i] == 1) continue;
+    if (w > 0 && st[0][w - 1] == st[0][i] * sh[i]) { sh[w - 1] *= sh[i]; st[0][w - 1] = st[0][i]; }
+    else { sh[w] = sh[i]; st[0][w] = st[0][i]; w++; }
+  }
+  r = w;
+  int64_t L = 1, s_in = 1;
+  if (r > 0 && sh[r - 1] <= (1 << 30)) {
+    L = sh[r - 1]; s_in = st[0][r - 1]; r--;
+    int64_t pieces = hb_run_pieces(L);
+    if (pieces > 1 && r < HB_R - nlead - 1) {  // long run: [pieces][L / pieces] keeps every warp busy
+      sh[r] = pieces; st[0][r] = (L / pieces) * s_in; r++;
+      L /= pieces;
+    }
+  }
+  R->rank = nlead + r;
+  for (int i = 0; i < r; i++) { R->shape[nlead + i] = (int)sh[i]; R->stride[nlead + i] = st[0][i]; }
+  R->L = (int)L;
+  R->s_in = s_in;
+  R->lshift = 0;
+  while ((1 << R->lshift) < L && R->lshift < 5) R->lshift++;
+  R->lp = 1 << R->lshift;
+  R->rows = 1;
+  for (int i = 0; i < R->rank; i++) R->rows *= R->shape[i];
+}
+
 static void fill_shm(hb_shm *S, int shm_rank, const int64_t *shm, int shp_rank, const int64_t *pshape,
                      const int64_t *pstride) {
   memset(S, 0, sizeof *S);
@@ -301,6 +461,30 @@ extern "C" int hb_gather(const hb_array *src, int shm_rank, const int64_t *shm, 
     }
     hb_array *o;
     HB_TRY(hb_new_array(src->dt, orank, osh, &o));
+    bool small_axes = true;
+    for (int k = 0; k < shm_rank; k++) small_axes = small_axes && shm[k] < (1ll << 31);
+    for (int i = 0; i < nrank; i++) small_axes = small_axes && src->shape[shp_rank + i] < (1ll << 31);
+    if (small_axes) {
+      hb_rowsp R;
+      memset(&R, 0, sizeof R);
+      R.mrank = shm_rank;
+      R.prank = shp_rank;
+      R.base = base;
+      for (int c = 0; c < shp_rank; c++) {
+        R.c0[c] = prog->c0[c];
+        R.pshape[c] = src->shape[c];
+        for (int k = 0; k < shm_rank; k++) R.coef[c][k] = prog->coef[c][k];
+      }
+      for (int k = 0; k < shm_rank; k++) { R.shape[k] = (int)shm[k]; R.stride[k] = fs[k]; }
+      rows_finish(&R, shm_rank, nrank, src->shape + shp_rank, src->strides + shp_rank);
+      int blocks = hb_rows_blocks(R.rows, R.L);
+      HB_DISPATCH_BYTES(src->dt, T,
+                        (hb_gather_rows_kernel<T, false><<<blocks, 256, 0, g_hb.stream>>>(
+                            R, nullptr, (const T *)hb_data(src), (T *)hb_data(o))));
+      HB_LAUNCHED();
+      *out = o;
+      return HB_OK;
+    }
     hb_affp A;
     memset(&A, 0, sizeof A);
     A.mrank = shm_rank;
@@ -346,17 +530,31 @@ extern "C" int hb_gather(const hb_array *src, int shm_rank, const int64_t *shm, 
     if (st != HB_OK) { hb_release(o); return st; }
     hb_vm_offsets_kernel<<<hb_blocks_for(M, 128), 128, 0, g_hb.stream>>>(prog->vm, S, M, (int64_t *)scr);
     HB_LAUNCHED();
-    hb_dims nd;
-    nd.rank = nrank;
-    for (int i = 0; i < HB_R; i++) {
-      nd.shape[i] = i < nrank ? src->shape[shp_rank + i] : 1;
-      nd.stride[i] = i < nrank ? src->strides[shp_rank + i] : 0;
+    bool small_axes = M < (1ll << 31);
+    for (int i = 0; i < nrank; i++) small_axes = small_axes && src->shape[shp_rank + i] < (1ll << 31);
+    if (small_axes) {
+      hb_rowsp R;
+      memset(&R, 0, sizeof R);
+      R.shape[0] = (int)M;
+      rows_finish(&R, 1, nrank, src->shape + shp_rank, src->strides + shp_rank);
+      int blocks = hb_rows_blocks(R.rows, R.L);
+      HB_DISPATCH_BYTES(src->dt, T,
+                        (hb_gather_rows_kernel<T, true><<<blocks, 256, 0, g_hb.stream>>>(
+                            R, (const int64_t *)scr, (const T *)hb_data(src), (T *)hb_data(o))));
+      HB_LAUNCHED();
+    } else {
+      hb_dims nd;
+      nd.rank = nrank;
+      for (int i = 0; i < HB_R; i++) {
+        nd.shape[i] = i < nrank ? src->shape[shp_rank + i] : 1;
+        nd.stride[i] = i < nrank ? src->strides[shp_rank + i] : 0;
+      }
+      int blocks = hb_blocks_for(total, 256, g_hb.sm_count * 32);
+      HB_DISPATCH_BYTES(src->dt, T,
+                        (hb_gather_copy_kernel<T><<<blocks, 256, 0, g_hb.stream>>>(
+                            (const int64_t *)scr, nd, Nn, total, (const T *)hb_data(src), (T *)hb_data(o))));
+      HB_LAUNCHED();
     }
-    int blocks = hb_blocks_for(total, 256, g_hb.sm_count * 32);
-    HB_DISPATCH_BYTES(src->dt, T,
-                      (hb_gather_copy_kernel<T><<<blocks, 256, 0, g_hb.stream>>>(
-                          (const int64_t *)scr, nd, Nn, total, (const T *)hb_data(src), (T *)hb_data(o))));
-    HB_LAUNCHED();
   }
   *out = o;
   return HB_OK;
@@ -549,6 +747,175 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ------------------------------------------------ row-structured scatter
+// Same decomposition as hb_gather_rows_kernel: a row = (leading index, outer
+// shn index), its inner run of L elements shares the index work.
+struct hb_srowsp {
+  int rank;                // axis 0 = the leading index space (M sources or Pn destinations)
+  int shape[HB_R];
+  int64_t sstride[HB_R];   // source strides of the outer shn axes (entry 0 unused)
+  int64_t ostride[HB_R];   // strides of the same axes inside one contiguous result slice
+  int64_t rows, Nn;
+  int L, lp, lshift;
+  int64_t s_in;
+};
+
+// moff[m] = source offset of shm position m
+__global__ void __launch_bounds__(256)
+    hb_scatter_moff_kernel(hb_dims md, int64_t M, int64_t *__restrict__ moff) {
+  int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m < M) moff[m] = hb_offset_of(md, m);
+}
+
+__device__ __forceinline__ void hb_srow_decode(const hb_srowsp &R, int64_t row, int64_t &lead, int64_t &soff,
+                                               int64_t &ooff) {
+  int64_t rem = row;
+  soff = 0;
+  ooff = 0;
+#pragma unroll 1
+  for (int k = R.rank - 1; k >= 1; k--) {
+    int64_t q = rem / R.shape[k];
+    int rr = (int)(rem - q * R.shape[k]);
+    soff += rr * R.sstride[k];
+    ooff += rr * R.ostride[k];
+    rem = q;
+  }
+  lead = rem;
+}
+
+// no destination hit twice: out[dest[m], ...] = src[m, ...]
+template <typename T>
+__global__ void __launch_bounds__(256)
+    hb_scatter_direct_rows_kernel(const __grid_constant__ hb_srowsp R, const int *__restrict__ dest,
+                                  const int *__restrict__ collision, const int64_t *__restrict__ moff,
+                                  const T *__restrict__ src, T *__restrict__ out) {
+  if (*collision) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int rpg = R.L <= 32 ? 32 : 1;
+  for (int64_t r0 = warp * rpg; r0 < R.rows; r0 += nwarps * rpg) {
+    int64_t row = r0 + (rpg == 32 ? lane : 0), so = 0, oo = INT64_MIN;
+    if (row < R.rows) {
+      int64_t m, soff, ooff;
+      hb_srow_decode(R, row, m, soff, ooff);
+      int d = dest[m];
+      if (d >= 0) { so = moff[m] + soff; oo = (int64_t)d * R.Nn + ooff; }
+    }
+    const int rpp = 32 >> R.lshift, sub = lane >> R.lshift, j0 = lane & (R.lp - 1);
+    for (int rb = 0; rb < rpg; rb += rpp) {
+      int rsel = rb + sub;
+      int64_t s_ = __shfl_sync(0xffffffffu, so, rsel), o_ = __shfl_sync(0xffffffffu, oo, rsel);
+      if (r0 + rsel >= R.rows || o_ == INT64_MIN) continue;
+      for (int j = j0; j < R.L; j += R.lp) out[o_ + j] = src[s_ + (int64_t)j * R.s_in];
+    }
+  }
+}
+
+// out[d, ...] = sum over the sorted source list of d (sequential, reference order)
+template <typename T>
+__global__ void __launch_bounds__(256)
+    hb_scatter_sum_rows_kernel(const __grid_constant__ hb_srowsp R, const int *__restrict__ collision,
+                               const int *__restrict__ starts, const int *__restrict__ counts,
+                               const int *__restrict__ seg, const int64_t *__restrict__ moff,
+                               const T *__restrict__ src, T *__restrict__ out) {
+  if (!*collision) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int rpg = R.L <= 32 ? 32 : 1;
+  for (int64_t r0 = warp * rpg; r0 < R.rows; r0 += nwarps * rpg) {
+    int64_t row = r0 + (rpg == 32 ? lane : 0), so = 0;
+    int cnt = 0, st = 0;
+    if (row < R.rows) {
+      int64_t d, soff, ooff;
+      hb_srow_decode(R, row, d, soff, ooff);
+      so = soff;
+      cnt = counts[d];
+      st = starts[d];
+    }
+    const int rpp = 32 >> R.lshift, sub = lane >> R.lshift, j0 = lane & (R.lp - 1);
+    for (int rb = 0; rb < rpg; rb += rpp) {
+      int rsel = rb + sub;
+      int64_t s_ = __shfl_sync(0xffffffffu, so, rsel);
+      int c = __shfl_sync(0xffffffffu, cnt, rsel), st_ = __shfl_sync(0xffffffffu, st, rsel);
+      int64_t rr = r0 + rsel;
+      if (rr >= R.rows || c == 0) continue;  // untouched destinations stay zero
+      const int *lst = seg + st_;
+      if (c <= 8) {
+        // the source offsets of this destination are the same for the whole run:
+        // fetch them once, then every element is c independent loads
+        int64_t so8[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) so8[i] = i < c ? moff[lst[i]] : 0;
+        for (int j = j0; j < R.L; j += R.lp) {
+          const T *sp = src + s_ + (int64_t)j * R.s_in;
+          T v[8];
+#pragma unroll
+          for (int i = 0; i < 8; i++) v[i] = i < c ? sp[so8[i]] : T(0);
+          T acc = R.Nn == 1 ? v[0] + T(0) : v[0];
+#pragma unroll
+          for (int i = 1; i < 8; i++)
+            if (i < c) acc = v[i] + acc;
+          out[rr * R.L + j] = acc;
+        }
+        continue;
+      }
+      for (int j = j0; j < R.L; j += R.lp) {
+        const T *sp = src + s_ + (int64_t)j * R.s_in;
+        T acc;
+        if (R.Nn == 1) {
+          // rank-0 slices: vec starts at 0 and adds u + u2 (OpsConcrete.hs:1594-1601)
+          acc = T(0);
+          for (int i = 0; i < c; i++) acc = sp[moff[lst[i]]] + acc;
+        } else {
+          // IntMap.insertWith (+): first slice stored as is, later ones new + old
+          acc = sp[moff[lst[0]]];
+          for (int i = 1; i < c; i++) acc = sp[moff[lst[i]]] + acc;
+        }
+        out[rr * R.L + j] = acc;
+      }
+    }
+  }
+}
+
+// Rows over [lead] ++ shn with the innermost collapsed shn axis as the run.
+static void srows_fill(hb_srowsp *R, int64_t lead, int nrank, const int64_t *nshape, const int64_t *nstride) {
+  memset(R, 0, sizeof *R);
+  int64_t sh[HB_R], ss[HB_R], os[HB_R];
+  int w = 0;
+  int64_t Nn = 1;
+  for (int i = 0; i < nrank; i++) Nn *= nshape[i];
+  R->Nn = Nn;
+  for (int i = 0; i < nrank; i++) {
+    if (nshape[i] == 1) continue;
+    if (w > 0 && ss[w - 1] == nstride[i] * nshape[i]) { sh[w - 1] *= nshape[i]; ss[w - 1] = nstride[i]; }
+    else { sh[w] = nshape[i]; ss[w] = nstride[i]; w++; }
+  }
+  int r = w;
+  int64_t L = 1, s_in = 1;
+  if (r > 0 && sh[r - 1] <= (1 << 30)) {
+    L = sh[r - 1]; s_in = ss[r - 1]; r--;
+    int64_t pieces = hb_run_pieces(L);
+    if (pieces > 1 && r < HB_R - 2) {
+      sh[r] = pieces; ss[r] = (L / pieces) * s_in; r++;
+      L /= pieces;
+    }
+  }
+  int64_t o = L;
+  for (int i = r - 1; i >= 0; i--) { os[i] = o; o *= sh[i]; }
+  R->rank = 1 + r;
+  R->shape[0] = (int)lead;
+  for (int i = 0; i < r; i++) { R->shape[1 + i] = (int)sh[i]; R->sstride[1 + i] = ss[i]; R->ostride[1 + i] = os[i]; }
+  R->L = (int)L;
+  R->s_in = s_in;
+  R->lshift = 0;
+  while ((1 << R->lshift) < L && R->lshift < 5) R->lshift++;
+  R->lp = 1 << R->lshift;
+  R->rows = lead;
+  for (int i = 0; i < r; i++) R->rows *= sh[i];
+}
+
 extern "C" int hb_scatter_add(const hb_array *src, int shm_rank, int shp_rank, const int64_t *shp,
                               const hb_ixprog *prog, hb_array **out) {
   hb_prof_scope prof_("scatter_add", src);
@@ -583,9 +950,11 @@ extern "C" int hb_scatter_add(const hb_array *src, int shm_rank, int shp_rank, c
   // scratch layout (ints): dest[M] | counts[Pn] | starts[Pn] | cursor[Pn] | seg[M] | flag | scan tmp
   int64_t tiles = (Pn + 1023) / 1024;
   size_t ints = (size_t)M * 2 + (size_t)Pn * 3 + 16 + (size_t)(tiles + 2) * 4;
+  ints = (ints + 1) & ~(size_t)1;
   void *scr;
-  int st = hb_scratch(ints * 4, &scr);
+  int st = hb_scratch(ints * 4 + (size_t)M * 8, &scr);  // + moff[M] (int64)
   if (st != HB_OK) { hb_release(o); return st; }
+  int64_t *moff = (int64_t *)((int *)scr + ints);
   int *dest = (int *)scr;
   int *counts = dest + M;
   int *starts = counts + Pn;
@@ -617,9 +986,22 @@ extern "C" int hb_scatter_add(const hb_array *src, int shm_rank, int shp_rank, c
   int bdst = hb_blocks_for(total_dst, 256, g_hb.sm_count * 32);
   st = exclusive_scan_i32(counts, starts, Pn, tmp);
   if (st != HB_OK) { hb_release(o); return st; }
+  bool rows_ok = true;
+  for (int i = 0; i < nrank; i++) rows_ok = rows_ok && src->shape[shm_rank + i] < (1ll << 31);
+  hb_srowsp Rs, Rd;
+  if (rows_ok) {
+    srows_fill(&Rs, M, nrank, src->shape + shm_rank, src->strides + shm_rank);
+    srows_fill(&Rd, Pn, nrank, src->shape + shm_rank, src->strides + shm_rank);
+    hb_scatter_moff_kernel<<<hb_blocks_for(M, 256), 256, 0, g_hb.stream>>>(md, M, moff);
+    HB_LAUNCHED();
+  }
   HB_DISPATCH_NUM(src->dt, T, {
-    hb_scatter_direct_kernel<T><<<bsrc, 256, 0, g_hb.stream>>>(dest, flag, sd, Nn, total_src,
-                                                               (const T *)hb_data(src), (T *)hb_data(o));
+    if (rows_ok)
+      hb_scatter_direct_rows_kernel<T><<<hb_rows_blocks(Rs.rows, Rs.L), 256, 0, g_hb.stream>>>(
+          Rs, dest, flag, moff, (const T *)hb_data(src), (T *)hb_data(o));
+    else
+      hb_scatter_direct_kernel<T><<<bsrc, 256, 0, g_hb.stream>>>(dest, flag, sd, Nn, total_src,
+                                                                 (const T *)hb_data(src), (T *)hb_data(o));
     HB_LAUNCHED();
     hb_scatter_fill_kernel<<<hb_blocks_for(M, 128), 128, 0, g_hb.stream>>>(dest, flag, starts, cursor, seg, M);
     HB_LAUNCHED();
@@ -627,8 +1009,12 @@ extern "C" int hb_scatter_add(const hb_array *src, int shm_rank, int shp_rank, c
     HB_LAUNCHED();
     hb_scatter_sort_long_kernel<<<hb_blocks_for(Pn, 1, g_hb.sm_count * 4), 256, 0, g_hb.stream>>>(flag, starts, counts, seg, Pn);
     HB_LAUNCHED();
-    hb_scatter_sum_kernel<T><<<bdst, 256, 0, g_hb.stream>>>(flag, starts, counts, seg, md, nd, Nn, total_dst,
-                                                            (const T *)hb_data(src), (T *)hb_data(o));
+    if (rows_ok)
+      hb_scatter_sum_rows_kernel<T><<<hb_rows_blocks(Rd.rows, Rd.L), 256, 0, g_hb.stream>>>(
+          Rd, flag, starts, counts, seg, moff, (const T *)hb_data(src), (T *)hb_data(o));
+    else
+      hb_scatter_sum_kernel<T><<<bdst, 256, 0, g_hb.stream>>>(flag, starts, counts, seg, md, nd, Nn, total_dst,
+                                                              (const T *)hb_data(src), (T *)hb_data(o));
     HB_LAUNCHED();
   });
   *out = o;

@@ -18,6 +18,7 @@
 //          reduced range, shared-memory tree over y.
 // HBM roofline: sizeof(T) bytes per input element (2x for dot), SURVEY 8d.
 #include "common.cuh"
+#include "iter.cuh"
 
 struct hb_redp {
   int krank, rrank;
@@ -97,6 +98,57 @@ __global__ void __launch_bounds__(256)
   }
   acc = hb_block_sum<ACC>(acc, smem);
   if (threadIdx.x == 0) out[s * p.K + k] = acc;
+}
+
+// rows kernel for the common layout "the innermost reduced axis is a unit-
+// stride run" (ssum0 / sdot0 of contiguous data; bias gradients = ssumN over
+// [N][H*W] runs of an NCHW tensor): no per-element index arithmetic, 128-bit
+// loads, four independent accumulators per thread (combined in a fixed order).
+template <typename T, typename ACC, bool DOT, bool VEC>
+__global__ void __launch_bounds__(256)
+    hb_reduce_runs_kernel(hb_redp p, const T *__restrict__ a, const T *__restrict__ b, ACC *__restrict__ out,
+                          int64_t rchunk) {
+  __shared__ ACC smem[32];
+  constexpr int V = VEC ? 16 / (int)sizeof(T) : 1;
+  typedef hb_vec<T, V> VT;
+  const int64_t k = blockIdx.x, s = blockIdx.y;
+  int64_t ka, kb;
+  hb_decomp2(p.krank, p.kshape, p.ksa, p.ksb, k, ka, kb);
+  const int64_t n1 = p.rshape[p.rrank - 1];
+  const int64_t s0a = p.rrank == 2 ? p.rsa[0] : 0, s0b = p.rrank == 2 ? p.rsb[0] : 0;
+  const int64_t r0 = s * rchunk, r1 = r0 + rchunk < p.R ? r0 + rchunk : p.R;
+  ACC acc[4] = {ACC(0), ACC(0), ACC(0), ACC(0)};
+  int64_t q = r0 / n1, m0 = r0 - q * n1;
+  for (int64_t r = r0; r < r1;) {
+    int64_t len = n1 - m0 < r1 - r ? n1 - m0 : r1 - r;
+    const VT *pa = reinterpret_cast<const VT *>(a + ka + q * s0a + m0);
+    const VT *pb = reinterpret_cast<const VT *>(b + kb + q * s0b + m0);
+    const int64_t nv = len / V;
+    int64_t i = threadIdx.x;
+    for (; i + 3 * 256 < nv; i += 4 * 256) {
+      VT x0 = pa[i], x1 = pa[i + 256], x2 = pa[i + 512], x3 = pa[i + 768];
+      VT y0, y1, y2, y3;
+      if (DOT) { y0 = pb[i]; y1 = pb[i + 256]; y2 = pb[i + 512]; y3 = pb[i + 768]; }
+#pragma unroll
+      for (int e = 0; e < V; e++) {
+        acc[0] += DOT ? (ACC)x0.v[e] * (ACC)y0.v[e] : (ACC)x0.v[e];
+        acc[1] += DOT ? (ACC)x1.v[e] * (ACC)y1.v[e] : (ACC)x1.v[e];
+        acc[2] += DOT ? (ACC)x2.v[e] * (ACC)y2.v[e] : (ACC)x2.v[e];
+        acc[3] += DOT ? (ACC)x3.v[e] * (ACC)y3.v[e] : (ACC)x3.v[e];
+      }
+    }
+    for (; i < nv; i += 256) {
+      VT x0 = pa[i], y0;
+      if (DOT) y0 = pb[i];
+#pragma unroll
+      for (int e = 0; e < V; e++) acc[0] += DOT ? (ACC)x0.v[e] * (ACC)y0.v[e] : (ACC)x0.v[e];
+    }
+    r += len;
+    q++;
+    m0 = 0;
+  }
+  ACC t = hb_block_sum<ACC>((acc[0] + acc[1]) + (acc[2] + acc[3]), smem);
+  if (threadIdx.x == 0) out[s * p.K + k] = t;
 }
 
 // blockDim = (BX, BY); x -> kept index, y interleaves the reduced range
@@ -213,6 +265,7 @@ static int reduce_typed(const hb_array *a, const hb_array *b, int nk, const int 
       if (S < 1) S = 1;
     }
     rchunk = (p.R + S - 1) / S;
+    rchunk = (rchunk + 15) / 16 * 16;  // keeps the 128-bit path of the runs kernel aligned
     S = (int)((p.R + rchunk - 1) / rchunk);
     HB_REQUIRE(p.K < (1ll << 31), "reduce: too many outputs for the rows kernel");
     grid = dim3((unsigned)p.K, S);
@@ -246,7 +299,21 @@ static int reduce_typed(const hb_array *a, const hb_array *b, int nk, const int 
     HB_TRY(hb_scratch((size_t)S * p.K * sizeof(ACC), &scr));
     dst = (ACC *)scr;
   }
-  if (rows)
+  // unit-stride inner run on every operand that moves, 256-thread blocks
+  bool runs = rows && block.x == 256 && p.rrank <= 2 && p.rsa[p.rrank - 1] == 1 && (!DOT || p.rsb[p.rrank - 1] == 1);
+  if (runs) {
+    constexpr int V = 16 / (int)sizeof(T);
+    const int64_t n1 = p.rshape[p.rrank - 1];
+    auto al = [&](const T *ptr, int64_t s0, const int64_t *ks) {
+      bool ok = ((uintptr_t)ptr % 16) == 0 && s0 % V == 0;
+      for (int i = 0; i < p.krank; i++) ok = ok && ks[i] % V == 0;
+      return ok;
+    };
+    bool vec = n1 % V == 0 && rchunk % V == 0 && al(pa, p.rrank == 2 ? p.rsa[0] : 0, p.ksa) &&
+               (!DOT || al(pb, p.rrank == 2 ? p.rsb[0] : 0, p.ksb));
+    if (vec) hb_reduce_runs_kernel<T, ACC, DOT, true><<<grid, block, 0, g_hb.stream>>>(p, pa, pb, dst, rchunk);
+    else hb_reduce_runs_kernel<T, ACC, DOT, false><<<grid, block, 0, g_hb.stream>>>(p, pa, pb, dst, rchunk);
+  } else if (rows)
     hb_reduce_rows_kernel<T, ACC, DOT><<<grid, block, 0, g_hb.stream>>>(p, pa, pb, dst, rchunk);
   else
     hb_reduce_cols_kernel<T, ACC, DOT><<<grid, block, 0, g_hb.stream>>>(p, pa, pb, dst, rchunk);
