@@ -84,6 +84,47 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// blockIdx.x = outer * nchunks + chunk, where "inner" is the product of the last
+// `irank` collapsed axes (short innermost axes, e.g. the [14,14,5] tail of a
+// broadcast im2col product): the outer index is decomposed once per block and
+// each element pays only `irank` small 32-bit divisions.
+template <int NOPS, typename F>
+__global__ void __launch_bounds__(256)
+    hb_iter_tile_kernel(hb_iterp<NOPS> it, int irank, int inner, int nchunks, int chunk, F f) {
+  int64_t outer = blockIdx.x / nchunks;
+  int c = blockIdx.x - outer * nchunks;
+  int64_t base[NOPS];
+#pragma unroll
+  for (int o = 0; o < NOPS; o++) base[o] = 0;
+  int64_t rem = outer;
+  const int orank = it.rank - irank;
+#pragma unroll 1
+  for (int d = orank - 1; d >= 0; d--) {
+    int64_t q = rem / it.shape[d];
+    int64_t r = rem - q * it.shape[d];
+#pragma unroll
+    for (int o = 0; o < NOPS; o++) base[o] += r * it.stride[o][d];
+    rem = q;
+  }
+  int i0 = c * chunk;
+  int i1 = i0 + chunk < inner ? i0 + chunk : inner;
+  for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+    int64_t off[NOPS];
+#pragma unroll
+    for (int o = 0; o < NOPS; o++) off[o] = base[o];
+    unsigned ri = (unsigned)i;
+#pragma unroll 1
+    for (int d = it.rank - 1; d >= orank; d--) {
+      unsigned sh = (unsigned)it.shape[d];
+      unsigned q = ri / sh, r = ri - q * sh;
+#pragma unroll
+      for (int o = 0; o < NOPS; o++) off[o] += (int64_t)r * it.stride[o][d];
+      ri = q;
+    }
+    f(outer * inner + i, off);
+  }
+}
+
 // Launch f(linear_index, offsets[NOPS]) over the iteration space.
 template <int NOPS, typename F>
 static int hb_launch_iter(const hb_iter &it, F f) {
@@ -102,6 +143,23 @@ static int hb_launch_iter(const hb_iter &it, F f) {
       hb_iter_rows_kernel<NOPS, F><<<(unsigned)blocks, 256, 0, g_hb.stream>>>(p, inner, nchunks, chunk, f);
       HB_LAUNCHED();
       return HB_OK;
+    }
+  }
+  if (it.rank >= 3 && n >= (1 << 16)) {
+    // short innermost axes: fold as many trailing axes as needed into a tile of >= 512 elements
+    int irank = 0;
+    int64_t tile = 1;
+    while (irank < it.rank - 1 && tile < 512) { tile *= it.shape[it.rank - 1 - irank]; irank++; }
+    int64_t outer = n / tile;
+    if (tile >= 64 && tile < (1 << 24)) {
+      int chunk = 2048;
+      int nchunks = (int)((tile + chunk - 1) / chunk);
+      int64_t blocks = outer * nchunks;
+      if (blocks < (1ll << 31)) {
+        hb_iter_tile_kernel<NOPS, F><<<(unsigned)blocks, 256, 0, g_hb.stream>>>(p, irank, (int)tile, nchunks, chunk, f);
+        HB_LAUNCHED();
+        return HB_OK;
+      }
     }
   }
   int blocks = hb_blocks_for(n, 256, g_hb.sm_count * 32);
