@@ -160,12 +160,16 @@ __device__ __forceinline__ void sp_stage(double (&acc)[MF][NQ][2], const int (&a
         const char *ia = Sb + (c * g.CS + kh * g.RS) * 8;
         const char *wb = Wb + (c * p.WCS + kh * p.KWP * p.TS) * 8;
         for (int g4 = 0; g4 < ng; g4++) {
+          // taps beyond KW exist only as padding of the k dimension: they contribute an
+          // exact zero whatever the data holds there (0 * Inf would be NaN)
+          const bool tapv = g4 * 4 + (int)(threadIdx.x & 3) < g.KW;
           double b[NQ];
 #pragma unroll
           for (int j = 0; j < NQ; j++) b[j] = *reinterpret_cast<const double *>(wb + j * 64);
 #pragma unroll
           for (int i = 0; i < NF; i++) {
             double a = *reinterpret_cast<const double *>(ia + aoff[i]);
+            a = tapv ? a : 0.0;
 #pragma unroll
             for (int j = 0; j < NQ; j++) dmma884(acc[i][j][0], acc[i][j][1], a, b[j]);
           }

@@ -206,3 +206,47 @@ def smap0N(T, f, t):
 def scond(T, b: bool, u, v):
     """scond / tcond (OpsConcrete.hs:113-119): a host `if` on a host Bool."""
     return u if b else v
+
+
+def szipWith0N(T, f, a, b):
+    """tszipWith0N (Ops.hs:934): per-element host function over two tensors."""
+    sh = list(T.shape(a))
+    n = int(np.prod(sh))
+    fa, fb = T.sreshape([n], a), T.sreshape([n], b)
+    out = T.sfromVector([f(x, y) for x, y in zip(T.sunravelToList(fa), T.sunravelToList(fb))])
+    return T.sreshape(sh, out)
+
+
+def sbuild(T, shm, f):
+    """tsbuild @shm (Ops.hs:913): f over every index of shm, row-major, results
+    of shape shn placed at their index: shm ++ shn."""
+    shm = list(shm)
+    if not shm:
+        return f(())
+    import itertools
+    parts = [f(ix) for ix in itertools.product(*[range(k) for k in shm])]
+    stacked = T.sfromVector(parts)                        # [prod shm] ++ shn
+    return T.sreshape(shm + list(T.shape(parts[0])), stacked)
+
+
+def sfromVectorLinear(T, shm, scalars):
+    """tsfromVectorLinear (Ops.hs:429): prod shm 0-d tensors -> shm."""
+    return T.sreshape(list(shm), T.sfromVector(list(scalars)))
+
+
+def stoListLinear(T, t):
+    """tstoListLinear (Ops.hs:439): the 0-d elements of t in row-major order."""
+    n = int(np.prod(T.shape(t))) if len(T.shape(t)) else 1
+    return T.sunravelToList(T.sreshape([n], t))
+
+
+def sminimum(T, t):
+    """sminimum (CommonShapedOps.hs:28-31): t ! argMin of the flattened tensor."""
+    flat = T.sreshape([int(np.prod(T.shape(t)))], t)
+    return T.sindex(flat, [int(T.kfromS(T.sargMin(flat)))])
+
+
+def smaximum(T, t):
+    """smaximum (CommonShapedOps.hs:33-36)."""
+    flat = T.sreshape([int(np.prod(T.shape(t)))], t)
+    return T.sindex(flat, [int(T.kfromS(T.sargMax(flat)))])

@@ -380,6 +380,19 @@ def test_conv_fwd_vjp_vs_oracle(dev, oracle, dtype, shape):
         close(dev.to_numpy(nn.conv2dPreservingS_vectorised(dev, dK_, dA_)), oracle.conv2dPreserving(K, A), dtype, scale=100)
 
 
+def test_conv_non_finite_input_stays_local(dev, oracle):
+    """An Inf in the input reaches exactly the outputs whose window covers it (as
+    on the oracle): the zero padding of the k dimension in the tap-k DMMA mode
+    must not turn 0 * Inf into NaN elsewhere."""
+    rng = np.random.default_rng(33)
+    K, A = rnd(rng, (16, 1, 5, 5)), rnd(rng, (3, 1, 28, 28))
+    A[1, 0, 10, 12] = np.inf
+    got = dev.to_numpy(dev.conv2dPreserving(dev.sconcrete(K), dev.sconcrete(A)))
+    ref = oracle.conv2dPreserving(K, A)
+    assert np.array_equal(np.isfinite(got), np.isfinite(ref))
+    np.testing.assert_allclose(got[np.isfinite(ref)], ref[np.isfinite(ref)], rtol=1e-11, atol=1e-13)
+
+
 def test_conv_full_size_adjoint_property(dev):
     """ConvVjpBench at BASELINE's size: size-independent checks (adjointness,
     linearity) instead of an oracle run."""
@@ -626,6 +639,14 @@ def test_folds_builds_and_cond(dev, oracle):
     m0 = nn.smap0N(dev, lambda x: dev.unary("negate", x), t)
     exact(dev.to_numpy(m0), -a0)
     assert nn.scond(dev, dev.all_leq(t, t), t, m0) is t
+    z = nn.szipWith0N(dev, lambda x, y: dev.binary("mul", x, y), t, m0)
+    exact(dev.to_numpy(z), a0 * -a0)
+    bld = nn.sbuild(dev, [2, 3], lambda ix: dev.srepl([4], float(10 * ix[0] + ix[1])))
+    exact(dev.to_numpy(bld), np.array([[[10.0 * i + j] * 4 for j in range(3)] for i in range(2)]))
+    lin = nn.stoListLinear(dev, t)
+    assert len(lin) == 12 and dev.kfromS(lin[5]) == a0.reshape(-1)[5]
+    exact(dev.to_numpy(nn.sfromVectorLinear(dev, [3, 4], lin)), a0)
+    assert dev.kfromS(nn.sminimum(dev, t)) == a0.min() and dev.kfromS(nn.smaximum(dev, t)) == a0.max()
 
 
 def test_graph_capture_replay(dev):
