@@ -168,6 +168,44 @@ def alg_work(tag: str, kh1: int, kw1: int):
     return None
 
 
+# ------------------------------------------------------- CPU oracle workers
+def _cpu_worker(args):
+    """One host core: `steps` oracle training steps (dual-number gradient of
+    convMnistLossFusedS + Adam) on its own shard of `batch` samples."""
+    seed, batch, steps = args
+    os.environ["OMP_NUM_THREADS"] = "1"
+    from horde_ad_b200 import ad, mnist_cnn
+    from oracle.concrete import ConcreteBackend
+    orc = ConcreteBackend()
+    rng = np.random.Generator(np.random.Philox(seed))
+    gl = rng.uniform(0, 1, (batch, 28, 28))
+    lb = np.eye(10)[rng.integers(0, 10, batch)]
+    ps = mnist_cnn.init_params(HYPER["kh"], HYPER["kw"], HYPER["c_out"], HYPER["n_hidden"])
+    ms = [np.zeros_like(p) for p in ps]
+    vs = [np.zeros_like(p) for p in ps]
+    val = 0.0
+    for t in range(steps):
+        val, grads = ad.grad(orc, lambda T, *p: mnist_cnn.convMnistLossFusedS(T, gl, lb, list(p), fused=True), ps)
+        for p, m, v, g in zip(ps, ms, vs, grads):
+            orc.adam_step(p, m, v, np.asarray(g), t + 1)
+    return float(val)
+
+
+def cpu_oracle_rate(per_worker_batch: int, steps: int, workers: int):
+    """samples/s of the oracle with `workers` processes, each owning a shard
+    (the data-parallel decomposition of the GPU arm, on host cores); the
+    reference's own interpreter is single-threaded, this is every core it
+    could be given."""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(workers) as pool:
+        pool.map(_cpu_worker, [(100 + i, 8, 1) for i in range(workers)])          # start-up + warm-up
+        t0 = time.perf_counter()
+        pool.map(_cpu_worker, [(42 + i, per_worker_batch, steps) for i in range(workers)])
+        dt = time.perf_counter() - t0
+    return workers * per_worker_batch * steps / dt, dt
+
+
 # ---------------------------------------------------------------- reference arm
 def run_reference(args, rank, world):
     """The reference's own CPU path: the oracle restatement of the Concrete
@@ -175,39 +213,20 @@ def run_reference(args, rank, world):
     (dual-number gradient of convMnistLossFusedS + Adam), bounded sample."""
     if rank != 0:
         return
-    from horde_ad_b200 import ad, mnist_cnn
-    from oracle.concrete import ConcreteBackend
-    orc = ConcreteBackend()
-    sample = args.cpu_sample
-    rng = np.random.Generator(np.random.Philox(42))
-    gl = rng.uniform(0, 1, (sample, 28, 28))
-    lb = np.eye(10)[rng.integers(0, 10, sample)]
-    hy = (HYPER["kh"], HYPER["kw"], HYPER["c_out"], HYPER["n_hidden"])
-    ps = mnist_cnn.init_params(*hy)
-    ms = [np.zeros_like(p) for p in ps]
-    vs = [np.zeros_like(p) for p in ps]
-
-    def step(t):
-        val, grads = ad.grad(orc, lambda T, *p: mnist_cnn.convMnistLossFusedS(T, gl, lb, list(p), fused=True), ps)
-        for p, m, v, g in zip(ps, ms, vs, grads):
-            orc.adam_step(p, m, v, np.asarray(g), t)
-        return float(val)
-
-    steps, warm = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
-    for i in range(warm):
-        step(i + 1)
-    t0 = time.perf_counter()
-    for i in range(steps):
-        step(warm + i + 1)
-    dt = (time.perf_counter() - t0) / steps
-    val = sample / dt
+    workers = args.cpu_workers or (os.cpu_count() or 1)
+    per = max(8, args.cpu_sample // workers)
+    steps, warm = max(1, min(args.steps, 3)), 1
+    val, dt_total = cpu_oracle_rate(per, steps, workers)
+    dt = dt_total / steps
+    sample = per * workers
     out = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": config_dict(args, world),
-        "cpu_baseline": {"value": val, "unit": "samples/s", "cores": 1, "kind": "port",
-                         "sample": f"{steps} steps of batch {sample} (of {PER_GPU_BATCH}); numpy oracle, single thread"},
+        "cpu_baseline": {"value": val, "unit": "samples/s", "cores": workers, "kind": "port",
+                         "sample": f"{steps} steps of {workers} shards x {per} samples (of {PER_GPU_BATCH}); numpy oracle, "
+                                   f"one process per host core"},
         "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "host": {"nproc": os.cpu_count()},
@@ -233,7 +252,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
-    ap.add_argument("--cpu-sample", type=int, default=512, help="batch of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=8192, help="samples per step of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-workers", type=int, default=0, help="host processes of the CPU baseline (0 = all cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-conv-vjp", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
@@ -411,7 +431,7 @@ def main():
     if not args.no_conv_vjp:
         out["conv_vjp"] = conv_vjp_bench(dev, ffi, hbm_peak, fp64_peak)
     if not args.no_cpu_baseline and world == 1:
-        out["cpu_baseline"] = cpu_baseline(args.cpu_sample)
+        out["cpu_baseline"] = cpu_baseline(args.cpu_sample, args.cpu_workers)
     print(json.dumps(out), flush=True)
     tr.close()
     if dist is not None:
@@ -516,27 +536,14 @@ def conv_vjp_bench(dev, ffi, hbm_peak, fp64_peak, reps=10):
     return out
 
 
-def cpu_baseline(sample: int):
+def cpu_baseline(sample: int, workers: int = 0):
     """The oracle on the box's host cores, bounded sample (same program)."""
-    from horde_ad_b200 import ad, mnist_cnn
-    from oracle.concrete import ConcreteBackend
-    orc = ConcreteBackend()
-    rng = np.random.Generator(np.random.Philox(42))
-    gl = rng.uniform(0, 1, (sample, 28, 28))
-    lb = np.eye(10)[rng.integers(0, 10, sample)]
-    ps = mnist_cnn.init_params(HYPER["kh"], HYPER["kw"], HYPER["c_out"], HYPER["n_hidden"])
-    ms = [np.zeros_like(p) for p in ps]
-    vs = [np.zeros_like(p) for p in ps]
-    reps = 2
-    t0 = time.perf_counter()
-    for t in range(reps):
-        _, grads = ad.grad(orc, lambda T, *p: mnist_cnn.convMnistLossFusedS(T, gl, lb, list(p), fused=True), ps)
-        for p, m, v, g in zip(ps, ms, vs, grads):
-            orc.adam_step(p, m, v, np.asarray(g), t + 1)
-    dt = (time.perf_counter() - t0) / reps
-    return {"value": sample / dt, "unit": "samples/s", "cores": 1, "kind": "port",
-            "sample": f"{reps} steps of batch {sample} (of {PER_GPU_BATCH}); numpy oracle, single thread",
-            "host_nproc": os.cpu_count()}
+    workers = workers or (os.cpu_count() or 1)
+    per = max(8, sample // workers)
+    rate, dt = cpu_oracle_rate(per, 2, workers)
+    return {"value": rate, "unit": "samples/s", "cores": workers, "kind": "port",
+            "sample": f"2 steps of {workers} shards x {per} samples (of {PER_GPU_BATCH}); numpy oracle, one process per "
+                      f"host core ({dt:.1f} s)", "host_nproc": os.cpu_count()}
 
 
 if __name__ == "__main__":
