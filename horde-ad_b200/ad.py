@@ -430,3 +430,210 @@ def grad(base, f: Callable, inputs: Sequence, dt=None):
         if grads[i] is None:
             grads[i] = base.srepl(base.shape(x), 0, base.dtype(x))
     return out.p, grads
+
+
+# =====================================================================
+# Forward mode: cjvp (ADEngine.hs:544-555; evalFwd, DeltaEval.hs:778)
+# =====================================================================
+class Dual:
+    """Primal + tangent (None = zero tangent / constant)."""
+    __slots__ = ("p", "t")
+
+    def __init__(self, p, t=None):
+        self.p = p
+        self.t = t
+
+    @property
+    def shape(self):
+        return tuple(self.p.shape)
+
+
+class FwdBackend:
+    """`target = ADVal base` evaluated forwards: every op computes its primal
+    and pushes the tangent through the same linear map the reverse rule
+    transposes.  Same method surface as ADBackend for the ops the example
+    networks use."""
+
+    def __init__(self, base):
+        self.B = base
+        self.name = "fwd(" + base.name + ")"
+
+    def lift(self, x):
+        return x if isinstance(x, Dual) else Dual(x)
+
+    def primal(self, x):
+        return x.p if isinstance(x, Dual) else x
+
+    def _lin(self, ts, f):
+        """f applied to the tangents (all operands of a linear op); None stays None."""
+        return None if all(t is None for t in ts) else f
+
+    def _add(self, a, b):
+        if a is None:
+            return b
+        if b is None:
+            return a
+        return self.B.binary("add", a, b)
+
+    def _zeros_like(self, p):
+        return self.B.srepl(list(self.B.shape(p)), 0, self.B.dtype(p))
+
+    def shape(self, t): return tuple(self.primal(t).shape)
+    def dtype(self, t): return self.B.dtype(self.primal(t))
+    def sconcrete(self, a): return Dual(self.B.sconcrete(a))
+    def srepl(self, shape, value, dtype=np.float64): return Dual(self.B.srepl(shape, value, dtype))
+    def sscalar(self, value, dtype=np.float64): return Dual(self.B.sscalar(value, dtype))
+    def kfromS(self, t): return self.B.kfromS(self.primal(t))
+    def sprimalPart(self, t): return self.primal(t)
+    def ix_tbl(self, t, ixs): return self.B.ix_tbl(self.primal(t), ixs)
+    def ix_argmax(self, t, ixs): return self.B.ix_argmax(self.primal(t), ixs)
+    def ix_argmin(self, t, ixs): return self.B.ix_argmin(self.primal(t), ixs)
+
+    def _map(self, x, f):
+        """A linear structural op: f on the primal and on the tangent."""
+        x = self.lift(x)
+        return Dual(f(x.p), None if x.t is None else f(x.t))
+
+    def binary(self, op, a, b):
+        B = self.B
+        a, b = self.lift(a), self.lift(b)
+        p = B.binary(op, a.p, b.p)
+        if a.t is None and b.t is None:
+            return Dual(p)
+        if op == "add":
+            return Dual(p, self._add(a.t, b.t))
+        if op == "sub":
+            return Dual(p, self._add(a.t, None if b.t is None else B.unary("negate", b.t)))
+        if op == "mul":
+            ta = None if a.t is None else B.binary("mul", a.t, b.p)
+            tb = None if b.t is None else B.binary("mul", a.p, b.t)
+            return Dual(p, self._add(ta, tb))
+        if op == "divide":
+            ta = None if a.t is None else B.binary("divide", a.t, b.p)
+            tb = None if b.t is None else B.unary("negate", B.binary("divide", B.binary("mul", p, b.t), b.p))
+            return Dual(p, self._add(ta, tb))
+        raise NotImplementedError(f"forward derivative of {op}")
+
+    def unary(self, op, a):
+        B = self.B
+        a = self.lift(a)
+        p = B.unary(op, a.p)
+        if a.t is None or op == "signum":
+            return Dual(p)
+        one = lambda: B.srepl(list(B.shape(p)), 1, B.dtype(p))
+        sq = lambda x: B.binary("mul", x, x)
+        k = {
+            "negate": lambda: B.unary("negate", one()), "abs": lambda: B.unary("signum", a.p),
+            "recip": lambda: B.unary("negate", sq(p)), "exp": lambda: p, "log": lambda: B.unary("recip", a.p),
+            "sqrt": lambda: B.unary("recip", B.binary("add", p, p)), "sin": lambda: B.unary("cos", a.p),
+            "cos": lambda: B.unary("negate", B.unary("sin", a.p)),
+            "tan": lambda: B.binary("add", one(), sq(p)), "tanh": lambda: B.binary("sub", one(), sq(p)),
+            "sinh": lambda: B.unary("cosh", a.p), "cosh": lambda: B.unary("sinh", a.p),
+            "atan": lambda: B.unary("recip", B.binary("add", one(), sq(a.p))),
+        }[op]()
+        return Dual(p, B.binary("mul", k, a.t))
+
+    def custom_unary(self, t, primal, vjp):
+        B = self.B
+        t = self.lift(t)
+        y = primal(B, t.p)
+        # an elementwise custom dual is symmetric: the vjp IS the jvp
+        return Dual(y, None if t.t is None else vjp(B, t.p, y, t.t))
+
+    def scast(self, t, dtype):
+        B = self.B
+        t = self.lift(t)
+        fl = np.issubdtype(np.dtype(dtype), np.floating) and np.issubdtype(B.dtype(t.p), np.floating)
+        return Dual(B.scast(t.p, dtype), B.scast(t.t, dtype) if (fl and t.t is not None) else None)
+
+    # structure (all linear)
+    def stranspose(self, perm, t): return self._map(t, lambda x: self.B.stranspose(list(perm), x))
+    def sreshape(self, sh, t): return self._map(t, lambda x: self.B.sreshape(list(sh), x))
+    def sreplicateN(self, shm, t): return self._map(t, lambda x: self.B.sreplicateN(list(shm), x))
+    def sreplicate(self, k, t): return self.sreplicateN([k], t)
+    def sreplicate0N(self, shm, t0): return self.sreplicateN(shm, t0)
+    def ssumN(self, t, n): return self._map(t, lambda x: self.B.ssumN(x, n))
+    def ssum(self, t): return self.ssumN(t, 1)
+    def ssum0(self, t): return self.ssumN(t, len(self.shape(t)))
+    def sslice(self, i, n, t): return self._map(t, lambda x: self.B.sslice(i, n, x))
+    def sreverse(self, t): return self._map(t, lambda x: self.B.sreverse(x))
+    def sindex(self, t, ixs): return self._map(t, lambda x: self.B.sindex(x, [int(i) for i in ixs]))
+    def sunravelToList(self, t): return [self.sindex(t, [i]) for i in range(self.shape(t)[0])]
+
+    def sgather(self, shm, t, f, shp_rank, prog=None):
+        return self._map(t, lambda x: self.B.sgather(list(shm), x, f, shp_rank, prog))
+
+    def sscatter(self, shp, t, f, shm_rank, prog=None):
+        return self._map(t, lambda x: self.B.sscatter(list(shp), x, f, shm_rank, prog))
+
+    def _tangent_or_zero(self, d):
+        return d.t if d.t is not None else self._zeros_like(d.p)
+
+    def sappend(self, a, b):
+        a, b = self.lift(a), self.lift(b)
+        t = None if (a.t is None and b.t is None) else self.B.sappend(self._tangent_or_zero(a), self._tangent_or_zero(b))
+        return Dual(self.B.sappend(a.p, b.p), t)
+
+    def sfromVector(self, ts):
+        ts = [self.lift(t) for t in ts]
+        tt = None if all(t.t is None for t in ts) else self.B.sfromVector([self._tangent_or_zero(t) for t in ts])
+        return Dual(self.B.sfromVector([t.p for t in ts]), tt)
+
+    # contractions (bilinear)
+    def _bilinear(self, f, a, b):
+        a, b = self.lift(a), self.lift(b)
+        ta = None if a.t is None else f(a.t, b.p)
+        tb = None if b.t is None else f(a.p, b.t)
+        return Dual(f(a.p, b.p), self._add(ta, tb))
+
+    def sdot0(self, a, b): return self._bilinear(self.B.sdot0, a, b)
+    def sdot1In(self, a, b): return self._bilinear(self.B.sdot1In, a, b)
+    def smatmul2(self, a, b): return self._bilinear(self.B.smatmul2, a, b)
+    def smatvecmul(self, m, v): return self._bilinear(self.B.smatvecmul, m, v)
+    def conv2dPreserving(self, K, A): return self._bilinear(self.B.conv2dPreserving, K, A)
+
+    def sdot1InSumN(self, a, b, n):
+        return self._bilinear(lambda x, y: self.B.sdot1InSumN(x, y, n), a, b)
+
+    # NN blocks
+    def relu(self, t):
+        B = self.B
+        t = self.lift(t)
+        y = B.relu(t.p)
+        return Dual(y, None if t.t is None else B.binary("mul", B.unary("signum", y), t.t))
+
+    def maxpool2d(self, x, ksize, stride):
+        """Tangent of the pooled value = the tangent at the window's argmax: a
+        gather whose index function reads the argmax tensor (table lookup)."""
+        B = self.B
+        x = self.lift(x)
+        y, am = B.maxpool2d(x.p, ksize, stride)
+        if x.t is None:
+            return Dual(y)
+        N, Cc, Ho, Wo = B.shape(y)
+
+        def f(ix):
+            a = B.ix_tbl(am, ix)
+            return [ix[0], ix[1], stride * ix[2] + a.quotH(ksize), stride * ix[3] + a.remH(ksize)]
+        return Dual(y, B.sgather([N, Cc, Ho, Wo], x.t, f, 4))
+
+    def conv_relu_pool(self, K, bias, A, ksize):
+        N, _, H, W = self.shape(A)
+        pre = self.binary("add", self.conv2dPreserving(K, A),
+                          self.stranspose([0, 3, 1, 2], self.sreplicateN([N, H, W], bias)))
+        return self.maxpool2d(self.relu(pre), ksize, ksize)
+
+    def softmax_xent(self, logits, expected, scale=1.0, want_grad=True):
+        B = self.B
+        logits = self.lift(logits)
+        loss, dl = B.softmax_xent(logits.p, self.primal(expected), scale, want_grad=logits.t is not None)
+        return Dual(loss, None if logits.t is None else B.sdot0(dl, logits.t)), None
+
+
+def jvp(base, f: Callable, inputs: Sequence, tangents: Sequence):
+    """cjvp (ADEngine.hs:544-555): (value, directional derivative of f at
+    `inputs` along `tangents`); a None tangent is zero."""
+    T = FwdBackend(base)
+    out = T.lift(f(T, *[Dual(x, t) for x, t in zip(inputs, tangents)]))
+    t = out.t if out.t is not None else T._zeros_like(out.p)
+    return out.p, t

@@ -649,6 +649,26 @@ def test_folds_builds_and_cond(dev, oracle):
     assert dev.kfromS(nn.sminimum(dev, t)) == a0.min() and dev.kfromS(nn.smaximum(dev, t)) == a0.max()
 
 
+@pytest.mark.parametrize("fused", [True, "nodes", False])
+def test_forward_reverse_duality_on_device(dev, fused):
+    """<cgrad f, ds> = cjvp f ds on the device (TestConvQuickCheck.hs:182-268): a
+    size-independent check that needs no oracle; the forward mode exercises the
+    gather-at-argmax index programs, the reverse mode their scatters."""
+    rng = np.random.Generator(np.random.Philox(14))
+    batch = 64 if fused is not False else 8
+    hyper = (4, 4, 16, 64) if fused is not False else (2, 2, 4, 8)
+    glyphs, labels = dev.sconcrete(rng.uniform(0, 1, (batch, 28, 28))), dev.sconcrete(np.eye(10)[rng.integers(0, 10, batch)])
+    host = mnist_cnn.init_params(*hyper)
+    params = [dev.sconcrete(p) for p in host]
+    ds_host = [rng.uniform(-1, 1, p.shape) for p in host]
+    ds = [dev.sconcrete(d) for d in ds_host]
+    f = lambda T, *ps: mnist_cnn.convMnistLossFusedS(T, glyphs, labels, list(ps), fused=fused)
+    _, grads = ad.grad(dev, f, params)
+    _, tan = ad.jvp(dev, f, params, ds)
+    lhs = sum(float(np.sum(dev.to_numpy(g) * d)) for g, d in zip(grads, ds_host))
+    np.testing.assert_allclose(float(dev.kfromS(tan)), lhs, rtol=1e-9)
+
+
 def test_graph_capture_replay(dev):
     rng = np.random.default_rng(20)
     x = dev.sconcrete(rng.uniform(-.5, .5, (64, 32)))

@@ -175,3 +175,26 @@ def test_committed_golden_fixture_is_in_sync(oracle):
         else:
             got = oracle.conv2d_dkrn(A, np.ones((A.shape[0], K.shape[0], A.shape[2], A.shape[3])), K.shape[2], K.shape[3])
         np.testing.assert_allclose(got.reshape(-1), e["expected_gradient"], atol=e["eps"], rtol=0)
+
+
+def test_forward_reverse_duality_on_the_oracle(oracle):
+    """<grad f, ds> = jvp f ds (the reference's QuickCheck property,
+    TestConvQuickCheck.hs:182-268) for the CNN, FCNN and a gather program."""
+    from horde_ad_b200 import mnist_cnn, mnist_fcnn
+    rng = np.random.Generator(np.random.Philox(8))
+    glyphs, labels = rng.uniform(0, 1, (3, 28, 28)), np.eye(10)[rng.integers(0, 10, 3)]
+    params = mnist_cnn.init_params(1, 2, 3, 4)
+    ds = [rng.uniform(-1, 1, p.shape) for p in params]
+    for fused in (True, "nodes", False):
+        f = lambda T, *ps: mnist_cnn.convMnistLossFusedS(T, glyphs, labels, list(ps), fused=fused)
+        _, grads = ad.grad(oracle, f, params)
+        _, tan = ad.jvp(oracle, f, params, ds)
+        lhs = sum(float(np.sum(np.asarray(g) * d)) for g, d in zip(grads, ds))
+        np.testing.assert_allclose(float(np.asarray(tan)), lhs, rtol=1e-10)
+    datum, target = rng.uniform(0, 1, 784), np.eye(10)[2]
+    fp = mnist_fcnn.init_params(5, 4, rng_range=0.3, q=np.float64)
+    fds = [rng.uniform(-1, 1, p.shape) for p in fp]
+    g = lambda T, *ps: mnist_fcnn.afcnnMnistLoss2(T, datum, target, list(ps))
+    _, grads = ad.grad(oracle, g, fp)
+    _, tan = ad.jvp(oracle, g, fp, fds)
+    np.testing.assert_allclose(float(np.asarray(tan)), sum(float(np.sum(np.asarray(a) * d)) for a, d in zip(grads, fds)), rtol=1e-10)
