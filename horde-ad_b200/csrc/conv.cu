@@ -28,6 +28,12 @@ int hb_conv_sp_dmma(const hb_array *K, const hb_array *in, hb_array *out, int fl
 int hb_conv_dk_dmma(const hb_array *A, const hb_array *dB, const hb_array *code, hb_array *out, int KH, int KW,
                     int *done);
 
+// conv_strip.cu: warp-autonomous kernels for the one-input-channel layer
+int hb_conv_strip_fwd(const hb_array *K, const hb_array *bias, const hb_array *A, hb_array *y, hb_array *code,
+                      int *done);
+int hb_conv_strip_dk(const hb_array *A, const hb_array *dy, const hb_array *code, int KH, int KW, hb_array *dK,
+                     hb_array *dbias, int *done);
+
 // Runs the DMMA fast path into a fresh [n0,n1,n2,n3] array when it applies.
 static int try_sp(const hb_array *K, const hb_array *in, const int64_t *osh, int flip, hb_array **out, int *done) {
   *done = 0;
@@ -234,7 +240,8 @@ extern "C" int hb_conv_relu_pool_fwd(const hb_array *K, const hb_array *bias, co
     int st = hb_new_array(HB_F64, 4, osh, &pf.y);
     if (st == HB_OK) st = hb_new_array(HB_I8, 4, osh, &pf.code);
     int done = 0;
-    if (st == HB_OK) st = hb_conv_sp_dmma(K, A, nullptr, 0, &pf, &done);
+    if (st == HB_OK) st = hb_conv_strip_fwd(K, bias, A, pf.y, pf.code, &done);
+    if (st == HB_OK && !done) st = hb_conv_sp_dmma(K, A, nullptr, 0, &pf, &done);
     if (st == HB_OK && done) {
       *out = pf.y;
       *code_out = pf.code;
@@ -271,6 +278,19 @@ extern "C" int hb_conv_relu_pool_bwd(const hb_array *K, const hb_array *A, const
     int done = 0;
     int64_t ksh[4] = {K->shape[0], K->shape[1], KH, KW};
     HB_TRY(hb_new_array(HB_F64, 4, ksh, &dk));
+    {
+      // one input channel: dK and the bias cotangent out of one warp-autonomous kernel
+      hb_array *db = nullptr;
+      if (dbias_out) st = hb_new_array(HB_F64, 1, &K->shape[0], &db);
+      if (st == HB_OK) st = hb_conv_strip_dk(A, dy, code, KH, KW, dk, db, &done);
+      if (st == HB_OK && done) {
+        *dK_out = dk;
+        if (dbias_out) *dbias_out = db;
+        return HB_OK;
+      }
+      hb_release(db);
+      if (st != HB_OK) { hb_release(dk); return st; }
+    }
     st = hb_conv_dk_dmma(A, dy, code, dk, KH, KW, &done);
     if (st == HB_OK && done) {
       if (dbias_out) st = hb_relu_pool_bwd(dy, code, ksize, H, W, nullptr, dbias_out);

@@ -1,0 +1,428 @@
+// conv_strip.cu -- warp-autonomous DMMA kernels for the ONE-input-channel
+// convolution layer (the first layer of MnistCnnShaped2: 1 -> c_out channels,
+// (kh+1) x (kw+1) taps on 28 x 28 glyphs, MnistCnnShaped2.hs:42-62), fused with
+// its bias + relu + 2x2 max-pool tail and, backwards, with the pooled cotangent.
+//
+// Why a separate kernel: with a single input channel a work item is tiny (a
+// pair of output rows = one pooled row needs a 6 x 36 input strip), so the
+// CTA-wide stage barriers of conv_dmma.cu dominated (ncu: DMMA pipe 39 % / 47 %
+// active).  Here nothing is shared between warps except the read-only weights:
+// every warp owns a stream of (image, row pair) items, stages its own strips
+// with cp.async (double-buffered, __syncwarp only), runs its DMMAs, pools in its
+// own shared tile and writes its pooled row.  No __syncthreads in steady state;
+// the other 15 warps of the SM hide each warp's latencies.
+//
+//   forward : M = 8 positions of the row pair, N = 8 output channels,
+//             K = 4 taps of the FLATTENED (kh, kw) tap list (25 -> 28, not
+//             5 x 8 = 40 as in the tap-k mode of conv_dmma.cu)
+//   dKrn    : M = 8 output channels, N = 8 flattened taps, K = 4 positions;
+//             the cotangent tile is expanded from (dy pooled, code) in shared
+//             memory; tap slot KH*KW carries a column of ONES, so the bias
+//             cotangent falls out of the same DMMAs; per-CTA partials are
+//             reduced in fixed order (deterministic).
+#include "common.cuh"
+
+namespace {
+
+constexpr int WPB = 16;            // warps per block
+constexpr int NTHR = WPB * 32;
+constexpr int MF = 7;              // position fragments of a row pair (2 * W <= 56)
+
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+      : "+d"(c0), "+d"(c1)
+      : "d"(a), "d"(b));
+}
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp16(void *s, const void *g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(s)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+struct StripP {
+  const double *A;       // [N, 1, H, W]
+  const double *wp;      // forward: packed weights [NT][TS] (tap-major, zero padded)
+  const double *bias;    // forward: [Q] or NULL
+  double *y;             // forward: pooled output [N, Q, H/2, W/2]
+  uint8_t *code;         // forward: out; dKrn: in
+  const double *dy;      // dKrn: pooled cotangent [N, Q, H/2, W/2]
+  double *part;          // dKrn: [gridDim.x][Q][KK + 1]
+  int N, Q, H, W, KH, KW, KK;
+  int NT;                // taps rounded up to 4 (forward) / 8 (dKrn)
+  int RS, TR, SD;        // strip row stride, rows, doubles
+  int TS, OPS, PS;       // weight tap stride; pooled-tile / cotangent-tile strides
+  int items;             // N * H / 2
+  int w_doubles;         // shared weights block (forward)
+  int warp_doubles;      // per-warp shared region
+};
+
+// rows [2 rp, 2 rp + TR) of image n -> strip (rows beyond the image zero; the halo columns stay zero)
+__device__ __forceinline__ void load_strip(double *dst, const StripP &p, int item, int lane) {
+  const int Ho = p.H >> 1;
+  const int n = item / Ho, rp = item - n * Ho;
+  const double *src = p.A + (int64_t)n * p.H * p.W + (int64_t)(2 * rp) * p.W;
+  const int cpr = p.W >> 1, total = p.TR * cpr;
+  for (int i = lane; i < total; i += 32) {
+    int t = i / cpr, ch = i - t * cpr;
+    double *d = dst + t * p.RS + 2 * ch;
+    if (2 * rp + t < p.H) cp16(d, src + t * p.W + 2 * ch);
+    else *reinterpret_cast<double2 *>(d) = make_double2(0.0, 0.0);
+  }
+}
+
+// ------------------------------------------------------------------ forward
+template <int NQ>
+__global__ void __launch_bounds__(NTHR, 1) strip_fwd_kernel(const __grid_constant__ StripP p) {
+  extern __shared__ __align__(16) double smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int fr = lane >> 2, fk = lane & 3;
+  double *Wsm = smem;
+  int *tapoff = reinterpret_cast<int *>(smem + p.w_doubles);          // [NT] byte offsets into a strip
+  double *mine = smem + p.w_doubles + ((p.NT + 1) >> 1) + warp * p.warp_doubles;
+  double *ot = mine + 2 * p.SD;                                        // [QT][OPS]
+
+  for (int i = tid; i < p.w_doubles; i += NTHR) Wsm[i] = p.wp[i];
+  for (int i = tid; i < p.NT; i += NTHR) tapoff[i] = i < p.KK ? ((i / p.KW) * p.RS + (i % p.KW)) * 8 : 0;
+  for (int i = lane; i < p.warp_doubles; i += 32) mine[i] = 0.0;
+  __syncthreads();
+
+  const int Wo = p.W >> 1, Ho = p.H >> 1, W2 = 2 * p.W;
+  int aoff[MF];
+#pragma unroll
+  for (int i = 0; i < MF; i++) {
+    int pos = i * 8 + fr;
+    int pc = pos < W2 ? pos : 0;
+    int yy = pc / p.W, x = pc - yy * p.W;
+    aoff[i] = (yy * p.RS + x) * 8;
+  }
+  double bv[NQ][2];
+#pragma unroll
+  for (int j = 0; j < NQ; j++)
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      int q = j * 8 + fk * 2 + e;
+      bv[j][e] = (p.bias && q < p.Q) ? p.bias[q] : 0.0;
+    }
+  const int64_t gw = (int64_t)blockIdx.x * WPB + warp, nw = (int64_t)gridDim.x * WPB;
+  const int ng = p.NT >> 2;
+  int buf = 0;
+  if (gw < p.items) load_strip(mine, p, (int)gw, lane);
+  cp_commit();
+  for (int64_t it = gw; it < p.items; it += nw) {
+    if (it + nw < p.items) {
+      load_strip(mine + (buf ^ 1) * p.SD, p, (int)(it + nw), lane);
+      cp_commit();
+      cp_wait<1>();
+    } else {
+      cp_wait<0>();
+    }
+    __syncwarp();
+    const char *Sb = reinterpret_cast<const char *>(mine + buf * p.SD);
+    double acc[MF][NQ][2];
+#pragma unroll
+    for (int i = 0; i < MF; i++)
+#pragma unroll
+      for (int j = 0; j < NQ; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int g = 0; g < ng; g++) {
+      const int t = g * 4 + fk;
+      const int to = tapoff[t];
+      const bool tv = t < p.KK;   // padded taps contribute exact zeros
+      double b[NQ];
+#pragma unroll
+      for (int j = 0; j < NQ; j++) b[j] = Wsm[t * p.TS + j * 8 + fr];
+#pragma unroll
+      for (int i = 0; i < MF; i++) {
+        double a = *reinterpret_cast<const double *>(Sb + aoff[i] + to);
+        a = tv ? a : 0.0;
+#pragma unroll
+        for (int j = 0; j < NQ; j++) dmma884(acc[i][j][0], acc[i][j][1], a, b[j]);
+      }
+    }
+    // bias, then the row pair's pre-activations into the warp's [channel][position] tile
+#pragma unroll
+    for (int i = 0; i < MF; i++) {
+      int pos = i * 8 + fr;
+      if (pos < W2) {
+#pragma unroll
+        for (int j = 0; j < NQ; j++)
+#pragma unroll
+          for (int e = 0; e < 2; e++) ot[(j * 8 + fk * 2 + e) * p.OPS + pos] = acc[i][j][e] + bv[j][e];
+      }
+    }
+    __syncwarp();
+    const int n = (int)(it / Ho), rp = (int)(it - (int64_t)n * Ho);
+    const int nout = p.Q * Wo;
+    for (int o = lane; o < nout; o += 32) {
+      int q = o / Wo, jj = o - q * Wo;
+      const double *oq = ot + q * p.OPS + 2 * jj;
+      double2 r0 = *reinterpret_cast<const double2 *>(oq), r1 = *reinterpret_cast<const double2 *>(oq + p.W);
+      double v[4] = {r0.x, r0.y, r1.x, r1.y};
+      double best = 0.0, bestpre = 0.0;
+      int bi = 0;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        double rl = (v[k] <= 0.0 ? 0.0 : 1.0) * v[k];
+        if (k == 0 || rl > best) { best = rl; bestpre = v[k]; bi = k; }
+      }
+      int64_t oi = (((int64_t)n * p.Q + q) * Ho + rp) * Wo + jj;
+      p.y[oi] = best;
+      p.code[oi] = (uint8_t)(bi | (bestpre > 0.0 ? 0x80 : 0));
+    }
+    __syncwarp();
+    buf ^= 1;
+  }
+}
+
+// --------------------------------------------------------------------- dKrn
+constexpr int NP = 4;  // column fragments: up to 31 taps + the ones column
+
+__global__ void __launch_bounds__(NTHR, 1) strip_dk_kernel(const __grid_constant__ StripP p) {
+  extern __shared__ __align__(16) double smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int fr = lane >> 2, fk = lane & 3;
+  int *lut = reinterpret_cast<int *>(smem);                            // [64] position -> strip byte offset
+  double *mine = smem + 32 + warp * p.warp_doubles;
+  double *dbx = mine + 2 * p.SD;                                       // [16][PS]
+  const int Wo = p.W >> 1, Ho = p.H >> 1, W2 = 2 * p.W;
+
+  for (int i = tid; i < 64; i += NTHR) {
+    int pc = i < W2 ? i : 0;
+    int yy = pc / p.W, x = pc - yy * p.W;
+    lut[i] = (yy * p.RS + x) * 8;
+  }
+  for (int i = lane; i < p.warp_doubles; i += 32) mine[i] = 0.0;
+  __syncthreads();
+
+  // column t = 8 j + fr of pair j: tap t (< KK), the ones column (t == KK), or padding
+  int pair_off[NP];
+  bool ones[NP];
+#pragma unroll
+  for (int j = 0; j < NP; j++) {
+    int t = j * 8 + fr;
+    pair_off[j] = t < p.KK ? ((t / p.KW) * p.RS + (t % p.KW)) * 8 : 0;
+    ones[j] = t == p.KK;
+  }
+  double acc[2][NP][2];
+#pragma unroll
+  for (int m = 0; m < 2; m++)
+#pragma unroll
+    for (int j = 0; j < NP; j++) acc[m][j][0] = acc[m][j][1] = 0.0;
+
+  const int64_t gw = (int64_t)blockIdx.x * WPB + warp, nw = (int64_t)gridDim.x * WPB;
+  const int nel = p.Q * Wo;                 // pooled elements of one item (<= 7 per lane)
+  double dyv[7];
+  unsigned cdv[7];
+  auto fetch = [&](int64_t item) {          // pooled cotangent + code of an item -> registers
+    const int n = (int)(item / Ho), rp = (int)(item - (int64_t)n * Ho);
+#pragma unroll
+    for (int k = 0; k < 7; k++) {
+      int e = lane + 32 * k;
+      dyv[k] = 0.0;
+      cdv[k] = 0;
+      if (e < nel) {
+        int q = e / Wo, jj = e - q * Wo;
+        int64_t oi = (((int64_t)n * p.Q + q) * Ho + rp) * Wo + jj;
+        dyv[k] = p.dy[oi];
+        cdv[k] = p.code[oi];
+      }
+    }
+  };
+  int buf = 0;
+  if (gw < p.items) {
+    load_strip(mine, p, (int)gw, lane);
+    fetch(gw);
+  }
+  cp_commit();
+  for (int64_t it = gw; it < p.items; it += nw) {
+    // expand this item's (dy, code) into the cotangent tile dbx[o][position]
+#pragma unroll
+    for (int k = 0; k < 7; k++) {
+      int e = lane + 32 * k;
+      if (e < nel) {
+        int q = e / Wo, jj = e - q * Wo;
+        double gv = (cdv[k] & 0x80u) ? dyv[k] : 0.0;
+        int bi = cdv[k] & 0x7f;
+        double *xp = dbx + q * p.PS + 2 * jj;
+        *reinterpret_cast<double2 *>(xp) = make_double2(bi == 0 ? gv : 0.0, bi == 1 ? gv : 0.0);
+        *reinterpret_cast<double2 *>(xp + p.W) = make_double2(bi == 2 ? gv : 0.0, bi == 3 ? gv : 0.0);
+      }
+    }
+    if (it + nw < p.items) {
+      load_strip(mine + (buf ^ 1) * p.SD, p, (int)(it + nw), lane);
+      cp_commit();
+      fetch(it + nw);                       // in flight during this item's DMMAs
+      cp_wait<1>();
+    } else {
+      cp_wait<0>();
+    }
+    __syncwarp();
+    const char *As = reinterpret_cast<const char *>(mine + buf * p.SD);
+    const double *Bs = dbx + fr * p.PS + fk;
+    for (int k0 = 0; k0 < W2; k0 += 4) {
+      const char *ap = As + lut[k0 + fk];
+      double a0 = Bs[k0], a1 = Bs[8 * p.PS + k0];
+#pragma unroll
+      for (int j = 0; j < NP; j++) {
+        double b = ones[j] ? 1.0 : *reinterpret_cast<const double *>(ap + pair_off[j]);
+        dmma884(acc[0][j][0], acc[0][j][1], a0, b);
+        dmma884(acc[1][j][0], acc[1][j][1], a1, b);
+      }
+    }
+    __syncwarp();
+    buf ^= 1;
+  }
+  // the 16 warps of the CTA are summed in fixed order through shared memory
+  __syncthreads();
+  double *red = smem + 32;                  // [warp][m][j][lane][2]
+#pragma unroll
+  for (int m = 0; m < 2; m++)
+#pragma unroll
+    for (int j = 0; j < NP; j++)
+      *reinterpret_cast<double2 *>(red + (((warp * 2 + m) * NP + j) * 32 + lane) * 2) =
+          make_double2(acc[m][j][0], acc[m][j][1]);
+  __syncthreads();
+  if (warp == 0) {
+    const int rowlen = p.KK + 1;
+    double *part = p.part + (int64_t)blockIdx.x * p.Q * rowlen;
+#pragma unroll
+    for (int m = 0; m < 2; m++)
+#pragma unroll
+      for (int j = 0; j < NP; j++) {
+        double s0 = 0.0, s1 = 0.0;
+        for (int w = 0; w < WPB; w++) {
+          double2 v = *reinterpret_cast<const double2 *>(red + (((w * 2 + m) * NP + j) * 32 + lane) * 2);
+          s0 += v.x;
+          s1 += v.y;
+        }
+        int o = m * 8 + fr, t = j * 8 + fk * 2;   // C fragment: row = o, cols = 2 taps
+        if (o < p.Q) {
+          if (t < rowlen) part[o * rowlen + t] = s0;
+          if (t + 1 < rowlen) part[o * rowlen + t + 1] = s1;
+        }
+      }
+  }
+}
+
+// out: dK[o][t] (t < KK) and dbias[o] from the per-CTA partials, CTAs in order
+__global__ void strip_dk_reduce_kernel(const double *__restrict__ part, int nparts, int Q, int KK,
+                                       double *__restrict__ dK, double *__restrict__ dbias) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int rowlen = KK + 1;
+  if (i >= Q * rowlen) return;
+  double s = 0.0;
+  for (int k = 0; k < nparts; k++) s += part[(int64_t)k * Q * rowlen + i];
+  int o = i / rowlen, t = i - o * rowlen;
+  if (t < KK) dK[o * KK + t] = s;
+  else if (dbias) dbias[o] = s;
+}
+
+// forward weights: Wt[t][q] = K[q, 0, t / KW, t % KW], tap stride TS, zero padded
+__global__ void strip_pack_kernel(const double *__restrict__ K, double *__restrict__ wp, int Q, int KK, int NT, int TS,
+                                  int64_t k_so, int KW, int64_t k_si, int64_t k_sj) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= NT * TS) return;
+  int t = i / TS, q = i - t * TS;
+  wp[i] = (t < KK && q < Q) ? K[q * k_so + (t / KW) * k_si + (t % KW) * k_sj] : 0.0;
+}
+
+static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+static bool strip_applicable(int64_t N, int64_t Ci, int64_t Co, int64_t H, int64_t W, int64_t KH, int64_t KW) {
+  return Ci == 1 && Co >= 1 && Co <= 16 && (H % 2) == 0 && (W % 2) == 0 && 2 * W > 48 && 2 * W <= 56 && KH >= 1 &&
+         KW >= 1 && KH * KW <= 31 && KH <= 8 && KW <= 8 && N * (H / 2) < (1ll << 31) && N * Co * H * W < (1ll << 31);
+}
+
+static void strip_geometry(StripP &p, int N, int Q, int H, int W, int KH, int KW) {
+  memset(&p, 0, sizeof p);
+  p.N = N; p.Q = Q; p.H = H; p.W = W; p.KH = KH; p.KW = KW; p.KK = KH * KW;
+  p.RS = round_up(W + KW - 1, 2);
+  p.TR = 2 + KH - 1;
+  p.SD = round_up(p.TR * p.RS, 2);
+  p.items = N * (H / 2);
+}
+
+}  // namespace
+
+// maxPool 2 2 (relu (conv2dPreserving K A + bias)) for a one-channel A; *done = 1 when it ran.
+int hb_conv_strip_fwd(const hb_array *K, const hb_array *bias, const hb_array *A, hb_array *y, hb_array *code,
+                      int *done) {
+  *done = 0;
+  if (A->dt != HB_F64 || !hb_contig(A) || !hb_contig(y) || !hb_contig(code) || (bias && !hb_contig(bias))) return HB_OK;
+  if (!strip_applicable(A->shape[0], A->shape[1], K->shape[0], A->shape[2], A->shape[3], K->shape[2], K->shape[3]))
+    return HB_OK;
+  if (((uintptr_t)hb_data(A) & 15) != 0) return HB_OK;
+  StripP p;
+  strip_geometry(p, (int)A->shape[0], (int)K->shape[0], (int)A->shape[2], (int)A->shape[3], (int)K->shape[2],
+                 (int)K->shape[3]);
+  const int NQ = p.Q <= 8 ? 1 : 2, QT = NQ * 8;
+  p.NT = round_up(p.KK, 4);
+  p.TS = QT + 4;
+  p.w_doubles = round_up(p.NT * p.TS, 2);
+  p.OPS = round_up(2 * p.W, 4) + 2;
+  p.warp_doubles = round_up(2 * p.SD + QT * p.OPS, 2);
+  p.A = (const double *)hb_data(A);
+  p.bias = bias ? (const double *)hb_data(bias) : nullptr;
+  p.y = (double *)hb_data(y);
+  p.code = (uint8_t *)hb_data(code);
+  void *scr;
+  HB_TRY(hb_scratch((size_t)p.w_doubles * 8, &scr));
+  p.wp = (const double *)scr;
+  strip_pack_kernel<<<(p.NT * p.TS + 255) / 256, 256, 0, g_hb.stream>>>((const double *)hb_data(K), (double *)scr, p.Q,
+                                                                        p.KK, p.NT, p.TS, K->strides[0], p.KW,
+                                                                        K->strides[2], K->strides[3]);
+  HB_LAUNCHED();
+  int smem = (p.w_doubles + ((p.NT + 1) >> 1) + WPB * p.warp_doubles) * 8;
+  if (smem > 227 * 1024) return HB_OK;
+  int64_t wneed = ((int64_t)p.items + WPB - 1) / WPB;
+  int grid = (int)(wneed < g_hb.sm_count ? wneed : g_hb.sm_count);
+  if (NQ == 1) {
+    HB_CUDA(cudaFuncSetAttribute(strip_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    strip_fwd_kernel<1><<<grid, NTHR, smem, g_hb.stream>>>(p);
+  } else {
+    HB_CUDA(cudaFuncSetAttribute(strip_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    strip_fwd_kernel<2><<<grid, NTHR, smem, g_hb.stream>>>(p);
+  }
+  HB_LAUNCHED();
+  *done = 1;
+  return HB_OK;
+}
+
+// dK [Co,1,KH,KW] and (optionally) dbias [Co] from A [N,1,H,W], the pooled cotangent dy and its code bytes.
+int hb_conv_strip_dk(const hb_array *A, const hb_array *dy, const hb_array *code, int KH, int KW, hb_array *dK,
+                     hb_array *dbias, int *done) {
+  *done = 0;
+  if (A->dt != HB_F64 || !hb_contig(A) || !hb_contig(dy) || !hb_contig(code) || !hb_contig(dK) ||
+      (dbias && !hb_contig(dbias)))
+    return HB_OK;
+  if (!strip_applicable(A->shape[0], A->shape[1], dy->shape[1], A->shape[2], A->shape[3], KH, KW)) return HB_OK;
+  if (((uintptr_t)hb_data(A) & 15) != 0) return HB_OK;
+  StripP p;
+  strip_geometry(p, (int)A->shape[0], (int)dy->shape[1], (int)A->shape[2], (int)A->shape[3], KH, KW);
+  p.NT = NP * 8;
+  p.PS = round_up(2 * p.W, 8) + 4;
+  p.warp_doubles = round_up(2 * p.SD + 16 * p.PS, 2);
+  if (p.warp_doubles < 2 * NP * 64) p.warp_doubles = 2 * NP * 64;   // end-of-kernel reduction area
+  p.A = (const double *)hb_data(A);
+  p.dy = (const double *)hb_data(dy);
+  p.code = (uint8_t *)hb_data(code);
+  int smem = (32 + WPB * p.warp_doubles) * 8;
+  if (smem > 227 * 1024) return HB_OK;
+  int64_t wneed = ((int64_t)p.items + WPB - 1) / WPB;
+  int grid = (int)(wneed < g_hb.sm_count ? wneed : g_hb.sm_count);
+  const int rowlen = p.KK + 1;
+  void *scr;
+  HB_TRY(hb_scratch((size_t)grid * p.Q * rowlen * 8, &scr));
+  p.part = (double *)scr;
+  HB_CUDA(cudaFuncSetAttribute(strip_dk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  strip_dk_kernel<<<grid, NTHR, smem, g_hb.stream>>>(p);
+  HB_LAUNCHED();
+  strip_dk_reduce_kernel<<<(p.Q * rowlen + 127) / 128, 128, 0, g_hb.stream>>>(
+      p.part, grid, p.Q, p.KK, (double *)hb_data(dK), dbias ? (double *)hb_data(dbias) : nullptr);
+  HB_LAUNCHED();
+  *done = 1;
+  return HB_OK;
+}

@@ -471,7 +471,10 @@ def test_fused_relu_pool(dev, oracle, dtype, shape, ks):
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 @pytest.mark.parametrize("shape,ks", [((37, 1, 16, 28, 28, 5, 5), 2), ((9, 16, 16, 14, 14, 5, 5), 2), ((3, 3, 40, 12, 20, 3, 3), 2),
                                       ((2, 5, 7, 9, 11, 2, 3), 2), ((2, 4, 4, 12, 12, 3, 3), 3), ((5, 8, 64, 28, 28, 3, 3), 2),
-                                      ((4, 2, 9, 30, 6, 3, 2), 2)])
+                                      ((4, 2, 9, 30, 6, 3, 2), 2),
+                                      # warp-autonomous one-channel kernels (conv_strip.cu): widths 26 / 28, odd item counts
+                                      ((5, 1, 9, 28, 26, 3, 4), 2), ((6, 1, 8, 4, 28, 2, 2), 2), ((131, 1, 16, 28, 28, 5, 5), 2),
+                                      ((3, 1, 5, 6, 28, 1, 1), 2)])
 def test_fused_conv_layer(dev, oracle, dtype, shape, ks):
     """hb_conv_relu_pool_fwd/bwd (a whole convMnistLayerS as one node): the fused
     DMMA epilogue / pooled-cotangent dKrn path and its unfused fallbacks agree
