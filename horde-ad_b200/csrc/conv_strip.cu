@@ -27,6 +27,10 @@ namespace {
 constexpr int WPB = 16;            // warps per block
 constexpr int NTHR = WPB * 32;
 constexpr int MF = 7;              // position fragments of a row pair (2 * W <= 56)
+// fixed shared-memory strides (W <= 28, KW <= 8), so that fragment addresses fold into immediates
+constexpr int kRS = 36;            // strip row stride  (>= W + KW - 1, even)
+constexpr int kOPS = 58;           // forward pooled-tile position stride (>= 56, = 2 mod 4)
+constexpr int kPS = 60;            // dKrn cotangent-tile position stride (>= 56, = 4 mod 8)
 
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -61,16 +65,15 @@ struct StripP {
 };
 
 // rows [2 rp, 2 rp + TR) of image n -> strip (rows beyond the image zero; the halo columns stay zero)
-__device__ __forceinline__ void load_strip(double *dst, const StripP &p, int item, int lane) {
-  const int Ho = p.H >> 1;
-  const int n = item / Ho, rp = item - n * Ho;
+__device__ __forceinline__ void load_strip(double *dst, const StripP &p, int n, int rp, int lane) {
   const double *src = p.A + (int64_t)n * p.H * p.W + (int64_t)(2 * rp) * p.W;
-  const int cpr = p.W >> 1, total = p.TR * cpr;
-  for (int i = lane; i < total; i += 32) {
-    int t = i / cpr, ch = i - t * cpr;
-    double *d = dst + t * p.RS + 2 * ch;
-    if (2 * rp + t < p.H) cp16(d, src + t * p.W + 2 * ch);
-    else *reinterpret_cast<double2 *>(d) = make_double2(0.0, 0.0);
+  const int cpr = p.W >> 1;
+  if (lane < cpr) {
+    for (int t = 0; t < p.TR; t++) {
+      double *d = dst + t * kRS + 2 * lane;
+      if (2 * rp + t < p.H) cp16(d, src + t * p.W + 2 * lane);
+      else *reinterpret_cast<double2 *>(d) = make_double2(0.0, 0.0);
+    }
   }
 }
 
@@ -83,10 +86,10 @@ __global__ void __launch_bounds__(NTHR, 1) strip_fwd_kernel(const __grid_constan
   double *Wsm = smem;
   int *tapoff = reinterpret_cast<int *>(smem + p.w_doubles);          // [NT] byte offsets into a strip
   double *mine = smem + p.w_doubles + ((p.NT + 1) >> 1) + warp * p.warp_doubles;
-  double *ot = mine + 2 * p.SD;                                        // [QT][OPS]
+  double *ot = mine + 2 * p.SD;                                        // [QT][kOPS]
 
   for (int i = tid; i < p.w_doubles; i += NTHR) Wsm[i] = p.wp[i];
-  for (int i = tid; i < p.NT; i += NTHR) tapoff[i] = i < p.KK ? ((i / p.KW) * p.RS + (i % p.KW)) * 8 : 0;
+  for (int i = tid; i < p.NT; i += NTHR) tapoff[i] = i < p.KK ? ((i / p.KW) * kRS + (i % p.KW)) * 8 : 0;
   for (int i = lane; i < p.warp_doubles; i += 32) mine[i] = 0.0;
   __syncthreads();
 
@@ -97,7 +100,7 @@ __global__ void __launch_bounds__(NTHR, 1) strip_fwd_kernel(const __grid_constan
     int pos = i * 8 + fr;
     int pc = pos < W2 ? pos : 0;
     int yy = pc / p.W, x = pc - yy * p.W;
-    aoff[i] = (yy * p.RS + x) * 8;
+    aoff[i] = (yy * kRS + x) * 8;
   }
   double bv[NQ][2];
 #pragma unroll
@@ -107,14 +110,24 @@ __global__ void __launch_bounds__(NTHR, 1) strip_fwd_kernel(const __grid_constan
       int q = j * 8 + fk * 2 + e;
       bv[j][e] = (p.bias && q < p.Q) ? p.bias[q] : 0.0;
     }
+  constexpr int TS = NQ * 8 + 4;
   const int64_t gw = (int64_t)blockIdx.x * WPB + warp, nw = (int64_t)gridDim.x * WPB;
   const int ng = p.NT >> 2;
+  const int HoWo = Ho * Wo, nout = p.Q * Wo;
+  const int q_lane = lane / Wo, j_lane = lane - q_lane * Wo;   // pooled output `lane` of an item
+  const int dq = 32 / Wo, dj = 32 - dq * Wo;                   // ... and the step to output lane + 32
+  double *const ot_w = ot + (fk * 2) * kOPS + fr;              // this lane's slot of fragment 0, channel pair 0
+  // item -> (image, row pair), advanced incrementally
+  int n = (int)(gw / Ho), rp = (int)(gw - (int64_t)n * Ho);
+  const int dn = (int)(nw / Ho), drp = (int)(nw - (int64_t)dn * Ho);
   int buf = 0;
-  if (gw < p.items) load_strip(mine, p, (int)gw, lane);
+  if (gw < p.items) load_strip(mine, p, n, rp, lane);
   cp_commit();
   for (int64_t it = gw; it < p.items; it += nw) {
+    int n2 = n + dn, rp2 = rp + drp;
+    if (rp2 >= Ho) { rp2 -= Ho; n2++; }
     if (it + nw < p.items) {
-      load_strip(mine + (buf ^ 1) * p.SD, p, (int)(it + nw), lane);
+      load_strip(mine + (buf ^ 1) * p.SD, p, n2, rp2, lane);
       cp_commit();
       cp_wait<1>();
     } else {
@@ -127,16 +140,29 @@ __global__ void __launch_bounds__(NTHR, 1) strip_fwd_kernel(const __grid_constan
     for (int i = 0; i < MF; i++)
 #pragma unroll
       for (int j = 0; j < NQ; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
-    for (int g = 0; g < ng; g++) {
-      const int t = g * 4 + fk;
-      const int to = tapoff[t];
-      const bool tv = t < p.KK;   // padded taps contribute exact zeros
+    const double *wl = Wsm + fk * TS + fr;
+    for (int g = 0; g < ng - 1; g++) {       // full tap groups: no padding possible
+      const char *sa = Sb + tapoff[g * 4 + fk];
       double b[NQ];
 #pragma unroll
-      for (int j = 0; j < NQ; j++) b[j] = Wsm[t * p.TS + j * 8 + fr];
+      for (int j = 0; j < NQ; j++) b[j] = wl[g * 4 * TS + j * 8];
 #pragma unroll
       for (int i = 0; i < MF; i++) {
-        double a = *reinterpret_cast<const double *>(Sb + aoff[i] + to);
+        double a = *reinterpret_cast<const double *>(sa + aoff[i]);
+#pragma unroll
+        for (int j = 0; j < NQ; j++) dmma884(acc[i][j][0], acc[i][j][1], a, b[j]);
+      }
+    }
+    {                                         // last group: padded taps contribute exact zeros
+      const int g = ng - 1, t = g * 4 + fk;
+      const char *sa = Sb + tapoff[t];
+      const bool tv = t < p.KK;
+      double b[NQ];
+#pragma unroll
+      for (int j = 0; j < NQ; j++) b[j] = wl[g * 4 * TS + j * 8];
+#pragma unroll
+      for (int i = 0; i < MF; i++) {
+        double a = *reinterpret_cast<const double *>(sa + aoff[i]);
         a = tv ? a : 0.0;
 #pragma unroll
         for (int j = 0; j < NQ; j++) dmma884(acc[i][j][0], acc[i][j][1], a, b[j]);
@@ -145,35 +171,41 @@ __global__ void __launch_bounds__(NTHR, 1) strip_fwd_kernel(const __grid_constan
     // bias, then the row pair's pre-activations into the warp's [channel][position] tile
 #pragma unroll
     for (int i = 0; i < MF; i++) {
-      int pos = i * 8 + fr;
-      if (pos < W2) {
+      if (i * 8 + fr < W2) {
 #pragma unroll
         for (int j = 0; j < NQ; j++)
 #pragma unroll
-          for (int e = 0; e < 2; e++) ot[(j * 8 + fk * 2 + e) * p.OPS + pos] = acc[i][j][e] + bv[j][e];
+          for (int e = 0; e < 2; e++) ot_w[(j * 8 + e) * kOPS + i * 8] = acc[i][j][e] + bv[j][e];
       }
     }
     __syncwarp();
-    const int n = (int)(it / Ho), rp = (int)(it - (int64_t)n * Ho);
-    const int nout = p.Q * Wo;
-    for (int o = lane; o < nout; o += 32) {
-      int q = o / Wo, jj = o - q * Wo;
-      const double *oq = ot + q * p.OPS + 2 * jj;
-      double2 r0 = *reinterpret_cast<const double2 *>(oq), r1 = *reinterpret_cast<const double2 *>(oq + p.W);
-      double v[4] = {r0.x, r0.y, r1.x, r1.y};
-      double best = 0.0, bestpre = 0.0;
-      int bi = 0;
+    {
+      int q = q_lane, jj = j_lane;
+      double *yb = p.y + ((int64_t)n * p.Q * Ho + rp) * Wo;
+      uint8_t *cb = p.code + ((int64_t)n * p.Q * Ho + rp) * Wo;
+      for (int o = lane; o < nout; o += 32) {
+        const double *oq = ot + q * kOPS + 2 * jj;
+        double2 r0 = *reinterpret_cast<const double2 *>(oq), r1 = *reinterpret_cast<const double2 *>(oq + p.W);
+        double v[4] = {r0.x, r0.y, r1.x, r1.y};
+        double best = 0.0, bestpre = 0.0;
+        int bi = 0;
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
-        double rl = (v[k] <= 0.0 ? 0.0 : 1.0) * v[k];
-        if (k == 0 || rl > best) { best = rl; bestpre = v[k]; bi = k; }
+        for (int k = 0; k < 4; k++) {
+          double rl = (v[k] <= 0.0 ? 0.0 : 1.0) * v[k];
+          if (k == 0 || rl > best) { best = rl; bestpre = v[k]; bi = k; }
+        }
+        int oi = q * HoWo + jj;
+        yb[oi] = best;
+        cb[oi] = (uint8_t)(bi | (bestpre > 0.0 ? 0x80 : 0));
+        q += dq;
+        jj += dj;
+        if (jj >= Wo) { jj -= Wo; q++; }
       }
-      int64_t oi = (((int64_t)n * p.Q + q) * Ho + rp) * Wo + jj;
-      p.y[oi] = best;
-      p.code[oi] = (uint8_t)(bi | (bestpre > 0.0 ? 0x80 : 0));
     }
     __syncwarp();
     buf ^= 1;
+    n = n2;
+    rp = rp2;
   }
 }
 
@@ -186,13 +218,13 @@ __global__ void __launch_bounds__(NTHR, 1) strip_dk_kernel(const __grid_constant
   const int fr = lane >> 2, fk = lane & 3;
   int *lut = reinterpret_cast<int *>(smem);                            // [64] position -> strip byte offset
   double *mine = smem + 32 + warp * p.warp_doubles;
-  double *dbx = mine + 2 * p.SD;                                       // [16][PS]
+  double *dbx = mine + 2 * p.SD;                                       // [16][kPS]
   const int Wo = p.W >> 1, Ho = p.H >> 1, W2 = 2 * p.W;
 
   for (int i = tid; i < 64; i += NTHR) {
     int pc = i < W2 ? i : 0;
     int yy = pc / p.W, x = pc - yy * p.W;
-    lut[i] = (yy * p.RS + x) * 8;
+    lut[i] = (yy * kRS + x) * 8;
   }
   for (int i = lane; i < p.warp_doubles; i += 32) mine[i] = 0.0;
   __syncthreads();
@@ -203,7 +235,7 @@ __global__ void __launch_bounds__(NTHR, 1) strip_dk_kernel(const __grid_constant
 #pragma unroll
   for (int j = 0; j < NP; j++) {
     int t = j * 8 + fr;
-    pair_off[j] = t < p.KK ? ((t / p.KW) * p.RS + (t % p.KW)) * 8 : 0;
+    pair_off[j] = t < p.KK ? ((t / p.KW) * kRS + (t % p.KW)) * 8 : 0;
     ones[j] = t == p.KK;
   }
   double acc[2][NP][2];
@@ -214,57 +246,67 @@ __global__ void __launch_bounds__(NTHR, 1) strip_dk_kernel(const __grid_constant
 
   const int64_t gw = (int64_t)blockIdx.x * WPB + warp, nw = (int64_t)gridDim.x * WPB;
   const int nel = p.Q * Wo;                 // pooled elements of one item (<= 7 per lane)
+  const int HoWo = Ho * Wo;
+  // pooled element e = lane + 32 k of an item: (channel, window) and its offsets, fixed for the kernel
+  int eoff[7], xoff[7];
+#pragma unroll
+  for (int k = 0; k < 7; k++) {
+    int e = lane + 32 * k;
+    int q = e / Wo, jj = e - q * Wo;
+    eoff[k] = e < nel ? q * HoWo + jj : -1;          // offset inside the image's pooled block
+    xoff[k] = q * kPS + 2 * jj;                      // first position of the window in the cotangent tile
+  }
   double dyv[7];
   unsigned cdv[7];
-  auto fetch = [&](int64_t item) {          // pooled cotangent + code of an item -> registers
-    const int n = (int)(item / Ho), rp = (int)(item - (int64_t)n * Ho);
+  auto fetch = [&](int n, int rp) {         // pooled cotangent + code of an item -> registers
+    const double *yb = p.dy + ((int64_t)n * p.Q * Ho + rp) * Wo;
+    const uint8_t *cb = p.code + ((int64_t)n * p.Q * Ho + rp) * Wo;
 #pragma unroll
     for (int k = 0; k < 7; k++) {
-      int e = lane + 32 * k;
       dyv[k] = 0.0;
       cdv[k] = 0;
-      if (e < nel) {
-        int q = e / Wo, jj = e - q * Wo;
-        int64_t oi = (((int64_t)n * p.Q + q) * Ho + rp) * Wo + jj;
-        dyv[k] = p.dy[oi];
-        cdv[k] = p.code[oi];
+      if (eoff[k] >= 0) {
+        dyv[k] = yb[eoff[k]];
+        cdv[k] = cb[eoff[k]];
       }
     }
   };
+  int n = (int)(gw / Ho), rp = (int)(gw - (int64_t)n * Ho);
+  const int dn = (int)(nw / Ho), drp = (int)(nw - (int64_t)dn * Ho);
   int buf = 0;
   if (gw < p.items) {
-    load_strip(mine, p, (int)gw, lane);
-    fetch(gw);
+    load_strip(mine, p, n, rp, lane);
+    fetch(n, rp);
   }
   cp_commit();
   for (int64_t it = gw; it < p.items; it += nw) {
     // expand this item's (dy, code) into the cotangent tile dbx[o][position]
 #pragma unroll
     for (int k = 0; k < 7; k++) {
-      int e = lane + 32 * k;
-      if (e < nel) {
-        int q = e / Wo, jj = e - q * Wo;
+      if (eoff[k] >= 0) {
         double gv = (cdv[k] & 0x80u) ? dyv[k] : 0.0;
         int bi = cdv[k] & 0x7f;
-        double *xp = dbx + q * p.PS + 2 * jj;
+        double *xp = dbx + xoff[k];
         *reinterpret_cast<double2 *>(xp) = make_double2(bi == 0 ? gv : 0.0, bi == 1 ? gv : 0.0);
         *reinterpret_cast<double2 *>(xp + p.W) = make_double2(bi == 2 ? gv : 0.0, bi == 3 ? gv : 0.0);
       }
     }
+    int n2 = n + dn, rp2 = rp + drp;
+    if (rp2 >= Ho) { rp2 -= Ho; n2++; }
     if (it + nw < p.items) {
-      load_strip(mine + (buf ^ 1) * p.SD, p, (int)(it + nw), lane);
+      load_strip(mine + (buf ^ 1) * p.SD, p, n2, rp2, lane);
       cp_commit();
-      fetch(it + nw);                       // in flight during this item's DMMAs
+      fetch(n2, rp2);                       // in flight during this item's DMMAs
       cp_wait<1>();
     } else {
       cp_wait<0>();
     }
     __syncwarp();
     const char *As = reinterpret_cast<const char *>(mine + buf * p.SD);
-    const double *Bs = dbx + fr * p.PS + fk;
+    const double *Bs = dbx + fr * kPS + fk;
     for (int k0 = 0; k0 < W2; k0 += 4) {
       const char *ap = As + lut[k0 + fk];
-      double a0 = Bs[k0], a1 = Bs[8 * p.PS + k0];
+      double a0 = Bs[k0], a1 = Bs[8 * kPS + k0];
 #pragma unroll
       for (int j = 0; j < NP; j++) {
         double b = ones[j] ? 1.0 : *reinterpret_cast<const double *>(ap + pair_off[j]);
@@ -274,6 +316,8 @@ __global__ void __launch_bounds__(NTHR, 1) strip_dk_kernel(const __grid_constant
     }
     __syncwarp();
     buf ^= 1;
+    n = n2;
+    rp = rp2;
   }
   // the 16 warps of the CTA are summed in fixed order through shared memory
   __syncthreads();
@@ -307,17 +351,22 @@ __global__ void __launch_bounds__(NTHR, 1) strip_dk_kernel(const __grid_constant
   }
 }
 
-// out: dK[o][t] (t < KK) and dbias[o] from the per-CTA partials, CTAs in order
-__global__ void strip_dk_reduce_kernel(const double *__restrict__ part, int nparts, int Q, int KK,
-                                       double *__restrict__ dK, double *__restrict__ dbias) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  int rowlen = KK + 1;
+// out: dK[o][t] (t < KK) and dbias[o] from the per-CTA partials: one warp per
+// output element, lanes take the partials round-robin (each in ascending CTA
+// order), then a fixed xor-shuffle tree -> deterministic
+__global__ void __launch_bounds__(128) strip_dk_reduce_kernel(const double *__restrict__ part, int nparts, int Q, int KK,
+                                                              double *__restrict__ dK, double *__restrict__ dbias) {
+  const int rowlen = KK + 1, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (i >= Q * rowlen) return;
   double s = 0.0;
-  for (int k = 0; k < nparts; k++) s += part[(int64_t)k * Q * rowlen + i];
-  int o = i / rowlen, t = i - o * rowlen;
-  if (t < KK) dK[o * KK + t] = s;
-  else if (dbias) dbias[o] = s;
+  for (int k = lane; k < nparts; k += 32) s += part[(int64_t)k * Q * rowlen + i];
+  s = hb_warp_sum(s);
+  if (lane == 0) {
+    int o = i / rowlen, t = i - o * rowlen;
+    if (t < KK) dK[o * KK + t] = s;
+    else if (dbias) dbias[o] = s;
+  }
 }
 
 // forward weights: Wt[t][q] = K[q, 0, t / KW, t % KW], tap stride TS, zero padded
@@ -339,9 +388,9 @@ static bool strip_applicable(int64_t N, int64_t Ci, int64_t Co, int64_t H, int64
 static void strip_geometry(StripP &p, int N, int Q, int H, int W, int KH, int KW) {
   memset(&p, 0, sizeof p);
   p.N = N; p.Q = Q; p.H = H; p.W = W; p.KH = KH; p.KW = KW; p.KK = KH * KW;
-  p.RS = round_up(W + KW - 1, 2);
+  p.RS = kRS;
   p.TR = 2 + KH - 1;
-  p.SD = round_up(p.TR * p.RS, 2);
+  p.SD = p.TR * kRS;
   p.items = N * (H / 2);
 }
 
@@ -362,8 +411,8 @@ int hb_conv_strip_fwd(const hb_array *K, const hb_array *bias, const hb_array *A
   p.NT = round_up(p.KK, 4);
   p.TS = QT + 4;
   p.w_doubles = round_up(p.NT * p.TS, 2);
-  p.OPS = round_up(2 * p.W, 4) + 2;
-  p.warp_doubles = round_up(2 * p.SD + QT * p.OPS, 2);
+  p.OPS = kOPS;
+  p.warp_doubles = round_up(2 * p.SD + QT * kOPS, 2);
   p.A = (const double *)hb_data(A);
   p.bias = bias ? (const double *)hb_data(bias) : nullptr;
   p.y = (double *)hb_data(y);
@@ -403,8 +452,8 @@ int hb_conv_strip_dk(const hb_array *A, const hb_array *dy, const hb_array *code
   StripP p;
   strip_geometry(p, (int)A->shape[0], (int)dy->shape[1], (int)A->shape[2], (int)A->shape[3], KH, KW);
   p.NT = NP * 8;
-  p.PS = round_up(2 * p.W, 8) + 4;
-  p.warp_doubles = round_up(2 * p.SD + 16 * p.PS, 2);
+  p.PS = kPS;
+  p.warp_doubles = round_up(2 * p.SD + 16 * kPS, 2);
   if (p.warp_doubles < 2 * NP * 64) p.warp_doubles = 2 * NP * 64;   // end-of-kernel reduction area
   p.A = (const double *)hb_data(A);
   p.dy = (const double *)hb_data(dy);
@@ -420,7 +469,7 @@ int hb_conv_strip_dk(const hb_array *A, const hb_array *dy, const hb_array *code
   HB_CUDA(cudaFuncSetAttribute(strip_dk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   strip_dk_kernel<<<grid, NTHR, smem, g_hb.stream>>>(p);
   HB_LAUNCHED();
-  strip_dk_reduce_kernel<<<(p.Q * rowlen + 127) / 128, 128, 0, g_hb.stream>>>(
+  strip_dk_reduce_kernel<<<(p.Q * rowlen + 3) / 4, 128, 0, g_hb.stream>>>(
       p.part, grid, p.Q, p.KK, (double *)hb_data(dK), dbias ? (double *)hb_data(dbias) : nullptr);
   HB_LAUNCHED();
   *done = 1;
