@@ -190,6 +190,36 @@ def main():
                                        "unit": "GB/s", "frac": by / (graph_ms * 1e-3) / 1e9 / hbm, "peak_source": src,
                                        "note": "batch 1: launch-latency bound by construction"}}), flush=True)
 
+    # ---------------------------------- secondary CNN config
+    # (kh,kw,c_out,n_hidden) = (2,2,64,128): 3x3 kernels, 64 channels (aligned with ConvVjpBench)
+    from horde_ad_b200.train import CnnTrainer
+    B2 = 512 if args.quick else 4096
+    tr = CnnTrainer(dev, B2, kh=2, kw=2, c_out=64, n_hidden=128)
+    gl = np.ascontiguousarray(rng.uniform(0, 1, (B2, 28, 28)))
+    lb = np.ascontiguousarray(np.eye(10)[rng.integers(0, 10, B2)])
+    tr.upload(gl.ctypes.data_as(C.c_void_p), lb.ctypes.data_as(C.c_void_p))
+    for _ in range(3):
+        tr.step_enqueue()
+    tr.reset()
+    cnt = [0]
+
+    def cnn2_step():
+        cnt[0] += 1
+        if cnt[0] % 8 == 0:
+            tr.reset()               # the reference objective diverges on random labels
+        tr.step_enqueue()
+    ms = timed(dev, cnn2_step, 10)
+    # conv flops (in-bounds taps ~ nominal): layer 1 1->64 at 28x28, layer 2 64->64 at 14x14, 3x3; fwd + dK (+ dInp for layer 2)
+    fl = 2.0 * B2 * 9 * (2 * 64 * 784 + 3 * 64 * 64 * 196) + 3 * 2.0 * B2 * (128 * 64 * 49 + 10 * 128)
+    tf = fl / (ms * 1e-3) / 1e12
+    print(json.dumps({"config": "MnistCnnShaped2 secondary", "hyper": {"kh": 2, "kw": 2, "c_out": 64, "n_hidden": 128},
+                      "per_gpu_batch": B2, "parameters": tr.n_params, "ms_per_step": ms, "samples_per_s": B2 / (ms * 1e-3),
+                      "roofline": {"bound": "tensor", "achieved": tf, "peak": fp64.value, "unit": "TFLOP/s",
+                                   "frac": tf / fp64.value, "peak_source": "hb_microbench FP64 DMMA, this run",
+                                   "algorithmic_flops": fl}}), flush=True)
+    tr.close()
+    del tr
+
     # -------------------------------------------------------------------- GEMM
     m, k, n = 512, 512, (2048 if args.quick else 8192)
     a, b = dev.sconcrete(rng.uniform(-.5, .5, (m, k))), dev.sconcrete(rng.uniform(-.5, .5, (k, n)))

@@ -165,6 +165,10 @@ extern "C" int hb_init(int device) {
   cudaDeviceProp prop;
   HB_CUDA(cudaGetDeviceProperties(&prop, device));
   g_hb.sm_count = prop.multiProcessorCount;
+  {
+    const char *e = getenv("HB_CONV_FULL_PADDING");
+    g_hb.conv_skip_padding = !(e && e[0] && e[0] != '0');
+  }
   HB_CUDA(cudaStreamCreateWithFlags(&g_hb.stream, cudaStreamNonBlocking));
   for (int i = 0; i < 64; i++) HB_CUDA(cudaEventCreate(&g_hb.events[i]));
   g_hb.device = device;

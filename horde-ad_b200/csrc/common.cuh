@@ -49,6 +49,9 @@ struct hb_global {
   size_t scratch_bytes = 0;
   bool capturing = false;
   bool profiling = false;  // hb_prof_begin .. hb_prof_end: one event per launch
+  // DMMA convolutions leave out the taps that fall entirely into the zero padding
+  // (HB_CONV_FULL_PADDING=1 computes them: only differs for non-finite operands, 0 * Inf)
+  bool conv_skip_padding = true;
   cudaEvent_t events[64] = {};
 };
 extern hb_global g_hb;

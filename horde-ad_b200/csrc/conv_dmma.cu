@@ -27,6 +27,7 @@
 // fragment load of a half-warp hits 16 distinct bank pairs.  CTAs are
 // persistent (grid = #SMs), two cp.async stages, one CTA per SM (up to 227 KB).
 #include "common.cuh"
+#include <algorithm>
 
 namespace {
 
@@ -59,42 +60,75 @@ struct TileGeo {
   int TR, RS, IS, CS;
   int oy, ox;  // tile row t holds input row y0+oy+t; input col x sits at tile col x-ox
   int bands;   // ceil(H / R)
+  int nblocks; // ceil(N / NI); item it = band * nblocks + image block (band-major: every CTA sees all bands)
   int vec;     // rows may be moved in 16-byte pieces
   int cpr, cshift;  // pieces per row and log2 of its power-of-two padding
+  int dc8, di8;     // 8 / NI and 8 % NI: plane step of a warp (8 warps) in (channel, image)
 };
 
+__device__ __forceinline__ void cp16s(unsigned s, const void *g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp8s(unsigned s, const void *g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(g) : "memory");
+}
+__device__ __forceinline__ void sts_zero16(unsigned s) {
+  asm volatile("st.shared.v2.f64 [%0], {%1, %1};\n" ::"r"(s), "d"(0.0) : "memory");
+}
+__device__ __forceinline__ void sts_zero8(unsigned s) {
+  asm volatile("st.shared.f64 [%0], %1;\n" ::"r"(s), "d"(0.0) : "memory");
+}
+
 // channels [c0, c0+CC) of images [n0, n0+NI), input rows of band y0 -> dst.
-// A warp owns whole (channel, image) planes; its lanes cover (row, piece) with
-// the pieces per row padded to a power of two, so the hot loop has no integer
-// division (one per plane).
+// A warp owns whole (channel, image) planes.  A lane keeps one piece column
+// (pieces per row padded to a power of two) and walks down the rows, so the
+// hot loop is two range compares, one cp.async (or zero store) and three adds:
+// ncu showed the former per-slot index arithmetic costing as many issue slots
+// per item as a third of the DMMA loop.
+template <bool VEC>
+__device__ __forceinline__ void load_in_tile_t(double *dst, const double *__restrict__ in, const TileGeo &g, int CC,
+                                               int c0, int P, int n0, int N, int y0, int64_t sn, int64_t sp,
+                                               int tid) {
+  constexpr int PB = VEC ? 16 : 8, PD = VEC ? 2 : 1;  // bytes / doubles per piece
+  const int warp = tid >> 5, lane = tid & 31;
+  const int planes = CC * g.NI;
+  // rows: lane (tr0, ch) with tstep rows per pass; rows wider than 32 pieces: a lane strides along the row
+  const bool wide = g.cshift > 5;
+  const int ch0 = wide ? lane : (lane & ((1 << g.cshift) - 1));
+  const int tr0 = wide ? 0 : (lane >> g.cshift), tstep = wide ? 1 : (32 >> g.cshift);
+  const unsigned sbase = smem_u32(dst);
+  const int ybase = y0 + g.oy;
+  int c = warp / g.NI, img = warp - c * g.NI;
+  for (int pl = warp; pl < planes; pl += kThreads / 32) {
+    const bool okp = c0 + c < P && n0 + img < N;
+    const unsigned d0 = sbase + (unsigned)((c * g.CS + img * g.IS - g.ox + tr0 * g.RS + PD * ch0) * 8);
+    const double *s0 = in + (n0 + img) * sn + (c0 + c) * sp + (int64_t)(ybase + tr0) * g.W + PD * ch0;
+    for (int cc = ch0; cc < g.cpr; cc += 32) {
+      unsigned d = d0 + (unsigned)((cc - ch0) * PB);
+      const double *sp_ = s0 + (cc - ch0) * PD;
+      for (int t = tr0; t < g.TR; t += tstep) {
+        const bool ok = okp && (unsigned)(ybase + t) < (unsigned)g.H;
+        if (VEC) {
+          if (ok) cp16s(d, sp_);
+          else sts_zero16(d);
+        } else {
+          if (ok) cp8s(d, sp_);
+          else sts_zero8(d);
+        }
+        d += (unsigned)(tstep * g.RS * 8);
+        sp_ += tstep * g.W;
+      }
+    }
+    img += g.di8;
+    c += g.dc8;
+    if (img >= g.NI) { img -= g.NI; c++; }
+  }
+}
 __device__ __forceinline__ void load_in_tile(double *dst, const double *__restrict__ in, const TileGeo &g, int CC,
                                              int c0, int P, int n0, int N, int y0, int64_t sn, int64_t sp,
                                              int tid) {
-  const int warp = tid >> 5, lane = tid & 31;
-  const int planes = CC * g.NI;
-  const int slots = g.TR << g.cshift, cmask = (1 << g.cshift) - 1;
-  for (int pl = warp; pl < planes; pl += kThreads / 32) {
-    int c = pl / g.NI, img = pl - c * g.NI;
-    int n = n0 + img, cg = c0 + c;
-    bool okp = cg < P && n < N;
-    double *d0 = dst + c * g.CS + img * g.IS - g.ox;
-    const double *s0 = in + n * sn + cg * sp + (int64_t)(y0 + g.oy) * g.W;
-    for (int sl = lane; sl < slots; sl += 32) {
-      int t = sl >> g.cshift, ch = sl & cmask;
-      if (ch >= g.cpr) continue;
-      int y = y0 + g.oy + t;
-      bool ok = okp && y >= 0 && y < g.H;
-      if (g.vec) {
-        double *d = d0 + t * g.RS + 2 * ch;
-        if (ok) cp16(d, s0 + t * g.W + 2 * ch);
-        else *reinterpret_cast<double2 *>(d) = make_double2(0.0, 0.0);
-      } else {
-        double *d = d0 + t * g.RS + ch;
-        if (ok) cp8(d, s0 + t * g.W + ch);
-        else *d = 0.0;
-      }
-    }
-  }
+  if (g.vec) load_in_tile_t<true>(dst, in, g, CC, c0, P, n0, N, y0, sn, sp, tid);
+  else load_in_tile_t<false>(dst, in, g, CC, c0, P, n0, N, y0, sn, sp, tid);
 }
 
 // contiguous n doubles (n even, both 16-byte aligned)
@@ -113,6 +147,8 @@ struct SpP {
   int Ppad;          // NCH * CC
   int items;         // ceil(N / NI) * bands
   int in_doubles, stage_doubles;
+  int wfix;          // one channel chunk: the packed weights are staged once per CTA at smem + wfix (doubles), not per stage
+  int tail;          // doubles used by the stages (and the fixed weights)
   int64_t sn, sp;
   int KWP;           // KW rounded up to 4 (TAPK)
   // fused tail of convMnistLayerS: out is never written; instead
@@ -122,6 +158,12 @@ struct SpP {
   double *pool_out;
   uint8_t *code_out;
   int qg, OPS;       // channels per pooling round, position stride of the output tile
+  // Zero-padding taps are not computed: slot s = i * WM + wm of the warp grid holds
+  // fragment perm[s]; fragments are dealt so that within a warp the ones whose
+  // rows reach furthest into the padding come last, and for tap row kh only the
+  // first nk[band & 3][wm][kh] fragments of warp-row wm have any in-image input row.
+  unsigned char perm[64];
+  unsigned char nk[4][8][16];
 };
 
 // Packs K into Wt[qt][p][tap][q] (tap stride TS, channel stride WCS), zero
@@ -148,55 +190,77 @@ __global__ void pack_sp_weights(const double *__restrict__ K, double *__restrict
   }
 }
 
-// One stage of the spatial kernel for a warp that owns exactly NF fragments.
-template <int NF, int MF, int NQ, bool TAPK>
-__device__ __forceinline__ void sp_stage(double (&acc)[MF][NQ][2], const int (&aoff)[MF], const char *Sb,
-                                         const char *Wb, const SpP &p) {
+// One stage of the tap-k spatial kernel (k = 4 kw taps of one channel) for a
+// warp that owns exactly NF fragments.
+template <int NF, int MF, int NQ>
+__device__ __forceinline__ void sp_stage_tap(double (&acc)[MF][NQ][2], const int (&aoff)[MF], const char *Sb,
+                                             const char *Wb, const SpP &p) {
   const TileGeo &g = p.g;
-  if (TAPK) {
-    const int ng = p.KWP >> 2;
-    for (int c = 0; c < p.CC; c++) {
-      for (int kh = 0; kh < g.KH; kh++) {
-        const char *ia = Sb + (c * g.CS + kh * g.RS) * 8;
-        const char *wb = Wb + (c * p.WCS + kh * p.KWP * p.TS) * 8;
-        for (int g4 = 0; g4 < ng; g4++) {
-          // taps beyond KW exist only as padding of the k dimension: they contribute an
-          // exact zero whatever the data holds there (0 * Inf would be NaN)
-          const bool tapv = g4 * 4 + (int)(threadIdx.x & 3) < g.KW;
-          double b[NQ];
+  const int ng = p.KWP >> 2;
+  for (int c = 0; c < p.CC; c++) {
+    for (int kh = 0; kh < g.KH; kh++) {
+      const char *ia = Sb + (c * g.CS + kh * g.RS) * 8;
+      const char *wb = Wb + (c * p.WCS + kh * p.KWP * p.TS) * 8;
+      for (int g4 = 0; g4 < ng; g4++) {
+        // taps beyond KW exist only as padding of the k dimension: they contribute an
+        // exact zero whatever the data holds there (0 * Inf would be NaN)
+        const bool tapv = g4 * 4 + (int)(threadIdx.x & 3) < g.KW;
+        double b[NQ];
 #pragma unroll
-          for (int j = 0; j < NQ; j++) b[j] = *reinterpret_cast<const double *>(wb + j * 64);
+        for (int j = 0; j < NQ; j++) b[j] = *reinterpret_cast<const double *>(wb + j * 64);
 #pragma unroll
-          for (int i = 0; i < NF; i++) {
-            double a = *reinterpret_cast<const double *>(ia + aoff[i]);
-            a = tapv ? a : 0.0;
+        for (int i = 0; i < NF; i++) {
+          double a = *reinterpret_cast<const double *>(ia + aoff[i]);
+          a = tapv ? a : 0.0;
 #pragma unroll
-            for (int j = 0; j < NQ; j++) dmma884(acc[i][j][0], acc[i][j][1], a, b[j]);
-          }
-          ia += 32;
-          wb += 4 * p.TS * 8;
+          for (int j = 0; j < NQ; j++) dmma884(acc[i][j][0], acc[i][j][1], a, b[j]);
         }
+        ia += 32;
+        wb += 4 * p.TS * 8;
       }
     }
-  } else {
-    const int tsb = p.TS * 8;
-    for (int c4 = 0; c4 < p.CC; c4 += 4) {
-      const char *wb = Wb + c4 * p.WCS * 8;
-      for (int kh = 0; kh < g.KH; kh++) {
-        const char *ia = Sb + (c4 * g.CS + kh * g.RS) * 8;
-        for (int kw = 0; kw < g.KW; kw++) {
-          double b[NQ];
+  }
+}
+
+// One tap row (kh fixed, all kw) of the channel-k spatial kernel over the first
+// NA fragments of the warp.
+template <int NA, int MF, int NQ>
+__device__ __forceinline__ void sp_row(double (&acc)[MF][NQ][2], const int (&aoff)[MF], const char *ia,
+                                       const char *wb, int tsb, int KW) {
+  for (int kw = 0; kw < KW; kw++) {
+    double b[NQ];
 #pragma unroll
-          for (int j = 0; j < NQ; j++) b[j] = *reinterpret_cast<const double *>(wb + j * 64);
+    for (int j = 0; j < NQ; j++) b[j] = *reinterpret_cast<const double *>(wb + j * 64);
 #pragma unroll
-          for (int i = 0; i < NF; i++) {
-            double a = *reinterpret_cast<const double *>(ia + aoff[i]);
+    for (int i = 0; i < NA; i++) {
+      double a = *reinterpret_cast<const double *>(ia + aoff[i]);
 #pragma unroll
-            for (int j = 0; j < NQ; j++) dmma884(acc[i][j][0], acc[i][j][1], a, b[j]);
-          }
-          ia += 8;
-          wb += tsb;
-        }
+      for (int j = 0; j < NQ; j++) dmma884(acc[i][j][0], acc[i][j][1], a, b[j]);
+    }
+    ia += 8;
+    wb += tsb;
+  }
+}
+
+// One stage of the channel-k spatial kernel (k = 4 input channels of one tap).
+// The number of fragments with an in-image row under tap row kh comes from
+// p.nk; predicated-off DMMAs would still occupy the tensor pipe, so the count
+// selects an exactly-sized instantiation by a warp-uniform switch.
+template <int MF, int NQ>
+__device__ __forceinline__ void sp_stage_chan(double (&acc)[MF][NQ][2], const int (&aoff)[MF], const char *Sb,
+                                              const char *Wb, const SpP &p, int band, int wm) {
+  const TileGeo &g = p.g;
+  const int tsb = p.TS * 8;
+  for (int c4 = 0; c4 < p.CC; c4 += 4) {
+    for (int kh = 0; kh < g.KH; kh++) {
+      const char *ia = Sb + (c4 * g.CS + kh * g.RS) * 8;
+      const char *wb = Wb + (c4 * p.WCS + kh * g.KW * p.TS) * 8;
+      switch (p.nk[band & 3][wm][kh]) {
+#define SP_ROW_CASE(k) \
+  case k: if (MF >= k) sp_row<(MF >= k ? k : MF), MF, NQ>(acc, aoff, ia, wb, tsb, g.KW); break;
+        SP_ROW_CASE(7) SP_ROW_CASE(6) SP_ROW_CASE(5) SP_ROW_CASE(4) SP_ROW_CASE(3) SP_ROW_CASE(2) SP_ROW_CASE(1)
+#undef SP_ROW_CASE
+        default: break;
       }
     }
   }
@@ -216,7 +280,7 @@ __global__ void __launch_bounds__(kThreads, MINB) conv_sp_kernel(const __grid_co
   const int RW = g.R * g.W, npos = g.NI * RW, HW = g.H * g.W;
   const int F = (npos + 7) >> 3;
   if (POOL) {  // window table: first position, image, pooled row in the band, pooled output offset
-    int4 *wl = reinterpret_cast<int4 *>(smem + 2 * p.stage_doubles + p.qg * p.OPS);
+    int4 *wl = reinterpret_cast<int4 *>(smem + p.tail + p.qg * p.OPS);
     const int Wo = g.W >> 1, Ho = g.H >> 1, wpi = (g.R >> 1) * Wo, nwin = g.NI * wpi;
     for (int w = tid; w < nwin; w += kThreads) {
       int img = w / wpi, rem = w - img * wpi;
@@ -225,7 +289,7 @@ __global__ void __launch_bounds__(kThreads, MINB) conv_sp_kernel(const __grid_co
     }
     __syncthreads();
   }
-  // fragment f = i * WM + wm (strided over the warps of a column: balanced)
+  // slot i * WM + wm holds fragment perm[slot] (dealt over the warps of a column: balanced)
   int nf = (F - wm + WM - 1) / WM;
   nf = nf < 0 ? 0 : (nf > MF ? MF : nf);
   // per fragment: byte offset of this lane's A element inside a stage (k part
@@ -233,7 +297,7 @@ __global__ void __launch_bounds__(kThreads, MINB) conv_sp_kernel(const __grid_co
   int aoff[MF], orel[MF], pimy[MF];
 #pragma unroll
   for (int i = 0; i < MF; i++) {
-    int pidx = (i * WM + wm) * 8 + fr;
+    int pidx = p.perm[(i * WM + wm) & 63] * 8 + fr;
     int off = 0, o = 0, iy = 0x7fff0000;
     if (pidx < npos) {
       int img = pidx / RW, rem = pidx - img * RW;
@@ -256,18 +320,19 @@ __global__ void __launch_bounds__(kThreads, MINB) conv_sp_kernel(const __grid_co
   const int my_items = (p.items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int T = my_items * p.NCH;
   const double *wbase = p.wp + (int64_t)qt * p.Ppad * p.WCS;
-  // this lane's B element inside a stage's weight block (k part included), bytes
-  const int woff = (p.in_doubles + wn * NQ * 8 + fr + (TAPK ? fk * p.TS : fk * p.WCS)) * 8;
+  // this lane's B element inside a weight block (k part included), bytes
+  const int wlane = (wn * NQ * 8 + fr + (TAPK ? fk * p.TS : fk * p.WCS)) * 8;
 
   auto issue = [&](int t) {
     int it = blockIdx.x + (t / p.NCH) * gridDim.x, ch = t % p.NCH;
-    int nblk = it / g.bands, band = it - nblk * g.bands;
+    int band = it / g.nblocks, nblk = it - band * g.nblocks;
     double *st = smem + (t & 1) * p.stage_doubles;
     load_in_tile(st, p.in, g, p.CC, ch * p.CC, p.P, nblk * g.NI, p.N, band * g.R, p.sn, p.sp, tid);
-    load_linear(st + p.in_doubles, wbase + (int64_t)ch * p.CC * p.WCS, p.CC * p.WCS, tid);
+    if (!p.wfix) load_linear(st + p.in_doubles, wbase + (int64_t)ch * p.CC * p.WCS, p.CC * p.WCS, tid);
     cp_commit();
   };
 
+  if (p.wfix && T > 0) load_linear(smem + p.wfix, wbase, p.CC * p.WCS, tid);  // joins the first commit group
   if (T > 0) issue(0);
   for (int t = 0; t < T; t++) {
     if (t + 1 < T) {
@@ -278,23 +343,28 @@ __global__ void __launch_bounds__(kThreads, MINB) conv_sp_kernel(const __grid_co
     }
     __syncthreads();
     const char *Sb = reinterpret_cast<const char *>(smem + (t & 1) * p.stage_doubles);
+    const char *Wl = (p.wfix ? reinterpret_cast<const char *>(smem + p.wfix) : Sb + p.in_doubles * 8) + wlane;
     // predicated-off DMMAs still occupy the tensor pipe (ncu: dmma cycles =
-    // issued slots, not useful ones), so the fragment count is a template
-    // parameter selected by a warp-uniform switch, never a predicate
-    switch (nf) {
-      case 7: if (MF >= 7) sp_stage<(MF >= 7 ? 7 : MF), MF, NQ, TAPK>(acc, aoff, Sb, Sb + woff, p); break;
-      case 6: if (MF >= 6) sp_stage<(MF >= 6 ? 6 : MF), MF, NQ, TAPK>(acc, aoff, Sb, Sb + woff, p); break;
-      case 5: if (MF >= 5) sp_stage<(MF >= 5 ? 5 : MF), MF, NQ, TAPK>(acc, aoff, Sb, Sb + woff, p); break;
-      case 4: if (MF >= 4) sp_stage<(MF >= 4 ? 4 : MF), MF, NQ, TAPK>(acc, aoff, Sb, Sb + woff, p); break;
-      case 3: sp_stage<3, MF, NQ, TAPK>(acc, aoff, Sb, Sb + woff, p); break;
-      case 2: sp_stage<2, MF, NQ, TAPK>(acc, aoff, Sb, Sb + woff, p); break;
-      case 1: sp_stage<1, MF, NQ, TAPK>(acc, aoff, Sb, Sb + woff, p); break;
-      default: break;
+    // issued slots, not useful ones), so fragment counts are template
+    // parameters selected by a warp-uniform switch, never a predicate
+    if (TAPK) {
+      switch (nf) {
+        case 7: if (MF >= 7) sp_stage_tap<(MF >= 7 ? 7 : MF), MF, NQ>(acc, aoff, Sb, Wl, p); break;
+        case 6: if (MF >= 6) sp_stage_tap<(MF >= 6 ? 6 : MF), MF, NQ>(acc, aoff, Sb, Wl, p); break;
+        case 5: if (MF >= 5) sp_stage_tap<(MF >= 5 ? 5 : MF), MF, NQ>(acc, aoff, Sb, Wl, p); break;
+        case 4: if (MF >= 4) sp_stage_tap<(MF >= 4 ? 4 : MF), MF, NQ>(acc, aoff, Sb, Wl, p); break;
+        case 3: sp_stage_tap<3, MF, NQ>(acc, aoff, Sb, Wl, p); break;
+        case 2: sp_stage_tap<2, MF, NQ>(acc, aoff, Sb, Wl, p); break;
+        case 1: sp_stage_tap<1, MF, NQ>(acc, aoff, Sb, Wl, p); break;
+        default: break;
+      }
+    } else {
+      sp_stage_chan<MF, NQ>(acc, aoff, Sb, Wl, p, (int)((blockIdx.x + (t / p.NCH) * gridDim.x) / g.nblocks), wm);
     }
     if ((t + 1) % p.NCH == 0) {
       // epilogue of this item: C fragment row = position, cols = 2 output channels
       int it = blockIdx.x + (t / p.NCH) * gridDim.x;
-      int nblk = it / g.bands, band = it - nblk * g.bands;
+      int band = it / g.nblocks, nblk = it - band * g.nblocks;
       int n0 = nblk * g.NI, y0 = band * g.R;
       const int q0 = qt * p.QT + wn * NQ * 8 + fk * 2;
       if (!POOL) {
@@ -317,7 +387,7 @@ __global__ void __launch_bounds__(kThreads, MINB) conv_sp_kernel(const __grid_co
       } else {
         // bias + relu + 2x2 max-pool through a shared [channel][position] tile,
         // qg channels per round; the pre-activation never goes to HBM
-        double *ot = smem + 2 * p.stage_doubles;
+        double *ot = smem + p.tail;
         const int4 *wl = reinterpret_cast<const int4 *>(ot + p.qg * p.OPS);
         const int Wo = g.W >> 1, Ho = g.H >> 1, nwin = npos >> 2;
         double bv[NQ][2];
@@ -330,7 +400,7 @@ __global__ void __launch_bounds__(kThreads, MINB) conv_sp_kernel(const __grid_co
 #pragma unroll
           for (int i = 0; i < MF; i++) {
             if (i < nf) {
-              int pidx = (i * WM + wm) * 8 + fr;
+              int pidx = p.perm[(i * WM + wm) & 63] * 8 + fr;
 #pragma unroll
               for (int j = 0; j < NQ; j++) {
 #pragma unroll
@@ -403,6 +473,10 @@ struct DkP {
   const uint8_t *code;
   int PW, PPS;     // pooled elements per (o, image) plane of a band, and their staging stride
   int dyvec;
+  // one image per stage, channel columns: positions whose row y has y + kh >= H only meet
+  // zero padding under tap row kh, so the K loop runs in row segments with the pair count
+  // shrinking (pairs are dealt round-robin over the warps, ascending in kh within a warp)
+  int skip;
 };
 
 constexpr int kNP = 9;  // max column pairs per warp
@@ -410,8 +484,9 @@ constexpr int kNP = 9;  // max column pairs per warp
 // One stage of the dKrn kernel for a warp that owns exactly NPW column pairs.
 template <int NPW, int MO>
 __device__ __forceinline__ void dk_stage(double (&acc)[MO][kNP][2], const int (&pair_off)[kNP], const char *As,
-                                         const double *Bs, const int *lutk, int kbeg, int kstep, const DkP &p) {
-  for (int k0 = kbeg; k0 < p.npos4; k0 += kstep) {
+                                         const double *Bs, const int *lutk, int kbeg, int kend, int kstep,
+                                         const DkP &p) {
+  for (int k0 = kbeg; k0 < kend; k0 += kstep) {
     const char *ap = As + lutk[k0];
     double a[MO];
 #pragma unroll
@@ -461,11 +536,11 @@ __global__ void __launch_bounds__(kThreads, 2) conv_dk_kernel(const __grid_const
   // column pairs of this warp (byte offsets into the A tile)
   const int c0 = blockIdx.y * p.CC;
   int pair_off[kNP];
-  int npw = p.npairs - wn * p.NPW;
-  npw = npw < 0 ? 0 : (npw > p.NPW ? p.NPW : npw);
+  int npw = (p.npairs - wn + p.WN - 1) / p.WN;  // pair j of this warp is j * WN + wn
+  npw = npw < 0 ? 0 : (npw > kNP ? kNP : npw);
 #pragma unroll
   for (int j = 0; j < kNP; j++) {
-    int pr = wn * p.NPW + j, off = 0;
+    int pr = j * p.WN + wn, off = 0;
     if (j < npw) {
       if (TAPW) {  // pr = (c * KH + kh) * NCF + kwg ; column = kw
         int kwg = pr % p.NCF, r = pr / p.NCF;
@@ -491,7 +566,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_dk_kernel(const __grid_const
 
   auto issue = [&](int t) {
     int it = blockIdx.x + t * gridDim.x;
-    int nblk = it / g.bands, band = it - nblk * g.bands;
+    int band = it / g.nblocks, nblk = it - band * g.nblocks;
     int n0 = nblk * g.NI, y0 = band * g.R;
     double *st = smem + (t & 1) * p.stage_doubles;
     load_in_tile(st, p.A, g, p.CC, c0, p.Ci, n0, p.N, y0, p.a_sn, p.a_sc, tid);
@@ -559,7 +634,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_dk_kernel(const __grid_const
       // window position `code & 0x7f` receives dy where the relu was active
       // (code & 0x80), the other three positions of the window zero
       int it = blockIdx.x + t * gridDim.x;
-      int nblk = it / g.bands, band = it - nblk * g.bands;
+      int band = it / g.nblocks, nblk = it - band * g.nblocks;
       int n0 = nblk * g.NI, y0 = band * g.R;
       int rows_ok = g.H - y0 < g.R ? g.H - y0 : g.R;
       const int Ho = g.H >> 1, Wo = g.W >> 1, nvalp = (rows_ok >> 1) * Wo;
@@ -585,17 +660,31 @@ __global__ void __launch_bounds__(kThreads, 2) conv_dk_kernel(const __grid_const
     const char *As = reinterpret_cast<const char *>(smem + (t & 1) * p.stage_doubles);
     const double *Bs = (p.pooled ? dbx : smem + (t & 1) * p.stage_doubles + p.a_doubles) + (wm * MO * 8 + fr) * p.PS + fk;
     const int kbeg = wk * 4, kstep = 4 * p.WK;
-    switch (npw) {  // exact pair count: no predicated-off DMMAs (they would still occupy the pipe)
-      case 9: dk_stage<9, MO>(acc, pair_off, As, Bs, lut + fk, kbeg, kstep, p); break;
-      case 8: dk_stage<8, MO>(acc, pair_off, As, Bs, lut + fk, kbeg, kstep, p); break;
-      case 7: dk_stage<7, MO>(acc, pair_off, As, Bs, lut + fk, kbeg, kstep, p); break;
-      case 6: dk_stage<6, MO>(acc, pair_off, As, Bs, lut + fk, kbeg, kstep, p); break;
-      case 5: dk_stage<5, MO>(acc, pair_off, As, Bs, lut + fk, kbeg, kstep, p); break;
-      case 4: dk_stage<4, MO>(acc, pair_off, As, Bs, lut + fk, kbeg, kstep, p); break;
-      case 3: dk_stage<3, MO>(acc, pair_off, As, Bs, lut + fk, kbeg, kstep, p); break;
-      case 2: dk_stage<2, MO>(acc, pair_off, As, Bs, lut + fk, kbeg, kstep, p); break;
-      case 1: dk_stage<1, MO>(acc, pair_off, As, Bs, lut + fk, kbeg, kstep, p); break;
-      default: break;
+    int kb = 0;
+    const int ytop = g.H - (int)((blockIdx.x + t * gridDim.x) / g.nblocks) * g.R;  // image rows from the band's first row on
+    for (int v = p.skip ? g.KH - 1 : 0; v >= 0; v--) {
+      // segment of positions whose row still has an in-image input row under tap rows <= v
+      int ke = p.npos4, n = npw;
+      if (p.skip) {
+        ke = ((ytop - v) * g.W + 3) & ~3;
+        ke = ke > p.npos4 ? p.npos4 : (ke < kb ? kb : ke);
+        n = ((v + 1) * g.KW * p.NCF - wn + p.WN - 1) / p.WN;  // pairs of this warp with kh <= v
+        n = n < 0 ? 0 : (n > npw ? npw : n);
+      }
+      const int ks = kb + ((kbeg - kb) & (kstep - 1));  // first k0 >= kb of this warp's K slice (kstep is a power of two)
+      switch (n) {  // exact pair count: no predicated-off DMMAs (they would still occupy the pipe)
+        case 9: dk_stage<9, MO>(acc, pair_off, As, Bs, lut + fk, ks, ke, kstep, p); break;
+        case 8: dk_stage<8, MO>(acc, pair_off, As, Bs, lut + fk, ks, ke, kstep, p); break;
+        case 7: dk_stage<7, MO>(acc, pair_off, As, Bs, lut + fk, ks, ke, kstep, p); break;
+        case 6: dk_stage<6, MO>(acc, pair_off, As, Bs, lut + fk, ks, ke, kstep, p); break;
+        case 5: dk_stage<5, MO>(acc, pair_off, As, Bs, lut + fk, ks, ke, kstep, p); break;
+        case 4: dk_stage<4, MO>(acc, pair_off, As, Bs, lut + fk, ks, ke, kstep, p); break;
+        case 3: dk_stage<3, MO>(acc, pair_off, As, Bs, lut + fk, ks, ke, kstep, p); break;
+        case 2: dk_stage<2, MO>(acc, pair_off, As, Bs, lut + fk, ks, ke, kstep, p); break;
+        case 1: dk_stage<1, MO>(acc, pair_off, As, Bs, lut + fk, ks, ke, kstep, p); break;
+        default: break;
+      }
+      kb = ke;
     }
     __syncthreads();
   }
@@ -637,7 +726,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_dk_kernel(const __grid_const
 #pragma unroll
   for (int j = 0; j < kNP; j++) {
     if (j < npw) {
-      int pr = wn * p.NPW + j;
+      int pr = j * p.WN + wn;
 #pragma unroll
       for (int m = 0; m < MO; m++) {
         int o = o_tile + wm * MO * 8 + m * 8 + fr;
@@ -699,6 +788,8 @@ static inline void set_pieces(TileGeo &g) {
   g.cpr = g.vec ? g.W / 2 : g.W;
   g.cshift = 0;
   while ((1 << g.cshift) < g.cpr) g.cshift++;
+  g.dc8 = (kThreads / 32) / g.NI;
+  g.di8 = (kThreads / 32) % g.NI;
 }
 
 template <typename K>
@@ -814,15 +905,55 @@ int hb_conv_sp_dmma(const hb_array *K, const hb_array *in, hb_array *out, int fl
   p.CC = CC;
   p.Ppad = p.NCH * CC;
   g.bands = (H + g.R - 1) / g.R;
-  p.items = ((N + g.NI - 1) / g.NI) * g.bands;
+  g.nblocks = (N + g.NI - 1) / g.NI;
+  p.items = g.nblocks * g.bands;
   p.in_doubles = CC * g.CS;
-  p.stage_doubles = round_up(p.in_doubles + CC * p.WCS, 2);
+  const bool wfixed = p.NCH == 1;
+  p.stage_doubles = round_up(p.in_doubles + (wfixed ? 0 : CC * p.WCS), 2);
+  p.wfix = wfixed ? 2 * p.stage_doubles : 0;
+  p.tail = 2 * p.stage_doubles + (wfixed ? round_up(CC * p.WCS, 2) : 0);
   p.N = N; p.P = P; p.Q = Q;
   p.sn = in->strides[0]; p.sp = in->strides[1];
   p.in = (const double *)hb_data(in);
   g.vec = (W % 2 == 0) && (g.ox % 2 == 0) && (((uintptr_t)p.in & 15) == 0) && (p.sn % 2 == 0) && (p.sp % 2 == 0);
   set_pieces(g);
-  int smem_bytes = 2 * p.stage_doubles * 8;
+  {
+    // fragment order and per-tap-row fragment counts (see SpP::perm).  Under tap row kh
+    // a fragment with rows [ymin, ymax] of band b (first row y0) has an in-image input row iff
+    // -oy - (y0 + ymax) <= kh <= H - 1 - oy - (y0 + ymin): forward (oy = 0) clips high kh for
+    // large ymin, dInp (oy = 1 - KH) clips low kh for small ymax -> ordering the fragments by
+    // ymin ascending (forward) or ymax descending (dInp) makes the active ones a prefix, as
+    // long as only that one bound is applied
+    const int npos = g.NI * g.R * W, F = (npos + 7) / 8, RW = g.R * W;
+    int ymin[64], ymax[64], order[64];
+    const bool skip = !tapk && g.bands <= 4 && g_hb.conv_skip_padding;
+    for (int f = 0; f < F; f++) {
+      int p0 = f * 8, p1 = p0 + 7 < npos ? p0 + 7 : npos - 1;
+      int i0 = p0 / RW, y0r = (p0 % RW) / W, i1 = p1 / RW, y1r = (p1 % RW) / W;
+      ymin[f] = i0 == i1 ? y0r : 0;
+      ymax[f] = i0 == i1 ? y1r : g.R - 1;
+      order[f] = f;
+    }
+    if (skip) {
+      if (flip) std::stable_sort(order, order + F, [&](int a, int b) { return ymax[a] > ymax[b]; });
+      else std::stable_sort(order, order + F, [&](int a, int b) { return ymin[a] < ymin[b]; });
+    }
+    for (int s = 0; s < 64; s++) p.perm[s] = (unsigned char)(s < F ? order[s] : 0);
+    for (int b = 0; b < 4; b++)
+      for (int wm = 0; wm < WM; wm++)
+        for (int kh = 0; kh < KH; kh++) {
+          int n = 0, y0 = b * g.R;
+          for (int i = 0; i < MF && i * WM + wm < F; i++) {
+            int f = order[i * WM + wm];
+            // only the bound the ordering is monotone in (a superset of the needed work: rows of a
+            // ragged last band beyond the image may be computed, they are never stored)
+            bool on = flip ? -g.oy - (y0 + ymax[f]) <= kh : kh <= H - 1 - g.oy - (y0 + ymin[f]);
+            if (on || !skip) n++;
+          }
+          p.nk[b][wm][kh] = (unsigned char)n;
+        }
+  }
+  int smem_bytes = p.tail * 8;
   if (pf) {
     const int np = g.NI * g.R * W;
     p.pool = 1;
@@ -980,7 +1111,8 @@ int hb_conv_dk_dmma(const hb_array *A, const hb_array *dB, const hb_array *code,
   if (!R) return HB_OK;
   fits(R, kSmemMax);
   g.bands = (H + g.R - 1) / g.R;
-  p.items = ((N + NI - 1) / NI) * g.bands;
+  g.nblocks = (N + NI - 1) / NI;
+  p.items = g.nblocks * g.bands;
   p.N = N; p.Ci = Ci; p.Co = Co;
   p.A = (const double *)hb_data(A);
   p.dB = (const double *)hb_data(dB);
@@ -996,6 +1128,7 @@ int hb_conv_dk_dmma(const hb_array *A, const hb_array *dB, const hb_array *code,
     p.code = (const uint8_t *)hb_data(code);
     p.dyvec = (((H / 2) * (W / 2)) % 2 == 0) && (p.PW % 2 == 0) && (((uintptr_t)p.dy & 15) == 0);
   }
+  p.skip = !tapw && NI == 1 && g_hb.conv_skip_padding;
   int smem_bytes = smem_need();
   if (smem_bytes < red_bytes) smem_bytes = red_bytes;
   int splits = g_hb.sm_count * ctas / (ncc * not_);
