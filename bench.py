@@ -460,18 +460,21 @@ def profile_step(dev, ffi, CnnTrainer, local_batch, gl, lb, world, steps=3):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed
-# `ncu --set full` capture (profiles/r01_conv_dmma_kernels_full_raw.csv), keyed
+# `ncu --set full` capture (profiles/r01_conv_kernels_v3_full_raw.csv), keyed
 # by (launch-site function, operand shapes of the entry)
-NCU_TRAFFIC = {
-    ("hb_conv_dk_dmma", "[4096,16,14,14]"): 205613568 + 5349632,     # conv2 dKrn
-    ("hb_conv_sp_dmma", "[16,16,5,5]"): 102898944 + 59005952,        # conv2 fwd / dInp (rest of the write still in L2)
-    ("hb_conv_dk_dmma", "[4096,1,28,28]"): 436843008 + 4918784,      # conv1 dKrn (unfused capture)
+NCU_TRAFFIC = {   # (launch site, C-ABI entry) -> dram__bytes_read.sum + dram__bytes_write.sum per launch
+    ("hb_conv_dk_dmma", "conv_relu_pool_bwd"): 205844736 + 7503104,    # conv2 dKrn
+    ("hb_conv_sp_dmma", "conv_relu_pool_fwd"): 102965248 + 11618304,   # conv2 fwd + bias/relu/pool
+    ("hb_conv_sp_dmma", "conv_relu_pool_bwd"): 102887936 + 58900736,   # conv2 dInp (rest of the write still in L2)
+    ("hb_conv_strip_fwd", "conv_relu_pool_fwd"): 25733120 + 59483136,  # conv1 fwd + bias/relu/pool
+    ("hb_conv_strip_dk", "conv_relu_pool_bwd"): 141334784 + 3828736,   # conv1 dKrn + bias cotangent
 }
+NCU_TRAFFIC_SOURCE = "profiles/r01_conv_kernels_v3_full_raw.csv (ncu --set full, per launch)"
 
 
 def ncu_traffic(entry: str, site: str):
-    for (fn, shape), by in NCU_TRAFFIC.items():
-        if site.startswith(fn) and shape in entry and "[4096," in entry:   # captured at per-GPU batch 4096
+    for (fn, name), by in NCU_TRAFFIC.items():
+        if site.startswith(fn) and entry.startswith(name + "{") and "[4096," in entry:   # captured at per-GPU batch 4096
             return by
     return None
 
@@ -503,7 +506,7 @@ def roofline_of(rows, hbm_peak, peak_src, fp64_peak):
             roof.update({"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
                          "peak_source": peak_src, "algorithmic_bytes": by})
         roof["traffic"] = ncu_traffic(top["entry"], top["site"])
-        roof["traffic_source"] = "profiles/r01_conv_dmma_kernels_full_raw.csv (ncu --set full, per launch)"
+        roof["traffic_source"] = NCU_TRAFFIC_SOURCE
     breakdown = [{"entry": r["entry"], "site": r["site"], "ms": round(r["ms_per_step"], 4),
                   "share": round(r["share"], 4), "n": r["launches_per_step"]} for r in rows[:12]]
     return roof, breakdown

@@ -88,7 +88,7 @@ __device__ __forceinline__ void sts_zero8(unsigned s) {
 template <bool VEC>
 __device__ __forceinline__ void load_in_tile_t(double *dst, const double *__restrict__ in, const TileGeo &g, int CC,
                                                int c0, int P, int n0, int N, int y0, int64_t sn, int64_t sp,
-                                               int tid) {
+                                               int tid, int cw, int iw) {
   constexpr int PB = VEC ? 16 : 8, PD = VEC ? 2 : 1;  // bytes / doubles per piece
   const int warp = tid >> 5, lane = tid & 31;
   const int planes = CC * g.NI;
@@ -98,7 +98,7 @@ __device__ __forceinline__ void load_in_tile_t(double *dst, const double *__rest
   const int tr0 = wide ? 0 : (lane >> g.cshift), tstep = wide ? 1 : (32 >> g.cshift);
   const unsigned sbase = smem_u32(dst);
   const int ybase = y0 + g.oy;
-  int c = warp / g.NI, img = warp - c * g.NI;
+  int c = cw, img = iw;  // = (warp / NI, warp % NI), computed once per kernel
   for (int pl = warp; pl < planes; pl += kThreads / 32) {
     const bool okp = c0 + c < P && n0 + img < N;
     const unsigned d0 = sbase + (unsigned)((c * g.CS + img * g.IS - g.ox + tr0 * g.RS + PD * ch0) * 8);
@@ -126,9 +126,9 @@ __device__ __forceinline__ void load_in_tile_t(double *dst, const double *__rest
 }
 __device__ __forceinline__ void load_in_tile(double *dst, const double *__restrict__ in, const TileGeo &g, int CC,
                                              int c0, int P, int n0, int N, int y0, int64_t sn, int64_t sp,
-                                             int tid) {
-  if (g.vec) load_in_tile_t<true>(dst, in, g, CC, c0, P, n0, N, y0, sn, sp, tid);
-  else load_in_tile_t<false>(dst, in, g, CC, c0, P, n0, N, y0, sn, sp, tid);
+                                             int tid, int cw, int iw) {
+  if (g.vec) load_in_tile_t<true>(dst, in, g, CC, c0, P, n0, N, y0, sn, sp, tid, cw, iw);
+  else load_in_tile_t<false>(dst, in, g, CC, c0, P, n0, N, y0, sn, sp, tid, cw, iw);
 }
 
 // contiguous n doubles (n even, both 16-byte aligned)
@@ -323,16 +323,33 @@ __global__ void __launch_bounds__(kThreads, MINB) conv_sp_kernel(const __grid_co
   // this lane's B element inside a weight block (k part included), bytes
   const int wlane = (wn * NQ * 8 + fr + (TAPK ? fk * p.TS : fk * p.WCS)) * 8;
 
+  const int cw = warp / g.NI, iw = warp - cw * g.NI;
+  // stage t = (item, channel chunk); both sides of the pipeline step through them without divisions
+  int is_ch = 0, is_n0, is_y0;   // next stage to issue
+  int cs_ch = 0, cs_n0, cs_y0, cs_band;  // stage being computed
+  {
+    int band = (int)blockIdx.x / g.nblocks, nblk = (int)blockIdx.x - band * g.nblocks;
+    is_n0 = cs_n0 = nblk * g.NI;
+    is_y0 = cs_y0 = band * g.R;
+    cs_band = band;
+  }
+  int is_it = blockIdx.x, cs_it = blockIdx.x;
   auto issue = [&](int t) {
-    int it = blockIdx.x + (t / p.NCH) * gridDim.x, ch = t % p.NCH;
-    int band = it / g.nblocks, nblk = it - band * g.nblocks;
     double *st = smem + (t & 1) * p.stage_doubles;
-    load_in_tile(st, p.in, g, p.CC, ch * p.CC, p.P, nblk * g.NI, p.N, band * g.R, p.sn, p.sp, tid);
-    if (!p.wfix) load_linear(st + p.in_doubles, wbase + (int64_t)ch * p.CC * p.WCS, p.CC * p.WCS, tid);
+    load_in_tile(st, p.in, g, p.CC, is_ch * p.CC, p.P, is_n0, p.N, is_y0, p.sn, p.sp, tid, cw, iw);
+    if (!p.wfix) load_linear(st + p.in_doubles, wbase + (int64_t)is_ch * p.CC * p.WCS, p.CC * p.WCS, tid);
     cp_commit();
+    if (++is_ch == p.NCH) {
+      is_ch = 0;
+      is_it += gridDim.x;
+      int band = is_it / g.nblocks, nblk = is_it - band * g.nblocks;
+      is_n0 = nblk * g.NI;
+      is_y0 = band * g.R;
+    }
   };
 
-  if (p.wfix && T > 0) load_linear(smem + p.wfix, wbase, p.CC * p.WCS, tid);  // joins the first commit group
+  // weights of all channel chunks staged once per CTA (joins the first commit group)
+  if (p.wfix && T > 0) load_linear(smem + p.wfix, wbase, p.Ppad * p.WCS, tid);
   if (T > 0) issue(0);
   for (int t = 0; t < T; t++) {
     if (t + 1 < T) {
@@ -343,7 +360,7 @@ __global__ void __launch_bounds__(kThreads, MINB) conv_sp_kernel(const __grid_co
     }
     __syncthreads();
     const char *Sb = reinterpret_cast<const char *>(smem + (t & 1) * p.stage_doubles);
-    const char *Wl = (p.wfix ? reinterpret_cast<const char *>(smem + p.wfix) : Sb + p.in_doubles * 8) + wlane;
+    const char *Wl = (p.wfix ? reinterpret_cast<const char *>(smem + p.wfix + cs_ch * p.CC * p.WCS) : Sb + p.in_doubles * 8) + wlane;
     // predicated-off DMMAs still occupy the tensor pipe (ncu: dmma cycles =
     // issued slots, not useful ones), so fragment counts are template
     // parameters selected by a warp-uniform switch, never a predicate
@@ -359,13 +376,19 @@ __global__ void __launch_bounds__(kThreads, MINB) conv_sp_kernel(const __grid_co
         default: break;
       }
     } else {
-      sp_stage_chan<MF, NQ>(acc, aoff, Sb, Wl, p, (int)((blockIdx.x + (t / p.NCH) * gridDim.x) / g.nblocks), wm);
+      sp_stage_chan<MF, NQ>(acc, aoff, Sb, Wl, p, cs_band, wm);
     }
-    if ((t + 1) % p.NCH == 0) {
+    if (++cs_ch == p.NCH) {
       // epilogue of this item: C fragment row = position, cols = 2 output channels
-      int it = blockIdx.x + (t / p.NCH) * gridDim.x;
-      int band = it / g.nblocks, nblk = it - band * g.nblocks;
-      int n0 = nblk * g.NI, y0 = band * g.R;
+      const int n0 = cs_n0, y0 = cs_y0;
+      {  // the item after this one
+        cs_ch = 0;
+        cs_it += gridDim.x;
+        const int it = cs_it;
+        cs_band = it / g.nblocks;
+        cs_n0 = (it - cs_band * g.nblocks) * g.NI;
+        cs_y0 = cs_band * g.R;
+      }
       const int q0 = qt * p.QT + wn * NQ * 8 + fk * 2;
       if (!POOL) {
         double *ob = p.out + ((int64_t)n0 * p.Q + q0) * HW + (int64_t)y0 * g.W;
@@ -564,12 +587,13 @@ __global__ void __launch_bounds__(kThreads, 2) conv_dk_kernel(const __grid_const
   const int T = (p.items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int co = p.Co - o_tile < WM * MO * 8 ? p.Co - o_tile : WM * MO * 8;
 
+  const int cw = warp / g.NI, iw = warp - cw * g.NI;
   auto issue = [&](int t) {
     int it = blockIdx.x + t * gridDim.x;
     int band = it / g.nblocks, nblk = it - band * g.nblocks;
     int n0 = nblk * g.NI, y0 = band * g.R;
     double *st = smem + (t & 1) * p.stage_doubles;
-    load_in_tile(st, p.A, g, p.CC, c0, p.Ci, n0, p.N, y0, p.a_sn, p.a_sc, tid);
+    load_in_tile(st, p.A, g, p.CC, c0, p.Ci, n0, p.N, y0, p.a_sn, p.a_sc, tid, cw, iw);
     double *db = st + p.a_doubles;
     int rows_ok = g.H - y0 < g.R ? g.H - y0 : g.R;
     const int planes = co * g.NI;
@@ -877,7 +901,10 @@ int hb_conv_sp_dmma(const hb_array *K, const hb_array *in, hb_array *out, int fl
         extra = (p.QT < 8 ? p.QT : 8) * pool_stride(np) * 8 + (np / 4) * 16 + 64;
       }
       if (budgets[bi] - extra < 0) continue;
+      // weights per stage next to their channels, or all channels' weights staged once per CTA
       int maxc = ((budgets[bi] - extra) / 8 / 2) / per_c;
+      int maxc_fix = ((budgets[bi] - extra) / 8 - round_up(Pq, 4) * p.WCS - 8) / 2 / CS;
+      if (maxc_fix > maxc) maxc = maxc_fix;
       if (!tapk) maxc = maxc / 4 * 4;
       if (maxc < (tapk ? 1 : 4)) continue;
       int CC = maxc < Pq ? maxc : Pq;
@@ -908,10 +935,14 @@ int hb_conv_sp_dmma(const hb_array *K, const hb_array *in, hb_array *out, int fl
   g.nblocks = (N + g.NI - 1) / g.NI;
   p.items = g.nblocks * g.bands;
   p.in_doubles = CC * g.CS;
-  const bool wfixed = p.NCH == 1;
+  // all chunks' weights once per CTA when that fits the budget the tile was chosen for
+  const int budget_used = ctas == 2 ? kSmemMax / 2 - 1024 : kSmemMax;
+  int pool_extra = 0;
+  if (pf) pool_extra = (p.QT < 8 ? p.QT : 8) * pool_stride(g.NI * g.R * W) * 8 + (g.NI * g.R * W / 4) * 16 + 64;
+  const bool wfixed = (2 * round_up(p.in_doubles, 2) + round_up(p.Ppad * p.WCS, 2)) * 8 + pool_extra <= budget_used;
   p.stage_doubles = round_up(p.in_doubles + (wfixed ? 0 : CC * p.WCS), 2);
   p.wfix = wfixed ? 2 * p.stage_doubles : 0;
-  p.tail = 2 * p.stage_doubles + (wfixed ? round_up(CC * p.WCS, 2) : 0);
+  p.tail = 2 * p.stage_doubles + (wfixed ? round_up(p.Ppad * p.WCS, 2) : 0);
   p.N = N; p.P = P; p.Q = Q;
   p.sn = in->strides[0]; p.sp = in->strides[1];
   p.in = (const double *)hb_data(in);
