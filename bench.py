@@ -393,6 +393,28 @@ def main():
     clk = clocks.stop()
     e2e_value = global_batch * K / e2e_s
 
+    # ---- the same step fed by the device-resident input pipeline: 60 000 synthetic
+    # glyphs as raw bytes in HBM, every minibatch assembled by hb_mnist_batch_into from the epoch's
+    # shuffle; only the 8-byte loss crosses PCIe (reported next to e2e, not instead of it)
+    from horde_ad_b200 import mnist_data
+    drng = np.random.Generator(np.random.Philox(4242 + rank))
+    dmn = mnist_data.DeviceMnist(dev, drng.integers(0, 256, (60000, 28, 28), dtype=np.uint8),
+                                 drng.integers(0, 10, 60000, dtype=np.uint8))
+    dmn.shuffle(42 + rank)
+    nb = dmn.n_batches(local_batch)
+    for i in range(2):
+        tr.train_step_device(dmn, i % nb)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        if i % RESET_EVERY == 0:
+            tr.reset()
+        tr.train_step_device(dmn, i % nb)
+    dev.sync()
+    resident_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    del dmn
+
     # ---- live per-kernel timing of the same step (eager, events per launch);
     # every rank runs it (the step contains the all-reduce), rank 0 reports
     prof = profile_step(dev, ffi, CnnTrainer, local_batch, gl, lb, world)
@@ -422,6 +444,10 @@ def main():
         "dtype": "f64", "data": "synthetic", "config": config_dict(args, world),
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d * world,
                 "d2h_bytes_per_step": 8 * world, "ms_per_step": e2e_s / K * 1e3},
+        "device_input_pipeline": {"value": global_batch * K / resident_s, "unit": "samples/s",
+                                  "ms_per_step": resident_s / K * 1e3, "h2d_bytes_per_step": 0,
+                                  "d2h_bytes_per_step": 8 * world,
+                                  "what": "minibatches assembled on the device from resident IDX bytes (hb_mnist_batch_into)"},
         "gpu_launches": int(n1.value - n0.value),
         "clocks": clk, "loss": loss if np.isfinite(loss) else None,
         "loss_resident": loss_resident if np.isfinite(loss_resident) else None,

@@ -496,3 +496,97 @@ extern "C" int hb_softmax_xent(const hb_array *logits, const hb_array *expected,
   if (dlogits_out) *dlogits_out = dl;
   return HB_OK;
 }
+
+// ------------------------------------------------- MNIST minibatch assembly
+// Device twin of the input pipeline of example/MnistData.hs:134-171
+// (readMnistData: glyph = fromIntegral pixel / 255, target = one-hot label;
+// mkMnistDataBatchS: stack `batch` samples; the epoch's `shuffle` arrives as
+// the `order` vector).  The raw IDX bytes stay resident in HBM (47 MB for the
+// 60 000 training glyphs), so a training step moves no tensor data over PCIe.
+template <typename T, typename I, int VEC>
+__global__ void __launch_bounds__(256)
+    hb_mnist_batch_kernel(const uint8_t *__restrict__ pix, const uint8_t *__restrict__ lab, const I *__restrict__ order,
+                          int64_t n, int64_t start, int64_t batch, int hw, int classes, T *__restrict__ glyphs,
+                          T *__restrict__ targets) {
+  const int per = hw / VEC;
+  const int64_t ng = batch * per, total = ng + batch * classes;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    if (i < ng) {
+      int64_t b = i / per;
+      int k = (int)(i - b * per) * VEC;
+      int64_t id = order ? (int64_t)order[start + b] : start + b;
+      const bool ok = id >= 0 && id < n;
+      T out[VEC];
+      if (VEC == 8) {
+        uint2 raw = ok ? *reinterpret_cast<const uint2 *>(pix + id * hw + k) : make_uint2(0u, 0u);
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          out[e] = (T)((raw.x >> (8 * e)) & 0xffu) / (T)255;
+          out[4 + e] = (T)((raw.y >> (8 * e)) & 0xffu) / (T)255;
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < VEC; e++) out[e] = ok ? (T)pix[id * hw + k + e] / (T)255 : (T)0;
+      }
+      T *g = glyphs + b * hw + k;
+#pragma unroll
+      for (int e = 0; e < VEC; e++) g[e] = out[e];
+    } else {
+      int64_t j = i - ng, b = j / classes;
+      int c = (int)(j - b * classes);
+      int64_t id = order ? (int64_t)order[start + b] : start + b;
+      const bool ok = id >= 0 && id < n;
+      targets[j] = (ok && (int)lab[id] == c) ? (T)1 : (T)0;
+    }
+  }
+}
+
+extern "C" int hb_mnist_batch_into(const hb_array *pixels, const hb_array *labels, const hb_array *order,
+                                   int64_t start, hb_array *glyphs_dst, hb_array *targets_dst) {
+  hb_prof_scope prof_("mnist_batch_into", glyphs_dst);
+  HB_CHECK_INIT();
+  HB_REQUIRE(pixels && labels && glyphs_dst && targets_dst, "null argument");
+  HB_REQUIRE(pixels->dt == HB_I8 && labels->dt == HB_I8 && pixels->rank >= 2 && labels->rank == 1 &&
+                 pixels->shape[0] == labels->shape[0] && hb_contig(pixels) && hb_contig(labels),
+             "mnist_batch: pixels [n,...] and labels [n] must be contiguous I8 (raw IDX bytes)");
+  HB_REQUIRE(hb_is_float(glyphs_dst->dt) && targets_dst->dt == glyphs_dst->dt && hb_contig(glyphs_dst) &&
+                 hb_contig(targets_dst) && glyphs_dst->rank == pixels->rank && targets_dst->rank == 2 &&
+                 targets_dst->shape[0] == glyphs_dst->shape[0],
+             "mnist_batch: glyphs [batch,...] and targets [batch,classes] must be contiguous and of one floating type");
+  const int64_t n = pixels->shape[0], batch = glyphs_dst->shape[0];
+  int64_t hw = 1;
+  for (int i = 1; i < pixels->rank; i++) {
+    HB_REQUIRE(pixels->shape[i] == glyphs_dst->shape[i], "mnist_batch: glyph extents %s vs %s",
+               hb_shape_str(pixels).c_str(), hb_shape_str(glyphs_dst).c_str());
+    hw *= pixels->shape[i];
+  }
+  const int64_t classes = targets_dst->shape[1];
+  HB_REQUIRE(hw < (1 << 30) && classes < (1 << 30), "mnist_batch: extents too large");
+  HB_REQUIRE(start >= 0, "mnist_batch: negative start");
+  if (order) {
+    HB_REQUIRE((order->dt == HB_I32 || order->dt == HB_I64) && order->rank == 1 && hb_contig(order),
+               "mnist_batch: order must be a contiguous I32 or I64 vector");
+    HB_REQUIRE(start + batch <= order->shape[0], "mnist_batch: batch [%lld, %lld) beyond the order vector (%lld)",
+               (long long)start, (long long)(start + batch), (long long)order->shape[0]);
+  }
+  if (batch == 0 || (hw == 0 && classes == 0)) return HB_OK;
+  const uint8_t *pp = (const uint8_t *)hb_data(pixels), *lp = (const uint8_t *)hb_data(labels);
+  const bool vec = hw % 8 == 0 && ((uintptr_t)pp & 7) == 0 && ((uintptr_t)hb_data(glyphs_dst) & 15) == 0;
+  const int64_t total = batch * (vec ? hw / 8 : hw) + batch * classes;
+  const int blocks = hb_blocks_for(total, 256, g_hb.sm_count * 16);
+#define MB_LAUNCH(T, I, V)                                                                                          \
+  hb_mnist_batch_kernel<T, I, V><<<blocks, 256, 0, g_hb.stream>>>(pp, lp, order ? (const I *)hb_data(order) : nullptr, \
+                                                                  n, start, batch, (int)hw, (int)classes,           \
+                                                                  (T *)hb_data(glyphs_dst), (T *)hb_data(targets_dst))
+#define MB_LAUNCH_T(T)                                                        \
+  do {                                                                        \
+    if (order && order->dt == HB_I64) { if (vec) MB_LAUNCH(T, int64_t, 8); else MB_LAUNCH(T, int64_t, 1); } \
+    else { if (vec) MB_LAUNCH(T, int32_t, 8); else MB_LAUNCH(T, int32_t, 1); }                             \
+  } while (0)
+  if (glyphs_dst->dt == HB_F64) MB_LAUNCH_T(double);
+  else MB_LAUNCH_T(float);
+#undef MB_LAUNCH_T
+#undef MB_LAUNCH
+  HB_LAUNCHED();
+  return HB_OK;
+}

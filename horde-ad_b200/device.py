@@ -419,3 +419,10 @@ class DeviceBackend:
 
     def upload_into(self, dst: DeviceArray, host_ptr):
         call("hb_upload_into", dst.h, host_ptr)
+
+    def mnist_batch_into(self, pixels: DeviceArray, labels: DeviceArray, order, start: int,
+                         glyphs_dst: DeviceArray, targets_dst: DeviceArray):
+        """mkMnistDataBatchS on the device (MnistData.hs:134-171): glyph = pixel / 255, target = one-hot
+        label, for the samples order[start : start + batch] (order None = file order)."""
+        call("hb_mnist_batch_into", pixels.h, labels.h, order.h if order is not None else None, int(start),
+             glyphs_dst.h, targets_dst.h)

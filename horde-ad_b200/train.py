@@ -167,6 +167,13 @@ class CnnTrainer:
             self._prefetched = (_addr(next_glyphs_ptr), _addr(next_labels_ptr))
         return float(self.dev.kfromS(self.dev.sslice(self.n_params, 1, bucket)))
 
+    def train_step_device(self, data, k: int) -> float:
+        """One step on minibatch k of a `mnist_data.DeviceMnist`: the batch is
+        assembled on the device from the resident IDX bytes; only the loss crosses PCIe."""
+        data.batch_into(k, self.glyphs, self.labels)
+        bucket = self.step_enqueue()
+        return float(self.dev.kfromS(self.dev.sslice(self.n_params, 1, bucket)))
+
     def loss_of(self, bucket) -> float:
         return float(self.dev.kfromS(self.dev.sslice(self.n_params, 1, bucket)))
 

@@ -403,6 +403,20 @@ int hb_conv_relu_pool_bwd(const hb_array *K, const hb_array *A,
 int hb_softmax_xent(const hb_array *logits, const hb_array *expected,
                     double scale, hb_array **loss_out, hb_array **dlogits_out);
 
+/* Device twin of the MNIST input pipeline (example/MnistData.hs:134-171,
+ * SURVEY.md 8f-3).  `pixels` [n,H,W] and `labels` [n] hold the raw IDX bytes
+ * (dtype I8, read as unsigned) resident on the device; the minibatch
+ *   glyphs[b,h,w] = fromIntegral pixels[id_b,h,w] / 255      (readMnistData)
+ *   targets[b,c]  = if c == labels[id_b] then 1 else 0
+ * with id_b = order[start + b] (order: I32 or I64 vector, the epoch's shuffle;
+ * NULL = identity) is written INTO glyphs_dst [batch,H,W] / targets_dst
+ * [batch,classes] (F64 or F32, contiguous): mkMnistDataBatchS without any
+ * host<->device tensor traffic.  Sample ids outside [0,n) give an all-zero
+ * glyph and target (the out-of-bounds rule of gather). */
+int hb_mnist_batch_into(const hb_array *pixels, const hb_array *labels,
+                        const hb_array *order, int64_t start,
+                        hb_array *glyphs_dst, hb_array *targets_dst);
+
 /* updateWithGradient (OptimizerTools.hs:20-51): p := p - gamma * g, in place.*/
 int hb_sgd_step(hb_array *p, const hb_array *g, double gamma);
 /* updateWithGradientAdam (OptimizerTools.hs:134-232, defaults :83-89): one

@@ -461,3 +461,21 @@ class ConcreteBackend:
         m[...] = T(beta1) * m + T(1 - beta1) * g
         v[...] = T(beta2) * v + T(1 - beta2) * (g * g)
         p[...] = p - (T(alphat) * m) / (np.sqrt(v) + T(epsilon))
+
+
+# ---------------------------------------------------------------- MNIST input pipeline
+def mnist_batch(pixels, labels, order, start, batch, classes=10, dtype=np.float64):
+    """readMnistData + mkMnistDataBatchS (example/MnistData.hs:127-152): for the samples
+    order[start : start + batch] (order None = file order) glyph = fromIntegral pixel / 255 and
+    target = one-hot label; sample ids outside [0, n) give zeros (gather's out-of-bounds rule)."""
+    pixels, labels = np.asarray(pixels, np.uint8), np.asarray(labels, np.uint8)
+    n = pixels.shape[0]
+    ids = np.arange(start, start + batch) if order is None else np.asarray(order)[start:start + batch]
+    glyphs = np.zeros((batch,) + pixels.shape[1:], dtype)
+    targets = np.zeros((batch, classes), dtype)
+    for b, i in enumerate(ids):
+        if 0 <= i < n:
+            glyphs[b] = pixels[i].astype(dtype) / np.dtype(dtype).type(255)
+            if labels[i] < classes:
+                targets[b, labels[i]] = 1
+    return glyphs, targets
