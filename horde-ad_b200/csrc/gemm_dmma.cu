@@ -47,6 +47,7 @@ struct GemmP {
   int64_t c_sm;         // row stride of C (columns contiguous)
   int kchunks;          // BK-chunks per split
   int a_vec, b_vec;     // 16-byte cp.async allowed
+  int *flags;           // serial split-K: per output tile, the number of K slices already accumulated into C
 };
 
 // Stage one operand tile: `rows` x BK where the operand's (row, k) element is
@@ -177,6 +178,149 @@ __global__ void __launch_bounds__(128 * KS) gemm_dmma_kernel(const __grid_consta
     }
 }
 
+// ---------------------------------------------------------------------------
+// Eight-warp variant: the same 64x64 CTA tile, but every warp owns a 32x16
+// piece over the FULL k range of a 32-deep chunk (no intra-CTA split-K, so no
+// shared-memory reduction), twice the DMMAs per barrier and per staged byte.
+// For output grids of about one tile per SM (the 512-wide recurrence GEMMs of
+// MnistRnnShaped2: 128 tiles) it replaces split-K across CTAs + a reduce
+// kernel: one launch, partial sums never leave the registers.
+constexpr int BK8 = 32, STAGES8 = 3;
+constexpr int LDK8 = BK8 + 4, LDM8 = 64 + 4;
+constexpr int TILE8 = 64 * LDK8 > BK8 * LDM8 ? 64 * LDK8 : BK8 * LDM8;
+
+template <bool KFAST>
+__device__ __forceinline__ void stage_tile8(double *dst, const double *__restrict__ base, int64_t s_row, int64_t s_k,
+                                            int row0, int nrows, int k0, int K, int vec, int tid) {
+  if (KFAST) {  // 64 rows x 32 k: 16 pieces per row
+#pragma unroll
+    for (int it = 0; it < 4; it++) {
+      int idx = tid + it * 256;
+      int r = idx >> 4, kk = (idx & 15) * 2;
+      double *d = dst + r * LDK8 + kk;
+      int row = row0 + r, k = k0 + kk;
+      const double *s = base + (int64_t)row * s_row + k;
+      if (row < nrows && k + 1 < K && vec) cp16(d, s);
+      else {
+        d[0] = (row < nrows && k < K) ? s[0] : 0.0;
+        d[1] = (row < nrows && k + 1 < K) ? s[1] : 0.0;
+      }
+    }
+  } else {      // 32 k x 64 rows: 32 pieces per k
+#pragma unroll
+    for (int it = 0; it < 4; it++) {
+      int idx = tid + it * 256;
+      int kk = idx >> 5, r = (idx & 31) * 2;
+      double *d = dst + kk * LDM8 + r;
+      int row = row0 + r, k = k0 + kk;
+      const double *s = base + (int64_t)k * s_k + row;
+      if (k < K && row + 1 < nrows && vec) cp16(d, s);
+      else {
+        d[0] = (k < K && row < nrows) ? s[0] : 0.0;
+        d[1] = (k < K && row + 1 < nrows) ? s[1] : 0.0;
+      }
+    }
+  }
+}
+
+template <bool A_KFAST, bool B_KFAST>
+__global__ void __launch_bounds__(256, 2) gemm8_dmma_kernel(const __grid_constant__ GemmP p) {
+  extern __shared__ __align__(16) double smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wm = (warp & 1) * 32, wn = (warp >> 1) * 16;
+  const int fr = lane >> 2, fk = lane & 3;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int kbeg = blockIdx.z * p.kchunks * BK8;
+  int kend = kbeg + p.kchunks * BK8;
+  if (kend > p.K) kend = p.K;
+  const int nk = kend > kbeg ? (kend - kbeg + BK8 - 1) / BK8 : 0;
+
+  auto issue = [&](int c) {
+    double *as = smem + (c % STAGES8) * 2 * TILE8, *bs = as + TILE8;
+    stage_tile8<A_KFAST>(as, p.A, p.a_sm, p.a_sk, m0, p.M, kbeg + c * BK8, kend, p.a_vec, tid);
+    stage_tile8<B_KFAST>(bs, p.B, p.b_sn, p.b_sk, n0, p.N, kbeg + c * BK8, kend, p.b_vec, tid);
+    cp_commit();
+  };
+  double acc[4][2][2];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 2; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  for (int c = 0; c < STAGES8 - 1; c++) {
+    if (c < nk) issue(c);
+    else cp_commit();
+  }
+  // this lane's fragment element inside a stage (k part included)
+  const int aoff = A_KFAST ? (wm + fr) * LDK8 + fk : fk * LDM8 + wm + fr;
+  const int boff = B_KFAST ? (wn + fr) * LDK8 + fk : fk * LDM8 + wn + fr;
+  constexpr int a_i = A_KFAST ? 8 * LDK8 : 8, a_k = A_KFAST ? 4 : 4 * LDM8;
+  constexpr int b_j = B_KFAST ? 8 * LDK8 : 8, b_k = B_KFAST ? 4 : 4 * LDM8;
+  for (int c = 0; c < nk; c++) {
+    cp_wait<STAGES8 - 2>();
+    __syncthreads();
+    if (c + STAGES8 - 1 < nk) issue(c + STAGES8 - 1);
+    else cp_commit();
+    const double *as = smem + (c % STAGES8) * 2 * TILE8 + aoff, *bs = smem + (c % STAGES8) * 2 * TILE8 + TILE8 + boff;
+#pragma unroll
+    for (int k4 = 0; k4 < BK8 / 4; k4++) {
+      double a[4], b[2];
+#pragma unroll
+      for (int i = 0; i < 4; i++) a[i] = as[i * a_i + k4 * a_k];
+#pragma unroll
+      for (int j = 0; j < 2; j++) b[j] = bs[j * b_j + k4 * b_k];
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 2; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+  }
+  // K slices of one tile: separate partial buffers (p.flags == NULL, reduced by gemm_reduce_kernel), or
+  // accumulated straight into C in slice order ("serial split-K": slice z waits until z slices are in,
+  // adds its registers to what they left, publishes z + 1; the last slice resets the flag) -- the order of
+  // the additions is fixed, so the result is deterministic, and the partial sums never travel through HBM
+  // more than once.  CTAs are dispatched in block-index order, so the slice waited for is always running.
+  const bool serial = p.flags != nullptr;
+  double *C = serial ? p.C : p.C + (int64_t)blockIdx.z * p.M * p.c_sm;
+  int *flag = serial ? p.flags + blockIdx.y * gridDim.x + blockIdx.x : nullptr;
+  const int z = blockIdx.z;
+  if (serial && z > 0) {
+    if (tid == 0) {
+      while (*reinterpret_cast<volatile int *>(flag) != z) __nanosleep(64);
+      __threadfence();
+    }
+    __syncthreads();
+  }
+  const bool addc = serial && z > 0;
+  const bool cvec = (p.c_sm & 1) == 0 && ((uintptr_t)C & 15) == 0;
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      int m = m0 + wm + i * 8 + fr, n = n0 + wn + j * 8 + fk * 2;
+      if (m < p.M) {
+        double *c = C + (int64_t)m * p.c_sm + n;
+        if (n + 1 < p.N && cvec) {
+          double2 o = make_double2(acc[i][j][0], acc[i][j][1]);
+          if (addc) {
+            double2 t = __ldcg(reinterpret_cast<const double2 *>(c));
+            o.x = t.x + o.x;
+            o.y = t.y + o.y;
+          }
+          __stcg(reinterpret_cast<double2 *>(c), o);
+        } else {
+          if (n < p.N) __stcg(c, addc ? __ldcg(c) + acc[i][j][0] : acc[i][j][0]);
+          if (n + 1 < p.N) __stcg(c + 1, addc ? __ldcg(c + 1) + acc[i][j][1] : acc[i][j][1]);
+        }
+      }
+    }
+  if (serial && gridDim.z > 1) {
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) *reinterpret_cast<volatile int *>(flag) = z + 1 == (int)gridDim.z ? 0 : z + 1;
+  }
+}
+
 __global__ void gemm_reduce_kernel(const double *__restrict__ part, double *__restrict__ out, int64_t n, int splits) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -186,6 +330,21 @@ __global__ void gemm_reduce_kernel(const double *__restrict__ part, double *__re
 }
 
 }  // namespace
+
+// per-tile slice counters of the serial split-K epilogue: zero between launches (the last slice
+// of a tile resets its counter), allocated once -- outside any graph capture, since every captured
+// program is run eagerly first
+constexpr int64_t kFlagTiles = 1 << 16;
+static int gemm_flags(int **out) {
+  static int *flags = nullptr;
+  if (!flags) {
+    HB_REQUIRE(!g_hb.capturing, "gemm: first use inside a graph capture");
+    HB_CUDA(cudaMalloc(&flags, kFlagTiles * sizeof(int)));
+    HB_CUDA(cudaMemsetAsync(flags, 0, kFlagTiles * sizeof(int), g_hb.stream));
+  }
+  *out = flags;
+  return HB_OK;
+}
 
 // C (contiguous [M,N] f64) = A x B with element strides; *done = 1 if handled.
 int hb_gemm_dmma(const double *A, int64_t a_sm, int64_t a_sk, const double *B, int64_t b_sk, int64_t b_sn, double *C,
@@ -207,6 +366,62 @@ int hb_gemm_dmma(const double *A, int64_t a_sm, int64_t a_sk, const double *B, i
   p.b_vec = ((uintptr_t)B & 15) == 0 && ((b_kfast ? b_sn : b_sk) % 2 == 0);
   int gm = (int)((M + BM - 1) / BM), gn = (int)((N + BN - 1) / BN);
   if (gn > 65535) return HB_OK;
+  {
+    // eight-warp kernel (see gemm8_dmma_kernel); K is sliced across CTAs until two CTAs per SM are busy
+    static const int force = getenv("HB_GEMM8") ? atoi(getenv("HB_GEMM8")) : -1;
+    const int64_t tiles8 = (int64_t)gm * gn;
+    const int chunks8 = (int)((K + BK8 - 1) / BK8);
+    int splits = 1;
+    if (tiles8 < 2 * (int64_t)g_hb.sm_count) {
+      splits = (int)(2 * (int64_t)g_hb.sm_count / tiles8);
+      if (splits > chunks8 / 4) splits = chunks8 / 4;  // at least 4 chunks (128 k) per slice
+      if (splits < 1) splits = 1;
+      if (splits > 64) splits = 64;
+    }
+    p.kchunks = (chunks8 + splits - 1) / splits;
+    splits = (chunks8 + p.kchunks - 1) / p.kchunks;
+    const bool serial = splits == 2 && tiles8 <= kFlagTiles;
+    // measured (tools/gemm_sweep.py): the eight-warp kernel wins on large grids (2048^3: 563 vs 602 us,
+    // [512,512]x[512,8192]: 145 vs 159 us), on ~one tile per SM with two K slices ([512,512]x[512,1024]:
+    // 29 vs 33 us) and on very deep K over a few tiles ([64,4096]x[4096,784]: 27 vs 32 us); the four-warp
+    // kernel with its finer split keeps the 64-tile / K = 1024 shapes (29 vs 36 us)
+    const int64_t ctas8 = tiles8 * splits, slots8 = 2 * (int64_t)g_hb.sm_count;
+    bool use8 = (splits == 1 && 3 * tiles8 >= 2 * slots8) || (splits == 2 && 5 * ctas8 >= 4 * slots8) ||
+                (splits > 4 && chunks8 >= 64);
+    if (force >= 0) use8 = force != 0;
+    if (use8) {
+      p.C = C;
+      p.flags = nullptr;
+      if (serial) {
+        HB_TRY(gemm_flags(&p.flags));
+      } else if (splits > 1) {
+        void *scr;
+        HB_TRY(hb_scratch((size_t)splits * M * N * 8, &scr));
+        p.C = (double *)scr;
+      }
+      dim3 grid((unsigned)gm, (unsigned)gn, (unsigned)splits);
+      size_t smem = (size_t)STAGES8 * 2 * TILE8 * 8;
+#define GEMM8_LAUNCH(AK, BKF)                                                                                  \
+  do {                                                                                                         \
+    HB_CUDA(cudaFuncSetAttribute(gemm8_dmma_kernel<AK, BKF>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                 (int)smem));                                                                  \
+    gemm8_dmma_kernel<AK, BKF><<<grid, 256, smem, g_hb.stream>>>(p);                                           \
+  } while (0)
+      if (a_kfast && b_kfast) GEMM8_LAUNCH(true, true);
+      else if (a_kfast) GEMM8_LAUNCH(true, false);
+      else if (b_kfast) GEMM8_LAUNCH(false, true);
+      else GEMM8_LAUNCH(false, false);
+#undef GEMM8_LAUNCH
+      HB_LAUNCHED();
+      if (splits > 1 && !serial) {
+        int64_t n = M * N;
+        gemm_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, g_hb.stream>>>(p.C, C, n, splits);
+        HB_LAUNCHED();
+      }
+      *done = 1;
+      return HB_OK;
+    }
+  }
   int chunks = (int)((K + BK - 1) / BK);
   int splits = 1;
   int64_t tiles = (int64_t)gm * gn;
