@@ -250,6 +250,26 @@ def test_matmul_family(dev, oracle, dtype):
     close(dev.to_numpy(lit(dev, dev.sconcrete(a), dev.sconcrete(b))), lit(oracle, a, b), dtype, scale=50)
 
 
+@pytest.mark.parametrize("shape", [(1024, 320, 1200),    # eight-warp kernel, one K slice, ragged N (304 tiles)
+                                   (512, 512, 1024),     # one tile per SM: two K slices accumulated serially into C
+                                   (500, 518, 1001),     # the same with ragged edges and an odd row stride of C
+                                   (100, 4100, 200),     # deep K over 8 tiles: many slices + fixed-order reduce
+                                   (512, 1024, 512)])    # four-warp kernel, split-K across CTAs
+def test_dmma_gemm_variants_and_determinism(dev, shape):
+    m, k, n = shape
+    rng = np.random.default_rng(91)
+    a, b = rnd(rng, (m, k)), rnd(rng, (k, n))
+    ref = a @ b
+    for ta in (False, True):
+        for tb in (False, True):
+            A = dev.stranspose([1, 0], dev.sconcrete(a.T.copy())) if ta else dev.sconcrete(a)
+            B = dev.stranspose([1, 0], dev.sconcrete(b.T.copy())) if tb else dev.sconcrete(b)
+            got = dev.to_numpy(dev.smatmul2(A, B))
+            close(got, ref, np.float64, scale=k)
+            for _ in range(3):       # K slices are combined in a fixed order: bit-identical from run to run
+                assert np.array_equal(dev.to_numpy(dev.smatmul2(A, B)), got)
+
+
 def test_argmax_argmin(dev, oracle):
     rng = np.random.default_rng(10)
     a = rng.integers(0, 4, (5, 6, 9)).astype(np.float64)     # many ties: first extremum wins
