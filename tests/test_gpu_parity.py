@@ -494,7 +494,10 @@ def test_fused_relu_pool(dev, oracle, dtype, shape, ks):
                                       ((4, 2, 9, 30, 6, 3, 2), 2),
                                       # warp-autonomous one-channel kernels (conv_strip.cu): widths 26 / 28, odd item counts
                                       ((5, 1, 9, 28, 26, 3, 4), 2), ((6, 1, 8, 4, 28, 2, 2), 2), ((131, 1, 16, 28, 28, 5, 5), 2),
-                                      ((3, 1, 5, 6, 28, 1, 1), 2)])
+                                      ((3, 1, 5, 6, 28, 1, 1), 2),
+                                      # ... with several groups of 16 output channels per strip
+                                      ((21, 1, 64, 28, 28, 3, 3), 2), ((7, 1, 32, 28, 28, 5, 5), 2), ((5, 1, 24, 10, 26, 2, 4), 2),
+                                      ((4, 1, 40, 28, 28, 5, 5), 2), ((150, 1, 17, 28, 28, 3, 3), 2)])
 def test_fused_conv_layer(dev, oracle, dtype, shape, ks):
     """hb_conv_relu_pool_fwd/bwd (a whole convMnistLayerS as one node): the fused
     DMMA epilogue / pooled-cotangent dKrn path and its unfused fallbacks agree
