@@ -28,6 +28,7 @@
 // persistent (grid = #SMs), two cp.async stages, one CTA per SM (up to 227 KB).
 #include "common.cuh"
 #include <algorithm>
+#include <cuda.h>  // CUtensorMap (the encoder is resolved through cudaGetDriverEntryPoint, libcuda is not linked)
 
 namespace {
 
@@ -50,6 +51,38 @@ __device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_grou
 template <int N>
 __device__ __forceinline__ void cp_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+// ---- TMA + mbarrier (sm_90+): one thread hands a whole [NI][CC][TR][RS] box of the input tensor to the
+// copy engine; rows and columns outside the image, channels beyond P and images beyond N arrive as zeros
+// (out-of-bounds fill), so the zero padding of conv2dPreservingS costs no instruction at all
+__device__ __forceinline__ void mbar_init(void *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(void *bar, int bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void *bar, int parity) {
+  unsigned done = 0;
+  while (!done) {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.b32 %0, 1, 0, p; }\n"
+                 : "=r"(done)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+  }
+}
+__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *tm, void *bar, int x, int y, int c, int n) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n" ::"r"(
+          smem_u32(dst)),
+      "l"(tm), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(c), "r"(n)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, int bytes, void *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
 
 // Geometry of one staged input tile: NI images x TR rows x RS columns per
@@ -138,6 +171,9 @@ __device__ __forceinline__ void load_linear(double *dst, const double *__restric
 
 // ===================================================== spatial (fwd / dInp)
 struct SpP {
+  alignas(64) CUtensorMap tmap;  // input [N][P][H][W], box [NI][CC][TR][RS] (tma != 0)
+  int tma, mbar;                 // TMA staging; offset (doubles) of the two stage mbarriers
+  int xs;                        // TMA boxes start on a 16-byte boundary: tile column 0 is input column ox - xs
   const double *in, *wp;
   double *out;
   TileGeo g;
@@ -268,13 +304,19 @@ __device__ __forceinline__ void sp_stage_chan(double (&acc)[MF][NQ][2], const in
 
 template <int WM, int WN, int MF, int NQ, bool TAPK, int MINB, bool POOL>
 __global__ void __launch_bounds__(kThreads, MINB) conv_sp_kernel(const __grid_constant__ SpP p) {
-  extern __shared__ __align__(16) double smem[];
+  extern __shared__ __align__(128) double smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wm = warp % WM, wn = warp / WM;
   const int fr = lane >> 2, fk = lane & 3;
   const TileGeo &g = p.g;
+  unsigned long long *mbar = reinterpret_cast<unsigned long long *>(smem + p.mbar);  // [2], TMA staging only
 
   for (int i = tid; i < 2 * p.stage_doubles; i += kThreads) smem[i] = 0.0;
+  if (!TAPK && p.tma && tid == 0) {
+    mbar_init(mbar, 1);
+    mbar_init(mbar + 1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
   __syncthreads();
 
   const int RW = g.R * g.W, npos = g.NI * RW, HW = g.H * g.W;
@@ -302,7 +344,7 @@ __global__ void __launch_bounds__(kThreads, MINB) conv_sp_kernel(const __grid_co
     if (pidx < npos) {
       int img = pidx / RW, rem = pidx - img * RW;
       int y = rem / g.W, x = rem - y * g.W;
-      off = img * g.IS + y * g.RS + x;
+      off = img * g.IS + y * g.RS + x + p.xs;
       o = img * p.Q * HW + y * g.W + x;
       iy = (img << 16) | y;
     }
@@ -336,9 +378,18 @@ __global__ void __launch_bounds__(kThreads, MINB) conv_sp_kernel(const __grid_co
   int is_it = blockIdx.x, cs_it = blockIdx.x;
   auto issue = [&](int t) {
     double *st = smem + (t & 1) * p.stage_doubles;
-    load_in_tile(st, p.in, g, p.CC, is_ch * p.CC, p.P, is_n0, p.N, is_y0, p.sn, p.sp, tid, cw, iw);
-    if (!p.wfix) load_linear(st + p.in_doubles, wbase + (int64_t)is_ch * p.CC * p.WCS, p.CC * p.WCS, tid);
-    cp_commit();
+    if (!TAPK && p.tma) {
+      if (tid == 0) {  // one thread, a handful of instructions: the copy engine generates every address
+        const int wbytes = p.wfix ? 0 : p.CC * p.WCS * 8;
+        mbar_expect_tx(mbar + (t & 1), p.in_doubles * 8 + wbytes);
+        tma_load_4d(st, &p.tmap, mbar + (t & 1), g.ox - p.xs, is_y0 + g.oy, is_ch * p.CC, is_n0);
+        if (wbytes) bulk_load(st + p.in_doubles, wbase + (int64_t)is_ch * p.CC * p.WCS, wbytes, mbar + (t & 1));
+      }
+    } else {
+      load_in_tile(st, p.in, g, p.CC, is_ch * p.CC, p.P, is_n0, p.N, is_y0, p.sn, p.sp, tid, cw, iw);
+      if (!p.wfix) load_linear(st + p.in_doubles, wbase + (int64_t)is_ch * p.CC * p.WCS, p.CC * p.WCS, tid);
+      cp_commit();
+    }
     if (++is_ch == p.NCH) {
       is_ch = 0;
       is_it += gridDim.x;
@@ -350,15 +401,26 @@ __global__ void __launch_bounds__(kThreads, MINB) conv_sp_kernel(const __grid_co
 
   // weights of all channel chunks staged once per CTA (joins the first commit group)
   if (p.wfix && T > 0) load_linear(smem + p.wfix, wbase, p.Ppad * p.WCS, tid);
+  if (!TAPK && p.tma) {  // the resident weights are the only cp.async traffic of the TMA path
+    cp_commit();
+    cp_wait<0>();
+    __syncthreads();
+  }
   if (T > 0) issue(0);
   for (int t = 0; t < T; t++) {
-    if (t + 1 < T) {
-      issue(t + 1);
-      cp_wait<1>();
+    if (!TAPK && p.tma) {
+      // stage (t + 1) & 1 was last read in iteration t - 1; every warp has passed that iteration's barrier
+      if (t + 1 < T) issue(t + 1);
+      mbar_wait(mbar + (t & 1), (t >> 1) & 1);
     } else {
-      cp_wait<0>();
+      if (t + 1 < T) {
+        issue(t + 1);
+        cp_wait<1>();
+      } else {
+        cp_wait<0>();
+      }
+      __syncthreads();
     }
-    __syncthreads();
     const char *Sb = reinterpret_cast<const char *>(smem + (t & 1) * p.stage_doubles);
     const char *Wl = (p.wfix ? reinterpret_cast<const char *>(smem + p.wfix + cs_ch * p.CC * p.WCS) : Sb + p.in_doubles * 8) + wlane;
     // predicated-off DMMAs still occupy the tensor pipe (ncu: dmma cycles =
@@ -794,6 +856,26 @@ __global__ void __launch_bounds__(1024) dk_reduce_kernel(const double *__restric
   }
 }
 
+typedef CUresult (*hb_tmap_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                      const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+// cuTensorMapEncodeTiled through the runtime (no libcuda link); NULL when unavailable or HB_CONV_TMA=0
+static hb_tmap_encode_fn tmap_encoder() {
+  static hb_tmap_encode_fn fn = [] {
+    const char *e = getenv("HB_CONV_TMA");
+    if (e && e[0] == '0') return (hb_tmap_encode_fn) nullptr;
+    void *f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      f = nullptr;
+    }
+    return (hb_tmap_encode_fn)f;
+  }();
+  return fn;
+}
+
 static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 // smallest s >= n with s = 4 (mod 8)
 static inline int stride4mod8(int n) {
@@ -934,18 +1016,56 @@ int hb_conv_sp_dmma(const hb_array *K, const hb_array *in, hb_array *out, int fl
   g.bands = (H + g.R - 1) / g.R;
   g.nblocks = (N + g.NI - 1) / g.NI;
   p.items = g.nblocks * g.bands;
-  p.in_doubles = CC * g.CS;
-  // all chunks' weights once per CTA when that fits the budget the tile was chosen for
-  const int budget_used = ctas == 2 ? kSmemMax / 2 - 1024 : kSmemMax;
-  int pool_extra = 0;
-  if (pf) pool_extra = (p.QT < 8 ? p.QT : 8) * pool_stride(g.NI * g.R * W) * 8 + (g.NI * g.R * W / 4) * 16 + 64;
-  const bool wfixed = (2 * round_up(p.in_doubles, 2) + round_up(p.Ppad * p.WCS, 2)) * 8 + pool_extra <= budget_used;
-  p.stage_doubles = round_up(p.in_doubles + (wfixed ? 0 : CC * p.WCS), 2);
-  p.wfix = wfixed ? 2 * p.stage_doubles : 0;
-  p.tail = 2 * p.stage_doubles + (wfixed ? round_up(p.Ppad * p.WCS, 2) : 0);
   p.N = N; p.P = P; p.Q = Q;
   p.sn = in->strides[0]; p.sp = in->strides[1];
   p.in = (const double *)hb_data(in);
+  const int budget_used = ctas == 2 ? kSmemMax / 2 - 1024 : kSmemMax;
+  int pool_extra = 0;
+  if (pf) pool_extra = (p.QT < 8 ? p.QT : 8) * pool_stride(g.NI * g.R * W) * 8 + (g.NI * g.R * W / 4) * 16 + 64;
+  // stage layout; all chunks' weights once per CTA when that fits the budget the tile was chosen for
+  auto layout = [&](int in_doubles, int align) {
+    p.in_doubles = in_doubles;
+    const bool wfixed =
+        (2 * round_up(in_doubles, align) + round_up(p.Ppad * p.WCS, align)) * 8 + pool_extra + 64 <= budget_used;
+    p.stage_doubles = round_up(in_doubles + (wfixed ? 0 : CC * p.WCS), align);
+    p.wfix = wfixed ? 2 * p.stage_doubles : 0;
+    p.tail = 2 * p.stage_doubles + (wfixed ? round_up(p.Ppad * p.WCS, align) : 0);
+    return p.tail * 8 + pool_extra + 64;
+  };
+  // TMA staging (channel-k mode): the tile is the dense box [NI][CC][TR][RS] the copy engine writes, so
+  // the channel stride is TR * RS; the box is widened by up to 6 columns until that is = 4 (mod 8)
+  // doubles (conflict-free fragment loads); shapes where no width does it keep the cp.async loader
+  p.tma = 0;
+  if (!tapk && tmap_encoder() && W % 2 == 0 && ((uintptr_t)p.in & 15) == 0 && p.sn == (int64_t)P * H * W &&
+      p.sp == (int64_t)H * W) {
+    // an odd first column (dInp with an even kernel width) would start the box off a 16-byte boundary,
+    // which the copy engine rejects: start one column further left and shift the fragment reads instead
+    const int xs = g.ox & 1, rs_min = round_up(W + halo_w + xs, 2);
+    int rs_t = 0;
+    for (int add = 0; add <= 6 && !rs_t; add += 2)
+      if ((g.TR * (rs_min + add)) % 8 == 4) rs_t = rs_min + add;
+    if (rs_t && rs_t <= 256 && g.TR <= 256 && CC <= 256 && g.NI <= 256) {
+      const int rs_old = g.RS, cs_old = g.CS, is_old = g.IS;
+      g.RS = rs_t; g.CS = g.TR * rs_t; g.IS = CC * g.CS;
+      if (layout(g.NI * g.IS, 16) <= budget_used) {
+        CUtensorMap tm;
+        cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)P, (cuuint64_t)N};
+        cuuint64_t strides[3] = {(cuuint64_t)W * 8, (cuuint64_t)H * W * 8, (cuuint64_t)P * H * W * 8};
+        cuuint32_t box[4] = {(cuuint32_t)rs_t, (cuuint32_t)g.TR, (cuuint32_t)CC, (cuuint32_t)g.NI};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        CUresult r = tmap_encoder()(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, (void *)p.in, dims, strides, box, es,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                    CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r == CUDA_SUCCESS) {
+          p.tmap = tm;
+          p.tma = 1;
+          p.xs = xs;
+        }
+      }
+      if (!p.tma) { g.RS = rs_old; g.CS = cs_old; g.IS = is_old; }
+    }
+  }
+  if (!p.tma) layout(CC * g.CS, 2);
   g.vec = (W % 2 == 0) && (g.ox % 2 == 0) && (((uintptr_t)p.in & 15) == 0) && (p.sn % 2 == 0) && (p.sp % 2 == 0);
   set_pieces(g);
   {
@@ -1001,6 +1121,9 @@ int hb_conv_sp_dmma(const hb_array *K, const hb_array *in, hb_array *out, int fl
   } else {
     p.out = (double *)hb_data(out);
   }
+  smem_bytes = round_up(smem_bytes, 8);
+  p.mbar = smem_bytes / 8;
+  smem_bytes += 16;
   if (smem_bytes > kSmemMax) return HB_OK;
   // packed weights in scratch
   int64_t wn = (int64_t)nqt * p.Ppad * p.WCS;
