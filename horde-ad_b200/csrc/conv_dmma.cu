@@ -537,6 +537,8 @@ __global__ void __launch_bounds__(kThreads, MINB) conv_sp_kernel(const __grid_co
 
 // ================================================================== dKrn
 struct DkP {
+  alignas(64) CUtensorMap tmap;  // A [N][Ci][H][W], box [1][CC][TR][RS] (tma != 0)
+  int tma, mbar;                 // TMA staging; offset (doubles) of the two stage mbarriers
   const double *A, *dB;
   double *part;  // [split][Co][Ci][KH][KW]
   TileGeo g;
@@ -587,7 +589,7 @@ __device__ __forceinline__ void dk_stage(double (&acc)[MO][kNP][2], const int (&
 
 template <int WM, int MO, bool TAPW>
 __global__ void __launch_bounds__(kThreads, 2) conv_dk_kernel(const __grid_constant__ DkP p) {
-  extern __shared__ __align__(16) double smem[];
+  extern __shared__ __align__(128) double smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wm = warp % WM, wn = (warp / WM) % p.WN, wk = warp / (WM * p.WN);
   const int fr = lane >> 2, fk = lane & 3;
@@ -599,6 +601,12 @@ __global__ void __launch_bounds__(kThreads, 2) conv_dk_kernel(const __grid_const
   int *lutp = lut + p.npos4;  // pooled index -> first position of its window inside one image band
 
   for (int i = tid; i < 2 * p.stage_doubles + (p.pooled ? otile_rows * p.PS : 0); i += kThreads) smem[i] = 0.0;
+  unsigned long long *mbar = reinterpret_cast<unsigned long long *>(smem + p.mbar);  // [2], TMA staging only
+  if (!TAPW && p.tma && tid == 0) {
+    mbar_init(mbar, 1);
+    mbar_init(mbar + 1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
   const int RW = g.R * g.W, npos = g.NI * RW;
   if (p.pooled) {
     const int Wo = g.W >> 1;
@@ -655,8 +663,18 @@ __global__ void __launch_bounds__(kThreads, 2) conv_dk_kernel(const __grid_const
     int band = it / g.nblocks, nblk = it - band * g.nblocks;
     int n0 = nblk * g.NI, y0 = band * g.R;
     double *st = smem + (t & 1) * p.stage_doubles;
-    load_in_tile(st, p.A, g, p.CC, c0, p.Ci, n0, p.N, y0, p.a_sn, p.a_sc, tid, cw, iw);
     double *db = st + p.a_doubles;
+    if (!TAPW && p.tma) {
+      // one thread: the A box (zero fill = the padding) and one contiguous row block of dB per output channel
+      if (tid == 0) {
+        mbar_expect_tx(mbar + (t & 1), p.a_doubles * 8 + co * RW * 8);
+        tma_load_4d(st, &p.tmap, mbar + (t & 1), 0, y0, c0, n0);
+        const double *s0 = p.dB + n0 * p.b_sn + o_tile * p.b_so + (int64_t)y0 * g.W;
+        for (int o = 0; o < co; o++) bulk_load(db + o * p.PS, s0 + o * p.b_so, RW * 8, mbar + (t & 1));
+      }
+      return;
+    }
+    load_in_tile(st, p.A, g, p.CC, c0, p.Ci, n0, p.N, y0, p.a_sn, p.a_sc, tid, cw, iw);
     int rows_ok = g.H - y0 < g.R ? g.H - y0 : g.R;
     const int planes = co * g.NI;
     if (p.pooled) {
@@ -708,13 +726,18 @@ __global__ void __launch_bounds__(kThreads, 2) conv_dk_kernel(const __grid_const
 
   if (T > 0) issue(0);
   for (int t = 0; t < T; t++) {
-    if (t + 1 < T) {
-      issue(t + 1);
-      cp_wait<1>();
+    if (!TAPW && p.tma) {
+      if (t + 1 < T) issue(t + 1);
+      mbar_wait(mbar + (t & 1), (t >> 1) & 1);
     } else {
-      cp_wait<0>();
+      if (t + 1 < T) {
+        issue(t + 1);
+        cp_wait<1>();
+      } else {
+        cp_wait<0>();
+      }
+      __syncthreads();
     }
-    __syncthreads();
     if (p.pooled) {
       // expand the staged pooled cotangent of stage t into the dB tile:
       // window position `code & 0x7f` receives dy where the relu was active
@@ -1283,7 +1306,42 @@ int hb_conv_dk_dmma(const hb_array *A, const hb_array *dB, const hb_array *code,
     p.dyvec = (((H / 2) * (W / 2)) % 2 == 0) && (p.PW % 2 == 0) && (((uintptr_t)p.dy & 15) == 0);
   }
   p.skip = !tapw && NI == 1 && g_hb.conv_skip_padding;
-  int smem_bytes = smem_need();
+  // TMA staging (see hb_conv_sp_dmma): the A box by one tensor copy, the dB rows of each output channel by
+  // one bulk copy; whole bands only (a ragged last band needs zeroed rows), unpooled cotangent only
+  p.tma = 0;
+  if (!tapw && !pooled && NI == 1 && tmap_encoder() && H % g.R == 0 && p.dbvec && ((uintptr_t)p.A & 15) == 0 &&
+      p.a_sn == (int64_t)Ci * H * W && p.a_sc == (int64_t)H * W) {
+    int rs_t = 0;
+    for (int add = 0; add <= 6 && !rs_t; add += 2)
+      if ((g.TR * (g.RS + add)) % 8 == 4) rs_t = g.RS + add;
+    if (rs_t && rs_t <= 256 && g.TR <= 256 && CC <= 256) {
+      g.RS = rs_t; g.IS = g.TR * rs_t; g.CS = g.IS;
+      p.a_doubles = round_up(CC * g.CS, 16);
+      p.stage_doubles = round_up(p.a_doubles + otile * p.PS, 16);
+      if (smem_need() + 32 <= (ctas == 2 ? kSmemMax / 2 - 1024 : kSmemMax)) {
+        CUtensorMap tm;
+        cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Ci, (cuuint64_t)N};
+        cuuint64_t strides[3] = {(cuuint64_t)W * 8, (cuuint64_t)H * W * 8, (cuuint64_t)Ci * H * W * 8};
+        cuuint32_t box[4] = {(cuuint32_t)rs_t, (cuuint32_t)g.TR, (cuuint32_t)CC, 1u};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        CUresult r = tmap_encoder()(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, (void *)p.A, dims, strides, box, es,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                    CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r == CUDA_SUCCESS) {
+          p.tmap = tm;
+          p.tma = 1;
+        }
+      }
+      if (!p.tma) {  // back to the cp.async layout
+        g.RS = round_up(W + halo_w, 2);
+        fits(R, kSmemMax);
+        set_pieces(g);
+      }
+    }
+  }
+  int smem_bytes = round_up(smem_need(), 8);
+  p.mbar = smem_bytes / 8;
+  smem_bytes += 16;
   if (smem_bytes < red_bytes) smem_bytes = red_bytes;
   int splits = g_hb.sm_count * ctas / (ncc * not_);
   if (splits < 1) splits = 1;
