@@ -81,7 +81,8 @@ __device__ __forceinline__ void load_strip(double *dst, const StripP &p, int n, 
 }
 
 // ------------------------------------------------------------------ forward
-template <int NQ>
+// MULTI = false: one group of output channels (weight stride and trip count are compile-time constants)
+template <int NQ, bool MULTI>
 __global__ void __launch_bounds__(NTHR, 1) strip_fwd_kernel(const __grid_constant__ StripP p) {
   extern __shared__ __align__(16) double smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -106,7 +107,7 @@ __global__ void __launch_bounds__(NTHR, 1) strip_fwd_kernel(const __grid_constan
     aoff[i] = (yy * kRS + x) * 8;
   }
   constexpr int QT = NQ * 8;
-  const int TS = p.TS;
+  const int TS = MULTI ? p.TS : QT + 4, QG = MULTI ? p.QG : 1;
   const int64_t gw = (int64_t)blockIdx.x * WPB + warp, nw = (int64_t)gridDim.x * WPB;
   const int ng = p.NT >> 2;
   const int HoWo = Ho * Wo;
@@ -132,7 +133,7 @@ __global__ void __launch_bounds__(NTHR, 1) strip_fwd_kernel(const __grid_constan
     __syncwarp();
     const char *Sb = reinterpret_cast<const char *>(mine + buf * p.SD);
     // the staged strip serves every group of 16 output channels in turn
-    for (int qg = 0; qg < p.QG; qg++) {
+    for (int qg = 0; qg < QG; qg++) {
       double acc[MF][NQ][2];
 #pragma unroll
       for (int i = 0; i < MF; i++)
@@ -447,13 +448,15 @@ int hb_conv_strip_fwd(const hb_array *K, const hb_array *bias, const hb_array *A
   if (smem > 227 * 1024) return HB_OK;
   int64_t wneed = ((int64_t)p.items + WPB - 1) / WPB;
   int grid = (int)(wneed < g_hb.sm_count ? wneed : g_hb.sm_count);
-  if (NQ == 1) {
-    HB_CUDA(cudaFuncSetAttribute(strip_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    strip_fwd_kernel<1><<<grid, NTHR, smem, g_hb.stream>>>(p);
-  } else {
-    HB_CUDA(cudaFuncSetAttribute(strip_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    strip_fwd_kernel<2><<<grid, NTHR, smem, g_hb.stream>>>(p);
-  }
+#define SFW_LAUNCH(NQ_, M_)                                                                                    \
+  do {                                                                                                        \
+    HB_CUDA(cudaFuncSetAttribute(strip_fwd_kernel<NQ_, M_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+    strip_fwd_kernel<NQ_, M_><<<grid, NTHR, smem, g_hb.stream>>>(p);                                         \
+  } while (0)
+  if (NQ == 1) SFW_LAUNCH(1, false);
+  else if (p.QG == 1) SFW_LAUNCH(2, false);
+  else SFW_LAUNCH(2, true);
+#undef SFW_LAUNCH
   HB_LAUNCHED();
   *done = 1;
   return HB_OK;
