@@ -4,6 +4,8 @@ Bar (BASELINE.json north_star): bit-exact for data movement, indexing and
 integer work; 1e-12 relative for Double, 1e-5 for Float floating point.
 Every test here needs a B200 (`-m gpu`); the library has no CPU fallback.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -411,6 +413,40 @@ def test_conv_non_finite_input_stays_local(dev, oracle):
     ref = oracle.conv2dPreserving(K, A)
     assert np.array_equal(np.isfinite(got), np.isfinite(ref))
     np.testing.assert_allclose(got[np.isfinite(ref)], ref[np.isfinite(ref)], rtol=1e-11, atol=1e-13)
+
+
+def test_conv_padding_taps_and_non_finite_weights():
+    """The DMMA kernels do not compute the taps that fall entirely into the zero padding.  That is
+    only observable with a non-finite WEIGHT: the reference's gather-then-multiply formulation turns
+    0 * Inf at a padded tap into NaN (the oracle does the same); HB_CONV_FULL_PADDING=1 computes every
+    tap and reproduces that pattern exactly.  (Own process: the switch is read by hb_init.)"""
+    import subprocess, sys, textwrap
+    code = textwrap.dedent("""
+        import numpy as np
+        from horde_ad_b200.device import DeviceBackend
+        from oracle.concrete import ConcreteBackend
+        dev, orc = DeviceBackend(0), ConcreteBackend()
+        rng = np.random.default_rng(3)
+        K, A = rng.uniform(-.5, .5, (16, 16, 5, 5)), rng.uniform(-.5, .5, (4, 16, 14, 14))
+        K[3, 2, 4, 1] = np.inf                                   # bottom tap row
+        got = dev.to_numpy(dev.conv2dPreserving(dev.sconcrete(K), dev.sconcrete(A)))
+        ref = orc.conv2dPreserving(K, A)
+        same_nan = np.array_equal(np.isnan(got), np.isnan(ref))
+        fin = np.isfinite(ref)
+        close = np.allclose(got[fin], ref[fin], rtol=1e-11, atol=1e-12)
+        extra_finite = int((np.isnan(ref) & ~np.isnan(got)).sum())
+        print("RESULT", int(same_nan), int(close), extra_finite, int(np.isnan(ref).sum()))
+    """)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    def run(env_extra):
+        env = dict(os.environ, PYTHONPATH=root, **env_extra)
+        out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300, cwd=root)
+        assert out.returncode == 0, out.stderr[-2000:]
+        return [int(x) for x in out.stdout.split("RESULT")[1].split()]
+    same_nan, close, extra, nnan = run({"HB_CONV_FULL_PADDING": "1"})
+    assert same_nan == 1 and close == 1 and nnan > 0           # every tap computed: the reference's NaN pattern
+    same_nan, close, extra, nnan = run({"HB_CONV_FULL_PADDING": "0"})
+    assert close == 1 and extra > 0 and extra < nnan            # default: finite wherever the Inf tap only met padding
 
 
 def test_conv_full_size_adjoint_property(dev):
