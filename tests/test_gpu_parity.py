@@ -272,6 +272,22 @@ def test_dmma_gemm_variants_and_determinism(dev, shape):
                 assert np.array_equal(dev.to_numpy(dev.smatmul2(A, B)), got)
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32, np.int8])
+def test_transposed_views_materialise_bit_exact(dev, dtype):
+    """hb_contiguous / reshape of transposed views (tiled shared-memory transpose fast path and the generic
+    iterator around it): ragged tile edges, trailing axes that collapse, ones that do not."""
+    rng = np.random.default_rng(77)
+    for shape in [(4096, 784), (33, 65), (32, 32), (100, 7), (5, 300), (1000, 3)]:
+        a = (rng.uniform(-100, 100, shape)).astype(dtype)
+        t = dev.stranspose([1, 0], dev.sconcrete(a))                       # [C, R] view with unit stride along axis 0
+        exact(dev.to_numpy(dev.sreshape([shape[1] * shape[0]], t)), np.ascontiguousarray(a.T).reshape(-1))
+    a = rng.uniform(-1, 1, (48, 4, 6, 40)).astype(dtype)                   # [N, c, h, w] -> view [w, N, c, h]: collapses
+    v = dev.stranspose([3, 0, 1, 2], dev.sconcrete(a))
+    exact(dev.to_numpy(dev.sreshape([40 * 48 * 24], v)), np.ascontiguousarray(np.transpose(a, (3, 0, 1, 2))).reshape(-1))
+    v = dev.stranspose([3, 1, 0, 2], dev.sconcrete(a))                     # does not collapse: generic path
+    exact(dev.to_numpy(dev.sreshape([40 * 48 * 24], v)), np.ascontiguousarray(np.transpose(a, (3, 1, 0, 2))).reshape(-1))
+
+
 def test_argmax_argmin(dev, oracle):
     rng = np.random.default_rng(10)
     a = rng.integers(0, 4, (5, 6, 9)).astype(np.float64)     # many ties: first extremum wins
