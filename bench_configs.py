@@ -238,7 +238,7 @@ def main():
     tstep = [0]
 
     def rnn_grad():
-        return ad.grad(dev, lambda T, *ps: mnist_rnn.rnnMnistLossFusedS(T, glyphs, labels, list(ps)), params)
+        return ad.grad(dev, lambda T, *ps: mnist_rnn.rnnMnistLossFusedS(T, glyphs, labels, list(ps), fused=True), params)
 
     def rnn_apply(grads):
         tstep[0] += 1

@@ -348,6 +348,18 @@ class ADBackend:
             return [dK, dbias, dA]
         return self._node(y, [K, bias, A], pb)
 
+    def tanh_affine(self, u, v, bias):
+        """The body of rnnMnistLayerS (MnistRnnShaped2.hs:55-69) as one node: tanh ((u + v) + bias
+        stretched over the batch); dz = (1 - y * y) * c is the cotangent of u and of v."""
+        B = self.B
+        u, v, bias = self.lift(u), self.lift(v), self.lift(bias)
+        y = B.tanh_affine_fwd(u.p, v.p, bias.p)
+
+        def pb(c):
+            dz, db = B.tanh_affine_bwd(y, c, want_bias=bias.d is not None)
+            return [dz, dz, db]
+        return self._node(y, [u, v, bias], pb)
+
     def custom_unary(self, t, primal, vjp):
         """tD with a hand-written dual part (e.g. logistic,
         CommonRankedOps.hs:55-63): primal(B, x) and vjp(B, x, y, c)."""
@@ -408,6 +420,9 @@ def grad(base, f: Callable, inputs: Sequence, dt=None):
         input_ix = {n.id: i for i, n in enumerate(in_nodes)}
         cot = {out.d.id: dt}
         nodes = {out.d.id: out.d}
+        # cotangents that this sweep itself created by an accumulation: only those may be updated in
+        # place (a pullback may hand the SAME array to several parents, e.g. `add` returns [c, c])
+        owned = set()
         heap = [-out.d.id]
         while heap:
             nid = -heapq.heappop(heap)
@@ -421,7 +436,11 @@ def grad(base, f: Callable, inputs: Sequence, dt=None):
                 if parent is None or pc is None:
                     continue
                 if parent.id in cot:
-                    cot[parent.id] = base.add_accumulate(cot[parent.id], pc)
+                    if parent.id in owned:
+                        cot[parent.id] = base.add_accumulate(cot[parent.id], pc)
+                    else:
+                        cot[parent.id] = base.binary("add", cot[parent.id], pc)
+                        owned.add(parent.id)
                 else:
                     cot[parent.id] = pc
                     nodes[parent.id] = parent
@@ -616,6 +635,11 @@ class FwdBackend:
             a = B.ix_tbl(am, ix)
             return [ix[0], ix[1], stride * ix[2] + a.quotH(ksize), stride * ix[3] + a.remH(ksize)]
         return Dual(y, B.sgather([N, Cc, Ho, Wo], x.t, f, 4))
+
+    def tanh_affine(self, u, v, bias):
+        batch = self.shape(u)[1]
+        return self.unary("tanh", self.binary("add", self.binary("add", u, v),
+                                              self.stranspose([1, 0], self.sreplicate(batch, bias))))
 
     def conv_relu_pool(self, K, bias, A, ksize):
         N, _, H, W = self.shape(A)

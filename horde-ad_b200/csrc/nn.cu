@@ -590,3 +590,112 @@ extern "C" int hb_mnist_batch_into(const hb_array *pixels, const hb_array *label
   HB_LAUNCHED();
   return HB_OK;
 }
+
+// ------------------------------------------------- recurrent layer body
+// rnnMnistLayerS (example/MnistRnnShaped2.hs:55-69) after its two matmuls:
+//   y = tanh ((u + v) + stretched bias),   u = wX x, v = wS s  : [width, batch]
+// one pass instead of three maps and a broadcast view, and its adjoint
+//   dz = (1 - y * y) * c  (the dual of tanh, same association as the generic rule),
+//   dbias[i] = sum_j dz[i, j]
+// one pass with the row sums reduced in a fixed order (deterministic).
+template <typename T>
+__global__ void __launch_bounds__(256)
+    hb_tanh_affine_fwd_kernel(const T *__restrict__ u, const T *__restrict__ v, const T *__restrict__ bias, int64_t rows,
+                              int64_t cols, T *__restrict__ y) {
+  const int64_t n = rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    T b = bias ? bias[i / cols] : T(0);
+    y[i] = tanh((u[i] + v[i]) + b);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+    hb_tanh_affine_bwd_kernel(const T *__restrict__ y, const T *__restrict__ c, int64_t cols, T *__restrict__ dz,
+                              T *__restrict__ dbias) {
+  __shared__ T red[256];
+  const int64_t row = blockIdx.x;
+  const T *yr = y + row * cols, *cr = c + row * cols;
+  T *dr = dz + row * cols;
+  T s = T(0);
+  for (int64_t j = threadIdx.x; j < cols; j += 256) {
+    T yy = yr[j];
+    T d = (T(1) - yy * yy) * cr[j];
+    dr[j] = d;
+    s += d;
+  }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && dbias) dbias[row] = red[0];
+}
+
+extern "C" int hb_tanh_affine_fwd(const hb_array *u, const hb_array *v, const hb_array *bias, hb_array **y_out) {
+  hb_prof_scope prof_("tanh_affine_fwd", u);
+  HB_CHECK_INIT();
+  HB_REQUIRE(u && v && y_out, "null argument");
+  HB_REQUIRE(u->rank == 2 && hb_same_shape(u, v) && u->dt == v->dt && hb_is_float(u->dt),
+             "tanh_affine: two floating [width, batch] operands of one shape required");
+  HB_REQUIRE(!bias || (bias->rank == 1 && bias->shape[0] == u->shape[0] && bias->dt == u->dt),
+             "tanh_affine: bias must be [width] of the operands' type");
+  const hb_array *uc = u, *vc = v, *bc = bias;
+  hb_array *t1 = nullptr, *t2 = nullptr, *t3 = nullptr, *y = nullptr;
+  int st = HB_OK;
+  if (!hb_contig(u)) { st = hb_contiguous(u, &t1); uc = t1; }
+  if (st == HB_OK && !hb_contig(v)) { st = hb_contiguous(v, &t2); vc = t2; }
+  if (st == HB_OK && bias && !hb_contig(bias)) { st = hb_contiguous(bias, &t3); bc = t3; }
+  if (st == HB_OK) st = hb_new_array(u->dt, 2, u->shape, &y);
+  const int64_t rows = u->shape[0], cols = u->shape[1], n = rows * cols;
+  if (st == HB_OK && n > 0) {
+    const int blocks = hb_blocks_for(n, 256, g_hb.sm_count * 16);
+    if (u->dt == HB_F64)
+      hb_tanh_affine_fwd_kernel<double><<<blocks, 256, 0, g_hb.stream>>>(
+          (const double *)hb_data(uc), (const double *)hb_data(vc), bc ? (const double *)hb_data(bc) : nullptr, rows, cols,
+          (double *)hb_data(y));
+    else
+      hb_tanh_affine_fwd_kernel<float><<<blocks, 256, 0, g_hb.stream>>>(
+          (const float *)hb_data(uc), (const float *)hb_data(vc), bc ? (const float *)hb_data(bc) : nullptr, rows, cols,
+          (float *)hb_data(y));
+    HB_LAUNCHED();
+  }
+  hb_release(t1); hb_release(t2); hb_release(t3);
+  if (st != HB_OK) { hb_release(y); return st; }
+  *y_out = y;
+  return HB_OK;
+}
+
+extern "C" int hb_tanh_affine_bwd(const hb_array *y, const hb_array *c, hb_array **dz_out, hb_array **dbias_out) {
+  hb_prof_scope prof_("tanh_affine_bwd", y);
+  HB_CHECK_INIT();
+  HB_REQUIRE(y && c && dz_out, "null argument");
+  HB_REQUIRE(y->rank == 2 && hb_same_shape(y, c) && y->dt == c->dt && hb_is_float(y->dt),
+             "tanh_affine_bwd: two floating [width, batch] operands of one shape required");
+  HB_REQUIRE(y->shape[0] < (1ll << 31), "tanh_affine_bwd: too many rows");
+  const hb_array *yc = y, *cc = c;
+  hb_array *t1 = nullptr, *t2 = nullptr, *dz = nullptr, *db = nullptr;
+  int st = HB_OK;
+  if (!hb_contig(y)) { st = hb_contiguous(y, &t1); yc = t1; }
+  if (st == HB_OK && !hb_contig(c)) { st = hb_contiguous(c, &t2); cc = t2; }
+  if (st == HB_OK) st = hb_new_array(y->dt, 2, y->shape, &dz);
+  if (st == HB_OK && dbias_out) st = hb_zeros(y->dt, 1, y->shape, &db);
+  const int64_t rows = y->shape[0], cols = y->shape[1];
+  if (st == HB_OK && rows > 0 && cols > 0) {
+    if (y->dt == HB_F64)
+      hb_tanh_affine_bwd_kernel<double><<<(unsigned)rows, 256, 0, g_hb.stream>>>(
+          (const double *)hb_data(yc), (const double *)hb_data(cc), cols, (double *)hb_data(dz),
+          db ? (double *)hb_data(db) : nullptr);
+    else
+      hb_tanh_affine_bwd_kernel<float><<<(unsigned)rows, 256, 0, g_hb.stream>>>(
+          (const float *)hb_data(yc), (const float *)hb_data(cc), cols, (float *)hb_data(dz),
+          db ? (float *)hb_data(db) : nullptr);
+    HB_LAUNCHED();
+  }
+  hb_release(t1); hb_release(t2);
+  if (st != HB_OK) { hb_release(dz); hb_release(db); return st; }
+  *dz_out = dz;
+  if (dbias_out) *dbias_out = db;
+  return HB_OK;
+}

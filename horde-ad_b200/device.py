@@ -420,6 +420,17 @@ class DeviceBackend:
     def upload_into(self, dst: DeviceArray, host_ptr):
         call("hb_upload_into", dst.h, host_ptr)
 
+    def tanh_affine_fwd(self, u: DeviceArray, v: DeviceArray, bias) -> DeviceArray:
+        """tanh ((u + v) + bias stretched over the batch): the body of rnnMnistLayerS in one pass."""
+        p = _out()
+        call("hb_tanh_affine_fwd", u.h, v.h, bias.h if bias is not None else None, C.byref(p))
+        return _wrap(p)
+
+    def tanh_affine_bwd(self, y: DeviceArray, c: DeviceArray, want_bias=True):
+        dz, db = _out(), _out()
+        call("hb_tanh_affine_bwd", y.h, c.h, C.byref(dz), C.byref(db) if want_bias else None)
+        return _wrap(dz), (_wrap(db) if want_bias else None)
+
     def mnist_batch_into(self, pixels: DeviceArray, labels: DeviceArray, order, start: int,
                          glyphs_dst: DeviceArray, targets_dst: DeviceArray):
         """mkMnistDataBatchS on the device (MnistData.hs:134-171): glyph = pixel / 255, target = one-hot

@@ -23,26 +23,29 @@ def init_params(out_width, seed=44, rng_range=0.4, dtype=np.float64, h=28):
     return [(2 * rng_range * (rng.random(s) - 0.5)).astype(dtype) for s in param_shapes(out_width, h)]
 
 
-def rnnMnistLayerS(T, s, x, wX, wS, b):
-    """rnnMnistLayerS (MnistRnnShaped2.hs:55-69): tanh (wX x + wS s + b)."""
+def rnnMnistLayerS(T, s, x, wX, wS, b, fused=False):
+    """rnnMnistLayerS (MnistRnnShaped2.hs:55-69): tanh (wX x + wS s + b).  `fused`: the two adds, the
+    stretched bias and tanh as the one contraction-pass node `tanh_affine`."""
     batch = T.shape(x)[1]
+    if fused:
+        return T.tanh_affine(T.smatmul2(wX, x), T.smatmul2(wS, s), b)
     y = T.binary("add", T.binary("add", T.smatmul2(wX, x), T.smatmul2(wS, s)),
                  T.stranspose([1, 0], T.sreplicate(batch, b)))
     return T.unary("tanh", y)
 
 
-def rnnMnistTwoS(T, s, x, layers):
+def rnnMnistTwoS(T, s, x, layers, fused=False):
     """rnnMnistTwoS (MnistRnnShaped2.hs:73-99): state = sappend vec1 vec2."""
     (wX, wS, b), (wX2, wS2, b2) = layers
     out_width = T.shape(wS)[0]
     s1, s2 = T.sslice(0, out_width, s), T.sslice(out_width, out_width, s)
-    vec1 = rnnMnistLayerS(T, s1, x, wX, wS, b)
-    vec2 = rnnMnistLayerS(T, s2, vec1, wX2, wS2, b2)
+    vec1 = rnnMnistLayerS(T, s1, x, wX, wS, b, fused)
+    vec2 = rnnMnistLayerS(T, s2, vec1, wX2, wS2, b2, fused)
     s3 = T.sappend(vec1, vec2)
     return T.sslice(out_width, out_width, s3), s3
 
 
-def rnnMnistZeroS(T, xs, params):
+def rnnMnistZeroS(T, xs, params, fused=False):
     """rnnMnistZeroS (MnistRnnShaped2.hs:103-117): zero state, unrollLastS."""
     wX, wS, b, wX2, wS2, b2, w3, b3 = params
     out_width = T.shape(wS)[0]
@@ -50,14 +53,14 @@ def rnnMnistZeroS(T, xs, params):
     s = T.srepl([2 * out_width, batch], 0, T.dtype(wS))
     out = None
     for x in T.sunravelToList(xs):          # foldl' over the rows (:45-52)
-        out, s = rnnMnistTwoS(T, s, x, ((wX, wS, b), (wX2, wS2, b2)))
+        out, s = rnnMnistTwoS(T, s, x, ((wX, wS, b), (wX2, wS2, b2)), fused)
     return T.binary("add", T.smatmul2(w3, out), T.stranspose([1, 0], T.sreplicate(batch, b3)))
 
 
-def rnnMnistLossFusedS(T, glyphs, labels, params):
+def rnnMnistLossFusedS(T, glyphs, labels, params, fused=False):
     """rnnMnistLossFusedS (MnistRnnShaped2.hs:119-139): glyphs [batch, h, w],
     labels [batch, 10]."""
     batch = T.shape(glyphs)[0]
     xs = T.stranspose([2, 1, 0], glyphs)
-    result = rnnMnistZeroS(T, xs, params)
+    result = rnnMnistZeroS(T, xs, params, fused)
     return nn.lossSoftMaxCrossEntropyS(T, T.stranspose([1, 0], labels), result, scale=1.0 / batch)

@@ -403,6 +403,18 @@ int hb_conv_relu_pool_bwd(const hb_array *K, const hb_array *A,
 int hb_softmax_xent(const hb_array *logits, const hb_array *expected,
                     double scale, hb_array **loss_out, hb_array **dlogits_out);
 
+/* The body of rnnMnistLayerS (example/MnistRnnShaped2.hs:55-69) behind its two
+ * matmuls, as one node of the device contraction pass:
+ *   y = tanh ((u + v) + bias stretched over the batch),  u, v : [width, batch]
+ * (bias [width], may be NULL), and its adjoint
+ *   dz = (1 - y*y) * c,   dbias[i] = sum_j dz[i,j]   (dbias_out may be NULL)
+ * -- dz is the cotangent of both u and v.  Same association as the generic
+ * tanh rule; the row sums are reduced in a fixed order. */
+int hb_tanh_affine_fwd(const hb_array *u, const hb_array *v,
+                       const hb_array *bias, hb_array **y_out);
+int hb_tanh_affine_bwd(const hb_array *y, const hb_array *c, hb_array **dz_out,
+                       hb_array **dbias_out);
+
 /* Device twin of the MNIST input pipeline (example/MnistData.hs:134-171,
  * SURVEY.md 8f-3).  `pixels` [n,H,W] and `labels` [n] hold the raw IDX bytes
  * (dtype I8, read as unsigned) resident on the device; the minibatch

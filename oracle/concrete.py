@@ -417,6 +417,14 @@ class ConcreteBackend:
     def conv_relu_pool_fwd(self, K, bias, A, ksize):
         return self.relu_pool_fwd(self.conv2dPreserving(K, A), bias, ksize)
 
+    # rnnMnistLayerS behind its matmuls (module-level restatements below)
+    def tanh_affine_fwd(self, u, v, bias):
+        return tanh_affine_fwd(u, v, bias)
+
+    def tanh_affine_bwd(self, y, c, want_bias=True):
+        dz, db = tanh_affine_bwd(y, c)
+        return dz, (db if want_bias else None)
+
     def conv_relu_pool_bwd(self, K, A, dy, code, ksize, want_bias=True, want_dA=True):
         dpre, db = self.relu_pool_bwd(dy, code, ksize, A.shape[2], A.shape[3], want_bias)
         return (self.conv2d_dkrn(A, dpre, K.shape[2], K.shape[3]), db,
@@ -461,6 +469,21 @@ class ConcreteBackend:
         m[...] = T(beta1) * m + T(1 - beta1) * g
         v[...] = T(beta2) * v + T(1 - beta2) * (g * g)
         p[...] = p - (T(alphat) * m) / (np.sqrt(v) + T(epsilon))
+
+
+# ---------------------------------------------------------------- recurrent layer body
+def tanh_affine_fwd(u, v, bias):
+    """rnnMnistLayerS behind its matmuls (example/MnistRnnShaped2.hs:55-69): tanh ((u + v) + stretched bias)."""
+    z = u + v
+    if bias is not None:
+        z = z + np.asarray(bias)[:, None]
+    return np.tanh(z)
+
+
+def tanh_affine_bwd(y, c):
+    """Its adjoint: dz = (1 - y * y) * c (cotangent of both u and v), dbias = row sums of dz."""
+    dz = (1 - y * y) * c
+    return dz, dz.sum(axis=1)
 
 
 # ---------------------------------------------------------------- MNIST input pipeline

@@ -288,6 +288,23 @@ def test_transposed_views_materialise_bit_exact(dev, dtype):
     exact(dev.to_numpy(dev.sreshape([40 * 48 * 24], v)), np.ascontiguousarray(np.transpose(a, (3, 1, 0, 2))).reshape(-1))
 
 
+def test_shared_cotangents_are_not_updated_in_place(dev, oracle):
+    """`add` hands the same cotangent array to both operands; a later accumulation into one of them
+    must not change what the other one sees (in-place taddTarget only into arrays the sweep owns)."""
+    rng = np.random.default_rng(5)
+    x = rnd(rng, (6, 50))
+
+    def f(T, x):
+        a, b = T.unary("exp", x), T.unary("sin", x)
+        q = T.unary("cos", a)                      # a second consumer of a, created before the add
+        return T.ssum0(T.binary("add", T.binary("add", a, b), q))
+    _, (g,) = ad.grad(dev, f, [dev.sconcrete(x)])
+    _, (go,) = ad.grad(oracle, f, [x])
+    close(dev.to_numpy(g), go, np.float64, scale=10)
+    ref = np.exp(x) + np.cos(x) - np.sin(np.exp(x)) * np.exp(x)
+    close(dev.to_numpy(g), ref, np.float64, scale=10)
+
+
 def test_argmax_argmin(dev, oracle):
     rng = np.random.default_rng(10)
     a = rng.integers(0, 4, (5, 6, 9)).astype(np.float64)     # many ties: first extremum wins
@@ -667,25 +684,49 @@ def test_mnist_fcnn_gradient_vs_oracle(dev, oracle, q):
         np.testing.assert_allclose(a, b, rtol=tol * 100, atol=tol * 10)
 
 
-def test_mnist_rnn_gradient_vs_oracle(dev, oracle):
+@pytest.mark.parametrize("fused", [False, True])
+def test_mnist_rnn_gradient_vs_oracle(dev, oracle, fused):
     """MnistRnnShaped2 (BASELINE config 5) at a small width: 28 unrolled steps of
-    two tanh layers (smatmul2 on the DMMA GEMM), loss and the 8 gradient leaves."""
+    two tanh layers (smatmul2 on the DMMA GEMM), loss and the 8 gradient leaves;
+    `fused`: the layer body as the tanh_affine node, checked against the oracle's
+    UNFUSED program."""
     from horde_ad_b200 import mnist_rnn
     rng = np.random.Generator(np.random.Philox(12))
     batch, width = 9, 24
     glyphs, labels = rng.uniform(0, 1, (batch, 28, 28)), np.eye(10)[rng.integers(0, 10, batch)]
     params = mnist_rnn.init_params(width, rng_range=0.2)
 
-    def run(B):
+    def run(B, fused):
         ins = [B.sconcrete(p) for p in params]
         g, l = B.sconcrete(glyphs), B.sconcrete(labels)
-        val, grads = ad.grad(B, lambda T, *ps: mnist_rnn.rnnMnistLossFusedS(T, g, l, list(ps)), ins)
+        val, grads = ad.grad(B, lambda T, *ps: mnist_rnn.rnnMnistLossFusedS(T, g, l, list(ps), fused=fused), ins)
         return float(B.kfromS(val)), [B.to_numpy(x) for x in grads]
-    dl, dg = run(dev)
-    ol, og = run(oracle)
+    dl, dg = run(dev, fused)
+    ol, og = run(oracle, False)
     np.testing.assert_allclose(dl, ol, rtol=1e-12)
     for a, b in zip(dg, og):
         np.testing.assert_allclose(a, b, rtol=1e-9, atol=1e-13)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("shape", [(512, 1024), (7, 3), (1, 1), (33, 257), (5, 0)])
+def test_tanh_affine_node(dev, dtype, shape):
+    """hb_tanh_affine_fwd/bwd (the body of rnnMnistLayerS) against the oracle; the forward value is the
+    same sequence of roundings as the unfused maps up to tanh itself."""
+    from oracle import concrete as OC
+    rng = np.random.default_rng(21)
+    u, v, b, c = rnd(rng, shape, dtype), rnd(rng, shape, dtype), rnd(rng, shape[:1], dtype), rnd(rng, shape, dtype)
+    y = dev.tanh_affine_fwd(dev.sconcrete(u), dev.sconcrete(v), dev.sconcrete(b))
+    close(dev.to_numpy(y), OC.tanh_affine_fwd(u, v, b).astype(dtype), dtype, scale=4)
+    y0 = dev.tanh_affine_fwd(dev.stranspose([1, 0], dev.sconcrete(u.T.copy())), dev.sconcrete(v), None)
+    close(dev.to_numpy(y0), OC.tanh_affine_fwd(u, v, None).astype(dtype), dtype, scale=4)
+    yh = dev.to_numpy(y)
+    dz, db = dev.tanh_affine_bwd(y, dev.sconcrete(c))
+    rdz, rdb = OC.tanh_affine_bwd(yh.astype(np.float64), c.astype(np.float64))
+    close(dev.to_numpy(dz), rdz.astype(dtype), dtype, scale=4)
+    close(dev.to_numpy(db), rdb.astype(dtype), dtype, scale=4 * max(1, shape[1]))
+    dz2, none = dev.tanh_affine_bwd(y, dev.sconcrete(c), want_bias=False)
+    assert none is None and np.array_equal(dev.to_numpy(dz2), dev.to_numpy(dz))
 
 
 def test_folds_builds_and_cond(dev, oracle):
