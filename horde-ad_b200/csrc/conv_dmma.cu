@@ -667,7 +667,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_dk_kernel(const __grid_const
     if (!TAPW && p.tma) {
       // one thread: the A box (zero fill = the padding) and one contiguous row block of dB per output channel
       if (tid == 0) {
-        mbar_expect_tx(mbar + (t & 1), p.a_doubles * 8 + co * RW * 8);
+        mbar_expect_tx(mbar + (t & 1), p.CC * g.CS * 8 + co * RW * 8);  // the box [CC][TR][RS] + co row blocks
         tma_load_4d(st, &p.tmap, mbar + (t & 1), 0, y0, c0, n0);
         const double *s0 = p.dB + n0 * p.b_sn + o_tile * p.b_so + (int64_t)y0 * g.W;
         for (int o = 0; o < co; o++) bulk_load(db + o * p.PS, s0 + o * p.b_so, RW * 8, mbar + (t & 1));
