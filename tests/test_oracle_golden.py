@@ -198,3 +198,22 @@ def test_forward_reverse_duality_on_the_oracle(oracle):
     _, grads = ad.grad(oracle, g, fp)
     _, tan = ad.jvp(oracle, g, fp, fds)
     np.testing.assert_allclose(float(np.asarray(tan)), sum(float(np.sum(np.asarray(a) * d)) for a, d in zip(grads, fds)), rtol=1e-10)
+
+
+def test_tanh_affine_node_equals_the_unfused_layer_on_the_oracle(oracle):
+    """rnnMnistLayerS with its body as one node (tanh_affine) against the literal program, in reverse mode
+    (all 8 gradient leaves) and in forward mode (duality <grad f, ds> = jvp f ds)."""
+    from horde_ad_b200 import mnist_rnn
+    rng = np.random.Generator(np.random.Philox(31))
+    batch, width = 5, 12
+    glyphs, labels = rng.uniform(0, 1, (batch, 28, 28)), np.eye(10)[rng.integers(0, 10, batch)]
+    params = mnist_rnn.init_params(width, rng_range=0.2)
+    f = lambda fused: (lambda T, *ps: mnist_rnn.rnnMnistLossFusedS(T, glyphs, labels, list(ps), fused=fused))
+    v0, g0 = ad.grad(oracle, f(False), params)
+    v1, g1 = ad.grad(oracle, f(True), params)
+    np.testing.assert_allclose(v1, v0, rtol=1e-14)
+    for a, b in zip(g1, g0):
+        np.testing.assert_allclose(a, b, rtol=1e-12, atol=1e-16)
+    ds = [rng.uniform(-1, 1, p.shape) for p in params]
+    _, t = ad.jvp(oracle, f(True), params, ds)
+    np.testing.assert_allclose(float(t), sum(float(np.sum(g * d)) for g, d in zip(g1, ds)), rtol=1e-10)
