@@ -752,6 +752,13 @@ def test_folds_builds_and_cond(dev, oracle):
     # fold golden on the device: testSin0Fold2 (TestRevFwdFold.hs:545-550)
     _, (g,) = ad.grad(dev, lambda T, x: nn.sfold(T, lambda a, _e: T.unary("sin", a), x, T.srepl([5], 42.0)), [dev.sscalar(1.1)])
     np.testing.assert_allclose(float(dev.kfromS(g)), 0.12389721944941383, atol=1e-10)
+    # a fold whose step is a fold: testSin0FoldNestedS1 (TestRevFwdFold.hs:2316-2326)
+    def nested(T, x0):
+        inner = lambda x, a: nn.sfold(T, lambda x2, a2: T.binary("mul", T.binary("mul", T.sscalar(0.7), x2), a2),
+                                      a, T.sreplicate(7, x))
+        return nn.sfold(T, inner, x0, T.sreplicate(3, x0))
+    _, (g,) = ad.grad(dev, nested, [dev.sscalar(1.1)])
+    np.testing.assert_allclose(float(dev.kfromS(g)), 2.0504979297616553e-43, rtol=1e-12)
     t = dev.sconcrete(a0)
     b1 = nn.sbuild1(dev, 4, lambda i: dev.binary("mul", t, dev.srepl([3, 4], float(i))))
     exact(dev.to_numpy(b1), np.stack([a0 * i for i in range(4)]))

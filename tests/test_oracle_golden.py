@@ -126,6 +126,16 @@ def test_fold_goldens(oracle):
         _, (g,) = ad.grad(o, f, [x0])
         np.testing.assert_allclose(float(np.asarray(g)), expected, atol=1e-10, rtol=0)
 
+    # testSin0FoldNestedS1 (TestRevFwdFold.hs:2316-2326): a fold whose step is a fold; the reference's eps
+    # is 1e-10 absolute, far above the value itself, so the known answer is also checked relatively
+    def nested(T, a0):
+        inner = lambda x, a: nn.sfold(T, lambda x2, a2: T.binary("mul", T.binary("mul", T.sscalar(0.7), x2), a2),
+                                      a, T.sreplicate(7, x))
+        return nn.sfold(T, inner, a0, T.sreplicate(3, a0))
+    _, (g,) = ad.grad(o, nested, [x0])
+    np.testing.assert_allclose(float(np.asarray(g)), 2.0504979297616553e-43, atol=1e-10, rtol=0)
+    np.testing.assert_allclose(float(np.asarray(g)), 2.0504979297616553e-43, rtol=1e-12)
+
     # testSin0Fold6 (= 6) and testSin0Fold7 (= 250): tensor-valued accumulators
     def fold6(T, a0):
         acc0 = T.sreplicate(2, T.sreplicate(1, a0))
