@@ -11,7 +11,7 @@ Sources (relative to the horde-ad tree):
 """
 import numpy as np
 
-from horde_ad_b200 import ix as ixm
+from horde_ad_b200 import ix as ixm, nn
 
 minH = ixm.minH
 
@@ -147,3 +147,45 @@ CONV_GOLDEN = [
     ("Konst5LittleC", np.full((2, 2, 2, 2), 5.0), T16B, "K",
      [40.1,8.0,11.0,-3.0,582625.89432,28.79432,-309.09999999999997,25.8,40.1,8.0,11.0,-3.0,582625.89432,28.79432,-309.09999999999997,25.8], 1e-8),
 ]
+
+
+# ---------------------------------------------------------------------------
+# testCNNOPP3 (test/simplified/TestGatherSimplified.hs:1365-1436,1574-1578): the toy "convolution" and
+# "max-pool" written with rbuild, rindex and ifH whose constant-folded value the reference prints as
+#   sfromListLinear [2,2,2,2] [14,0,14,0,0,...,0]
+# on a [3,3,3,3] glyph of sevens.  Every index may run out of bounds (then `!` is 0) and the guard
+# `within3` keeps only indices that are 0 or dim - 2.  Non-vectorised code by construction: host loops.
+def _within3(sh, ix):
+    return all(i == 0 or d - 2 == i for i, d in zip(ix, sh))
+
+
+def _indexz03(T, d, ix):
+    zero = T.srepl([], 0.0, T.dtype(d))
+    return nn.scond(T, _within3(T.shape(d), ix), T.sindex(d, list(ix)), zero)
+
+
+def _slicez4(T, sh_out, d, ix_base):
+    return nn.sbuild(T, sh_out, lambda ixr: _indexz03(T, d, [a + b for a, b in zip(ix_base, ixr)]))
+
+
+def _slicez3(T, sh_out, d, ix_base):
+    return nn.sbuild(T, sh_out, lambda _ixr: _indexz03(T, d, [a + a for a in ix_base]))
+
+
+def conv2dPreserving3(T, arrA):
+    def at(ix):
+        iImg, _, iBh, iBw = ix
+        arrAt = _slicez4(T, [2, 2, 2, 2], arrA, [iImg, 0, iBw, 1])
+        return T.binary("add", T.sindex(arrAt, [0, iBw, iImg, iBh]), T.sindex(arrAt, [iImg, 1, iBw + 1, iBh]))
+    return nn.sbuild(T, [2, 2, 2, 2], at)
+
+
+def maxPool2dUnpadded3(T, arr):
+    def at(ix):
+        aa, bb, iBh, iBw = ix
+        arrt = _slicez3(T, [2, 2, 2, 2], arr, [iBh // 2, aa, bb, iBw])
+        return T.sindex(arrt, [0, 0, 0, 0])
+    return nn.sbuild(T, [2, 2, 2, 2], at)
+
+
+CNNOPP3_GOLDEN = [14.0, 0.0, 14.0, 0.0] + [0.0] * 12

@@ -729,6 +729,18 @@ def test_tanh_affine_node(dev, dtype, shape):
     assert none is None and np.array_equal(dev.to_numpy(dz2), dev.to_numpy(dz))
 
 
+def test_cnn_opp3_on_the_device(dev):
+    """testCNNOPP3 / testCNNOPP3b (TestGatherSimplified.hs:1365-1391) through the C ABI: out-of-bounds
+    index -> 0, stacking of 0-d results, host conditionals; known folded value and gradient."""
+    g = np.full((3, 3, 3, 3), 7.0)
+    prog = lambda T, u: P.maxPool2dUnpadded3(T, P.conv2dPreserving3(T, u))
+    v, (gr,) = ad.grad(dev, prog, [dev.sconcrete(g)])
+    assert dev.to_numpy(v).reshape(-1).tolist() == P.CNNOPP3_GOLDEN
+    expect = np.zeros((3, 3, 3, 3))
+    expect[0, 0, 0, 1] = expect[0, 1, 1, 1] = 2.0
+    exact(dev.to_numpy(gr), expect)
+
+
 def test_folds_builds_and_cond(dev, oracle):
     """tmapAccumL / tfold / tscan as host loops over device slices, tsbuild1,
     tsmap0N, scond (non-vectorised code paths: they must work, not be fast)."""

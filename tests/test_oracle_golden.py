@@ -227,3 +227,16 @@ def test_tanh_affine_node_equals_the_unfused_layer_on_the_oracle(oracle):
     ds = [rng.uniform(-1, 1, p.shape) for p in params]
     _, t = ad.jvp(oracle, f(True), params, ds)
     np.testing.assert_allclose(float(t), sum(float(np.sum(g * d)) for g, d in zip(g1, ds)), rtol=1e-10)
+
+
+def test_cnn_opp3_folded_value_and_gradient(oracle):
+    """testCNNOPP3 / testCNNOPP3b (TestGatherSimplified.hs:1365-1391): the toy conv/max-pool built from
+    rbuild, rindex and ifH folds to [14, 0, 14, 0, 0, ...] on a glyph of sevens, and its simplified gradient
+    artifact is `soneHot x [0,0,0,1] + soneHot x [0,1,1,1]` with x = the sum of two cotangent entries."""
+    g = np.full((3, 3, 3, 3), 7.0)
+    prog = lambda T, u: P.maxPool2dUnpadded3(T, P.conv2dPreserving3(T, u))
+    v, (gr,) = ad.grad(oracle, prog, [g])
+    assert np.asarray(v).shape == (2, 2, 2, 2) and np.asarray(v).reshape(-1).tolist() == P.CNNOPP3_GOLDEN
+    expect = np.zeros((3, 3, 3, 3))
+    expect[0, 0, 0, 1] = expect[0, 1, 1, 1] = 2.0
+    assert np.array_equal(np.asarray(gr), expect)
