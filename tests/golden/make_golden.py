@@ -38,6 +38,8 @@ out = {
         {"name": "testListProd", "cite": "test/simplified/TestAdaptorSimplified.hs:1043-1053", "input": [1, 2, 3, 4], "value": [24, 12, 8, 6]},
         {"name": "testSin0Fold2", "cite": "test/simplified/TestRevFwdFold.hs:545-550", "value": 0.12389721944941383},
         {"name": "testCNNOPP3 folded value", "cite": "test/simplified/TestGatherSimplified.hs:1375", "shape": [2, 2, 2, 2], "value": P.CNNOPP3_GOLDEN},
+        {"name": "testCNNOPP6 folded value", "cite": "test/simplified/TestGatherSimplified.hs:1590", "shape": [2, 2, 2, 2], "value": P.CNNOPP6_GOLDEN},
+        {"name": "testCNNOPP7 folded value", "cite": "test/simplified/TestGatherSimplified.hs:1628", "shape": [2, 2, 2, 2], "value": P.CNNOPP7_GOLDEN},
         {"name": "testSin0FoldNestedS1", "cite": "test/simplified/TestRevFwdFold.hs:2316-2326", "value": 2.0504979297616553e-43},
         {"name": "testSin0Fold3", "cite": "test/simplified/TestRevFwdFold.hs:558-563", "value": 0.4535961214255773},
         {"name": "testSin0Fold4", "cite": "test/simplified/TestRevFwdFold.hs:565-570", "value": -0.7053476446727861},

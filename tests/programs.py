@@ -189,3 +189,33 @@ def maxPool2dUnpadded3(T, arr):
 
 
 CNNOPP3_GOLDEN = [14.0, 0.0, 14.0, 0.0] + [0.0] * 12
+
+
+# testCNNOPP6 / testCNNOPP7 (TestGatherSimplified.hs:1580-1650): the same helpers with every base index
+# doubled (slicez3); folded values [7,0,7,0,0,...] and [7,0,0,...] on a [2,2,2,2] glyph of sevens.
+def conv2dPreserving3z(T, arrA):
+    def at(ix):
+        iImg, _, iBh, iBw = ix
+        arrAt = _slicez3(T, [2, 2, 2, 2], arrA, [iImg, iImg, iImg, iBw])
+        return T.sindex(arrAt, [iBh, iBw, iImg, iBh])
+    return nn.sbuild(T, [2, 2, 2, 2], at)
+
+
+def conv2dPreserving3y(T, arrA):
+    def at(ix):
+        iImg, _, iBh, iBw = ix
+        arrAt = _slicez3(T, [2, 2, 2, 2], arrA, [iImg, iImg, iImg, iBh])
+        return T.sindex(arrAt, [iBh, iBw, iImg, iBh])
+    return nn.sbuild(T, [2, 2, 2, 2], at)
+
+
+def maxPool2dUnpadded3y(T, arr):
+    def at(ix):
+        aa, bb, iBh, iBw = ix
+        arrt = _slicez3(T, [2, 2, 2, 2], arr, [iBh, aa, bb, iBw])
+        return T.sindex(arrt, [0, 0, 0, 0])
+    return nn.sbuild(T, [2, 2, 2, 2], at)
+
+
+CNNOPP6_GOLDEN = [7.0, 0.0, 7.0, 0.0] + [0.0] * 12
+CNNOPP7_GOLDEN = [7.0] + [0.0] * 15

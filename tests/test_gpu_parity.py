@@ -739,6 +739,9 @@ def test_cnn_opp3_on_the_device(dev):
     expect = np.zeros((3, 3, 3, 3))
     expect[0, 0, 0, 1] = expect[0, 1, 1, 1] = 2.0
     exact(dev.to_numpy(gr), expect)
+    g2 = dev.sconcrete(np.full((2, 2, 2, 2), 7.0))                       # testCNNOPP6 / testCNNOPP7
+    assert dev.to_numpy(P.maxPool2dUnpadded3(dev, P.conv2dPreserving3z(dev, g2))).reshape(-1).tolist() == P.CNNOPP6_GOLDEN
+    assert dev.to_numpy(P.maxPool2dUnpadded3y(dev, P.conv2dPreserving3y(dev, g2))).reshape(-1).tolist() == P.CNNOPP7_GOLDEN
 
 
 def test_folds_builds_and_cond(dev, oracle):

@@ -240,3 +240,13 @@ def test_cnn_opp3_folded_value_and_gradient(oracle):
     expect = np.zeros((3, 3, 3, 3))
     expect[0, 0, 0, 1] = expect[0, 1, 1, 1] = 2.0
     assert np.array_equal(np.asarray(gr), expect)
+
+
+def test_cnn_opp6_and_opp7_folded_values(oracle):
+    """testCNNOPP6 / testCNNOPP7 (TestGatherSimplified.hs:1580-1650; the same literals at
+    TestConvSimplified.hs:1507,1546): folded values of the doubled-index variants."""
+    g = np.full((2, 2, 2, 2), 7.0)
+    v6 = P.maxPool2dUnpadded3(oracle, P.conv2dPreserving3z(oracle, g))
+    v7 = P.maxPool2dUnpadded3y(oracle, P.conv2dPreserving3y(oracle, g))
+    assert np.asarray(v6).reshape(-1).tolist() == P.CNNOPP6_GOLDEN
+    assert np.asarray(v7).reshape(-1).tolist() == P.CNNOPP7_GOLDEN
