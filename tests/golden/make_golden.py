@@ -40,6 +40,7 @@ out = {
         {"name": "testCNNOPP3 folded value", "cite": "test/simplified/TestGatherSimplified.hs:1375", "shape": [2, 2, 2, 2], "value": P.CNNOPP3_GOLDEN},
         {"name": "testCNNOPP6 folded value", "cite": "test/simplified/TestGatherSimplified.hs:1590", "shape": [2, 2, 2, 2], "value": P.CNNOPP6_GOLDEN},
         {"name": "testCNNOPP7 folded value", "cite": "test/simplified/TestGatherSimplified.hs:1628", "shape": [2, 2, 2, 2], "value": P.CNNOPP7_GOLDEN},
+        *[{"name": "vstackABC " + n, "cite": "test/simplified/TestAdaptorSimplified.hs:815-835,949", "value": e} for n, _mk, e in P.VSTACK_GOLDEN],
         {"name": "testSin0FoldNestedS1", "cite": "test/simplified/TestRevFwdFold.hs:2316-2326", "value": 2.0504979297616553e-43},
         {"name": "testSin0Fold3", "cite": "test/simplified/TestRevFwdFold.hs:558-563", "value": 0.4535961214255773},
         {"name": "testSin0Fold4", "cite": "test/simplified/TestRevFwdFold.hs:565-570", "value": -0.7053476446727861},

@@ -219,3 +219,37 @@ def maxPool2dUnpadded3y(T, arr):
 
 CNNOPP6_GOLDEN = [7.0, 0.0, 7.0, 0.0] + [0.0] * 12
 CNNOPP7_GOLDEN = [7.0] + [0.0] * 15
+
+
+# ---------------------------------------------------------------------------
+# vstackABC / vstackBuild (test/simplified/TestAdaptorSimplified.hs:785-813) and their known answers
+# (:815-835, :949): a[0]+b[1] | a[1:n-1]+b[2:n]+c[:n-2] | a[n-1]+c[n-2], once with slices and appends,
+# once as rbuild1 over host conditionals.
+def vstackABC(T, a, b, c):
+    n = T.shape(a)[0]
+    add = lambda x, y: T.binary("add", x, y)
+    head = T.sreplicate(1, add(T.sindex(a, [0]), T.sindex(b, [1])))
+    mid = add(T.sslice(1, n - 2, a), add(T.sslice(2, n - 2, b), T.sslice(0, n - 2, c)))
+    last = T.sreplicate(1, add(T.sindex(a, [n - 1]), T.sindex(c, [n - 2])))
+    return T.sappend(head, T.sappend(mid, last))
+
+
+def vstackBuild(T, a, b, c):
+    n = T.shape(a)[0]
+    add = lambda x, y: T.binary("add", x, y)
+
+    def at(i):
+        if i == 0:
+            return add(T.sindex(a, [0]), T.sindex(b, [1]))
+        if i == n - 1:
+            return add(T.sindex(a, [n - 1]), T.sindex(c, [n - 2]))
+        return add(add(T.sindex(a, [i]), T.sindex(b, [i + 1])), T.sindex(c, [i - 1]))
+    return nn.sbuild1(T, n, at)
+
+
+VSTACK_GOLDEN = [
+    ("repl", lambda n: (np.full(n, 1.0), np.full(n, 2.0), np.full(n, 3.0)), [3.0, 6.0, 6.0, 6.0, 6.0, 6.0, 6.0, 6.0, 6.0, 4.0]),
+    ("iota", lambda n: (np.arange(n, dtype=float),) * 3, [1.0, 3.0, 6.0, 9.0, 12.0, 15.0, 18.0, 21.0, 24.0, 17.0]),
+    ("replIota", lambda n: (1.0 * np.arange(n), 2.0 * np.arange(n), 3.0 * np.arange(n)),
+     [2.0, 5.0, 11.0, 17.0, 23.0, 29.0, 35.0, 41.0, 47.0, 33.0]),
+]

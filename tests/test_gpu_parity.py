@@ -729,6 +729,22 @@ def test_tanh_affine_node(dev, dtype, shape):
     assert none is None and np.array_equal(dev.to_numpy(dz2), dev.to_numpy(dz))
 
 
+@pytest.mark.parametrize("name,mk,expected", P.VSTACK_GOLDEN, ids=[v[0] for v in P.VSTACK_GOLDEN])
+def test_vstack_known_answers_on_the_device(dev, name, mk, expected):
+    """vstackABC / vstackBuild (TestAdaptorSimplified.hs:785-835, 949) through the C ABI, and the
+    reference's 1e6-element agreement test (testVstackConcatConcrete, :850-853) for the slice/append form."""
+    a, b, c = (dev.sconcrete(x) for x in mk(10))
+    assert dev.to_numpy(P.vstackABC(dev, a, b, c)).tolist() == expected
+    assert dev.to_numpy(P.vstackBuild(dev, a, b, c)).tolist() == expected
+    n = 10**6
+    ha, hb, hc = mk(n)
+    got = dev.to_numpy(P.vstackABC(dev, dev.sconcrete(ha), dev.sconcrete(hb), dev.sconcrete(hc)))
+    ref = np.concatenate([[ha[0] + hb[1]], ha[1:n - 1] + hb[2:n] + hc[:n - 2], [ha[n - 1] + hc[n - 2]]])
+    exact(got, ref)
+    f32 = dev.to_numpy(P.vstackABC(dev, *(dev.sconcrete(x.astype(np.float32)) for x in (ha, hb, hc))))
+    exact(f32.astype(np.float64), ref)         # "trustedResult": the Float run, cast, equals the Double run
+
+
 def test_cnn_opp3_on_the_device(dev):
     """testCNNOPP3 / testCNNOPP3b (TestGatherSimplified.hs:1365-1391) through the C ABI: out-of-bounds
     index -> 0, stacking of 0-d results, host conditionals; known folded value and gradient."""

@@ -250,3 +250,12 @@ def test_cnn_opp6_and_opp7_folded_values(oracle):
     v7 = P.maxPool2dUnpadded3y(oracle, P.conv2dPreserving3y(oracle, g))
     assert np.asarray(v6).reshape(-1).tolist() == P.CNNOPP6_GOLDEN
     assert np.asarray(v7).reshape(-1).tolist() == P.CNNOPP7_GOLDEN
+
+
+@pytest.mark.parametrize("name,mk,expected", P.VSTACK_GOLDEN, ids=[v[0] for v in P.VSTACK_GOLDEN])
+def test_vstack_known_answers(oracle, name, mk, expected):
+    """testTrustVstackConcatRepl10 / Iota10 / ReplIota10 and the folded value of vstackBuild
+    (TestAdaptorSimplified.hs:815-835, 949): slices + appends and rbuild1 agree with the literals."""
+    a, b, c = mk(10)
+    assert np.asarray(P.vstackABC(oracle, a, b, c)).tolist() == expected
+    assert np.asarray(P.vstackBuild(oracle, a, b, c)).tolist() == expected
