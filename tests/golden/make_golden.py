@@ -19,6 +19,7 @@ out = {
     "fixtures": {
         "t16b": {"cite": "test/tool/CrossTesting.hs:460-462", "shape": list(P.T16B.shape), "data": P.T16B.reshape(-1).tolist()},
         "t128": {"cite": "test/tool/CrossTesting.hs:463-473", "shape": list(P.T128.shape), "data": P.T128.reshape(-1).tolist()},
+        "t48": {"cite": "test/tool/CrossTesting.hs:463-464", "shape": list(P.T48.shape), "data": P.T48.reshape(-1).tolist()},
         "vals72": {"cite": "test/simplified/TestGatherSimplified.hs:212", "shape": [7, 2], "data": P.VALS72.reshape(-1).tolist()},
     },
     "gather_scatter_gradients": [
@@ -41,6 +42,9 @@ out = {
         {"name": "testCNNOPP6 folded value", "cite": "test/simplified/TestGatherSimplified.hs:1590", "shape": [2, 2, 2, 2], "value": P.CNNOPP6_GOLDEN},
         {"name": "testCNNOPP7 folded value", "cite": "test/simplified/TestGatherSimplified.hs:1628", "shape": [2, 2, 2, 2], "value": P.CNNOPP7_GOLDEN},
         *[{"name": "vstackABC " + n, "cite": "test/simplified/TestAdaptorSimplified.hs:815-835,949", "value": e} for n, _mk, e in P.VSTACK_GOLDEN],
+        {"name": "testGatherTranspose33", "cite": "test/simplified/TestGatherSimplified.hs:564-600", "value": P.GT33_GOLDEN},
+        {"name": "testGatherTransposeBuild33", "cite": "test/simplified/TestGatherSimplified.hs:600-606", "value": P.GT33_BUILD_GOLDEN},
+        {"name": "testGatherCond / testGatherCond2", "cite": "test/simplified/TestGatherSimplified.hs:716-770", "value": P.GATHER_COND_GOLDEN},
         {"name": "testSin0FoldNestedS1", "cite": "test/simplified/TestRevFwdFold.hs:2316-2326", "value": 2.0504979297616553e-43},
         {"name": "testSin0Fold3", "cite": "test/simplified/TestRevFwdFold.hs:558-563", "value": 0.4535961214255773},
         {"name": "testSin0Fold4", "cite": "test/simplified/TestRevFwdFold.hs:565-570", "value": -0.7053476446727861},

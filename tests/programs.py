@@ -253,3 +253,81 @@ VSTACK_GOLDEN = [
     ("replIota", lambda n: (1.0 * np.arange(n), 2.0 * np.arange(n), 3.0 * np.arange(n)),
      [2.0, 5.0, 11.0, 17.0, 23.0, 29.0, 35.0, 41.0, 47.0, 33.0]),
 ]
+
+
+# ---------------------------------------------------------------------------
+# testGatherTranspose33 / testGatherTransposeBuild33 (test/simplified/TestGatherSimplified.hs:564-606):
+# 21 transpositions (several with permutations shorter than the rank) and two reshapes of the rank-10
+# fixture t128, then a matmul with the fixture t48 (test/tool/CrossTesting.hs:463-464); the 128-element
+# gradients are the reference's literals.  Pins the permutation convention of tstranspose.
+T48 = np.array([18.1, 29.1, 32.1, 40.1, 52.0, 53.99432, 97.1, 58.8943200001, 18.1, 29.1, 32.1, 40.1, 58.0, 54.99432, 97.1,
+                52.8943200001, 5, 2, 6, 1, -2, 0.92, 0.1, -0.2, 13.1, 9, 8, -4, 34, 2.99432, -33, 26, 2, 2, 2, 2, -0.2, -0.2,
+                -0.2, -0.2, 25.0003, -0.2, -0.2, -0.2, 25.0003, 25.0003, 25.0003, 25.0003]).reshape(3, 1, 2, 2, 1, 2, 2)
+
+
+def gatherTranspose33(T, t):
+    x = T.stranspose([0, 1, 7, 4, 5, 3, 6, 2, 8], t)
+    for perm in ([1, 0], [0, 1], [0], [], [0, 1, 2, 4, 3, 5, 6, 7, 9, 8], [5, 0, 1, 2, 3, 4], [0, 1, 2, 3, 4, 5, 6],
+                 [0, 1, 2, 3, 7, 5, 6, 4], [0, 1, 2, 3, 4, 5, 6, 7, 9, 8], [1, 0, 3, 2], [1, 2, 3, 0], [0, 1, 2, 3]):
+        x = T.stranspose(perm, x)
+    x = T.sreshape([2, 2, 8, 4], x)
+    for perm in ([3, 0, 2, 1], [1, 2, 3, 0], [0, 1, 2, 3], [1, 0], [1, 0, 2], [1, 2, 0], [2, 0, 1], [0, 1, 2]):
+        x = T.stranspose(perm, x)
+    x = T.sreshape([16, 8], x)
+    return T.smatmul2(T.sreshape([6, 8], T.sconcrete(T48)), T.stranspose([1, 0], x))
+
+
+def gatherTransposeBuild33(T, t):
+    """rbuild1 4 (\\i -> gatherTranspose33 (t * replicate0N i))"""
+    sh = list(T.shape(t))
+    return nn.sbuild1(T, 4, lambda i: gatherTranspose33(T, T.binary("mul", t, T.srepl(sh, float(i), T.dtype(t)))))
+
+
+GT33_GOLDEN = [
+    81.3003, 71.0, 81.3003, 71.0, 81.3003, 71.0, 81.3003, 71.0, 80.0, 79.0, 80.0, 79.0, 80.0, 79.0, 80.0, 79.0,
+    81.3003, 71.0, 81.3003, 71.0, 81.3003, 71.0, 81.3003, 71.0, 80.0, 79.0, 80.0, 79.0, 80.0, 79.0, 80.0, 79.0,
+    81.3003, 71.0, 81.3003, 71.0, 81.3003, 71.0, 81.3003, 71.0, 80.0, 79.0, 80.0, 79.0, 80.0, 79.0, 80.0, 79.0,
+    81.3003, 71.0, 81.3003, 71.0, 81.3003, 71.0, 81.3003, 71.0, 80.0, 79.0, 80.0, 79.0, 80.0, 79.0, 80.0, 79.0,
+    166.8003, 137.70326, 166.8003, 137.70326, 166.8003, 137.70326, 166.8003, 137.70326, 186.1003, 162.3889400002,
+    186.1003, 162.3889400002, 186.1003, 162.3889400002, 186.1003, 162.3889400002, 166.8003, 137.70326, 166.8003,
+    137.70326, 166.8003, 137.70326, 166.8003, 137.70326, 186.1003, 162.3889400002, 186.1003, 162.3889400002,
+    186.1003, 162.3889400002, 186.1003, 162.3889400002, 166.8003, 137.70326, 166.8003, 137.70326, 166.8003,
+    137.70326, 166.8003, 137.70326, 186.1003, 162.3889400002, 186.1003, 162.3889400002, 186.1003, 162.3889400002,
+    186.1003, 162.3889400002, 166.8003, 137.70326, 166.8003, 137.70326, 166.8003, 137.70326, 166.8003, 137.70326,
+    186.1003, 162.3889400002, 186.1003, 162.3889400002, 186.1003, 162.3889400002, 186.1003, 162.3889400002,
+]
+GT33_BUILD_GOLDEN = [
+    487.80179999999996, 426.0, 487.80179999999996, 426.0, 487.80179999999996, 426.0, 487.80179999999996, 426.0,
+    480.0, 474.0, 480.0, 474.0, 480.0, 474.0, 480.0, 474.0, 487.80179999999996, 426.0, 487.80179999999996, 426.0,
+    487.80179999999996, 426.0, 487.80179999999996, 426.0, 480.0, 474.0, 480.0, 474.0, 480.0, 474.0, 480.0, 474.0,
+    487.80179999999996, 426.0, 487.80179999999996, 426.0, 487.80179999999996, 426.0, 487.80179999999996, 426.0,
+    480.0, 474.0, 480.0, 474.0, 480.0, 474.0, 480.0, 474.0, 487.80179999999996, 426.0, 487.80179999999996, 426.0,
+    487.80179999999996, 426.0, 487.80179999999996, 426.0, 480.0, 474.0, 480.0, 474.0, 480.0, 474.0, 480.0, 474.0,
+    1000.8018, 826.21956, 1000.8018, 826.21956, 1000.8018, 826.21956, 1000.8018, 826.21956, 1116.6018,
+    974.3336400012, 1116.6018, 974.3336400012, 1116.6018, 974.3336400012, 1116.6018, 974.3336400012, 1000.8018,
+    826.21956, 1000.8018, 826.21956, 1000.8018, 826.21956, 1000.8018, 826.21956, 1116.6018, 974.3336400012,
+    1116.6018, 974.3336400012, 1116.6018, 974.3336400012, 1116.6018, 974.3336400012, 1000.8018, 826.21956,
+    1000.8018, 826.21956, 1000.8018, 826.21956, 1000.8018, 826.21956, 1116.6018, 974.3336400012, 1116.6018,
+    974.3336400012, 1116.6018, 974.3336400012, 1116.6018, 974.3336400012, 1000.8018, 826.21956, 1000.8018,
+    826.21956, 1000.8018, 826.21956, 1000.8018, 826.21956, 1116.6018, 974.3336400012, 1116.6018, 974.3336400012,
+    1116.6018, 974.3336400012, 1116.6018, 974.3336400012,
+]
+
+
+# ---------------------------------------------------------------------------
+# gatherCond / gatherCond2 (test/simplified/TestGatherSimplified.hs:716-770; the tests are parked behind a
+# "re-enable once we drop GHC 9.10" comment, their expected gradients are still stated): a conditional
+# `ifH (i ==. 3) 0 j` inside the index function of a gather.
+def gatherCond(T, u):
+    w = T.shape(u)[0]
+    v = T.stranspose([2, 0, 1], T.sreplicate(2 * w, u))
+    return T.sgather([w, 2], v, lambda ix: [ixm.ifH(ix[0].eq(3), 0, ix[1]), 2 * ix[0], ix[0]], 3)
+
+
+def gatherCond2(T, u):
+    w = T.shape(u)[0]
+    v = T.sreplicate(2 * w, u)
+    return T.stranspose([1, 0], T.sgather([2, w], v, lambda ix: [2 * ix[1], ix[1], ixm.ifH(ix[1].eq(3), 0, ix[0])], 3))
+
+
+GATHER_COND_GOLDEN = [1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 2.0, 0.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0]

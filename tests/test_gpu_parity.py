@@ -745,6 +745,28 @@ def test_vstack_known_answers_on_the_device(dev, name, mk, expected):
     exact(f32.astype(np.float64), ref)         # "trustedResult": the Float run, cast, equals the Double run
 
 
+@pytest.mark.parametrize("prog", [P.gatherCond, P.gatherCond2], ids=["gatherCond", "gatherCond2"])
+def test_gather_with_conditional_index_on_the_device(dev, oracle, prog):
+    """testGatherCond / Cond2 and their rbuild1 variants (TestGatherSimplified.hs:716-770): `ifH (i ==. 3) 0 j`
+    compiled into the index program; values bit-exact vs the oracle, gradients = the reference's literals."""
+    t = np.tile(np.array([0.0, 1.0]), (7, 1))
+    data = np.arange(14, dtype=np.float64).reshape(7, 2) * 1.5 - 3
+    exact(dev.to_numpy(prog(dev, dev.sconcrete(data))), np.ascontiguousarray(prog(oracle, data)))
+    _, (g,) = ad.grad(dev, prog, [dev.sconcrete(t)])
+    assert dev.to_numpy(g).reshape(-1).tolist() == P.GATHER_COND_GOLDEN
+    build = lambda T, x: nn.sbuild1(T, 4, lambda i: prog(T, T.binary("mul", x, T.srepl([7, 2], float(i)))))
+    _, (g,) = ad.grad(dev, build, [dev.sconcrete(t)])
+    assert dev.to_numpy(g).reshape(-1).tolist() == [6 * x for x in P.GATHER_COND_GOLDEN]
+
+
+def test_gather_transpose33_on_the_device(dev):
+    """testGatherTranspose33 / Build33 (TestGatherSimplified.hs:564-606) through the C ABI: rank-10 views,
+    permutations shorter than the rank, reshapes of non-contiguous views, the DMMA GEMM."""
+    for f, expected in ((P.gatherTranspose33, P.GT33_GOLDEN), (P.gatherTransposeBuild33, P.GT33_BUILD_GOLDEN)):
+        _, (g,) = ad.grad(dev, f, [dev.sconcrete(P.T128)])
+        np.testing.assert_allclose(dev.to_numpy(g).reshape(-1), np.array(expected), atol=1e-10, rtol=0)
+
+
 def test_cnn_opp3_on_the_device(dev):
     """testCNNOPP3 / testCNNOPP3b (TestGatherSimplified.hs:1365-1391) through the C ABI: out-of-bounds
     index -> 0, stacking of 0-d results, host conditionals; known folded value and gradient."""

@@ -259,3 +259,35 @@ def test_vstack_known_answers(oracle, name, mk, expected):
     a, b, c = mk(10)
     assert np.asarray(P.vstackABC(oracle, a, b, c)).tolist() == expected
     assert np.asarray(P.vstackBuild(oracle, a, b, c)).tolist() == expected
+
+
+def test_gather_transpose33_gradients(oracle):
+    """testGatherTranspose33 / testGatherTransposeBuild33 (TestGatherSimplified.hs:564-606): the chain of
+    21 transpositions + 2 reshapes + matmul; pins the permutation convention (also for permutations
+    shorter than the rank) against the reference's 128-element literals, eps 1e-10 as there."""
+    for f, expected in ((P.gatherTranspose33, P.GT33_GOLDEN), (P.gatherTransposeBuild33, P.GT33_BUILD_GOLDEN)):
+        _, (g,) = ad.grad(oracle, f, [P.T128])
+        np.testing.assert_allclose(np.asarray(g).reshape(-1), np.array(expected), atol=1e-10, rtol=0)
+
+
+def test_gather_reshape22_gradients(oracle):
+    """testGatherReshape22 / testGatherReshapeBuild22 (TestGatherSimplified.hs:439-468): five nested
+    reshapes are the identity on the gradient (ones), 0+1+2+3 = 6 under rbuild1 4."""
+    t = np.tile(np.array([0.0, 1.0]), (6, 1))
+    resh = lambda T, x: T.sreshape([2, 6], T.sreshape([3, 1, 2, 1, 1, 2], T.sreshape([1, 12, 1], T.sreshape([3, 1, 1, 4], T.sreshape([2, 2, 3], x)))))
+    _, (g,) = ad.grad(oracle, resh, [t])
+    assert np.array_equal(np.asarray(g), np.ones((6, 2)))
+    build = lambda T, x: nn.sbuild1(T, 4, lambda i: resh(T, T.binary("mul", x, T.srepl([6, 2], float(i)))))
+    _, (g,) = ad.grad(oracle, build, [t])
+    assert np.array_equal(np.asarray(g), np.full((6, 2), 6.0))
+
+
+@pytest.mark.parametrize("prog", [P.gatherCond, P.gatherCond2], ids=["gatherCond", "gatherCond2"])
+def test_gather_with_conditional_index_gradients(oracle, prog):
+    """testGatherCond / CondBuild / Cond2 / CondBuild2 (TestGatherSimplified.hs:716-770)."""
+    t = np.tile(np.array([0.0, 1.0]), (7, 1))
+    _, (g,) = ad.grad(oracle, prog, [t])
+    assert np.asarray(g).reshape(-1).tolist() == P.GATHER_COND_GOLDEN
+    build = lambda T, x: nn.sbuild1(T, 4, lambda i: prog(T, T.binary("mul", x, T.srepl([7, 2], float(i)))))
+    _, (g,) = ad.grad(oracle, build, [t])
+    assert np.asarray(g).reshape(-1).tolist() == [6 * x for x in P.GATHER_COND_GOLDEN]
