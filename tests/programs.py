@@ -331,3 +331,31 @@ def gatherCond2(T, u):
 
 
 GATHER_COND_GOLDEN = [1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 2.0, 0.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0]
+
+
+# gatherCond3 .. gatherCond6 (TestGatherSimplified.hs:795-915): the same with index components that run
+# out of bounds (2 * i over a short axis): out-of-bounds elements read 0 and receive no cotangent.
+def gatherCond3(T, u):
+    w = T.shape(u)[0]
+    v = T.stranspose([2, 0, 1], T.sreplicate(2 * w, u))
+    return T.sgather([w, 2], v, lambda ix: [2 * ix[0], ix[0], ixm.ifH(ix[0].eq(3), 0, ix[1])], 3)
+
+
+def gatherCond4(T, u):
+    w = T.shape(u)[0]
+    v = T.sreplicate(2 * w, u)
+    return T.stranspose([1, 0], T.sgather([2, w], v, lambda ix: [ix[1], ixm.ifH(ix[1].eq(3), 0, ix[0]), 2 * ix[1]], 3))
+
+
+def gatherCond5(T, v):
+    return T.sgather([T.shape(v)[0], 2], v, lambda ix: [ixm.ifH(ix[0].eq(1), 0, ix[1]), 2 * ix[0], ix[0]], 3)
+
+
+def gatherCond6(T, u):
+    v = T.stranspose([2, 0, 1], u)
+    return T.stranspose([1, 0], T.sgather([2, T.shape(v)[0]], v,
+                                          lambda ix: [ix[1], ixm.ifH(ix[1].eq(1), 0, ix[0]), 2 * ix[1]], 3))
+
+
+GATHER_COND34_GOLDEN = [1.0, 0.0, 1.0, 0.0] + [0.0] * 10                  # input [7, 2]
+GATHER_COND56_GOLDEN = [1.0, 0.0, 0.0, 0.0, 0.0, 2.0, 0.0, 0.0, 1.0] + [0.0] * 7   # input [2, 4, 2]

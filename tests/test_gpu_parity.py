@@ -745,18 +745,24 @@ def test_vstack_known_answers_on_the_device(dev, name, mk, expected):
     exact(f32.astype(np.float64), ref)         # "trustedResult": the Float run, cast, equals the Double run
 
 
-@pytest.mark.parametrize("prog", [P.gatherCond, P.gatherCond2], ids=["gatherCond", "gatherCond2"])
-def test_gather_with_conditional_index_on_the_device(dev, oracle, prog):
-    """testGatherCond / Cond2 and their rbuild1 variants (TestGatherSimplified.hs:716-770): `ifH (i ==. 3) 0 j`
-    compiled into the index program; values bit-exact vs the oracle, gradients = the reference's literals."""
-    t = np.tile(np.array([0.0, 1.0]), (7, 1))
-    data = np.arange(14, dtype=np.float64).reshape(7, 2) * 1.5 - 3
+GATHER_COND_CASES = [(P.gatherCond, (7, 2), P.GATHER_COND_GOLDEN), (P.gatherCond2, (7, 2), P.GATHER_COND_GOLDEN),
+                     (P.gatherCond3, (7, 2), P.GATHER_COND34_GOLDEN), (P.gatherCond4, (7, 2), P.GATHER_COND34_GOLDEN),
+                     (P.gatherCond5, (2, 4, 2), P.GATHER_COND56_GOLDEN), (P.gatherCond6, (2, 4, 2), P.GATHER_COND56_GOLDEN)]
+
+
+@pytest.mark.parametrize("prog,shape,expected", GATHER_COND_CASES, ids=[c[0].__name__ for c in GATHER_COND_CASES])
+def test_gather_with_conditional_index_on_the_device(dev, oracle, prog, shape, expected):
+    """testGatherCond .. testGatherCond6 and their rbuild1 variants (TestGatherSimplified.hs:716-915):
+    `ifH (i ==. 3) 0 j` compiled into the index program, index components that run out of bounds;
+    values bit-exact vs the oracle, gradients = the reference's literals."""
+    t = np.broadcast_to(np.array([0.0, 1.0]), shape).copy()
+    data = np.arange(t.size, dtype=np.float64).reshape(shape) * 1.5 - 3
     exact(dev.to_numpy(prog(dev, dev.sconcrete(data))), np.ascontiguousarray(prog(oracle, data)))
     _, (g,) = ad.grad(dev, prog, [dev.sconcrete(t)])
-    assert dev.to_numpy(g).reshape(-1).tolist() == P.GATHER_COND_GOLDEN
-    build = lambda T, x: nn.sbuild1(T, 4, lambda i: prog(T, T.binary("mul", x, T.srepl([7, 2], float(i)))))
+    assert dev.to_numpy(g).reshape(-1).tolist() == expected
+    build = lambda T, x: nn.sbuild1(T, 4, lambda i: prog(T, T.binary("mul", x, T.srepl(list(shape), float(i)))))
     _, (g,) = ad.grad(dev, build, [dev.sconcrete(t)])
-    assert dev.to_numpy(g).reshape(-1).tolist() == [6 * x for x in P.GATHER_COND_GOLDEN]
+    assert dev.to_numpy(g).reshape(-1).tolist() == [6 * x for x in expected]
 
 
 def test_gather_transpose33_on_the_device(dev):

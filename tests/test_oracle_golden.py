@@ -282,12 +282,17 @@ def test_gather_reshape22_gradients(oracle):
     assert np.array_equal(np.asarray(g), np.full((6, 2), 6.0))
 
 
-@pytest.mark.parametrize("prog", [P.gatherCond, P.gatherCond2], ids=["gatherCond", "gatherCond2"])
-def test_gather_with_conditional_index_gradients(oracle, prog):
-    """testGatherCond / CondBuild / Cond2 / CondBuild2 (TestGatherSimplified.hs:716-770)."""
-    t = np.tile(np.array([0.0, 1.0]), (7, 1))
+GATHER_COND_CASES = [(P.gatherCond, (7, 2), P.GATHER_COND_GOLDEN), (P.gatherCond2, (7, 2), P.GATHER_COND_GOLDEN),
+                     (P.gatherCond3, (7, 2), P.GATHER_COND34_GOLDEN), (P.gatherCond4, (7, 2), P.GATHER_COND34_GOLDEN),
+                     (P.gatherCond5, (2, 4, 2), P.GATHER_COND56_GOLDEN), (P.gatherCond6, (2, 4, 2), P.GATHER_COND56_GOLDEN)]
+
+
+@pytest.mark.parametrize("prog,shape,expected", GATHER_COND_CASES, ids=[c[0].__name__ for c in GATHER_COND_CASES])
+def test_gather_with_conditional_index_gradients(oracle, prog, shape, expected):
+    """testGatherCond .. testGatherCond6 and their rbuild1 variants (TestGatherSimplified.hs:716-915)."""
+    t = np.broadcast_to(np.array([0.0, 1.0]), shape).copy()
     _, (g,) = ad.grad(oracle, prog, [t])
-    assert np.asarray(g).reshape(-1).tolist() == P.GATHER_COND_GOLDEN
-    build = lambda T, x: nn.sbuild1(T, 4, lambda i: prog(T, T.binary("mul", x, T.srepl([7, 2], float(i)))))
+    assert np.asarray(g).reshape(-1).tolist() == expected
+    build = lambda T, x: nn.sbuild1(T, 4, lambda i: prog(T, T.binary("mul", x, T.srepl(list(shape), float(i)))))
     _, (g,) = ad.grad(oracle, build, [t])
-    assert np.asarray(g).reshape(-1).tolist() == [6 * x for x in P.GATHER_COND_GOLDEN]
+    assert np.asarray(g).reshape(-1).tolist() == [6 * x for x in expected]
