@@ -47,6 +47,8 @@ out = {
         {"name": "testGatherCond / testGatherCond2", "cite": "test/simplified/TestGatherSimplified.hs:716-770", "value": P.GATHER_COND_GOLDEN},
         {"name": "testGatherCond3 / testGatherCond4", "cite": "test/simplified/TestGatherSimplified.hs:795-835", "value": P.GATHER_COND34_GOLDEN},
         {"name": "testGatherCond5 / testGatherCond6", "cite": "test/simplified/TestGatherSimplified.hs:870-915", "value": P.GATHER_COND56_GOLDEN},
+        *[{"name": "test" + n[0].upper() + n[1:], "cite": "test/simplified/TestGatherSimplified.hs:161-398,968-1232", "value": e}
+          for n, _f, e in P.GATHER_BUILD_GOLDEN],
         {"name": "testSin0FoldNestedS1", "cite": "test/simplified/TestRevFwdFold.hs:2316-2326", "value": 2.0504979297616553e-43},
         {"name": "testSin0Fold3", "cite": "test/simplified/TestRevFwdFold.hs:558-563", "value": 0.4535961214255773},
         {"name": "testSin0Fold4", "cite": "test/simplified/TestRevFwdFold.hs:565-570", "value": -0.7053476446727861},

@@ -359,3 +359,36 @@ def gatherCond6(T, u):
 
 GATHER_COND34_GOLDEN = [1.0, 0.0, 1.0, 0.0] + [0.0] * 10                  # input [7, 2]
 GATHER_COND56_GOLDEN = [1.0, 0.0, 0.0, 0.0, 0.0, 2.0, 0.0, 0.0, 1.0] + [0.0] * 7   # input [2, 4, 2]
+
+
+# ---------------------------------------------------------------------------
+# The rbuild1 variants of the gather / scatter tests (TestGatherSimplified.hs:161-398, 968-1232):
+#   build1:  rbuild1 5 (\i -> ifH (i >. 2) (prog t) (t ! [i]))
+#   build2:  rbuild1 4 (\i -> prog (t * replicate0N i))              -> 6 x the plain gradient
+#   build12: rbuild1 5 (\i -> ifH (i >. 2) (prog t) (rtr (rreplicate 4 (t ! [i])))) ! [1]
+def build1_variant(prog):
+    return lambda T, t: nn.sbuild1(T, 5, lambda i: prog(T, t) if i > 2 else T.sindex(t, [i]))
+
+
+def build2_variant(prog):
+    return lambda T, t: nn.sbuild1(T, 4, lambda i: prog(T, T.binary("mul", t, T.srepl(list(T.shape(t)), float(i), T.dtype(t)))))
+
+
+def build12_variant(prog):
+    return lambda T, t: T.sindex(nn.sbuild1(
+        T, 5, lambda i: prog(T, t) if i > 2 else T.stranspose([1, 0], T.sreplicate(4, T.sindex(t, [i])))), [1])
+
+
+_G1B = [3.0, 1.0, 1.0, 1.0, 1.0, 3.0] + [0.0] * 8
+_S1B = [3.0] * 6 + [2.0] * 8
+_B12 = [0.0, 0.0, 4.0, 4.0] + [0.0] * 10
+_G2 = [1.0, 0.0, 0.0, 0.0, 1.0, 1.0, 0.0, 0.0, 1.0, 1.0, 0.0, 0.0, 0.0, 1.0]
+GATHER_BUILD_GOLDEN = [
+    ("gatherNestedBuild1", build1_variant(gatherNested1), _G1B), ("gatherBuild1", build1_variant(gather1), _G1B),
+    ("scatterNestedBuild1", build1_variant(scatterNested1), _S1B), ("scatterBuild1", build1_variant(scatter1), _S1B),
+    ("gatherNestedBuild2", build2_variant(gatherNested2), [6 * x for x in _G2]),
+    ("gatherBuild2", build2_variant(gather2), [6 * x for x in _G2]),
+    ("scatterNestedBuild2", build2_variant(scatterNested2), [6.0] * 14), ("scatterBuild2", build2_variant(scatter2), [6.0] * 14),
+    ("gatherNestedBuild12", build12_variant(gatherNested12), _B12), ("gatherBuild12", build12_variant(gather12), _B12),
+    ("scatterNestedBuild12", build12_variant(scatterNested12), _B12), ("scatterBuild12", build12_variant(scatter12), _B12),
+]

@@ -745,6 +745,15 @@ def test_vstack_known_answers_on_the_device(dev, name, mk, expected):
     exact(f32.astype(np.float64), ref)         # "trustedResult": the Float run, cast, equals the Double run
 
 
+@pytest.mark.parametrize("name,prog,expected", P.GATHER_BUILD_GOLDEN, ids=[g[0] for g in P.GATHER_BUILD_GOLDEN])
+def test_gather_scatter_build_variants_on_the_device(dev, name, prog, expected):
+    """The rbuild1 variants of the reference's gather / scatter tests (TestGatherSimplified.hs:161-398,
+    968-1232) through the C ABI."""
+    t = np.tile(np.array([0.0, 1.0]), (7, 1))
+    _, (g,) = ad.grad(dev, prog, [dev.sconcrete(t)])
+    assert dev.to_numpy(g).reshape(-1).tolist() == expected
+
+
 GATHER_COND_CASES = [(P.gatherCond, (7, 2), P.GATHER_COND_GOLDEN), (P.gatherCond2, (7, 2), P.GATHER_COND_GOLDEN),
                      (P.gatherCond3, (7, 2), P.GATHER_COND34_GOLDEN), (P.gatherCond4, (7, 2), P.GATHER_COND34_GOLDEN),
                      (P.gatherCond5, (2, 4, 2), P.GATHER_COND56_GOLDEN), (P.gatherCond6, (2, 4, 2), P.GATHER_COND56_GOLDEN)]

@@ -296,3 +296,12 @@ def test_gather_with_conditional_index_gradients(oracle, prog, shape, expected):
     build = lambda T, x: nn.sbuild1(T, 4, lambda i: prog(T, T.binary("mul", x, T.srepl(list(shape), float(i)))))
     _, (g,) = ad.grad(oracle, build, [t])
     assert np.asarray(g).reshape(-1).tolist() == [6 * x for x in expected]
+
+
+@pytest.mark.parametrize("name,prog,expected", P.GATHER_BUILD_GOLDEN, ids=[g[0] for g in P.GATHER_BUILD_GOLDEN])
+def test_gather_scatter_build_variants(oracle, name, prog, expected):
+    """testGather(Nested)Build1/2/12 and testScatter(Nested)Build1/2/12 (TestGatherSimplified.hs:161-398,
+    968-1232): the gather / scatter programs under rbuild1 with host conditionals and indexing."""
+    t = np.tile(np.array([0.0, 1.0]), (7, 1))
+    _, (g,) = ad.grad(oracle, prog, [t])
+    assert np.asarray(g).reshape(-1).tolist() == expected
