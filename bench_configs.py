@@ -72,6 +72,19 @@ def families(dev, rng, hbm, src, quick):
     report("unary exp, contiguous f64", timed(dev, lambda: dev.unary("exp", a), 10), 2 * 8 * n)
     report("taddTarget in place (cotangent accumulation)", timed(dev, lambda: dev.add_accumulate(dev.binary("add", a, b), b), 10) -
            timed(dev, lambda: dev.binary("add", a, b), 10), 3 * 8 * n)
+    from horde_ad_b200 import ix as ixm
+    from horde_ad_b200.device import Program
+    ea, eb = ixm.map_input(0, True), ixm.map_input(1, True)
+    chain = (ea * eb + ea) * ixm.maxH(ea, eb)
+    cprog = Program([chain], 0)
+    arr2 = (C.c_void_p * 2)(a.h, b.h)
+
+    def fused():
+        p = C.c_void_p()
+        ffi.call("hb_fused_map", cprog.h, 2, arr2, ffi.F64, C.byref(p))
+        ffi._lib.hb_release(p)
+    report("fused map chain (a*b + a) * max(a, b): one generated kernel, 16-byte accesses", timed(dev, fused, 10), 3 * 8 * n,
+           {"unfused_passes": 4})
     report("ssum0 (full reduction)", timed(dev, lambda: dev.ssum0(a), 10), 8 * n)
     report("sdot0", timed(dev, lambda: dev.sdot0(a, b), 10), 2 * 8 * n)
     m = dev.sconcrete(np.zeros(n)), dev.sconcrete(np.zeros(n))

@@ -19,6 +19,10 @@
 // HBM roofline: 2*sizeof(T) bytes per moved element (+ index tables).
 #include "iter.cuh"
 #include "vm.cuh"
+#include "jit.cuh"
+
+#include <mutex>
+#include <vector>
 
 // ------------------------------------------------------------------ build
 extern "C" int hb_ixprog_build(const hb_insn *code, int n_insns, int n_vars, int n_out,
@@ -134,6 +138,45 @@ extern "C" int hb_ixprog_is_affine(const hb_ixprog *p, int *flag) {
   HB_REQUIRE(p && flag, "null argument");
   *flag = p->affine ? 1 : 0;
   return HB_OK;
+}
+
+// ------------------------------------------------------ generated kernels
+// Looks up (or generates and compiles) the kernel of `p` for one set of call
+// constants.  nullptr -> the caller runs the VM interpreter kernel instead.
+static std::mutex g_gen_mu;
+template <typename MakeSource>
+static CUfunction hb_generated(const hb_ixprog *p, const std::string &key, MakeSource make) {
+  if (!hb_jit_enabled()) return nullptr;
+  std::lock_guard<std::mutex> lk(g_gen_mu);
+  for (auto &e : p->generated)
+    if (e.first == key) return (CUfunction)e.second;
+  CUfunction f = hb_jit_kernel(make(), "hbj_k");
+  p->generated.emplace_back(key, (void *)f);
+  return f;
+}
+static void key_add(std::string &k, const void *p, size_t n) { k.append((const char *)p, n); }
+
+// index-function kernel (kinds: jit.cuh) for shm -> (pshape, pstride)
+static CUfunction hb_generated_index(const hb_ixprog *p, int kind, int shm_rank, const int64_t *shm, int prank,
+                                     const int64_t *pshape, const int64_t *pstride, int es) {
+  std::string key;
+  int hdr[4] = {kind, shm_rank, prank, es};
+  key_add(key, hdr, sizeof hdr);
+  key_add(key, shm, sizeof(int64_t) * shm_rank);
+  key_add(key, pshape, sizeof(int64_t) * prank);
+  key_add(key, pstride, sizeof(int64_t) * prank);
+  return hb_generated(p, key, [&] {
+    return hb_jit_index_source(p->vm, p->n_tensors, kind, shm_rank, shm, prank, pshape, pstride, es);
+  });
+}
+// launches a generated index kernel: `lead` = the kind's own leading arguments, then the tensor operands
+static int hb_launch_index(CUfunction f, const hb_ixprog *p, int64_t M, void **lead, int n_lead) {
+  void *args[8 + HB_VM_MAX_TENSORS];
+  const void *tptr[HB_VM_MAX_TENSORS];
+  int n = 0;
+  for (int i = 0; i < n_lead; i++) args[n++] = lead[i];
+  for (int t = 0; t < p->n_tensors; t++) { tptr[t] = p->vm.tensors[t].ptr; args[n++] = &tptr[t]; }
+  return hb_jit_launch(f, (unsigned)hb_blocks_for(M, 256), 256, args);
 }
 
 // ------------------------------------------------------------- VM kernels
@@ -263,100 +306,121 @@ static int hb_rows_blocks(int64_t rows, int L) {
 //   TABLE = true : axis 0 is the whole shm space, its source offset comes from
 //                  the table the VM kernel wrote (INT64_MIN = out of bounds).
 struct hb_rowsp {
-  int rank;               // outer axes (everything except the inner run)
-  int mrank, prank;       // affine: leading shm axes carry index coefficients
+  int rank;               // outer axes (everything except the inner run), in ENUMERATION order
+  int prank;              // affine: number of bound-checked index components
+  int idx32;              // rows < 2^31: 32-bit row decomposition
   int64_t rows;
   int shape[HB_R];
   int64_t stride[HB_R];   // source stride of each outer axis
+  int64_t ostride[HB_R];  // result stride of each outer axis (the result is contiguous)
   int64_t c0[HB_VM_MAX_OUT], pshape[HB_VM_MAX_OUT];
-  int64_t coef[HB_VM_MAX_OUT][HB_R];
+  int64_t coef[HB_VM_MAX_OUT][HB_R];  // index coefficient of each outer axis (0 for shn axes)
   int64_t base;
   int L, lp, lshift;      // run length, its power-of-two padding (<= 32) and log2
+  int tshift;             // table offsets are in units of 2^tshift row elements (vectorised rows)
   int64_t s_in;           // source stride along the run
 };
+
+// 16-byte element for the vectorised instantiations (two f64 / four f32 ... per access)
+struct __align__(16) hb_b16 {
+  uint64_t x, y;
+  hb_b16() = default;
+  __host__ __device__ explicit hb_b16(int) : x(0), y(0) {}
+};
+
+// source / result offsets of one row; source = INT64_MIN when an index component is out of bounds
+template <bool TABLE, typename IT>
+__device__ __forceinline__ void hb_grow_decode(const hb_rowsp &R, const int64_t *__restrict__ table, int64_t row,
+                                               int64_t &off, int64_t &ooff) {
+  IT rem = (IT)row;
+  int64_t o = R.base, oo = 0;
+  int64_t pc[HB_VM_MAX_OUT];
+#pragma unroll
+  for (int c = 0; c < HB_VM_MAX_OUT; c++) pc[c] = c < R.prank ? R.c0[c] : 0;
+#pragma unroll 1
+  for (int k = R.rank - 1; k >= (TABLE ? 1 : 0); k--) {
+    IT q = rem / (IT)R.shape[k];
+    int rr = (int)(rem - q * (IT)R.shape[k]);
+    o += rr * R.stride[k];
+    oo += rr * R.ostride[k];
+    if (!TABLE) {
+#pragma unroll
+      for (int c = 0; c < HB_VM_MAX_OUT; c++)
+        if (c < R.prank) pc[c] += rr * R.coef[c][k];
+    }
+    rem = q;
+  }
+  bool inb = true;
+  if (TABLE) {
+    int64_t t = table[rem];
+    inb = t != INT64_MIN;
+    o += inb ? (t >> R.tshift) : 0;
+    oo += (int64_t)rem * R.ostride[0];
+  } else {
+#pragma unroll
+    for (int c = 0; c < HB_VM_MAX_OUT; c++)
+      if (c < R.prank) inb = inb && pc[c] >= 0 && pc[c] < R.pshape[c];
+  }
+  off = inb ? o : INT64_MIN;
+  ooff = oo;
+}
 
 template <typename T, bool TABLE>
 __global__ void __launch_bounds__(256)
     hb_gather_rows_kernel(const __grid_constant__ hb_rowsp R, const int64_t *__restrict__ table,
                           const T *__restrict__ src, T *__restrict__ out) {
-  const int lane = threadIdx.x & 31;
+  __shared__ longlong2 s_rows[8][32];  // (source, result) offsets of the warp's 32 rows
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   // short runs: 32 rows per warp pass (lane r decodes row r); long runs: one row
   // per warp (every lane decodes it; the cost is amortised over the run)
   const int rpg = R.L <= 32 ? 32 : 1;
   for (int64_t r0 = warp * rpg; r0 < R.rows; r0 += nwarps * rpg) {
-    // lane r: source offset of row r0 + r (INT64_MIN when out of bounds)
-    int64_t row = r0 + (rpg == 32 ? lane : 0), off = INT64_MIN;
+    int64_t row = r0 + (rpg == 32 ? lane : 0), off = INT64_MIN, ooff = 0;
     if (row < R.rows) {
-      int64_t rem = row, o = R.base;
-      int64_t pc[HB_VM_MAX_OUT];
-#pragma unroll
-      for (int c = 0; c < HB_VM_MAX_OUT; c++) pc[c] = c < R.prank ? R.c0[c] : 0;
-#pragma unroll 1
-      for (int k = R.rank - 1; k >= (TABLE ? 1 : 0); k--) {
-        int64_t q = rem / R.shape[k];
-        int rr = (int)(rem - q * R.shape[k]);
-        o += rr * R.stride[k];
-        if (!TABLE && k < R.mrank) {
-#pragma unroll
-          for (int c = 0; c < HB_VM_MAX_OUT; c++)
-            if (c < R.prank) pc[c] += rr * R.coef[c][k];
-        }
-        rem = q;
-      }
-      bool inb = true;
-      if (TABLE) {
-        int64_t t = table[rem];
-        inb = t != INT64_MIN;
-        o += inb ? t : 0;
-      } else {
-#pragma unroll
-        for (int c = 0; c < HB_VM_MAX_OUT; c++)
-          if (c < R.prank) inb = inb && pc[c] >= 0 && pc[c] < R.pshape[c];
-      }
-      off = inb ? o : INT64_MIN;
+      if (R.idx32) hb_grow_decode<TABLE, uint32_t>(R, table, row, off, ooff);
+      else hb_grow_decode<TABLE, int64_t>(R, table, row, off, ooff);
     }
-    // walk the 32 rows, 32 / lp of them per pass; four passes (or four pieces
-    // of a long run) are loaded before any is stored, for memory-level parallelism
-    const int rpp = 32 >> R.lshift, sub = lane >> R.lshift, j0 = lane & (R.lp - 1);
     if (R.L <= 32) {
-      for (int rb = 0; rb < 32; rb += 4 * rpp) {
+      // walk the 32 rows, 32 / lp of them per pass; four passes are loaded before
+      // any is stored, for memory-level parallelism
+      const int rpp = 32 >> R.lshift, sub = lane >> R.lshift, j0 = lane & (R.lp - 1);
+      s_rows[wib][lane] = make_longlong2(off, ooff);
+      __syncwarp();
+      const int nrows = (int)min((int64_t)32, R.rows - r0);
+      for (int rb = 0; rb < nrows; rb += 4 * rpp) {
         T v[4];
         int64_t dsto[4];
 #pragma unroll
         for (int u = 0; u < 4; u++) {
           int rsel = rb + u * rpp + sub;
-          int64_t o = __shfl_sync(0xffffffffu, off, rsel & 31);
-          int64_t rr = r0 + rsel;
-          bool live = rsel < 32 && rr < R.rows && j0 < R.L;
-          dsto[u] = live ? rr * R.L + j0 : -1;
-          v[u] = (live && o != INT64_MIN) ? src[o + (int64_t)j0 * R.s_in] : T(0);
+          longlong2 oo = s_rows[wib][rsel & 31];
+          bool live = rsel < nrows && j0 < R.L;
+          dsto[u] = live ? oo.y + j0 : -1;
+          v[u] = (live && oo.x != INT64_MIN) ? src[oo.x + (int64_t)j0 * R.s_in] : T(0);
         }
 #pragma unroll
         for (int u = 0; u < 4; u++)
           if (dsto[u] >= 0) out[dsto[u]] = v[u];
       }
+      __syncwarp();
     } else {
-      {
-        int64_t o = off;
-        int64_t rr = r0;
-        T *dst = out + rr * R.L;
-        const bool inb = o != INT64_MIN;
-        const T *sp = src + (inb ? o : 0);
-        int j = lane;
-        for (; j + 96 < R.L; j += 128) {
-          T a = T(0), b = T(0), c = T(0), d = T(0);
-          if (inb) {
-            a = sp[(int64_t)j * R.s_in];
-            b = sp[(int64_t)(j + 32) * R.s_in];
-            c = sp[(int64_t)(j + 64) * R.s_in];
-            d = sp[(int64_t)(j + 96) * R.s_in];
-          }
-          dst[j] = a; dst[j + 32] = b; dst[j + 64] = c; dst[j + 96] = d;
+      T *dst = out + ooff;
+      const bool inb = off != INT64_MIN;
+      const T *sp = src + (inb ? off : 0);
+      int j = lane;
+      for (; j + 96 < R.L; j += 128) {
+        T a = T(0), b = T(0), c = T(0), d = T(0);
+        if (inb) {
+          a = sp[(int64_t)j * R.s_in];
+          b = sp[(int64_t)(j + 32) * R.s_in];
+          c = sp[(int64_t)(j + 64) * R.s_in];
+          d = sp[(int64_t)(j + 96) * R.s_in];
         }
-        for (; j < R.L; j += 32) dst[j] = inb ? sp[(int64_t)j * R.s_in] : T(0);
+        dst[j] = a; dst[j + 32] = b; dst[j + 64] = c; dst[j + 96] = d;
       }
+      for (; j < R.L; j += 32) dst[j] = inb ? sp[(int64_t)j * R.s_in] : T(0);
     }
   }
 }
@@ -394,6 +458,87 @@ static void rows_finish(hb_rowsp *R, int nlead, int nrank, const int64_t *nshape
   R->lp = 1 << R->lshift;
   R->rows = 1;
   for (int i = 0; i < R->rank; i++) R->rows *= R->shape[i];
+  R->idx32 = R->rows < (1ll << 31);
+  int64_t o = L;  // the result is contiguous over (outer axes ++ run)
+  for (int i = R->rank - 1; i >= 0; i--) { R->ostride[i] = o; o *= R->shape[i]; }
+}
+
+// Overlapping windows (two shm axes feeding one index component, e.g. the
+// i + j of an im2col gather) re-read every source element once per window.
+// Walking the result in row-major order puts those re-reads a whole plane of
+// the other axes apart -- out of L2 for large tensors.  The rows are therefore
+// ENUMERATED with the window axes moved inside the other outer axes, but
+// outside a tail of innermost axes that keeps every warp's writes in
+// contiguous runs of >= 2 KB: re-reads then hit L1/L2 and the DRAM traffic
+// drops to the algorithmic bytes.  The result itself is unchanged (each row
+// carries its own result offset).
+static void rows_window_order(hb_rowsp *R, int nlead, size_t es) {
+  bool win[HB_R] = {};
+  bool any = false;
+  for (int k = 0; k < nlead; k++)
+    for (int k2 = 0; k2 < nlead; k2++)
+      if (k != k2 && R->shape[k] > 1 && R->shape[k2] > 1)
+        for (int c = 0; c < R->prank; c++)
+          if (R->coef[c][k] != 0 && R->coef[c][k2] != 0) { win[k] = true; any = true; }
+  if (!any) return;
+  int tail = R->rank;  // axes [tail, rank) stay innermost
+  int64_t run = (int64_t)R->L * (int64_t)es;
+  while (tail > 0 && !win[tail - 1] && run < 2048) {
+    const int k = tail - 1;
+    const int64_t need = (2048 + run - 1) / run;
+    int64_t f = 0;  // smallest divisor of the axis that completes a 2 KB run
+    if (R->shape[k] >= 2 * need && R->rank < HB_R)
+      for (int64_t d = need; d * 2 <= R->shape[k] && d <= need * 64; d++)
+        if (R->shape[k] % d == 0) { f = d; break; }
+    if (f) {
+      // split axis k into [shape / f][f]: the inner part stays in the tail, the outer part goes outside the windows
+      for (int i = R->rank; i > k + 1; i--) {
+        R->shape[i] = R->shape[i - 1]; R->stride[i] = R->stride[i - 1]; R->ostride[i] = R->ostride[i - 1];
+        win[i] = win[i - 1];
+        for (int c = 0; c < HB_VM_MAX_OUT; c++) R->coef[c][i] = R->coef[c][i - 1];
+      }
+      R->rank++;
+      R->shape[k + 1] = (int)f; R->stride[k + 1] = R->stride[k]; R->ostride[k + 1] = R->ostride[k]; win[k + 1] = false;
+      R->shape[k] = (int)(R->shape[k] / f); R->stride[k] *= f; R->ostride[k] *= f;
+      for (int c = 0; c < HB_VM_MAX_OUT; c++) { R->coef[c][k + 1] = R->coef[c][k]; R->coef[c][k] *= f; }
+      tail = k + 1;
+      break;
+    }
+    tail--;
+    run *= R->shape[tail];
+  }
+  int order[HB_R], n = 0;
+  for (int k = 0; k < tail; k++) if (!win[k]) order[n++] = k;
+  for (int k = 0; k < tail; k++) if (win[k]) order[n++] = k;
+  for (int k = tail; k < R->rank; k++) order[n++] = k;
+  hb_rowsp Q = *R;
+  for (int i = 0; i < R->rank; i++) {
+    int k = order[i];
+    R->shape[i] = Q.shape[k];
+    R->stride[i] = Q.stride[k];
+    R->ostride[i] = Q.ostride[k];
+    for (int c = 0; c < HB_VM_MAX_OUT; c++) R->coef[c][i] = Q.coef[c][k];
+  }
+}
+
+// 16-byte accesses: when the run, every source stride and the base are
+// multiples of v = 16 / sizeof(T) elements and both pointers are 16-byte
+// aligned, the same gather is a gather of 16-byte elements.
+static bool rows_vectorise(hb_rowsp *R, size_t es, const void *src, const void *dst, int64_t table_align) {
+  if (es >= 16 || R->s_in != 1) return false;
+  const int64_t v = 16 / (int64_t)es;
+  if (R->L % v || R->base % v || table_align % v) return false;
+  if (((uintptr_t)src | (uintptr_t)dst) & 15) return false;
+  for (int i = 0; i < R->rank; i++)
+    if (R->shape[i] > 1 && (R->stride[i] % v || R->ostride[i] % v)) return false;
+  R->L /= (int)v;
+  R->base /= v;
+  while ((1 << R->tshift) < v) R->tshift++;
+  for (int i = 0; i < R->rank; i++) { R->stride[i] /= v; R->ostride[i] /= v; }
+  R->lshift = 0;
+  while ((1 << R->lshift) < R->L && R->lshift < 5) R->lshift++;
+  R->lp = 1 << R->lshift;
+  return true;
 }
 
 static void fill_shm(hb_shm *S, int shm_rank, const int64_t *shm, int shp_rank, const int64_t *pshape,
@@ -467,7 +612,6 @@ extern "C" int hb_gather(const hb_array *src, int shm_rank, const int64_t *shm, 
     if (small_axes) {
       hb_rowsp R;
       memset(&R, 0, sizeof R);
-      R.mrank = shm_rank;
       R.prank = shp_rank;
       R.base = base;
       for (int c = 0; c < shp_rank; c++) {
@@ -477,10 +621,16 @@ extern "C" int hb_gather(const hb_array *src, int shm_rank, const int64_t *shm, 
       }
       for (int k = 0; k < shm_rank; k++) { R.shape[k] = (int)shm[k]; R.stride[k] = fs[k]; }
       rows_finish(&R, shm_rank, nrank, src->shape + shp_rank, src->strides + shp_rank);
+      rows_window_order(&R, shm_rank, hb_dtype_size(src->dt));
       int blocks = hb_rows_blocks(R.rows, R.L);
-      HB_DISPATCH_BYTES(src->dt, T,
-                        (hb_gather_rows_kernel<T, false><<<blocks, 256, 0, g_hb.stream>>>(
-                            R, nullptr, (const T *)hb_data(src), (T *)hb_data(o))));
+      if (rows_vectorise(&R, hb_dtype_size(src->dt), hb_data(src), hb_data(o), 0)) {
+        hb_gather_rows_kernel<hb_b16, false><<<blocks, 256, 0, g_hb.stream>>>(
+            R, nullptr, (const hb_b16 *)hb_data(src), (hb_b16 *)hb_data(o));
+      } else {
+        HB_DISPATCH_BYTES(src->dt, T,
+                          (hb_gather_rows_kernel<T, false><<<blocks, 256, 0, g_hb.stream>>>(
+                              R, nullptr, (const T *)hb_data(src), (T *)hb_data(o))));
+      }
       HB_LAUNCHED();
       *out = o;
       return HB_OK;
@@ -519,16 +669,33 @@ extern "C" int hb_gather(const hb_array *src, int shm_rank, const int64_t *shm, 
   if (Nn == 1) {
     int64_t tail = 0;  // offset of the (all size-1) shn axes is 0
     (void)tail;
-    int blocks = hb_blocks_for(M, 128);
-    HB_DISPATCH_BYTES(src->dt, T,
-                      (hb_vm_gather0_kernel<T><<<blocks, 128, 0, g_hb.stream>>>(
-                          prog->vm, S, M, (const T *)hb_data(src), (T *)hb_data(o))));
+    CUfunction gen = hb_generated_index(prog, 1, shm_rank, shm, shp_rank, src->shape, src->strides,
+                                        (int)hb_dtype_size(src->dt));
+    if (gen) {
+      const void *sp = hb_data(src);
+      void *op = hb_data(o);
+      void *lead[2] = {&sp, &op};
+      int st = hb_launch_index(gen, prog, M, lead, 2);
+      if (st != HB_OK) { hb_release(o); return st; }
+    } else {
+      int blocks = hb_blocks_for(M, 128);
+      HB_DISPATCH_BYTES(src->dt, T,
+                        (hb_vm_gather0_kernel<T><<<blocks, 128, 0, g_hb.stream>>>(
+                            prog->vm, S, M, (const T *)hb_data(src), (T *)hb_data(o))));
+    }
     HB_LAUNCHED();
   } else {
     void *scr;
     int st = hb_scratch((size_t)M * 8, &scr);
     if (st != HB_OK) { hb_release(o); return st; }
-    hb_vm_offsets_kernel<<<hb_blocks_for(M, 128), 128, 0, g_hb.stream>>>(prog->vm, S, M, (int64_t *)scr);
+    CUfunction gen = hb_generated_index(prog, 0, shm_rank, shm, shp_rank, src->shape, src->strides, 0);
+    if (gen) {
+      void *lead[1] = {&scr};
+      st = hb_launch_index(gen, prog, M, lead, 1);
+      if (st != HB_OK) { hb_release(o); return st; }
+    } else {
+      hb_vm_offsets_kernel<<<hb_blocks_for(M, 128), 128, 0, g_hb.stream>>>(prog->vm, S, M, (int64_t *)scr);
+    }
     HB_LAUNCHED();
     bool small_axes = M < (1ll << 31);
     for (int i = 0; i < nrank; i++) small_axes = small_axes && src->shape[shp_rank + i] < (1ll << 31);
@@ -538,9 +705,17 @@ extern "C" int hb_gather(const hb_array *src, int shm_rank, const int64_t *shm, 
       R.shape[0] = (int)M;
       rows_finish(&R, 1, nrank, src->shape + shp_rank, src->strides + shp_rank);
       int blocks = hb_rows_blocks(R.rows, R.L);
-      HB_DISPATCH_BYTES(src->dt, T,
-                        (hb_gather_rows_kernel<T, true><<<blocks, 256, 0, g_hb.stream>>>(
-                            R, (const int64_t *)scr, (const T *)hb_data(src), (T *)hb_data(o))));
+      int64_t talign = 0;  // table offsets are combinations of the indexed axes' strides
+      for (int c = 0; c < shp_rank; c++)
+        if (src->shape[c] > 1) talign |= src->strides[c];
+      if (rows_vectorise(&R, hb_dtype_size(src->dt), hb_data(src), hb_data(o), talign & 15)) {
+        hb_gather_rows_kernel<hb_b16, true><<<blocks, 256, 0, g_hb.stream>>>(
+            R, (const int64_t *)scr, (const hb_b16 *)hb_data(src), (hb_b16 *)hb_data(o));
+      } else {
+        HB_DISPATCH_BYTES(src->dt, T,
+                          (hb_gather_rows_kernel<T, true><<<blocks, 256, 0, g_hb.stream>>>(
+                              R, (const int64_t *)scr, (const T *)hb_data(src), (T *)hb_data(o))));
+      }
       HB_LAUNCHED();
     } else {
       hb_dims nd;
@@ -752,11 +927,12 @@ __global__ void __launch_bounds__(256)
 // shn index), its inner run of L elements shares the index work.
 struct hb_srowsp {
   int rank;                // axis 0 = the leading index space (M sources or Pn destinations)
+  int idx32;               // rows < 2^31: 32-bit row decomposition
   int shape[HB_R];
   int64_t sstride[HB_R];   // source strides of the outer shn axes (entry 0 unused)
   int64_t ostride[HB_R];   // strides of the same axes inside one contiguous result slice
   int64_t rows, Nn;
-  int L, lp, lshift;
+  int L, lp, lshift;       // run length in accesses of V elements
   int64_t s_in;
 };
 
@@ -767,20 +943,26 @@ __global__ void __launch_bounds__(256)
   if (m < M) moff[m] = hb_offset_of(md, m);
 }
 
-__device__ __forceinline__ void hb_srow_decode(const hb_srowsp &R, int64_t row, int64_t &lead, int64_t &soff,
-                                               int64_t &ooff) {
-  int64_t rem = row;
+template <typename IT>
+__device__ __forceinline__ void hb_srow_decode_t(const hb_srowsp &R, int64_t row, int64_t &lead, int64_t &soff,
+                                                 int64_t &ooff) {
+  IT rem = (IT)row;
   soff = 0;
   ooff = 0;
 #pragma unroll 1
   for (int k = R.rank - 1; k >= 1; k--) {
-    int64_t q = rem / R.shape[k];
-    int rr = (int)(rem - q * R.shape[k]);
+    IT q = rem / (IT)R.shape[k];
+    int rr = (int)(rem - q * (IT)R.shape[k]);
     soff += rr * R.sstride[k];
     ooff += rr * R.ostride[k];
     rem = q;
   }
-  lead = rem;
+  lead = (int64_t)rem;
+}
+__device__ __forceinline__ void hb_srow_decode(const hb_srowsp &R, int64_t row, int64_t &lead, int64_t &soff,
+                                               int64_t &ooff) {
+  if (R.idx32) hb_srow_decode_t<uint32_t>(R, row, lead, soff, ooff);
+  else hb_srow_decode_t<int64_t>(R, row, lead, soff, ooff);
 }
 
 // no destination hit twice: out[dest[m], ...] = src[m, ...]
@@ -812,18 +994,38 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// out[d, ...] = sum over the sorted source list of d (sequential, reference order)
-template <typename T>
+// V elements of T moved by one access
+template <typename T, int V>
+struct alignas(sizeof(T) * V) hb_vecn {
+  T e[V];
+};
+template <typename T, int V>
+__device__ __forceinline__ hb_vecn<T, V> hb_vecn_zero() {
+  hb_vecn<T, V> z;
+#pragma unroll
+  for (int i = 0; i < V; i++) z.e[i] = T(0);
+  return z;
+}
+
+// out[d, ...] = sum over the sorted source list of d (sequential, reference
+// order); destinations nobody writes get their zeros here (the result is NOT
+// zero-filled beforehand).  When no destination is hit twice the direct
+// kernel has moved the data and only those zeros are left to write.
+// V > 1: the run, the slice strides and the source offsets are multiples of
+// V elements and 16-byte aligned -> one access moves V elements.
+template <typename T, int V>
 __global__ void __launch_bounds__(256)
     hb_scatter_sum_rows_kernel(const __grid_constant__ hb_srowsp R, const int *__restrict__ collision,
                                const int *__restrict__ starts, const int *__restrict__ counts,
                                const int *__restrict__ seg, const int64_t *__restrict__ moff,
                                const T *__restrict__ src, T *__restrict__ out) {
-  if (!*collision) return;
+  typedef hb_vecn<T, V> VT;
+  const bool coll = *collision != 0;
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int rpg = R.L <= 32 ? 32 : 1;
+  const int64_t Lt = (int64_t)R.L * V;  // run length in elements
   for (int64_t r0 = warp * rpg; r0 < R.rows; r0 += nwarps * rpg) {
     int64_t row = r0 + (rpg == 32 ? lane : 0), so = 0;
     int cnt = 0, st = 0;
@@ -840,40 +1042,57 @@ __global__ void __launch_bounds__(256)
       int64_t s_ = __shfl_sync(0xffffffffu, so, rsel);
       int c = __shfl_sync(0xffffffffu, cnt, rsel), st_ = __shfl_sync(0xffffffffu, st, rsel);
       int64_t rr = r0 + rsel;
-      if (rr >= R.rows || c == 0) continue;  // untouched destinations stay zero
+      if (rr >= R.rows) continue;
+      VT *op = (VT *)(out + rr * Lt);
+      if (c == 0) {
+        const VT z = hb_vecn_zero<T, V>();
+        for (int j = j0; j < R.L; j += R.lp) op[j] = z;
+        continue;
+      }
+      if (!coll) continue;  // moved by hb_scatter_direct_rows_kernel
       const int *lst = seg + st_;
       if (c <= 8) {
         // the source offsets of this destination are the same for the whole run:
-        // fetch them once, then every element is c independent loads
+        // fetch them once, then every access is c independent loads
         int64_t so8[8];
 #pragma unroll
         for (int i = 0; i < 8; i++) so8[i] = i < c ? moff[lst[i]] : 0;
         for (int j = j0; j < R.L; j += R.lp) {
-          const T *sp = src + s_ + (int64_t)j * R.s_in;
-          T v[8];
+          VT v[8];
 #pragma unroll
-          for (int i = 0; i < 8; i++) v[i] = i < c ? sp[so8[i]] : T(0);
-          T acc = R.Nn == 1 ? v[0] + T(0) : v[0];
+          for (int i = 0; i < 8; i++)
+            if (i < c) {
+              if (V == 1) v[i].e[0] = src[s_ + so8[i] + (int64_t)j * R.s_in];
+              else v[i] = ((const VT *)(src + s_ + so8[i]))[j];
+            }
+          VT acc;
+#pragma unroll
+          for (int e = 0; e < V; e++) acc.e[e] = R.Nn == 1 ? v[0].e[e] + T(0) : v[0].e[e];
 #pragma unroll
           for (int i = 1; i < 8; i++)
-            if (i < c) acc = v[i] + acc;
-          out[rr * R.L + j] = acc;
+            if (i < c) {
+#pragma unroll
+              for (int e = 0; e < V; e++) acc.e[e] = v[i].e[e] + acc.e[e];
+            }
+          op[j] = acc;
         }
         continue;
       }
       for (int j = j0; j < R.L; j += R.lp) {
-        const T *sp = src + s_ + (int64_t)j * R.s_in;
-        T acc;
-        if (R.Nn == 1) {
-          // rank-0 slices: vec starts at 0 and adds u + u2 (OpsConcrete.hs:1594-1601)
-          acc = T(0);
-          for (int i = 0; i < c; i++) acc = sp[moff[lst[i]]] + acc;
-        } else {
-          // IntMap.insertWith (+): first slice stored as is, later ones new + old
-          acc = sp[moff[lst[0]]];
-          for (int i = 1; i < c; i++) acc = sp[moff[lst[i]]] + acc;
+        VT acc;
+        // rank-0 slices: vec starts at 0 and adds u + u2 (OpsConcrete.hs:1594-1601);
+        // otherwise IntMap.insertWith (+): first slice stored as is, later ones new + old
+        for (int i = 0; i < c; i++) {
+          VT v;
+          if (V == 1) v.e[0] = src[s_ + moff[lst[i]] + (int64_t)j * R.s_in];
+          else v = ((const VT *)(src + s_ + moff[lst[i]]))[j];
+#pragma unroll
+          for (int e = 0; e < V; e++) {
+            if (i == 0) acc.e[e] = R.Nn == 1 ? v.e[e] + T(0) : v.e[e];
+            else acc.e[e] = v.e[e] + acc.e[e];
+          }
         }
-        out[rr * R.L + j] = acc;
+        op[j] = acc;
       }
     }
   }
@@ -914,6 +1133,21 @@ static void srows_fill(hb_srowsp *R, int64_t lead, int nrank, const int64_t *nsh
   R->lp = 1 << R->lshift;
   R->rows = lead;
   for (int i = 0; i < r; i++) R->rows *= sh[i];
+  R->idx32 = R->rows < (1ll << 31);
+}
+
+// can the rows be moved V elements per access?  (run and slice strides multiples of V)
+static bool srows_can_vec(const hb_srowsp *R, int V) {
+  if (V <= 1 || R->s_in != 1 || R->L % V) return false;
+  for (int i = 1; i < R->rank; i++)
+    if (R->shape[i] > 1 && R->sstride[i] % V) return false;
+  return true;
+}
+static void srows_set_vec(hb_srowsp *R, int V) {
+  R->L /= V;
+  R->lshift = 0;
+  while ((1 << R->lshift) < R->L && R->lshift < 5) R->lshift++;
+  R->lp = 1 << R->lshift;
 }
 
 extern "C" int hb_scatter_add(const hb_array *src, int shm_rank, int shp_rank, const int64_t *shp,
@@ -936,12 +1170,18 @@ extern "C" int hb_scatter_add(const hb_array *src, int shm_rank, int shp_rank, c
   for (int i = 0; i < shp_rank; i++) { osh[i] = shp[i]; Pn *= shp[i]; }
   for (int i = 0; i < nrank; i++) { osh[shp_rank + i] = src->shape[shm_rank + i]; Nn *= src->shape[shm_rank + i]; }
   hb_array *o;
-  HB_TRY(hb_zeros(src->dt, shp_rank + nrank, osh, &o));
-  if (M * Nn == 0 || Pn == 0) { *out = o; return HB_OK; }
-  if (M >= (1ll << 31) - 1 || Pn >= (1ll << 31) - 1) {
-    hb_release(o);
-    HB_FAIL(HB_ERR_UNSUPPORTED, "scatter: index spaces of 2^31 positions or more are not supported");
+  bool rows_ok = true;
+  for (int i = 0; i < nrank; i++) rows_ok = rows_ok && src->shape[shm_rank + i] < (1ll << 31);
+  if (M * Nn == 0 || Pn == 0) {
+    HB_TRY(hb_zeros(src->dt, shp_rank + nrank, osh, &o));
+    *out = o;
+    return HB_OK;
   }
+  HB_REQUIRE(M < (1ll << 31) - 1 && Pn < (1ll << 31) - 1,
+             "scatter: index spaces of 2^31 positions or more are not supported");
+  // the row kernels write every element of the result exactly once (zeros included)
+  if (rows_ok) HB_TRY(hb_new_array(src->dt, shp_rank + nrank, osh, &o));
+  else HB_TRY(hb_zeros(src->dt, shp_rank + nrank, osh, &o));
   // contiguous strides of the shp space
   int64_t pstr[HB_VM_MAX_OUT];
   { int64_t s = 1; for (int i = shp_rank - 1; i >= 0; i--) { pstr[i] = s; s *= shp[i]; } }
@@ -965,7 +1205,16 @@ extern "C" int hb_scatter_add(const hb_array *src, int shm_rank, int shp_rank, c
   // zero counts, starts, cursor, flag in one memset
   cudaError_t e = cudaMemsetAsync(counts, 0, ((size_t)Pn * 3 + 16) * 4, g_hb.stream);
   if (e != cudaSuccess) { hb_release(o); HB_CUDA(e); }
-  hb_scatter_dest_kernel<<<hb_blocks_for(M, 128), 128, 0, g_hb.stream>>>(prog->vm, S, M, dest, counts, flag);
+  {
+    CUfunction gen = hb_generated_index(prog, 2, shm_rank, src->shape, shp_rank, shp, pstr, 0);
+    if (gen) {
+      void *lead[3] = {&dest, &counts, &flag};
+      st = hb_launch_index(gen, prog, M, lead, 3);
+      if (st != HB_OK) { hb_release(o); return st; }
+    } else {
+      hb_scatter_dest_kernel<<<hb_blocks_for(M, 128), 128, 0, g_hb.stream>>>(prog->vm, S, M, dest, counts, flag);
+    }
+  }
   HB_LAUNCHED();
   hb_dims sd;  // full source dims (shm ++ shn) for the direct kernel
   sd.rank = src->rank;
@@ -986,14 +1235,19 @@ extern "C" int hb_scatter_add(const hb_array *src, int shm_rank, int shp_rank, c
   int bdst = hb_blocks_for(total_dst, 256, g_hb.sm_count * 32);
   st = exclusive_scan_i32(counts, starts, Pn, tmp);
   if (st != HB_OK) { hb_release(o); return st; }
-  bool rows_ok = true;
-  for (int i = 0; i < nrank; i++) rows_ok = rows_ok && src->shape[shm_rank + i] < (1ll << 31);
   hb_srowsp Rs, Rd;
+  int vec = 1;
   if (rows_ok) {
     srows_fill(&Rs, M, nrank, src->shape + shm_rank, src->strides + shm_rank);
     srows_fill(&Rd, Pn, nrank, src->shape + shm_rank, src->strides + shm_rank);
     hb_scatter_moff_kernel<<<hb_blocks_for(M, 256), 256, 0, g_hb.stream>>>(md, M, moff);
     HB_LAUNCHED();
+    // 16-byte accesses in the sum kernel: source offsets of the shm positions, the
+    // slice strides and the run are multiples of V elements, pointers 16-byte aligned
+    int V = 16 / (int)hb_dtype_size(src->dt);
+    bool ok = srows_can_vec(&Rd, V) && ((((uintptr_t)hb_data(src)) | ((uintptr_t)hb_data(o))) & 15) == 0;
+    for (int i = 0; i < shm_rank; i++) ok = ok && (src->shape[i] == 1 || src->strides[i] % V == 0);
+    if (ok) { vec = V; srows_set_vec(&Rd, V); }
   }
   HB_DISPATCH_NUM(src->dt, T, {
     if (rows_ok)
@@ -1009,12 +1263,18 @@ extern "C" int hb_scatter_add(const hb_array *src, int shm_rank, int shp_rank, c
     HB_LAUNCHED();
     hb_scatter_sort_long_kernel<<<hb_blocks_for(Pn, 1, g_hb.sm_count * 4), 256, 0, g_hb.stream>>>(flag, starts, counts, seg, Pn);
     HB_LAUNCHED();
-    if (rows_ok)
-      hb_scatter_sum_rows_kernel<T><<<hb_rows_blocks(Rd.rows, Rd.L), 256, 0, g_hb.stream>>>(
-          Rd, flag, starts, counts, seg, moff, (const T *)hb_data(src), (T *)hb_data(o));
-    else
+    if (rows_ok) {
+      constexpr int VV = 16 / (int)sizeof(T);
+      if (vec > 1)
+        hb_scatter_sum_rows_kernel<T, VV><<<hb_rows_blocks(Rd.rows, Rd.L), 256, 0, g_hb.stream>>>(
+            Rd, flag, starts, counts, seg, moff, (const T *)hb_data(src), (T *)hb_data(o));
+      else
+        hb_scatter_sum_rows_kernel<T, 1><<<hb_rows_blocks(Rd.rows, Rd.L), 256, 0, g_hb.stream>>>(
+            Rd, flag, starts, counts, seg, moff, (const T *)hb_data(src), (T *)hb_data(o));
+    } else {
       hb_scatter_sum_kernel<T><<<bdst, 256, 0, g_hb.stream>>>(flag, starts, counts, seg, md, nd, Nn, total_dst,
                                                               (const T *)hb_data(src), (T *)hb_data(o));
+    }
     HB_LAUNCHED();
   });
   *out = o;
@@ -1056,15 +1316,6 @@ extern "C" int hb_onehot(const hb_array *v, int shp_rank, const int64_t *shp, co
 }
 
 // -------------------------------------------------------------- fused map
-#define HB_MAP_MAXIN 6
-struct hb_mapp {
-  int rank, n_in;
-  int64_t shape[HB_R];
-  int64_t stride[HB_MAP_MAXIN][HB_R];
-  const void *ptr[HB_MAP_MAXIN];
-  int dtype[HB_MAP_MAXIN];
-};
-
 struct hb_map_in {
   const hb_mapp *mp;
   const int64_t *off;
@@ -1130,8 +1381,37 @@ extern "C" int hb_fused_map(const hb_ixprog *prog, int n_in, hb_array *const *in
     hb_collapse(&mp.rank, mp.shape, n_in, str);
     for (int k = 0; k < n_in; k++)
       for (int d = 0; d < mp.rank; d++) mp.stride[k][d] = str[k][d];
-    int blocks = hb_blocks_for(n, 128, g_hb.sm_count * 32);
-    HB_DISPATCH_ALL(dt, T, (hb_fused_map_kernel<T><<<blocks, 128, 0, g_hb.stream>>>(prog->vm, mp, n, (T *)hb_data(o))));
+    // generated kernel: shapes / strides / dtypes baked in; 16-byte accesses when every input is
+    // contiguous or a broadcast scalar and the pointers are aligned
+    int es_max = (int)hb_dtype_size(dt);
+    for (int k = 0; k < n_in; k++) es_max = std::max(es_max, (int)hb_dtype_size(ins[k]->dt));
+    int vec = 16 / es_max;
+    if (mp.rank != 1 || n % vec) vec = 1;
+    for (int k = 0; k < n_in && vec > 1; k++) {
+      if (mp.stride[k][0] != 0 && mp.stride[k][0] != 1) vec = 1;
+      else if (mp.stride[k][0] == 1 && ((uintptr_t)mp.ptr[k] % (hb_dtype_size(ins[k]->dt) * vec))) vec = 1;
+    }
+    if ((uintptr_t)hb_data(o) % (hb_dtype_size(dt) * (size_t)vec)) vec = 1;
+    std::string key;
+    int hdr[5] = {3, mp.rank, n_in, (int)dt, vec};
+    key_add(key, hdr, sizeof hdr);
+    key_add(key, mp.shape, sizeof(int64_t) * mp.rank);
+    for (int k = 0; k < n_in; k++) { key_add(key, mp.stride[k], sizeof(int64_t) * mp.rank); key_add(key, &mp.dtype[k], sizeof(int)); }
+    CUfunction gen = hb_generated(prog, key, [&] { return hb_jit_map_source(prog->vm, prog->n_tensors, mp, dt, n, vec); });
+    if (gen) {
+      void *op = hb_data(o);
+      void *args[1 + HB_MAP_MAXIN + HB_VM_MAX_TENSORS];
+      const void *tptr[HB_VM_MAX_TENSORS];
+      int na = 0;
+      args[na++] = &op;
+      for (int k = 0; k < n_in; k++) args[na++] = &mp.ptr[k];
+      for (int t = 0; t < prog->n_tensors; t++) { tptr[t] = prog->vm.tensors[t].ptr; args[na++] = &tptr[t]; }
+      int st = hb_jit_launch(gen, (unsigned)hb_blocks_for(n / vec, 256, g_hb.sm_count * 16), 256, args);
+      if (st != HB_OK) { hb_release(o); return st; }
+    } else {
+      int blocks = hb_blocks_for(n, 128, g_hb.sm_count * 32);
+      HB_DISPATCH_ALL(dt, T, (hb_fused_map_kernel<T><<<blocks, 128, 0, g_hb.stream>>>(prog->vm, mp, n, (T *)hb_data(o))));
+    }
     HB_LAUNCHED();
   }
   *out = o;

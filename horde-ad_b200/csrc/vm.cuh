@@ -3,6 +3,10 @@
 // (Ops.hs:689-705; grammar: SURVEY.md appendix B = the Int/Bool sub-language
 // of Ast.hs:487-528,575-579,654-665) and fused elementwise chains.
 #pragma once
+#include <string>
+#include <utility>
+#include <vector>
+
 #include "common.cuh"
 #include "ops.cuh"
 
@@ -30,6 +34,8 @@ struct hb_ixprog {
   bool affine;                          // every OUT is affine in the variables
   int64_t c0[HB_VM_MAX_OUT];            // out_c = c0[c] + sum_k coef[c][k]*var_k
   int64_t coef[HB_VM_MAX_OUT][HB_R];
+  // generated kernels of this program, keyed by the call's constants (jit.cuh)
+  mutable std::vector<std::pair<std::string, void *>> generated;
 };
 
 #ifdef __CUDACC__

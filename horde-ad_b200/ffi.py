@@ -83,6 +83,10 @@ PROTOTYPES = {
     "hb_scatter_add": [P, C.c_int, C.c_int, I64P, P, PP],
     "hb_onehot": [P, C.c_int, I64P, I64P, PP],
     "hb_fused_map": [P, C.c_int, PP, C.c_int, PP],
+    "hb_jit_stats": [IP, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)],
+    "hb_jit_index_source_text": [P, C.c_int, C.c_int, I64P, C.c_int, I64P, I64P, C.c_int, C.c_char_p, C.c_size_t],
+    "hb_jit_map_source_text": [P, C.c_int, I64P, C.c_int, I64P, IP, C.c_int, C.c_int, C.c_char_p, C.c_size_t],
+    "hb_jit_compile_only": [C.c_char_p, C.POINTER(C.c_size_t), C.c_char_p, C.c_size_t],
     "hb_sum_leading": [P, C.c_int, PP], "hb_sum_all": [P, PP], "hb_dot_all": [P, P, PP],
     "hb_dot_inner": [P, P, PP], "hb_dot_inner_sum_leading": [P, P, C.c_int, PP],
     "hb_matmul2": [P, P, PP], "hb_matvecmul": [P, P, PP],

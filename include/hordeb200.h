@@ -314,6 +314,35 @@ int hb_onehot(const hb_array *v, int shp_rank, const int64_t *shp,
 int hb_fused_map(const hb_ixprog *prog, int n_in, hb_array *const *ins,
                  hb_dtype dt, hb_array **out);
 
+/* The kernel generator behind hb_gather / hb_scatter_add / hb_fused_map:
+ * general (non-affine) index programs and map programs are translated to
+ * straight-line CUDA C with the call's shapes, strides, dtypes and bounds as
+ * constants, compiled for sm_100a by NVRTC (libnvrtc.so.12, resolved with
+ * dlopen) on first use and cached; HB_JIT=0 or a box without NVRTC runs the
+ * same programs on the bytecode interpreter kernels instead (device code
+ * either way).  `available`: 1 when the generator is usable on this device. */
+int hb_jit_stats(int *available, uint64_t *compiled, uint64_t *cache_hits,
+                 uint64_t *failed);
+/* The CUDA C text the generator emits for an index program (entry `hbj_k`).
+ * kind 0: offset table of prog over shm into a target of (pshape, pstride);
+ * kind 1: rank-0 gather of es-byte elements; kind 2: scatter destinations and
+ * collision counts.  Needs no device (used by the CPU-side tests). */
+int hb_jit_index_source_text(const hb_ixprog *prog, int kind, int shm_rank,
+                             const int64_t *shm, int prank,
+                             const int64_t *pshape, const int64_t *pstride,
+                             int es, char *buf, size_t len);
+/* ... and for a map program over `rank` collapsed dims of `shape`, n_in
+ * inputs with element strides strides[k * rank + d] and dtypes dtypes[k];
+ * vec > 1 = that many elements per access (rank 1, strides 0/1). */
+int hb_jit_map_source_text(const hb_ixprog *prog, int rank,
+                           const int64_t *shape, int n_in,
+                           const int64_t *strides, const int *dtypes,
+                           hb_dtype out_dtype, int vec, char *buf, size_t len);
+/* Compile CUDA C text to an sm_100a cubin with NVRTC without loading it
+ * (works without a GPU); the compiler log lands in `log`. */
+int hb_jit_compile_only(const char *source, size_t *cubin_bytes, char *log,
+                        size_t log_len);
+
 /* -------------------------------------------------------- reduce / contract */
 
 /* tssum / tssumN (OpsConcrete.hs:215-228): sum over the n_axes LEADING axes.*/

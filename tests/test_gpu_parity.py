@@ -189,6 +189,59 @@ def test_fused_map(dev, oracle):
         close(got, ref, dtype, scale=4)
 
 
+def _jit_stats():
+    import ctypes as C
+    avail, z = C.c_int(-1), [C.c_uint64() for _ in range(3)]
+    ffi.call("hb_jit_stats", C.byref(avail), C.byref(z[0]), C.byref(z[1]), C.byref(z[2]))
+    return avail.value, z[0].value, z[1].value, z[2].value
+
+
+def test_fused_map_generated_kernels(dev, oracle):
+    """Fused chains through the kernel generator: contiguous operands and a broadcast scalar take the 16-byte
+    path, transposed / odd-sized / mixed-dtype operands the scalar one; integer outputs; bit-exact where the
+    chain is only + * max select (each step rounds like the reference's separate passes: no FMA contraction)."""
+    if os.environ.get("HB_JIT", "1") != "0":
+        assert _jit_stats()[0] == 1, "the kernel generator is not available on this box"
+    rng = np.random.default_rng(61)
+    a, b, c = ixm.map_input(0, True), ixm.map_input(1, True), ixm.map_input(2, True)
+    for dtype in (np.float64, np.float32):
+        for n in (1 << 12, 4097):
+            x, y = rnd(rng, (n,), dtype), rnd(rng, (n,), dtype)
+            s = np.array(0.37, dtype=dtype)
+            expr = (a * b + c) * ixm.maxH(a, b)
+            ins = [dev.sconcrete(x), dev.sconcrete(y), dev.sreplicateN([n], dev.sscalar(float(s), dtype))]
+            got = dev.to_numpy(dev.fused_map(expr, ins, dtype))
+            exact(got, ((x * y + s) * np.maximum(x, y)).astype(dtype))
+            exact(got, oracle.fused_map(expr, [x, y, np.broadcast_to(s, (n,))], dtype))
+        # a slice that starts off a 16-byte boundary
+        x = rnd(rng, (1025,), dtype)
+        got = dev.to_numpy(dev.fused_map(a * a, [dev.sslice(1, 1024, dev.sconcrete(x))], dtype))
+        exact(got, x[1:] * x[1:])
+    # mixed dtypes: an Int64 operand converted inside the chain, Int64 result by floor
+    xi, yf = rng.integers(-50, 50, (7, 33)).astype(np.int64), rnd(rng, (7, 33), np.float64, -3, 3)
+    ai, bf = ixm.map_input(0, False), ixm.map_input(1, True)
+    expr = ixm.floorH(ixm.fromIntegral(ai) * bf) + ai.remH(7)
+    got = dev.to_numpy(dev.fused_map(expr, [dev.sconcrete(xi), dev.stranspose([1, 0], dev.sconcrete(yf.T.copy()))], np.int64))
+    exact(got, oracle.fused_map(expr, [xi, yf], np.int64))
+    if os.environ.get("HB_JIT", "1") != "0":
+        avail, compiled, hits, failed = _jit_stats()
+        assert compiled > 0 and failed == 0, (compiled, hits, failed)
+
+
+def test_interpreter_kernels_agree_with_generated_kernels():
+    """HB_JIT=0 runs every index / map program on the bytecode interpreter kernels: the same parity tests must
+    pass there (the path of a box without libnvrtc)."""
+    import subprocess
+    import sys
+    if os.environ.get("HB_JIT") == "0":
+        pytest.skip("already the interpreter run")
+    env = dict(os.environ, HB_JIT="0")
+    sel = "gather_kinds or gather_data_dependent or scatter_bit_exact or scatter_long or fused_map or row_kernels or Gather or Scatter"
+    r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-m", "gpu", "-x", "-q", "-k", sel],
+                       env=env, capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(__file__)))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
 def test_add_accumulate_in_place(dev):
     a = np.arange(12.0).reshape(3, 4)
     acc = dev.sconcrete(a)
@@ -386,6 +439,43 @@ def test_scatter_long_segments(dev, oracle):
     src2 = rng.uniform(-.5, .5, (300, 4))
     f2 = lambda i: [i[0].remH(2)]                                    # 150 slices per destination
     exact(dev.to_numpy(dev.sscatter([2], dev.sconcrete(src2), f2, 1)), oracle.sscatter([2], src2, f2, 1))
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32, np.int16, np.int8])
+@pytest.mark.parametrize("W", [8, 7, 16, 40])
+def test_gather_scatter_row_kernels_window_order_and_16_byte_paths(dev, oracle, dtype, W):
+    """The im2col-style gather out[i,j,n,c,:] = x[n,c,i+j,:] and its adjoint: overlapping windows are walked
+    window-axes-inside (every row carries its own result offset), runs move by 16-byte accesses when the run,
+    the strides and the base allow it (W = 7: never; sliced sources with odd bases: never)."""
+    rng = np.random.default_rng(16)
+    N, Cc, H, KH = 3, 4, 6, 3
+    x = rnd(rng, (N, Cc, H, W), dtype)
+    f = lambda i: [i[0] + i[1]]
+    for perm in ([2, 0, 1, 3], [2, 1, 0, 3]):
+        xh, d = np.transpose(x, perm), dev.stranspose(perm, dev.sconcrete(x))
+        got = dev.sgather([H, KH], d, f, 1)
+        ref = oracle.sgather([H, KH], xh, f, 1)
+        exact(dev.to_numpy(got), np.ascontiguousarray(ref))
+        exact(dev.to_numpy(dev.sscatter([H], got, f, 2)), oracle.sscatter([H], np.ascontiguousarray(ref), f, 2))
+    # contiguous source: the trailing axes merge into one long run (> 32 accesses)
+    exact(dev.to_numpy(dev.sgather([N + 1, 2], dev.sconcrete(x), f, 1)), np.ascontiguousarray(oracle.sgather([N + 1, 2], x, f, 1)))
+    # odd base offset (a slice of a flat buffer) and a both-sides out-of-bounds two-component window
+    flat = rnd(rng, (1 + H * H * W,), dtype)
+    v, dv = flat[1:].reshape(H, H, W), dev.sreshape([H, H, W], dev.sslice(1, H * H * W, dev.sconcrete(flat)))
+    g = lambda i: [i[0] + i[1] - 1, i[2] - i[0] + 1]
+    got = dev.sgather([H, 3, H], dv, g, 2)
+    ref = oracle.sgather([H, 3, H], v, g, 2)
+    exact(dev.to_numpy(got), np.ascontiguousarray(ref))
+    exact(dev.to_numpy(dev.sscatter([H, H], got, g, 3)), oracle.sscatter([H, H], np.ascontiguousarray(ref), g, 3))
+    # data-dependent index (offset table) over slices: table offsets are multiples of the access width or not
+    tbl = rng.integers(-1, H + 1, (5,)).astype(np.int64)
+    for src_np, src_d in ((v, dv), (x[0], dev.sindex(dev.sconcrete(x), [0]))):
+        h = lambda T: (lambda i: [T.ix_tbl(T.sconcrete(tbl), [i[0]])])
+        exact(dev.to_numpy(dev.sgather([5], src_d, h(dev), 1)), np.ascontiguousarray(oracle.sgather([5], src_np, h(oracle), 1)))
+    # scatter with untouched destinations (zeros written by the sum kernel), with and without collisions
+    y = rnd(rng, (4, 6, W), dtype)
+    for k in (lambda i: [2 * i[0]], lambda i: [i[0].quotH(2) * 3]):
+        exact(dev.to_numpy(dev.sscatter([9], dev.sconcrete(y), k, 1)), oracle.sscatter([9], y, k, 1))
 
 
 def test_gather_scatter_adjoint(dev):
