@@ -45,6 +45,11 @@ static int map2_into(hb_array *out, const hb_array *a, const hb_array *b, F f) {
   const hb_array *ops[3] = {out, a, b};
   hb_iter it;
   hb_make_iter(3, ops, &it);
+  if (hb_contig(out)) {
+    bool handled = false;
+    HB_TRY((hb_try_vecrows2<TO, TA, TB, F>(po, pa, pb, it, f, &handled)));
+    if (handled) return HB_OK;
+  }
   auto body = [=] __device__(int64_t, const int64_t *off) {
     po[off[0]] = f(pa[off[1]], pb[off[2]]);
   };
@@ -631,6 +636,60 @@ __global__ void hb_adam_kernel(T *p, T *m, T *v, const T *g, T alphat, T b1, T b
   }
 }
 
+// 16-byte accesses, two independent vectors per thread (seven streams:
+// p, m, v read + written, g read); same per-element arithmetic as above.
+template <typename T, int V>
+__global__ void __launch_bounds__(256)
+    hb_adam_vec_kernel(T *__restrict__ p, T *__restrict__ m, T *__restrict__ v, const T *__restrict__ g, T alphat,
+                       T b1, T b2, T eps, int64_t nvec) {
+  typedef hb_vec<T, V> VT;
+  VT *pv = reinterpret_cast<VT *>(p), *mv = reinterpret_cast<VT *>(m), *vv = reinterpret_cast<VT *>(v);
+  const VT *gv = reinterpret_cast<const VT *>(g);
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t s = (int64_t)gridDim.x * blockDim.x;
+  const T one = (T)1;
+  auto upd = [&](VT &pp, VT &mm, VT &vw, const VT &gg) {
+#pragma unroll
+    for (int k = 0; k < V; k++) {
+      T gi = gg.v[k];
+      T mn = b1 * mm.v[k] + (one - b1) * gi;
+      T vn = b2 * vw.v[k] + (one - b2) * (gi * gi);
+      mm.v[k] = mn;
+      vw.v[k] = vn;
+      pp.v[k] = pp.v[k] - alphat * mn / (sqrt(vn) + eps);
+    }
+  };
+  for (; i + s < nvec; i += 2 * s) {
+    VT g0 = gv[i], g1 = gv[i + s], m0 = mv[i], m1 = mv[i + s], v0 = vv[i], v1 = vv[i + s], p0 = pv[i], p1 = pv[i + s];
+    upd(p0, m0, v0, g0);
+    upd(p1, m1, v1, g1);
+    mv[i] = m0; vv[i] = v0; pv[i] = p0;
+    mv[i + s] = m1; vv[i + s] = v1; pv[i + s] = p1;
+  }
+  for (; i < nvec; i += s) {
+    VT g0 = gv[i], m0 = mv[i], v0 = vv[i], p0 = pv[i];
+    upd(p0, m0, v0, g0);
+    mv[i] = m0; vv[i] = v0; pv[i] = p0;
+  }
+}
+
+template <typename T>
+static void adam_launch(T *p, T *m, T *v, const T *g, T alphat, T b1, T b2, T eps, int64_t n) {
+  constexpr int V = 16 / (int)sizeof(T);
+  int64_t nvec = 0;
+  if (hb_aligned16(p) && hb_aligned16(m) && hb_aligned16(v) && hb_aligned16(g) && n >= 4 * V) {
+    nvec = n / V;
+    int blocks = hb_blocks_for((nvec + 1) / 2, 256, g_hb.sm_count * 16);
+    hb_adam_vec_kernel<T, V><<<blocks, 256, 0, g_hb.stream>>>(p, m, v, g, alphat, b1, b2, eps, nvec);
+  }
+  int64_t done = nvec * V;
+  if (done < n) {
+    if (done) g_hb.launches.fetch_add(1, std::memory_order_relaxed);  // second launch of this call
+    int blocks = hb_blocks_for(n - done, 256, g_hb.sm_count * 16);
+    hb_adam_kernel<T><<<blocks, 256, 0, g_hb.stream>>>(p + done, m + done, v + done, g + done, alphat, b1, b2, eps, n - done);
+  }
+}
+
 extern "C" int hb_adam_step(hb_array *p, hb_array *m, hb_array *v, const hb_array *g, double alpha,
                             double beta1, double beta2, double epsilon, int64_t t) {
   hb_prof_scope prof_("adam_step", p);
@@ -648,17 +707,15 @@ extern "C" int hb_adam_step(hb_array *p, hb_array *m, hb_array *v, const hb_arra
     gc = tmp;
   }
   double alphat = alpha * sqrt(1.0 - pow(beta2, (double)t)) / (1.0 - pow(beta1, (double)t));
-  int blocks = hb_blocks_for(n, 256, g_hb.sm_count * 16);
   int st = HB_OK;
   switch (p->dt) {
     case HB_F64:
-      hb_adam_kernel<double><<<blocks, 256, 0, g_hb.stream>>>((double *)hb_data(p), (double *)hb_data(m), (double *)hb_data(v),
-                                                              (const double *)hb_data(gc), alphat, beta1, beta2, epsilon, n);
+      adam_launch<double>((double *)hb_data(p), (double *)hb_data(m), (double *)hb_data(v), (const double *)hb_data(gc),
+                          alphat, beta1, beta2, epsilon, n);
       break;
     case HB_F32:
-      hb_adam_kernel<float><<<blocks, 256, 0, g_hb.stream>>>((float *)hb_data(p), (float *)hb_data(m), (float *)hb_data(v),
-                                                             (const float *)hb_data(gc), (float)alphat, (float)beta1,
-                                                             (float)beta2, (float)epsilon, n);
+      adam_launch<float>((float *)hb_data(p), (float *)hb_data(m), (float *)hb_data(v), (const float *)hb_data(gc),
+                         (float)alphat, (float)beta1, (float)beta2, (float)epsilon, n);
       break;
     default: hb_set_error("adam: floating dtype required"); st = HB_ERR_INVALID;
   }

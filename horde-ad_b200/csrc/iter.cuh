@@ -246,6 +246,122 @@ static int hb_try_vec2(TO *o, const TA *a, bool sa, const TB *b, bool sb, int64_
   return HB_OK;
 }
 
+// out (contiguous) = f(a, b) where the innermost collapsed axis of every
+// operand has stride 1 or 0 and the outer axes are arbitrary (bias add through
+// a stride-0 sreplicate view, NCHW tensor x per-channel factor, a row times a
+// column): 128-bit accesses on the unit-stride operands, one 32-bit
+// decomposition of the outer index per vector, 2 vectors in flight per thread.
+// The one-element-per-thread rows kernel moved such a bias add at 57 % of HBM.
+template <typename TO, typename TA, typename TB, int V, typename F>
+__global__ void __launch_bounds__(256)
+    hb_vecrows2_kernel(TO *__restrict__ o, const TA *__restrict__ a, const TB *__restrict__ b,
+                       const __grid_constant__ hb_iterp<3> it, unsigned nvrow, int64_t nvec, F f) {
+  const int orank = it.rank - 1;
+  const bool ua = it.stride[1][orank] != 0, ub = it.stride[2][orank] != 0;
+  int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t gstride = (int64_t)gridDim.x * blockDim.x;
+  hb_vec<TO, V> *ov = reinterpret_cast<hb_vec<TO, V> *>(o);
+  auto offsets = [&](int64_t v, int64_t &oa, int64_t &ob) {
+    unsigned outer = (unsigned)(v / nvrow);
+    unsigned iv = (unsigned)(v - (int64_t)outer * nvrow);
+    oa = ua ? (int64_t)iv * V : 0;
+    ob = ub ? (int64_t)iv * V : 0;
+#pragma unroll 1
+    for (int d = orank - 1; d >= 0; d--) {
+      unsigned sh = (unsigned)it.shape[d];
+      unsigned q = outer / sh, r = outer - q * sh;
+      oa += (int64_t)r * it.stride[1][d];
+      ob += (int64_t)r * it.stride[2][d];
+      outer = q;
+    }
+  };
+  auto load_a = [&](int64_t off, hb_vec<TA, V> &x) {
+    if (ua) x = *reinterpret_cast<const hb_vec<TA, V> *>(a + off);
+    else {
+      TA s = a[off];
+#pragma unroll
+      for (int k = 0; k < V; k++) x.v[k] = s;
+    }
+  };
+  auto load_b = [&](int64_t off, hb_vec<TB, V> &x) {
+    if (ub) x = *reinterpret_cast<const hb_vec<TB, V> *>(b + off);
+    else {
+      TB s = b[off];
+#pragma unroll
+      for (int k = 0; k < V; k++) x.v[k] = s;
+    }
+  };
+  int64_t i = gid;
+  for (; i + gstride < nvec; i += 2 * gstride) {
+    int64_t oa0, ob0, oa1, ob1;
+    offsets(i, oa0, ob0);
+    offsets(i + gstride, oa1, ob1);
+    hb_vec<TA, V> a0, a1;
+    hb_vec<TB, V> b0, b1;
+    load_a(oa0, a0);
+    load_a(oa1, a1);
+    load_b(ob0, b0);
+    load_b(ob1, b1);
+    hb_vec<TO, V> r0, r1;
+#pragma unroll
+    for (int k = 0; k < V; k++) {
+      r0.v[k] = f(a0.v[k], b0.v[k]);
+      r1.v[k] = f(a1.v[k], b1.v[k]);
+    }
+    ov[i] = r0;
+    ov[i + gstride] = r1;
+  }
+  for (; i < nvec; i += gstride) {
+    int64_t oa0, ob0;
+    offsets(i, oa0, ob0);
+    hb_vec<TA, V> a0;
+    hb_vec<TB, V> b0;
+    load_a(oa0, a0);
+    load_b(ob0, b0);
+    hb_vec<TO, V> r0;
+#pragma unroll
+    for (int k = 0; k < V; k++) r0.v[k] = f(a0.v[k], b0.v[k]);
+    ov[i] = r0;
+  }
+}
+
+// Returns handled = true if (out, a, b) fit the vector-rows shape; `it` is the
+// collapsed iteration space of (out, a, b) with out contiguous.
+template <typename TO, typename TA, typename TB, typename F>
+static int hb_try_vecrows2(TO *o, const TA *a, const TB *b, const hb_iter &it, F f, bool *handled) {
+  constexpr size_t big = sizeof(TO) > sizeof(TA) ? (sizeof(TO) > sizeof(TB) ? sizeof(TO) : sizeof(TB))
+                                                 : (sizeof(TA) > sizeof(TB) ? sizeof(TA) : sizeof(TB));
+  constexpr int V = 16 / big;
+  *handled = false;
+  if (it.rank < 2) return HB_OK;
+  const int last = it.rank - 1;
+  const int64_t inner = it.shape[last];
+  if (inner % V || inner < 4 * V || it.stride[0][last] != 1) return HB_OK;
+  int64_t n = 1;
+  for (int d = 0; d < it.rank; d++) n *= it.shape[d];
+  if (n < (1 << 16) || n / inner >= (1ll << 31) || inner / V >= (1ll << 31)) return HB_OK;
+  if (((uintptr_t)o) % (sizeof(TO) * V)) return HB_OK;
+  const size_t esz[3] = {sizeof(TO), sizeof(TA), sizeof(TB)};
+  const void *ptr[3] = {o, a, b};
+  for (int op = 1; op < 3; op++) {
+    int64_t sl = it.stride[op][last];
+    if (sl != 0 && sl != 1) return HB_OK;
+    if (sl == 1) {
+      if (((uintptr_t)ptr[op]) % (esz[op] * V)) return HB_OK;
+      for (int d = 0; d < last; d++)
+        if (it.stride[op][d] % V) return HB_OK;
+    }
+  }
+  hb_iterp<3> p;
+  hb_iterp_from<3>(it, &p);
+  int64_t nvec = n / V;
+  int blocks = hb_blocks_for((nvec + 1) / 2 + 1, 256, g_hb.sm_count * 16);
+  hb_vecrows2_kernel<TO, TA, TB, V, F><<<blocks, 256, 0, g_hb.stream>>>(o, a, b, p, (unsigned)(inner / V), nvec, f);
+  HB_LAUNCHED();
+  *handled = true;
+  return HB_OK;
+}
+
 #endif  // __CUDACC__
 
 // operand classification for the vector path

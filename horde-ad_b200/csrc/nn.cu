@@ -250,20 +250,18 @@ __global__ void __launch_bounds__(256)
   __shared__ T sm[8];
   const int c = blockIdx.x, chunk = blockIdx.y;
   const int n0 = chunk * npc, n1 = n0 + npc < N ? n0 + npc : N;
-  const int HW = Ho * Wo;
-  const int64_t cnt = (int64_t)(n1 - n0) * HW;
+  const unsigned HW = (unsigned)(Ho * Wo);
+  const unsigned cnt = (unsigned)(n1 - n0) * HW;   // < 2^31 (checked by the host)
   T acc = T(0);
-  for (int64_t i = threadIdx.x; i < cnt; i += blockDim.x) {
-    int n = n0 + (int)(i / HW), w = (int)(i % HW);
-    int wi = w / Wo, wj = w - wi * Wo;
-    int64_t o = ((int64_t)n * C + c) * HW + w;
-    uint8_t cd = code[o];
-    T dv = dy[o];               // independent of the code load (no serialised latency)
+  // one pooled element: 32-bit index arithmetic, the window written with two 16-byte stores
+  auto elem = [&](unsigned i, uint8_t cd, T dv) {
     T g = (cd & 0x80) ? dv : T(0);
     acc += g;
-    if (!WRITE) continue;
+    if (!WRITE) return;
+    unsigned nn = i / HW, w = i - nn * HW;
+    unsigned wi = w / (unsigned)Wo, wj = w - wi * (unsigned)Wo;
     int bi = cd & 0x7f;
-    T *p = dpre + (((int64_t)n * C + c) * H + (int64_t)wi * ks) * W + (int64_t)wj * ks;
+    T *p = dpre + (((int64_t)(n0 + (int)nn) * C + c) * H + (int64_t)wi * ks) * W + (int64_t)wj * ks;
     if (VEC2) {
       typedef hb_vec<T, 2> V;
       V r0, r1;
@@ -275,6 +273,25 @@ __global__ void __launch_bounds__(256)
       for (int a = 0; a < ks; a++)
         for (int b = 0; b < ks; b++) p[(int64_t)a * W + b] = (a * ks + b == bi) ? g : T(0);
     }
+  };
+  // element i of image n0 + i / HW sits at ((n0 * C + c) * HW + i) + (i / HW) * (C - 1) * HW
+  const T *dyb = dy + ((int64_t)n0 * C + c) * HW;
+  const uint8_t *cdb = code + ((int64_t)n0 * C + c) * HW;
+  const int64_t skip = (int64_t)(C - 1) * HW;
+  unsigned i = threadIdx.x;
+  for (; i + 768 < cnt; i += 1024) {           // four independent loads of dy and code in flight
+    int64_t o0 = i + (i / HW) * skip, o1 = (i + 256) + ((i + 256) / HW) * skip;
+    int64_t o2 = (i + 512) + ((i + 512) / HW) * skip, o3 = (i + 768) + ((i + 768) / HW) * skip;
+    uint8_t c0 = cdb[o0], c1 = cdb[o1], c2 = cdb[o2], c3 = cdb[o3];
+    T d0 = dyb[o0], d1 = dyb[o1], d2 = dyb[o2], d3 = dyb[o3];
+    elem(i, c0, d0);
+    elem(i + 256, c1, d1);
+    elem(i + 512, c2, d2);
+    elem(i + 768, c3, d3);
+  }
+  for (; i < cnt; i += 256) {
+    int64_t o0 = i + (i / HW) * skip;
+    elem(i, cdb[o0], dyb[o0]);
   }
   acc = hb_warp_sum(acc);
   if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
@@ -325,11 +342,15 @@ extern "C" int hb_relu_pool_bwd(const hb_array *dy, const hb_array *code, int ks
       cudaError_t e = cudaMemsetAsync(hb_data(dx), 0, (size_t)hb_numel(dx) * es, g_hb.stream);
       if (e != cudaSuccess) { hb_set_error("memset: %s", cudaGetErrorString(e)); st = HB_ERR_CUDA; }
     }
-    int nchunks = (int)((4 * (int64_t)g_hb.sm_count + C - 1) / C);
+    int nchunks = (int)((8 * (int64_t)g_hb.sm_count + C - 1) / C);
     if (nchunks > N) nchunks = (int)N;
     if (nchunks < 1) nchunks = 1;
     int npc = (int)((N + nchunks - 1) / nchunks);
     nchunks = (int)((N + npc - 1) / npc);
+    if (st == HB_OK && (int64_t)npc * dy->shape[2] * dy->shape[3] >= (1ll << 31)) {
+      hb_set_error("relu_pool_bwd: more than 2^31 pooled elements per (channel, image chunk)");
+      st = HB_ERR_INVALID;
+    }
     void *scr = nullptr;
     if (st == HB_OK) st = hb_scratch((size_t)C * nchunks * es, &scr);
     if (st == HB_OK && hb_numel(dy) > 0) {

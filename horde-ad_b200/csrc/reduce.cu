@@ -202,6 +202,21 @@ __global__ void hb_finish_partials_kernel(const ACC *__restrict__ part, T *__res
   out[k] = (T)acc;
 }
 
+// Few outputs, many partials (ssum0 / sdot0: K = 1, S ~ 1200): one block per
+// output, threads take the partials interleaved, fixed-shape tree at the end
+// (the one-thread loop above is a chain of S dependent adds behind L2 loads:
+// 40 us of a 130 us ssum0 at n = 2^26).
+template <typename ACC, typename T>
+__global__ void __launch_bounds__(256)
+    hb_finish_partials_block_kernel(const ACC *__restrict__ part, T *__restrict__ out, int64_t K, int S) {
+  __shared__ ACC smem[32];
+  const int64_t k = blockIdx.x;
+  ACC acc = ACC(0);
+  for (int s = threadIdx.x; s < S; s += 256) acc += part[(int64_t)s * K + k];
+  acc = hb_block_sum<ACC>(acc, smem);
+  if (threadIdx.x == 0) out[k] = (T)acc;
+}
+
 // kept axes / reduced axes given as index lists into the operands' axes.
 template <typename T, bool DOT>
 static int reduce_typed(const hb_array *a, const hb_array *b, int nk, const int *kax, int nr,
@@ -319,7 +334,10 @@ static int reduce_typed(const hb_array *a, const hb_array *b, int nk, const int 
     hb_reduce_cols_kernel<T, ACC, DOT><<<grid, block, 0, g_hb.stream>>>(p, pa, pb, dst, rchunk);
   HB_LAUNCHED();
   if (!direct) {
-    hb_finish_partials_kernel<ACC, T><<<hb_blocks_for(p.K, 256), 256, 0, g_hb.stream>>>(dst, po, p.K, S);
+    if (S >= 64 && p.K <= 4096)
+      hb_finish_partials_block_kernel<ACC, T><<<(unsigned)p.K, 256, 0, g_hb.stream>>>(dst, po, p.K, S);
+    else
+      hb_finish_partials_kernel<ACC, T><<<hb_blocks_for(p.K, 256), 256, 0, g_hb.stream>>>(dst, po, p.K, S);
     HB_LAUNCHED();
   }
   return HB_OK;

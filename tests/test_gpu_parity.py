@@ -159,6 +159,60 @@ def test_large_vector_path(dev):
     exact(dev.to_numpy(dev.unary("negate", off)), -a[1:])
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32, np.int64, np.int32, np.int16, np.int8])
+def test_vector_rows_path_broadcast_views(dev, oracle, dtype):
+    """hb_vecrows2_kernel: unit-stride or stride-0 innermost axis, arbitrary
+    outer strides (stride-0 sreplicate views, sreverse, slices, permuted outer
+    axes), >= 2^16 elements; bit-exact against numpy for every width."""
+    rng = np.random.default_rng(41)
+    N, Cc, H, W = 9, 6, 28, 64
+    x = rnd(rng, (N, Cc, H, W), dtype)
+    dx = dev.sconcrete(x)
+    bias = rnd(rng, (Cc,), dtype)
+    # per-channel operand seen through sreplicate + stranspose (innermost stride 0)
+    dv = dev.stranspose([0, 3, 1, 2], dev.sreplicateN([N, H, W], dev.sconcrete(bias)))
+    rv = oracle.stranspose([0, 3, 1, 2], oracle.sreplicateN([N, H, W], bias))
+    exact(dev.to_numpy(dev.binary("add", dx, dv)), x + rv)
+    exact(dev.to_numpy(dev.binary("sub", dv, dx)), rv - x)
+    # a row broadcast along every outer axis (innermost stride 1, outer strides 0)
+    row = rnd(rng, (W,), dtype)
+    exact(dev.to_numpy(dev.binary("mul", dx, dev.sreplicateN([N, Cc, H], dev.sconcrete(row)))), x * row)
+    # outer axes permuted / reversed / sliced, innermost axis untouched
+    y = rnd(rng, (Cc, N, H, W), dtype)
+    exact(dev.to_numpy(dev.binary("add", dx, dev.stranspose([1, 0, 2, 3], dev.sconcrete(y)))), x + y.transpose(1, 0, 2, 3))
+    z = rnd(rng, (N + 3, Cc, H, W), dtype)
+    dz = dev.sconcrete(z)
+    exact(dev.to_numpy(dev.binary("add", dev.sreverse(dx), dev.sslice(2, N, dz))), x[::-1] + z[2:2 + N])
+    # both operands broadcast differently: outer product [N*Cc*H] x [W]
+    col = rnd(rng, (N, Cc, H), dtype)
+    dcol = dev.stranspose([1, 2, 3, 0], dev.sreplicateN([W], dev.sconcrete(col)))
+    exact(dev.to_numpy(dev.binary("mul", dcol, dev.sreplicateN([N, Cc, H], dev.sconcrete(row)))), col[..., None] * row)
+    # innermost extent not a multiple of the vector width -> the scalar rows kernel, same answer
+    x2 = rnd(rng, (N, Cc, H, W + 1), dtype)
+    dv2 = dev.stranspose([0, 3, 1, 2], dev.sreplicateN([N, H, W + 1], dev.sconcrete(bias)))
+    exact(dev.to_numpy(dev.binary("add", dev.sconcrete(x2), dv2)),
+          x2 + oracle.stranspose([0, 3, 1, 2], oracle.sreplicateN([N, H, W + 1], bias)))
+
+
+def test_full_reductions_block_finish(dev, oracle):
+    """ssum0 / sdot0 over > 2^21 elements go through ~1200 partials and the
+    block-wide finish kernel; two runs give the same bits (fixed tree)."""
+    rng = np.random.default_rng(43)
+    for dtype in (np.float64, np.float32):
+        n = (1 << 22) + 40
+        a, b = rnd(rng, (n,), dtype), rnd(rng, (n,), dtype)
+        da, db = dev.sconcrete(a), dev.sconcrete(b)
+        s1, s2 = dev.to_numpy(dev.ssum0(da)).reshape(1), dev.to_numpy(dev.ssum0(da)).reshape(1)
+        exact(s1, s2)
+        close(s1.reshape(()), np.asarray(a.astype(np.float64).sum()).astype(dtype), dtype, scale=100)
+        d1, d2 = dev.to_numpy(dev.sdot0(da, db)).reshape(1), dev.to_numpy(dev.sdot0(da, db)).reshape(1)
+        exact(d1, d2)
+        close(d1.reshape(()), np.asarray(np.dot(a.astype(np.float64), b.astype(np.float64))).astype(dtype), dtype, scale=100)
+    # few outputs, long reduced axis: K = 3 outputs, each through its own block of the finish kernel
+    t = rng.uniform(-.5, .5, (3, 1 << 20))
+    close(dev.to_numpy(dev.ssumN(dev.stranspose([1, 0], dev.sconcrete(t)), 1)), t.sum(axis=1), scale=100)
+
+
 def test_casts_iota_compare(dev, oracle):
     rng = np.random.default_rng(5)
     for src in ALL_DTYPES:
@@ -691,13 +745,14 @@ def test_fused_conv_layer(dev, oracle, dtype, shape, ks):
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
-def test_optimizers(dev, oracle, dtype):
+@pytest.mark.parametrize("n", [1000, 1003, 3])     # 16-byte vectors only / vectors + scalar tail / scalar only
+def test_optimizers(dev, oracle, dtype, n):
     rng = np.random.default_rng(18)
-    p, g = rnd(rng, (1000,), dtype), rnd(rng, (1000,), dtype)
-    m, v = np.zeros(1000, dtype), np.zeros(1000, dtype)
+    p, g = rnd(rng, (n,), dtype), rnd(rng, (n,), dtype)
+    m, v = np.zeros(n, dtype), np.zeros(n, dtype)
     dp, dm, dv = dev.sconcrete(p), dev.sconcrete(m), dev.sconcrete(v)
     for t in range(1, 4):
-        g = rnd(rng, (1000,), dtype)
+        g = rnd(rng, (n,), dtype)
         dev.adam_step(dp, dm, dv, dev.sconcrete(g), t)
         oracle.adam_step(p, m, v, g, t)
     close(dev.to_numpy(dp), p, dtype, scale=10)
