@@ -1213,7 +1213,8 @@ int hb_conv_dk_dmma(const hb_array *A, const hb_array *dB, const hb_array *code,
   if (Co <= 8) { WM = 1; MO = 1; }
   else if (Co <= 16) { WM = 1; MO = 2; }
   else if (Co <= 32) { WM = 2; MO = 2; }
-  else { WM = 4; MO = 2; }
+  else { WM = 2; MO = 2; }  // 32-channel tiles: two CTAs per SM (see the band choice below)
+  if (Co > 32) { const char *e = getenv("HB_DK_WM"); if (e && atoi(e) == 4) WM = 4; }
   int otile = WM * MO * 8, not_ = (Co + otile - 1) / otile;
   int wrest = 8 / WM;  // warps left for pairs x K
   int KK = KH * KW;
@@ -1232,6 +1233,11 @@ int hb_conv_dk_dmma(const hb_array *A, const hb_array *dB, const hb_array *code,
     int ncf = maxpairs / KK;  // column fragments of 8 channels
     int need = (Ci + 7) / 8;
     if (ncf > need) ncf = need;
+    // 32-channel output tiles take 16 input channels per CTA (K split over the two spare warps) so that two
+    // CTAs fit one SM: ConvVjpBench dKrn 0.613 ms (64 x 16 tile, one CTA) -> 0.513 (32 x 32, one CTA, TMA)
+    // -> 0.501 ms (32 x 16, two CTAs, TMA)
+    if (WM == 2 && ncf > 2) ncf = 2;
+    { const char *e = getenv("HB_DK_NCF"); if (e && atoi(e) > 0 && atoi(e) <= maxpairs / KK) ncf = atoi(e) < need ? atoi(e) : need; }
     // balance the chunks
     int chunks = (need + ncf - 1) / ncf;
     ncf = (need + chunks - 1) / chunks;
@@ -1277,14 +1283,34 @@ int hb_conv_dk_dmma(const hb_array *A, const hb_array *dB, const hb_array *code,
     return smem_need() <= budget && red_bytes <= budget;
   };
   int R = 0;
-  for (int nb = 1; nb <= H && !R; nb++) {  // fewest bands first
-    int r = (H + nb - 1) / nb;
-    if (nb <= 4 && fits(r, kSmemMax / 2 - 1024)) { R = r; ctas = 2; }
+  int maxnb2 = 4, forceR = 0;
+  { const char *e = getenv("HB_DK_MAXNB"); if (e) maxnb2 = atoi(e); e = getenv("HB_DK_R"); if (e) forceR = atoi(e); }
+  if (forceR > 0 && forceR <= H) {
+    if (fits(forceR, kSmemMax / 2 - 1024)) { R = forceR; ctas = 2; }
+    else if (fits(forceR, kSmemMax)) { R = forceR; ctas = 1; }
   }
+  // Two CTAs per SM first: with one CTA (two warps per scheduler) ncu shows the DMMA pipe idle a third of
+  // the time on fixed-latency waits (ConvVjpBench shape: 65 % -> 77 % of the FP64 peak with two).  Fewest
+  // bands first, but a band height that divides H (whole bands: TMA staging applies) wins over a ragged one
+  // as long as bands keep at least 4 rows.
+  int r_any = 0;
   for (int nb = 1; nb <= H && !R; nb++) {
     int r = (H + nb - 1) / nb;
-    if (fits(r, kSmemMax)) { R = r; ctas = 1; }
+    if (nb > maxnb2 && r < 4) break;
+    if (!fits(r, kSmemMax / 2 - 1024)) continue;
+    if (H % r == 0 || pooled || tapw) { R = r; ctas = 2; }
+    else if (!r_any) r_any = r;
   }
+  if (!R && r_any) { R = r_any; ctas = 2; }
+  r_any = 0;
+  for (int nb = 1; nb <= H && !R; nb++) {  // one CTA per SM: same preference for whole bands
+    int r = (H + nb - 1) / nb;
+    if (r_any && r < 4) break;
+    if (!fits(r, kSmemMax)) continue;
+    if (H % r == 0 || pooled || tapw) { R = r; ctas = 1; }
+    else if (!r_any) r_any = r;
+  }
+  if (!R && r_any) { R = r_any; ctas = 1; }
   if (!R) return HB_OK;
   fits(R, kSmemMax);
   g.bands = (H + g.R - 1) / g.R;
@@ -1351,6 +1377,9 @@ int hb_conv_dk_dmma(const hb_array *A, const hb_array *dB, const hb_array *code,
   HB_TRY(hb_scratch((size_t)splits * nout * 8, &scr));
   p.part = (double *)scr;
   dim3 grid((unsigned)splits, (unsigned)ncc, (unsigned)not_);
+  if (getenv("HB_CONV_DEBUG"))
+    fprintf(stderr, "dk: WM=%d MO=%d CC=%d npairs=%d WN=%d WK=%d R=%d ctas=%d tma=%d RS=%d smem=%d grid=(%d,%d,%d) items=%d\n", WM, MO,
+            CC, npairs, p.WN, p.WK, g.R, ctas, p.tma, g.RS, smem_bytes, splits, ncc, not_, p.items);
 #define DK_LAUNCH(WM_, MO_)                                                                  \
   do {                                                                                       \
     if (tapw) {                                                                              \
