@@ -306,7 +306,10 @@ template <int WM, int WN, int MF, int NQ, bool TAPK, int MINB, bool POOL>
 __global__ void __launch_bounds__(kThreads, MINB) conv_sp_kernel(const __grid_constant__ SpP p) {
   extern __shared__ __align__(128) double smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int wm = warp % WM, wn = warp / WM;
+  // Warp w runs on scheduler w % 4, so with WM = 4 the two warps of a scheduler (w, w + 4) would own the same
+  // warp row: 25 fragments over 4 rows is 7/6/6/6, i.e. 14 fragment columns on one tensor pipe and 12 on the
+  // others.  The second channel column takes its rows rotated by two: 13/12/13/12.
+  const int wn = warp / WM, wm = (warp % WM + ((WN == 2 && WM == 4) ? 2 * wn : 0)) % WM;
   const int fr = lane >> 2, fk = lane & 3;
   const TileGeo &g = p.g;
   unsigned long long *mbar = reinterpret_cast<unsigned long long *>(smem + p.mbar);  // [2], TMA staging only
