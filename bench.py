@@ -486,16 +486,16 @@ def profile_step(dev, ffi, CnnTrainer, local_batch, gl, lb, world, steps=3):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed
-# `ncu --set full` capture (profiles/r01_conv_kernels_v4_full_raw.csv), keyed
+# `ncu --set full` capture (profiles/r01_conv_kernels_v5_full_raw.csv), keyed
 # by (launch-site function, operand shapes of the entry)
 NCU_TRAFFIC = {   # (launch site, C-ABI entry) -> dram__bytes_read.sum + dram__bytes_write.sum per launch
-    ("hb_conv_dk_dmma", "conv_relu_pool_bwd"): 242541056 + 4610560,    # conv2 dKrn (two row bands per image: halo rows read twice)
-    ("hb_conv_sp_dmma", "conv_relu_pool_fwd"): 102901760 + 11578624,   # conv2 fwd + bias/relu/pool
-    ("hb_conv_sp_dmma", "conv_relu_pool_bwd"): 102915840 + 59598336,   # conv2 dInp (rest of the write still in L2)
-    ("hb_conv_strip_fwd", "conv_relu_pool_fwd"): 25731840 + 58855936,  # conv1 fwd + bias/relu/pool
-    ("hb_conv_strip_dk", "conv_relu_pool_bwd"): 141382144 + 4252928,   # conv1 dKrn + bias cotangent
+    ("hb_conv_dk_dmma", "conv_relu_pool_bwd"): 242468096 + 5267200,    # conv2 dKrn (two row bands per image: halo rows read twice)
+    ("hb_conv_sp_dmma", "conv_relu_pool_fwd"): 102900992 + 14155520,   # conv2 fwd + bias/relu/pool
+    ("hb_conv_sp_dmma", "conv_relu_pool_bwd"): 102893824 + 58643200,   # conv2 dInp (rest of the write still in L2)
+    ("hb_conv_strip_fwd", "conv_relu_pool_fwd"): 25750528 + 58959616,  # conv1 fwd + bias/relu/pool
+    ("hb_conv_strip_dk", "conv_relu_pool_bwd"): 141343232 + 3762944,   # conv1 dKrn + bias cotangent
 }
-NCU_TRAFFIC_SOURCE = "profiles/r01_conv_kernels_v4_full_raw.csv (ncu --set full, per launch)"
+NCU_TRAFFIC_SOURCE = "profiles/r01_conv_kernels_v5_full_raw.csv (ncu --set full, per launch)"
 
 
 def ncu_traffic(entry: str, site: str):

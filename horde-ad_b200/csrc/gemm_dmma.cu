@@ -380,7 +380,10 @@ int hb_gemm_dmma(const double *A, int64_t a_sm, int64_t a_sk, const double *B, i
     }
     p.kchunks = (chunks8 + splits - 1) / splits;
     splits = (chunks8 + p.kchunks - 1) / p.kchunks;
-    const bool serial = splits == 2 && tiles8 <= kFlagTiles;
+    // serial split-K up to three slices ([128,4096]x[4096,3136], 98 tiles x 3: 125 vs 168 us with the four-warp
+    // kernel + reduce); four slices over 64 tiles lose to it ([512,1024]x[1024,512]: 36 vs 29 us)
+    static const int serial_max = getenv("HB_GEMM_SERIAL") ? atoi(getenv("HB_GEMM_SERIAL")) : 3;
+    const bool serial = splits >= 2 && splits <= serial_max && tiles8 <= kFlagTiles;
     // measured (tools/gemm_sweep.py): the eight-warp kernel wins on large grids (2048^3: 563 vs 602 us,
     // [512,512]x[512,8192]: 145 vs 159 us), on ~one tile per SM with two K slices ([512,512]x[512,1024]:
     // 29 vs 33 us) and on very deep K over a few tiles ([64,4096]x[4096,784]: 27 vs 32 us); the four-warp
@@ -388,6 +391,7 @@ int hb_gemm_dmma(const double *A, int64_t a_sm, int64_t a_sk, const double *B, i
     const int64_t ctas8 = tiles8 * splits, slots8 = 2 * (int64_t)g_hb.sm_count;
     bool use8 = (splits == 1 && 3 * tiles8 >= 2 * slots8) || (splits == 2 && 5 * ctas8 >= 4 * slots8) ||
                 (splits > 4 && chunks8 >= 64);
+    if (serial && splits > 2) use8 = true;
     if (force >= 0) use8 = force != 0;
     if (use8) {
       p.C = C;

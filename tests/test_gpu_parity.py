@@ -363,7 +363,8 @@ def test_matmul_family(dev, oracle, dtype):
                                    (512, 512, 1024),     # one tile per SM: two K slices accumulated serially into C
                                    (500, 518, 1001),     # the same with ragged edges and an odd row stride of C
                                    (100, 4100, 200),     # deep K over 8 tiles: many slices + fixed-order reduce
-                                   (512, 1024, 512)])    # four-warp kernel, split-K across CTAs
+                                   (512, 1024, 512),     # four-warp kernel, split-K across CTAs
+                                   (128, 1030, 3136)])   # 98 tiles: three K slices accumulated serially into C
 def test_dmma_gemm_variants_and_determinism(dev, shape):
     m, k, n = shape
     rng = np.random.default_rng(91)
