@@ -19,6 +19,7 @@ DeltaEval.hs:720-730; accumulation :139-148,317-332).
 from __future__ import annotations
 
 import heapq
+import os
 import itertools
 from typing import Callable, Sequence
 
@@ -312,9 +313,12 @@ class ADBackend:
     def smatmul2(self, a, b):
         B = self.B
         a, b = self.lift(a), self.lift(b)
+        # the two cotangents are handed to the sweep as DEFERRED products, so that a contribution to a cotangent
+        # that already exists (a weight used at every time step of an unrolled loop) is accumulated by the GEMM
+        # itself (`smatmul2_acc`) instead of being materialised and added in a second pass
         return self._node(B.smatmul2(a.p, b.p), [a, b],
-                          lambda c: [B.smatmul2(c, B.stranspose([1, 0], b.p)),
-                                     B.smatmul2(B.stranspose([1, 0], a.p), c)])
+                          lambda c: [DeferredMatmul(c, B.stranspose([1, 0], b.p)),
+                                     DeferredMatmul(B.stranspose([1, 0], a.p), c)])
 
     def smatvecmul(self, m, v):
         B = self.B
@@ -401,6 +405,20 @@ class ADBackend:
         return self._node(prod, [x], lambda c: [B.prod_fold_grad(x.p, float(B.kfromS(c)))[1]])
 
 
+_NO_MATMUL_ACC = bool(os.environ.get("HB_AD_NO_MATMUL_ACC"))   # measurement switch: product + separate add
+
+
+class DeferredMatmul:
+    """A cotangent contribution `smatmul2 a b` not yet evaluated (see ADBackend.smatmul2)."""
+    __slots__ = ("a", "b")
+
+    def __init__(self, a, b):
+        self.a, self.b = a, b
+
+    def force(self, base):
+        return base.smatmul2(self.a, self.b)
+
+
 def grad(base, f: Callable, inputs: Sequence, dt=None):
     """cgrad / cvjp (ADEngine.hs:544-555): returns (value, [gradients]).
 
@@ -435,13 +453,22 @@ def grad(base, f: Callable, inputs: Sequence, dt=None):
             for parent, pc in zip(node.parents, cs):
                 if parent is None or pc is None:
                     continue
+                deferred = isinstance(pc, DeferredMatmul)
                 if parent.id in cot:
                     if parent.id in owned:
-                        cot[parent.id] = base.add_accumulate(cot[parent.id], pc)
+                        if deferred and not _NO_MATMUL_ACC:
+                            cot[parent.id] = base.smatmul2_acc(cot[parent.id], pc.a, pc.b)
+                        elif deferred:
+                            cot[parent.id] = base.add_accumulate(cot[parent.id], pc.force(base))
+                        else:
+                            cot[parent.id] = base.add_accumulate(cot[parent.id], pc)
                     else:
-                        cot[parent.id] = base.binary("add", cot[parent.id], pc)
+                        cot[parent.id] = base.binary("add", cot[parent.id], pc.force(base) if deferred else pc)
                         owned.add(parent.id)
                 else:
+                    if deferred:   # a fresh array that nobody else holds: the sweep may update it in place
+                        pc = pc.force(base)
+                        owned.add(parent.id)
                     cot[parent.id] = pc
                     nodes[parent.id] = parent
                     heapq.heappush(heap, -parent.id)

@@ -248,13 +248,16 @@ static int launch_contract(hb_contractp &P, const hb_array *a, const hb_array *b
 
 // gemm_dmma.cu
 int hb_gemm_dmma(const double *A, int64_t a_sm, int64_t a_sk, const double *B, int64_t b_sk, int64_t b_sn, double *C,
-                 int64_t M, int64_t N, int64_t K, int *done);
+                 int64_t M, int64_t N, int64_t K, int accum, int *done);
 int hb_reduce_generic(const hb_array *a, const hb_array *b, int nk, const int *kax, int nr,
                       const int *rax, hb_array *out);
 
 // a, b: equal shapes.  Axes [0, n_lead) and the last axis are contracted; the
 // axes in between index the result.
-static int contract_impl(const hb_array *a, const hb_array *b, int n_lead, hb_array **out) {
+// `acc` (hb_matmul2_acc): a uniquely referenced contiguous f64 array of the result's shape that the DMMA GEMM
+// may accumulate into (C += A x B); *acc_used reports whether it did (then *out = acc, retained).
+static int contract_impl(const hb_array *a, const hb_array *b, int n_lead, hb_array **out, hb_array *acc = nullptr,
+                         int *acc_used = nullptr) {
   HB_CHECK_INIT();
   HB_REQUIRE(a && b && out, "null argument");
   HB_REQUIRE(a->dt == b->dt && hb_same_shape(a, b), "sdot1In: %s %s vs %s %s", hb_dtype_name(a->dt),
@@ -328,10 +331,18 @@ static int contract_impl(const hb_array *a, const hb_array *b, int n_lead, hb_ar
           if (st == HB_OK) { pb = (const double *)hb_data(tb); P.N.sb[0] = P.K.n; P.K.sb[0] = 1; }
         }
         if (st != HB_OK) { hb_release(ta); hb_release(tb); hb_release(o); return st; }
+        const int accum = acc != nullptr;
+        if (accum) pc = (double *)hb_data(acc);  // same shape, contiguous: same layout as o
         if (P.N.sc[0] == 1 && P.M.sc[0] == P.N.n)
-          st = hb_gemm_dmma(pa, P.M.sa[0], P.K.sa[0], pb, P.K.sb[0], P.N.sb[0], pc, P.M.n, P.N.n, P.K.n, &done);
+          st = hb_gemm_dmma(pa, P.M.sa[0], P.K.sa[0], pb, P.K.sb[0], P.N.sb[0], pc, P.M.n, P.N.n, P.K.n, accum, &done);
         else if (P.M.sc[0] == 1 && P.N.sc[0] == P.M.n)  // output is [N, M]: C^T = B^T A^T
-          st = hb_gemm_dmma(pb, P.N.sb[0], P.K.sb[0], pa, P.K.sa[0], P.M.sa[0], pc, P.N.n, P.M.n, P.K.n, &done);
+          st = hb_gemm_dmma(pb, P.N.sb[0], P.K.sb[0], pa, P.K.sa[0], P.M.sa[0], pc, P.N.n, P.M.n, P.K.n, accum, &done);
+        if (accum && done && st == HB_OK) {
+          hb_release(o);
+          hb_retain(acc);
+          o = acc;
+          *acc_used = 1;
+        }
         hb_release(ta);
         hb_release(tb);
       }
@@ -385,6 +396,40 @@ extern "C" int hb_matmul2(const hb_array *a, const hb_array *b, hb_array **out) 
   int st = contract_impl(av, bv, 0, out);
   hb_release(av);
   hb_release(bv);
+  return st;
+}
+
+// acc + a x b.  Cotangent accumulation of a weight (taddTarget of evalRev, DeltaEval.hs:317-332, applied to the
+// result of the transposition rule of tsmatmul2): when `acc` is uniquely referenced, contiguous and f64 and the
+// DMMA GEMM takes the shape, the product is accumulated straight into acc's storage (the GEMM epilogue reads C) and
+// *out = acc; otherwise the product is formed and added as hb_matmul2 + hb_add_inplace_or_new would.
+extern "C" int hb_matmul2_acc(hb_array *acc, const hb_array *a, const hb_array *b, hb_array **out) {
+  hb_prof_scope prof_("matmul2_acc", a, b);
+  HB_REQUIRE(acc && a && b && out, "null argument");
+  HB_REQUIRE(a->rank == 2 && b->rank == 2 && a->shape[1] == b->shape[0], "smatmul2: %s x %s",
+             hb_shape_str(a).c_str(), hb_shape_str(b).c_str());
+  HB_REQUIRE(acc->rank == 2 && acc->shape[0] == a->shape[0] && acc->shape[1] == b->shape[1] && acc->dt == a->dt,
+             "matmul2_acc: accumulator %s %s does not match the product", hb_dtype_name(acc->dt),
+             hb_shape_str(acc).c_str());
+  const bool unique = acc->dt == HB_F64 && acc->rc.load() == 1 && acc->st && acc->st->rc.load() == 1 &&
+                      hb_contig(acc) && acc->st != a->st && acc->st != b->st;
+  hb_array *av = hb_new_view(a), *bv = hb_new_view(b);
+  av->rank = bv->rank = 3;
+  av->shape[0] = a->shape[0]; av->strides[0] = a->strides[0];
+  av->shape[1] = b->shape[1]; av->strides[1] = 0;
+  av->shape[2] = a->shape[1]; av->strides[2] = a->strides[1];
+  bv->shape[0] = a->shape[0]; bv->strides[0] = 0;
+  bv->shape[1] = b->shape[1]; bv->strides[1] = b->strides[1];
+  bv->shape[2] = b->shape[0]; bv->strides[2] = b->strides[0];
+  hb_array *prod = nullptr;
+  int used = 0;
+  int st = contract_impl(av, bv, 0, &prod, unique ? acc : nullptr, &used);
+  hb_release(av);
+  hb_release(bv);
+  if (st != HB_OK) return st;
+  if (used) { *out = prod; return HB_OK; }
+  st = hb_add_inplace_or_new(acc, prod, out);
+  hb_release(prod);
   return st;
 }
 

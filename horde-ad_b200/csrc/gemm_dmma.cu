@@ -48,6 +48,7 @@ struct GemmP {
   int kchunks;          // BK-chunks per split
   int a_vec, b_vec;     // 16-byte cp.async allowed
   int *flags;           // serial split-K: per output tile, the number of K slices already accumulated into C
+  int accum;            // C += A x B (taddTarget fused into the product: cotangent accumulation of a weight)
 };
 
 // Stage one operand tile: `rows` x BK where the operand's (row, k) element is
@@ -168,11 +169,18 @@ __global__ void __launch_bounds__(128 * KS) gemm_dmma_kernel(const __grid_consta
       int m = m0 + wm + i * 8 + fr, n = n0 + wn + j * 8 + fk * 2;
       if (m < p.M) {
         double *c = C + (int64_t)m * p.c_sm + n;
-        if (n + 1 < p.N && (p.c_sm & 1) == 0 && ((uintptr_t)C & 15) == 0)
-          *reinterpret_cast<double2 *>(c) = make_double2(acc[i][j][0], acc[i][j][1]);
-        else {
-          if (n < p.N) c[0] = acc[i][j][0];
-          if (n + 1 < p.N) c[1] = acc[i][j][1];
+        const bool addc = p.accum && gridDim.z == 1;  // with K slices the reduce kernel adds the old C
+        if (n + 1 < p.N && (p.c_sm & 1) == 0 && ((uintptr_t)C & 15) == 0) {
+          double2 o = make_double2(acc[i][j][0], acc[i][j][1]);
+          if (addc) {
+            double2 t = *reinterpret_cast<const double2 *>(c);
+            o.x = t.x + o.x;
+            o.y = t.y + o.y;
+          }
+          *reinterpret_cast<double2 *>(c) = o;
+        } else {
+          if (n < p.N) c[0] = addc ? c[0] + acc[i][j][0] : acc[i][j][0];
+          if (n + 1 < p.N) c[1] = addc ? c[1] + acc[i][j][1] : acc[i][j][1];
         }
       }
     }
@@ -291,7 +299,7 @@ __global__ void __launch_bounds__(256, 2) gemm8_dmma_kernel(const __grid_constan
     }
     __syncthreads();
   }
-  const bool addc = serial && z > 0;
+  const bool addc = serial ? (z > 0 || p.accum) : (p.accum && gridDim.z == 1);
   const bool cvec = (p.c_sm & 1) == 0 && ((uintptr_t)C & 15) == 0;
 #pragma unroll
   for (int i = 0; i < 4; i++)
@@ -321,12 +329,13 @@ __global__ void __launch_bounds__(256, 2) gemm8_dmma_kernel(const __grid_constan
   }
 }
 
-__global__ void gemm_reduce_kernel(const double *__restrict__ part, double *__restrict__ out, int64_t n, int splits) {
+__global__ void gemm_reduce_kernel(const double *__restrict__ part, double *__restrict__ out, int64_t n, int splits,
+                                   int accum) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double s = 0.0;
   for (int k = 0; k < splits; k++) s += part[(int64_t)k * n + i];
-  out[i] = s;
+  out[i] = accum ? out[i] + s : s;
 }
 
 }  // namespace
@@ -348,7 +357,7 @@ static int gemm_flags(int **out) {
 
 // C (contiguous [M,N] f64) = A x B with element strides; *done = 1 if handled.
 int hb_gemm_dmma(const double *A, int64_t a_sm, int64_t a_sk, const double *B, int64_t b_sk, int64_t b_sn, double *C,
-                 int64_t M, int64_t N, int64_t K, int *done) {
+                 int64_t M, int64_t N, int64_t K, int accum, int *done) {
   *done = 0;
   if (M <= 0 || N <= 0 || K <= 0) return HB_OK;
   if (M >= (1ll << 31) || N >= (1ll << 31) || K >= (1ll << 31)) return HB_OK;
@@ -362,6 +371,7 @@ int hb_gemm_dmma(const double *A, int64_t a_sm, int64_t a_sk, const double *B, i
   p.M = (int)M; p.N = (int)N; p.K = (int)K;
   p.a_sm = a_sm; p.a_sk = a_sk; p.b_sk = b_sk; p.b_sn = b_sn;
   p.c_sm = N;
+  p.accum = accum;
   p.a_vec = ((uintptr_t)A & 15) == 0 && ((a_kfast ? a_sm : a_sk) % 2 == 0);
   p.b_vec = ((uintptr_t)B & 15) == 0 && ((b_kfast ? b_sn : b_sk) % 2 == 0);
   int gm = (int)((M + BM - 1) / BM), gn = (int)((N + BN - 1) / BN);
@@ -419,7 +429,7 @@ int hb_gemm_dmma(const double *A, int64_t a_sm, int64_t a_sk, const double *B, i
       HB_LAUNCHED();
       if (splits > 1 && !serial) {
         int64_t n = M * N;
-        gemm_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, g_hb.stream>>>(p.C, C, n, splits);
+        gemm_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, g_hb.stream>>>(p.C, C, n, splits, accum);
         HB_LAUNCHED();
       }
       *done = 1;
@@ -470,7 +480,7 @@ int hb_gemm_dmma(const double *A, int64_t a_sm, int64_t a_sk, const double *B, i
   HB_LAUNCHED();
   if (splits > 1) {
     int64_t n = M * N;
-    gemm_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, g_hb.stream>>>(p.C, C, n, splits);
+    gemm_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, g_hb.stream>>>(p.C, C, n, splits, accum);
     HB_LAUNCHED();
   }
   *done = 1;

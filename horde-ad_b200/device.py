@@ -300,6 +300,16 @@ class DeviceBackend:
         call("hb_matmul2", a.h, b.h, C.byref(p))
         return _wrap(p)
 
+    def smatmul2_acc(self, acc, a, b):
+        """taddTarget acc (smatmul2 a b) in one call: accumulated by the GEMM epilogue straight into `acc`
+        when it is uniquely referenced (hb_matmul2_acc)."""
+        p = _out()
+        call("hb_matmul2_acc", acc.h, a.h, b.h, C.byref(p))
+        if p.value == acc.h.value:  # same handle, retained once more
+            ffi._lib.hb_release(p)
+            return acc
+        return _wrap(p)
+
     def smatvecmul(self, m, v):
         p = _out()
         call("hb_matvecmul", m.h, v.h, C.byref(p))

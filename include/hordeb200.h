@@ -364,6 +364,14 @@ int hb_dot_inner_sum_leading(const hb_array *a, const hb_array *b, int n_axes,
 /* tsmatmul2 / tsmatvecmul (OpsConcrete.hs:236-242). */
 int hb_matmul2(const hb_array *a, const hb_array *b, hb_array **out);
 int hb_matvecmul(const hb_array *m, const hb_array *v, hb_array **out);
+/* acc + a x b: the cotangent accumulation `taddTarget acc (tsmatmul2 a b)` of
+ * evalRev (DeltaEval.hs:139-148,317-332 applied to the transposition rule of
+ * tsmatmul2) as one call.  When `acc` is uniquely referenced, contiguous and
+ * f64 and the DMMA GEMM takes the shape, the product is accumulated straight
+ * into acc's storage by the GEMM epilogue and *out is acc (retained once
+ * more); otherwise it equals hb_matmul2 followed by hb_add_inplace_or_new. */
+int hb_matmul2_acc(hb_array *acc, const hb_array *a, const hb_array *b,
+                   hb_array **out);
 /* tsargMax / tsargMin (OpsConcrete.hs:1712-1746): reduce the LAST axis,
  * result shape Init sh, dtype I64; first extremum wins. */
 int hb_argmax_last(const hb_array *a, hb_array **out);

@@ -233,6 +233,10 @@ class ConcreteBackend:
         b = self.stranspose([0, 2, 1], self.sreplicate(m1.shape[0], m2))
         return self.sdot1In(a, b)
 
+    def smatmul2_acc(self, acc, m1, m2):
+        """taddTarget acc (tsmatmul2 m1 m2) (DeltaEval.hs:139-148)."""
+        return acc + self.smatmul2(m1, m2)
+
     # tsargMax / tsargMin reduce the LAST axis, Int result of shape Init sh
     # (OpsConcrete.hs:1712-1746); first extremum (unpinned in the reference)
     def sargMax(self, t):

@@ -380,6 +380,62 @@ def test_dmma_gemm_variants_and_determinism(dev, shape):
                 assert np.array_equal(dev.to_numpy(dev.smatmul2(A, B)), got)
 
 
+@pytest.mark.parametrize("shape", [(512, 1024, 512),     # four-warp kernel + reduce kernel that adds the old C
+                                   (512, 512, 1024),     # two K slices accumulated serially, slice 0 adds the old C
+                                   (1024, 320, 1200),    # eight-warp kernel, one slice
+                                   (128, 1030, 3136),    # three serial slices
+                                   (64, 70, 48),         # four-warp kernel, one slice
+                                   (512, 1024, 28),      # thin N
+                                   (3, 5, 2)])           # no GEMM path: product + add
+def test_matmul2_acc(dev, shape):
+    """hb_matmul2_acc = taddTarget acc (tsmatmul2 a b): in place through the GEMM epilogue when `acc` is
+    uniquely referenced, a fresh array otherwise; same value either way (1e-12 relative)."""
+    m, k, n = shape
+    rng = np.random.default_rng(92)
+    a, b, c0 = rnd(rng, (m, k)), rnd(rng, (k, n)), rnd(rng, (m, n))
+    ref = c0 + a @ b
+    A, B = dev.sconcrete(a), dev.stranspose([1, 0], dev.sconcrete(b.T.copy()))
+    acc = dev.sconcrete(c0)
+    out = dev.smatmul2_acc(acc, A, B)
+    close(dev.to_numpy(out), ref, np.float64, scale=k)
+    if min(m, n) >= 16:
+        assert out is acc                                   # accumulated in place
+    out2 = dev.smatmul2_acc(out, A, B)                      # and again (the cotangent of a weight used twice)
+    close(dev.to_numpy(out2), ref + a @ b, np.float64, scale=2 * k)
+    # an accumulator that somebody else still holds is not touched
+    acc = dev.sconcrete(c0)
+    alias = dev.sreshape([m, n], acc)                       # a second handle on the same storage
+    out = dev.smatmul2_acc(acc, A, B)
+    assert out is not acc
+    exact(dev.to_numpy(alias), c0)
+    close(dev.to_numpy(out), ref, np.float64, scale=k)
+    # a transposed (non-contiguous) accumulator: product + add
+    acct = dev.stranspose([1, 0], dev.sconcrete(c0.T.copy()))
+    close(dev.to_numpy(dev.smatmul2_acc(acct, A, B)), ref, np.float64, scale=k)
+    # deterministic
+    r1 = dev.to_numpy(dev.smatmul2_acc(dev.sconcrete(c0), A, B))
+    r2 = dev.to_numpy(dev.smatmul2_acc(dev.sconcrete(c0), A, B))
+    assert np.array_equal(r1, r2)
+
+
+def test_grad_accumulates_weight_cotangents_in_the_gemm(dev, oracle):
+    """A weight used at every step of an unrolled loop: the sweep hands its cotangent contributions to
+    smatmul2_acc (ad.DeferredMatmul); same gradient as the oracle's matmul + add."""
+    rng = np.random.default_rng(93)
+    w, x = rng.uniform(-.3, .3, (64, 64)), rng.uniform(-.5, .5, (64, 96))
+
+    def f(T, W, X):
+        h = X
+        for _ in range(4):
+            h = T.unary("tanh", T.smatmul2(W, h))
+        return T.ssum0(T.binary("mul", h, h))
+    dv, dg = ad.grad(dev, f, [dev.sconcrete(w), dev.sconcrete(x)])
+    ov, og = ad.grad(oracle, f, [w, x])
+    close(dev.to_numpy(dv).reshape(()), np.asarray(ov), scale=100)
+    for g, o in zip(dg, og):
+        close(dev.to_numpy(g), np.asarray(o), scale=1000)
+
+
 @pytest.mark.parametrize("dtype", [np.float64, np.float32, np.int8])
 def test_transposed_views_materialise_bit_exact(dev, dtype):
     """hb_contiguous / reshape of transposed views (tiled shared-memory transpose fast path and the generic
