@@ -34,6 +34,10 @@ from horde_ad_b200 import ad, ffi, mnist_fcnn, mnist_rnn  # noqa: E402
 from horde_ad_b200.device import DeviceBackend  # noqa: E402
 
 
+# fusion level of the RNN layer body: "pair" (smatmul2_sum + tanh_affine nodes), "1" (tanh_affine only), "0" (literal)
+RNN_FUSION = {"pair": "pair", "1": True, "0": False}[os.environ.get("HB_RNN_FUSION", "pair")]
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     return (float(json.load(open(p))["hbm_gbs"]), "measured") if os.path.exists(p) else (6650.0, "fallback")
@@ -251,7 +255,7 @@ def main():
     tstep = [0]
 
     def rnn_grad():
-        return ad.grad(dev, lambda T, *ps: mnist_rnn.rnnMnistLossFusedS(T, glyphs, labels, list(ps), fused=True), params)
+        return ad.grad(dev, lambda T, *ps: mnist_rnn.rnnMnistLossFusedS(T, glyphs, labels, list(ps), fused=RNN_FUSION), params)
 
     def rnn_apply(grads):
         tstep[0] += 1

@@ -320,6 +320,28 @@ class ADBackend:
                           lambda c: [DeferredMatmul(c, B.stranspose([1, 0], b.p)),
                                      DeferredMatmul(B.stranspose([1, 0], a.p), c)])
 
+    def smatmul2_sum(self, a1, b1, a2, b2):
+        """smatmul2 a1 b1 + smatmul2 a2 b2 as ONE node (the pre-activation `wX x + wS s` of rnnMnistLayerS,
+        MnistRnnShaped2.hs:55-69): one paired launch forward; backward the two left cotangents are deferred
+        products marked as partners (the sweep accumulates both weights' cotangents in one launch) and the two
+        right cotangents, which share c, come from one paired launch."""
+        B = self.B
+        a1, b1, a2, b2 = self.lift(a1), self.lift(b1), self.lift(a2), self.lift(b2)
+        tr = lambda t: B.stranspose([1, 0], t)
+
+        def pb(c):
+            da1 = DeferredMatmul(c, tr(b1.p)) if a1.d is not None else None
+            da2 = DeferredMatmul(c, tr(b2.p)) if a2.d is not None else None
+            if da1 is not None and da2 is not None:
+                da1.partner, da2.partner = 2, 0          # slot of the partner in this node's parent list
+            if b1.d is not None and b2.d is not None and B.shape(a1.p) == B.shape(a2.p):
+                db1, db2 = B.smatmul2_pair(tr(a1.p), c, tr(a2.p), c)
+            else:
+                db1 = DeferredMatmul(tr(a1.p), c) if b1.d is not None else None
+                db2 = DeferredMatmul(tr(a2.p), c) if b2.d is not None else None
+            return [da1, db1, da2, db2]
+        return self._node(B.smatmul2_sum(a1.p, b1.p, a2.p, b2.p), [a1, b1, a2, b2], pb)
+
     def smatvecmul(self, m, v):
         B = self.B
         m, v = self.lift(m), self.lift(v)
@@ -356,7 +378,15 @@ class ADBackend:
         """The body of rnnMnistLayerS (MnistRnnShaped2.hs:55-69) as one node: tanh ((u + v) + bias
         stretched over the batch); dz = (1 - y * y) * c is the cotangent of u and of v."""
         B = self.B
-        u, v, bias = self.lift(u), self.lift(v), self.lift(bias)
+        u, bias = self.lift(u), self.lift(bias)
+        if v is None:        # u already holds the sum (smatmul2_sum)
+            y = B.tanh_affine_fwd(u.p, None, bias.p)
+
+            def pb1(c):
+                dz, db = B.tanh_affine_bwd(y, c, want_bias=bias.d is not None)
+                return [dz, db]
+            return self._node(y, [u, bias], pb1)
+        v = self.lift(v)
         y = B.tanh_affine_fwd(u.p, v.p, bias.p)
 
         def pb(c):
@@ -410,10 +440,11 @@ _NO_MATMUL_ACC = bool(os.environ.get("HB_AD_NO_MATMUL_ACC"))   # measurement swi
 
 class DeferredMatmul:
     """A cotangent contribution `smatmul2 a b` not yet evaluated (see ADBackend.smatmul2)."""
-    __slots__ = ("a", "b")
+    __slots__ = ("a", "b", "partner")
 
     def __init__(self, a, b):
         self.a, self.b = a, b
+        self.partner = None     # parent slot of a second deferred product that may share the launch
 
     def force(self, base):
         return base.smatmul2(self.a, self.b)
@@ -449,7 +480,18 @@ def grad(base, f: Callable, inputs: Sequence, dt=None):
             if nid in input_ix:
                 grads[input_ix[nid]] = c
                 continue
-            cs = node.pullback(c)
+            cs = list(node.pullback(c))
+            # two deferred products marked as partners whose cotangents both exist and are owned by the sweep:
+            # both accumulations in one launch
+            for i, pc in enumerate(cs):
+                j = pc.partner if isinstance(pc, DeferredMatmul) else None
+                if j is None or j <= i or not isinstance(cs[j], DeferredMatmul) or _NO_MATMUL_ACC:
+                    continue
+                pi, pj = node.parents[i], node.parents[j]
+                if (pi is not None and pj is not None and pi.id != pj.id and pi.id in owned and pj.id in owned
+                        and pi.id in cot and pj.id in cot):
+                    cot[pi.id], cot[pj.id] = base.smatmul2_acc_pair(cot[pi.id], pc.a, pc.b, cot[pj.id], cs[j].a, cs[j].b)
+                    cs[i] = cs[j] = None
             for parent, pc in zip(node.parents, cs):
                 if parent is None or pc is None:
                     continue
@@ -636,6 +678,9 @@ class FwdBackend:
     def sdot1In(self, a, b): return self._bilinear(self.B.sdot1In, a, b)
     def smatmul2(self, a, b): return self._bilinear(self.B.smatmul2, a, b)
     def smatvecmul(self, m, v): return self._bilinear(self.B.smatvecmul, m, v)
+
+    def smatmul2_sum(self, a1, b1, a2, b2):
+        return self.binary("add", self.smatmul2(a1, b1), self.smatmul2(a2, b2))
     def conv2dPreserving(self, K, A): return self._bilinear(self.B.conv2dPreserving, K, A)
 
     def sdot1InSumN(self, a, b, n):
@@ -665,7 +710,7 @@ class FwdBackend:
 
     def tanh_affine(self, u, v, bias):
         batch = self.shape(u)[1]
-        return self.unary("tanh", self.binary("add", self.binary("add", u, v),
+        return self.unary("tanh", self.binary("add", self.binary("add", u, v) if v is not None else u,
                                               self.stranspose([1, 0], self.sreplicate(batch, bias))))
 
     def conv_relu_pool(self, K, bias, A, ksize):

@@ -249,6 +249,10 @@ static int launch_contract(hb_contractp &P, const hb_array *a, const hb_array *b
 // gemm_dmma.cu
 int hb_gemm_dmma(const double *A, int64_t a_sm, int64_t a_sk, const double *B, int64_t b_sk, int64_t b_sn, double *C,
                  int64_t M, int64_t N, int64_t K, int accum, int *done);
+int hb_gemm_dmma_pair(const double *A1, int64_t a1_sm, int64_t a1_sk, const double *B1, int64_t b1_sk, int64_t b1_sn,
+                      int64_t K1, const double *A2, int64_t a2_sm, int64_t a2_sk, const double *B2, int64_t b2_sk,
+                      int64_t b2_sn, int64_t K2, double *C1, double *C2, int64_t M, int64_t N, int chain, int accum,
+                      int *done);
 int hb_reduce_generic(const hb_array *a, const hb_array *b, int nk, const int *kax, int nr,
                       const int *rax, hb_array *out);
 
@@ -430,6 +434,130 @@ extern "C" int hb_matmul2_acc(hb_array *acc, const hb_array *a, const hb_array *
   if (used) { *out = prod; return HB_OK; }
   st = hb_add_inplace_or_new(acc, prod, out);
   hb_release(prod);
+  return st;
+}
+
+// ---- pairs of products in one launch (the recurrent layer wX x + wS s of MnistRnnShaped2.hs:55-69 and the
+// transposition rules of its two tsmatmul2) ----
+namespace {
+struct Op2 { const double *p; int64_t s0, s1; };
+// a rank-2 f64 array as a GEMM operand with one unit stride; size-1 axes get a benign stride
+bool op2(const hb_array *a, Op2 *o) {
+  if (!a || a->rank != 2 || a->dt != HB_F64 || a->shape[0] <= 0 || a->shape[1] <= 0) return false;
+  o->p = (const double *)hb_data(a);
+  o->s0 = a->strides[0];
+  o->s1 = a->strides[1];
+  if (a->shape[0] == 1) o->s0 = o->s1 == 1 ? a->shape[1] : 1;
+  if (a->shape[1] == 1) o->s1 = o->s0 == 1 ? a->shape[0] : 1;
+  return o->s0 == 1 || o->s1 == 1;
+}
+// ... packing an operand with no unit stride first (a row slice of a transposed batch, e.g. the glyph rows of
+// MnistRnnShaped2): O(rows * K) against the O(M * N * K) product.  *tmp holds the packed copy (release it).
+bool op2_pack(const hb_array *a, Op2 *o, hb_array **tmp) {
+  *tmp = nullptr;
+  if (op2(a, o)) return true;
+  if (!a || a->rank != 2 || a->dt != HB_F64 || a->shape[0] <= 0 || a->shape[1] <= 0) return false;
+  if (hb_contiguous(a, tmp) != HB_OK) { *tmp = nullptr; return false; }
+  return op2(*tmp, o);
+}
+bool pair_shapes_ok(const hb_array *a1, const hb_array *b1, const hb_array *a2, const hb_array *b2) {
+  return a1->rank == 2 && b1->rank == 2 && a2->rank == 2 && b2->rank == 2 && a1->shape[1] == b1->shape[0] &&
+         a2->shape[1] == b2->shape[0] && a1->shape[0] == a2->shape[0] && b1->shape[1] == b2->shape[1];
+}
+bool acc_unique(const hb_array *acc, const hb_array *a, const hb_array *b) {
+  return acc->dt == HB_F64 && acc->rc.load() == 1 && acc->st && acc->st->rc.load() == 1 && hb_contig(acc) &&
+         acc->st != a->st && acc->st != b->st;
+}
+}  // namespace
+
+extern "C" int hb_matmul2_sum(const hb_array *a1, const hb_array *b1, const hb_array *a2, const hb_array *b2,
+                              hb_array **out) {
+  hb_prof_scope prof_("matmul2_sum", a1, b1);
+  HB_CHECK_INIT();
+  HB_REQUIRE(a1 && b1 && a2 && b2 && out, "null argument");
+  HB_REQUIRE(pair_shapes_ok(a1, b1, a2, b2), "smatmul2 + smatmul2: %s x %s + %s x %s", hb_shape_str(a1).c_str(),
+             hb_shape_str(b1).c_str(), hb_shape_str(a2).c_str(), hb_shape_str(b2).c_str());
+  Op2 A1, B1, A2, B2;
+  hb_array *tmp[4] = {nullptr, nullptr, nullptr, nullptr};
+  auto drop = [&]() { for (hb_array *t : tmp) hb_release(t); };
+  if (op2_pack(a1, &A1, &tmp[0]) && op2_pack(b1, &B1, &tmp[1]) && op2_pack(a2, &A2, &tmp[2]) &&
+      op2_pack(b2, &B2, &tmp[3])) {
+    int64_t sh[2] = {a1->shape[0], b1->shape[1]};
+    hb_array *o;
+    int st = hb_new_array(HB_F64, 2, sh, &o);
+    if (st != HB_OK) { drop(); return st; }
+    int done = 0;
+    st = hb_gemm_dmma_pair(A1.p, A1.s0, A1.s1, B1.p, B1.s0, B1.s1, a1->shape[1], A2.p, A2.s0, A2.s1, B2.p, B2.s0,
+                           B2.s1, a2->shape[1], (double *)hb_data(o), nullptr, sh[0], sh[1], 1, 0, &done);
+    if (st != HB_OK || done) drop();
+    if (st != HB_OK) { hb_release(o); return st; }
+    if (done) { *out = o; return HB_OK; }
+    hb_release(o);
+  }
+  drop();
+  hb_array *t = nullptr;
+  HB_TRY(hb_matmul2(a1, b1, &t));
+  int st = hb_matmul2_acc(t, a2, b2, out);
+  hb_release(t);
+  return st;
+}
+
+extern "C" int hb_matmul2_pair(const hb_array *a1, const hb_array *b1, const hb_array *a2, const hb_array *b2,
+                               hb_array **out1, hb_array **out2) {
+  hb_prof_scope prof_("matmul2_pair", a1, b1);
+  HB_CHECK_INIT();
+  HB_REQUIRE(a1 && b1 && a2 && b2 && out1 && out2, "null argument");
+  HB_REQUIRE(a1->rank == 2 && b1->rank == 2 && a2->rank == 2 && b2->rank == 2 && a1->shape[1] == b1->shape[0] &&
+                 a2->shape[1] == b2->shape[0],
+             "smatmul2 pair: %s x %s, %s x %s", hb_shape_str(a1).c_str(), hb_shape_str(b1).c_str(),
+             hb_shape_str(a2).c_str(), hb_shape_str(b2).c_str());
+  Op2 A1, B1, A2, B2;
+  if (pair_shapes_ok(a1, b1, a2, b2) && op2(a1, &A1) && op2(b1, &B1) && op2(a2, &A2) && op2(b2, &B2)) {
+    int64_t sh[2] = {a1->shape[0], b1->shape[1]};
+    hb_array *o1, *o2;
+    HB_TRY(hb_new_array(HB_F64, 2, sh, &o1));
+    int st = hb_new_array(HB_F64, 2, sh, &o2);
+    if (st != HB_OK) { hb_release(o1); return st; }
+    int done = 0;
+    st = hb_gemm_dmma_pair(A1.p, A1.s0, A1.s1, B1.p, B1.s0, B1.s1, a1->shape[1], A2.p, A2.s0, A2.s1, B2.p, B2.s0,
+                           B2.s1, a2->shape[1], (double *)hb_data(o1), (double *)hb_data(o2), sh[0], sh[1], 0, 0, &done);
+    if (st == HB_OK && done) { *out1 = o1; *out2 = o2; return HB_OK; }
+    hb_release(o1);
+    hb_release(o2);
+    if (st != HB_OK) return st;
+  }
+  HB_TRY(hb_matmul2(a1, b1, out1));
+  int st = hb_matmul2(a2, b2, out2);
+  if (st != HB_OK) { hb_release(*out1); *out1 = nullptr; }
+  return st;
+}
+
+extern "C" int hb_matmul2_acc_pair(hb_array *acc1, const hb_array *a1, const hb_array *b1, hb_array *acc2,
+                                   const hb_array *a2, const hb_array *b2, hb_array **out1, hb_array **out2) {
+  hb_prof_scope prof_("matmul2_acc_pair", a1, b1);
+  HB_CHECK_INIT();
+  HB_REQUIRE(acc1 && acc2 && a1 && b1 && a2 && b2 && out1 && out2, "null argument");
+  Op2 A1, B1, A2, B2;
+  if (a1->rank == 2 && b1->rank == 2 && a2->rank == 2 && b2->rank == 2 && pair_shapes_ok(a1, b1, a2, b2) &&
+      acc1->rank == 2 && acc2->rank == 2 && acc1->shape[0] == a1->shape[0] && acc1->shape[1] == b1->shape[1] &&
+      hb_same_shape(acc1, acc2) && acc_unique(acc1, a1, b1) && acc_unique(acc2, a2, b2) && acc1->st != acc2->st &&
+      acc1->st != a2->st && acc1->st != b2->st && acc2->st != a1->st && acc2->st != b1->st && op2(a1, &A1) &&
+      op2(b1, &B1) && op2(a2, &A2) && op2(b2, &B2)) {
+    int done = 0;
+    HB_TRY(hb_gemm_dmma_pair(A1.p, A1.s0, A1.s1, B1.p, B1.s0, B1.s1, a1->shape[1], A2.p, A2.s0, A2.s1, B2.p, B2.s0,
+                             B2.s1, a2->shape[1], (double *)hb_data(acc1), (double *)hb_data(acc2), acc1->shape[0],
+                             acc1->shape[1], 0, 1, &done));
+    if (done) {
+      hb_retain(acc1);
+      hb_retain(acc2);
+      *out1 = acc1;
+      *out2 = acc2;
+      return HB_OK;
+    }
+  }
+  HB_TRY(hb_matmul2_acc(acc1, a1, b1, out1));
+  int st = hb_matmul2_acc(acc2, a2, b2, out2);
+  if (st != HB_OK) { hb_release(*out1); *out1 = nullptr; }
   return st;
 }
 

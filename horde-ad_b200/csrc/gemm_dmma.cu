@@ -49,6 +49,14 @@ struct GemmP {
   int a_vec, b_vec;     // 16-byte cp.async allowed
   int *flags;           // serial split-K: per output tile, the number of K slices already accumulated into C
   int accum;            // C += A x B (taddTarget fused into the product: cotangent accumulation of a weight)
+  // A second product of the same [M, N] in the same launch (hb_gemm_dmma_pair): K slices z >= zsplit work on it.
+  // chain = 1: both products are accumulated into ONE C in one serial chain (C = A x B + A2 x B2);
+  // chain = 0: two results, C and C2, each with its own serial chain (flags of the second at flags + tiles).
+  const double *A2, *B2;
+  double *C2;
+  int K2, kchunks2, a_vec2, b_vec2;
+  int64_t a_sm2, a_sk2, b_sk2, b_sn2;
+  int zsplit, chain;
 };
 
 // Stage one operand tile: `rows` x BK where the operand's (row, k) element is
@@ -238,15 +246,23 @@ __global__ void __launch_bounds__(256, 2) gemm8_dmma_kernel(const __grid_constan
   const int wm = (warp & 1) * 32, wn = (warp >> 1) * 16;
   const int fr = lane >> 2, fk = lane & 3;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
-  const int kbeg = blockIdx.z * p.kchunks * BK8;
-  int kend = kbeg + p.kchunks * BK8;
-  if (kend > p.K) kend = p.K;
+  // which product this K slice belongs to, and its slice index there
+  const bool second = p.zsplit > 0 && (int)blockIdx.z >= p.zsplit;
+  const double *__restrict__ gA = second ? p.A2 : p.A, *__restrict__ gB = second ? p.B2 : p.B;
+  const int64_t a_sm = second ? p.a_sm2 : p.a_sm, a_sk = second ? p.a_sk2 : p.a_sk;
+  const int64_t b_sk = second ? p.b_sk2 : p.b_sk, b_sn = second ? p.b_sn2 : p.b_sn;
+  const int a_vec = second ? p.a_vec2 : p.a_vec, b_vec = second ? p.b_vec2 : p.b_vec;
+  const int Kp = second ? p.K2 : p.K, kch = second ? p.kchunks2 : p.kchunks;
+  const int zl = second ? (int)blockIdx.z - p.zsplit : (int)blockIdx.z;
+  const int kbeg = zl * kch * BK8;
+  int kend = kbeg + kch * BK8;
+  if (kend > Kp) kend = Kp;
   const int nk = kend > kbeg ? (kend - kbeg + BK8 - 1) / BK8 : 0;
 
   auto issue = [&](int c) {
     double *as = smem + (c % STAGES8) * 2 * TILE8, *bs = as + TILE8;
-    stage_tile8<A_KFAST>(as, p.A, p.a_sm, p.a_sk, m0, p.M, kbeg + c * BK8, kend, p.a_vec, tid);
-    stage_tile8<B_KFAST>(bs, p.B, p.b_sn, p.b_sk, n0, p.N, kbeg + c * BK8, kend, p.b_vec, tid);
+    stage_tile8<A_KFAST>(as, gA, a_sm, a_sk, m0, p.M, kbeg + c * BK8, kend, a_vec, tid);
+    stage_tile8<B_KFAST>(bs, gB, b_sn, b_sk, n0, p.N, kbeg + c * BK8, kend, b_vec, tid);
     cp_commit();
   };
   double acc[4][2][2];
@@ -291,7 +307,15 @@ __global__ void __launch_bounds__(256, 2) gemm8_dmma_kernel(const __grid_constan
   const bool serial = p.flags != nullptr;
   double *C = serial ? p.C : p.C + (int64_t)blockIdx.z * p.M * p.c_sm;
   int *flag = serial ? p.flags + blockIdx.y * gridDim.x + blockIdx.x : nullptr;
-  const int z = blockIdx.z;
+  int z = blockIdx.z, zlen = gridDim.z;   // position in / length of this tile's serial chain
+  if (p.zsplit > 0 && !p.chain) {          // two results: each product has its own chain
+    z = zl;
+    zlen = second ? (int)gridDim.z - p.zsplit : p.zsplit;
+    if (second) {
+      C = p.C2;
+      flag += gridDim.x * gridDim.y;
+    }
+  }
   if (serial && z > 0) {
     if (tid == 0) {
       while (*reinterpret_cast<volatile int *>(flag) != z) __nanosleep(64);
@@ -322,10 +346,10 @@ __global__ void __launch_bounds__(256, 2) gemm8_dmma_kernel(const __grid_constan
         }
       }
     }
-  if (serial && gridDim.z > 1) {
+  if (serial && zlen > 1) {
     __threadfence();
     __syncthreads();
-    if (tid == 0) *reinterpret_cast<volatile int *>(flag) = z + 1 == (int)gridDim.z ? 0 : z + 1;
+    if (tid == 0) *reinterpret_cast<volatile int *>(flag) = z + 1 == zlen ? 0 : z + 1;
   }
 }
 
@@ -486,3 +510,77 @@ int hb_gemm_dmma(const double *A, int64_t a_sm, int64_t a_sk, const double *B, i
   *done = 1;
   return HB_OK;
 }
+
+// Two products of the same [M, N] in ONE launch of the eight-warp kernel (the recurrent layer of
+// MnistRnnShaped2 runs ~one 64 x 64 tile per SM per product: pairing fills the second CTA slot of every SM
+// and halves launches and epilogues):
+//   chain = 1:  C  = (accum ? C : 0) + A1 x B1 + A2 x B2        (C2 ignored)   -- wX x + wS s
+//   chain = 0:  C  = (accum ? C  : 0) + A1 x B1,  C2 = (accum ? C2 : 0) + A2 x B2 -- the two input cotangents
+//               that share dY, or the two weight cotangents that share it on the other side
+// K may differ between the products; both must have the same operand orientations.  Slices of one tile are
+// combined in slice order through the per-tile flags (deterministic).  *done = 0: shapes not taken.
+int hb_gemm_dmma_pair(const double *A1, int64_t a1_sm, int64_t a1_sk, const double *B1, int64_t b1_sk, int64_t b1_sn,
+                      int64_t K1, const double *A2, int64_t a2_sm, int64_t a2_sk, const double *B2, int64_t b2_sk,
+                      int64_t b2_sn, int64_t K2, double *C1, double *C2, int64_t M, int64_t N, int chain, int accum,
+                      int *done) {
+  *done = 0;
+  if (M <= 0 || N <= 0 || K1 <= 0 || K2 <= 0) return HB_OK;
+  if (M >= (1ll << 31) || N >= (1ll << 31) || K1 >= (1ll << 31) || K2 >= (1ll << 31)) return HB_OK;
+  const bool a_kfast = a1_sk == 1, b_kfast = b1_sk == 1;
+  // one template instantiation serves both products: same operand orientations
+  if (a_kfast ? a2_sk != 1 : (a1_sm != 1 || a2_sm != 1)) return HB_OK;
+  if (b_kfast ? b2_sk != 1 : (b1_sn != 1 || b2_sn != 1)) return HB_OK;
+  GemmP p;
+  memset(&p, 0, sizeof p);
+  p.A = A1; p.B = B1; p.C = C1;
+  p.A2 = A2; p.B2 = B2; p.C2 = chain ? C1 : C2;
+  p.M = (int)M; p.N = (int)N; p.K = (int)K1; p.K2 = (int)K2;
+  p.a_sm = a1_sm; p.a_sk = a1_sk; p.b_sk = b1_sk; p.b_sn = b1_sn;
+  p.a_sm2 = a2_sm; p.a_sk2 = a2_sk; p.b_sk2 = b2_sk; p.b_sn2 = b2_sn;
+  p.c_sm = N;
+  p.accum = accum;
+  p.chain = chain;
+  p.a_vec = ((uintptr_t)A1 & 15) == 0 && ((a_kfast ? a1_sm : a1_sk) % 2 == 0);
+  p.b_vec = ((uintptr_t)B1 & 15) == 0 && ((b_kfast ? b1_sn : b1_sk) % 2 == 0);
+  p.a_vec2 = ((uintptr_t)A2 & 15) == 0 && ((a_kfast ? a2_sm : a2_sk) % 2 == 0);
+  p.b_vec2 = ((uintptr_t)B2 & 15) == 0 && ((b_kfast ? b2_sn : b2_sk) % 2 == 0);
+  const int gm = (int)((M + BM - 1) / BM), gn = (int)((N + BN - 1) / BN);
+  if (gn > 65535) return HB_OK;
+  const int64_t tiles = (int64_t)gm * gn;
+  if (2 * tiles > kFlagTiles) return HB_OK;
+  // K slices: about two CTAs per SM over BOTH products, every slice about the same depth (a K = 28 product next
+  // to a K = 512 one gets one slice and the deep one two, so the real work is still 256 CTAs of K = 256), at
+  // least 4 chunks (128 k) per slice, at most 3 slices per product
+  const int chunks1 = (int)((K1 + BK8 - 1) / BK8), chunks2 = (int)((K2 + BK8 - 1) / BK8);
+  int budget = (int)(2 * (int64_t)g_hb.sm_count / tiles);
+  if (budget < 2) budget = 2;
+  int per = (chunks1 + chunks2 + budget - 1) / budget;
+  if (per < 4) per = 4;
+  auto slices = [&](int chunks, int *kchunks) {
+    int sp = (chunks + per - 1) / per;
+    if (sp > 3) sp = 3;
+    if (sp < 1) sp = 1;
+    *kchunks = (chunks + sp - 1) / sp;
+    return (chunks + *kchunks - 1) / *kchunks;
+  };
+  const int s1 = slices(chunks1, &p.kchunks), s2 = slices(chunks2, &p.kchunks2);
+  p.zsplit = s1;
+  HB_TRY(gemm_flags(&p.flags));
+  dim3 grid((unsigned)gm, (unsigned)gn, (unsigned)(s1 + s2));
+  size_t smem = (size_t)STAGES8 * 2 * TILE8 * 8;
+#define GEMM8_LAUNCH(AK, BKF)                                                                                  \
+  do {                                                                                                         \
+    HB_CUDA(cudaFuncSetAttribute(gemm8_dmma_kernel<AK, BKF>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                 (int)smem));                                                                  \
+    gemm8_dmma_kernel<AK, BKF><<<grid, 256, smem, g_hb.stream>>>(p);                                           \
+  } while (0)
+  if (a_kfast && b_kfast) GEMM8_LAUNCH(true, true);
+  else if (a_kfast) GEMM8_LAUNCH(true, false);
+  else if (b_kfast) GEMM8_LAUNCH(false, true);
+  else GEMM8_LAUNCH(false, false);
+#undef GEMM8_LAUNCH
+  HB_LAUNCHED();
+  *done = 1;
+  return HB_OK;
+}
+

@@ -626,7 +626,7 @@ __global__ void __launch_bounds__(256)
   const int64_t n = rows * cols;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     T b = bias ? bias[i / cols] : T(0);
-    y[i] = tanh((u[i] + v[i]) + b);
+    y[i] = tanh((v ? u[i] + v[i] : u[i]) + b);
   }
 }
 
@@ -657,16 +657,16 @@ __global__ void __launch_bounds__(256)
 extern "C" int hb_tanh_affine_fwd(const hb_array *u, const hb_array *v, const hb_array *bias, hb_array **y_out) {
   hb_prof_scope prof_("tanh_affine_fwd", u);
   HB_CHECK_INIT();
-  HB_REQUIRE(u && v && y_out, "null argument");
-  HB_REQUIRE(u->rank == 2 && hb_same_shape(u, v) && u->dt == v->dt && hb_is_float(u->dt),
-             "tanh_affine: two floating [width, batch] operands of one shape required");
+  HB_REQUIRE(u && y_out, "null argument");
+  HB_REQUIRE(u->rank == 2 && hb_is_float(u->dt) && (!v || (hb_same_shape(u, v) && u->dt == v->dt)),
+             "tanh_affine: floating [width, batch] operands of one shape required");
   HB_REQUIRE(!bias || (bias->rank == 1 && bias->shape[0] == u->shape[0] && bias->dt == u->dt),
              "tanh_affine: bias must be [width] of the operands' type");
   const hb_array *uc = u, *vc = v, *bc = bias;
   hb_array *t1 = nullptr, *t2 = nullptr, *t3 = nullptr, *y = nullptr;
   int st = HB_OK;
   if (!hb_contig(u)) { st = hb_contiguous(u, &t1); uc = t1; }
-  if (st == HB_OK && !hb_contig(v)) { st = hb_contiguous(v, &t2); vc = t2; }
+  if (st == HB_OK && v && !hb_contig(v)) { st = hb_contiguous(v, &t2); vc = t2; }
   if (st == HB_OK && bias && !hb_contig(bias)) { st = hb_contiguous(bias, &t3); bc = t3; }
   if (st == HB_OK) st = hb_new_array(u->dt, 2, u->shape, &y);
   const int64_t rows = u->shape[0], cols = u->shape[1], n = rows * cols;
@@ -674,12 +674,12 @@ extern "C" int hb_tanh_affine_fwd(const hb_array *u, const hb_array *v, const hb
     const int blocks = hb_blocks_for(n, 256, g_hb.sm_count * 16);
     if (u->dt == HB_F64)
       hb_tanh_affine_fwd_kernel<double><<<blocks, 256, 0, g_hb.stream>>>(
-          (const double *)hb_data(uc), (const double *)hb_data(vc), bc ? (const double *)hb_data(bc) : nullptr, rows, cols,
-          (double *)hb_data(y));
+          (const double *)hb_data(uc), vc ? (const double *)hb_data(vc) : nullptr,
+          bc ? (const double *)hb_data(bc) : nullptr, rows, cols, (double *)hb_data(y));
     else
       hb_tanh_affine_fwd_kernel<float><<<blocks, 256, 0, g_hb.stream>>>(
-          (const float *)hb_data(uc), (const float *)hb_data(vc), bc ? (const float *)hb_data(bc) : nullptr, rows, cols,
-          (float *)hb_data(y));
+          (const float *)hb_data(uc), vc ? (const float *)hb_data(vc) : nullptr,
+          bc ? (const float *)hb_data(bc) : nullptr, rows, cols, (float *)hb_data(y));
     HB_LAUNCHED();
   }
   hb_release(t1); hb_release(t2); hb_release(t3);

@@ -310,6 +310,31 @@ class DeviceBackend:
             return acc
         return _wrap(p)
 
+    def smatmul2_sum(self, a1, b1, a2, b2):
+        """smatmul2 a1 b1 + smatmul2 a2 b2 in one launch (hb_matmul2_sum)."""
+        p = _out()
+        call("hb_matmul2_sum", a1.h, b1.h, a2.h, b2.h, C.byref(p))
+        return _wrap(p)
+
+    def smatmul2_pair(self, a1, b1, a2, b2):
+        """(smatmul2 a1 b1, smatmul2 a2 b2) in one launch (hb_matmul2_pair)."""
+        p1, p2 = _out(), _out()
+        call("hb_matmul2_pair", a1.h, b1.h, a2.h, b2.h, C.byref(p1), C.byref(p2))
+        return _wrap(p1), _wrap(p2)
+
+    def smatmul2_acc_pair(self, acc1, a1, b1, acc2, a2, b2):
+        """(acc1 + a1 b1, acc2 + a2 b2) in one launch, in place when both accumulators are uniquely referenced."""
+        p1, p2 = _out(), _out()
+        call("hb_matmul2_acc_pair", acc1.h, a1.h, b1.h, acc2.h, a2.h, b2.h, C.byref(p1), C.byref(p2))
+        outs = []
+        for p, acc in ((p1, acc1), (p2, acc2)):
+            if p.value == acc.h.value:
+                ffi._lib.hb_release(p)
+                outs.append(acc)
+            else:
+                outs.append(_wrap(p))
+        return outs[0], outs[1]
+
     def smatvecmul(self, m, v):
         p = _out()
         call("hb_matvecmul", m.h, v.h, C.byref(p))
@@ -433,7 +458,7 @@ class DeviceBackend:
     def tanh_affine_fwd(self, u: DeviceArray, v: DeviceArray, bias) -> DeviceArray:
         """tanh ((u + v) + bias stretched over the batch): the body of rnnMnistLayerS in one pass."""
         p = _out()
-        call("hb_tanh_affine_fwd", u.h, v.h, bias.h if bias is not None else None, C.byref(p))
+        call("hb_tanh_affine_fwd", u.h, v.h if v is not None else None, bias.h if bias is not None else None, C.byref(p))
         return _wrap(p)
 
     def tanh_affine_bwd(self, y: DeviceArray, c: DeviceArray, want_bias=True):

@@ -25,8 +25,11 @@ def init_params(out_width, seed=44, rng_range=0.4, dtype=np.float64, h=28):
 
 def rnnMnistLayerS(T, s, x, wX, wS, b, fused=False):
     """rnnMnistLayerS (MnistRnnShaped2.hs:55-69): tanh (wX x + wS s + b).  `fused`: the two adds, the
-    stretched bias and tanh as the one contraction-pass node `tanh_affine`."""
+    stretched bias and tanh as the one contraction-pass node `tanh_affine`; `fused == "pair"`: additionally
+    `wX x + wS s` as the node `smatmul2_sum`."""
     batch = T.shape(x)[1]
+    if fused == "pair":   # the two products and their sum as one node as well (one paired GEMM launch)
+        return T.tanh_affine(T.smatmul2_sum(wX, x, wS, s), None, b)
     if fused:
         return T.tanh_affine(T.smatmul2(wX, x), T.smatmul2(wS, s), b)
     y = T.binary("add", T.binary("add", T.smatmul2(wX, x), T.smatmul2(wS, s)),

@@ -372,6 +372,27 @@ int hb_matvecmul(const hb_array *m, const hb_array *v, hb_array **out);
  * more); otherwise it equals hb_matmul2 followed by hb_add_inplace_or_new. */
 int hb_matmul2_acc(hb_array *acc, const hb_array *a, const hb_array *b,
                    hb_array **out);
+/* Pairs of tsmatmul2 products of one result shape in ONE launch (device
+ * contraction-pass nodes for the recurrent layer `wX x + wS s` of
+ * rnnMnistLayerS, example/MnistRnnShaped2.hs:55-69, and for the transposition
+ * rules of its two products, DeltaEval.hs:274-718): each product alone fills
+ * about one 64x64 tile per SM, a pair fills both CTA slots.
+ *   hb_matmul2_sum      out  = a1 x b1 + a2 x b2   (K may differ)
+ *   hb_matmul2_pair     out1 = a1 x b1, out2 = a2 x b2
+ *   hb_matmul2_acc_pair out1 = acc1 + a1 x b1, out2 = acc2 + a2 x b2 (in place
+ *                       under the conditions of hb_matmul2_acc)
+ * K slices are combined in a fixed order (deterministic).  Operands that the
+ * paired kernel does not take (not f64, no unit stride, differing
+ * orientations) are computed by the single-product entry points instead. */
+int hb_matmul2_sum(const hb_array *a1, const hb_array *b1, const hb_array *a2,
+                   const hb_array *b2, hb_array **out);
+int hb_matmul2_pair(const hb_array *a1, const hb_array *b1,
+                    const hb_array *a2, const hb_array *b2, hb_array **out1,
+                    hb_array **out2);
+int hb_matmul2_acc_pair(hb_array *acc1, const hb_array *a1,
+                        const hb_array *b1, hb_array *acc2,
+                        const hb_array *a2, const hb_array *b2,
+                        hb_array **out1, hb_array **out2);
 /* tsargMax / tsargMin (OpsConcrete.hs:1712-1746): reduce the LAST axis,
  * result shape Init sh, dtype I64; first extremum wins. */
 int hb_argmax_last(const hb_array *a, hb_array **out);
@@ -443,7 +464,8 @@ int hb_softmax_xent(const hb_array *logits, const hb_array *expected,
 /* The body of rnnMnistLayerS (example/MnistRnnShaped2.hs:55-69) behind its two
  * matmuls, as one node of the device contraction pass:
  *   y = tanh ((u + v) + bias stretched over the batch),  u, v : [width, batch]
- * (bias [width], may be NULL), and its adjoint
+ * (bias [width], may be NULL; v may be NULL when u already holds the sum, see
+ * hb_matmul2_sum), and its adjoint
  *   dz = (1 - y*y) * c,   dbias[i] = sum_j dz[i,j]   (dbias_out may be NULL)
  * -- dz is the cotangent of both u and v.  Same association as the generic
  * tanh rule; the row sums are reduced in a fixed order. */

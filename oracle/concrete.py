@@ -237,6 +237,16 @@ class ConcreteBackend:
         """taddTarget acc (tsmatmul2 m1 m2) (DeltaEval.hs:139-148)."""
         return acc + self.smatmul2(m1, m2)
 
+    def smatmul2_sum(self, a1, b1, a2, b2):
+        """tsmatmul2 a1 b1 + tsmatmul2 a2 b2 (the pre-activation of rnnMnistLayerS, MnistRnnShaped2.hs:55-69)."""
+        return self.smatmul2(a1, b1) + self.smatmul2(a2, b2)
+
+    def smatmul2_pair(self, a1, b1, a2, b2):
+        return self.smatmul2(a1, b1), self.smatmul2(a2, b2)
+
+    def smatmul2_acc_pair(self, acc1, a1, b1, acc2, a2, b2):
+        return acc1 + self.smatmul2(a1, b1), acc2 + self.smatmul2(a2, b2)
+
     # tsargMax / tsargMin reduce the LAST axis, Int result of shape Init sh
     # (OpsConcrete.hs:1712-1746); first extremum (unpinned in the reference)
     def sargMax(self, t):
@@ -478,7 +488,7 @@ class ConcreteBackend:
 # ---------------------------------------------------------------- recurrent layer body
 def tanh_affine_fwd(u, v, bias):
     """rnnMnistLayerS behind its matmuls (example/MnistRnnShaped2.hs:55-69): tanh ((u + v) + stretched bias)."""
-    z = u + v
+    z = u + v if v is not None else u
     if bias is not None:
         z = z + np.asarray(bias)[:, None]
     return np.tanh(z)

@@ -418,6 +418,50 @@ def test_matmul2_acc(dev, shape):
     assert np.array_equal(r1, r2)
 
 
+@pytest.mark.parametrize("shape", [(512, 512, 28, 1024),   # the recurrent layer: K = 512 and K = 28, one tile per SM each
+                                   (512, 512, 512, 1024),
+                                   (512, 1024, 1024, 512),  # the weight cotangents: 64 tiles, two K slices per product
+                                   (70, 33, 129, 50),       # ragged tiles, odd strides
+                                   (24, 28, 24, 9)])
+def test_matmul2_pairs(dev, shape):
+    """hb_matmul2_sum / _pair / _acc_pair (two products per launch) against numpy, every operand orientation
+    the layer and its transposition rules use; bit-identical from run to run."""
+    m, k1, k2, n = shape
+    rng = np.random.default_rng(94)
+    a1, b1, a2, b2 = rnd(rng, (m, k1)), rnd(rng, (k1, n)), rnd(rng, (m, k2)), rnd(rng, (k2, n))
+    T = lambda x: dev.stranspose([1, 0], dev.sconcrete(np.ascontiguousarray(x.T)))
+    for ta in (False, True):
+        for tb in (False, True):
+            A1, A2 = (T(a1), T(a2)) if ta else (dev.sconcrete(a1), dev.sconcrete(a2))
+            B1, B2 = (T(b1), T(b2)) if tb else (dev.sconcrete(b1), dev.sconcrete(b2))
+            got = dev.to_numpy(dev.smatmul2_sum(A1, B1, A2, B2))
+            close(got, a1 @ b1 + a2 @ b2, np.float64, scale=k1 + k2)
+            assert np.array_equal(dev.to_numpy(dev.smatmul2_sum(A1, B1, A2, B2)), got)
+            if k1 == k2:
+                o1, o2 = dev.smatmul2_pair(A1, B1, A2, B2)
+                close(dev.to_numpy(o1), a1 @ b1, np.float64, scale=k1)
+                close(dev.to_numpy(o2), a2 @ b2, np.float64, scale=k2)
+                c1, c2 = rnd(rng, (m, n)), rnd(rng, (m, n))
+                acc1, acc2 = dev.sconcrete(c1), dev.sconcrete(c2)
+                r1, r2 = dev.smatmul2_acc_pair(acc1, A1, B1, acc2, A2, B2)
+                assert r1 is acc1 and r2 is acc2                    # both accumulated in place
+                close(dev.to_numpy(r1), c1 + a1 @ b1, np.float64, scale=k1)
+                close(dev.to_numpy(r2), c2 + a2 @ b2, np.float64, scale=k2)
+                # one accumulator shared with somebody else: nothing is updated in place behind their back
+                acc1, acc2 = dev.sconcrete(c1), dev.sconcrete(c2)
+                alias = dev.sreshape([m, n], acc2)
+                r1, r2 = dev.smatmul2_acc_pair(acc1, A1, B1, acc2, A2, B2)
+                exact(dev.to_numpy(alias), c2)
+                close(dev.to_numpy(r1), c1 + a1 @ b1, np.float64, scale=k1)
+                close(dev.to_numpy(r2), c2 + a2 @ b2, np.float64, scale=k2)
+    # mixed orientations between the two products, float32, broadcast operands: the single-product entry points
+    got = dev.to_numpy(dev.smatmul2_sum(dev.sconcrete(a1), dev.sconcrete(b1), T(a2), dev.sconcrete(b2)))
+    close(got, a1 @ b1 + a2 @ b2, np.float64, scale=k1 + k2)
+    f = lambda x: dev.sconcrete(x.astype(np.float32))
+    got = dev.to_numpy(dev.smatmul2_sum(f(a1), f(b1), f(a2), f(b2)))
+    close(got, (a1 @ b1 + a2 @ b2).astype(np.float32), np.float32, scale=k1 + k2)
+
+
 def test_grad_accumulates_weight_cotangents_in_the_gemm(dev, oracle):
     """A weight used at every step of an unrolled loop: the sweep hands its cotangent contributions to
     smatmul2_acc (ad.DeferredMatmul); same gradient as the oracle's matmul + add."""
@@ -886,17 +930,17 @@ def test_mnist_fcnn_gradient_vs_oracle(dev, oracle, q):
         np.testing.assert_allclose(a, b, rtol=tol * 100, atol=tol * 10)
 
 
-@pytest.mark.parametrize("fused", [False, True])
-def test_mnist_rnn_gradient_vs_oracle(dev, oracle, fused):
+@pytest.mark.parametrize("fused,batch,width", [(False, 9, 24), (True, 9, 24), ("pair", 9, 24), ("pair", 200, 128)])
+def test_mnist_rnn_gradient_vs_oracle(dev, oracle, fused, batch, width):
     """MnistRnnShaped2 (BASELINE config 5) at a small width: 28 unrolled steps of
     two tanh layers (smatmul2 on the DMMA GEMM), loss and the 8 gradient leaves;
-    `fused`: the layer body as the tanh_affine node, checked against the oracle's
-    UNFUSED program."""
+    `fused`: the layer body as the tanh_affine node (`"pair"`: `wX x + wS s` as the smatmul2_sum node too:
+    paired GEMM launches forward and in both transposition rules), checked against the oracle's UNFUSED
+    program."""
     from horde_ad_b200 import mnist_rnn
     rng = np.random.Generator(np.random.Philox(12))
-    batch, width = 9, 24
     glyphs, labels = rng.uniform(0, 1, (batch, 28, 28)), np.eye(10)[rng.integers(0, 10, batch)]
-    params = mnist_rnn.init_params(width, rng_range=0.2)
+    params = mnist_rnn.init_params(width, rng_range=0.2 if width < 100 else 0.05)
 
     def run(B, fused):
         ins = [B.sconcrete(p) for p in params]

@@ -227,6 +227,13 @@ def test_tanh_affine_node_equals_the_unfused_layer_on_the_oracle(oracle):
     ds = [rng.uniform(-1, 1, p.shape) for p in params]
     _, t = ad.jvp(oracle, f(True), params, ds)
     np.testing.assert_allclose(float(t), sum(float(np.sum(g * d)) for g, d in zip(g1, ds)), rtol=1e-10)
+    # ... and with `wX x + wS s` as the one node smatmul2_sum (paired products, paired weight cotangents)
+    v2, g2 = ad.grad(oracle, f("pair"), params)
+    np.testing.assert_allclose(v2, v0, rtol=1e-14)
+    for a, b in zip(g2, g0):
+        np.testing.assert_allclose(a, b, rtol=1e-12, atol=1e-16)
+    _, t2 = ad.jvp(oracle, f("pair"), params, ds)
+    np.testing.assert_allclose(float(t2), float(t), rtol=1e-12)
 
 
 def test_cnn_opp3_folded_value_and_gradient(oracle):

@@ -10,7 +10,8 @@ width, batch = 512, 1024
 params = [dev.sconcrete(p) for p in mnist_rnn.init_params(width, rng_range=0.05)]
 glyphs = dev.sconcrete(rng.uniform(0, 1, (batch, 28, 28)))
 labels = dev.sconcrete(np.eye(10)[rng.integers(0, 10, batch)])
-f = lambda: ad.grad(dev, lambda T, *ps: mnist_rnn.rnnMnistLossFusedS(T, glyphs, labels, list(ps)), params)
+fused = {'fused': True, 'pair': 'pair'}.get(sys.argv[1] if len(sys.argv) > 1 else '', False)
+f = lambda: ad.grad(dev, lambda T, *ps: mnist_rnn.rnnMnistLossFusedS(T, glyphs, labels, list(ps), fused=fused), params)
 f(); f(); dev.sync()
 ffi.call("hb_prof_begin"); f(); ffi.call("hb_prof_end")
 buf = C.create_string_buffer(1 << 16)
