@@ -234,12 +234,12 @@ class ADBackend:
         total, rest, dt = sh[0], list(sh[1:]), B.dtype(t.p)
 
         def pb(c):
-            parts = c
-            if i > 0:
-                parts = B.sappend(B.srepl([i] + rest, 0, dt), parts)
-            if total - i - n > 0:
-                parts = B.sappend(parts, B.srepl([total - i - n] + rest, 0, dt))
-            return [parts]
+            # the zero-padded cotangent (DeltaSlice, DeltaEval.hs:538-562) is handed over unevaluated: two slices
+            # that tile the parent (state = sappend vec1 vec2 read back as two halves) become ONE sappend in the
+            # sweep instead of two zero fills, four copies and an add
+            if n == total:
+                return [c]
+            return [DeferredPad(c, i, n, total, rest, dt)]
         return self._node(B.sslice(i, n, t.p), [t], pb)
 
     def sappend(self, a, b):
@@ -450,6 +450,33 @@ class DeferredMatmul:
         return base.smatmul2(self.a, self.b)
 
 
+class DeferredPad:
+    """A cotangent contribution `zeros ++ c ++ zeros` along the outermost axis, not yet evaluated."""
+    __slots__ = ("c", "i", "n", "total", "rest", "dt")
+
+    def __init__(self, c, i, n, total, rest, dt):
+        self.c, self.i, self.n, self.total, self.rest, self.dt = c, i, n, total, rest, dt
+
+    def force(self, base):
+        parts = self.c
+        if self.i > 0:
+            parts = base.sappend(base.srepl([self.i] + self.rest, 0, self.dt), parts)
+        if self.total - self.i - self.n > 0:
+            parts = base.sappend(parts, base.srepl([self.total - self.i - self.n] + self.rest, 0, self.dt))
+        return parts
+
+    def tile_with(self, other, base):
+        """self + other when the two windows are adjacent: one sappend (still a pad if they do not cover the
+        whole axis); None when they overlap or leave a gap."""
+        lo, hi = (self, other) if self.i <= other.i else (other, self)
+        if lo.i + lo.n != hi.i:
+            return None
+        joined = base.sappend(lo.c, hi.c)
+        if lo.i == 0 and hi.i + hi.n == self.total:
+            return joined
+        return DeferredPad(joined, lo.i, lo.n + hi.n, self.total, self.rest, self.dt)
+
+
 def grad(base, f: Callable, inputs: Sequence, dt=None):
     """cgrad / cvjp (ADEngine.hs:544-555): returns (value, [gradients]).
 
@@ -477,6 +504,8 @@ def grad(base, f: Callable, inputs: Sequence, dt=None):
             nid = -heapq.heappop(heap)
             node = nodes.pop(nid)
             c = cot.pop(nid)
+            if isinstance(c, DeferredPad):
+                c = c.force(base)
             if nid in input_ix:
                 grads[input_ix[nid]] = c
                 continue
@@ -496,6 +525,26 @@ def grad(base, f: Callable, inputs: Sequence, dt=None):
                 if parent is None or pc is None:
                     continue
                 deferred = isinstance(pc, DeferredMatmul)
+                if isinstance(pc, DeferredPad):
+                    old = cot.get(parent.id)
+                    if old is None:                       # stays unevaluated until a second window arrives
+                        cot[parent.id] = pc
+                        nodes[parent.id] = parent
+                        heapq.heappush(heap, -parent.id)
+                        continue
+                    if isinstance(old, DeferredPad):
+                        joined = old.tile_with(pc, base)
+                        if joined is not None:
+                            cot[parent.id] = joined
+                            if not isinstance(joined, DeferredPad):
+                                owned.add(parent.id)      # a fresh array nobody else holds
+                            continue
+                        cot[parent.id] = old.force(base)
+                        owned.add(parent.id)
+                    pc = pc.force(base)
+                elif isinstance(cot.get(parent.id), DeferredPad):
+                    cot[parent.id] = cot[parent.id].force(base)
+                    owned.add(parent.id)
                 if parent.id in cot:
                     if parent.id in owned:
                         if deferred and not _NO_MATMUL_ACC:
