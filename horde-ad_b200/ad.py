@@ -649,6 +649,16 @@ class FwdBackend:
             ta = None if a.t is None else B.binary("divide", a.t, b.p)
             tb = None if b.t is None else B.unary("negate", B.binary("divide", B.binary("mul", p, b.t), b.p))
             return Dual(p, self._add(ta, tb))
+        if op == "atan2":  # atan2H y x: d/dy = x / (x^2 + y^2), d/dx = -y / (x^2 + y^2)  (same factors as the pullback)
+            r2 = B.binary("add", B.binary("mul", a.p, a.p), B.binary("mul", b.p, b.p))
+            ta = None if a.t is None else B.binary("mul", a.t, B.binary("divide", b.p, r2))
+            tb = None if b.t is None else B.binary("mul", b.t, B.unary("negate", B.binary("divide", a.p, r2)))
+            return Dual(p, self._add(ta, tb))
+        if op == "power":
+            one = B.srepl(B.shape(p), 1, B.dtype(p))
+            ta = None if a.t is None else B.binary("mul", a.t, B.binary("mul", b.p, B.binary("power", a.p, B.binary("sub", b.p, one))))
+            tb = None if b.t is None else B.binary("mul", b.t, B.binary("mul", p, B.unary("log", a.p)))
+            return Dual(p, self._add(ta, tb))
         raise NotImplementedError(f"forward derivative of {op}")
 
     def unary(self, op, a):

@@ -54,6 +54,13 @@ out = {
         {"name": "testSin0Fold4", "cite": "test/simplified/TestRevFwdFold.hs:565-570", "value": -0.7053476446727861},
         {"name": "testSin0Fold6", "cite": "test/simplified/TestRevFwdFold.hs:583-590", "value": 6},
         {"name": "testSin0Fold7", "cite": "test/simplified/TestRevFwdFold.hs:592-598", "value": 250},
+        *[{"name": n, "cite": "test/simplified/TestAdaptorSimplified.hs:1247-1251,1300-1345,1404-1462,1850-1895",
+           "inputs": [x.reshape(-1).tolist() for x in ins], "expected_gradients": [e.reshape(-1).tolist() for e in exp], "eps": 1e-10}
+          for n, _f, ins, exp in P.ADAPTOR_REV_GOLDEN],
+        *[{"name": n, "cite": "test/simplified/TestAdaptorSimplified.hs:1843-1848,1872-1877", "input": float(x), "dt": float(dt),
+           "value": float(e)} for n, _f, x, dt, e in P.ADAPTOR_VJP_GOLDEN],
+        *[{"name": n, "cite": "test/simplified/TestAdaptorSimplified.hs:1896-1925", "input": x.reshape(-1).tolist(),
+           "tangent": dx.reshape(-1).tolist(), "value": e.reshape(-1).tolist()} for n, _f, x, dx, e in P.ADAPTOR_FWD_GOLDEN],
     ],
 }
 with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_goldens.json"), "w") as f:

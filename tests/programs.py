@@ -392,3 +392,70 @@ GATHER_BUILD_GOLDEN = [
     ("gatherNestedBuild12", build12_variant(gatherNested12), _B12), ("gatherBuild12", build12_variant(gather12), _B12),
     ("scatterNestedBuild12", build12_variant(scatterNested12), _B12), ("scatterBuild12", build12_variant(scatter12), _B12),
 ]
+
+
+# ---- relu / reluMax / barRelu known answers (TestAdaptorSimplified.hs:1247-1251, 1300-1345, 1404-1462,
+#      1836-1925): relu = oneIfGtZero * v (CommonRankedOps.hs:40-49), reluMax = rmap0N (maxH 0) with
+#      maxH u v = ifH (u >=. v) u v (OpsTensor.hs:327-329) as a per-element host function (tsmap0N),
+#      bar (x, y) = let w = foo2 (x, y, x) * sin y in atan2H x w + y * w (:1585-1588) ----------------------
+RELU_IN = np.array([1.1, -2.2, 0, 4.4, 5.5, 6.6, 7.7, 8.8, -9.9, -10, 11, 12]).reshape(3, 4)
+RELU_MASK = np.array([1.0, 0.0, 0.0, 1.0, 1.0, 1.0, 1.0, 1.0, 0.0, 0.0, 1.0, 1.0]).reshape(3, 4)
+BAR_IN = np.array([1.1, 2, 3, 4.2]).reshape(2, 1, 2)
+BAR_GRAD = np.array([4.5309153191767395, 4.5302138998556, -9.39547533946234, 95.29759282497125]).reshape(2, 1, 2)
+BAR_TAN = np.array([0.1, 0.2, 0.3, 0.42]).reshape(2, 1, 2)
+BAR_FWD = np.array([0.45309153191767404, 0.9060427799711201, -2.8186426018387007, 40.02498898648793]).reshape(2, 1, 2)
+
+
+def relu_(T, v):
+    from horde_ad_b200 import nn
+    return nn.reluS(T, v)
+
+
+def reluMax(T, v):
+    from horde_ad_b200 import nn
+    zero = lambda: T.sscalar(0.0)
+    return nn.smap0N(T, lambda s: zero() if 0.0 >= float(T.kfromS(s)) else s, v)
+
+
+def reluT2(act):
+    """reluT2 (t, r) = act (t * rreplicate 3 (rreplicate 4 r))  (:1300-1306, 1327-1336, 1451-1459)."""
+    def f(T, t, r):
+        return act(T, T.binary("mul", t, T.sreplicate0N([3, 4], r)))
+    return f
+
+
+def barRelu0(T, x):
+    return relu_(T, _bar(T, x, relu_(T, x)))
+
+
+def barReluMax(T, x):
+    return reluMax(T, _bar(T, x, reluMax(T, x)))
+
+
+def barReluMax0(T, x):
+    return reluMax(T, _bar(T, x, x))
+
+
+# (name, f, inputs, expected gradients) -- gradient of the SUM of the result (rev' / grad (rsum0 . f)), eps 1e-10
+ADAPTOR_REV_GOLDEN = [
+    ("testReluSimpler", relu_, [RELU_IN], [RELU_MASK]),
+    ("testReluSimpler3", reluT2(relu_), [RELU_IN, np.array(7.0)], [7.0 * RELU_MASK, np.array(57.1)]),
+    ("testReluMax", reluMax, [RELU_IN], [RELU_MASK]),
+    ("testReluMax3", reluT2(reluMax), [RELU_IN, np.array(7.0)], [7.0 * RELU_MASK, np.array(57.1)]),
+    ("testBarRelu", barRelu0, [np.array(1.1)], [np.array(4.5309153191767395)]),
+    ("testBarRelu3", barRelu0, [BAR_IN], [BAR_GRAD]),
+    ("testBarReluMax", barReluMax, [np.array(1.1)], [np.array(4.5309153191767395)]),
+    ("testBarReluMax30", barReluMax0, [np.array([1.1])], [np.array([4.5309153191767395])]),
+    ("testBarReluMax31", barReluMax, [BAR_IN], [BAR_GRAD]),
+]
+# vjp with an incoming cotangent (:1843-1848, 1872-1877): (name, f, input, dt, expected)
+ADAPTOR_VJP_GOLDEN = [
+    ("testBarReluDt", barRelu0, np.array(1.1), np.array(42.2), np.array(191.20462646925841)),
+    ("testBarReluMaxDt", barReluMax, np.array(1.1), np.array(42.2), np.array(191.20462646925841)),
+]
+# forward mode (:1896-1925): (name, f, input, tangent, expected)
+ADAPTOR_FWD_GOLDEN = [
+    ("testBarReluMax3CFwd", barReluMax, BAR_IN, BAR_TAN, BAR_FWD),
+    ("testBarReluMax3FwdS", barReluMax, BAR_IN, BAR_TAN, BAR_FWD),
+]
+

@@ -1125,3 +1125,24 @@ def test_graph_capture_replay(dev):
         ffi.call("hb_graph_launch", g)
     assert dev.kfromS(out) == eager
     ffi.call("hb_graph_free", g)
+
+
+@pytest.mark.parametrize("name,f,inputs,expected", P.ADAPTOR_REV_GOLDEN, ids=[g[0] for g in P.ADAPTOR_REV_GOLDEN])
+def test_relu_and_bar_relu_known_answers_on_the_device(dev, name, f, inputs, expected):
+    """The reference's literal gradients (TestAdaptorSimplified.hs:1247-1251, 1300-1345, 1404-1462, 1850-1895,
+    eps 1e-10) reproduced by the CUDA path: relu mask, per-element maxH through tsmap0N, atan2/sin chains."""
+    _, grads = ad.grad(dev, lambda T, *xs: T.ssum0(f(T, *xs)), [dev.sconcrete(np.asarray(x, np.float64)) for x in inputs])
+    for g, e in zip(grads, expected):
+        np.testing.assert_allclose(dev.to_numpy(g), e, atol=1e-10, rtol=0)
+
+
+def test_bar_relu_vjp_and_forward_known_answers_on_the_device(dev):
+    """testBarReluDt / testBarReluMaxDt (vjp, cotangent 42.2) and testBarReluMax3CFwd / FwdS (cjvp / jvp),
+    TestAdaptorSimplified.hs:1843-1848, 1872-1877, 1896-1925."""
+    for name, f, x, dt, expected in P.ADAPTOR_VJP_GOLDEN:
+        _, (g,) = ad.grad(dev, f, [dev.sconcrete(x)], dt=dev.sconcrete(dt))
+        np.testing.assert_allclose(dev.to_numpy(g), expected, atol=1e-10, rtol=0, err_msg=name)
+    for name, f, x, dx, expected in P.ADAPTOR_FWD_GOLDEN:
+        _, t = ad.jvp(dev, f, [dev.sconcrete(x)], [dev.sconcrete(dx)])
+        np.testing.assert_allclose(dev.to_numpy(t), expected, atol=1e-10, rtol=0, err_msg=name)
+

@@ -312,3 +312,27 @@ def test_gather_scatter_build_variants(oracle, name, prog, expected):
     t = np.tile(np.array([0.0, 1.0]), (7, 1))
     _, (g,) = ad.grad(oracle, prog, [t])
     assert np.asarray(g).reshape(-1).tolist() == expected
+
+
+@pytest.mark.parametrize("name,f,inputs,expected", P.ADAPTOR_REV_GOLDEN, ids=[g[0] for g in P.ADAPTOR_REV_GOLDEN])
+def test_relu_and_bar_relu_known_answers(oracle, name, f, inputs, expected):
+    """testReluSimpler/3, testReluMax/3, testBarRelu/3, testBarReluMax/30/31 (TestAdaptorSimplified.hs:1247-1251,
+    1300-1345, 1404-1462, 1850-1895), eps 1e-10."""
+    _, grads = ad.grad(oracle, lambda T, *xs: T.ssum0(f(T, *xs)), [oracle.sconcrete(x) for x in inputs])
+    for g, e in zip(grads, expected):
+        np.testing.assert_allclose(oracle.to_numpy(g), e, atol=1e-10, rtol=0)
+
+
+@pytest.mark.parametrize("name,f,x,dt,expected", P.ADAPTOR_VJP_GOLDEN, ids=[g[0] for g in P.ADAPTOR_VJP_GOLDEN])
+def test_bar_relu_vjp_known_answers(oracle, name, f, x, dt, expected):
+    """testBarReluDt / testBarReluMaxDt (TestAdaptorSimplified.hs:1843-1848, 1872-1877): vjp with cotangent 42.2."""
+    _, (g,) = ad.grad(oracle, f, [oracle.sconcrete(x)], dt=oracle.sconcrete(dt))
+    np.testing.assert_allclose(oracle.to_numpy(g), expected, atol=1e-10, rtol=0)
+
+
+@pytest.mark.parametrize("name,f,x,dx,expected", P.ADAPTOR_FWD_GOLDEN, ids=[g[0] for g in P.ADAPTOR_FWD_GOLDEN])
+def test_bar_relu_forward_known_answers(oracle, name, f, x, dx, expected):
+    """testBarReluMax3CFwd / testBarReluMax3FwdS (TestAdaptorSimplified.hs:1896-1925): cjvp / jvp."""
+    _, t = ad.jvp(oracle, f, [oracle.sconcrete(x)], [oracle.sconcrete(dx)])
+    np.testing.assert_allclose(oracle.to_numpy(t), expected, atol=1e-10, rtol=0)
+
