@@ -694,6 +694,14 @@ class FwdBackend:
         return Dual(B.scast(t.p, dtype), B.scast(t.t, dtype) if (fl and t.t is not None) else None)
 
     # structure (all linear)
+    # integer-valued results carry no tangent (tprimalPart of a plain tensor)
+    def sfromIntegral(self, t, dtype): return Dual(self.B.sfromIntegral(self.primal(t), dtype))
+    def sfloor(self, t, dtype=np.int64): return Dual(self.B.sfloor(self.primal(t), dtype))
+    def sargMax(self, t): return Dual(self.B.sargMax(self.primal(t)))
+    def sargMin(self, t): return Dual(self.B.sargMin(self.primal(t)))
+    def siota(self, n, dtype=np.int64): return Dual(self.B.siota(n, dtype))
+    def to_numpy(self, t): return self.B.to_numpy(self.primal(t))
+
     def stranspose(self, perm, t): return self._map(t, lambda x: self.B.stranspose(list(perm), x))
     def sreshape(self, sh, t): return self._map(t, lambda x: self.B.sreshape(list(sh), x))
     def sreplicateN(self, shm, t): return self._map(t, lambda x: self.B.sreplicateN(list(shm), x))

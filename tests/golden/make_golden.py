@@ -7,6 +7,8 @@ The reference is Haskell and cannot be executed in this environment (no GHC),
 so these literals -- not outputs of a run -- are what pins the oracle.
 """
 import json
+
+import numpy as np
 import os
 import sys
 
@@ -57,8 +59,9 @@ out = {
         *[{"name": n, "cite": "test/simplified/TestAdaptorSimplified.hs:1247-1251,1300-1345,1404-1462,1850-1895",
            "inputs": [x.reshape(-1).tolist() for x in ins], "expected_gradients": [e.reshape(-1).tolist() for e in exp], "eps": 1e-10}
           for n, _f, ins, exp in P.ADAPTOR_REV_GOLDEN],
-        *[{"name": n, "cite": "test/simplified/TestAdaptorSimplified.hs:1843-1848,1872-1877", "input": float(x), "dt": float(dt),
-           "value": float(e)} for n, _f, x, dt, e in P.ADAPTOR_VJP_GOLDEN],
+        *[{"name": n, "cite": "test/simplified/TestAdaptorSimplified.hs:1843-1848,1872-1877", "input": np.asarray(x).reshape(-1).tolist(),
+           "dt": np.asarray(dt).reshape(-1).tolist(), "value": np.asarray(e).reshape(-1).tolist()}
+          for n, _f, x, dt, e in P.ADAPTOR_VJP_GOLDEN],
         *[{"name": n, "cite": "test/simplified/TestAdaptorSimplified.hs:1896-1925", "input": x.reshape(-1).tolist(),
            "tangent": dx.reshape(-1).tolist(), "value": e.reshape(-1).tolist()} for n, _f, x, dx, e in P.ADAPTOR_FWD_GOLDEN],
     ],

@@ -436,6 +436,29 @@ def barReluMax0(T, x):
     return reluMax(T, _bar(T, x, x))
 
 
+def fooBuild1(T, v):
+    """fooBuild1 (TestAdaptorSimplified.hs:1690-1700): rbuild1 3 over rsum0, rminimum and rindex v [ix + 1]."""
+    from horde_ad_b200 import nn
+    r = T.ssum0(v)
+    vmin = nn.sminimum(T, v)
+    three, five = T.sscalar(3.0), T.sscalar(5.0)
+
+    def body(ix):
+        a = T.binary("mul", r, _foo(T, three, T.binary("mul", five, r),
+                                    T.binary("mul", T.binary("mul", r, nn.sminimum(T, v)), vmin)))
+        return T.binary("add", a, _bar(T, r, T.sindex(v, [ix + 1])))
+    return nn.sbuild1(T, 3, body)
+
+
+def nestedBuildIndex(T, v):
+    """nestedBuildIndex (TestAdaptorSimplified.hs:1826-1830): three nested rbuild1 / rindex pairs."""
+    from horde_ad_b200 import nn
+    inner = lambda: nn.sbuild1(T, 4, lambda i4: T.sindex(v, [i4]))
+    mid = lambda: nn.sbuild1(T, 3, lambda i3: T.sindex(inner(), [i3]))
+    return nn.sbuild1(T, 2, lambda i2: T.sindex(mid(), [i2]))
+
+
+FOOBUILD_IN = np.array([1.1, 2.2, 3.3, 4])
 # (name, f, inputs, expected gradients) -- gradient of the SUM of the result (rev' / grad (rsum0 . f)), eps 1e-10
 ADAPTOR_REV_GOLDEN = [
     ("testReluSimpler", relu_, [RELU_IN], [RELU_MASK]),
@@ -447,15 +470,23 @@ ADAPTOR_REV_GOLDEN = [
     ("testBarReluMax", barReluMax, [np.array(1.1)], [np.array(4.5309153191767395)]),
     ("testBarReluMax30", barReluMax0, [np.array([1.1])], [np.array([4.5309153191767395])]),
     ("testBarReluMax31", barReluMax, [BAR_IN], [BAR_GRAD]),
+    ("testFooBuild", fooBuild1, [FOOBUILD_IN],                                      # :1724-1728
+     [np.array([-4521.201512195087, -5568.7163677622175, -5298.386349932494, -4907.349735554627])]),
+    ("testNestedBuildIndex", nestedBuildIndex, [np.array([1.1, 2.2, 3.3, 4, -5.22])],   # :1832-1836
+     [np.array([1.0, 1, 0, 0, 0])]),
 ]
 # vjp with an incoming cotangent (:1843-1848, 1872-1877): (name, f, input, dt, expected)
 ADAPTOR_VJP_GOLDEN = [
     ("testBarReluDt", barRelu0, np.array(1.1), np.array(42.2), np.array(191.20462646925841)),
     ("testBarReluMaxDt", barReluMax, np.array(1.1), np.array(42.2), np.array(191.20462646925841)),
+    ("testFooBuildDt", fooBuild1, FOOBUILD_IN, np.full(3, 42.0),                      # :1703-1708 (eps 1e-5)
+     np.array([-189890.46351219364, -233886.08744601303, -222532.22669716467, -206108.68889329425])),
 ]
 # forward mode (:1896-1925): (name, f, input, tangent, expected)
 ADAPTOR_FWD_GOLDEN = [
     ("testBarReluMax3CFwd", barReluMax, BAR_IN, BAR_TAN, BAR_FWD),
     ("testBarReluMax3FwdS", barReluMax, BAR_IN, BAR_TAN, BAR_FWD),
+    ("testFooBuildFwd", fooBuild1, FOOBUILD_IN, np.full(4, 42.0),                     # :1710-1722 (eps 1e-5)
+     np.array([-296584.8166864211, -290062.472288043, -265770.1775742018])),
 ]
 
