@@ -128,7 +128,8 @@ class DeviceBackend:
 
     # ------------------------------------------------------------ transfer
     def sconcrete(self, a) -> DeviceArray:
-        a = np.ascontiguousarray(a)
+        shape = np.shape(a)                 # np.ascontiguousarray turns a 0-d array into shape (1,)
+        a = np.ascontiguousarray(a).reshape(shape)
         p = _out()
         call("hb_from_host", _dt(a.dtype), a.ndim, ffi.shape_arg(a.shape),
              a.ctypes.data_as(C.c_void_p), C.byref(p))

@@ -58,6 +58,8 @@ def test_roundtrip_and_views(dev, oracle, dtype):
     exact(dev.to_numpy(dev.sslice(1, 2, d)), a[1:3])
     exact(dev.to_numpy(dev.sreverse(d)), np.ascontiguousarray(a[::-1]))
     exact(dev.to_numpy(dev.sreshape([4, 15], d)), a.reshape(4, 15))
+    z = dev.sconcrete(a[1, 2, 3])                       # a 0-d array stays 0-d (TKS '[] r)
+    assert z.shape == () and dev.to_numpy(z).reshape(1)[0] == a[1, 2, 3]
     exact(dev.to_numpy(dev.sreshape([5, 12], dev.stranspose([2, 1, 0], d))), np.transpose(a, (2, 1, 0)).reshape(5, 12))
     exact(dev.to_numpy(dev.sindex(d, [2, 1])), a[2, 1])
     exact(dev.to_numpy(dev.sindex(d, [3, 1])), np.zeros(5, dtype))      # OOB -> zeros
