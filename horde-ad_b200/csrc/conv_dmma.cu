@@ -1200,9 +1200,25 @@ int hb_conv_sp_dmma(const hb_array *K, const hb_array *in, hb_array *out, int fl
 // dK[Co,Ci,KH,KW] from A[N,Ci,H,W], dB[N,Co,H,W] (contiguous f64).  With
 // `code` != NULL, dB is instead the POOLED cotangent dy [N,Co,H/2,W/2] of the
 // fused bias + relu + 2x2 max-pool and `code` its adjoint code bytes.
+// measurement switches of the dKrn tile choice (read once): HB_DK_WM=4 -> 64-channel output tiles,
+// HB_DK_NCF=n -> n column fragments of 8 input channels per CTA, HB_DK_R=r -> band height r,
+// HB_DK_MAXNB=n -> accept two-CTA bands of fewer than 4 rows up to n bands, HB_CONV_DEBUG -> print the choice
+namespace {
+struct DkKnobs {
+  int wm = 0, ncf = 0, r = 0, maxnb = 4, debug = 0;
+  DkKnobs() {
+    auto num = [](const char *name, int dflt) { const char *e = getenv(name); return e ? atoi(e) : dflt; };
+    wm = num("HB_DK_WM", 0); ncf = num("HB_DK_NCF", 0); r = num("HB_DK_R", 0); maxnb = num("HB_DK_MAXNB", 4);
+    debug = getenv("HB_CONV_DEBUG") != nullptr;
+  }
+};
+const DkKnobs &dk_knobs() { static const DkKnobs k; return k; }
+}  // namespace
+
 int hb_conv_dk_dmma(const hb_array *A, const hb_array *dB, const hb_array *code, hb_array *out, int KH, int KW,
                     int *done) {
   *done = 0;
+  const DkKnobs &knobs = dk_knobs();
   if (A->dt != HB_F64 || !hb_contig(A) || !hb_contig(dB) || !hb_contig(out)) return HB_OK;
   int N = (int)A->shape[0], Ci = (int)A->shape[1], H = (int)A->shape[2], W = (int)A->shape[3];
   int Co = (int)dB->shape[1];
@@ -1219,7 +1235,7 @@ int hb_conv_dk_dmma(const hb_array *A, const hb_array *dB, const hb_array *code,
   else if (Co <= 16) { WM = 1; MO = 2; }
   else if (Co <= 32) { WM = 2; MO = 2; }
   else { WM = 2; MO = 2; }  // 32-channel tiles: two CTAs per SM (see the band choice below)
-  if (Co > 32) { const char *e = getenv("HB_DK_WM"); if (e && atoi(e) == 4) WM = 4; }
+  if (Co > 32 && knobs.wm == 4) WM = 4;
   int otile = WM * MO * 8, not_ = (Co + otile - 1) / otile;
   int wrest = 8 / WM;  // warps left for pairs x K
   int KK = KH * KW;
@@ -1242,7 +1258,7 @@ int hb_conv_dk_dmma(const hb_array *A, const hb_array *dB, const hb_array *code,
     // CTAs fit one SM: ConvVjpBench dKrn 0.613 ms (64 x 16 tile, one CTA) -> 0.513 (32 x 32, one CTA, TMA)
     // -> 0.501 ms (32 x 16, two CTAs, TMA)
     if (WM == 2 && ncf > 2) ncf = 2;
-    { const char *e = getenv("HB_DK_NCF"); if (e && atoi(e) > 0 && atoi(e) <= maxpairs / KK) ncf = atoi(e) < need ? atoi(e) : need; }
+    if (knobs.ncf > 0 && knobs.ncf <= maxpairs / KK) ncf = knobs.ncf < need ? knobs.ncf : need;
     // balance the chunks
     int chunks = (need + ncf - 1) / ncf;
     ncf = (need + chunks - 1) / chunks;
@@ -1288,8 +1304,7 @@ int hb_conv_dk_dmma(const hb_array *A, const hb_array *dB, const hb_array *code,
     return smem_need() <= budget && red_bytes <= budget;
   };
   int R = 0;
-  int maxnb2 = 4, forceR = 0;
-  { const char *e = getenv("HB_DK_MAXNB"); if (e) maxnb2 = atoi(e); e = getenv("HB_DK_R"); if (e) forceR = atoi(e); }
+  const int maxnb2 = knobs.maxnb, forceR = knobs.r;
   if (forceR > 0 && forceR <= H) {
     if (fits(forceR, kSmemMax / 2 - 1024)) { R = forceR; ctas = 2; }
     else if (fits(forceR, kSmemMax)) { R = forceR; ctas = 1; }
@@ -1382,7 +1397,7 @@ int hb_conv_dk_dmma(const hb_array *A, const hb_array *dB, const hb_array *code,
   HB_TRY(hb_scratch((size_t)splits * nout * 8, &scr));
   p.part = (double *)scr;
   dim3 grid((unsigned)splits, (unsigned)ncc, (unsigned)not_);
-  if (getenv("HB_CONV_DEBUG"))
+  if (knobs.debug)
     fprintf(stderr, "dk: WM=%d MO=%d CC=%d npairs=%d WN=%d WK=%d R=%d ctas=%d tma=%d RS=%d smem=%d grid=(%d,%d,%d) items=%d\n", WM, MO,
             CC, npairs, p.WN, p.WK, g.R, ctas, p.tma, g.RS, smem_bytes, splits, ncc, not_, p.items);
 #define DK_LAUNCH(WM_, MO_)                                                                  \
