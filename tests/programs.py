@@ -149,6 +149,35 @@ CONV_GOLDEN = [
 ]
 
 
+def _conv_goldens_from_file():
+    """tests/golden/conv_goldens.json (written by tests/golden/make_conv_goldens.py from the literals of
+    TestConvSimplified.hs:196-470): conv2dPreserving over t16b / t128b / t128c held constant as the kernel
+    (conv2dB*: gradient wrt the input) or as the input (conv2dC* = flip conv2dPreserving: gradient wrt the
+    kernel), at a constant point or at [37, 36 .. -10]."""
+    import json
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "conv_goldens.json")
+    fixtures = {"t16b": T16B, "t128b": T128B, "t128c": T128C}
+    have = {c[0] for c in CONV_GOLDEN}
+    out = []
+    for t in json.load(open(path))["tests"]:
+        name = t["name"][len("test"):]
+        if name in have:
+            continue
+        pt = t["point"]
+        if pt["kind"] == "constant":
+            x = np.full(pt["shape"], pt["value"], dtype=np.float64)
+        else:
+            x = np.arange(37, -11, -1, dtype=np.float64).reshape(pt["shape"])
+        fx = fixtures[t["fixture"]]
+        K, A = (fx, x) if t["wrt"] == "A" else (x, fx)
+        out.append((name, K, A, t["wrt"], t["expected"], t["eps"]))
+    return out
+
+
+CONV_GOLDEN = CONV_GOLDEN + _conv_goldens_from_file()
+
+
 # ---------------------------------------------------------------------------
 # testCNNOPP3 (test/simplified/TestGatherSimplified.hs:1365-1436,1574-1578): the toy "convolution" and
 # "max-pool" written with rbuild, rindex and ifH whose constant-folded value the reference prints as
