@@ -56,6 +56,8 @@ out = {
         {"name": "testSin0Fold4", "cite": "test/simplified/TestRevFwdFold.hs:565-570", "value": -0.7053476446727861},
         {"name": "testSin0Fold6", "cite": "test/simplified/TestRevFwdFold.hs:583-590", "value": 6},
         {"name": "testSin0Fold7", "cite": "test/simplified/TestRevFwdFold.hs:592-598", "value": 250},
+        *[{"name": n, "cite": "test/simplified/TestRevFwdFold.hs:934-1000", "input": x.reshape(-1).tolist(),
+           "expected_gradient": e.reshape(-1).tolist(), "eps": 1e-10} for n, _f, x, e in P.SCAN_GOLDEN],
         *[{"name": n, "cite": "test/simplified/TestAdaptorSimplified.hs:1247-1251,1300-1345,1404-1462,1850-1895",
            "inputs": [x.reshape(-1).tolist() for x in ins], "expected_gradients": [e.reshape(-1).tolist() for e in exp], "eps": 1e-10}
           for n, _f, ins, exp in P.ADAPTOR_REV_GOLDEN],

@@ -519,3 +519,47 @@ ADAPTOR_FWD_GOLDEN = [
      np.array([-296584.8166864211, -290062.472288043, -265770.1775742018])),
 ]
 
+
+# ---- rscan known answers (TestRevFwdFold.hs:934-1000): rev' = gradient of the sum of the stacked accumulators ----
+def _rtr(T, t):
+    r = len(T.shape(t))
+    return T.stranspose([1, 0] + list(range(2, r)), t)
+
+
+def sin0Scan1(T, x0):      # rscan (\x _a -> sin x) x0 (rrepl [1] 42)
+    from horde_ad_b200 import nn
+    return nn.sscan(T, lambda x, _a: T.unary("sin", x), x0, T.srepl([1], 42.0))
+
+
+def sin0Scan2(T, x0):      # ... (rrepl [5] 42)
+    from horde_ad_b200 import nn
+    return nn.sscan(T, lambda x, _a: T.unary("sin", x), x0, T.srepl([5], 42.0))
+
+
+def sin0Scan3(T, a0):      # rscan (\_x a -> sin a) (rreplicate0N [1,1,1,1,1] 84) (rreplicate 3 a0)
+    from horde_ad_b200 import nn
+    return nn.sscan(T, lambda _x, a: T.unary("sin", a), T.srepl([1, 1, 1, 1, 1], 84.0), T.sreplicate(3, a0))
+
+
+def sin0Scan4(T, a0):      # rscan (\x a -> atan2H (sin x) (sin a)) (2 * a0) (rreplicate 3 a0)
+    from horde_ad_b200 import nn
+    two = T.srepl([1, 1, 1, 1, 1], 2.0)
+    return nn.sscan(T, lambda x, a: T.binary("atan2", T.unary("sin", x), T.unary("sin", a)),
+                    T.binary("mul", two, a0), T.sreplicate(3, a0))
+
+
+def sin0Scan6(T, a0):      # rscan (\x a -> rtr (rtr x + rreplicate 1 (rreplicate 2 a))) (rreplicate 2 (rreplicate 1 a0)) (rreplicate 2 a0)
+    from horde_ad_b200 import nn
+    step = lambda x, a: _rtr(T, T.binary("add", _rtr(T, x), T.sreplicate(1, T.sreplicate(2, a))))
+    return nn.sscan(T, step, T.sreplicate(2, T.sreplicate(1, a0)), T.sreplicate(2, a0))
+
+
+_X5 = np.full((1, 1, 1, 1, 1), 1.1)
+SCAN_GOLDEN = [   # (name, f, input, expected gradient of the sum), eps 1e-10
+    ("testSin0Scan1", sin0Scan1, _X5, np.full((1, 1, 1, 1, 1), 1.4535961214255773)),
+    ("testSin0Scan2", sin0Scan2, _X5, np.full((1, 1, 1, 1, 1), 2.2207726343670955)),
+    ("testSin0Scan3", sin0Scan3, _X5, np.full((1, 1, 1, 1, 1), 1.360788364276732)),
+    ("testSin0Scan4", sin0Scan4, _X5, np.full((1, 1, 1, 1, 1), -0.4458209450295252)),
+    ("testSin0Scan6", sin0Scan6, np.full((1, 1), 1.1), np.full((1, 1), 12.0)),
+]
+

@@ -1148,3 +1148,10 @@ def test_bar_relu_vjp_and_forward_known_answers_on_the_device(dev):
         _, t = ad.jvp(dev, f, [dev.sconcrete(x)], [dev.sconcrete(dx)])
         np.testing.assert_allclose(dev.to_numpy(t), expected, atol=1e-10, rtol=1e-11, err_msg=name)
 
+
+@pytest.mark.parametrize("name,f,x,expected", P.SCAN_GOLDEN, ids=[g[0] for g in P.SCAN_GOLDEN])
+def test_scan_known_answers_on_the_device(dev, name, f, x, expected):
+    """testSin0Scan1/2/3/4/6 (TestRevFwdFold.hs:934-1000) reproduced by the CUDA path, eps 1e-10."""
+    _, (g,) = ad.grad(dev, lambda T, t: T.ssum0(f(T, t)), [dev.sconcrete(x)])
+    np.testing.assert_allclose(dev.to_numpy(g), expected, atol=1e-10, rtol=0)
+

@@ -336,3 +336,11 @@ def test_bar_relu_forward_known_answers(oracle, name, f, x, dx, expected):
     _, t = ad.jvp(oracle, f, [oracle.sconcrete(x)], [oracle.sconcrete(dx)])
     np.testing.assert_allclose(oracle.to_numpy(t), expected, atol=1e-10, rtol=1e-11)
 
+
+@pytest.mark.parametrize("name,f,x,expected", P.SCAN_GOLDEN, ids=[g[0] for g in P.SCAN_GOLDEN])
+def test_scan_known_answers(oracle, name, f, x, expected):
+    """testSin0Scan1/2/3/4/6 (TestRevFwdFold.hs:934-1000): rscan = a host loop over the slices (tscan,
+    OpsConcrete.hs:66-90) whose unrolled ops transpose to the reference's gradients, eps 1e-10."""
+    _, (g,) = ad.grad(oracle, lambda T, t: T.ssum0(f(T, t)), [oracle.sconcrete(x)])
+    np.testing.assert_allclose(oracle.to_numpy(g), expected, atol=1e-10, rtol=0)
+
