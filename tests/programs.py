@@ -563,3 +563,15 @@ SCAN_GOLDEN = [   # (name, f, input, expected gradient of the sum), eps 1e-10
     ("testSin0Scan6", sin0Scan6, np.full((1, 1), 1.1), np.full((1, 1), 12.0)),
 ]
 
+
+# ---- overleaf (TestAdaptorSimplified.hs:498-600): rsum (rbuild [50] (\[i] -> rindex v [i `remH` 28])), which the
+#      reference prints as  ssum0 (sgather1 @50 v (\i -> [remH i 28]))  with the gradient artifact
+#      sscatter1 @50 (sreplicate0N @[50] dret) (\i -> [remH i 28])  -- a gather with wrap-around and a scatter
+#      with collisions, in Double and in every integer width ----
+def overleaf(T, v):
+    n = T.shape(v)[0]
+    return T.ssum0(T.sgather([50], v, lambda ix: [ix[0].remH(n)], 1))
+
+
+OVERLEAF_GRAD = [2.0] * 22 + [1.0] * 6
+

@@ -344,3 +344,18 @@ def test_scan_known_answers(oracle, name, f, x, expected):
     _, (g,) = ad.grad(oracle, lambda T, t: T.ssum0(f(T, t)), [oracle.sconcrete(x)])
     np.testing.assert_allclose(oracle.to_numpy(g), expected, atol=1e-10, rtol=0)
 
+
+@pytest.mark.parametrize("dtype", [np.float64, np.int64, np.int32, np.int16, np.int8])
+def test_overleaf_gather_with_wraparound(oracle, dtype):
+    """testOverleaf, testOverleafInt64p / CIntp / Int16p / Int8p (TestAdaptorSimplified.hs:507-585): gradient of
+    ssum0 (sgather1 @50 v (\\i -> [remH i 28])) = sscatter1 with collisions = [2 x 22, 1 x 6], in the tensor's own
+    (integer) arithmetic; testOverleafGrad1 (:515-519): a one-element vector collects all 50."""
+    v = np.arange(28).astype(dtype)
+    val, (g,) = ad.grad(oracle, P.overleaf, [oracle.sconcrete(v)])
+    got = oracle.to_numpy(g)
+    assert got.dtype == np.dtype(dtype)
+    np.testing.assert_array_equal(got, np.array(P.OVERLEAF_GRAD).astype(dtype))
+    assert oracle.to_numpy(val) == np.array((np.arange(50) % 28).sum()).astype(dtype)      # Int8 wraps like the reference's
+    _, (g1,) = ad.grad(oracle, P.overleaf, [oracle.sconcrete(np.array([27.0]))])
+    np.testing.assert_array_equal(oracle.to_numpy(g1), [50.0])
+
