@@ -359,3 +359,17 @@ def test_overleaf_gather_with_wraparound(oracle, dtype):
     _, (g1,) = ad.grad(oracle, P.overleaf, [oracle.sconcrete(np.array([27.0]))])
     np.testing.assert_array_equal(oracle.to_numpy(g1), [50.0])
 
+
+def test_high_rank_logistic_and_bar_relu_known_answers(oracle):
+    """testLogistic0 / 5 / 52, testBarReluADVal / ADVal3 / ADValDt (TestHighRankSimplified.hs:527-560, 696-712): rank-5
+    and rank-7 tensors through logistic's hand-written dual (CommonRankedOps.hs:55-63) and the atan2 / sin / relu chain."""
+    g = lambda f, x, dt=None: oracle.to_numpy(ad.grad(oracle, f, [oracle.sconcrete(x)], dt=dt)[1][0])
+    ssum = lambda f: (lambda T, t: T.ssum0(f(T, t)))
+    np.testing.assert_allclose(g(ssum(nn.logistic), np.array(3.0)), 4.5176659730912e-2, atol=1e-10, rtol=0)
+    np.testing.assert_allclose(g(ssum(nn.logistic), P.T16), P.LOGISTIC5_GRAD, atol=1e-10, rtol=0)
+    np.testing.assert_allclose(g(ssum(lambda T, t: nn.logistic(T, nn.logistic(T, t))), P.T16), P.LOGISTIC52_GRAD, atol=1e-10, rtol=0)
+    np.testing.assert_allclose(g(ssum(P.barRelu), P.T48), P.BARRELU_T48_GRAD, atol=1e-10, rtol=0)
+    np.testing.assert_allclose(g(ssum(P.barRelu), 0.001 * P.T48), P.BARRELU_T48_SCALED_GRAD, atol=1e-10, rtol=0)
+    dt = oracle.sconcrete(np.full(P.T16.shape, 42.2))
+    np.testing.assert_allclose(g(P.barRelu, P.T16, dt), P.BARRELU_T16_DT_GRAD, atol=1e-6, rtol=0)
+
