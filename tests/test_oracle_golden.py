@@ -373,3 +373,28 @@ def test_high_rank_logistic_and_bar_relu_known_answers(oracle):
     dt = oracle.sconcrete(np.full(P.T16.shape, 42.2))
     np.testing.assert_allclose(g(P.barRelu, P.T16, dt), P.BARRELU_T16_DT_GRAD, atol=1e-6, rtol=0)
 
+
+def test_map_accum_empty_and_single_step_known_answers(oracle):
+    """testSin0rmapAccumRD0R0 / 0R2 / 0R3 / 0S / 01SN (TestRevFwdFold.hs:1264-1281, 1542-1625): tmapAccum over an
+    EMPTY sequence returns the initial accumulator (gradient 1), zero-length tensors flow through replicate /
+    reverse / + with a zero gradient, and a single step with a pair accumulator gives cos 1.1."""
+    x0 = oracle.sconcrete(np.array(1.1))
+    # 0R0: rreverse (rreverse (rreplicate 0 x0) + rreplicate 0 x0), rev' = gradient of the (empty) sum
+    f0 = lambda T, x: T.ssum0(T.sreverse(T.binary("add", T.sreverse(T.sreplicate(0, x)), T.sreplicate(0, x))))
+    v, (g,) = ad.grad(oracle, f0, [x0])
+    assert float(oracle.to_numpy(v)) == 0.0 and float(oracle.to_numpy(g)) == 0.0
+    # 0S / 0R2 / 0R3: tproject1 (tmapAccumR g x0 (empty)) with g x _a = (sin x, sin x)
+    def f1(T, x):
+        acc, bs = nn.smapAccumL(T, lambda a, _e: (T.unary("sin", a), T.unary("sin", a)), x, T.srepl([0], 0.0))
+        assert bs is None
+        return acc
+    _, (g,) = ad.grad(oracle, f1, [x0])
+    np.testing.assert_allclose(oracle.to_numpy(g), 1.0, atol=1e-10, rtol=0)
+    # 01SN: one step, accumulator = (3, x0), g xh _a = let x = snd xh in ((sin x, sin x), sin x); result = the stacked bs
+    def f2(T, x):
+        step = lambda xh, _a: ((T.unary("sin", xh[1]), T.unary("sin", xh[1])), T.unary("sin", xh[1]))
+        _acc, bs = nn.smapAccumL(T, step, (T.sscalar(3.0), x), T.srepl([1], 0.0))
+        return T.ssum0(bs)
+    _, (g,) = ad.grad(oracle, f2, [x0])
+    np.testing.assert_allclose(oracle.to_numpy(g), 0.4535961214255773, atol=1e-10, rtol=0)
+
