@@ -584,3 +584,46 @@ BARRELU_T48_GRAD = np.array([3.513740871835189e-4,3.8830416352632824e-4,3.981974
 BARRELU_T48_SCALED_GRAD = np.array([2.8846476339094805e-4,2.885038541771792e-4,2.885145151321922e-4,2.8854294397024206e-4,2.885852309100301e-4,2.885923176600045e-4,2.887454843457817e-4,2.886097295122454e-4,2.8846476339094805e-4,2.885038541771792e-4,2.885145151321922e-4,2.8854294397024206e-4,2.8860655161315664e-4,2.88595871110374e-4,2.887454843457817e-4,2.885884088500461e-4,2.884182085399516e-4,2.884075468755327e-4,2.8842176240868867e-4,2.8840399312321096e-4,0.0,2.8840370860416445e-4,2.884007943794131e-4,0.0,2.884469945274759e-4,2.8843242392031246e-4,2.884288700806792e-4,0.0,2.885212670262263e-4,2.884110805753153e-4,0.0,2.8849283778617973e-4,2.884075468755327e-4,2.884075468755327e-4,2.884075468755327e-4,2.884075468755327e-4,0.0,0.0,0.0,0.0,2.884892851579934e-4,0.0,0.0,0.0,2.884892851579934e-4,2.884892851579934e-4,2.884892851579934e-4,2.884892851579934e-4]).reshape(3, 1, 2, 2, 1, 2, 2)
 BARRELU_T16_DT_GRAD = np.array([1.2916050471365906e-2,1.2469757606504572e-2,1.3064120086501589e-2,1.2320300700062944e-2,0.0,1.217049789428711e-2,1.2185494267265312e-2,0.0,1.4105363649830907e-2,1.3506236503127638e-2,1.3359213691150671e-2,0.0,1.7066665416485535e-2,1.2618022646204737e-2,0.0,1.595161947206668e-2]).reshape(2, 2, 1, 2, 2)
 
+
+# ---- rbuild / rindex / rfromList programs of TestHighRankSimplified.hs:557-690 (non-vectorised host loops) ----
+def braidedBuilds(T, r):
+    r"""rbuild [3, 4] (\[ix1, ix2] -> rfromList [rfromIndex0 ix2, 7, rsum0 (rslice 1 1 r), -0.2] ! [ix1])  (:559-563)."""
+    from horde_ad_b200 import nn
+
+    def f(ix):
+        ix1, ix2 = ix
+        lst = T.sfromVector([T.sscalar(float(ix2)), T.sscalar(7.0), T.ssum0(T.sslice(1, 1, r)), T.sscalar(-0.2)])
+        return T.sindex(lst, [ix1])
+    return nn.sbuild(T, [3, 4], f)
+
+
+def concatBuild2(T, r):
+    r"""rbuild1 5 (\i -> rbuild1 2 (\j -> rmap0N (* rfromIndex0 (maxH j (i `quotH` (j + 1)))) r))  (:672-676)."""
+    from horde_ad_b200 import nn
+    sh = list(T.shape(r))
+    scale = lambda k: T.binary("mul", r, T.srepl(sh, float(k)))
+    return nn.sbuild1(T, 5, lambda i: nn.sbuild1(T, 2, lambda j: scale(max(j, i // (j + 1)))))
+
+
+def concatBuildm(T, r):
+    r"""rbuild1 7 (\i -> rmap0N (* rfromIndex0 (kfloor (rsum0 (r ! [i])))) r)  (:640-645); r ! [i] is all zeros
+    when i runs past the leading extent (OpsConcrete.hs:1448-1450)."""
+    from horde_ad_b200 import nn
+    sh = list(T.shape(r))
+
+    def row(i):
+        k = int(np.floor(float(T.kfromS(T.ssum0(T.sindex(r, [i]))))))
+        return T.binary("mul", r, T.srepl(sh, float(k)))
+    return nn.sbuild1(T, 7, row)
+
+
+V7 = np.array([0.651, 0.14, 0.3414, -0.14, 0.0014, 0.0020014, 0.9999])
+BUILD_GOLDEN = [   # (name, f, input, expected gradient of the sum), eps 1e-10
+    ("testBraidedBuilds", braidedBuilds, np.full(4, 3.4), np.array([0.0, 4.0, 0.0, 0.0])),
+    ("testBraidedBuilds1", braidedBuilds, T16, np.array([0.0] * 8 + [4.0] * 8).reshape(2, 2, 1, 2, 2)),
+    ("testConcatBuild2", concatBuild2, np.array([0.651, 0.14, 0.3414]), np.full(3, 16.0)),
+    ("testConcatBuild22", concatBuild2, T48, np.full(T48.shape, 16.0)),
+    ("testConcatBuild0m", concatBuildm, V7, np.full(7, -1.0)),
+    ("testConcatBuild1m", concatBuildm, T48, np.full(T48.shape, 962.0)),
+]
+

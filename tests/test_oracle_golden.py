@@ -398,3 +398,11 @@ def test_map_accum_empty_and_single_step_known_answers(oracle):
     _, (g,) = ad.grad(oracle, f2, [x0])
     np.testing.assert_allclose(oracle.to_numpy(g), 0.4535961214255773, atol=1e-10, rtol=0)
 
+
+@pytest.mark.parametrize("name,f,x,expected", P.BUILD_GOLDEN, ids=[g[0] for g in P.BUILD_GOLDEN])
+def test_high_rank_build_known_answers(oracle, name, f, x, expected):
+    """testBraidedBuilds/1, testConcatBuild2/22/0m/1m (TestHighRankSimplified.hs:565-690): rbuild / rfromList /
+    rindex / rslice host loops incl. an index that runs out of bounds (zeros), eps 1e-10."""
+    _, (g,) = ad.grad(oracle, lambda T, t: T.ssum0(f(T, t)), [oracle.sconcrete(x)])
+    np.testing.assert_allclose(oracle.to_numpy(g), expected, atol=1e-10, rtol=0)
+
