@@ -1,0 +1,127 @@
+"""Host-side logic of the reverse sweep (horde-ad_b200/ad.py) that the device path shares: deferred products
+accumulated by `smatmul2_acc` / `smatmul2_acc_pair`, zero-padded slice cotangents joined by one `sappend`.
+Runs on the CPU oracle with a call-counting wrapper; values are checked against the plain rules."""
+import numpy as np
+import pytest
+
+from horde_ad_b200 import ad
+from oracle.concrete import ConcreteBackend
+
+
+class Counting(ConcreteBackend):
+    """ConcreteBackend that counts the calls of the methods the sweep chooses between."""
+
+    def __init__(self):
+        super().__init__()
+        self.calls = {}
+
+    def _count(self, name):
+        self.calls[name] = self.calls.get(name, 0) + 1
+
+
+for _name in ("smatmul2", "smatmul2_acc", "smatmul2_acc_pair", "smatmul2_pair", "smatmul2_sum", "sappend", "srepl",
+              "add_accumulate"):
+    def _wrap(name):
+        base = getattr(ConcreteBackend, name)
+
+        def method(self, *a, **k):
+            self._count(name)
+            return base(self, *a, **k)
+        return method
+    setattr(Counting, _name, _wrap(_name))
+
+
+def fd_grad(f, x, eps=1e-6):
+    g = np.zeros_like(x)
+    for i in np.ndindex(*x.shape):
+        d = np.zeros_like(x)
+        d[i] = eps
+        g[i] = (f(x + d) - f(x - d)) / (2 * eps)
+    return g
+
+
+def test_two_halves_of_a_state_become_one_append():
+    rng = np.random.default_rng(0)
+    s = rng.uniform(-1, 1, (6, 3))
+
+    def f(T, t):
+        a, b = T.sslice(0, 2, t), T.sslice(2, 4, t)                      # two windows that tile the leading axis
+        return T.binary("add", T.ssum0(T.unary("sin", a)), T.ssum0(T.binary("mul", b, b)))
+    B = Counting()
+    _, (g,) = ad.grad(B, f, [s])
+    np.testing.assert_allclose(g, np.concatenate([np.cos(s[:2]), 2 * s[2:]]), rtol=1e-14)
+    # one append, no zero blocks (the only srepl is the cotangent of ones of the result), nothing added
+    assert B.calls.get("sappend") == 1
+    assert B.calls.get("srepl", 0) == 1 and B.calls.get("add_accumulate", 0) == 0
+
+
+@pytest.mark.parametrize("windows", [[(0, 2), (3, 3)],            # a gap
+                                     [(0, 4), (2, 4)],            # an overlap
+                                     [(1, 2)],                    # a single interior window
+                                     [(0, 2), (2, 2), (4, 2)],    # three windows that tile the axis
+                                     [(4, 2), (0, 2), (2, 2)]])   # ... arriving out of order
+def test_slice_windows_against_finite_differences(windows):
+    rng = np.random.default_rng(1)
+    s = rng.uniform(-1, 1, (6, 2))
+
+    def prog(T, t):
+        out = None
+        for k, (i, n) in enumerate(windows):
+            term = T.ssum0(T.unary("sin", T.binary("mul", T.sslice(i, n, t), T.srepl([n, 2], float(k + 1)))))
+            out = term if out is None else T.binary("add", out, term)
+        return out
+    B = ConcreteBackend()
+    _, (g,) = ad.grad(B, prog, [s])
+    ref = fd_grad(lambda x: sum(np.sin(x[i:i + n] * (k + 1)).sum() for k, (i, n) in enumerate(windows)), s)
+    np.testing.assert_allclose(g, ref, rtol=1e-7, atol=1e-9)
+
+
+def test_weight_used_at_every_step_accumulates_in_the_product():
+    rng = np.random.default_rng(2)
+    w, x = rng.uniform(-.3, .3, (5, 5)), rng.uniform(-.5, .5, (5, 4))
+
+    def f(T, W, X):
+        h = X
+        for _ in range(3):
+            h = T.unary("tanh", T.smatmul2(W, h))
+        return T.ssum0(h)
+    B = Counting()
+    _, (gw, gx) = ad.grad(B, f, [w, x])
+    # three uses of W: the first cotangent is a product, the other two are accumulated by smatmul2_acc
+    assert B.calls.get("smatmul2_acc") == 2
+
+    def val(W):
+        h = x
+        for _ in range(3):
+            h = np.tanh(W @ h)
+        return h.sum()
+    np.testing.assert_allclose(gw, fd_grad(val, w), rtol=1e-7, atol=1e-9)
+
+
+def test_paired_layer_node_pairs_its_cotangents():
+    rng = np.random.default_rng(3)
+    wx, ws = rng.uniform(-.3, .3, (4, 4)), rng.uniform(-.3, .3, (4, 4))
+    x0, s0 = rng.uniform(-.5, .5, (4, 3)), rng.uniform(-.5, .5, (4, 3))
+
+    def f(T, WX, WS, X, S):
+        x, s = X, S
+        for _ in range(3):                                   # both weights used three times
+            y = T.unary("tanh", T.smatmul2_sum(WX, x, WS, s))
+            x, s = s, y
+        return T.ssum0(y)
+    B = Counting()
+    v, grads = ad.grad(B, f, [wx, ws, x0, s0])
+    assert B.calls.get("smatmul2_sum") == 3
+    assert B.calls.get("smatmul2_acc_pair") == 2             # second and third contribution to (dWX, dWS)
+    assert B.calls.get("smatmul2_pair", 0) >= 2              # (dX, dS) of a step share one launch
+
+    def val(WX, WS, X, S):
+        x, s = X, S
+        for _ in range(3):
+            y = np.tanh(WX @ x + WS @ s)
+            x, s = s, y
+        return y.sum()
+    args = [wx, ws, x0, s0]
+    for k in range(4):
+        ref = fd_grad(lambda a: val(*[a if j == k else args[j] for j in range(4)]), args[k])
+        np.testing.assert_allclose(grads[k], ref, rtol=1e-7, atol=1e-9)
