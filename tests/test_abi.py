@@ -72,3 +72,23 @@ def test_product_package_never_imports_the_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(root, fn)).read()
             assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), fn
+
+
+def test_generated_haskell_ffi_module_covers_the_header():
+    """bindings/haskell/HordeAd/Core/DeviceFFI.hs (tools/gen_haskell_ffi.py) declares one `foreign import ccall`
+    per symbol of include/hordeb200.h with the arity of the ctypes prototype (no GHC here: text-level check)."""
+    import os
+    import re
+    from horde_ad_b200 import ffi
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bindings", "haskell", "HordeAd",
+                        "Core", "DeviceFFI.hs")
+    hs = open(path).read()
+    sigs = dict(re.findall(r'"hordeb200.h (hb_[a-z0-9_]+)"\n  c_\w+ :: (.*)', hs))
+    assert sorted(sigs) == ffi.header_symbols()
+    for name, sig in sigs.items():
+        depth, arrows = 0, 0
+        for tok in re.split(r"(\(|\)| -> )", sig):
+            depth += (tok == "(") - (tok == ")")
+            arrows += tok == " -> " and depth == 0
+        assert arrows == len(ffi.PROTOTYPES[name]), (name, sig)
+
