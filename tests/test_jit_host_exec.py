@@ -1,0 +1,126 @@
+"""The kernel generator's OUTPUT executed on the CPU: the CUDA C text that csrc/jit.cu emits for an index program
+(`hb_jit_index_source_text`, kind 0 = offset table) is compiled with g++ behind a small shim (blockIdx / threadIdx
+as globals, the bit-cast intrinsics) and run over every position; the offsets must equal the oracle's independent
+evaluation of the same index function (ixsToLinearMaybe, OpsConcrete.hs:944-950: out of bounds -> no offset).
+Covers every tensor-free index function of the reference's gather / scatter goldens (tests/programs.py) plus the
+grammar corner cases (quotH / remH by zero, ifH, minH / maxH, negative indices).  The same kernels are compared on
+the device in tests/test_gpu_parity.py; this is the no-GPU half."""
+import ctypes as C
+import hashlib
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from horde_ad_b200 import ad, ffi, ix as ixm
+from oracle.concrete import ConcreteBackend
+from tests import programs as P
+
+SHIM = r"""
+#include <cstring>
+#define __device__
+#define __forceinline__ inline
+#define __global__
+#define __restrict__
+#define __launch_bounds__(x)
+struct hb_dim3 { unsigned x, y, z; };
+static hb_dim3 blockIdx, threadIdx;
+static inline double __longlong_as_double(long long v) { double d; std::memcpy(&d, &v, 8); return d; }
+static inline long long __double_as_longlong(double d) { long long v; std::memcpy(&v, &d, 8); return v; }
+static inline int atomicAdd(int *p, int v) { int o = *p; *p += v; return o; }
+"""
+DRIVER = r"""
+extern "C" void hbj_run(long long n, long long *offsets) {
+  for (long long b = 0; b < (n + 255) / 256; b++)
+    for (unsigned t = 0; t < 256; t++) { blockIdx.x = (unsigned)b; threadIdx.x = t; hbj_k(offsets); }
+}
+"""
+I64MIN = -(1 << 63)
+_cache = {}
+
+
+def _host_offsets(text: bytes, n: int) -> np.ndarray:
+    key = hashlib.sha1(text).hexdigest()
+    if key not in _cache:
+        d = tempfile.mkdtemp(prefix="hbj_")
+        src, so = os.path.join(d, "k.cpp"), os.path.join(d, "k.so")
+        open(src, "w").write(SHIM + text.decode() + DRIVER)
+        subprocess.run(["g++", "-O1", "-shared", "-fPIC", "-w", "-o", so, src], check=True)
+        _cache[key] = C.CDLL(so)
+    out = np.full(max(n, 1), 7, dtype=np.int64)
+    _cache[key].hbj_run(C.c_longlong(n), out.ctypes.data_as(C.c_void_p))
+    return out[:n]
+
+
+def _kernel_text(f, shm, shp):
+    """CUDA C of the offset-table kernel for index function f : Ix shm -> Ix shp; None if f reads tensors."""
+    prog = ixm.compile_program(ixm.reify(f, len(shm)), len(shm))
+    if prog.tensors:
+        return None
+    arr = (ffi.Insn * max(1, len(prog.insns)))(*prog.insns)
+    p = C.c_void_p()
+    ffi.call("hb_ixprog_build", arr, len(prog.insns), len(shm), prog.n_out, (C.c_void_p * 1)(), 0, 0, C.byref(p))
+    try:
+        strides = [int(np.prod(shp[k + 1:])) for k in range(len(shp))]
+        i64 = lambda xs: (C.c_int64 * max(1, len(xs)))(*xs)
+        buf = C.create_string_buffer(1 << 17)
+        ffi.call("hb_jit_index_source_text", p, 0, len(shm), i64(shm), len(shp), i64(shp), i64(strides), 0, buf, len(buf))
+        return buf.value
+    finally:
+        ffi.call("hb_ixprog_free", p)
+
+
+def _check(f, shm, shp, oracle):
+    shm, shp = [int(x) for x in shm], [int(x) for x in shp]
+    text = _kernel_text(f, shm, shp)
+    if text is None:
+        return False
+    n = int(np.prod(shm)) if shm else 1
+    want = ConcreteBackend._targets(oracle, shm, f, shp)          # row-major linear target, -1 = out of bounds
+    got = _host_offsets(text, n)
+    np.testing.assert_array_equal(got, np.where(want >= 0, want, I64MIN))
+    return True
+
+
+class Recording(ConcreteBackend):
+    """Records every (shm, index function, shp) that a program hands to sgather / sscatter."""
+
+    def __init__(self):
+        super().__init__()
+        self.seen = []
+
+    def _targets(self, shm, f, shp):
+        self.seen.append((list(shm), f, list(shp)))
+        return super()._targets(shm, f, shp)
+
+
+def test_generated_offset_kernels_match_the_oracle_on_the_reference_gather_scatter_programs():
+    rec = Recording()
+    for _name, prog, inp, _expected in P.GATHER_GOLDEN:
+        ad.grad(rec, lambda T, t: T.ssum0(prog(T, t)), [rec.sconcrete(inp)])      # forward gathers + adjoint scatters
+    for prog, shape, _e in getattr(P, "GATHER_COND_CASES", []):
+        prog(rec, rec.sconcrete(np.arange(int(np.prod(shape)), dtype=np.float64).reshape(shape)))
+    assert len(rec.seen) >= 20
+    plain = ConcreteBackend()
+    checked = sum(_check(f, shm, shp, plain) for shm, f, shp in rec.seen)
+    assert checked >= 20, checked
+
+
+@pytest.mark.parametrize("case", ["quot_rem_by_zero_and_negative", "ifh_min_max", "affine_out_of_bounds", "rank0"])
+def test_generated_offset_kernels_grammar_corner_cases(case):
+    plain = ConcreteBackend()
+    if case == "quot_rem_by_zero_and_negative":      # quotH a 0 = a, remH a 0 = a; truncation toward zero (Types.hs:394-419)
+        f = lambda i: [(i[0] - 3).quotH(i[1] - 1), (i[0] - 3).remH(i[1] - 1) + 2]
+        assert _check(f, [7, 4], [9, 5], plain)
+    elif case == "ifh_min_max":
+        f = lambda i: [ixm.ifH((i[0] <= 2) & ~(i[1].eq(1)), i[0], 8 - i[0]), ixm.maxH(ixm.minH(i[0] - i[1], 3), 0),
+                       abs(i[1] - 2) * (i[0] - 2).signum() + 1]
+        assert _check(f, [6, 5], [9, 4, 4], plain)
+    elif case == "affine_out_of_bounds":             # windows that run past both ends: those positions have no offset
+        f = lambda i: [i[0] + i[1] - 2, 2 * i[2] - 1]
+        assert _check(f, [5, 4, 4], [6, 5], plain)
+    else:                                            # no index variables: one position
+        assert _check(lambda i: [ixm.Ix.lift(2), ixm.Ix.lift(1)], [], [3, 2], plain)
+        assert _check(lambda i: [ixm.Ix.lift(3)], [], [3], plain)          # out of bounds
