@@ -20,13 +20,15 @@ from tests import programs as P
 
 SHIM = r"""
 #include <cstring>
+#include <cmath>
+using std::floor; using std::fabs; using std::sqrt; using std::exp; using std::log; using std::tanh; using std::sin; using std::cos;
 #define __device__
 #define __forceinline__ inline
 #define __global__
 #define __restrict__
 #define __launch_bounds__(x)
 struct hb_dim3 { unsigned x, y, z; };
-static hb_dim3 blockIdx, threadIdx;
+static hb_dim3 blockIdx, threadIdx, gridDim;
 static inline double __longlong_as_double(long long v) { double d; std::memcpy(&d, &v, 8); return d; }
 static inline long long __double_as_longlong(double d) { long long v; std::memcpy(&v, &d, 8); return v; }
 static inline int atomicAdd(int *p, int v) { int o = *p; *p += v; return o; }
@@ -124,3 +126,59 @@ def test_generated_offset_kernels_grammar_corner_cases(case):
     else:                                            # no index variables: one position
         assert _check(lambda i: [ixm.Ix.lift(2), ixm.Ix.lift(1)], [], [3, 2], plain)
         assert _check(lambda i: [ixm.Ix.lift(3)], [], [3], plain)          # out of bounds
+
+
+MAP_DRIVER = r"""
+extern "C" void hbj_run_map(unsigned nblocks, double *out, const void *p0, const void *p1) {
+  gridDim.x = nblocks;
+  for (unsigned b = 0; b < nblocks; b++)
+    for (unsigned t = 0; t < 256; t++) { blockIdx.x = b; threadIdx.x = t; hbj_k(out, p0, p1); }
+}
+"""
+
+
+def _run_map(text: bytes, out, a, b):
+    d = tempfile.mkdtemp(prefix="hbj_")
+    src, so = os.path.join(d, "k.cpp"), os.path.join(d, "k.so")
+    open(src, "w").write(SHIM + text.decode() + MAP_DRIVER)
+    subprocess.run(["g++", "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-w", "-o", so, src], check=True)
+    C.CDLL(so).hbj_run_map(C.c_uint(3), out.ctypes.data_as(C.c_void_p), a.ctypes.data_as(C.c_void_p),
+                           b.ctypes.data_as(C.c_void_p))
+
+
+def test_generated_map_kernels_match_the_oracle_on_the_host():
+    """A fused elementwise chain (ifH, maxH, floor, fromIntegral, tanh / exp / sqrt): the strided scalar-access kernel
+    over a transposed Double view and a row-major operand, and the 16-byte kernel over a contiguous operand and a
+    broadcast scalar, executed on the CPU and compared with the oracle's evaluation of the same expression."""
+    oracle = ConcreteBackend()
+    x, y = ixm.map_input(0, True), ixm.map_input(1, True)
+    e = ixm.fun1("tanh", x * y + 0.5) / (ixm.fun1("exp", -x) + 1.0) - ixm.fun1("sqrt", abs(y))
+    e = ixm.ifH(x <= y, e, ixm.maxH(x, y) * ixm.fromIntegral(ixm.floorH(y)))
+    prog = ixm.compile_program([e], 0)
+    arr = (ffi.Insn * len(prog.insns))(*prog.insns)
+    p = C.c_void_p()
+    ffi.call("hb_ixprog_build", arr, len(prog.insns), 0, prog.n_out, (C.c_void_p * 1)(), 0, 0, C.byref(p))
+    i64 = lambda xs: (C.c_int64 * len(xs))(*xs)
+    rng = np.random.default_rng(5)
+    try:
+        buf = C.create_string_buffer(1 << 17)
+        # (a) logical [30, 50]: operand 0 = transposed view of a [50, 30] array, operand 1 = row-major [30, 50]
+        a_store = rng.uniform(-2, 2, (50, 30))
+        b_store = rng.uniform(-3, 3, (30, 50))
+        ffi.call("hb_jit_map_source_text", p, 2, i64([30, 50]), 2, i64([1, 30, 50, 1]), (C.c_int * 2)(ffi.F64, ffi.F64),
+                 ffi.F64, 1, buf, len(buf))
+        out = np.full((30, 50), np.nan)
+        _run_map(buf.value, out, a_store, b_store)
+        want = oracle.fused_map(e, [a_store.T, b_store], np.float64)
+        np.testing.assert_allclose(out, want, rtol=1e-14, atol=1e-15)
+        # (b) contiguous Double [1024] and a broadcast scalar, two elements per access
+        a2, s2 = rng.uniform(-2, 2, 1024), np.array([0.75])
+        ffi.call("hb_jit_map_source_text", p, 1, i64([1024]), 2, i64([1, 0]), (C.c_int * 2)(ffi.F64, ffi.F64), ffi.F64, 2,
+                 buf, len(buf))
+        out2 = np.full(1024, np.nan)
+        _run_map(buf.value, out2, a2, s2)
+        want2 = oracle.fused_map(e, [a2, np.full(1024, 0.75)], np.float64)
+        np.testing.assert_allclose(out2, want2, rtol=1e-14, atol=1e-15)
+    finally:
+        ffi.call("hb_ixprog_free", p)
+
