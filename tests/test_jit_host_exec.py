@@ -182,3 +182,78 @@ def test_generated_map_kernels_match_the_oracle_on_the_host():
     finally:
         ffi.call("hb_ixprog_free", p)
 
+
+GATHER_DRIVER = r"""
+extern "C" void hbj_run_gather(long long n, const void *src, void *out) {
+  for (long long b = 0; b < (n + 255) / 256; b++)
+    for (unsigned t = 0; t < 256; t++) { blockIdx.x = (unsigned)b; threadIdx.x = t; hbj_k((const ELEM *)src, (ELEM *)out); }
+}
+"""
+SCATTER_DRIVER = r"""
+extern "C" void hbj_run_scatter(long long n, int *dest, int *counts, int *collision) {
+  for (long long b = 0; b < (n + 255) / 256; b++)
+    for (unsigned t = 0; t < 256; t++) { blockIdx.x = (unsigned)b; threadIdx.x = t; hbj_k(dest, counts, collision); }
+}
+"""
+
+
+def _so(text: str, driver: str):
+    d = tempfile.mkdtemp(prefix="hbj_")
+    src, so = os.path.join(d, "k.cpp"), os.path.join(d, "k.so")
+    open(src, "w").write(SHIM + text + driver)
+    subprocess.run(["g++", "-O1", "-shared", "-fPIC", "-w", "-o", so, src], check=True)
+    return C.CDLL(so)
+
+
+def _index_kernel(f, shm, shp, kind, es):
+    prog = ixm.compile_program(ixm.reify(f, len(shm)), len(shm))
+    arr = (ffi.Insn * max(1, len(prog.insns)))(*prog.insns)
+    p = C.c_void_p()
+    ffi.call("hb_ixprog_build", arr, len(prog.insns), len(shm), prog.n_out, (C.c_void_p * 1)(), 0, 0, C.byref(p))
+    try:
+        strides = [int(np.prod(shp[k + 1:])) for k in range(len(shp))]
+        i64 = lambda xs: (C.c_int64 * max(1, len(xs)))(*xs)
+        buf = C.create_string_buffer(1 << 17)
+        ffi.call("hb_jit_index_source_text", p, kind, len(shm), i64(shm), len(shp), i64(shp), i64(strides), es, buf, len(buf))
+        return buf.value.decode()
+    finally:
+        ffi.call("hb_ixprog_free", p)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32, np.int16, np.int8])
+def test_generated_element_gather_kernels_on_the_host(dtype):
+    """kind 1: the rank-0 gather (one element of 8 / 4 / 2 / 1 bytes per position, zero when out of bounds,
+    OpsConcrete.hs:1488-1490) executed on the CPU = the oracle's sgather, bit for bit."""
+    import re
+    oracle = ConcreteBackend()
+    f = lambda i: [i[0] + i[1] - 1, ixm.ifH(i[0].eq(3), -4, (2 * i[1]).remH(5))]      # row 3: out of bounds
+    shm, shp = [6, 4], [7, 5]
+    es = np.dtype(dtype).itemsize
+    text = _index_kernel(f, shm, shp, 1, es)
+    elem = re.search(r"hbj_k\(const (.+?) \*__restrict__ src", text).group(1)
+    lib = _so(text, GATHER_DRIVER.replace("ELEM", elem))
+    rng = np.random.default_rng(6)
+    src = (rng.uniform(-100, 100, shp)).astype(dtype)
+    out = np.full(shm, 1, dtype=dtype)
+    lib.hbj_run_gather(C.c_longlong(24), src.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    want = oracle.sgather(shm, src, f, 2)
+    assert out.tobytes() == np.ascontiguousarray(want).tobytes()
+
+
+def test_generated_scatter_destination_kernels_on_the_host():
+    """kind 2: destination of every source position (-1 = dropped, OpsConcrete.hs:1527-1528), per-destination
+    counts and the collision flag that selects the deterministic ordered path."""
+    oracle = ConcreteBackend()
+    for f, shm, shp, collide in ((lambda i: [i[0] + i[1] - 1], [5, 3], [6], True),
+                                 (lambda i: [i[0], i[1]], [3, 4], [3, 5], False)):
+        text = _index_kernel(f, shm, shp, 2, 0)
+        lib = _so(text, SCATTER_DRIVER)
+        n, P_ = int(np.prod(shm)), int(np.prod(shp))
+        dest, counts, coll = np.full(n, 99, np.int32), np.zeros(P_, np.int32), np.zeros(1, np.int32)
+        lib.hbj_run_scatter(C.c_longlong(n), dest.ctypes.data_as(C.c_void_p), counts.ctypes.data_as(C.c_void_p),
+                            coll.ctypes.data_as(C.c_void_p))
+        want = ConcreteBackend._targets(oracle, shm, f, shp)
+        np.testing.assert_array_equal(dest, want)
+        np.testing.assert_array_equal(counts, np.bincount(want[want >= 0], minlength=P_))
+        assert bool(coll[0]) == collide
+
