@@ -627,3 +627,38 @@ BUILD_GOLDEN = [   # (name, f, input, expected gradient of the sum), eps 1e-10
     ("testConcatBuild1m", concatBuildm, T48, np.full(T48.shape, 962.0)),
 ]
 
+
+# ---- detSquare (TestGatherSimplified.hs:1725-1790): the determinant as a sum over all permutations,
+#      det a = ssum0 (kbuild1 @(ell!) (\i -> (-1) ** q[i] * rfold (*) 1 (rgather1 ell a (\i2 -> [i2, p[i, i2]]))))
+#      with p = the permutation table (idx_to_perm: factorial-base digits pick the n-th free spot = lexicographic
+#      order) and q = the inversion numbers; a data-dependent gather (table look-up inside the index function), a
+#      product fold and a per-element host build in one program ----
+def _perm_tables(n):
+    import itertools
+    perms = np.array(list(itertools.permutations(range(n))), dtype=np.int64)           # lexicographic = idx_to_perm
+    inv = np.array([sum(1 for a in range(n) for b in range(a + 1, n) if p[a] > p[b]) for p in perms], dtype=np.int64)
+    return perms, inv
+
+
+def detSquare(T, a):
+    from horde_ad_b200 import nn
+    ell = T.shape(a)[1]
+    perms, inv = _perm_tables(ell)
+    p = T.sconcrete(perms) if not hasattr(T, "B") else T.B.sconcrete(perms)     # a plain (non-differentiated) table
+    one = T.sscalar(1.0)
+
+    def f(i):
+        row = T.sgather([ell], a, lambda ix: [ix[0], T.ix_tbl(p, [i, ix[0]])], 2)
+        prod = nn.sfold(T, lambda acc, e: T.binary("mul", acc, e), one, row)
+        return T.binary("mul", T.sscalar(float((-1.0) ** int(inv[i]))), prod)
+    return T.ssum0(T.sfromVector([f(i) for i in range(len(perms))]))
+
+
+DET6_IN = 0.01 * np.array([40.1, 32.1, 40.1, 32.1, 40.1, 22.0,
+                           9.71, 58.8943200001, 18.1, 29.1, 32.1, 40.1,
+                           55.8943200001, 1, -2, 0.97, 58.200001, 1,
+                           40.1, 29.0, 53.99432, 7.1, 58.8943200001, 18.1,
+                           32.1, 40.1, 29.0, 53.99432, 2.971, 58.8943200001,
+                           40.1, 32.0, 53.99432, 0.97, 25.8943200001, 5]).reshape(6, 6)
+DET6_GRAD = np.array([-4.869053606042778e-3,5.097805950791719e-4,2.8429105389292052e-3,2.7764540017998364e-2,4.728231081593177e-3,-2.4786176657837146e-2,-2.3469141678115176e-3,1.1152144353350756e-2,-5.653171988563392e-3,-2.9237121329780706e-3,1.9330615364900276e-3,-9.47499409844526e-4,8.025631739575951e-3,1.532840697726606e-3,-7.047121923697899e-3,-4.305940089911722e-3,1.4834586948324607e-4,1.9922535230070225e-3,-8.022565662650867e-3,-1.2603575569596842e-2,8.144948602197404e-3,-9.343418236792108e-3,8.06305133890595e-3,1.7102844846324558e-2,4.888906896881243e-3,-4.884300437195866e-3,4.144990592410334e-4,-4.765756648788264e-3,-4.741976230085896e-3,1.3056977293001447e-2,1.0096879396193574e-2,1.1166653675142208e-2,-1.279846251614077e-4,-7.896243314270949e-3,-9.67019219688691e-3,-5.316279354872351e-3]).reshape(6, 6)
+

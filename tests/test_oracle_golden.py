@@ -406,3 +406,12 @@ def test_high_rank_build_known_answers(oracle, name, f, x, expected):
     _, (g,) = ad.grad(oracle, lambda T, t: T.ssum0(f(T, t)), [oracle.sconcrete(x)])
     np.testing.assert_allclose(oracle.to_numpy(g), expected, atol=1e-10, rtol=0)
 
+
+def test_det_square_known_answer(oracle):
+    """testDetSquare3 (TestGatherSimplified.hs:1825-1838, eps 1e-5): the gradient of the permutation-sum determinant
+    of a 6 x 6 matrix (720 data-dependent gathers + product folds) = the reference's literal = det(a) * inv(a)^T."""
+    v, (g,) = ad.grad(oracle, P.detSquare, [oracle.sconcrete(P.DET6_IN)])
+    np.testing.assert_allclose(float(oracle.to_numpy(v)), np.linalg.det(P.DET6_IN), rtol=1e-10)
+    np.testing.assert_allclose(oracle.to_numpy(g), P.DET6_GRAD, atol=1e-5, rtol=0)
+    np.testing.assert_allclose(oracle.to_numpy(g), np.linalg.det(P.DET6_IN) * np.linalg.inv(P.DET6_IN).T, rtol=1e-8, atol=1e-12)
+
