@@ -415,3 +415,28 @@ def test_det_square_known_answer(oracle):
     np.testing.assert_allclose(oracle.to_numpy(g), P.DET6_GRAD, atol=1e-5, rtol=0)
     np.testing.assert_allclose(oracle.to_numpy(g), np.linalg.det(P.DET6_IN) * np.linalg.inv(P.DET6_IN).T, rtol=1e-8, atol=1e-12)
 
+
+def test_fold_goldens_with_tensor_steps(oracle):
+    """testSin0Fold5 (1.2992412552109085) and testSin0Fold8 (-2.200311410593445), TestRevFwdFold.hs:572-582, 598-608:
+    fold steps built from rsum / rtr / rreplicate / atan2H over rank-1 and rank-2 intermediates, eps 1e-10."""
+    o = oracle
+    tr = lambda T, t: T.stranspose([1, 0] + list(range(2, len(T.shape(t)))), t)
+    sin = lambda T, v: T.unary("sin", v)
+
+    def fold5(T, a0):
+        def step(x, a):                                   # x : [], a : [2, 5]
+            inner = T.ssum(sin(T, T.ssum(tr(T, T.sreplicate(7, a)))))        # [7,2,5] -> [2,7,5] -> [7,5] -> sin -> [5]
+            return T.ssum(T.binary("atan2", sin(T, T.sreplicate(5, x)), inner))
+        return nn.sfold(T, step, T.binary("mul", T.sscalar(2.0), a0), T.sreplicate(3, T.sreplicate(2, T.sreplicate(5, a0))))
+
+    def fold8(T, a0):
+        def step(x, a):                                   # x : [2, 5], a : []
+            num = T.ssum(tr(T, sin(T, x)))                                    # [5,2] -> [2]
+            den = T.sreplicate(2, sin(T, T.ssum(T.sreplicate(7, a))))         # [2]
+            return tr(T, T.sreplicate(5, T.binary("atan2", num, den)))        # [5,2] -> [2,5]
+        acc0 = T.sreplicate(2, T.sreplicate(5, T.binary("mul", T.sscalar(2.0), a0)))
+        return T.ssum0(nn.sfold(T, step, acc0, T.sreplicate(3, a0)))
+    for f, expected in ((fold5, 1.2992412552109085), (fold8, -2.200311410593445)):
+        _, (g,) = ad.grad(o, f, [o.sscalar(1.1)])
+        np.testing.assert_allclose(float(np.asarray(g)), expected, atol=1e-10, rtol=0)
+
