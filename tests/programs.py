@@ -662,3 +662,25 @@ DET6_IN = 0.01 * np.array([40.1, 32.1, 40.1, 32.1, 40.1, 22.0,
                            40.1, 32.0, 53.99432, 0.97, 25.8943200001, 5]).reshape(6, 6)
 DET6_GRAD = np.array([-4.869053606042778e-3,5.097805950791719e-4,2.8429105389292052e-3,2.7764540017998364e-2,4.728231081593177e-3,-2.4786176657837146e-2,-2.3469141678115176e-3,1.1152144353350756e-2,-5.653171988563392e-3,-2.9237121329780706e-3,1.9330615364900276e-3,-9.47499409844526e-4,8.025631739575951e-3,1.532840697726606e-3,-7.047121923697899e-3,-4.305940089911722e-3,1.4834586948324607e-4,1.9922535230070225e-3,-8.022565662650867e-3,-1.2603575569596842e-2,8.144948602197404e-3,-9.343418236792108e-3,8.06305133890595e-3,1.7102844846324558e-2,4.888906896881243e-3,-4.884300437195866e-3,4.144990592410334e-4,-4.765756648788264e-3,-4.741976230085896e-3,1.3056977293001447e-2,1.0096879396193574e-2,1.1166653675142208e-2,-1.279846251614077e-4,-7.896243314270949e-3,-9.67019219688691e-3,-5.316279354872351e-3]).reshape(6, 6)
 
+
+def fooNoGo(T, v):
+    """fooNoGo (TestAdaptorSimplified.hs:1730-1745): rbuild1 with an index clamped by minH / maxH after a floor of
+    the sum, ifH on a tensor element, rmap0N with a data-dependent choice, rslice, elementwise / and *."""
+    from horde_ad_b200 import nn
+    r = T.ssum0(v)
+    rv = float(T.kfromS(r))
+
+    def body(ix):
+        j = max(min(ix + int(np.floor(rv)), 2), 0)
+        inner = _bar(T, T.sscalar(3.14), _bar(T, T.sscalar(3.14), T.sindex(v, [j])))
+        cond = float(T.kfromS(T.sindex(v, [ix * 2]))) <= 0 and 6 > abs(ix)
+        return T.binary("add", inner, r if cond else T.binary("mul", T.sscalar(5.0), r))
+    built = nn.sbuild1(T, 3, body)
+    mapped = nn.smap0N(T, lambda x: r if float(T.kfromS(x)) > rv else x, v)
+    ones = nn.sbuild1(T, 3, lambda _i: T.sscalar(1.0))
+    return T.binary("mul", T.binary("divide", built, T.sslice(1, 3, mapped)), ones)
+
+
+FOONOGO_IN = np.array([1.1, 2.2, 3.3, 4, 5])
+FOONOGO_GRAD = np.array([5.037878787878788, -14.394255484765257, 43.23648655081373, -0.8403418295960368, 5.037878787878788])
+

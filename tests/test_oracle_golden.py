@@ -440,3 +440,9 @@ def test_fold_goldens_with_tensor_steps(oracle):
         _, (g,) = ad.grad(o, f, [o.sscalar(1.1)])
         np.testing.assert_allclose(float(np.asarray(g)), expected, atol=1e-10, rtol=0)
 
+
+def test_foo_no_go_known_answer(oracle):
+    """testFooNoGo0 (TestAdaptorSimplified.hs:1747-1752, eps 1e-6)."""
+    _, (g,) = ad.grad(oracle, lambda T, t: T.ssum0(P.fooNoGo(T, t)), [oracle.sconcrete(P.FOONOGO_IN)])
+    np.testing.assert_allclose(oracle.to_numpy(g), P.FOONOGO_GRAD, atol=1e-6, rtol=0)
+
