@@ -446,3 +446,17 @@ def test_foo_no_go_known_answer(oracle):
     _, (g,) = ad.grad(oracle, lambda T, t: T.ssum0(P.fooNoGo(T, t)), [oracle.sconcrete(P.FOONOGO_IN)])
     np.testing.assert_allclose(oracle.to_numpy(g), P.FOONOGO_GRAD, atol=1e-6, rtol=0)
 
+
+def test_foo_float_rank5_known_answer(oracle):
+    """testFoo (TestHighRankSimplified.hs:102-106): grad (rsum0 @5 @Float . foo) (t16, t16, t16) in single precision,
+    eps 1e-3 as in the reference."""
+    exp = [[-4.6947093,1.5697206,-1.6332961,0.34882763,1.5697206,-1.0,-0.9784988,-0.9158946,6.6326222,3.6699238,7.85237,-2.9069107,17.976654,0.3914159,32.98194,19.807974],
+           [6.943779,-1.436789,33.67549,0.22397964,-1.436789,-1.0,-0.975235,-0.90365005,147.06645,-73.022705,-9.238474,-10.042692,-980.2843,-7.900571,-14.451739,436.9084],
+           [-4.8945336,2.067469,-1.7196897,1.3341143,2.067469,1.0,0.99846554,0.99536234,6.6943173,3.7482092,7.977362,-3.1475093,18.000969,0.48736274,33.01224,19.845064]]
+    t16 = P.T16.astype(np.float32)
+    _, grads = ad.grad(oracle, lambda T, x, y, z: T.ssum0(P._foo(T, x, y, z)), [oracle.sconcrete(t16)] * 3)
+    for g, e in zip(grads, exp):
+        got = oracle.to_numpy(g)
+        assert got.dtype == np.float32
+        np.testing.assert_allclose(got.reshape(-1), np.array(e, np.float32), atol=1e-3, rtol=1e-5)
+
