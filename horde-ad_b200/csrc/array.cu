@@ -13,6 +13,18 @@
 
 hb_global g_hb;
 
+static std::recursive_mutex g_entry_mu;
+static thread_local int tl_bound_device = -1;
+
+hb_entry_guard::hb_entry_guard() {
+  g_entry_mu.lock();
+  if (tl_bound_device != g_hb.device && g_hb.device >= 0) {
+    cudaSetDevice(g_hb.device);  // thread-local in the runtime: cheap, and required for cuLaunchKernel / cudaMalloc
+    tl_bound_device = g_hb.device;
+  }
+}
+hb_entry_guard::~hb_entry_guard() { g_entry_mu.unlock(); }
+
 static thread_local char tl_error[512] = "";
 
 void hb_set_error(const char *fmt, ...) {
@@ -113,6 +125,9 @@ int hb_alloc_storage(size_t bytes, hb_storage **out) {
   return HB_OK;
 }
 
+// pools of graphs that have been freed: their blocks belong to the general pool again
+static std::vector<int> g_retired_pools;
+
 void hb_storage_release(hb_storage *st) {
   if (!st) return;
   if (st->rc.fetch_sub(1) == 1) {
@@ -122,7 +137,10 @@ void hb_storage_release(hb_storage *st) {
       // single library stream before this point, and every later producer is
       // enqueued after it, so the block can be recycled immediately.
       std::lock_guard<std::mutex> lk(g_alloc_mu);
-      g_pools[st->pool].insert({st->bytes, st->ptr});
+      int pool = st->pool;
+      if (pool != 0 && std::find(g_retired_pools.begin(), g_retired_pools.end(), pool) != g_retired_pools.end())
+        pool = 0;  // the graph that owned this block is gone: nothing replays into it any more
+      g_pools[pool].insert({st->bytes, st->ptr});
     }
     delete st;
   }
@@ -850,6 +868,7 @@ extern "C" int hb_graph_free(hb_graph *g) {
       for (auto &kv : it->second) g_pools[0].insert(kv);
       g_pools.erase(it);
     }
+    g_retired_pools.push_back(g->pool);
   }
   delete g;
   return HB_OK;

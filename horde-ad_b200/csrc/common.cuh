@@ -79,7 +79,22 @@ void hb_set_error(const char *fmt, ...);
     int s_ = (call);            \
     if (s_ != HB_OK) return s_; \
   } while (0)
-#define HB_CHECK_INIT() HB_REQUIRE(g_hb.inited, "hb_init has not been called")
+// Re-entrancy (GHC -threaded, up to -N8 capabilities, finalisers on arbitrary OS threads): every
+// compute entry point runs under ONE process-wide recursive lock (entry points nest) and binds the library's device
+// to the calling OS thread on first use -- the single stream, the reduction/scatter scratch, the profiler and the
+// capture state are therefore only ever touched by one thread at a time, and a foreign thread on rank/device k > 0
+// allocates and launches on device k, not on device 0.  hb_release/hb_retain and the metadata/view calls take no
+// lock (atomics + the allocator's own mutex).
+struct hb_entry_guard {
+  hb_entry_guard();
+  ~hb_entry_guard();
+};
+#define HB_CAT2_(a, b) a##b
+#define HB_CAT_(a, b) HB_CAT2_(a, b)
+#define HB_ENTRY_LOCK() hb_entry_guard HB_CAT_(hb_guard_, __LINE__)
+#define HB_CHECK_INIT()                                        \
+  HB_REQUIRE(g_hb.inited, "hb_init has not been called");      \
+  HB_ENTRY_LOCK()
 
 // per-launch profiler (array.cu): an event after every launch while enabled
 void hb_prof_mark(const char *func, int line);

@@ -589,6 +589,11 @@ extern "C" int hb_mnist_batch_into(const hb_array *pixels, const hb_array *label
                "mnist_batch: order must be a contiguous I32 or I64 vector");
     HB_REQUIRE(start + batch <= order->shape[0], "mnist_batch: batch [%lld, %lld) beyond the order vector (%lld)",
                (long long)start, (long long)(start + batch), (long long)order->shape[0]);
+  } else {
+    // file order: a batch that runs past the data would silently train on all-zero glyphs (the reference's
+    // chunksOf just hands out a short last batch, MnistData.hs:134-171) -- refuse it instead
+    HB_REQUIRE(start + batch <= n, "mnist_batch: batch [%lld, %lld) beyond the %lld samples", (long long)start,
+               (long long)(start + batch), (long long)n);
   }
   if (batch == 0 || (hw == 0 && classes == 0)) return HB_OK;
   const uint8_t *pp = (const uint8_t *)hb_data(pixels), *lp = (const uint8_t *)hb_data(labels);

@@ -22,6 +22,51 @@ from .device import DeviceArray, DeviceBackend
 from .ffi import call
 
 
+def shard_range(rank: int, world: int, batch: int) -> tuple[int, int]:
+    """Rank r owns samples [r*B/G, (r+1)*B/G); the batch must split evenly
+    (the loss is a mean over the shard, so unequal shards would bias it)."""
+    if batch % world != 0:
+        raise ValueError(f"batch {batch} does not split evenly over {world} ranks")
+    per = batch // world
+    return rank * per, (rank + 1) * per
+
+
+def exchange_scale(world: int) -> float:
+    """Factor applied to the all-reduce SUM: the mean of per-shard mean losses / gradients equals the global
+    mean for equal shards (MnistCnnShaped2.hs:136)."""
+    return 1.0 / world
+
+
+class BucketLayout:
+    """Offsets of the gradient leaves of the TKProduct (MnistCnnShaped2.hs:30-40, in parameter order) inside
+    the one flat bucket that is exchanged; one extra trailing slot carries the loss.  The same object lays out
+    the flat parameter / Adam-moment buffers of `CnnTrainer` (its leaves are views at these offsets), and the
+    world_size-2 gloo test drives it on the CPU."""
+
+    def __init__(self, shapes):
+        self.shapes = [tuple(s) for s in shapes]
+        self.sizes = [int(np.prod(s)) if len(s) else 1 for s in self.shapes]
+        self.offsets = [0]
+        for n in self.sizes:
+            self.offsets.append(self.offsets[-1] + n)
+        self.n_params = self.offsets[-1]
+        self.n_total = self.n_params + 1
+
+    def flatten(self, leaves, loss: float) -> np.ndarray:
+        assert len(leaves) == len(self.shapes)
+        out = np.empty(self.n_total, dtype=np.asarray(leaves[0]).dtype)
+        for leaf, off, n, sh in zip(leaves, self.offsets, self.sizes, self.shapes):
+            leaf = np.asarray(leaf)
+            assert tuple(leaf.shape) == sh, (leaf.shape, sh)
+            out[off:off + n] = leaf.reshape(-1)
+        out[self.n_params] = loss
+        return out
+
+    def unflatten(self, bucket: np.ndarray):
+        leaves = [bucket[o:o + n].reshape(sh) for o, n, sh in zip(self.offsets, self.sizes, self.shapes)]
+        return leaves, float(bucket[self.n_params])
+
+
 class PinnedBuffer:
     """Pinned host staging memory exposed as a numpy array."""
 
@@ -57,10 +102,9 @@ class CnnTrainer:
         self.optimizer, self.gamma = optimizer, gamma
         self.hyper = (kh, kw, c_out, n_hidden)
         host_params = mnist_cnn.init_params(kh, kw, c_out, n_hidden, seed=seed, dtype=dtype)
-        self.shapes = [p.shape for p in host_params]
-        self.sizes = [int(p.size) for p in host_params]
-        self.n_params = sum(self.sizes)
-        flat = np.concatenate([p.reshape(-1) for p in host_params])
+        self.layout = BucketLayout([p.shape for p in host_params])
+        self.shapes, self.sizes, self.n_params = self.layout.shapes, self.layout.sizes, self.layout.n_params
+        flat = self.layout.flatten(host_params, 0.0)[:self.n_params]
         self.flat_p = dev.sconcrete(flat)
         self.flat_m = dev.sconcrete(np.zeros_like(flat))
         self.flat_v = dev.sconcrete(np.zeros_like(flat))
@@ -80,11 +124,8 @@ class CnnTrainer:
         self._stage_g = self._stage_l = None
 
     def _leaves(self, flat: DeviceArray):
-        out, pos = [], 0
-        for sh, n in zip(self.shapes, self.sizes):
-            out.append(self.dev.sreshape(list(sh), self.dev.sslice(pos, n, flat)))
-            pos += n
-        return out
+        return [self.dev.sreshape(list(sh), self.dev.sslice(off, n, flat))
+                for sh, n, off in zip(self.layout.shapes, self.layout.sizes, self.layout.offsets)]
 
     # ---- one step, enqueued op by op -------------------------------------
     def _gradient_program(self):
@@ -93,7 +134,7 @@ class CnnTrainer:
             dev, lambda T, *ps: mnist_cnn.convMnistLossFusedS(T, self.glyphs, self.labels, list(ps), fused=True),
             self.params)
         bucket = dev.flatten_concat(list(grads) + [loss])
-        call("hb_allreduce_sum", bucket.h, 1.0 / self.world)
+        call("hb_allreduce_sum", bucket.h, exchange_scale(self.world))
         return bucket
 
     def _apply(self, bucket):

@@ -1,5 +1,6 @@
 """The N>1 path on CPU: world_size-2 gloo processes run the host-side data-
-parallel logic (shard ranges, bucket layout, sum + 1/world exchange) with the
+parallel logic of horde-ad_b200/train.py -- the very objects `CnnTrainer` lays its
+flat parameter / bucket buffers out with (shard ranges, bucket layout, sum + 1/world exchange) -- with the
 oracle computing each shard's gradient; the exchanged bucket must equal the
 serial mean of the shard buckets."""
 import os
@@ -20,7 +21,7 @@ def _free_port():
 def _worker(rank, world, port, batch, q):
     import torch
     import torch.distributed as dist
-    from horde_ad_b200 import ad, dp, mnist_cnn
+    from horde_ad_b200 import ad, mnist_cnn, train as dp
     from oracle.concrete import ConcreteBackend
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -71,7 +72,7 @@ def test_sharded_gradient_exchange_gloo_world2():
 
 
 def test_exchange_is_mean_of_shard_buckets():
-    from horde_ad_b200 import dp
+    from horde_ad_b200 import train as dp
     lay = dp.BucketLayout([(2, 3), (4,), ()])
     assert lay.n_params == 11 and lay.n_total == 12 and lay.offsets == [0, 6, 10, 11]
     rng = np.random.default_rng(0)

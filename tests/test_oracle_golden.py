@@ -58,7 +58,7 @@ def test_list_prod_gradient(oracle):
     # testListProd (TestAdaptorSimplified.hs:1043-1053): grad of the product of [1,2,3,4]
     x = oracle.sconcrete(np.array([1.0, 2.0, 3.0, 4.0]))
     val, (g,) = ad.grad(oracle, lambda T, t: T.prod_fold(t), [x])
-    assert float(val) == 24.0
+    assert float(oracle.to_numpy(val)) == 24.0
     np.testing.assert_allclose(oracle.to_numpy(g), [24, 12, 8, 6], atol=1e-10)
 
 
@@ -124,7 +124,7 @@ def test_fold_goldens(oracle):
     ]
     for f, expected in cases:
         _, (g,) = ad.grad(o, f, [x0])
-        np.testing.assert_allclose(float(np.asarray(g)), expected, atol=1e-10, rtol=0)
+        np.testing.assert_allclose(float(o.to_numpy(g)), expected, atol=1e-10, rtol=0)
 
     # testSin0FoldNestedS1 (TestRevFwdFold.hs:2316-2326): a fold whose step is a fold; the reference's eps
     # is 1e-10 absolute, far above the value itself, so the known answer is also checked relatively
@@ -133,8 +133,8 @@ def test_fold_goldens(oracle):
                                       a, T.sreplicate(7, x))
         return nn.sfold(T, inner, a0, T.sreplicate(3, a0))
     _, (g,) = ad.grad(o, nested, [x0])
-    np.testing.assert_allclose(float(np.asarray(g)), 2.0504979297616553e-43, atol=1e-10, rtol=0)
-    np.testing.assert_allclose(float(np.asarray(g)), 2.0504979297616553e-43, rtol=1e-12)
+    np.testing.assert_allclose(float(o.to_numpy(g)), 2.0504979297616553e-43, atol=1e-10, rtol=0)
+    np.testing.assert_allclose(float(o.to_numpy(g)), 2.0504979297616553e-43, rtol=1e-12)
 
     # testSin0Fold6 (= 6) and testSin0Fold7 (= 250): tensor-valued accumulators
     def fold6(T, a0):
@@ -148,7 +148,7 @@ def test_fold_goldens(oracle):
         return T.ssum0(nn.sfold(T, step, acc0, T.sreplicate(2, a0)))
     for f, expected in ((fold6, 6.0), (fold7, 250.0)):
         _, (g,) = ad.grad(o, f, [x0])
-        np.testing.assert_allclose(float(np.asarray(g)), expected, atol=1e-10, rtol=0)
+        np.testing.assert_allclose(float(o.to_numpy(g)), expected, atol=1e-10, rtol=0)
 
 
 def test_fcnn_and_rnn_gradients_match_finite_differences(oracle):
@@ -438,7 +438,7 @@ def test_fold_goldens_with_tensor_steps(oracle):
         return T.ssum0(nn.sfold(T, step, acc0, T.sreplicate(3, a0)))
     for f, expected in ((fold5, 1.2992412552109085), (fold8, -2.200311410593445)):
         _, (g,) = ad.grad(o, f, [o.sscalar(1.1)])
-        np.testing.assert_allclose(float(np.asarray(g)), expected, atol=1e-10, rtol=0)
+        np.testing.assert_allclose(float(o.to_numpy(g)), expected, atol=1e-10, rtol=0)
 
 
 def test_foo_no_go_known_answer(oracle):
