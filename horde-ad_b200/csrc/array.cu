@@ -82,6 +82,15 @@ int hb_alloc_storage(size_t bytes, hb_storage **out) {
   size_t sz = size_class(bytes);
   void *p = nullptr;
   int pool;
+  if (g_hb.trace_only) {  // no device: constants live in host memory (hb_init_trace_only)
+    hb_storage *st = new hb_storage;
+    st->ptr = calloc(1, sz);
+    st->bytes = sz;
+    st->pool = HB_POOL_HOST;
+    st->rc.store(1);
+    *out = st;
+    return HB_OK;
+  }
   {
     std::lock_guard<std::mutex> lk(g_alloc_mu);
     pool = g_capture_pool;
@@ -131,6 +140,16 @@ static std::vector<int> g_retired_pools;
 void hb_storage_release(hb_storage *st) {
   if (!st) return;
   if (st->rc.fetch_sub(1) == 1) {
+    if (st->pool == HB_POOL_VIRTUAL) {  // output block of a lazy node: drop whatever it currently stands for
+      if (st->bound) hb_storage_release(st->bound);
+      delete st;
+      return;
+    }
+    if (st->pool == HB_POOL_HOST) {
+      free(st->ptr);
+      delete st;
+      return;
+    }
     g_hb.live_bytes -= st->bytes;
     {
       // Stream-ordered reuse: every consumer of the block was enqueued on the
@@ -167,6 +186,7 @@ int hb_scratch(size_t bytes, void **ptr) {
 // --------------------------------------------------------------- lifecycle
 extern "C" int hb_init(int device) {
   if (g_hb.inited) {
+    HB_REQUIRE(!g_hb.trace_only, "hb_init: the library was initialised with hb_init_trace_only (no device)");
     HB_REQUIRE(g_hb.device == device, "hb_init: already initialised on device %d", g_hb.device);
     return HB_OK;
   }
@@ -197,6 +217,12 @@ extern "C" int hb_init(int device) {
 
 extern "C" int hb_shutdown(void) {
   if (!g_hb.inited) return HB_OK;
+  if (g_hb.trace_only) {
+    g_hb.inited = false;
+    g_hb.trace_only = false;
+    g_hb.device = 0;
+    return HB_OK;
+  }
   cudaStreamSynchronize(g_hb.stream);
   {
     std::lock_guard<std::mutex> lk(g_alloc_mu);
@@ -379,7 +405,7 @@ extern "C" int hb_release(hb_array *a) {
 
 // ------------------------------------------------------------ construction
 int hb_new_array(hb_dtype dt, int rank, const int64_t *shape, hb_array **out) {
-  HB_CHECK_INIT();
+  HB_CHECK_INIT_LAZY();
   HB_REQUIRE(rank >= 0 && rank <= HB_R, "rank %d out of range (max %d)", rank, HB_R);
   HB_REQUIRE((int)dt >= 0 && (int)dt <= HB_BOOL, "bad dtype %d", (int)dt);
   hb_array *a = new hb_array;
@@ -436,11 +462,22 @@ int hb_zeros(hb_dtype dt, int rank, const int64_t *shape, hb_array **out) {
 // ---------------------------------------------------------------- transfer
 extern "C" int hb_from_host(hb_dtype dt, int rank, const int64_t *shape, const void *host,
                             hb_array **out) {
-  HB_CHECK_INIT();
+  HB_CHECK_INIT_LAZY();   // constants are created eagerly even while a lazy program is being recorded
   HB_REQUIRE(out, "null out");
   hb_array *a;
   HB_TRY(hb_new_array(dt, rank, shape, &a));
   int64_t n = hb_numel(a);
+  if (n > 0 && host && (size_t)n * hb_dtype_size(dt) <= 4096) {
+    // small constants (index tables, [0.0,1.0]) keep a host image for the contraction pass
+    const uint8_t *hp = (const uint8_t *)host;
+    a->st->host = std::make_shared<std::vector<uint8_t>>(hp, hp + (size_t)n * hb_dtype_size(dt));
+  }
+  if (n > 0 && g_hb.trace_only) {
+    HB_REQUIRE(host, "null host pointer");
+    memcpy(hb_data(a), host, (size_t)n * hb_dtype_size(dt));
+    *out = a;
+    return HB_OK;
+  }
   if (n > 0) {
     HB_REQUIRE(host, "null host pointer");
     cudaError_t e = cudaMemcpyAsync(hb_data(a), host, (size_t)n * hb_dtype_size(dt),
@@ -514,11 +551,19 @@ extern "C" int hb_prefetch_consumed(void) {
 }
 
 extern "C" int hb_to_host(const hb_array *a, void *host) {
-  HB_CHECK_INIT();
+  HB_CHECK_INIT_LAZY();
   HB_REQUIRE(a, "null array");
   int64_t n = hb_numel(a);
   if (n == 0) return HB_OK;
   HB_REQUIRE(host, "null host pointer");
+  HB_REQUIRE(hb_data(a), "hb_to_host: the array is a lazy value that has not been computed (only the outputs of a lazy "
+                         "program hold values, after hb_lazy_run)");
+  if (g_hb.trace_only) {
+    HB_REQUIRE(hb_contig(a), "hb_to_host: trace-only mode can only read back contiguous constants");
+    memcpy(host, hb_data(a), (size_t)n * hb_dtype_size(a->dt));
+    return HB_OK;
+  }
+  HB_REQUIRE(!hb_lazy_on() || hb_contig(a), "hb_to_host: a strided view cannot be materialised while recording");
   const hb_array *src = a;
   hb_array *tmp = nullptr;
   if (!hb_contig(a)) {
@@ -534,10 +579,15 @@ extern "C" int hb_to_host(const hb_array *a, void *host) {
 }
 
 extern "C" int hb_scalar_to_host(const hb_array *a, void *value) {
-  HB_CHECK_INIT();
+  HB_CHECK_INIT_LAZY();
   HB_REQUIRE(a && value, "null argument");
   HB_REQUIRE(hb_numel(a) == 1, "hb_scalar_to_host: array %s has %lld elements",
              hb_shape_str(a).c_str(), (long long)hb_numel(a));
+  HB_REQUIRE(hb_data(a), "hb_scalar_to_host: the array is a lazy value that has not been computed");
+  if (g_hb.trace_only) {
+    memcpy(value, hb_data(a), hb_dtype_size(a->dt));
+    return HB_OK;
+  }
   HB_CUDA(cudaMemcpyAsync(value, hb_data(a), hb_dtype_size(a->dt), cudaMemcpyDeviceToHost,
                           g_hb.stream));
   HB_CUDA(cudaStreamSynchronize(g_hb.stream));
@@ -546,14 +596,17 @@ extern "C" int hb_scalar_to_host(const hb_array *a, void *value) {
 
 extern "C" int hb_full(hb_dtype dt, int rank, const int64_t *shape, const void *value,
                        hb_array **out) {
-  HB_CHECK_INIT();
+  HB_CHECK_INIT_LAZY();
   HB_REQUIRE(value && out, "null argument");
   HB_REQUIRE(rank >= 0 && rank <= HB_R, "rank %d out of range", rank);
   int64_t one = 1;
   hb_array *s;
   HB_TRY(hb_new_array(dt, 0, &one, &s));
+  s->st->host = std::make_shared<std::vector<uint8_t>>((const uint8_t *)value, (const uint8_t *)value + hb_dtype_size(dt));
   // the value travels as a kernel parameter (safe under graph capture)
-  int st = hb_fill_scalar(hb_data(s), dt, value);
+  int st = HB_OK;
+  if (g_hb.trace_only) memcpy(hb_data(s), value, hb_dtype_size(dt));
+  else st = hb_fill_scalar(hb_data(s), dt, value);
   if (st != HB_OK) {
     hb_release(s);
     return st;
@@ -568,11 +621,19 @@ extern "C" int hb_full(hb_dtype dt, int rank, const int64_t *shape, const void *
 }
 
 extern "C" int hb_host_alloc(size_t bytes, void **ptr) {
-  HB_CHECK_INIT();
+  HB_CHECK_INIT_LAZY();
+  if (g_hb.trace_only) {
+    *ptr = calloc(1, bytes ? bytes : 1);
+    return HB_OK;
+  }
   HB_CUDA(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault));
   return HB_OK;
 }
 extern "C" int hb_host_free(void *ptr) {
+  if (ptr && g_hb.trace_only) {
+    free(ptr);
+    return HB_OK;
+  }
   if (ptr) HB_CUDA(cudaFreeHost(ptr));
   return HB_OK;
 }

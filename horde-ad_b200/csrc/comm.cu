@@ -10,6 +10,7 @@
 #include <dlfcn.h>
 
 #include "common.cuh"
+#include "lazy.cuh"
 
 typedef struct ncclComm *ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
@@ -82,10 +83,13 @@ __global__ void hb_scale_kernel(T *p, T s, int64_t n) {
 
 extern "C" int hb_allreduce_sum(hb_array *bucket, double scale) {
   hb_prof_scope prof_("allreduce_sum", bucket);
-  HB_CHECK_INIT();
+  HB_CHECK_INIT_LAZY();
   HB_REQUIRE(bucket, "null argument");
   HB_REQUIRE(hb_contig(bucket), "allreduce: bucket must be contiguous");
   HB_REQUIRE(hb_is_float(bucket->dt), "allreduce: floating bucket required");
+  if (hb_lazy_on())
+    return hb_lrec(HB_L_EFFECT, "allreduce_sum").in(bucket).farg(0, scale).commit(
+        [=](hb_lnode &n, hb_array *const *in, hb_array **o) { return hb_allreduce_sum(in[0], n.fa[0]); });
   int64_t n = hb_numel(bucket);
   if (n == 0) return HB_OK;
   if (g_nccl.world > 1) {

@@ -9,6 +9,7 @@
 #include <string.h>
 
 #include <atomic>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -21,9 +22,20 @@
 struct hb_storage {
   void *ptr;
   size_t bytes;      // size-class size handed out by the allocator
-  int pool;          // allocator pool the block returns to (0 = general)
+  int pool;          // allocator pool the block returns to (0 = general; HB_POOL_VIRTUAL / HB_POOL_HOST below)
   std::atomic<int> rc;
+  // lazy programs (lazy.cuh): a VIRTUAL block has no memory of its own; `producer` is the recorded node whose
+  // out_idx-th output it is, and while the program runs `bound` is the real block it currently stands for
+  // (ptr mirrors bound's address).
+  void *producer = nullptr;
+  int out_idx = 0;
+  hb_storage *bound = nullptr;
+  // host image of small constant arrays (index tables, the [0.0, 1.0] relu table): what the rewriter reads to
+  // recognise affine window tables without a device round trip
+  std::shared_ptr<std::vector<uint8_t>> host;
 };
+#define HB_POOL_VIRTUAL (-1)
+#define HB_POOL_HOST (-2)   // trace-only mode (no device): plain host memory
 
 struct hb_array {
   std::atomic<int> rc;
@@ -52,6 +64,9 @@ struct hb_global {
   // DMMA convolutions leave out the taps that fall entirely into the zero padding
   // (HB_CONV_FULL_PADDING=1 computes them: only differs for non-finite operands, 0 * Inf)
   bool conv_skip_padding = true;
+  // hb_init_trace_only: no device at all; constants live in host memory and every compute entry point must be
+  // recorded (hb_lazy_begin) -- lets the contraction pass be exercised on a box without a GPU
+  bool trace_only = false;
   cudaEvent_t events[64] = {};
 };
 extern hb_global g_hb;
@@ -92,9 +107,18 @@ struct hb_entry_guard {
 #define HB_CAT2_(a, b) a##b
 #define HB_CAT_(a, b) HB_CAT2_(a, b)
 #define HB_ENTRY_LOCK() hb_entry_guard HB_CAT_(hb_guard_, __LINE__)
-#define HB_CHECK_INIT()                                        \
+bool hb_lazy_on();  // lazy.cu: a program is being recorded (and recording is not suspended by a replay)
+// entry points that can be RECORDED (they branch on hb_lazy_on() themselves) and the constant constructors
+#define HB_CHECK_INIT_LAZY()                                   \
   HB_REQUIRE(g_hb.inited, "hb_init has not been called");      \
   HB_ENTRY_LOCK()
+// every other entry point: eager only -- refused while a lazy program is being recorded (its result would not be
+// part of the program) and in trace-only mode (there is no device to run it on)
+#define HB_CHECK_INIT()                                                                                         \
+  HB_CHECK_INIT_LAZY();                                                                                         \
+  HB_REQUIRE(!hb_lazy_on(), "%s: this entry point cannot be recorded into a lazy program (hb_lazy_begin is active)", \
+             __func__);                                                                                         \
+  HB_REQUIRE(!g_hb.trace_only, "%s: trace-only mode has no device to run on", __func__)
 
 // per-launch profiler (array.cu): an event after every launch while enabled
 void hb_prof_mark(const char *func, int line);

@@ -17,6 +17,7 @@
 // has no FP64 kind) for doubles, FFMA register tiles for floats.  Tensor-pipe
 // roofline: 2*M*N*K flops against the measured FP64 peak (hb_microbench).
 #include "common.cuh"
+#include "lazy.cuh"
 
 #define TM 64
 #define TN 64
@@ -262,12 +263,16 @@ int hb_reduce_generic(const hb_array *a, const hb_array *b, int nk, const int *k
 // may accumulate into (C += A x B); *acc_used reports whether it did (then *out = acc, retained).
 static int contract_impl(const hb_array *a, const hb_array *b, int n_lead, hb_array **out, hb_array *acc = nullptr,
                          int *acc_used = nullptr) {
-  HB_CHECK_INIT();
+  HB_CHECK_INIT_LAZY();
   HB_REQUIRE(a && b && out, "null argument");
   HB_REQUIRE(a->dt == b->dt && hb_same_shape(a, b), "sdot1In: %s %s vs %s %s", hb_dtype_name(a->dt),
              hb_shape_str(a).c_str(), hb_dtype_name(b->dt), hb_shape_str(b).c_str());
   HB_REQUIRE(a->rank >= 1 && n_lead >= 0 && n_lead <= a->rank - 1, "sdot1In: bad rank");
   HB_REQUIRE(a->dt != HB_BOOL, "sdot1In: numeric dtype required");
+  if (hb_lazy_on() && !acc)
+    return hb_lrec(HB_L_DOT_INNER, n_lead ? "dot_inner_sum_leading" : "dot_inner").in(a).in(b).iarg(0, n_lead)
+        .out(out, a->dt, a->rank - 1 - n_lead, a->shape + n_lead).commit(
+        [=](hb_lnode &n, hb_array *const *in, hb_array **o) { return contract_impl(in[0], in[1], (int)n.ia[0], &o[0]); });
   int r = a->rank;
   hb_array *o;
   HB_TRY(hb_new_array(a->dt, r - 1 - n_lead, a->shape + n_lead, &o));
@@ -388,6 +393,13 @@ extern "C" int hb_matmul2(const hb_array *a, const hb_array *b, hb_array **out) 
   HB_REQUIRE(a && b && out, "null argument");
   HB_REQUIRE(a->rank == 2 && b->rank == 2 && a->shape[1] == b->shape[0], "smatmul2: %s x %s",
              hb_shape_str(a).c_str(), hb_shape_str(b).c_str());
+  HB_CHECK_INIT_LAZY();
+  if (hb_lazy_on()) {
+    HB_REQUIRE(a->dt == b->dt, "smatmul2: dtype mismatch");
+    int64_t sh_[2] = {a->shape[0], b->shape[1]};
+    return hb_lrec(HB_L_MATMUL2, "matmul2").in(a).in(b).out(out, a->dt, 2, sh_).commit(
+        [=](hb_lnode &n, hb_array *const *in, hb_array **o) { return hb_matmul2(in[0], in[1], &o[0]); });
+  }
   hb_array *av = hb_new_view(a), *bv = hb_new_view(b);
   // av[m, p, n] = a[m, n] ; bv[m, p, n] = b[n, p]
   av->rank = bv->rank = 3;
@@ -415,6 +427,10 @@ extern "C" int hb_matmul2_acc(hb_array *acc, const hb_array *a, const hb_array *
   HB_REQUIRE(acc->rank == 2 && acc->shape[0] == a->shape[0] && acc->shape[1] == b->shape[1] && acc->dt == a->dt,
              "matmul2_acc: accumulator %s %s does not match the product", hb_dtype_name(acc->dt),
              hb_shape_str(acc).c_str());
+  HB_CHECK_INIT_LAZY();
+  if (hb_lazy_on())
+    return hb_lrec(HB_L_GENERIC, "matmul2_acc").in(acc).in(a).in(b).out(out, acc->dt, 2, acc->shape).commit(
+        [=](hb_lnode &n, hb_array *const *in, hb_array **o) { return hb_matmul2_acc(in[0], in[1], in[2], &o[0]); });
   const bool unique = acc->dt == HB_F64 && acc->rc.load() == 1 && acc->st && acc->st->rc.load() == 1 &&
                       hb_contig(acc) && acc->st != a->st && acc->st != b->st;
   hb_array *av = hb_new_view(a), *bv = hb_new_view(b);
@@ -473,10 +489,15 @@ bool acc_unique(const hb_array *acc, const hb_array *a, const hb_array *b) {
 extern "C" int hb_matmul2_sum(const hb_array *a1, const hb_array *b1, const hb_array *a2, const hb_array *b2,
                               hb_array **out) {
   hb_prof_scope prof_("matmul2_sum", a1, b1);
-  HB_CHECK_INIT();
+  HB_CHECK_INIT_LAZY();
   HB_REQUIRE(a1 && b1 && a2 && b2 && out, "null argument");
   HB_REQUIRE(pair_shapes_ok(a1, b1, a2, b2), "smatmul2 + smatmul2: %s x %s + %s x %s", hb_shape_str(a1).c_str(),
              hb_shape_str(b1).c_str(), hb_shape_str(a2).c_str(), hb_shape_str(b2).c_str());
+  if (hb_lazy_on()) {
+    int64_t sh_[2] = {a1->shape[0], b1->shape[1]};
+    return hb_lrec(HB_L_GENERIC, "matmul2_sum").in(a1).in(b1).in(a2).in(b2).out(out, a1->dt, 2, sh_).commit(
+        [=](hb_lnode &n, hb_array *const *in, hb_array **o) { return hb_matmul2_sum(in[0], in[1], in[2], in[3], &o[0]); });
+  }
   Op2 A1, B1, A2, B2;
   hb_array *tmp[4] = {nullptr, nullptr, nullptr, nullptr};
   auto drop = [&]() { for (hb_array *t : tmp) hb_release(t); };
@@ -505,12 +526,17 @@ extern "C" int hb_matmul2_sum(const hb_array *a1, const hb_array *b1, const hb_a
 extern "C" int hb_matmul2_pair(const hb_array *a1, const hb_array *b1, const hb_array *a2, const hb_array *b2,
                                hb_array **out1, hb_array **out2) {
   hb_prof_scope prof_("matmul2_pair", a1, b1);
-  HB_CHECK_INIT();
+  HB_CHECK_INIT_LAZY();
   HB_REQUIRE(a1 && b1 && a2 && b2 && out1 && out2, "null argument");
   HB_REQUIRE(a1->rank == 2 && b1->rank == 2 && a2->rank == 2 && b2->rank == 2 && a1->shape[1] == b1->shape[0] &&
                  a2->shape[1] == b2->shape[0],
              "smatmul2 pair: %s x %s, %s x %s", hb_shape_str(a1).c_str(), hb_shape_str(b1).c_str(),
              hb_shape_str(a2).c_str(), hb_shape_str(b2).c_str());
+  if (hb_lazy_on()) {
+    int64_t s1_[2] = {a1->shape[0], b1->shape[1]}, s2_[2] = {a2->shape[0], b2->shape[1]};
+    return hb_lrec(HB_L_GENERIC, "matmul2_pair").in(a1).in(b1).in(a2).in(b2).out(out1, a1->dt, 2, s1_).out(out2, a2->dt, 2, s2_)
+        .commit([=](hb_lnode &n, hb_array *const *in, hb_array **o) { return hb_matmul2_pair(in[0], in[1], in[2], in[3], &o[0], &o[1]); });
+  }
   Op2 A1, B1, A2, B2;
   if (pair_shapes_ok(a1, b1, a2, b2) && op2(a1, &A1) && op2(b1, &B1) && op2(a2, &A2) && op2(b2, &B2)) {
     int64_t sh[2] = {a1->shape[0], b1->shape[1]};
@@ -535,8 +561,12 @@ extern "C" int hb_matmul2_pair(const hb_array *a1, const hb_array *b1, const hb_
 extern "C" int hb_matmul2_acc_pair(hb_array *acc1, const hb_array *a1, const hb_array *b1, hb_array *acc2,
                                    const hb_array *a2, const hb_array *b2, hb_array **out1, hb_array **out2) {
   hb_prof_scope prof_("matmul2_acc_pair", a1, b1);
-  HB_CHECK_INIT();
+  HB_CHECK_INIT_LAZY();
   HB_REQUIRE(acc1 && acc2 && a1 && b1 && a2 && b2 && out1 && out2, "null argument");
+  if (hb_lazy_on())
+    return hb_lrec(HB_L_GENERIC, "matmul2_acc_pair").in(acc1).in(a1).in(b1).in(acc2).in(a2).in(b2)
+        .out(out1, acc1->dt, acc1->rank, acc1->shape).out(out2, acc2->dt, acc2->rank, acc2->shape)
+        .commit([=](hb_lnode &n, hb_array *const *in, hb_array **o) { return hb_matmul2_acc_pair(in[0], in[1], in[2], in[3], in[4], in[5], &o[0], &o[1]); });
   Op2 A1, B1, A2, B2;
   if (a1->rank == 2 && b1->rank == 2 && a2->rank == 2 && b2->rank == 2 && pair_shapes_ok(a1, b1, a2, b2) &&
       acc1->rank == 2 && acc2->rank == 2 && acc1->shape[0] == a1->shape[0] && acc1->shape[1] == b1->shape[1] &&
@@ -567,6 +597,10 @@ extern "C" int hb_matvecmul(const hb_array *m, const hb_array *v, hb_array **out
   HB_REQUIRE(m && v && out, "null argument");
   HB_REQUIRE(m->rank == 2 && v->rank == 1 && m->shape[1] == v->shape[0], "smatvecmul: %s x %s",
              hb_shape_str(m).c_str(), hb_shape_str(v).c_str());
+  HB_CHECK_INIT_LAZY();
+  if (hb_lazy_on())
+    return hb_lrec(HB_L_GENERIC, "matvecmul").in(m).in(v).out(out, m->dt, 1, m->shape).commit(
+        [=](hb_lnode &n, hb_array *const *in, hb_array **o) { return hb_matvecmul(in[0], in[1], &o[0]); });
   hb_array *vv = hb_new_view(v);
   vv->rank = 2;
   vv->shape[0] = m->shape[0]; vv->strides[0] = 0;

@@ -16,6 +16,7 @@
 // Algorithmic bytes per pass at ConvVjpBench: 205.8 MB,
 // 14.80 GFLOP -> FP64 tensor pipe bound.
 #include "common.cuh"
+#include "lazy.cuh"
 
 int hb_copy_into(hb_array *dst, const hb_array *src);  // elementwise.cu
 // conv_dmma.cu: shared-memory-staged DMMA kernels (contiguous f64 operands)
@@ -87,7 +88,7 @@ static hb_array *view6(const hb_array *base, int64_t off, const int64_t *shape, 
 
 extern "C" int hb_conv2d_preserving(const hb_array *K, const hb_array *A, hb_array **out) {
   hb_prof_scope prof_("conv2d_preserving", K, A);
-  HB_CHECK_INIT();
+  HB_CHECK_INIT_LAZY();
   HB_REQUIRE(K && A && out, "null argument");
   HB_REQUIRE(K->rank == 4 && A->rank == 4 && K->dt == A->dt && hb_is_float(A->dt),
              "conv2dPreserving: rank-4 floating operands required");
@@ -95,6 +96,11 @@ extern "C" int hb_conv2d_preserving(const hb_array *K, const hb_array *A, hb_arr
              hb_shape_str(A).c_str());
   int64_t N = A->shape[0], Ci = A->shape[1], H = A->shape[2], W = A->shape[3];
   int64_t Co = K->shape[0], KH = K->shape[2], KW = K->shape[3];
+  if (hb_lazy_on()) {
+    int64_t sh_[4] = {N, Co, H, W};
+    return hb_lrec(HB_L_CONV_FWD, "conv2d_preserving").in(K).in(A).out(out, A->dt, 4, sh_).commit(
+        [=](hb_lnode &n, hb_array *const *in, hb_array **o) { return hb_conv2d_preserving(in[0], in[1], &o[0]); });
+  }
   if (N * Co * H * W == 0 || Ci * KH * KW == 0) {
     int64_t sh[4] = {N, Co, H, W};
     return hb_zeros(A->dt, 4, sh, out);
@@ -125,7 +131,7 @@ extern "C" int hb_conv2d_preserving(const hb_array *K, const hb_array *A, hb_arr
 extern "C" int hb_conv2d_preserving_dkrn(const hb_array *A, const hb_array *dB, int KH, int KW,
                                          hb_array **out) {
   hb_prof_scope prof_("conv2d_preserving_dkrn", A, dB);
-  HB_CHECK_INIT();
+  HB_CHECK_INIT_LAZY();
   HB_REQUIRE(A && dB && out, "null argument");
   HB_REQUIRE(A->rank == 4 && dB->rank == 4 && A->dt == dB->dt && hb_is_float(A->dt),
              "conv2dPreserving_dKrn: rank-4 floating operands required");
@@ -134,6 +140,9 @@ extern "C" int hb_conv2d_preserving_dkrn(const hb_array *A, const hb_array *dB, 
   HB_REQUIRE(KH >= 0 && KW >= 0, "conv2dPreserving_dKrn: bad kernel size");
   int64_t N = A->shape[0], Ci = A->shape[1], H = A->shape[2], W = A->shape[3], Co = dB->shape[1];
   int64_t ksh[4] = {Co, Ci, KH, KW};
+  if (hb_lazy_on())
+    return hb_lrec(HB_L_CONV_DK, "conv2d_dkrn").in(A).in(dB).iarg(0, KH).iarg(1, KW).out(out, A->dt, 4, ksh).commit(
+        [=](hb_lnode &n, hb_array *const *in, hb_array **o) { return hb_conv2d_preserving_dkrn(in[0], in[1], (int)n.ia[0], (int)n.ia[1], &o[0]); });
   if (N * H * W == 0 || Co * Ci * KH * KW == 0) return hb_zeros(A->dt, 4, ksh, out);
   if (A->dt == HB_F64 && hb_contig(A) && hb_contig(dB)) {
     hb_array *o;
@@ -179,7 +188,7 @@ extern "C" int hb_conv2d_preserving_dkrn(const hb_array *A, const hb_array *dB, 
 
 extern "C" int hb_conv2d_preserving_dinp(const hb_array *K, const hb_array *dB, hb_array **out) {
   hb_prof_scope prof_("conv2d_preserving_dinp", K, dB);
-  HB_CHECK_INIT();
+  HB_CHECK_INIT_LAZY();
   HB_REQUIRE(K && dB && out, "null argument");
   HB_REQUIRE(K->rank == 4 && dB->rank == 4 && K->dt == dB->dt && hb_is_float(K->dt),
              "conv2dPreserving_dInp: rank-4 floating operands required");
@@ -188,6 +197,9 @@ extern "C" int hb_conv2d_preserving_dinp(const hb_array *K, const hb_array *dB, 
   int64_t N = dB->shape[0], Co = dB->shape[1], H = dB->shape[2], W = dB->shape[3];
   int64_t Ci = K->shape[1], KH = K->shape[2], KW = K->shape[3];
   int64_t ash[4] = {N, Ci, H, W};
+  if (hb_lazy_on())
+    return hb_lrec(HB_L_CONV_DI, "conv2d_dinp").in(K).in(dB).out(out, K->dt, 4, ash).commit(
+        [=](hb_lnode &n, hb_array *const *in, hb_array **o) { return hb_conv2d_preserving_dinp(in[0], in[1], &o[0]); });
   if (N * Ci * H * W == 0 || Co * KH * KW == 0) return hb_zeros(K->dt, 4, ash, out);
   {
     int done = 0;
@@ -224,7 +236,7 @@ extern "C" int hb_relu_pool_bwd(const hb_array *dy, const hb_array *code, int ks
 extern "C" int hb_conv_relu_pool_fwd(const hb_array *K, const hb_array *bias, const hb_array *A, int ksize,
                                      hb_array **out, hb_array **code_out) {
   hb_prof_scope prof_("conv_relu_pool_fwd", K, A);
-  HB_CHECK_INIT();
+  HB_CHECK_INIT_LAZY();
   HB_REQUIRE(K && A && out && code_out, "null argument");
   HB_REQUIRE(K->rank == 4 && A->rank == 4 && K->dt == A->dt && hb_is_float(A->dt) && K->shape[1] == A->shape[1],
              "conv_relu_pool: kernel %s vs input %s", hb_shape_str(K).c_str(), hb_shape_str(A).c_str());
@@ -232,6 +244,18 @@ extern "C" int hb_conv_relu_pool_fwd(const hb_array *K, const hb_array *bias, co
              "conv_relu_pool: bias must be [%lld]", (long long)K->shape[0]);
   HB_REQUIRE(ksize >= 1 && ksize <= 11, "conv_relu_pool: window must be 1..11");
   int64_t N = A->shape[0], Co = K->shape[0], H = A->shape[2], W = A->shape[3];
+  if (hb_lazy_on()) {
+    int64_t sh_[4] = {N, Co, H / ksize, W / ksize};
+    const bool hb_ = bias != nullptr;
+    hb_lrec r(HB_L_CRP_FWD, "conv_relu_pool_fwd");
+    r.in(K);
+    if (hb_) r.in(bias);
+    return r.in(A).iarg(0, ksize).iarg(1, hb_).out(out, A->dt, 4, sh_).out(code_out, HB_I8, 4, sh_).commit(
+        [=](hb_lnode &n, hb_array *const *in, hb_array **o) {
+          const bool b_ = n.ia[1] != 0;
+          return hb_conv_relu_pool_fwd(in[0], b_ ? in[1] : nullptr, in[b_ ? 2 : 1], (int)n.ia[0], &o[0], &o[1]);
+        });
+  }
   if (ksize == 2 && A->dt == HB_F64 && N * Co * (H / 2) * (W / 2) > 0 && K->shape[1] * K->shape[2] * K->shape[3] > 0) {
     int64_t osh[4] = {N, Co, H / 2, W / 2};
     hb_pool_fuse pf;
@@ -265,12 +289,21 @@ extern "C" int hb_conv_relu_pool_fwd(const hb_array *K, const hb_array *bias, co
 extern "C" int hb_conv_relu_pool_bwd(const hb_array *K, const hb_array *A, const hb_array *dy, const hb_array *code,
                                      int ksize, hb_array **dK_out, hb_array **dbias_out, hb_array **dA_out) {
   hb_prof_scope prof_("conv_relu_pool_bwd", A, dy);
-  HB_CHECK_INIT();
+  HB_CHECK_INIT_LAZY();
   HB_REQUIRE(K && A && dy && code && dK_out, "null argument");
   HB_REQUIRE(K->rank == 4 && A->rank == 4 && dy->rank == 4 && K->dt == A->dt && dy->dt == A->dt && hb_is_float(A->dt),
              "conv_relu_pool_bwd: bad operands");
   int64_t H = A->shape[2], W = A->shape[3];
   int KH = (int)K->shape[2], KW = (int)K->shape[3];
+  if (hb_lazy_on()) {
+    int64_t co_ = K->shape[0];
+    return hb_lrec(HB_L_CRP_BWD, "conv_relu_pool_bwd").in(K).in(A).in(dy).in(code).iarg(0, ksize)
+        .out(dK_out, K->dt, 4, K->shape).out(dbias_out, K->dt, 1, &co_).out(dA_out, A->dt, 4, A->shape)
+        .commit([=](hb_lnode &n, hb_array *const *in, hb_array **o) {
+          return hb_conv_relu_pool_bwd(in[0], in[1], in[2], in[3], (int)n.ia[0], &o[0], n.out[1] ? &o[1] : nullptr,
+                                       n.out[2] ? &o[2] : nullptr);
+        });
+  }
   int st = HB_OK;
   if (!dA_out && ksize == 2 && A->dt == HB_F64 && hb_contig(A) && hb_contig(dy) && hb_numel(dy) > 0 &&
       K->shape[1] * KH * KW > 0) {

@@ -8,6 +8,7 @@
 // Roofline: every kernel here is HBM-bound, (k+1)*sizeof(T) algorithmic bytes
 // per element for k inputs.
 #include "iter.cuh"
+#include "lazy.cuh"
 #include "ops.cuh"
 
 // ------------------------------------------------------------ fill scalar
@@ -117,8 +118,11 @@ int hb_copy_into(hb_array *dst, const hb_array *src) { return copy_into(dst, src
 
 extern "C" int hb_contiguous(const hb_array *a, hb_array **out) {
   hb_prof_scope prof_("contiguous", a);
-  HB_CHECK_INIT();
+  HB_CHECK_INIT_LAZY();
   HB_REQUIRE(a && out, "null argument");
+  if (hb_lazy_on())
+    return hb_lrec(HB_L_COPY, "contiguous").in(a).out(out, a->dt, a->rank, a->shape).commit(
+        [](hb_lnode &n, hb_array *const *in, hb_array **o) { return hb_contiguous(in[0], &o[0]); });
   hb_array *o;
   HB_TRY(hb_new_array(a->dt, a->rank, a->shape, &o));
   int st = copy_into(o, a);
@@ -132,7 +136,7 @@ extern "C" int hb_contiguous(const hb_array *a, hb_array **out) {
 
 extern "C" int hb_append(const hb_array *a, const hb_array *b, hb_array **out) {
   hb_prof_scope prof_("append", a, b);
-  HB_CHECK_INIT();
+  HB_CHECK_INIT_LAZY();
   HB_REQUIRE(a && b && out, "null argument");
   HB_REQUIRE(a->rank >= 1 && a->rank == b->rank && a->dt == b->dt, "append: rank/dtype mismatch");
   for (int i = 1; i < a->rank; i++)
@@ -141,6 +145,9 @@ extern "C" int hb_append(const hb_array *a, const hb_array *b, hb_array **out) {
   int64_t sh[HB_R];
   memcpy(sh, a->shape, sizeof sh);
   sh[0] = a->shape[0] + b->shape[0];
+  if (hb_lazy_on())
+    return hb_lrec(HB_L_GENERIC, "append").in(a).in(b).out(out, a->dt, a->rank, sh).commit(
+        [](hb_lnode &n, hb_array *const *in, hb_array **o) { return hb_append(in[0], in[1], &o[0]); });
   hb_array *o;
   HB_TRY(hb_new_array(a->dt, a->rank, sh, &o));
   hb_array *v1 = nullptr, *v2 = nullptr;
@@ -160,7 +167,7 @@ extern "C" int hb_append(const hb_array *a, const hb_array *b, hb_array **out) {
 
 extern "C" int hb_stack(int k, hb_array *const *arrs, hb_array **out) {
   hb_prof_scope prof_("stack");
-  HB_CHECK_INIT();
+  HB_CHECK_INIT_LAZY();
   HB_REQUIRE(out, "null argument");
   HB_REQUIRE(k > 0 && arrs, "sfromVector: empty vector");  // OpsConcrete.hs:129
   const hb_array *a0 = arrs[0];
@@ -171,6 +178,12 @@ extern "C" int hb_stack(int k, hb_array *const *arrs, hb_array **out) {
   int64_t sh[HB_R];
   sh[0] = k;
   for (int i = 0; i < a0->rank; i++) sh[i + 1] = a0->shape[i];
+  if (hb_lazy_on()) {
+    hb_lrec r(HB_L_GENERIC, "stack");
+    for (int i = 0; i < k; i++) r.in(arrs[i]);
+    return r.out(out, a0->dt, a0->rank + 1, sh).commit(
+        [](hb_lnode &n, hb_array *const *in, hb_array **o) { return hb_stack((int)n.in.size(), in, &o[0]); });
+  }
   hb_array *o;
   HB_TRY(hb_new_array(a0->dt, a0->rank + 1, sh, &o));
   for (int i = 0; i < k; i++) {
@@ -207,7 +220,7 @@ __global__ void __launch_bounds__(256) hb_concat_kernel(const __grid_constant__ 
 
 extern "C" int hb_flatten_concat(int k, hb_array *const *arrs, hb_array **out) {
   hb_prof_scope prof_("flatten_concat");
-  HB_CHECK_INIT();
+  HB_CHECK_INIT_LAZY();
   HB_REQUIRE(out && k > 0 && arrs, "flatten_concat: empty list");
   int64_t total = 0, maxn = 0;
   bool all_contig = k <= 16;
@@ -217,6 +230,12 @@ extern "C" int hb_flatten_concat(int k, hb_array *const *arrs, hb_array **out) {
     total += n;
     if (n > maxn) maxn = n;
     if (!hb_contig(arrs[i])) all_contig = false;
+  }
+  if (hb_lazy_on()) {
+    hb_lrec r(HB_L_GENERIC, "flatten_concat");
+    for (int i = 0; i < k; i++) r.in(arrs[i]);
+    return r.out(out, arrs[0]->dt, 1, &total).commit(
+        [](hb_lnode &n, hb_array *const *in, hb_array **o) { return hb_flatten_concat((int)n.in.size(), in, &o[0]); });
   }
   hb_array *o;
   HB_TRY(hb_new_array(arrs[0]->dt, 1, &total, &o));
@@ -267,10 +286,22 @@ __global__ void hb_iota_kernel(T *o, int64_t n) {
 }
 
 extern "C" int hb_iota(hb_dtype dt, int64_t n, hb_array **out) {
-  HB_CHECK_INIT();
+  HB_CHECK_INIT_LAZY();   // a constant: created eagerly even while recording
   HB_REQUIRE(out && n >= 0, "iota: bad argument");
   hb_array *o;
   HB_TRY(hb_new_array(dt, 1, &n, &o));
+  if (n > 0 && (n * hb_dtype_size(dt) <= 4096 || g_hb.trace_only) && dt != HB_BOOL) {
+    auto img = std::make_shared<std::vector<uint8_t>>((size_t)n * hb_dtype_size(dt));
+    for (int64_t i = 0; i < n; i++) {
+      HB_DISPATCH_NUM(dt, T, ((T *)img->data())[i] = (T)i);
+    }
+    o->st->host = img;
+    if (g_hb.trace_only) {
+      memcpy(hb_data(o), img->data(), img->size());
+      *out = o;
+      return HB_OK;
+    }
+  }
   if (n > 0) {
     HB_DISPATCH_ALL(dt, T, hb_iota_kernel<T><<<hb_blocks_for(n, 256), 256, 0, g_hb.stream>>>((T *)hb_data(o), n));
     HB_LAUNCHED();
@@ -310,8 +341,11 @@ static int unary_dispatch(hb_unop op, hb_array *o, const hb_array *a) {
 
 extern "C" int hb_unary(hb_unop op, const hb_array *a, hb_array **out) {
   hb_prof_scope prof_("unary", a);
-  HB_CHECK_INIT();
+  HB_CHECK_INIT_LAZY();
   HB_REQUIRE(a && out, "null argument");
+  if (hb_lazy_on())
+    return hb_lrec(HB_L_UNARY, "unary").in(a).iarg(0, (int)op).out(out, a->dt, a->rank, a->shape).commit(
+        [](hb_lnode &n, hb_array *const *in, hb_array **o) { return hb_unary((hb_unop)n.ia[0], in[0], &o[0]); });
   hb_array *o;
   HB_TRY(hb_new_array(a->dt, a->rank, a->shape, &o));
   int st = HB_OK;
@@ -373,11 +407,14 @@ static int binary_into(hb_binop op, hb_array *o, const hb_array *a, const hb_arr
 
 extern "C" int hb_binary(hb_binop op, const hb_array *a, const hb_array *b, hb_array **out) {
   hb_prof_scope prof_("binary", a, b);
-  HB_CHECK_INIT();
+  HB_CHECK_INIT_LAZY();
   HB_REQUIRE(a && b && out, "null argument");
   HB_REQUIRE(a->dt == b->dt, "binary op: dtype %s vs %s", hb_dtype_name(a->dt), hb_dtype_name(b->dt));
   HB_REQUIRE(hb_same_shape(a, b), "binary op: shape %s vs %s", hb_shape_str(a).c_str(),
              hb_shape_str(b).c_str());
+  if (hb_lazy_on())
+    return hb_lrec(HB_L_BINARY, "binary").in(a).in(b).iarg(0, (int)op).out(out, a->dt, a->rank, a->shape).commit(
+        [](hb_lnode &n, hb_array *const *in, hb_array **o) { return hb_binary((hb_binop)n.ia[0], in[0], in[1], &o[0]); });
   hb_array *o;
   HB_TRY(hb_new_array(a->dt, a->rank, a->shape, &o));
   int st = binary_into(op, o, a, b);
@@ -391,11 +428,24 @@ extern "C" int hb_binary(hb_binop op, const hb_array *a, const hb_array *b, hb_a
 
 extern "C" int hb_add_inplace_or_new(hb_array *acc, const hb_array *c, hb_array **out) {
   hb_prof_scope prof_("add_inplace_or_new", acc, c);
-  HB_CHECK_INIT();
+  HB_CHECK_INIT_LAZY();
   HB_REQUIRE(acc && c && out, "null argument");
   HB_REQUIRE(acc->dt == c->dt && hb_same_shape(acc, c), "taddTarget: %s %s vs %s %s",
              hb_dtype_name(acc->dt), hb_shape_str(acc).c_str(), hb_dtype_name(c->dt),
              hb_shape_str(c).c_str());
+  if (hb_lazy_on())
+    // taddTarget: whether the sum may overwrite `acc` is decided by the program's liveness analysis (acc dies here),
+    // not by the reference counts at recording time
+    return hb_lrec(HB_L_ADD_ACC, "add_acc").in(acc).in(c).out(out, acc->dt, acc->rank, acc->shape).commit(
+        [](hb_lnode &n, hb_array *const *in, hb_array **o) {
+          if (n.inplace_ok) {
+            HB_TRY(binary_into(HB_ADD, in[0], in[0], in[1]));
+            hb_retain(in[0]);
+            o[0] = in[0];
+            return HB_OK;
+          }
+          return hb_binary(HB_ADD, in[0], in[1], &o[0]);
+        });
   bool unique = acc->rc.load() == 1 && acc->st && acc->st->rc.load() == 1 && hb_contig(acc) &&
                 (c->st != acc->st);
   if (unique) {
@@ -432,8 +482,11 @@ static int cast_from(hb_array *o, const hb_array *a) {
 
 extern "C" int hb_cast(const hb_array *a, hb_dtype dt, hb_array **out) {
   hb_prof_scope prof_("cast", a);
-  HB_CHECK_INIT();
+  HB_CHECK_INIT_LAZY();
   HB_REQUIRE(a && out, "null argument");
+  if (hb_lazy_on())
+    return hb_lrec(HB_L_GENERIC, "cast").in(a).iarg(0, (int)dt).out(out, dt, a->rank, a->shape).commit(
+        [](hb_lnode &n, hb_array *const *in, hb_array **o) { return hb_cast(in[0], (hb_dtype)n.ia[0], &o[0]); });
   hb_array *o;
   HB_TRY(hb_new_array(dt, a->rank, a->shape, &o));
   int st;
@@ -461,10 +514,13 @@ static int floor_typed(hb_array *o, const hb_array *a) {
 }
 
 extern "C" int hb_floor(const hb_array *a, hb_dtype dt, hb_array **out) {
-  HB_CHECK_INIT();
+  HB_CHECK_INIT_LAZY();
   HB_REQUIRE(a && out, "null argument");
   HB_REQUIRE(hb_is_float(a->dt), "floor: source must be floating, got %s", hb_dtype_name(a->dt));
   HB_REQUIRE(!hb_is_float(dt) && dt != HB_BOOL, "floor: target must be integral, got %s", hb_dtype_name(dt));
+  if (hb_lazy_on())
+    return hb_lrec(HB_L_GENERIC, "floor").in(a).iarg(0, (int)dt).out(out, dt, a->rank, a->shape).commit(
+        [](hb_lnode &n, hb_array *const *in, hb_array **o) { return hb_floor(in[0], (hb_dtype)n.ia[0], &o[0]); });
   hb_array *o;
   HB_TRY(hb_new_array(dt, a->rank, a->shape, &o));
   int st = HB_OK;
@@ -567,8 +623,11 @@ extern "C" int hb_compare_all(int op, const hb_array *a, const hb_array *b, int 
 // oneIfGtZero = ifH (x <=. 0) 0 1.
 extern "C" int hb_relu(const hb_array *x, hb_array **out) {
   hb_prof_scope prof_("relu", x);
-  HB_CHECK_INIT();
+  HB_CHECK_INIT_LAZY();
   HB_REQUIRE(x && out, "null argument");
+  if (hb_lazy_on())
+    return hb_lrec(HB_L_GENERIC, "relu").in(x).out(out, x->dt, x->rank, x->shape).commit(
+        [](hb_lnode &n, hb_array *const *in, hb_array **o) { return hb_relu(in[0], &o[0]); });
   hb_array *o;
   HB_TRY(hb_new_array(x->dt, x->rank, x->shape, &o));
   int st = HB_OK;
@@ -592,10 +651,13 @@ __global__ void hb_sgd_kernel(T *p, const T *g, T gamma, int64_t n) {
 
 extern "C" int hb_sgd_step(hb_array *p, const hb_array *g, double gamma) {
   hb_prof_scope prof_("sgd_step", p);
-  HB_CHECK_INIT();
+  HB_CHECK_INIT_LAZY();
   HB_REQUIRE(p && g, "null argument");
   HB_REQUIRE(p->dt == g->dt && hb_same_shape(p, g), "sgd: parameter/gradient mismatch");
   HB_REQUIRE(hb_contig(p), "sgd: parameters must be contiguous");
+  if (hb_lazy_on())
+    return hb_lrec(HB_L_EFFECT, "sgd_step").in(p).in(g).farg(0, gamma).commit(
+        [](hb_lnode &n, hb_array *const *in, hb_array **o) { return hb_sgd_step(in[0], in[1], n.fa[0]); });
   int64_t n = hb_numel(p);
   if (n == 0) return HB_OK;
   const hb_array *gc = g;
@@ -693,11 +755,14 @@ static void adam_launch(T *p, T *m, T *v, const T *g, T alphat, T b1, T b2, T ep
 extern "C" int hb_adam_step(hb_array *p, hb_array *m, hb_array *v, const hb_array *g, double alpha,
                             double beta1, double beta2, double epsilon, int64_t t) {
   hb_prof_scope prof_("adam_step", p);
-  HB_CHECK_INIT();
+  HB_CHECK_INIT_LAZY();
   HB_REQUIRE(p && m && v && g, "null argument");
   HB_REQUIRE(p->dt == g->dt && p->dt == m->dt && p->dt == v->dt, "adam: dtype mismatch");
   HB_REQUIRE(hb_same_shape(p, g) && hb_same_shape(p, m) && hb_same_shape(p, v), "adam: shape mismatch");
   HB_REQUIRE(hb_contig(p) && hb_contig(m) && hb_contig(v), "adam: state must be contiguous");
+  if (hb_lazy_on())
+    return hb_lrec(HB_L_EFFECT, "adam_step").in(p).in(m).in(v).in(g).commit(
+        [=](hb_lnode &n, hb_array *const *in, hb_array **o) { return hb_adam_step(in[0], in[1], in[2], in[3], alpha, beta1, beta2, epsilon, t); });
   int64_t n = hb_numel(p);
   if (n == 0) return HB_OK;
   const hb_array *gc = g;

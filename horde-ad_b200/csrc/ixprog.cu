@@ -18,6 +18,7 @@
 // exit immediately and a direct store kernel does the work.
 // HBM roofline: 2*sizeof(T) bytes per moved element (+ index tables).
 #include "iter.cuh"
+#include "lazy.cuh"
 #include "vm.cuh"
 #include "jit.cuh"
 
@@ -129,6 +130,7 @@ extern "C" int hb_ixprog_build(const hb_insn *code, int n_insns, int n_vars, int
 
 extern "C" int hb_ixprog_free(hb_ixprog *p) {
   if (!p) return HB_OK;
+  if (p->rc.fetch_sub(1) != 1) return HB_OK;   // still referenced by a recorded lazy node
   for (int t = 0; t < p->n_tensors; t++) hb_release(p->held[t]);
   delete p;
   return HB_OK;
@@ -556,7 +558,7 @@ static void fill_shm(hb_shm *S, int shm_rank, const int64_t *shm, int shp_rank, 
 extern "C" int hb_gather(const hb_array *src, int shm_rank, const int64_t *shm, int shp_rank,
                          const hb_ixprog *prog, hb_array **out) {
   hb_prof_scope prof_("gather", src);
-  HB_CHECK_INIT();
+  HB_CHECK_INIT_LAZY();
   HB_REQUIRE(src && prog && out, "null argument");
   HB_REQUIRE(shm_rank >= 0 && shm_rank <= HB_R && (shm_rank == 0 || shm), "gather: bad shm");
   HB_REQUIRE(shp_rank >= 0 && shp_rank <= src->rank, "gather: |shp| = %d exceeds source rank %d", shp_rank,
@@ -571,6 +573,11 @@ extern "C" int hb_gather(const hb_array *src, int shm_rank, const int64_t *shm, 
   for (int i = 0; i < shm_rank; i++) { osh[i] = shm[i]; M *= shm[i]; }
   for (int i = 0; i < nrank; i++) { osh[shm_rank + i] = src->shape[shp_rank + i]; Nn *= src->shape[shp_rank + i]; }
   int orank = shm_rank + nrank;
+  if (hb_lazy_on())
+    return hb_lrec(HB_L_GATHER, "gather").in(src).iarg(0, shm_rank).iarg(1, shp_rank).prog(prog).out(out, src->dt, orank, osh)
+        .commit([=](hb_lnode &n, hb_array *const *in, hb_array **o) {
+          return hb_gather(in[0], (int)n.ia[0], n.out[0]->shape, (int)n.ia[1], n.prog, &o[0]);
+        });
 
   if (prog->affine) {
     // folded strides: stride of shm axis k = sum_c coef[c][k] * src.stride[c]
@@ -1153,7 +1160,7 @@ static void srows_set_vec(hb_srowsp *R, int V) {
 extern "C" int hb_scatter_add(const hb_array *src, int shm_rank, int shp_rank, const int64_t *shp,
                               const hb_ixprog *prog, hb_array **out) {
   hb_prof_scope prof_("scatter_add", src);
-  HB_CHECK_INIT();
+  HB_CHECK_INIT_LAZY();
   HB_REQUIRE(src && prog && out, "null argument");
   HB_REQUIRE(shm_rank >= 0 && shm_rank <= src->rank, "scatter: |shm| = %d exceeds source rank %d", shm_rank,
              src->rank);
@@ -1169,6 +1176,12 @@ extern "C" int hb_scatter_add(const hb_array *src, int shm_rank, int shp_rank, c
   for (int i = 0; i < shm_rank; i++) M *= src->shape[i];
   for (int i = 0; i < shp_rank; i++) { osh[i] = shp[i]; Pn *= shp[i]; }
   for (int i = 0; i < nrank; i++) { osh[shp_rank + i] = src->shape[shm_rank + i]; Nn *= src->shape[shm_rank + i]; }
+  if (hb_lazy_on())
+    return hb_lrec(HB_L_SCATTER, "scatter_add").in(src).iarg(0, shm_rank).iarg(1, shp_rank).prog(prog)
+        .out(out, src->dt, shp_rank + nrank, osh)
+        .commit([=](hb_lnode &n, hb_array *const *in, hb_array **o) {
+          return hb_scatter_add(in[0], (int)n.ia[0], (int)n.ia[1], n.out[0]->shape, n.prog, &o[0]);
+        });
   hb_array *o;
   bool rows_ok = true;
   for (int i = 0; i < nrank; i++) rows_ok = rows_ok && src->shape[shm_rank + i] < (1ll << 31);
@@ -1284,12 +1297,19 @@ extern "C" int hb_scatter_add(const hb_array *src, int shm_rank, int shp_rank, c
 extern "C" int hb_onehot(const hb_array *v, int shp_rank, const int64_t *shp, const int64_t *ix,
                          hb_array **out) {
   hb_prof_scope prof_("onehot", v);
-  HB_CHECK_INIT();
+  HB_CHECK_INIT_LAZY();
   HB_REQUIRE(v && out, "null argument");
   HB_REQUIRE(shp_rank >= 0 && shp_rank + v->rank <= HB_R, "oneHot: rank too large");
   int64_t osh[HB_R];
   for (int i = 0; i < shp_rank; i++) osh[i] = shp[i];
   for (int i = 0; i < v->rank; i++) osh[shp_rank + i] = v->shape[i];
+  if (hb_lazy_on()) {
+    std::vector<int64_t> ix_(ix, ix + shp_rank);
+    return hb_lrec(HB_L_GENERIC, "onehot").in(v).iarg(0, shp_rank).out(out, v->dt, shp_rank + v->rank, osh).commit(
+        [ix_](hb_lnode &n, hb_array *const *in, hb_array **o) {
+          return hb_onehot(in[0], (int)n.ia[0], n.out[0]->shape, ix_.data(), &o[0]);
+        });
+  }
   hb_array *o;
   HB_TRY(hb_zeros(v->dt, shp_rank + v->rank, osh, &o));
   bool inb = true;
@@ -1356,13 +1376,19 @@ __global__ void __launch_bounds__(128)
 extern "C" int hb_fused_map(const hb_ixprog *prog, int n_in, hb_array *const *ins, hb_dtype dt,
                             hb_array **out) {
   hb_prof_scope prof_("fused_map");
-  HB_CHECK_INIT();
+  HB_CHECK_INIT_LAZY();
   HB_REQUIRE(prog && out && ins, "null argument");
   HB_REQUIRE(n_in >= 1 && n_in <= HB_MAP_MAXIN, "fused map: %d inputs (max %d)", n_in, HB_MAP_MAXIN);
   HB_REQUIRE(prog->vm.n_out == 1, "fused map: program must have exactly one output");
   for (int i = 1; i < n_in; i++)
     HB_REQUIRE(hb_same_shape(ins[0], ins[i]), "fused map: input %d has shape %s, expected %s", i,
                hb_shape_str(ins[i]).c_str(), hb_shape_str(ins[0]).c_str());
+  if (hb_lazy_on()) {
+    hb_lrec r(HB_L_GENERIC, "fused_map");
+    for (int i = 0; i < n_in; i++) r.in(ins[i]);
+    return r.prog(prog).out(out, dt, ins[0]->rank, ins[0]->shape).commit(
+        [=](hb_lnode &n, hb_array *const *in, hb_array **o) { return hb_fused_map(n.prog, (int)n.in.size(), in, n.out[0]->dt, &o[0]); });
+  }
   hb_array *o;
   HB_TRY(hb_new_array(dt, ins[0]->rank, ins[0]->shape, &o));
   int64_t n = hb_numel(o);

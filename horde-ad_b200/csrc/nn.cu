@@ -5,6 +5,7 @@
 // softmax-cross-entropy loss (lossSoftMaxCrossEntropyS, :89-111).
 // All kernels are HBM-bound single passes.
 #include "common.cuh"
+#include "lazy.cuh"
 #include "iter.cuh"
 
 // one thread per output window; value at the FIRST maximum of the row-major
@@ -42,12 +43,15 @@ __global__ void __launch_bounds__(256)
 
 extern "C" int hb_maxpool2d(const hb_array *x, int ksize, int stride, hb_array **out, hb_array **argmax_out) {
   hb_prof_scope prof_("maxpool2d", x);
-  HB_CHECK_INIT();
+  HB_CHECK_INIT_LAZY();
   HB_REQUIRE(x && out, "null argument");
   HB_REQUIRE(x->rank == 4 && hb_is_float(x->dt), "maxPool2d: rank-4 floating input required");
   HB_REQUIRE(ksize >= 1 && stride >= 1, "maxPool2d: bad window");
   int64_t H = x->shape[2], W = x->shape[3];
   int64_t osh[4] = {x->shape[0], x->shape[1], H / stride, W / stride};
+  if (hb_lazy_on())
+    return hb_lrec(HB_L_GENERIC, "maxpool2d").in(x).iarg(0, ksize).iarg(1, stride).out(out, x->dt, 4, osh).out(argmax_out, HB_I64, 4, osh)
+        .commit([=](hb_lnode &n, hb_array *const *in, hb_array **o) { return hb_maxpool2d(in[0], (int)n.ia[0], (int)n.ia[1], &o[0], n.out[1] ? &o[1] : nullptr); });
   hb_array *y, *am = nullptr;
   HB_TRY(hb_new_array(x->dt, 4, osh, &y));
   if (argmax_out) {
@@ -102,11 +106,16 @@ __global__ void __launch_bounds__(256)
 extern "C" int hb_maxpool2d_bwd(const hb_array *dy, const hb_array *argmax, int ksize, int stride, int64_t H,
                                 int64_t W, hb_array **out) {
   hb_prof_scope prof_("maxpool2d_bwd", dy);
-  HB_CHECK_INIT();
+  HB_CHECK_INIT_LAZY();
   HB_REQUIRE(dy && argmax && out, "null argument");
   HB_REQUIRE(dy->rank == 4 && hb_is_float(dy->dt) && argmax->dt == HB_I64 && hb_same_shape(dy, argmax),
              "maxPool2d_bwd: bad operands");
   HB_REQUIRE(dy->shape[2] == H / stride && dy->shape[3] == W / stride, "maxPool2d_bwd: output extents do not match");
+  if (hb_lazy_on()) {
+    int64_t sh_[4] = {dy->shape[0], dy->shape[1], H, W};
+    return hb_lrec(HB_L_GENERIC, "maxpool2d_bwd").in(dy).in(argmax).iarg(0, ksize).iarg(1, stride).out(out, dy->dt, 4, sh_).commit(
+        [=](hb_lnode &n, hb_array *const *in, hb_array **o) { return hb_maxpool2d_bwd(in[0], in[1], (int)n.ia[0], (int)n.ia[1], n.out[0]->shape[2], n.out[0]->shape[3], &o[0]); });
+  }
   const hb_array *dyc = dy, *amc = argmax;
   hb_array *t1 = nullptr, *t2 = nullptr;
   if (!hb_contig(dy)) { HB_TRY(hb_contiguous(dy, &t1)); dyc = t1; }
@@ -192,12 +201,20 @@ __global__ void __launch_bounds__(256)
 extern "C" int hb_relu_pool_fwd(const hb_array *pre, const hb_array *bias, int ksize, hb_array **out,
                                 hb_array **code_out) {
   hb_prof_scope prof_("relu_pool_fwd", pre);
-  HB_CHECK_INIT();
+  HB_CHECK_INIT_LAZY();
   HB_REQUIRE(pre && out && code_out, "null argument");
   HB_REQUIRE(pre->rank == 4 && hb_is_float(pre->dt), "relu_pool: rank-4 floating input required");
   HB_REQUIRE(ksize >= 1 && ksize <= 11, "relu_pool: window must be 1..11");
   HB_REQUIRE(!bias || (bias->rank == 1 && bias->dt == pre->dt && bias->shape[0] == pre->shape[1]),
              "relu_pool: bias must be [%lld]", (long long)pre->shape[1]);
+  if (hb_lazy_on()) {
+    int64_t sh_[4] = {pre->shape[0], pre->shape[1], pre->shape[2] / ksize, pre->shape[3] / ksize};
+    hb_lrec r(HB_L_RELU_POOL_FWD, "relu_pool_fwd");
+    r.in(pre);
+    if (bias) r.in(bias);
+    return r.iarg(0, ksize).out(out, pre->dt, 4, sh_).out(code_out, HB_I8, 4, sh_).commit(
+        [=](hb_lnode &n, hb_array *const *in, hb_array **o) { return hb_relu_pool_fwd(in[0], n.in.size() > 1 ? in[1] : nullptr, (int)n.ia[0], &o[0], &o[1]); });
+  }
   const hb_array *pc = pre, *bc = bias;
   hb_array *t1 = nullptr, *t2 = nullptr;
   if (!hb_contig(pre)) { HB_TRY(hb_contiguous(pre, &t1)); pc = t1; }
@@ -315,13 +332,22 @@ __global__ void hb_bias_finish_kernel(const T *__restrict__ part, int C, int nch
 extern "C" int hb_relu_pool_bwd(const hb_array *dy, const hb_array *code, int ksize, int64_t H, int64_t W,
                                 hb_array **dpre_out, hb_array **dbias_out) {
   hb_prof_scope prof_("relu_pool_bwd", dy);
-  HB_CHECK_INIT();
+  HB_CHECK_INIT_LAZY();
   HB_REQUIRE(dy && code && (dpre_out || dbias_out), "null argument");
   const bool write = dpre_out != nullptr;  // NULL: only the bias cotangent is wanted
   HB_REQUIRE(dy->rank == 4 && hb_is_float(dy->dt) && code->dt == HB_I8 && hb_same_shape(dy, code),
              "relu_pool_bwd: bad operands");
   HB_REQUIRE(ksize >= 1 && ksize <= 11 && dy->shape[2] == H / ksize && dy->shape[3] == W / ksize,
              "relu_pool_bwd: extents do not match");
+  if (hb_lazy_on()) {
+    int64_t sh_[4] = {dy->shape[0], dy->shape[1], H, W};
+    return hb_lrec(HB_L_RELU_POOL_BWD, "relu_pool_bwd").in(dy).in(code).iarg(0, ksize).iarg(1, H).iarg(2, W)
+        .out(dpre_out, dy->dt, 4, sh_).out(dbias_out, dy->dt, 1, &dy->shape[1])
+        .commit([=](hb_lnode &n, hb_array *const *in, hb_array **o) {
+          return hb_relu_pool_bwd(in[0], in[1], (int)n.ia[0], n.ia[1], n.ia[2], n.out[0] ? &o[0] : nullptr,
+                                  n.out[1] ? &o[1] : nullptr);
+        });
+  }
   const hb_array *dyc = dy, *cc = code;
   hb_array *t1 = nullptr, *t2 = nullptr;
   if (!hb_contig(dy)) { HB_TRY(hb_contiguous(dy, &t1)); dyc = t1; }
@@ -486,12 +512,18 @@ static int softmax_xent_launch(const hb_array *logits, const hb_array *expected,
 extern "C" int hb_softmax_xent(const hb_array *logits, const hb_array *expected, double scale,
                                hb_array **loss_out, hb_array **dlogits_out) {
   hb_prof_scope prof_("softmax_xent", logits);
-  HB_CHECK_INIT();
+  HB_CHECK_INIT_LAZY();
   HB_REQUIRE(logits && expected && loss_out, "null argument");
   HB_REQUIRE(hb_is_float(logits->dt) && logits->dt == expected->dt && hb_same_shape(logits, expected),
              "softmax-xent: logits %s vs expected %s", hb_shape_str(logits).c_str(), hb_shape_str(expected).c_str());
   int64_t n = hb_numel(logits);
   HB_REQUIRE(n > 0, "softmax-xent: empty logits");
+  if (hb_lazy_on()) {
+    int64_t one_ = 1;
+    return hb_lrec(HB_L_GENERIC, "softmax_xent").in(logits).in(expected).farg(0, scale).out(loss_out, logits->dt, 0, &one_)
+        .out(dlogits_out, logits->dt, logits->rank, logits->shape)
+        .commit([=](hb_lnode &n, hb_array *const *in, hb_array **o) { return hb_softmax_xent(in[0], in[1], n.fa[0], &o[0], n.out[1] ? &o[1] : nullptr); });
+  }
   hb_array *loss, *dl = nullptr;
   int64_t one = 1;
   HB_TRY(hb_new_array(logits->dt, 0, &one, &loss));
@@ -565,7 +597,7 @@ __global__ void __launch_bounds__(256)
 extern "C" int hb_mnist_batch_into(const hb_array *pixels, const hb_array *labels, const hb_array *order,
                                    int64_t start, hb_array *glyphs_dst, hb_array *targets_dst) {
   hb_prof_scope prof_("mnist_batch_into", glyphs_dst);
-  HB_CHECK_INIT();
+  HB_CHECK_INIT_LAZY();
   HB_REQUIRE(pixels && labels && glyphs_dst && targets_dst, "null argument");
   HB_REQUIRE(pixels->dt == HB_I8 && labels->dt == HB_I8 && pixels->rank >= 2 && labels->rank == 1 &&
                  pixels->shape[0] == labels->shape[0] && hb_contig(pixels) && hb_contig(labels),
@@ -594,6 +626,14 @@ extern "C" int hb_mnist_batch_into(const hb_array *pixels, const hb_array *label
     // chunksOf just hands out a short last batch, MnistData.hs:134-171) -- refuse it instead
     HB_REQUIRE(start + batch <= n, "mnist_batch: batch [%lld, %lld) beyond the %lld samples", (long long)start,
                (long long)(start + batch), (long long)n);
+  }
+  if (hb_lazy_on()) {
+    hb_lrec r(HB_L_EFFECT, "mnist_batch_into");
+    r.in(pixels).in(labels).in(glyphs_dst).in(targets_dst);
+    if (order) r.in(order);
+    return r.commit([=](hb_lnode &n, hb_array *const *in, hb_array **o) {
+      return hb_mnist_batch_into(in[0], in[1], n.in.size() > 4 ? in[4] : nullptr, start, in[2], in[3]);
+    });
   }
   if (batch == 0 || (hw == 0 && classes == 0)) return HB_OK;
   const uint8_t *pp = (const uint8_t *)hb_data(pixels), *lp = (const uint8_t *)hb_data(labels);
@@ -661,12 +701,22 @@ __global__ void __launch_bounds__(256)
 
 extern "C" int hb_tanh_affine_fwd(const hb_array *u, const hb_array *v, const hb_array *bias, hb_array **y_out) {
   hb_prof_scope prof_("tanh_affine_fwd", u);
-  HB_CHECK_INIT();
+  HB_CHECK_INIT_LAZY();
   HB_REQUIRE(u && y_out, "null argument");
   HB_REQUIRE(u->rank == 2 && hb_is_float(u->dt) && (!v || (hb_same_shape(u, v) && u->dt == v->dt)),
              "tanh_affine: floating [width, batch] operands of one shape required");
   HB_REQUIRE(!bias || (bias->rank == 1 && bias->shape[0] == u->shape[0] && bias->dt == u->dt),
              "tanh_affine: bias must be [width] of the operands' type");
+  if (hb_lazy_on()) {
+    const bool hv_ = v != nullptr, hb_ = bias != nullptr;
+    hb_lrec r(HB_L_GENERIC, "tanh_affine_fwd");
+    r.in(u);
+    if (hv_) r.in(v);
+    if (hb_) r.in(bias);
+    return r.out(y_out, u->dt, 2, u->shape).commit([=](hb_lnode &n, hb_array *const *in, hb_array **o) {
+      return hb_tanh_affine_fwd(in[0], hv_ ? in[1] : nullptr, hb_ ? in[hv_ ? 2 : 1] : nullptr, &o[0]);
+    });
+  }
   const hb_array *uc = u, *vc = v, *bc = bias;
   hb_array *t1 = nullptr, *t2 = nullptr, *t3 = nullptr, *y = nullptr;
   int st = HB_OK;
@@ -695,11 +745,14 @@ extern "C" int hb_tanh_affine_fwd(const hb_array *u, const hb_array *v, const hb
 
 extern "C" int hb_tanh_affine_bwd(const hb_array *y, const hb_array *c, hb_array **dz_out, hb_array **dbias_out) {
   hb_prof_scope prof_("tanh_affine_bwd", y);
-  HB_CHECK_INIT();
+  HB_CHECK_INIT_LAZY();
   HB_REQUIRE(y && c && dz_out, "null argument");
   HB_REQUIRE(y->rank == 2 && hb_same_shape(y, c) && y->dt == c->dt && hb_is_float(y->dt),
              "tanh_affine_bwd: two floating [width, batch] operands of one shape required");
   HB_REQUIRE(y->shape[0] < (1ll << 31), "tanh_affine_bwd: too many rows");
+  if (hb_lazy_on())
+    return hb_lrec(HB_L_GENERIC, "tanh_affine_bwd").in(y).in(c).out(dz_out, y->dt, 2, y->shape).out(dbias_out, y->dt, 1, y->shape)
+        .commit([=](hb_lnode &n, hb_array *const *in, hb_array **o) { return hb_tanh_affine_bwd(in[0], in[1], &o[0], n.out[1] ? &o[1] : nullptr); });
   const hb_array *yc = y, *cc = c;
   hb_array *t1 = nullptr, *t2 = nullptr, *dz = nullptr, *db = nullptr;
   int st = HB_OK;

@@ -18,6 +18,7 @@
 //          reduced range, shared-memory tree over y.
 // HBM roofline: sizeof(T) bytes per input element (2x for dot), SURVEY 8d.
 #include "common.cuh"
+#include "lazy.cuh"
 #include "iter.cuh"
 
 struct hb_redp {
@@ -355,10 +356,13 @@ int hb_reduce_generic(const hb_array *a, const hb_array *b, int nk, const int *k
 
 extern "C" int hb_sum_leading(const hb_array *a, int n_axes, hb_array **out) {
   hb_prof_scope prof_("sum_leading", a);
-  HB_CHECK_INIT();
+  HB_CHECK_INIT_LAZY();
   HB_REQUIRE(a && out, "null argument");
   HB_REQUIRE(n_axes >= 0 && n_axes <= a->rank, "ssumN: %d axes of rank %d", n_axes, a->rank);
   HB_REQUIRE(a->dt != HB_BOOL, "ssum: numeric dtype required");
+  if (hb_lazy_on())
+    return hb_lrec(HB_L_SUM_LEADING, "sum_leading").in(a).iarg(0, n_axes).out(out, a->dt, a->rank - n_axes, a->shape + n_axes).commit(
+        [=](hb_lnode &n, hb_array *const *in, hb_array **o) { return hb_sum_leading(in[0], (int)n.ia[0], &o[0]); });
   hb_array *o;
   HB_TRY(hb_new_array(a->dt, a->rank - n_axes, a->shape + n_axes, &o));
   int kax[HB_R], rax[HB_R];
@@ -381,11 +385,16 @@ extern "C" int hb_sum_all(const hb_array *a, hb_array **out) {
 
 extern "C" int hb_dot_all(const hb_array *a, const hb_array *b, hb_array **out) {
   hb_prof_scope prof_("dot_all", a, b);
-  HB_CHECK_INIT();
+  HB_CHECK_INIT_LAZY();
   HB_REQUIRE(a && b && out, "null argument");
   HB_REQUIRE(a->dt == b->dt && hb_same_shape(a, b), "sdot0: %s %s vs %s %s", hb_dtype_name(a->dt),
              hb_shape_str(a).c_str(), hb_dtype_name(b->dt), hb_shape_str(b).c_str());
   HB_REQUIRE(a->dt != HB_BOOL, "sdot0: numeric dtype required");
+  if (hb_lazy_on()) {
+    int64_t one_ = 1;
+    return hb_lrec(HB_L_GENERIC, "dot_all").in(a).in(b).out(out, a->dt, 0, &one_).commit(
+        [=](hb_lnode &n, hb_array *const *in, hb_array **o) { return hb_dot_all(in[0], in[1], &o[0]); });
+  }
   hb_array *o;
   int64_t one = 1;
   HB_TRY(hb_new_array(a->dt, 0, &one, &o));
@@ -429,10 +438,13 @@ __global__ void hb_argext_kernel(hb_dims d /* kept axes */, int64_t n, int64_t s
 
 template <bool MAXI>
 static int argext(const hb_array *a, hb_array **out) {
-  HB_CHECK_INIT();
+  HB_CHECK_INIT_LAZY();
   HB_REQUIRE(a && out, "null argument");
   HB_REQUIRE(a->rank >= 1, "argMax: rank 0");
   HB_REQUIRE(a->dt != HB_BOOL, "argMax: numeric dtype required");
+  if (hb_lazy_on())
+    return hb_lrec(HB_L_GENERIC, MAXI ? "argmax_last" : "argmin_last").in(a).out(out, HB_I64, a->rank - 1, a->shape).commit(
+        [=](hb_lnode &n, hb_array *const *in, hb_array **o) { return argext<MAXI>(in[0], &o[0]); });
   int64_t n = a->shape[a->rank - 1];
   hb_array *o;
   HB_TRY(hb_new_array(HB_I64, a->rank - 1, a->shape, &o));

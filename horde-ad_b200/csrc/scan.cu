@@ -13,6 +13,7 @@
 // products -> tile rescans producing the gradient; in-tile scans are ordered warp-shuffle scans.  HBM traffic 24 bytes per element (two
 // reads, one write) against the 16-byte minimum.
 #include "common.cuh"
+#include "lazy.cuh"
 #include "iter.cuh"
 
 #define PT 2048  // elements per tile (256 threads x 8)
@@ -218,11 +219,16 @@ static int prod_launch(const hb_array *x, int64_t n, int64_t nt, double dt, void
 
 extern "C" int hb_prod_fold_grad(const hb_array *x, double dt, hb_array **prod_out, hb_array **grad_out) {
   hb_prof_scope prof_("prod_fold_grad", x);
-  HB_CHECK_INIT();
+  HB_CHECK_INIT_LAZY();
   HB_REQUIRE(x && prod_out, "null argument");
   HB_REQUIRE(x->rank == 1 && hb_is_float(x->dt), "prod fold: rank-1 floating vector required");
   int64_t n = x->shape[0];
   HB_REQUIRE(n <= (int64_t)PT * GT * GT, "prod fold: vector too long (%lld elements)", (long long)n);
+  if (hb_lazy_on()) {
+    int64_t one_ = 1;
+    return hb_lrec(HB_L_GENERIC, "prod_fold_grad").in(x).farg(0, dt).out(prod_out, x->dt, 0, &one_).out(grad_out, x->dt, 1, x->shape)
+        .commit([=](hb_lnode &n, hb_array *const *in, hb_array **o) { return hb_prod_fold_grad(in[0], n.fa[0], &o[0], n.out[1] ? &o[1] : nullptr); });
+  }
   int64_t one = 1;
   hb_array *prod, *grad = nullptr;
   HB_TRY(hb_new_array(x->dt, 0, &one, &prod));

@@ -28,6 +28,7 @@ struct hb_vm_prog {
 
 // host-side compiled program
 struct hb_ixprog {
+  std::atomic<int> rc{1};               // handle + recorded lazy nodes (lazy.cuh)
   hb_vm_prog vm;
   hb_array *held[HB_VM_MAX_TENSORS];
   int n_tensors;

@@ -118,13 +118,65 @@ class Program:
             self.h = None
 
 
+class LazyProgram:
+    """A recorded + rewritten op program (hb_lazy_*, include/hordeb200.h): `run()` replays it; the arrays
+    given as `outs` hold the results afterwards."""
+
+    def __init__(self, handle, outs):
+        self.h = handle
+        self.outs = list(outs)
+
+    def run(self):
+        call("hb_lazy_run", self.h)
+
+    @property
+    def stats(self) -> tuple:
+        rec, live = C.c_int(), C.c_int()
+        call("hb_lazy_stats", self.h, C.byref(rec), C.byref(live))
+        return rec.value, live.value
+
+    def dump(self) -> str:
+        buf = C.create_string_buffer(1 << 20)
+        call("hb_lazy_dump", self.h, buf, len(buf))
+        return buf.value.decode(errors="replace")
+
+    def close(self):
+        if self.h is not None and ffi._lib is not None:
+            ffi._lib.hb_lazy_free(self.h)
+        self.h = None
+
+    def __del__(self):
+        self.close()
+
+
 class DeviceBackend:
     """`target = Device`."""
 
     name = "device"
 
-    def __init__(self, device: int | None = None):
-        self.device = ffi.init(device)
+    def __init__(self, device: int | None = None, trace_only: bool = False):
+        self.device = ffi.init_trace_only() if trace_only else ffi.init(device)
+
+    # ------------------------------------------------------- lazy programs
+    def record(self, build: Callable, rewrite: bool = True, fuse_layers: bool = True) -> LazyProgram:
+        """Record the C-ABI calls `build()` makes into a lazy program (nothing is launched), run the device
+        contraction pass over it (`rewrite`), and return the program; `build` returns the output array(s)."""
+        call("hb_lazy_begin")
+        try:
+            outs = build()
+        except BaseException:
+            call("hb_lazy_abort")
+            raise
+        outs = list(outs) if isinstance(outs, (list, tuple)) else [outs]
+        arr = (C.c_void_p * max(1, len(outs)))(*[o.h for o in outs])
+        flags = (ffi.LAZY_REWRITE if rewrite else 0) | (0 if fuse_layers else ffi.LAZY_NO_FUSE_LAYER)
+        p = _out()
+        try:
+            call("hb_lazy_end", len(outs), arr, flags, C.byref(p))
+        except BaseException:
+            call("hb_lazy_abort")
+            raise
+        return LazyProgram(p, outs)
 
     # ------------------------------------------------------------ transfer
     def sconcrete(self, a) -> DeviceArray:

@@ -113,7 +113,12 @@ PROTOTYPES = {
     "hb_comm_unique_id": [P], "hb_comm_init": [C.c_int, C.c_int, P],
     "hb_allreduce_sum": [P, C.c_double], "hb_comm_destroy": [],
     "hb_microbench": [C.c_int, C.POINTER(C.c_double)],
+    "hb_lazy_begin": [], "hb_lazy_end": [C.c_int, PP, C.c_uint, PP], "hb_lazy_abort": [],
+    "hb_lazy_run": [P], "hb_lazy_free": [P], "hb_lazy_stats": [P, IP, IP],
+    "hb_lazy_dump": [P, C.c_char_p, C.c_size_t], "hb_init_trace_only": [],
 }
+
+LAZY_REWRITE, LAZY_NO_FUSE_LAYER = 1, 2
 
 
 def header_symbols(path: str = HEADER_PATH) -> list[str]:
@@ -175,6 +180,15 @@ def init(device: int | None = None) -> int:
     call("hb_init", device)
     _inited_device = device
     return device
+
+
+def init_trace_only() -> int:
+    """hb_init_trace_only: no device; compute calls can only be recorded (hb_lazy_begin), never run.  For
+    exercising the contraction pass on a box without a GPU."""
+    global _inited_device
+    call("hb_init_trace_only")
+    _inited_device = -1
+    return -1
 
 
 def device_count() -> int:

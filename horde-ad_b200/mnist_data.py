@@ -81,10 +81,10 @@ class DeviceMnist:
     def shuffle(self, seed: int):
         self.set_order(shuffle_order(self.n, seed))
 
-    def set_order(self, order: np.ndarray):
+    def set_order(self, order: np.ndarray, validate: bool = True):
         """Any sample-id vector: an epoch's shuffle, or this rank's shard of it."""
         order = np.ascontiguousarray(order)
-        if order.size and (int(order.min()) < 0 or int(order.max()) >= self.n):
+        if validate and order.size and (int(order.min()) < 0 or int(order.max()) >= self.n):
             # validated once on the host: a bad id would otherwise yield an all-zero glyph and target on the device
             raise ValueError(f"set_order: sample ids must lie in [0, {self.n})")
         if order.dtype not in (np.int32, np.int64):

@@ -511,6 +511,46 @@ int hb_graph_end(hb_graph **out);
 int hb_graph_launch(hb_graph *g);
 int hb_graph_free(hb_graph *g);
 
+/* ------------------------------------------- lazy programs + contraction pass
+ * The device-specific contraction pass (the reference's sibling
+ * is contractAst, AstTraverse.hs:290-699, which anticipates "one such pass per
+ * backend").  horde-ad interprets a gradient artifact -- a fixed, shape-specific
+ * op program (README.md:174-184, AstInterpret.hs:69-366) -- by calling one class
+ * method per AST node.  Between hb_lazy_begin and hb_lazy_end those calls are
+ * RECORDED instead of launched: every compute entry point returns a lazy array
+ * (shape, dtype and views work as usual; it has no value yet) and appends a node
+ * to the program.  hb_lazy_end runs the rewriter over the recorded DAG:
+ *   - chains of affine sgather (i + j windows, constant window tables), views,
+ *     broadcast `*`, ssum/ssumN, sdot1In and affine sscatter are composed
+ *     symbolically into ONE index-affine contraction and matched against
+ *     conv2dPreservingS / its dKrn / its dInp (CommonShapedOps.hs:136-157,
+ *     TestConvQuickCheck.hs:290-349)             -> hb_conv2d_preserving*;
+ *   - the [0.0,1.0]-table gather with `ifH (0 <=. negate x) 0 1` times x  -> relu;
+ *     sgather at `kargMax` of the window tensor   -> max-pool; their adjoint
+ *     scatters -> hb_relu_pool_bwd; conv + bias + relu + pool -> hb_conv_relu_pool_*;
+ *   - dead nodes are dropped, taddTarget runs in place where its operand dies.
+ * hb_lazy_run replays the rewritten program (eagerly, or inside
+ * hb_graph_begin/end to bake it into a CUDA graph); the handles passed as `outs`
+ * hold the results after each run.  Values of lazy arrays other than `outs` are
+ * never materialised.  Entry points that need a value on the host
+ * (hb_to_host, hb_scalar_to_host, hb_compare_all) are refused while recording. */
+typedef struct hb_lazy hb_lazy;
+#define HB_LAZY_REWRITE 1u      /* run the contraction pass (0: replay as recorded) */
+#define HB_LAZY_NO_FUSE_LAYER 2u /* keep conv / relu+pool as separate nodes */
+int hb_lazy_begin(void);
+int hb_lazy_end(int n_out, hb_array *const *outs, unsigned flags, hb_lazy **prog);
+int hb_lazy_abort(void);
+int hb_lazy_run(hb_lazy *prog);
+int hb_lazy_free(hb_lazy *prog);
+/* nodes recorded / nodes left after the pass */
+int hb_lazy_stats(const hb_lazy *prog, int *recorded, int *live);
+/* Text listing of the rewritten program and of the pass's decisions. */
+int hb_lazy_dump(const hb_lazy *prog, char *buf, size_t len);
+/* Initialise WITHOUT a device: constants live in host memory and compute entry
+ * points can only be recorded, never run.  For exercising the contraction pass
+ * on a box without a GPU (the CPU-side tests); mutually exclusive with hb_init. */
+int hb_init_trace_only(void);
+
 /* -------------------------------------------------------------- distributed
  * Data-parallel gradient exchange: NCCL over NVLink/NVSwitch,
  * resolved at run time with dlopen("libnccl.so.2"). */

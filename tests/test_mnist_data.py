@@ -79,8 +79,10 @@ def test_device_batches_equal_the_oracle_bit_for_bit(dev, dtype, order_dtype):
     order = None
     if order_dtype is not None:
         order = MD.shuffle_order(64, 3).astype(order_dtype)
-        order[5], order[17] = -3, 64                      # out-of-range ids -> zeros
-        data.set_order(order)
+        order[5], order[17] = -3, 64                      # out-of-range ids -> zeros (the kernel's own rule)
+        with pytest.raises(ValueError, match="sample ids"):
+            data.set_order(order)                         # the host-side check refuses them ...
+        data.set_order(order, validate=False)             # ... unless it is switched off
     for batch in (1, 7, 16):
         for k in range(data.n_batches(batch)):
             g, t = data.batch(k, batch, dtype)
