@@ -7,9 +7,15 @@ samples/s at 1/2/4/8 B200; conv VJP achieved HBM GB/s").
 A "step" is one pass of the hot path over one batch of synthetic MNIST-shaped
 input: the MnistCnnShaped2 gradient program (example/MnistCnnShaped2.hs:111-136)
 interpreted over the device carrier + one all-reduce of the gradient bucket +
-the Adam step (OptimizerTools.hs:134-232).  Per-GPU batch 4096 (BASELINE
-config 4); with N GPUs every rank owns 4096 samples (weak scaling; `--scaling
-strong` shards ONE batch of 4096 instead).  One JSON line on stdout (rank 0).
+the Adam step (OptimizerTools.hs:134-232).  The program handed to the C ABI is
+the UNCHANGED vectorised one (gather chains, sdot1In over broadcast views,
+kargMax gathers, scatters: `CnnTrainer(program="vectorised")`); the library
+records it once, its contraction pass rewrites it into fused nodes, and the
+step replays the result inside a CUDA graph.  Batch 4096 (BASELINE config 4) is
+SHARDED over the N GPUs (`--scaling strong`, the default: 4096/N samples per
+rank, as SURVEY.md 8d-4 prescribes); `--scaling weak` gives every rank 4096
+samples, and at N > 1 the default run reports that line too under
+`weak_scaling`.  One JSON line on stdout (rank 0).
 
 `value`  : samples/s with the minibatch already resident in HBM.
 `e2e`    : the same through the public call `CnnTrainer.train_step(host ptrs)`:
@@ -236,7 +242,8 @@ def run_reference(args, rank, world):
 
 def config_dict(args, world):
     local = PER_GPU_BATCH if args.scaling == "weak" else PER_GPU_BATCH // world
-    return {"workload": "MnistCnnShaped2 training step (convMnistLossFusedS gradient + Adam), synthetic MNIST 28x28",
+    return {"workload": "MnistCnnShaped2 training step (convMnistLossFusedS gradient + Adam), synthetic MNIST 28x28; "
+                        "batch 4096 sharded over the GPUs" + ("" if args.scaling == "strong" else " -- WEAK: 4096 per GPU"),
             "per_gpu_batch": local, "global_batch": local * world,
             "hyper": "kh=kw=4 (5x5 kernels), c_out=16, n_hidden=64",
             "parallelism": f"dp{world}", "optimizer": "adam",
@@ -251,7 +258,10 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"])
+    ap.add_argument("--program", default="vectorised", choices=["vectorised", "vectorised-eager", "fused"],
+                    help="what the step hands to the C ABI (see CnnTrainer)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the drop-in / hand-fused / weak-scaling side measurements")
     ap.add_argument("--cpu-sample", type=int, default=8192, help="samples per step of the bounded CPU-baseline sample")
     ap.add_argument("--cpu-workers", type=int, default=0, help="host processes of the CPU baseline (0 = all cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -329,7 +339,7 @@ def main():
 
     local_batch = PER_GPU_BATCH if args.scaling == "weak" else PER_GPU_BATCH // world
     global_batch = local_batch * world
-    tr = CnnTrainer(dev, local_batch, **HYPER, world=world, use_graph=not args.no_graph)
+    tr = CnnTrainer(dev, local_batch, **HYPER, world=world, use_graph=not args.no_graph, program=args.program)
     rng = np.random.Generator(np.random.Philox(42 + 1000 * rank))
     gl = PinnedBuffer((local_batch, 28, 28), np.float64)
     lb = PinnedBuffer((local_batch, 10), np.float64)
@@ -415,9 +425,59 @@ def main():
     barrier()
     del dmn
 
+    # ---- cross-rank consistency: after the timed loops every rank must hold bit-identical parameters
+    # (replicated weights + identical all-reduced bucket + identical Adam step)
+    import hashlib
+    digest = hashlib.sha256(np.concatenate([p.reshape(-1) for p in tr.get_params()]).tobytes()).hexdigest()
+    params_identical = True
+    if dist is not None:
+        objs = [None] * world
+        dist.all_gather_object(objs, digest)
+        params_identical = len(set(objs)) == 1
+        if not params_identical:
+            raise SystemExit(f"[rank {rank}] parameters differ across ranks after the timed loop: {objs}")
+    pass_stats = tr.prog.stats if tr.prog is not None else None
+
+    # ---- side measurements (every rank runs them: the step contains the all-reduce)
+    def time_program(program, steps, warm, batch=None, graph=True):
+        t2 = CnnTrainer(dev, batch or local_batch, **HYPER, world=world, use_graph=graph, program=program)
+        g2, l2 = gl, lb
+        if batch and batch != local_batch:
+            g2 = PinnedBuffer((batch, 28, 28), np.float64)
+            l2 = PinnedBuffer((batch, 10), np.float64)
+            g2.array[...] = rng.uniform(0, 1, g2.array.shape)
+            l2.array[...] = np.eye(10)[rng.integers(0, 10, batch)]
+        t2.upload(g2.ptr, l2.ptr)
+        for _ in range(warm):
+            t2.step_enqueue()
+        barrier()
+        ffi.call("hb_event_record", 4)
+        for i in range(steps):
+            if i % RESET_EVERY == 0:
+                t2.reset()
+            b2 = t2.step_enqueue()
+        ffi.call("hb_event_record", 5)
+        m2 = C.c_float()
+        ffi.call("hb_event_elapsed_ms", 4, 5, C.byref(m2))
+        l = t2.loss_of(b2)
+        t2.close()
+        del t2
+        return max_over_ranks(float(m2.value)) / steps, l
+    extras = {}
+    if not args.no_extras and args.program == "vectorised":
+        # the same recorded calls launched op by op as they arrive, WITHOUT the contraction pass: the raw drop-in step
+        extras["dropin_unfused_ms"], l_raw = time_program("vectorised-eager", 2, 1, graph=False)
+        # round 1's hand-fused model (fused=True above the ABI): what the pass has to reach
+        extras["hand_fused_ms"], l_fused = time_program("fused", min(K, 20), 3)
+        extras["loss_check"] = {"rewritten": loss_resident, "hand_fused": l_fused, "unfused_eager": l_raw}
+        if world > 1 and args.scaling == "strong":
+            wms, _ = time_program("vectorised", min(K, 20), 3, batch=PER_GPU_BATCH)
+            extras["weak_scaling"] = {"per_gpu_batch": PER_GPU_BATCH, "ms_per_step": wms,
+                                      "value": PER_GPU_BATCH * world / (wms * 1e-3), "unit": "samples/s"}
+
     # ---- live per-kernel timing of the same step (eager, events per launch);
     # every rank runs it (the step contains the all-reduce), rank 0 reports
-    prof = profile_step(dev, ffi, CnnTrainer, local_batch, gl, lb, world)
+    prof = profile_step(dev, ffi, CnnTrainer, local_batch, gl, lb, world, program=args.program)
     barrier()
     dbg("profile done")
     if rank != 0:
@@ -453,7 +513,11 @@ def main():
         "loss_resident": loss_resident if np.isfinite(loss_resident) else None,
         "roofline": roof, "breakdown": breakdown,
         "fp64_peak_tflops": {"dmma": fp64_dmma.value, "dfma": fp64_fma.value, "how": "hb_microbench, this run"},
+        "program": args.program,
+        "contraction_pass": ({"recorded_nodes": pass_stats[0], "nodes_after_pass": pass_stats[1]} if pass_stats else None),
+        "params_identical_across_ranks": params_identical,
     }
+    out.update(extras)
     if not args.no_conv_vjp:
         out["conv_vjp"] = conv_vjp_bench(dev, ffi, hbm_peak, fp64_peak)
     if not args.no_cpu_baseline and world == 1:
@@ -465,9 +529,9 @@ def main():
         dist.destroy_process_group()
 
 
-def profile_step(dev, ffi, CnnTrainer, local_batch, gl, lb, world, steps=3):
-    """Per-launch CUDA-event timing of the eager (non-graph) step."""
-    tr = CnnTrainer(dev, local_batch, **HYPER, world=world, use_graph=False)
+def profile_step(dev, ffi, CnnTrainer, local_batch, gl, lb, world, steps=3, program="vectorised"):
+    """Per-launch CUDA-event timing of the step replayed node by node (no CUDA graph)."""
+    tr = CnnTrainer(dev, local_batch, **HYPER, world=world, use_graph=False, program=program)
     tr.upload(gl.ptr, lb.ptr)
     for _ in range(2):
         tr.step_enqueue()
@@ -505,6 +569,18 @@ def ncu_traffic(entry: str, site: str):
     return None
 
 
+def issued_ratio(tag: str, kh1: int) -> float:
+    """Fraction of the nominal conv flops whose tap row meets the image at all (the DMMA kernels skip the others)."""
+    name, dt, a, b = _shapes(tag)
+    if a is None or not name.startswith("conv"):
+        return 1.0
+    H = a[2] if name in ("conv_relu_pool_bwd", "conv2d_preserving_dkrn") else (b[2] if b else a[2])
+    KH = a[2] if name in ("conv2d_preserving", "conv2d_preserving_dinp", "conv_relu_pool_fwd") else kh1
+    if not H or not KH:
+        return 1.0
+    return sum(max(0, H - k) for k in range(KH)) / (H * KH)
+
+
 def roofline_of(rows, hbm_peak, peak_src, fp64_peak):
     kh1 = kw1 = HYPER["kh"] + 1
     total = sum(r["ms_per_step"] for r in rows)
@@ -524,7 +600,9 @@ def roofline_of(rows, hbm_peak, peak_src, fp64_peak):
         ridge = fp64_peak * 1e12 / (hbm_peak * 1e9)
         if ai > ridge:
             roof.update({"bound": "tensor", "achieved": tfs, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": tfs / fp64_peak, "peak_source": "hb_microbench FP64 (DMMA/DFMA) this run; "
+                         "frac": tfs / fp64_peak, "frac_issued": tfs * issued_ratio(top["entry"], kh1) / fp64_peak,
+                         "frac_issued_note": "flops of the DMMAs actually issued (tap rows that only meet the zero "
+                                             "padding are skipped: sum_kh (H - kh) / (H KH) of the nominal ones) / peak", "peak_source": "hb_microbench FP64 (DMMA/DFMA) this run; "
                          "MEASURED_PEAKS.json has no FP64 figure", "algorithmic_flops": fl,
                          "hbm_view": {"achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
                                       "algorithmic_bytes": by, "peak_source": peak_src}})

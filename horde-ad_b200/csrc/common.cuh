@@ -137,6 +137,8 @@ struct hb_prof_scope {
     cudaError_t e_ = cudaPeekAtLastError();                            \
     if (e_ != cudaSuccess) {                                           \
       cudaGetLastError();                                              \
+      if (g_hb.trace_only)                                             \
+        HB_FAIL(HB_ERR_UNSUPPORTED, "%s: trace-only mode has no device to run on (record the call instead)", __func__); \
       HB_FAIL(HB_ERR_CUDA, "kernel launch failed: %s (%s:%d)",         \
               cudaGetErrorString(e_), __FILE__, __LINE__);             \
     }                                                                  \

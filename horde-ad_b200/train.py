@@ -1,7 +1,7 @@
 """Batch-sharded MNIST CNN training loop over the device carrier (SURVEY.md 8e;
 BASELINE.json config 4): every rank owns batch/world samples, interprets the
-same gradient program (the fused nodes of the device contraction pass) over
-its shard, and ONE all-reduce of the flattened gradient bucket (plus the loss
+same gradient program (the unchanged vectorised program, rewritten into fused nodes by the library's
+contraction pass) over its shard, and ONE all-reduce of the flattened gradient bucket (plus the loss
 in its last slot) over NVLink precedes the identical Adam step on every rank.
 
 The whole step (gradient program + bucket + all-reduce + optimizer) is
@@ -96,8 +96,20 @@ def _devptr(t: DeviceArray) -> C.c_void_p:
 
 
 class CnnTrainer:
+    """`program` selects what is handed to the C ABI each step:
+      "vectorised" (default) -- the UNCHANGED program horde-ad sends: chained i+j gathers, sdot1In over broadcast
+          views, [0.0,1.0]-table relu masks, kargMax gathers and their adjoint scatters (`fused=False` model +
+          the dual-number sweep of ad.py).  It is RECORDED once through the C ABI (hb_lazy_begin/end), rewritten by
+          the library's contraction pass into whole-layer nodes, and replayed (inside a CUDA graph);
+      "vectorised-eager"     -- the same calls launched op by op as they arrive (no pass): the raw drop-in cost;
+      "fused"                -- round 1's hand-fused model (`fused=True`): the pass's target, kept as a cross-check."""
+
     def __init__(self, dev: DeviceBackend, local_batch: int, kh=4, kw=4, c_out=16, n_hidden=64,
-                 dtype=np.float64, world=1, seed=44, use_graph=True, optimizer="adam", gamma=0.02):
+                 dtype=np.float64, world=1, seed=44, use_graph=True, optimizer="adam", gamma=0.02,
+                 program="vectorised"):
+        assert program in ("vectorised", "vectorised-eager", "fused")
+        self.program = program
+        self.prog = None
         self.dev, self.B, self.world, self.dtype = dev, local_batch, world, np.dtype(dtype)
         self.optimizer, self.gamma = optimizer, gamma
         self.hyper = (kh, kw, c_out, n_hidden)
@@ -130,8 +142,9 @@ class CnnTrainer:
     # ---- one step, enqueued op by op -------------------------------------
     def _gradient_program(self):
         dev = self.dev
+        fused = self.program == "fused"
         loss, grads = ad.grad(
-            dev, lambda T, *ps: mnist_cnn.convMnistLossFusedS(T, self.glyphs, self.labels, list(ps), fused=True),
+            dev, lambda T, *ps: mnist_cnn.convMnistLossFusedS(T, self.glyphs, self.labels, list(ps), fused=fused),
             self.params)
         bucket = dev.flatten_concat(list(grads) + [loss])
         call("hb_allreduce_sum", bucket.h, exchange_scale(self.world))
@@ -149,12 +162,19 @@ class CnnTrainer:
     def step_enqueue(self):
         """Enqueue one training step on the inputs currently in self.glyphs /
         self.labels; returns the bucket whose last element is the mean loss."""
-        if self.use_graph:
+        if self.use_graph and self.program != "vectorised-eager":
             if self.graph is None:
                 self._capture()
             call("hb_graph_launch", self.graph)
             if self.optimizer == "adam":
                 self._apply(self.bucket)
+            return self.bucket
+        if self.program == "vectorised":        # the rewritten program, replayed node by node (no CUDA graph)
+            if self.prog is None:
+                self.prog = self.dev.record(self._gradient_program)
+                self.bucket = self.prog.outs[0]
+            self.prog.run()
+            self._apply(self.bucket)
             return self.bucket
         bucket = self._gradient_program()
         self._apply(bucket)
@@ -162,6 +182,23 @@ class CnnTrainer:
         return bucket
 
     def _capture(self):
+        if self.program == "vectorised":
+            # record the unchanged program once (nothing is launched), let the library's contraction pass rewrite
+            # it, run the result once eagerly (allocations, scratch, NCCL channels), then bake it into a graph
+            self.prog = self.dev.record(self._gradient_program)
+            self.bucket = self.prog.outs[0]
+            self.prog.run()
+            self.dev.sync()
+            call("hb_graph_begin")
+            try:
+                self.prog.run()
+                if self.optimizer != "adam":
+                    self._apply(self.bucket)
+            finally:
+                g = C.c_void_p()
+                call("hb_graph_end", C.byref(g))
+            self.graph = g
+            return
         # run once eagerly so every size class and the scratch buffer exist
         # (and NCCL has set up its channels before the all-reduce is captured)
         b = self._gradient_program()
@@ -233,6 +270,9 @@ class CnnTrainer:
         if self.graph is not None:
             call("hb_graph_free", self.graph)
             self.graph = None
+        if self.prog is not None:
+            self.prog.close()
+            self.prog = None
 
 
 def comm_init(rank: int, world: int, broadcast_bytes) -> None:

@@ -1,0 +1,187 @@
+"""The device contraction pass (hb_lazy_*, csrc/lazy.cu + lazy_rewrite.cu) on the device:
+the UNCHANGED vectorised program -- chained i+j gathers, sdot1In over broadcast views, [0.0,1.0]-table relu masks,
+kargMax gathers and their adjoint scatters, exactly what horde-ad's interpreter sends -- recorded through the C ABI,
+rewritten, replayed, and compared with (a) the same program run eagerly op by op, (b) the hand-fused program and
+(c) the CPU oracle's UNFUSED program."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from horde_ad_b200 import ad, ffi, mnist_cnn, nn
+
+pytestmark = pytest.mark.gpu
+
+
+def _cnn_inputs(batch, hyper, seed=42):
+    rng = np.random.Generator(np.random.Philox(seed))
+    params = mnist_cnn.init_params(*hyper)
+    glyphs = rng.uniform(0, 1, (batch, 28, 28))
+    labels = np.eye(10)[rng.integers(0, 10, batch)]
+    return params, glyphs, labels
+
+
+def _bucket(B, params, glyphs, labels, fused):
+    loss, grads = ad.grad(B, lambda T, *ps: mnist_cnn.convMnistLossFusedS(T, glyphs, labels, list(ps), fused=fused), params)
+    return B.flatten_concat(list(grads) + [loss]) if hasattr(B, "flatten_concat") else \
+        np.concatenate([np.asarray(g).reshape(-1) for g in grads] + [np.asarray(loss).reshape(1)])
+
+
+def test_replay_without_the_pass_is_the_eager_program_bit_for_bit(dev):
+    params, glyphs, labels = _cnn_inputs(5, (2, 2, 3, 6))
+    dp = [dev.sconcrete(p) for p in params]
+    g, l = dev.sconcrete(glyphs), dev.sconcrete(labels)
+    eager = dev.to_numpy(_bucket(dev, dp, g, l, False))
+    prog = dev.record(lambda: _bucket(dev, dp, g, l, False), rewrite=False)
+    rec, live = prog.stats
+    assert rec >= live > 40
+    prog.run()
+    got = dev.to_numpy(prog.outs[0])
+    assert np.array_equal(got, eager)
+    prog.run()                                   # replays rebind their outputs
+    assert np.array_equal(dev.to_numpy(prog.outs[0]), eager)
+
+
+@pytest.mark.parametrize("batch,hyper", [(6, (2, 2, 4, 8)), (33, (4, 4, 16, 16)), (8, (2, 3, 5, 7))])
+def test_contraction_pass_on_the_vectorised_cnn_gradient(dev, oracle, batch, hyper):
+    params, glyphs, labels = _cnn_inputs(batch, hyper)
+    dp = [dev.sconcrete(p) for p in params]
+    g, l = dev.sconcrete(glyphs), dev.sconcrete(labels)
+    prog = dev.record(lambda: _bucket(dev, dp, g, l, False))
+    text = prog.dump()
+    rec, live = prog.stats
+    # both conv layers and both adjoints were recognised, whole-layer nodes emitted, gathers / scatters gone
+    assert text.count("conv_relu_pool_fwd f64") == 2 and text.count("conv_relu_pool_bwd f64") == 2, text
+    body = text.split("--")[0]
+    assert "gather" not in body.replace("%21 gather", "") or body.count(" gather ") <= 1, text   # only the dense layer's mask
+    assert " scatter_add " not in body and " dot_inner" not in body, text
+    assert live <= 24 < rec
+    prog.run()
+    got = dev.to_numpy(prog.outs[0])
+    eager_unfused = dev.to_numpy(_bucket(dev, dp, g, l, False))        # the recorded program, run op by op
+    fused = dev.to_numpy(_bucket(dev, dp, g, l, True))                # the hand-fused model of round 1
+    ref = _bucket(oracle, [oracle.sconcrete(p) for p in params], glyphs, labels, False)   # oracle, UNFUSED
+    scale = np.maximum(np.abs(ref), 1e-3 * np.max(np.abs(ref)))
+    assert np.max(np.abs(got - ref) / scale) < 1e-10
+    assert np.max(np.abs(got - eager_unfused) / scale) < 1e-10
+    # same kernels as the hand-fused program: bit-identical
+    assert np.array_equal(got, fused)
+    # data-movement parts of the recorded program are exact: max-pool routing picks the same elements
+    nz_ref, nz_got = ref != 0, got != 0
+    assert np.array_equal(nz_ref, nz_got)
+
+
+def test_pass_without_layer_fusion_keeps_conv_and_pool_nodes_apart(dev, oracle):
+    params, glyphs, labels = _cnn_inputs(7, (2, 2, 4, 8))
+    dp = [dev.sconcrete(p) for p in params]
+    g, l = dev.sconcrete(glyphs), dev.sconcrete(labels)
+    prog = dev.record(lambda: _bucket(dev, dp, g, l, False), fuse_layers=False)
+    body = prog.dump().split("--")[0]
+    for name in ("conv2d_preserving f64", "conv2d_dkrn f64", "conv2d_dinp f64", "relu_pool_fwd f64", "relu_pool_bwd f64"):
+        assert name in body, (name, body)
+    prog.run()
+    ref = _bucket(oracle, [oracle.sconcrete(p) for p in params], glyphs, labels, False)
+    got = dev.to_numpy(prog.outs[0])
+    scale = np.maximum(np.abs(ref), 1e-3 * np.max(np.abs(ref)))
+    assert np.max(np.abs(got - ref) / scale) < 1e-10
+
+
+def test_conv_vjp_patterns_alone(dev, oracle):
+    """ConvVjpBench's three programs (bench/ConvVjpBench.hs:428-555): the vectorised forward, and the dual-number
+    adjoints w.r.t. kernel and input, each recorded on its own and rewritten to one conv node."""
+    rng = np.random.default_rng(3)
+    N, Ci, Co, H, W, KH, KW = 3, 5, 6, 9, 11, 3, 2
+    K, A, dB = rng.uniform(-.5, .5, (Co, Ci, KH, KW)), rng.uniform(-.5, .5, (N, Ci, H, W)), rng.uniform(-.5, .5, (N, Co, H, W))
+    dK_, dA_, dB_ = dev.sconcrete(K), dev.sconcrete(A), dev.sconcrete(dB)
+    fwd = dev.record(lambda: nn.conv2dPreservingS_vectorised(dev, dK_, dA_))
+    assert "conv2d_preserving f64" in fwd.dump() and fwd.stats[1] == 1, fwd.dump()
+    fwd.run()
+    np.testing.assert_allclose(dev.to_numpy(fwd.outs[0]), oracle.conv2dPreserving(K, A), rtol=1e-12, atol=1e-13)
+
+    def vjp():
+        _, (gk, ga) = ad.grad(dev, lambda T, k, a: nn.conv2dPreservingS_vectorised(T, k, a), [dK_, dA_], dt=dB_)
+        return [gk, ga]
+    bwd = dev.record(vjp)
+    text = bwd.dump()
+    assert "conv2d_dkrn f64" in text and "conv2d_dinp f64" in text, text
+    bwd.run()
+    np.testing.assert_allclose(dev.to_numpy(bwd.outs[0]), oracle.conv2d_dkrn(A, dB, KH, KW), rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(dev.to_numpy(bwd.outs[1]), oracle.conv2d_dinp(K, dB), rtol=1e-12, atol=1e-13)
+
+
+def test_unmatched_programs_are_left_alone(dev, oracle):
+    """Patterns that only LOOK like the fused forms must not be rewritten: a stride-3 window over a 2-wide pool,
+    a gather with an offset, a `valid` (non-preserving) window."""
+    rng = np.random.default_rng(8)
+    x = rng.uniform(-1, 1, (4, 3, 12, 12))
+    dx = dev.sconcrete(x)
+    # windows at stride 3 with 2x2 extent: not maxPool k k
+    th = dev.sconcrete((3 * np.arange(4)[:, None] + np.arange(2)[None, :]).astype(np.int64))
+
+    def odd_pool():
+        xt = dev.stranspose([2, 3, 0, 1], nn.reluS_vectorised(dev, dx))
+        win = dev.sgather([4, 4, 2, 2], xt, lambda ix: [dev.ix_tbl(th, [ix[0], ix[2]]), dev.ix_tbl(th, [ix[1], ix[3]])], 2)
+        u = dev.sreshape([4, 3, 4, 4, 4], dev.stranspose([4, 5, 0, 1, 2, 3], win))
+        return dev.sgather([4, 3, 4, 4], u, lambda ix: [ix[0], ix[1], ix[2], ix[3], dev.ix_argmax(u, ix)], 5)
+    p = dev.record(odd_pool)
+    assert "relu_pool_fwd" not in p.dump()
+    p.run()
+    got = dev.to_numpy(p.outs[0])
+    r = np.maximum(x, 0)
+    ref = np.stack([[r[:, :, 3 * i:3 * i + 2, 3 * j:3 * j + 2].max(axis=(2, 3)) for j in range(4)] for i in range(4)])
+    np.testing.assert_array_equal(got, np.transpose(ref, (2, 3, 0, 1)))
+    # shifted window i + j + 1: not conv2dPreservingS
+    K = dev.sconcrete(rng.uniform(-1, 1, (2, 3, 2, 2)))
+
+    def shifted():
+        g1 = dev.sgather([12, 2], dev.stranspose([2, 0, 1, 3], dx), lambda ix: [ix[0] + ix[1] + 1], 1)
+        g2 = dev.sgather([12, 2], dev.stranspose([4, 0, 1, 2, 3], g1), lambda ix: [ix[0] + ix[1]], 1)
+        pt = dev.stranspose([1, 2, 3, 0], dev.sreplicate(2, dev.stranspose([5, 3, 4, 2, 0, 1], g2)))
+        k = dev.stranspose([3, 4, 0, 5, 1, 2], dev.sreplicateN([4, 12, 12], dev.stranspose([1, 2, 0, 3], K)))
+        return dev.ssumN(dev.sdot1In(pt, k), 2)
+    q = dev.record(shifted)
+    assert "conv2d" not in q.dump().split("--")[0]
+    q.run()
+    eager = dev.to_numpy(shifted())
+    assert np.array_equal(dev.to_numpy(q.outs[0]), eager)
+
+
+def test_lazy_program_inside_a_cuda_graph_follows_new_inputs(dev, oracle):
+    params, glyphs, labels = _cnn_inputs(6, (2, 2, 4, 8))
+    dp = [dev.sconcrete(p) for p in params]
+    g, l = dev.sconcrete(glyphs), dev.sconcrete(labels)
+    prog = dev.record(lambda: _bucket(dev, dp, g, l, False))
+    prog.run()
+    first = dev.to_numpy(prog.outs[0])
+    dev.sync()
+    ffi.call("hb_graph_begin")
+    try:
+        prog.run()
+    finally:
+        gr = C.c_void_p()
+        ffi.call("hb_graph_end", C.byref(gr))
+    ffi.call("hb_graph_launch", gr)
+    assert np.array_equal(dev.to_numpy(prog.outs[0]), first)
+    g2 = np.ascontiguousarray(glyphs[::-1])
+    dev.upload_into(g, g2.ctypes.data_as(C.c_void_p))
+    dev.sync()
+    ffi.call("hb_graph_launch", gr)
+    second = dev.to_numpy(prog.outs[0])
+    ref = _bucket(oracle, [oracle.sconcrete(p) for p in params], g2, labels, False)
+    scale = np.maximum(np.abs(ref), 1e-3 * np.max(np.abs(ref)))
+    assert np.max(np.abs(second - ref) / scale) < 1e-10 and not np.array_equal(first, second)
+    ffi.call("hb_graph_free", gr)
+
+
+def test_values_are_refused_while_recording(dev):
+    x = dev.sconcrete(np.arange(6.0))
+    ffi.call("hb_lazy_begin")
+    try:
+        y = dev.binary("add", x, x)
+        with pytest.raises(ffi.HordeError, match="lazy value"):
+            dev.to_numpy(y)
+        with pytest.raises(ffi.HordeError, match="cannot be recorded"):
+            dev.all_eq(x, x)
+    finally:
+        ffi.call("hb_lazy_abort")
+    assert dev.to_numpy(dev.binary("add", x, x)).tolist() == [0, 2, 4, 6, 8, 10]
