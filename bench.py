@@ -459,7 +459,8 @@ def main():
         ffi.call("hb_event_record", 5)
         m2 = C.c_float()
         ffi.call("hb_event_elapsed_ms", 4, 5, C.byref(m2))
-        l = t2.loss_of(b2)
+        t2.reset()                      # loss of the FIRST step from the initial parameters: comparable across programs
+        l = t2.loss_of(t2.step_enqueue())
         t2.close()
         del t2
         return max_over_ranks(float(m2.value)) / steps, l
@@ -469,7 +470,10 @@ def main():
         extras["dropin_unfused_ms"], l_raw = time_program("vectorised-eager", 2, 1, graph=False)
         # round 1's hand-fused model (fused=True above the ABI): what the pass has to reach
         extras["hand_fused_ms"], l_fused = time_program("fused", min(K, 20), 3)
-        extras["loss_check"] = {"rewritten": loss_resident, "hand_fused": l_fused, "unfused_eager": l_raw}
+        tr.reset()
+        l_rew = tr.loss_of(tr.step_enqueue())
+        extras["first_step_loss"] = {"rewritten": l_rew, "hand_fused": l_fused, "unfused_eager": l_raw,
+                                     "what": "same inputs, initial parameters: the three programs compute one value"}
         if world > 1 and args.scaling == "strong":
             wms, _ = time_program("vectorised", min(K, 20), 3, batch=PER_GPU_BATCH)
             extras["weak_scaling"] = {"per_gpu_batch": PER_GPU_BATCH, "ms_per_step": wms,
