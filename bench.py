@@ -261,6 +261,8 @@ def main():
     ap.add_argument("--scaling", default="strong", choices=["weak", "strong"])
     ap.add_argument("--program", default="vectorised", choices=["vectorised", "vectorised-eager", "fused"],
                     help="what the step hands to the C ABI (see CnnTrainer)")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
+                    help="gradient exchange: the one-kernel peer-memory all-reduce + Adam, or ncclAllReduce + scale + Adam")
     ap.add_argument("--no-extras", action="store_true", help="skip the drop-in / hand-fused / weak-scaling side measurements")
     ap.add_argument("--cpu-sample", type=int, default=8192, help="samples per step of the bounded CPU-baseline sample")
     ap.add_argument("--cpu-workers", type=int, default=0, help="host processes of the CPU baseline (0 = all cores)")
@@ -339,7 +341,8 @@ def main():
 
     local_batch = PER_GPU_BATCH if args.scaling == "weak" else PER_GPU_BATCH // world
     global_batch = local_batch * world
-    tr = CnnTrainer(dev, local_batch, **HYPER, world=world, use_graph=not args.no_graph, program=args.program)
+    tr = CnnTrainer(dev, local_batch, **HYPER, world=world, use_graph=not args.no_graph, program=args.program,
+                    exchange=args.exchange)
     rng = np.random.Generator(np.random.Philox(42 + 1000 * rank))
     gl = PinnedBuffer((local_batch, 28, 28), np.float64)
     lb = PinnedBuffer((local_batch, 10), np.float64)
@@ -439,8 +442,9 @@ def main():
     pass_stats = tr.prog.stats if tr.prog is not None else None
 
     # ---- side measurements (every rank runs them: the step contains the all-reduce)
-    def time_program(program, steps, warm, batch=None, graph=True):
-        t2 = CnnTrainer(dev, batch or local_batch, **HYPER, world=world, use_graph=graph, program=program)
+    def time_program(program, steps, warm, batch=None, graph=True, exchange=None):
+        t2 = CnnTrainer(dev, batch or local_batch, **HYPER, world=world, use_graph=graph, program=program,
+                        exchange=exchange or args.exchange)
         g2, l2 = gl, lb
         if batch and batch != local_batch:
             g2 = PinnedBuffer((batch, 28, 28), np.float64)
@@ -474,6 +478,11 @@ def main():
         l_rew = tr.loss_of(tr.step_enqueue())
         extras["first_step_loss"] = {"rewritten": l_rew, "hand_fused": l_fused, "unfused_eager": l_raw,
                                      "what": "same inputs, initial parameters: the three programs compute one value"}
+        if world > 1:
+            # the same step with ncclAllReduce + scale kernel + Adam kernel instead of the fused exchange kernel
+            other = "nccl" if args.exchange == "fused" else "fused"
+            extras["exchange_comparison"] = {"this_run": args.exchange, "other": other,
+                                             "other_ms_per_step": time_program("vectorised", min(K, 20), 3, exchange=other)[0]}
         if world > 1 and args.scaling == "strong":
             wms, _ = time_program("vectorised", min(K, 20), 3, batch=PER_GPU_BATCH)
             extras["weak_scaling"] = {"per_gpu_batch": PER_GPU_BATCH, "ms_per_step": wms,
@@ -481,7 +490,7 @@ def main():
 
     # ---- live per-kernel timing of the same step (eager, events per launch);
     # every rank runs it (the step contains the all-reduce), rank 0 reports
-    prof = profile_step(dev, ffi, CnnTrainer, local_batch, gl, lb, world, program=args.program)
+    prof = profile_step(dev, ffi, CnnTrainer, local_batch, gl, lb, world, program=args.program, exchange=args.exchange)
     barrier()
     dbg("profile done")
     if rank != 0:
@@ -517,7 +526,7 @@ def main():
         "loss_resident": loss_resident if np.isfinite(loss_resident) else None,
         "roofline": roof, "breakdown": breakdown,
         "fp64_peak_tflops": {"dmma": fp64_dmma.value, "dfma": fp64_fma.value, "how": "hb_microbench, this run"},
-        "program": args.program,
+        "program": args.program, "exchange": args.exchange,
         "contraction_pass": ({"recorded_nodes": pass_stats[0], "nodes_after_pass": pass_stats[1]} if pass_stats else None),
         "params_identical_across_ranks": params_identical,
     }
@@ -533,9 +542,9 @@ def main():
         dist.destroy_process_group()
 
 
-def profile_step(dev, ffi, CnnTrainer, local_batch, gl, lb, world, steps=3, program="vectorised"):
+def profile_step(dev, ffi, CnnTrainer, local_batch, gl, lb, world, steps=3, program="vectorised", exchange="fused"):
     """Per-launch CUDA-event timing of the step replayed node by node (no CUDA graph)."""
-    tr = CnnTrainer(dev, local_batch, **HYPER, world=world, use_graph=False, program=program)
+    tr = CnnTrainer(dev, local_batch, **HYPER, world=world, use_graph=False, program=program, exchange=exchange)
     tr.upload(gl.ptr, lb.ptr)
     for _ in range(2):
         tr.step_enqueue()

@@ -9,6 +9,9 @@
 // process, if any.
 #include <dlfcn.h>
 
+#include <algorithm>
+#include <vector>
+
 #include "common.cuh"
 #include "lazy.cuh"
 
@@ -22,6 +25,7 @@ static struct {
   ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
   ncclComm_t comm = nullptr;
@@ -39,6 +43,7 @@ static int load_nccl() {
   SYM(GetUniqueId, "ncclGetUniqueId")
   SYM(CommInitRank, "ncclCommInitRank")
   SYM(AllReduce, "ncclAllReduce")
+  SYM(AllGather, "ncclAllGather")
   SYM(CommDestroy, "ncclCommDestroy")
   SYM(GetErrorString, "ncclGetErrorString")
 #undef SYM
@@ -60,18 +65,22 @@ extern "C" int hb_comm_unique_id(void *id_bytes) {
   return HB_OK;
 }
 
+static int fcomm_setup(size_t cap_bytes);
+
 extern "C" int hb_comm_init(int rank, int world, const void *id_bytes) {
   HB_CHECK_INIT();
   HB_REQUIRE(world >= 1 && rank >= 0 && rank < world, "comm: rank %d of %d", rank, world);
   g_nccl.rank = rank;
   g_nccl.world = world;
-  if (world == 1) return HB_OK;
+  if (world == 1) return fcomm_setup(0);
   HB_REQUIRE(id_bytes, "null unique id");
   HB_TRY(load_nccl());
   ncclUniqueId id;
   memcpy(&id, id_bytes, HB_UNIQUE_ID_BYTES);
   HB_NCCL(g_nccl.CommInitRank(&g_nccl.comm, world, id, rank));
-  return HB_OK;
+  // peer-mapped exchange buffers of the fused all-reduce + optimizer kernel (32 MB per parity: every model of the
+  // reference's examples fits -- MnistFcnnRanked2 at 1500|500 has 1.93 M parameters = 15.4 MB in Double)
+  return fcomm_setup((size_t)32 << 20);
 }
 
 template <typename T>
@@ -108,7 +117,207 @@ extern "C" int hb_allreduce_sum(hb_array *bucket, double scale) {
   return HB_OK;
 }
 
+// ------------------------------------------------- fused exchange + optimizer
+// ONE kernel per training step does what ncclAllReduce + hb_scale_kernel + hb_adam_kernel did in three launches
+// (65 us + 2 launches for a 0.46 MB bucket at 8 GPUs, the top entry of the strong-scaling step in round 1):
+//   every rank publishes its gradient bucket in a peer-mapped buffer (cudaIpc over NVLink 5 / NVSwitch: every GPU
+//   reaches every peer at full bandwidth), raises a per-chunk flag in every peer's memory, waits for the peers'
+//   flags, then PULLS the G buckets with plain peer loads and adds them in rank order 0..G-1 -- the same order on
+//   every rank, so the reduced bucket (and therefore the replicated parameters) are bit-identical across ranks and
+//   across runs, independently of NCCL's algorithm choice -- scales by 1/G and applies the Adam update
+//   (OptimizerTools.hs:134-232) to its replica in the same pass.
+// Chunk c of rank A only ever waits for chunk c of the peers (no grid-wide barrier); buckets are double-buffered
+// by step parity, so one flag round per step is the only synchronisation: a rank reaches step e+2 (which overwrites
+// the parity-e buffer) only after its step e+1 kernel saw every peer's e+1 flags, i.e. after every peer finished
+// its step-e kernel and with it all reads of the parity-e buffers.
+// The step counter of Adam lives on the device (a CUDA graph replays the launch unchanged).
+#define HB_COMM_MAXCHUNKS 64
+struct hb_fcomm {
+  int rank = 0, world = 1;
+  char *buf[8] = {};                  // peer-mapped: [2 parities][cap bytes]
+  unsigned long long *flags[8] = {};  // peer-mapped: [world][HB_COMM_MAXCHUNKS] step numbers
+  unsigned long long *ctl = nullptr;  // local: [0] = steps completed, [1] = CTAs done in the running step
+  size_t cap = 0;
+};
+static hb_fcomm g_fc;
+static void *g_fc_block = nullptr;
+static void *g_fc_peer[8] = {};
+static bool g_fc_ready = false;
+static unsigned long long *g_fc_ctl_single = nullptr;   // world == 1: only the control words
+
+__device__ __forceinline__ void hb_st_release_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long hb_ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+template <typename T>
+__device__ __forceinline__ T hb_ld_peer(const T *p) {  // peer memory: never from a stale L1 line
+  return *(const volatile T *)p;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+    hb_allreduce_adam_kernel(hb_fcomm C, T *__restrict__ bucket, int64_t n, int64_t n_params, T *__restrict__ p,
+                             T *__restrict__ m, T *__restrict__ v, long long *__restrict__ tcount, double alpha,
+                             double beta1, double beta2, double epsilon, T scale) {
+  const int c = blockIdx.x, nchunks = gridDim.x;
+  const unsigned long long e = *(volatile unsigned long long *)&C.ctl[0] + 1;   // this step's number
+  const long long t = *(volatile long long *)tcount + 1;                        // Adam's step count after increment
+  const int64_t per = ((n + nchunks - 1) / nchunks + 1) & ~(int64_t)1;
+  const int64_t lo = min((int64_t)c * per, n), hi = min(lo + per, n);
+  const int par = (int)(e & 1);
+  if (C.world > 1) {
+    T *mine = (T *)(C.buf[C.rank] + (size_t)par * C.cap);
+    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) mine[i] = bucket[i];
+    __syncthreads();
+    if (threadIdx.x == 0) __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < C.world && threadIdx.x != C.rank)
+      hb_st_release_sys(C.flags[threadIdx.x] + (size_t)C.rank * HB_COMM_MAXCHUNKS + c, e);
+    if (threadIdx.x < C.world && threadIdx.x != C.rank) {
+      const unsigned long long *f = C.flags[C.rank] + (size_t)threadIdx.x * HB_COMM_MAXCHUNKS + c;
+      while (hb_ld_acquire_sys(f) < e) __nanosleep(64);
+    }
+    __syncthreads();
+  }
+  const T one = (T)1;
+  const double alphat_d = alpha * sqrt(1.0 - hb_powi_ghc(beta2, t)) / (1.0 - hb_powi_ghc(beta1, t));
+  const T alphat = (T)alphat_d, b1 = (T)beta1, b2 = (T)beta2, eps = (T)epsilon;
+  for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    T acc;
+    if (C.world > 1) {
+      acc = (T)0;
+      for (int r = 0; r < C.world; r++)   // fixed rank order: bit-identical on every rank
+        acc = acc + (r == C.rank ? bucket[i] : hb_ld_peer((const T *)(C.buf[r] + (size_t)par * C.cap) + i));
+    } else {
+      acc = bucket[i];
+    }
+    acc = acc * scale;
+    bucket[i] = acc;
+    if (i < n_params) {
+      T mn = b1 * m[i] + (one - b1) * acc;
+      T vn = b2 * v[i] + (one - b2) * (acc * acc);
+      m[i] = mn;
+      v[i] = vn;
+      p[i] = p[i] - alphat * mn / (sqrt(vn) + eps);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&C.ctl[1], 1ull) == (unsigned long long)nchunks - 1) {   // last chunk of this rank: close the step
+      C.ctl[1] = 0;
+      *tcount = t;
+      __threadfence();
+      *(volatile unsigned long long *)&C.ctl[0] = e;
+    }
+  }
+}
+
+// Set up the peer-mapped buffers: collective over the communicator (called from hb_comm_init).
+static int fcomm_setup(size_t cap_bytes) {
+  g_fc = hb_fcomm();
+  g_fc.rank = g_nccl.rank;
+  g_fc.world = g_nccl.world;
+  g_fc.cap = cap_bytes;
+  const size_t flag_bytes = (size_t)8 * HB_COMM_MAXCHUNKS * sizeof(unsigned long long);
+  const size_t ctl_bytes = 256;
+  if (g_nccl.world == 1) {
+    if (!g_fc_ctl_single) {
+      HB_CUDA(cudaMalloc((void **)&g_fc_ctl_single, ctl_bytes));
+      HB_CUDA(cudaMemset(g_fc_ctl_single, 0, ctl_bytes));
+    }
+    g_fc.ctl = g_fc_ctl_single;
+    g_fc_ready = true;
+    return HB_OK;
+  }
+  HB_REQUIRE(g_nccl.world <= 8, "fused exchange: at most 8 ranks of one NVSwitch domain (have %d)", g_nccl.world);
+  const size_t total = flag_bytes + ctl_bytes + 2 * cap_bytes;
+  HB_CUDA(cudaMalloc(&g_fc_block, total));
+  HB_CUDA(cudaMemset(g_fc_block, 0, total));
+  // the block is zero before its handle leaves this process: a peer can only raise a flag in it after the exchange
+  HB_CUDA(cudaDeviceSynchronize());
+  // exchange the IPC handles through the communicator itself
+  cudaIpcMemHandle_t mine;
+  HB_CUDA(cudaIpcGetMemHandle(&mine, g_fc_block));
+  char *dsend = nullptr, *drecv = nullptr;
+  HB_CUDA(cudaMalloc((void **)&dsend, sizeof mine));
+  HB_CUDA(cudaMalloc((void **)&drecv, sizeof mine * g_nccl.world));
+  HB_CUDA(cudaMemcpy(dsend, &mine, sizeof mine, cudaMemcpyHostToDevice));
+  HB_NCCL(g_nccl.AllGather(dsend, drecv, sizeof mine, /*ncclInt8*/ 0, g_nccl.comm, g_hb.stream));
+  HB_CUDA(cudaStreamSynchronize(g_hb.stream));
+  std::vector<cudaIpcMemHandle_t> all(g_nccl.world);
+  HB_CUDA(cudaMemcpy(all.data(), drecv, sizeof mine * g_nccl.world, cudaMemcpyDeviceToHost));
+  cudaFree(dsend);
+  cudaFree(drecv);
+  for (int r = 0; r < g_nccl.world; r++) {
+    void *base = g_fc_block;
+    if (r != g_nccl.rank) {
+      HB_CUDA(cudaIpcOpenMemHandle(&base, all[r], cudaIpcMemLazyEnablePeerAccess));
+      g_fc_peer[r] = base;
+    }
+    g_fc.flags[r] = (unsigned long long *)base;
+    g_fc.buf[r] = (char *)base + flag_bytes + ctl_bytes;
+  }
+  g_fc.ctl = (unsigned long long *)((char *)g_fc_block + flag_bytes);
+  g_fc_ready = true;
+  return HB_OK;
+}
+
+static void fcomm_teardown() {
+  for (int r = 0; r < 8; r++)
+    if (g_fc_peer[r]) {
+      cudaIpcCloseMemHandle(g_fc_peer[r]);
+      g_fc_peer[r] = nullptr;
+    }
+  if (g_fc_block) cudaFree(g_fc_block);
+  g_fc_block = nullptr;
+  g_fc_ready = false;
+}
+
+extern "C" int hb_allreduce_adam_step(hb_array *bucket, int64_t n_params, hb_array *p, hb_array *m, hb_array *v,
+                                      hb_array *t_counter, double alpha, double beta1, double beta2,
+                                      double epsilon, double scale) {
+  hb_prof_scope prof_("allreduce_adam_step", bucket);
+  HB_CHECK_INIT_LAZY();
+  HB_REQUIRE(bucket && p && m && v && t_counter, "null argument");
+  HB_REQUIRE(hb_contig(bucket) && hb_contig(p) && hb_contig(m) && hb_contig(v), "allreduce_adam: contiguous arrays required");
+  HB_REQUIRE(hb_is_float(bucket->dt) && p->dt == bucket->dt && m->dt == bucket->dt && v->dt == bucket->dt,
+             "allreduce_adam: one floating dtype required");
+  HB_REQUIRE(t_counter->dt == HB_I64 && hb_numel(t_counter) == 1, "allreduce_adam: the step counter is a 0-d I64 array");
+  int64_t n = hb_numel(bucket);
+  HB_REQUIRE(n_params >= 0 && n_params <= n && hb_numel(p) == n_params && hb_numel(m) == n_params && hb_numel(v) == n_params,
+             "allreduce_adam: %lld parameters, bucket of %lld, state of %lld", (long long)n_params, (long long)n,
+             (long long)hb_numel(p));
+  if (hb_lazy_on())
+    return hb_lrec(HB_L_EFFECT, "allreduce_adam_step").in(bucket).in(p).in(m).in(v).in(t_counter).commit(
+        [=](hb_lnode &, hb_array *const *in, hb_array **) {
+          return hb_allreduce_adam_step(in[0], n_params, in[1], in[2], in[3], in[4], alpha, beta1, beta2, epsilon, scale);
+        });
+  HB_REQUIRE(!g_hb.trace_only, "allreduce_adam: trace-only mode has no device to run on");
+  if (n == 0) return HB_OK;
+  if (!g_fc_ready) HB_TRY(fcomm_setup(0));   // single process without hb_comm_init
+  HB_REQUIRE(g_fc.world == 1 || (size_t)n * hb_dtype_size(bucket->dt) <= g_fc.cap,
+             "allreduce_adam: bucket of %lld bytes exceeds the exchange buffer (%zu)", (long long)n * 8, g_fc.cap);
+  // chunks: enough CTAs to saturate the links on a MB-sized bucket, few enough that all are co-resident
+  int chunks = (int)std::min<int64_t>(HB_COMM_MAXCHUNKS, std::max<int64_t>(1, n / 2048));
+  if (bucket->dt == HB_F64)
+    hb_allreduce_adam_kernel<double><<<chunks, 256, 0, g_hb.stream>>>(
+        g_fc, (double *)hb_data(bucket), n, n_params, (double *)hb_data(p), (double *)hb_data(m), (double *)hb_data(v),
+        (long long *)hb_data(t_counter), alpha, beta1, beta2, epsilon, scale);
+  else
+    hb_allreduce_adam_kernel<float><<<chunks, 256, 0, g_hb.stream>>>(
+        g_fc, (float *)hb_data(bucket), n, n_params, (float *)hb_data(p), (float *)hb_data(m), (float *)hb_data(v),
+        (long long *)hb_data(t_counter), alpha, beta1, beta2, epsilon, (float)scale);
+  HB_LAUNCHED();
+  return HB_OK;
+}
+
 extern "C" int hb_comm_destroy(void) {
+  fcomm_teardown();
   if (g_nccl.comm) {
     g_nccl.CommDestroy(g_nccl.comm);
     g_nccl.comm = nullptr;

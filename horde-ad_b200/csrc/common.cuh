@@ -153,6 +153,25 @@ static inline size_t hb_dtype_size(hb_dtype dt) {
     default: return 1;
   }
 }
+// x ^ y for y >= 1 exactly as GHC's (^) computes it (GHC.Real.powImpl / powImplAcc: binary exponentiation, a
+// fixed sequence of multiplications) -- updateWithGradientAdam's `betaOne ^ tAdamNew` (OptimizerTools.hs:154-155)
+// is therefore reproduced bit for bit on the host, in device code and in the oracle.
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+static inline double hb_powi_ghc(double x, long long y) {
+  if (y <= 0) return 1.0;
+  while ((y & 1) == 0) { x = x * x; y >>= 1; }
+  if (y == 1) return x;
+  double z = x;               // powImplAcc (x*x) (y `quot` 2) x
+  x = x * x; y >>= 1;
+  for (;;) {
+    if ((y & 1) == 0) { x = x * x; y >>= 1; continue; }
+    if (y == 1) return x * z;
+    z = x * z; x = x * x; y >>= 1;
+  }
+}
+
 static inline bool hb_is_float(hb_dtype dt) { return dt == HB_F64 || dt == HB_F32; }
 static inline const char *hb_dtype_name(hb_dtype dt) {
   static const char *n[] = {"f64", "f32", "i64", "i32", "i16", "i8", "bool"};

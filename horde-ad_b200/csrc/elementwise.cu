@@ -771,7 +771,7 @@ extern "C" int hb_adam_step(hb_array *p, hb_array *m, hb_array *v, const hb_arra
     HB_TRY(hb_contiguous(g, &tmp));
     gc = tmp;
   }
-  double alphat = alpha * sqrt(1.0 - pow(beta2, (double)t)) / (1.0 - pow(beta1, (double)t));
+  double alphat = alpha * sqrt(1.0 - hb_powi_ghc(beta2, t)) / (1.0 - hb_powi_ghc(beta1, t));
   int st = HB_OK;
   switch (p->dt) {
     case HB_F64:

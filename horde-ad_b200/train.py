@@ -106,9 +106,14 @@ class CnnTrainer:
 
     def __init__(self, dev: DeviceBackend, local_batch: int, kh=4, kw=4, c_out=16, n_hidden=64,
                  dtype=np.float64, world=1, seed=44, use_graph=True, optimizer="adam", gamma=0.02,
-                 program="vectorised"):
+                 program="vectorised", exchange="fused"):
         assert program in ("vectorised", "vectorised-eager", "fused")
+        assert exchange in ("fused", "nccl")
         self.program = program
+        # "fused": gradient exchange + 1/world + Adam in ONE kernel over peer-mapped buffers (hb_allreduce_adam_step,
+        # deterministic rank-order sum, step counter on the device, so the whole step is one graph launch);
+        # "nccl": ncclAllReduce, then the scale kernel, then the Adam kernel (round 1's path, the comparison arm)
+        self.exchange = exchange if optimizer == "adam" else "nccl"
         self.prog = None
         self.dev, self.B, self.world, self.dtype = dev, local_batch, world, np.dtype(dtype)
         self.optimizer, self.gamma = optimizer, gamma
@@ -126,6 +131,8 @@ class CnnTrainer:
         self.glyphs = dev.sconcrete(np.zeros((local_batch, 28, 28), dtype))
         self.labels = dev.sconcrete(np.zeros((local_batch, 10), dtype))
         self.t = 0
+        self.t_dev = dev.sconcrete(np.zeros((), np.int64))     # Adam's step count on the device (fused exchange)
+        self._t0 = dev.sconcrete(np.zeros((), np.int64))
         self.graph = None
         # the graph holds the gradient program + bucket + all-reduce; Adam's
         # bias-corrected step size depends on t, so it is one eager launch after it
@@ -147,11 +154,18 @@ class CnnTrainer:
             dev, lambda T, *ps: mnist_cnn.convMnistLossFusedS(T, self.glyphs, self.labels, list(ps), fused=fused),
             self.params)
         bucket = dev.flatten_concat(list(grads) + [loss])
-        call("hb_allreduce_sum", bucket.h, exchange_scale(self.world))
+        if self.exchange == "fused":
+            call("hb_allreduce_adam_step", bucket.h, self.n_params, self.flat_p.h, self.flat_m.h, self.flat_v.h,
+                 self.t_dev.h, 1e-3, 0.9, 0.999, 1e-7, exchange_scale(self.world))
+        else:
+            call("hb_allreduce_sum", bucket.h, exchange_scale(self.world))
         return bucket
 
     def _apply(self, bucket):
         dev = self.dev
+        if self.exchange == "fused":
+            self.t += 1                  # the update itself happened inside the exchange kernel
+            return
         g = dev.sslice(0, self.n_params, bucket)
         if self.optimizer == "adam":
             self.t += 1
@@ -181,7 +195,27 @@ class CnnTrainer:
         self.bucket = bucket
         return bucket
 
+    def _state_snapshot(self):
+        """The warm-up run before a capture executes the whole step; with the fused exchange that includes the Adam
+        update, so the optimizer state is put back afterwards (four small device-to-device copies, once)."""
+        if self.exchange != "fused":
+            return None
+        return [self.dev.scontiguous(x) for x in (self.flat_p, self.flat_m, self.flat_v, self.t_dev)]   # fresh copies
+
+    def _state_restore(self, snap):
+        if snap is None:
+            return
+        for dst, src in zip((self.flat_p, self.flat_m, self.flat_v, self.t_dev), snap):
+            self.dev.upload_into(dst, _devptr(src))
+
     def _capture(self):
+        snap = self._state_snapshot()
+        try:
+            self._capture_inner()
+        finally:
+            self._state_restore(snap)
+
+    def _capture_inner(self):
         if self.program == "vectorised":
             # record the unchanged program once (nothing is launched), let the library's contraction pass rewrite
             # it, run the result once eagerly (allocations, scratch, NCCL channels), then bake it into a graph
@@ -261,6 +295,7 @@ class CnnTrainer:
         self.dev.upload_into(self.flat_p, _devptr(self._p0))
         self.dev.upload_into(self.flat_m, _devptr(self._z0))
         self.dev.upload_into(self.flat_v, _devptr(self._z0))
+        self.dev.upload_into(self.t_dev, _devptr(self._t0))
         self.t = 0
 
     def get_params(self):

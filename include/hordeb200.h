@@ -560,6 +560,20 @@ int hb_comm_init(int rank, int world, const void *id_bytes);
 /* In-place sum over all ranks of a contiguous array, then scale by `scale`
  * (1/world for the mean of per-shard mean gradients). */
 int hb_allreduce_sum(hb_array *bucket, double scale);
+/* The exchange AND the optimizer step in ONE kernel (no NCCL on the data path):
+ * every rank publishes `bucket` in a peer-mapped buffer (cudaIpc over NVLink /
+ * NVSwitch, set up by hb_comm_init), pulls the peers' buckets and adds them in
+ * rank order 0..G-1 -- the same order on every rank, so the result is
+ * bit-identical across ranks and runs -- scales by `scale`, writes the reduced
+ * bucket back in place, and applies updateWithGradientAdam
+ * (OptimizerTools.hs:134-232) to p, m, v with g = bucket[0 : n_params].
+ * `t_counter` (0-d I64 device array) is Adam's step count: incremented on the
+ * device, so the call can be replayed from a CUDA graph; `betaOne ^ t` is
+ * computed as GHC's (^) does.  World size 1 (or no communicator): scale + Adam. */
+int hb_allreduce_adam_step(hb_array *bucket, int64_t n_params, hb_array *p,
+                           hb_array *m, hb_array *v, hb_array *t_counter,
+                           double alpha, double beta1, double beta2,
+                           double epsilon, double scale);
 int hb_comm_destroy(void);
 
 /* -------------------------------------------------------- micro-benchmarks

@@ -34,6 +34,26 @@ def _is_float(a) -> bool:
     return np.issubdtype(a.dtype, np.floating)
 
 
+def _pow_ghc(x: float, y: int) -> float:
+    """`x ^ y` as GHC computes it (GHC.Real.powImpl / powImplAcc: binary exponentiation by a fixed sequence of
+    multiplications) -- the `betaOne ^ tAdamNew` of updateWithGradientAdam (OptimizerTools.hs:154-155)."""
+    x = float(x)
+    if y <= 0:
+        return 1.0
+    while y % 2 == 0:
+        x, y = x * x, y // 2
+    if y == 1:
+        return x
+    z, x, y = x, x * x, y // 2
+    while True:
+        if y % 2 == 0:
+            x, y = x * x, y // 2
+        elif y == 1:
+            return x * z
+        else:
+            z, x, y = x * z, x * x, y // 2
+
+
 class ConcreteBackend:
     """`target = Concrete` (CarriersConcrete.hs:150-155,293)."""
 
@@ -479,7 +499,7 @@ class ConcreteBackend:
     # updateWithGradientAdam (OptimizerTools.hs:134-232; defaults :83-89)
     def adam_step(self, p, m, v, g, t, alpha=1e-3, beta1=0.9, beta2=0.999, epsilon=1e-7):
         T = p.dtype.type
-        alphat = alpha * np.sqrt(1 - beta2 ** t) / (1 - beta1 ** t)
+        alphat = alpha * np.sqrt(1 - _pow_ghc(beta2, t)) / (1 - _pow_ghc(beta1, t))
         m[...] = T(beta1) * m + T(1 - beta1) * g
         v[...] = T(beta2) * v + T(1 - beta2) * (g * g)
         p[...] = p - (T(alphat) * m) / (np.sqrt(v) + T(epsilon))
