@@ -474,6 +474,7 @@ def main():
         extras["dropin_unfused_ms"], l_raw = time_program("vectorised-eager", 2, 1, graph=False)
         # round 1's hand-fused model (fused=True above the ABI): what the pass has to reach
         extras["hand_fused_ms"], l_fused = time_program("fused", min(K, 20), 3)
+        tr.upload(gl.ptr, lb.ptr)       # the e2e / device-pipeline loops left other batches in the input buffers
         tr.reset()
         l_rew = tr.loss_of(tr.step_enqueue())
         extras["first_step_loss"] = {"rewritten": l_rew, "hand_fused": l_fused, "unfused_eager": l_raw,

@@ -179,7 +179,12 @@ __global__ void __launch_bounds__(256)
       hb_st_release_sys(C.flags[threadIdx.x] + (size_t)C.rank * HB_COMM_MAXCHUNKS + c, e);
     if (threadIdx.x < C.world && threadIdx.x != C.rank) {
       const unsigned long long *f = C.flags[C.rank] + (size_t)threadIdx.x * HB_COMM_MAXCHUNKS + c;
-      while (hb_ld_acquire_sys(f) < e) __nanosleep(64);
+      // a peer that never arrives (crashed rank) must not hang the GPU: give up after ~10 s and fault the launch
+      const long long t0 = clock64();
+      while (hb_ld_acquire_sys(f) < e) {
+        __nanosleep(64);
+        if (clock64() - t0 > 20000000000ll) __trap();
+      }
     }
     __syncthreads();
   }

@@ -78,25 +78,20 @@ def _worker(rank, world, port, q):
     dist.all_gather_object(pall, res["fused"][0])
     out["params_identical_across_ranks"] = bool(all(np.array_equal(pall[0], p) for p in pall))
     # the exchanged bucket of the LAST step == mean of what each rank computes alone on its shard with the same weights
-    tr1 = CnnTrainer(dev, B, **hyper, world=1, exchange="nccl", optimizer="sgd", gamma=0.0, use_graph=False)
+    from horde_ad_b200 import ad, mnist_cnn
     tr0 = CnnTrainer(dev, B, **hyper, world=world, exchange="fused")
     for _ in range(4):
         tr0.train_step(gl.ptr, lb.ptr)
-    w = np.concatenate([p.reshape(-1) for p in tr0.get_params()])
-    tr1.dev.upload_into(tr1.flat_p, dev.sconcrete(w).h) if False else None
-    hw = dev.sconcrete(w)
-    ptr = C.c_void_p()
-    ffi.call("hb_device_ptr", hw.h, C.byref(ptr))
-    dev.upload_into(tr1.flat_p, ptr)
-    tr1.upload(gl.ptr, lb.ptr)
-    local = dev.to_numpy(tr1.step_enqueue())
+    tr0.upload(gl.ptr, lb.ptr)
+    loss, grads = ad.grad(dev, lambda T, *ps: mnist_cnn.convMnistLossFusedS(T, tr0.glyphs, tr0.labels, list(ps), fused=True),
+                          tr0.params)
+    local = dev.to_numpy(dev.flatten_concat(list(grads) + [loss]))       # no exchange: this rank's shard bucket
     tr0.train_step(gl.ptr, lb.ptr)
     exchanged = dev.to_numpy(tr0.bucket)
     locs = [None] * world
     dist.all_gather_object(locs, local)
     out["bucket_is_mean_of_shards"] = bool(np.allclose(exchanged, sum(locs) * exchange_scale(world), rtol=1e-13, atol=1e-300))
     tr0.close()
-    tr1.close()
     if rank == 0:
         q.put(out)
     dist.barrier()
