@@ -263,6 +263,8 @@ def main():
                     help="what the step hands to the C ABI (see CnnTrainer)")
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
                     help="gradient exchange: the one-kernel peer-memory all-reduce + Adam, or ncclAllReduce + scale + Adam")
+    ap.add_argument("--no-other-configs", action="store_true",
+                    help="skip the other BASELINE configs (LongProd, FCNN, RNN, secondary CNN, kernel families)")
     ap.add_argument("--no-extras", action="store_true", help="skip the drop-in / hand-fused / weak-scaling side measurements")
     ap.add_argument("--cpu-sample", type=int, default=8192, help="samples per step of the bounded CPU-baseline sample")
     ap.add_argument("--cpu-workers", type=int, default=0, help="host processes of the CPU baseline (0 = all cores)")
@@ -534,6 +536,34 @@ def main():
     out.update(extras)
     if not args.no_conv_vjp:
         out["conv_vjp"] = conv_vjp_bench(dev, ffi, hbm_peak, fp64_peak)
+    if not args.no_other_configs and world == 1:
+        # the other BASELINE configs (LongProdBench, ShortMnistForCI, RNN, secondary CNN, kernel families), each group
+        # with its own nvidia-smi clock samples: the numbers bench_configs.py prints, on the driver's record
+        import contextlib
+        import bench_configs
+        recs = []
+        cur = {"clk": None, "name": None, "first": 0}
+
+        @contextlib.contextmanager
+        def section(name):
+            smp = ClockSampler(local_rank)
+            smp.start()
+            first = len(recs)
+            try:
+                yield
+            finally:
+                dev.sync()
+                c = smp.stop()
+                for r in recs[first:]:
+                    r["section"] = name
+                    r["clocks"] = c
+        t0 = time.perf_counter()
+        try:
+            bench_configs.run_configs(dev, quick=False, emit=recs.append, section=section)
+        except Exception as e:        # a side measurement must not take the headline line down with it
+            recs.append({"config": "error", "error": repr(e)[:300]})
+        out["other_configs"] = recs
+        out["other_configs_wall_s"] = time.perf_counter() - t0
     if not args.no_cpu_baseline and world == 1:
         out["cpu_baseline"] = cpu_baseline(args.cpu_sample, args.cpu_workers)
     print(json.dumps(out), flush=True)

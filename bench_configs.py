@@ -56,7 +56,8 @@ def timed(dev, f, reps, warm=3):
     return ms.value / reps
 
 
-def families(dev, rng, hbm, src, quick):
+def families(dev, rng, hbm, src, quick, emit=None):
+    emit = emit or (lambda d: print(json.dumps(d), flush=True))
     """Achieved HBM GB/s of the data-parallel kernel families against their
     algorithmic bytes (SURVEY.md 8d table)."""
     from horde_ad_b200 import nn
@@ -70,7 +71,7 @@ def families(dev, rng, hbm, src, quick):
              "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm, "peak_source": src}}
         if extra:
             d.update(extra)
-        print(json.dumps(d), flush=True)
+        emit(d)
 
     report("binary add, contiguous f64 [2^26]", timed(dev, lambda: dev.binary("add", a, b), 10), 3 * 8 * n)
     report("unary exp, contiguous f64", timed(dev, lambda: dev.unary("exp", a), 10), 2 * 8 * n)
@@ -137,6 +138,31 @@ def families(dev, rng, hbm, src, quick):
            2 * 8 * (48 * 3 * 3 * 3 * 50 + 48 * 3 * 48 * 3 * 3 * 3), {"note": "L2-resident, launch-bound"})
 
 
+import contextlib
+
+
+@contextlib.contextmanager
+def _no_section(_name):
+    yield
+
+
+class _Sections:
+    """begin(name) closes the running section and opens the next one (the blocks below stay flat)."""
+
+    def __init__(self, factory):
+        self.factory, self.cur = factory, None
+
+    def begin(self, name):
+        self.end()
+        self.cur = self.factory(name)
+        self.cur.__enter__()
+
+    def end(self):
+        if self.cur is not None:
+            self.cur.__exit__(None, None, None)
+            self.cur = None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
@@ -144,19 +170,33 @@ def main():
     ap.add_argument("--only-families", action="store_true")
     args = ap.parse_args()
     dev = DeviceBackend(int(os.environ.get("LOCAL_RANK", "0")))
+    run_configs(dev, args.quick, args.skip_families, args.only_families)
+
+
+def run_configs(dev, quick=False, skip_families=False, only_families=False, emit=None, section=None):
+    """Runs every config; `emit(record)` receives one dict per measurement (default: print a JSON line), `section(name)`
+    is a context manager entered around each group (bench.py samples the GPU clocks inside it)."""
+    import types
+    args = types.SimpleNamespace(quick=quick, skip_families=skip_families, only_families=only_families)
+    emit = emit or (lambda d: print(json.dumps(d), flush=True))
+    section = section or _no_section
     hbm, src = peaks()
     fp64 = C.c_double()
     ffi.call("hb_microbench", 1, C.byref(fp64))
     rng = np.random.Generator(np.random.Philox(42))
     if args.only_families:
-        families(dev, rng, hbm, src, args.quick)
+        with section("kernel families"):
+            families(dev, rng, hbm, src, args.quick, emit)
         return
 
     # ------------------------------------------ HBM-bound kernel families (8a rows)
     if not args.skip_families:
-        families(dev, rng, hbm, src, args.quick)
+        with section("kernel families"):
+            families(dev, rng, hbm, src, args.quick, emit)
 
+    sec = _Sections(section)
     # ---------------------------------------------------------------- LongProd
+    sec.begin("LongProdBench")
     for n in ([10**6, 10**7] if args.quick else [10**6, 10**7, 10**8]):
         x = dev.sconcrete(np.exp(rng.uniform(-1e-3, 1e-3, n)))      # mean-zero log: the product stays finite
         ms = timed(dev, lambda: dev.prod_fold_grad(x, 1.0), 10 if n < 10**8 else 5)
@@ -166,13 +206,23 @@ def main():
         p = float(dev.kfromS(pr))
         err = float(np.max(np.abs(dev.to_numpy(chk) / p - 1.0)))
         gbs = 16.0 * n / (ms * 1e-3) / 1e9
-        print(json.dumps({"config": "LongProdBench", "n": n, "ms": ms, "algorithmic_bytes": 16 * n,
+        # the same through the PROGRAM the reference writes -- cgrad of `sfold (*) 1 x` -- whose step function the
+        # carrier recognises (nn.sfold); includes the probe recording and the host read of the 0-d cotangent
+        from horde_ad_b200 import nn
+
+        def via_program():
+            return ad.grad(dev, lambda T, t: nn.sfold(T, lambda a, e: T.binary("mul", a, e), T.sscalar(1.0), t), [x])
+        ms_prog = timed(dev, via_program, 5, warm=1)
+        emit(({"config": "LongProdBench", "n": n, "ms": ms, "ms_via_sfold_program": ms_prog, "algorithmic_bytes": 16 * n,
+               "hbm_traffic_note": "a prefix AND a suffix product are needed: x is read twice unless it fits in L2 "
+                                   "(16 n bytes of HBM traffic for n <= ~1.5e7, 24 n above)",
                           "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
                                        "peak_source": src},
-                          "max_rel_err_of_g_i_times_x_i_vs_prod": err}), flush=True)
+                          "max_rel_err_of_g_i_times_x_i_vs_prod": err}))
         del x, pr, g, chk
 
     # ----------------------------------------------------------- ShortMnistForCI
+    sec.begin("ShortMnistForCI")
     for (h1, h2) in ([(300, 100)] if args.quick else [(30, 10), (300, 100), (500, 150), (1500, 500)]):
         params = [dev.sconcrete(p) for p in mnist_fcnn.init_params(h1, h2)]
         datum = dev.sconcrete(rng.uniform(0, 1, 784))
@@ -200,14 +250,15 @@ def main():
         ffi.call("hb_graph_free", gph)
         nparam = sum(int(np.prod(p.shape)) for p in params)
         by = 3 * sum(int(np.prod(p.shape)) * p.dtype.itemsize for p in params)   # W read fwd + bwd, dW write
-        print(json.dumps({"config": "ShortMnistForCI / MnistFcnnRanked2", "widths": [h1, h2], "batch": 1,
+        emit(({"config": "ShortMnistForCI / MnistFcnnRanked2", "widths": [h1, h2], "batch": 1,
                           "parameters": nparam, "ms_per_sample_eager": eager_ms, "ms_per_sample_graph": graph_ms,
                           "samples_per_s_graph": 1e3 / graph_ms,
                           "roofline": {"bound": "hbm", "achieved": by / (graph_ms * 1e-3) / 1e9, "peak": hbm,
                                        "unit": "GB/s", "frac": by / (graph_ms * 1e-3) / 1e9 / hbm, "peak_source": src,
-                                       "note": "batch 1: launch-latency bound by construction"}}), flush=True)
+                                       "note": "batch 1: launch-latency bound by construction"}}))
 
     # ---------------------------------- secondary CNN config
+    sec.begin("MnistCnnShaped2 secondary")
     # (kh,kw,c_out,n_hidden) = (2,2,64,128): 3x3 kernels, 64 channels (aligned with ConvVjpBench)
     from horde_ad_b200.train import CnnTrainer
     B2 = 512 if args.quick else 4096
@@ -229,24 +280,26 @@ def main():
     # conv flops (in-bounds taps ~ nominal): layer 1 1->64 at 28x28, layer 2 64->64 at 14x14, 3x3; fwd + dK (+ dInp for layer 2)
     fl = 2.0 * B2 * 9 * (2 * 64 * 784 + 3 * 64 * 64 * 196) + 3 * 2.0 * B2 * (128 * 64 * 49 + 10 * 128)
     tf = fl / (ms * 1e-3) / 1e12
-    print(json.dumps({"config": "MnistCnnShaped2 secondary", "hyper": {"kh": 2, "kw": 2, "c_out": 64, "n_hidden": 128},
+    emit(({"config": "MnistCnnShaped2 secondary", "hyper": {"kh": 2, "kw": 2, "c_out": 64, "n_hidden": 128},
                       "per_gpu_batch": B2, "parameters": tr.n_params, "ms_per_step": ms, "samples_per_s": B2 / (ms * 1e-3),
                       "roofline": {"bound": "tensor", "achieved": tf, "peak": fp64.value, "unit": "TFLOP/s",
                                    "frac": tf / fp64.value, "peak_source": "hb_microbench FP64 DMMA, this run",
-                                   "algorithmic_flops": fl}}), flush=True)
+                                   "algorithmic_flops": fl}}))
     tr.close()
     del tr
 
     # -------------------------------------------------------------------- GEMM
+    sec.begin("smatmul2")
     m, k, n = 512, 512, (2048 if args.quick else 8192)
     a, b = dev.sconcrete(rng.uniform(-.5, .5, (m, k))), dev.sconcrete(rng.uniform(-.5, .5, (k, n)))
     ms = timed(dev, lambda: dev.smatmul2(a, b), 20)
     tf = 2.0 * m * k * n / (ms * 1e-3) / 1e12
-    print(json.dumps({"config": "smatmul2", "shape": [m, k, n], "ms": ms,
+    emit(({"config": "smatmul2", "shape": [m, k, n], "ms": ms,
                       "roofline": {"bound": "tensor", "achieved": tf, "peak": fp64.value, "unit": "TFLOP/s",
-                                   "frac": tf / fp64.value, "peak_source": "hb_microbench FP64 DMMA, this run"}}), flush=True)
+                                   "frac": tf / fp64.value, "peak_source": "hb_microbench FP64 DMMA, this run"}}))
 
     # --------------------------------------------------------------------- RNN
+    sec.begin("MnistRnnShaped2")
     width, batch = 512, (256 if args.quick else 1024)
     params = [dev.sconcrete(p) for p in mnist_rnn.init_params(width, rng_range=0.05)]
     glyphs = dev.sconcrete(rng.uniform(0, 1, (batch, 28, 28)))
@@ -289,12 +342,14 @@ def main():
     # flops: per time step 2 layers x (W_x x + W_s s), fwd + 2x bwd
     fl = 28 * 3 * 2.0 * batch * (28 * width + 3 * width * width)
     tf = fl / (step_ms * 1e-3) / 1e12
-    print(json.dumps({"config": "MnistRnnShaped2", "width": width, "seq": 28, "per_gpu_batch": batch, "ms_per_step": step_ms,
+    emit(({"config": "MnistRnnShaped2", "width": width, "seq": 28, "per_gpu_batch": batch, "ms_per_step": step_ms,
                       "ms_per_step_eager": eager_ms,
                       "samples_per_s": batch / (step_ms * 1e-3), "loss": loss if np.isfinite(loss) else None,
                       "roofline": {"bound": "tensor", "achieved": tf, "peak": fp64.value, "unit": "TFLOP/s",
                                    "frac": tf / fp64.value, "peak_source": "hb_microbench FP64 DMMA, this run",
-                                   "algorithmic_flops": fl}}), flush=True)
+                                   "algorithmic_flops": fl}}))
+    sec.end()
+
 
 
 if __name__ == "__main__":

@@ -347,7 +347,12 @@ extern "C" int hb_lazy_dump(const hb_lazy *P, char *buf, size_t len) {
   std::string s;
   for (const hb_lnode *n : P->nodes) {
     if (n->dead) continue;
-    s += "%" + std::to_string(n->id) + " " + n->name + " ";
+    s += "%" + std::to_string(n->id) + " " + n->name;
+    if (n->op == HB_L_BINARY) {
+      static const char *bn[] = {"add", "sub", "mul", "divide", "power", "logbase", "atan2", "quot", "rem", "max", "min"};
+      s += std::string(".") + (n->ia[0] >= 0 && n->ia[0] < 11 ? bn[n->ia[0]] : "?");
+    }
+    s += " ";
     for (size_t k = 0; k < n->out.size(); k++) s += (k ? "," : "") + (n->out[k] ? hb_dtype_name(n->out[k]->dt) + hb_shape_str(n->out[k]) : std::string("-"));
     s += " <-";
     for (const hb_array *a : n->in) s += " " + describe(a);

@@ -155,6 +155,7 @@ class DeviceBackend:
     name = "device"
 
     def __init__(self, device: int | None = None, trace_only: bool = False):
+        self.trace_only = trace_only
         self.device = ffi.init_trace_only() if trace_only else ffi.init(device)
 
     # ------------------------------------------------------- lazy programs
@@ -492,6 +493,10 @@ class DeviceBackend:
         call("hb_softmax_xent", logits.h, expected.h, float(scale), C.byref(l),
              C.byref(d) if want_grad else None)
         return _wrap(l), (_wrap(d) if want_grad else None)
+
+    def prod_fold(self, x):
+        """sfold (*) 1 x (forward value; the AD carrier attaches the scan-based reverse rule)."""
+        return self.prod_fold_grad(x, 1.0, want_grad=False)[0]
 
     def prod_fold_grad(self, x, dt=1.0, want_grad=True):
         pr, g = _out(), _out()

@@ -174,8 +174,49 @@ def smapAccumL(T, f, acc0, es):
     return acc, (T.sfromVector(bs) if bs else None)
 
 
+def _step_is_product(T, f, acc0, es) -> bool:
+    """Is the fold's step function `\\acc e -> acc * e` (or `e * acc`)?
+
+    horde-ad hands `tmapAccumL` its step as a function value (an `HFun`, Ops.hs:1106-1125); a device instance can
+    look inside it.  Here the step is a Python closure, and it is reified the same way index functions are
+    (option A): it is applied ONCE to two 0-d probes while the library RECORDS instead of
+    launching (hb_lazy_begin / hb_lazy_end); the step is the product iff the recording is exactly one
+    `binary.mul` of the two probes.  Only device carriers can record; everything else folds on the host."""
+    base = getattr(T, "B", T)
+    if not hasattr(base, "record") or not hasattr(T, "prod_fold"):
+        return False
+    sh = T.shape(es)
+    if len(sh) != 1 or len(T.shape(acc0)) != 0 or np.dtype(T.dtype(es)).kind != "f":
+        return False
+    dt = T.dtype(es)
+    pa, pe = base.sscalar(2.0, dt), base.sscalar(3.0, dt)
+    try:
+        prog = base.record(lambda: getattr(T, "primal", lambda x: x)(f(T.sfromPrimal(pa) if hasattr(T, "sfromPrimal") else pa,
+                                                                  T.sfromPrimal(pe) if hasattr(T, "sfromPrimal") else pe)),
+                           rewrite=False)
+    except Exception:       # the step does something that cannot be recorded (needs a value on the host, ...)
+        return False
+    lines = [ln for ln in prog.dump().split("--")[0].strip().splitlines() if ln]
+    rec, _ = prog.stats
+    ok = rec == 1 and len(lines) == 1 and lines[0].split()[1] == "binary.mul" and lines[0].count("<-const") == 2
+    # the two operands must be the two probes (not the same probe twice): distinguishable by evaluating once
+    if ok and not getattr(base, "trace_only", False):
+        try:
+            prog.run()
+            ok = float(base.kfromS(prog.outs[0])) == 6.0
+        except Exception:
+            ok = False
+    prog.close()
+    return ok
+
+
 def sfold(T, f, acc0, es):
-    """sfold / rfold (Ops.hs:188-210): left fold of f :: acc -> e -> acc."""
+    """sfold / rfold (Ops.hs:188-210): left fold of f :: acc -> e -> acc.  `sfold (*) acc0 es` (LongProdBench,
+    bench/common/BenchProdTools.hs:154-182) is recognised from its step function and runs as the product-scan
+    kernel (hb_prod_fold_grad) instead of n host iterations; every other step folds on the host like the reference
+    (tmapAccumLC, OpsConcrete.hs:990-1019)."""
+    if _step_is_product(T, f, acc0, es):
+        return T.binary("mul", acc0, T.prod_fold(es))
     return smapAccumL(T, lambda a, e: (f(a, e), None), acc0, es)[0]
 
 

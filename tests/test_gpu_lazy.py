@@ -186,3 +186,51 @@ def test_values_are_refused_while_recording(dev):
     finally:
         ffi.call("hb_lazy_abort")
     assert dev.to_numpy(dev.binary("add", x, x)).tolist() == [0, 2, 4, 6, 8, 10]
+
+
+def test_sfold_product_is_recognised_from_its_step_function(dev, oracle):
+    """`sfold (*) 1 x` (LongProdBench, bench/common/BenchProdTools.hs:154-182): the step closure is reified by
+    recording it once (nn._step_is_product) and the fold runs as the product-scan kernel; the oracle runs the
+    reference's n sequential host iterations.  Other steps are NOT mistaken for a product."""
+    rng = np.random.default_rng(5)
+    x = np.exp(rng.uniform(-1e-2, 1e-2, 3000))
+    for step in (lambda T: (lambda a, e: T.binary("mul", a, e)), lambda T: (lambda a, e: T.binary("mul", e, a))):
+        n0 = C.c_uint64()
+        ffi.call("hb_launch_count", C.byref(n0))
+        dv, (dg,) = ad.grad(dev, lambda T, t: nn.sfold(T, step(T), T.sscalar(1.0), t), [dev.sconcrete(x)])
+        n1 = C.c_uint64()
+        ffi.call("hb_launch_count", C.byref(n1))
+        assert n1.value - n0.value < 40, "the fold ran as a host loop"          # not 3000 iterations
+        ov, (og,) = ad.grad(oracle, lambda T, t: nn.sfold(T, step(T), T.sscalar(1.0), t), [oracle.sconcrete(x)])
+        np.testing.assert_allclose(float(dev.kfromS(dv)), float(ov), rtol=1e-12)
+        np.testing.assert_allclose(dev.to_numpy(dg), np.asarray(og), rtol=1e-11)
+    assert nn._step_is_product(dev, lambda a, e: dev.binary("mul", a, e), dev.sscalar(1.0), dev.sconcrete(x))
+    assert not nn._step_is_product(dev, lambda a, e: dev.binary("add", a, e), dev.sscalar(1.0), dev.sconcrete(x))
+    assert not nn._step_is_product(dev, lambda a, e: dev.binary("mul", a, a), dev.sscalar(1.0), dev.sconcrete(x))
+    assert not nn._step_is_product(dev, lambda a, e: dev.binary("mul", dev.binary("mul", a, e), e), dev.sscalar(1.0), dev.sconcrete(x))
+    xs = x[:40]
+    f = lambda T: (lambda a, e: T.binary("add", T.binary("mul", a, e), e))
+    dv, (dg,) = ad.grad(dev, lambda T, t: nn.sfold(T, f(T), T.sscalar(1.0), t), [dev.sconcrete(xs)])
+    ov, (og,) = ad.grad(oracle, lambda T, t: nn.sfold(T, f(T), T.sscalar(1.0), t), [oracle.sconcrete(xs)])
+    np.testing.assert_allclose(dev.to_numpy(dg), np.asarray(og), rtol=1e-12)
+
+
+@pytest.mark.parametrize("n", [1, 7, 2048, 2049, 100_003, 3_000_017])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_fused_product_scan_kernel(dev, n, dtype):
+    """The one-launch persistent product scan (phase A tile products, grid barrier, phase B gradient): values against
+    a float64 host fold, the size-independent identity g_i * x_i = prod, exact zeros, and equality with the
+    four-launch pipeline of round 1 is not required (different association), only the tolerance."""
+    rng = np.random.default_rng(n)
+    x = np.exp(rng.uniform(-3e-3, 3e-3, n)).astype(dtype)
+    pr, g = dev.prod_fold_grad(dev.sconcrete(x), 1.5)
+    p64 = float(np.prod(x.astype(np.float64)))
+    tol = 1e-12 if dtype == np.float64 else 3e-5
+    np.testing.assert_allclose(float(dev.kfromS(pr)), p64, rtol=tol * max(1, np.sqrt(n) / 30))
+    got = dev.to_numpy(g).astype(np.float64)
+    np.testing.assert_allclose(got * x.astype(np.float64), 1.5 * p64, rtol=tol * max(1, np.sqrt(n) / 30))
+    if n >= 7:
+        x[3] = 0.0
+        _, g0 = dev.prod_fold_grad(dev.sconcrete(x), 1.0)
+        g0 = dev.to_numpy(g0)
+        assert np.count_nonzero(g0) == 1 and g0[3] != 0        # no division: exact zeros everywhere else
