@@ -272,6 +272,8 @@ def main():
     ap.add_argument("--no-conv-vjp", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--breakdown-file", default=None, help="write the full per-launch-site table of one step here")
+    ap.add_argument("--shard-batch", type=int, default=0,
+                    help="diagnostic: run THIS many samples per GPU (e.g. 512 on one GPU = the N=8 strong-scaling shard)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -342,6 +344,8 @@ def main():
         return float(t[0])
 
     local_batch = PER_GPU_BATCH if args.scaling == "weak" else PER_GPU_BATCH // world
+    if args.shard_batch:
+        local_batch = args.shard_batch
     global_batch = local_batch * world
     tr = CnnTrainer(dev, local_batch, **HYPER, world=world, use_graph=not args.no_graph, program=args.program,
                     exchange=args.exchange)
@@ -536,6 +540,11 @@ def main():
     out.update(extras)
     if not args.no_conv_vjp:
         out["conv_vjp"] = conv_vjp_bench(dev, ffi, hbm_peak, fp64_peak)
+        f32_peak, f32_src = f32_tensor_peak()
+        out["conv_vjp_f32"] = conv_vjp_bench(dev, ffi, hbm_peak, f32_peak, dtype=np.float32)
+        out["conv_vjp_f32"]["engine"] = "tcgen05.mma kind::tf32, three-term split (csrc/contract_tf32.cu)"
+        out["conv_vjp_f32"]["tensor_peak"] = {"tflops": f32_peak, "source": f32_src}
+        out["smatmul2_f32"] = f32_matmul_bench(dev, ffi)
     if not args.no_other_configs and world == 1:
         # the other BASELINE configs (LongProdBench, ShortMnistForCI, RNN, secondary CNN, kernel families), each group
         # with its own nvidia-smi clock samples: the numbers bench_configs.py prints, on the driver's record
@@ -660,16 +669,17 @@ def roofline_of(rows, hbm_peak, peak_src, fp64_peak):
     return roof, breakdown
 
 
-def conv_vjp_bench(dev, ffi, hbm_peak, fp64_peak, reps=10):
-    """ConvVjpBench at BASELINE config 3: K[64,64,3,3], A,dB[256,64,28,28] Double."""
+def conv_vjp_bench(dev, ffi, hbm_peak, fp64_peak, reps=10, dtype=np.float64):
+    """ConvVjpBench at BASELINE config 3: K[64,64,3,3], A,dB[256,64,28,28], Double (the reference's benchmark type)
+    or Float (the tcgen05 3xTF32 engine; `fp64_peak` is then the Float tensor peak to compare with)."""
     rng = np.random.Generator(np.random.Philox(42))
-    K = dev.sconcrete(rng.uniform(-.5, .5, (64, 64, 3, 3)))
-    A = dev.sconcrete(rng.uniform(-.5, .5, (256, 64, 28, 28)))
-    dB = dev.sconcrete(rng.uniform(-.5, .5, (256, 64, 28, 28)))
-    by = (2 * 256 * 64 * 28 * 28 + 64 * 64 * 9) * 8
+    K = dev.sconcrete(rng.uniform(-.5, .5, (64, 64, 3, 3)).astype(dtype))
+    A = dev.sconcrete(rng.uniform(-.5, .5, (256, 64, 28, 28)).astype(dtype))
+    dB = dev.sconcrete(rng.uniform(-.5, .5, (256, 64, 28, 28)).astype(dtype))
+    by = (2 * 256 * 64 * 28 * 28 + 64 * 64 * 9) * np.dtype(dtype).itemsize
     fl = 2 * 256 * 64 * 28 * 28 * 64 * 9
-    out = {"config": "K[64,64,3,3], A,dB[256,64,28,28] f64", "algorithmic_bytes_per_pass": by,
-           "algorithmic_flops_per_pass": fl}
+    out = {"config": f"K[64,64,3,3], A,dB[256,64,28,28] {'f64' if dtype == np.float64 else 'f32'}",
+           "algorithmic_bytes_per_pass": by, "algorithmic_flops_per_pass": fl}
     ms = C.c_float()
     for name, f in (("fwd", lambda: dev.conv2dPreserving(K, A)), ("dkrn", lambda: dev.conv2d_dkrn(A, dB, 3, 3)),
                     ("dinp", lambda: dev.conv2d_dinp(K, dB))):
@@ -683,8 +693,41 @@ def conv_vjp_bench(dev, ffi, hbm_peak, fp64_peak, reps=10):
         ffi.call("hb_event_elapsed_ms", 2, 3, C.byref(ms))
         t = ms.value / reps * 1e-3
         out[name] = {"ms": t * 1e3, "hbm_gbs": by / t / 1e9, "hbm_frac": by / t / 1e9 / hbm_peak,
-                     "tflops": fl / t / 1e12, "fp64_frac": fl / t / 1e12 / fp64_peak}
+                     "tflops": fl / t / 1e12,
+                     ("fp64_frac" if dtype == np.float64 else "tensor_frac"): fl / t / 1e12 / fp64_peak}
     return out
+
+
+def f32_tensor_peak():
+    """Float contractions run as three kind::tf32 MMAs per product: peak = (TF32 dense = 1/2 of the measured bf16
+    figure of MEASURED_PEAKS.json) / 3."""
+    _, _, d = peaks()
+    bf16 = float(d.get("bf16_tflops", 1590.0))
+    return bf16 / 2 / 3, ("measured bf16 burst (MEASURED_PEAKS.json) / 2 (TF32) / 3 (three-term split)"
+                          if d else "fallback bf16 1590 / 2 / 3")
+
+
+def f32_matmul_bench(dev, ffi, reps=10):
+    """smatmul2 in Float on the tcgen05 engine: [4096,4096] x [4096,4096]."""
+    rng = np.random.Generator(np.random.Philox(43))
+    n = 4096
+    a = dev.sconcrete(rng.uniform(-.5, .5, (n, n)).astype(np.float32))
+    b = dev.sconcrete(rng.uniform(-.5, .5, (n, n)).astype(np.float32))
+    ms = C.c_float()
+    for _ in range(3):
+        dev.smatmul2(a, b)
+    dev.sync()
+    ffi.call("hb_event_record", 2)
+    for _ in range(reps):
+        dev.smatmul2(a, b)
+    ffi.call("hb_event_record", 3)
+    ffi.call("hb_event_elapsed_ms", 2, 3, C.byref(ms))
+    t = ms.value / reps * 1e-3
+    peak, src = f32_tensor_peak()
+    tf = 2.0 * n ** 3 / t / 1e12
+    return {"shape": [n, n, n], "ms": t * 1e3,
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
+                         "peak_source": src}}
 
 
 def cpu_baseline(sample: int, workers: int = 0):

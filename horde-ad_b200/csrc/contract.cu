@@ -17,35 +17,12 @@
 // has no FP64 kind) for doubles, FFMA register tiles for floats.  Tensor-pipe
 // roofline: 2*M*N*K flops against the measured FP64 peak (hb_microbench).
 #include "common.cuh"
+#include "contract.cuh"
 #include "lazy.cuh"
 
 #define TM 64
 #define TN 64
 #define TK 16
-
-struct hb_cgroup {
-  int rank;
-  int64_t n;  // product of extents
-  int64_t shape[HB_R];
-  int64_t sa[HB_R], sb[HB_R], sc[HB_R];
-};
-
-struct hb_contractp {
-  hb_cgroup M, N, B, K;
-};
-
-__device__ __forceinline__ void hb_cg_offsets(const hb_cgroup &g, int64_t lin, int64_t &oa, int64_t &ob,
-                                              int64_t &oc) {
-  oa = ob = oc = 0;
-#pragma unroll 1
-  for (int d = g.rank - 1; d >= 0; d--) {
-    int64_t q = lin / g.shape[d], r = lin - q * g.shape[d];
-    oa += r * g.sa[d];
-    ob += r * g.sb[d];
-    oc += r * g.sc[d];
-    lin = q;
-  }
-}
 
 // ---- FP64 tensor-core tile product: warp computes 32(m) x 16(n) of the tile
 __device__ __forceinline__ void hb_dmma(double &c0, double &c1, double a, double b) {
@@ -232,6 +209,13 @@ template <typename T>
 static int launch_contract(hb_contractp &P, const hb_array *a, const hb_array *b, hb_array *o) {
   cg_finish(&P.M); cg_finish(&P.N); cg_finish(&P.B); cg_finish(&P.K);
   if (P.M.n == 0 || P.N.n == 0 || P.B.n == 0) return HB_OK;
+  if constexpr (std::is_same<T, float>::value) {
+    // Float: the tcgen05 engine (3xTF32 on the tensor cores, TMEM accumulators) takes every shape with a tile's
+    // worth of work; what it declines stays on the FFMA register-tile kernel below
+    int done = 0;
+    HB_TRY(hb_contract_tf32(P, (const float *)hb_data(a), (const float *)hb_data(b), (float *)hb_data(o), &done));
+    if (done) return HB_OK;
+  }
   HB_REQUIRE(P.B.n < 65536 && (P.N.n + TN - 1) / TN < 65536, "contract: grid too large");
   bool a_kfast = min_abs_stride(P.K, P.K.sa) <= min_abs_stride(P.M, P.M.sa);
   bool b_kfast = min_abs_stride(P.K, P.K.sb) <= min_abs_stride(P.N, P.N.sb);
