@@ -41,7 +41,10 @@ struct tf32_params {
   hb_cgroup M, N, B, K;       // roles as the kernel sees them: "a" = the operand on the TMEM-lane side
   int64_t Mtot, Ntot, Ktot;
   int bn;                     // N tile (32, 64, 96, 128)
-  int a_kfast, b_kfast;       // builder thread mapping per operand (coalescing)
+  // per operand (0 = a, 1 = b): shared-memory layout and how a builder thread fetches its 4-element units
+  int mn[2];                  // fetch pattern: 0 = k-fast (4 consecutive k of one row), 1 = m-fast (4 rows of one k)
+  int contig4[2];             // the 4 elements of a fetch are at consecutive addresses
+  int vec[2];                 // ... and 16-byte aligned: one 128-bit load
   int splits;                 // split-K factor; > 1: compact partial output
   int kb_per_split;           // k blocks (of BK) per split
   float *partial;             // [batch][split][n][m] when splits > 1
@@ -68,7 +71,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       : "memory");
 }
 
-// shared-memory matrix descriptor: K-major, no swizzle, version 1 (sm_100)
+// shared-memory matrix descriptor: K-major, no swizzle, version 1 (sm_100).  Tile = [row/8][k/4][row%8][16 B]:
+// core matrices adjacent in K are LBO = 128 B apart, 8-row groups SBO = 1 KB.  (An MN-major no-swizzle tile for the
+// m-contiguous operands did not give correct products on the B200 for kind::tf32 with either reading of LBO/SBO --
+// measured, round 2 -- so m-contiguous views are transposed in registers into this layout instead.)
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)(LBO >> 4) << 16) | ((uint64_t)(SBO >> 4) << 32) |
          (1ull << 46);
@@ -156,7 +162,7 @@ __global__ void __launch_bounds__(NBUILD + 32, 1)
   if (warp == 8) {
     if (lane == 0) {
       for (int s = 0; s < STAGES; s++) {
-        mbar_init(ready_bar(s), NBUILD);
+        mbar_init(ready_bar(s), NBUILD / 32);
         mbar_init(empty_bar(s), 1);
       }
       mbar_init(acc_bar, 1);
@@ -200,61 +206,129 @@ __global__ void __launch_bounds__(NBUILD + 32, 1)
     }
   } else {
     // ================================================================ builders
-    // thread -> (k chunk of 4, base row in 0..31) per operand; rows r0 + 32 j
-    const int a_kc = P.a_kfast ? (lane >> 3) + 4 * (warp & 1) : warp;
-    const int a_r0 = P.a_kfast ? (warp >> 1) * 8 + (lane & 7) : lane;
-    const int b_kc = P.b_kfast ? (lane >> 3) + 4 * (warp & 1) : warp;
-    const int b_r0 = P.b_kfast ? (warp >> 1) * 8 + (lane & 7) : lane;
-    // which k of the stage this LANE decomposes for its warp, and where a thread fetches its four from
-    const int a_kbase = P.a_kfast ? 16 * (warp & 1) : 4 * warp, a_nk = P.a_kfast ? 16 : 4;
-    const int b_kbase = P.b_kfast ? 16 * (warp & 1) : 4 * warp, b_nk = P.b_kfast ? 16 : 4;
-    const int a_src = P.a_kfast ? (lane >> 3) * 4 : 0, b_src = P.b_kfast ? (lane >> 3) * 4 : 0;
-    const int nrb = BN >> 5;   // row groups of the B tile
-
-    int am_off[4], bn_off[4];
-    bool am_ok[4], bn_ok[4];
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      am_off[j] = offAm[a_r0 + 32 * j];
-      am_ok[j] = m0 + a_r0 + 32 * j < P.Mtot;
-      bn_off[j] = offBn[b_r0 + 32 * j];
-      bn_ok[j] = j < nrb && n0 + b_r0 + 32 * j < P.Ntot;
-    }
-    // byte offset of (row, k chunk) inside a tile
-    uint32_t a_st[4], b_st[4];
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      int ra = a_r0 + 32 * j, rb = b_r0 + 32 * j;
-      a_st[j] = (uint32_t)((ra >> 3) * SBO + a_kc * LBO + (ra & 7) * 16);
-      b_st[j] = (uint32_t)((rb >> 3) * SBO + b_kc * LBO + (rb & 7) * 16);
-    }
-
-    float ra[4][4], rb[4][4];
-    auto load_stage = [&](int kb) {
-      // element offsets of this stage's k values: one decomposition per lane, exchanged by shuffles
-      int ka_off = 0, kb_off = 0, dummy;
-      bool ka_ok = false, kbv_ok = false;
-      {
-        int64_t k = (int64_t)kb * BK + a_kbase + lane;
-        if (lane < a_nk && k < P.Ktot) { cg_off32(P.K, (uint32_t)k, ka_off, dummy); ka_ok = true; }
-        k = (int64_t)kb * BK + b_kbase + lane;
-        if (lane < b_nk && k < P.Ktot) { cg_off32(P.K, (uint32_t)k, dummy, kb_off); kbv_ok = true; }
-      }
-      const unsigned ma = __ballot_sync(0xffffffffu, ka_ok), mb = __ballot_sync(0xffffffffu, kbv_ok);
-#pragma unroll
-      for (int i = 0; i < 4; i++) {
-        const int oa = __shfl_sync(0xffffffffu, ka_off, a_src + i);
-        const int ob = __shfl_sync(0xffffffffu, kb_off, b_src + i);
-        const bool va = (ma >> (a_src + i)) & 1u, vb = (mb >> (b_src + i)) & 1u;
+    // A builder thread owns 4 UNITS of each operand tile per stage; a unit is 16 bytes of the tile:
+    //   K-major tile : 4 consecutive k (chunk kc) of row r0 + 32 j          (lanes: 8 rows x 4 chunks per warp)
+    //   MN-major tile: rows 4 mi .. 4 mi + 3 of one k, mi = mi0 + 4 j        (lanes: 8 k x 4 row groups per warp)
+    // Either way the eight lanes of a quarter warp write eight different 16-byte columns of a 128-byte core matrix
+    // (no bank conflicts) and a warp-wide load touches whole 32-byte sectors when the fast axis is contiguous.
+    struct op_thread {
+      int kq;             // first k (inside the stage) of this thread's 4-k chunk
+      int row[4];         // row whose 4-k chunk is written by store step j
+      uint32_t st[4];     // byte offset of that chunk inside the K-major tile
+      int rot;            // m-fast fetch: rows are stored rotated by `rot` (see below)
+    };
+    // Two fetch patterns, one shared-memory layout (K-major core matrices):
+    //   k-fast: lanes = 8 rows x 4 chunks per warp; a thread fetches the 4-k chunk of rows r0 + 32 j (one 128-bit
+    //           load each when the view is k-contiguous and aligned);
+    //   m-fast: lanes = 32 consecutive 4-row groups, the warp index is the chunk; a thread fetches a 4 x 4 block
+    //           (rows 4 lane .. 4 lane + 3; one 128-bit load along m per k when m-contiguous and aligned: 512
+    //           contiguous bytes per warp) and transposes it in registers.  Its four 16-byte stores go to rows
+    //           4 lane + ((j + rot) & 3), rot = (lane >> 1) & 3, so that the eight lanes of a quarter warp hit
+    //           eight different 16-byte columns of the 128-byte core matrices (no bank conflicts).
+    auto make_op = [&](int mn) {
+      op_thread t;
+      if (!mn) {
+        const int kc = (lane >> 3) + 4 * (warp & 1), r0 = (warp >> 1) * 8 + (lane & 7);
+        t.kq = kc * 4;
+        t.rot = 0;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-          ra[j][i] = (va && am_ok[j]) ? __ldg(A + am_off[j] + oa) : 0.f;
-          rb[j][i] = (vb && bn_ok[j]) ? __ldg(Bm + bn_off[j] + ob) : 0.f;
+          const int r = r0 + 32 * j;
+          t.row[j] = r;
+          t.st[j] = (uint32_t)((r >> 3) * SBO + kc * LBO + (r & 7) * 16);
+        }
+      } else {
+        t.kq = 4 * warp;
+        t.rot = (lane >> 1) & 3;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int r = 4 * lane + ((j + t.rot) & 3);
+          t.row[j] = r;
+          t.st[j] = (uint32_t)((r >> 3) * SBO + warp * LBO + (r & 7) * 16);
+        }
+      }
+      return t;
+    };
+    const op_thread ta = make_op(P.mn[0]), tb = make_op(P.mn[1]);
+    const int rows_a = (int)min((int64_t)BM, P.Mtot - m0), rows_b = (int)min((int64_t)BN, P.Ntot - n0);
+
+    // element offset of reduced index k in operand `which`
+    auto koff = [&](int64_t k, int which) {
+      int oa, ob;
+      if (P.K.rank == 1) return (int)k * (int)(which ? P.K.sb[0] : P.K.sa[0]);
+      cg_off32(P.K, (uint32_t)k, oa, ob);
+      return which ? ob : oa;
+    };
+    // fetch this thread's 16 elements of one operand for k block kb: r[j][i] = (row j of the thread, k = chunk + i)
+    auto load_op = [&](const op_thread &t, int which, const float *__restrict__ base, const int *offtab, int rows,
+                       int kb, float (&r)[4][4]) {
+      const int mn = P.mn[which], contig = P.contig4[which], vec = P.vec[which];
+      const int64_t k0 = (int64_t)kb * BK + t.kq;
+      int ko[4];
+      bool kv[4];
+      if (!mn) {
+        if (contig) {
+          const int o = k0 < P.Ktot ? koff(k0, which) : 0;
+#pragma unroll
+          for (int i = 0; i < 4; i++) { ko[i] = o + i; kv[i] = k0 < P.Ktot; }   // Ktot % 4 == 0 here
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; i++) { kv[i] = k0 + i < P.Ktot; ko[i] = kv[i] ? koff(k0 + i, which) : 0; }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const bool rv = t.row[j] < rows;
+          const int ro = rv ? offtab[t.row[j]] : 0;
+          if (vec) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (rv && kv[0]) v = __ldg((const float4 *)(base + ro + ko[0]));
+            r[j][0] = v.x; r[j][1] = v.y; r[j][2] = v.z; r[j][3] = v.w;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; i++) r[j][i] = (rv && kv[i]) ? __ldg(base + ro + ko[i]) : 0.f;
+          }
+        }
+      } else {
+        // the chunk is warp-uniform: lanes 0..3 decompose one k each
+        if (P.K.rank == 1) {
+#pragma unroll
+          for (int i = 0; i < 4; i++) { kv[i] = k0 + i < P.Ktot; ko[i] = kv[i] ? koff(k0 + i, which) : 0; }
+        } else {
+          int mine = 0;
+          const bool ok = lane < 4 && k0 + lane < P.Ktot;
+          if (ok) mine = koff(k0 + lane, which);
+          const unsigned m = __ballot_sync(0xffffffffu, ok);
+#pragma unroll
+          for (int i = 0; i < 4; i++) { ko[i] = __shfl_sync(0xffffffffu, mine, i); kv[i] = (m >> i) & 1u; }
+        }
+        const int r0 = 4 * lane;
+        if (contig) {
+          const bool rv = r0 < rows;     // tile extents are multiples of 4 here: all four rows or none
+          const int ro = rv ? offtab[r0] : 0;
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            if (vec) {
+              float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (rv && kv[i]) v = __ldg((const float4 *)(base + ro + ko[i]));
+              r[0][i] = v.x; r[1][i] = v.y; r[2][i] = v.z; r[3][i] = v.w;
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; j++) r[j][i] = (rv && kv[i]) ? __ldg(base + ro + j + ko[i]) : 0.f;
+            }
+          }
+        } else {
+          const int4 ro = *(const int4 *)(offtab + r0);
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            r[0][i] = (kv[i] && r0 + 0 < rows) ? __ldg(base + ro.x + ko[i]) : 0.f;
+            r[1][i] = (kv[i] && r0 + 1 < rows) ? __ldg(base + ro.y + ko[i]) : 0.f;
+            r[2][i] = (kv[i] && r0 + 2 < rows) ? __ldg(base + ro.z + ko[i]) : 0.f;
+            r[3][i] = (kv[i] && r0 + 3 < rows) ? __ldg(base + ro.w + ko[i]) : 0.f;
+          }
         }
       }
     };
     auto split_store = [&](uint8_t *tile_hi, uint32_t off, const float (&v)[4]) {
-      float4 hi, lo;
       float h[4], l[4];
 #pragma unroll
       for (int i = 0; i < 4; i++) {
@@ -262,25 +336,48 @@ __global__ void __launch_bounds__(NBUILD + 32, 1)
         float d = v[i] - h[i];
         l[i] = (fabsf(h[i]) <= 3.0e38f) ? tf32_rn(d) : 0.f;   // Inf/NaN stay in the hi term only
       }
-      hi = make_float4(h[0], h[1], h[2], h[3]);
-      lo = make_float4(l[0], l[1], l[2], l[3]);
-      *(float4 *)(tile_hi + off) = hi;
-      *(float4 *)(tile_hi + TILE_BYTES + off) = lo;
+      *(float4 *)(tile_hi + off) = make_float4(h[0], h[1], h[2], h[3]);
+      *(float4 *)(tile_hi + TILE_BYTES + off) = make_float4(l[0], l[1], l[2], l[3]);
+    };
+    // store step j writes row (j + rot) & 3 of the thread's block: rotate the rows by rot with two select levels
+    auto store_op = [&](uint8_t *tile_hi, const op_thread &t, const float (&r)[4][4], int nrows) {
+      float s1[4][4], s2[4][4];
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+#pragma unroll
+        for (int i = 0; i < 4; i++) s1[j][i] = (t.rot & 1) ? r[(j + 1) & 3][i] : r[j][i];
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+#pragma unroll
+        for (int i = 0; i < 4; i++) s2[j][i] = (t.rot & 2) ? s1[(j + 2) & 3][i] : s1[j][i];
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+        if (t.row[j] < nrows) split_store(tile_hi, t.st[j], s2[j]);
     };
 
-    if (nkb > 0) load_stage(kb0);
-    for (int i = 0; i < nkb; i++) {
+    auto build = [&](int i, const float (&ra)[4][4], const float (&rb)[4][4]) {
       const int s = i % STAGES;
       mbar_wait(empty_bar(s), (uint32_t)(((i / STAGES) & 1) ^ 1));
       uint8_t *st = smem + (size_t)s * STAGE_BYTES;
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        split_store(st, a_st[j], ra[j]);
-        if (j < nrb) split_store(st + 2 * TILE_BYTES, b_st[j], rb[j]);
-      }
+      store_op(st, ta, ra, BM);
+      store_op(st + 2 * TILE_BYTES, tb, rb, BN);   // rows of the B tile beyond BN are never read by the MMA
+      // generic-proxy writes -> visible to the tensor core's async-proxy reads, then one arrival per warp
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_arrive(ready_bar(s));
-      if (i + 1 < nkb) load_stage(kb0 + i + 1);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ready_bar(s));
+    };
+
+    // two k blocks of loads in flight per thread: registers of block i + 2 are requested before block i + 1 is split
+    float ra0[4][4], rb0[4][4], ra1[4][4], rb1[4][4];
+    if (nkb > 0) { load_op(ta, 0, A, offAm, rows_a, kb0, ra0); load_op(tb, 1, Bm, offBn, rows_b, kb0, rb0); }
+    if (nkb > 1) { load_op(ta, 0, A, offAm, rows_a, kb0 + 1, ra1); load_op(tb, 1, Bm, offBn, rows_b, kb0 + 1, rb1); }
+    for (int i = 0; i < nkb; i += 2) {
+      build(i, ra0, rb0);
+      if (i + 2 < nkb) { load_op(ta, 0, A, offAm, rows_a, kb0 + i + 2, ra0); load_op(tb, 1, Bm, offBn, rows_b, kb0 + i + 2, rb0); }
+      if (i + 1 < nkb) {
+        build(i + 1, ra1, rb1);
+        if (i + 3 < nkb) { load_op(ta, 0, A, offAm, rows_a, kb0 + i + 3, ra1); load_op(tb, 1, Bm, offBn, rows_b, kb0 + i + 3, rb1); }
+      }
     }
 
     // ================================================================ epilogue
@@ -414,16 +511,48 @@ int hb_contract_tf32(const hb_contractp &Pin, const float *A, const float *B, fl
   }
   P.Mtot = P.M.n; P.Ntot = P.N.n; P.Ktot = K;
   P.bn = (int)std::min<int64_t>(128, ((P.Ntot + 31) / 32) * 32);
-  // builder mapping: lanes along k when k is the faster axis of the operand and long enough to fill a 64-byte run
-  auto kfast = [&](const int64_t *ks, const hb_cgroup &g, const int64_t *ms) {
-    int64_t sk = min_abs(P.K, ks), sm = min_abs(g, ms);
-    int64_t inner = P.K.rank ? P.K.shape[P.K.rank - 1] : 1;
-    if (sk < sm) return inner >= 8 || sm > 16;
-    if (sk == sm) return inner >= 32;
-    return false;
+  // per operand: tile layout (K-major / MN-major) and fetch width, from the strides of the view
+  auto configure = [&](int which, const hb_cgroup &G, const float *base) {
+    auto str = [&](const hb_cgroup &g, int i) { return which ? g.sb[i] : g.sa[i]; };
+    auto last_contig = [&](const hb_cgroup &g) {
+      return g.rank > 0 && str(g, g.rank - 1) == 1 && g.shape[g.rank - 1] % 4 == 0;
+    };
+    // every stride other than the unit one a multiple of 4 elements, base 16-byte aligned
+    auto aligned = [&](const hb_cgroup &fast) {
+      if ((uintptr_t)base % 16) return false;
+      const hb_cgroup *gs[3] = {&G, &P.K, &P.B};
+      for (const hb_cgroup *g : gs)
+        for (int i = 0; i < g->rank; i++) {
+          if (g == &fast && i == g->rank - 1) continue;
+          if (str(*g, i) % 4) return false;
+        }
+      return true;
+    };
+    bool kc = last_contig(P.K), mc = last_contig(G);
+    static const char *force = getenv("HB_TF32_LAYOUT");   // measurement / debugging: "k" or "mn" tiles only
+    int mn, contig, vec = 0;
+    if (force && force[0] == 'k') mc = false;
+    if (force && force[0] == 'm') kc = false;
+    if (kc && (!mc || aligned(P.K) || !aligned(G))) { mn = 0; contig = 1; vec = aligned(P.K); }
+    else if (mc) { mn = 1; contig = 1; vec = aligned(G); }
+    else {
+      // no 4-element run either way: lanes along the axis with the smaller stride (coalescing), scalar fetches
+      auto min_stride = [&](const hb_cgroup &g) {
+        int64_t m = INT64_MAX;
+        for (int i = 0; i < g.rank; i++) {
+          int64_t x = str(g, i) < 0 ? -str(g, i) : str(g, i);
+          if (x && x < m) m = x;
+        }
+        return m;
+      };
+      mn = min_stride(G) < min_stride(P.K);
+      if (force) mn = force[0] == 'm';
+      contig = 0;
+    }
+    P.mn[which] = mn; P.contig4[which] = contig; P.vec[which] = vec;
   };
-  P.a_kfast = kfast(P.K.sa, P.M, P.M.sa);
-  P.b_kfast = kfast(P.K.sb, P.N, P.N.sb);
+  configure(0, P.M, A);
+  configure(1, P.N, B);
 
   const int64_t tm = (P.Mtot + BM - 1) / BM, tn = (P.Ntot + P.bn - 1) / P.bn;
   const int nkb = (int)((K + BK - 1) / BK);

@@ -62,6 +62,34 @@ __device__ __forceinline__ T hb_block_excl_prod(T p, bool rev, T *smem /* 8 */) 
   return excl * wp;
 }
 
+// both directions at once (exclusive prefix and exclusive suffix of this thread over the block's 256 values) behind
+// ONE pair of barriers; same association per direction as hb_block_excl_prod -> bit-identical results
+template <typename T>
+__device__ __forceinline__ void hb_block_excl_prod2(T p, T *smem /* 16 */, T &pre, T &suf) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  T up = p, dn = p;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    T u = __shfl_up_sync(0xffffffffu, up, o);
+    T d = __shfl_down_sync(0xffffffffu, dn, o);
+    if (lane >= o) up = u * up;
+    if (lane + o < 32) dn = dn * d;
+  }
+  T eu = __shfl_up_sync(0xffffffffu, up, 1), ed = __shfl_down_sync(0xffffffffu, dn, 1);
+  if (lane == 0) eu = T(1);
+  if (lane == 31) ed = T(1);
+  __syncthreads();  // smem may still be read by a previous call
+  if (lane == 31) smem[w] = up;
+  if (lane == 0) smem[8 + w] = dn;
+  __syncthreads();
+  T wp = T(1);
+  for (int i = 0; i < w; i++) wp = wp * smem[i];
+  pre = wp * eu;
+  T ws = T(1);
+  for (int i = 7; i > w; i--) ws = smem[8 + i] * ws;
+  suf = ed * ws;
+}
+
 template <typename T, bool VEC>
 __global__ void __launch_bounds__(256)
     hb_prod_tiles_kernel(const T *__restrict__ x, int64_t stride, int64_t n, T *__restrict__ tileprod) {
@@ -252,13 +280,15 @@ __device__ __forceinline__ T hb_block_range_prod(const T *__restrict__ tp, int64
 template <typename T, bool VEC>
 __global__ void __launch_bounds__(256)
     hb_prod_fused_kernel(const T *__restrict__ x, int64_t stride, int64_t n, int64_t nt, T dt, T *__restrict__ tp,
-                         unsigned *__restrict__ bar, T *__restrict__ total, T *__restrict__ grad, int own_cap) {
+                         T *__restrict__ cp, unsigned *__restrict__ bar, T *__restrict__ total, T *__restrict__ grad,
+                         int own_cap) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   T *own_pre = reinterpret_cast<T *>(dyn_smem);   // [own_cap]: product of everything before own tile k
-  __shared__ T smem[9];
+  __shared__ T smem[16];
   const int64_t G = gridDim.x, b = blockIdx.x;
   const int64_t t0 = b * nt / G, t1 = (b + 1) * nt / G;
   // ---- phase A
+  T own = T(1);   // thread 255: product of this CTA's tiles, left to right
   for (int64_t t = t0; t < t1; t++) {
     int64_t base = t * PT + threadIdx.x * 8;
     T v[8];
@@ -267,17 +297,18 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
     for (int i = 0; i < 8; i++) p *= v[i];
     T before = hb_block_excl_prod<T>(p, false, smem);
-    if (threadIdx.x == 255) tp[t] = before * p;
+    if (threadIdx.x == 255) {
+      T tile = before * p;
+      tp[t] = tile;
+      own = own * tile;
+    }
   }
+  if (threadIdx.x == 255) cp[b] = own;
   hb_grid_barrier(bar, (unsigned)G);
-  // ---- phase S
-  T e0 = hb_block_range_prod<T>(tp, 0, t0, smem);
-  T e1 = hb_block_range_prod<T>(tp, t1, nt, smem);
-  if (b == 0 && threadIdx.x == 0) {  // prod x = (own range of CTA 0) * (everything after it), in order
-    T r = T(1);
-    for (int64_t t = t0; t < t1; t++) r = r * __ldcg(tp + t);
-    *total = r * e1;
-  }
+  // ---- phase S: G per-CTA products (a few KB), not nt tile products, are what every CTA re-reads
+  T e0 = hb_block_range_prod<T>(cp, 0, b, smem);
+  T e1 = hb_block_range_prod<T>(cp, b + 1, G, smem);
+  if (b == 0 && threadIdx.x == 0) *total = __ldcg(cp) * e1;   // prod x = (own range of CTA 0) * (everything after it)
   if (!grad) return;
   e1 = e1 * dt;
   if (threadIdx.x == 0) {
@@ -297,8 +328,10 @@ __global__ void __launch_bounds__(256)
     T p = T(1);
 #pragma unroll
     for (int i = 0; i < 8; i++) p *= v[i];
-    T a = own_pre[t - t0] * hb_block_excl_prod<T>(p, false, smem);
-    T c = hb_block_excl_prod<T>(p, true, smem) * suf;
+    T a, c;
+    hb_block_excl_prod2<T>(p, smem, a, c);
+    a = own_pre[t - t0] * a;
+    c = c * suf;
     T out[8];
     T r = c;
 #pragma unroll
@@ -336,7 +369,7 @@ static int prod_launch_fused(const hb_array *x, int64_t n, int64_t nt, double dt
   if (getenv("HB_PROD_UNFUSED")) return HB_OK;   // measurement switch: the four-launch pipeline of round 1
   const T *xp = (const T *)hb_data(x);
   const bool vec = x->strides[0] == 1 && ((uintptr_t)xp & 15) == 0 && (!grad || ((uintptr_t)hb_data(grad) & 15) == 0);
-  void (*kern)(const T *, int64_t, int64_t, int64_t, T, T *, unsigned *, T *, T *, int) =
+  void (*kern)(const T *, int64_t, int64_t, int64_t, T, T *, T *, unsigned *, T *, T *, int) =
       vec ? hb_prod_fused_kernel<T, true> : hb_prod_fused_kernel<T, false>;
   int occ = 0;
   const int own_guess = 64;
@@ -355,14 +388,14 @@ static int prod_launch_fused(const hb_array *x, int64_t n, int64_t nt, double dt
     own = (nt + G - 1) / G + 1;
     if ((size_t)own * sizeof(T) > dyn) return HB_OK;
   }
-  T *tp = (T *)scr;
+  T *tp = (T *)scr, *cp = tp + nt;   // G <= nt per-CTA products in the round-1 pipeline's `pre` region
   unsigned *bar = (unsigned *)((char *)scr + (size_t)(nt * 3 + GT) * sizeof(T));
   HB_CUDA(cudaMemsetAsync(bar, 0, sizeof(unsigned), g_hb.stream));
   int64_t stride = x->strides[0];
   T dtt = (T)dt;
   T *tot = (T *)hb_data(prod), *gp = grad ? (T *)hb_data(grad) : nullptr;
   int own_cap = (int)own;
-  void *args[] = {(void *)&xp, (void *)&stride, (void *)&n, (void *)&nt, (void *)&dtt, (void *)&tp, (void *)&bar,
+  void *args[] = {(void *)&xp, (void *)&stride, (void *)&n, (void *)&nt, (void *)&dtt, (void *)&tp, (void *)&cp, (void *)&bar,
                   (void *)&tot, (void *)&gp, (void *)&own_cap};
   // cooperative launch = the runtime guarantees (or refuses) co-residency of all G CTAs: the barrier cannot hang
   cudaError_t e = cudaLaunchCooperativeKernel((const void *)kern, dim3((unsigned)G), dim3(256), args, dyn, g_hb.stream);
