@@ -93,12 +93,6 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-__device__ __forceinline__ float tf32_rn(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
-
 // row-major linear index over g.shape -> 32-bit element offsets in a and b
 __device__ __forceinline__ void cg_off32(const hb_cgroup &g, uint32_t lin, int &oa, int &ob) {
   oa = ob = 0;
@@ -206,36 +200,37 @@ __global__ void __launch_bounds__(NBUILD + 32, 1)
     }
   } else {
     // ================================================================ builders
-    // A builder thread owns 4 UNITS of each operand tile per stage; a unit is 16 bytes of the tile:
-    //   K-major tile : 4 consecutive k (chunk kc) of row r0 + 32 j          (lanes: 8 rows x 4 chunks per warp)
-    //   MN-major tile: rows 4 mi .. 4 mi + 3 of one k, mi = mi0 + 4 j        (lanes: 8 k x 4 row groups per warp)
-    // Either way the eight lanes of a quarter warp write eight different 16-byte columns of a 128-byte core matrix
-    // (no bank conflicts) and a warp-wide load touches whole 32-byte sectors when the fast axis is contiguous.
+    // Two fetch patterns, one shared-memory layout (K-major core matrices).  Per stage and operand a thread owns
+    // 16 elements r[j][i] = (its row j, k = its 4-k chunk + i):
+    //   k-fast: lanes = 8 rows x 4 chunks per warp; rows r0 + 32 j (one 128-bit load each when the view is
+    //           k-contiguous and aligned);
+    //   m-fast: lanes = 32 consecutive 4-row groups, the warp index is the chunk; rows 4 lane .. 4 lane + 3 (one
+    //           128-bit load along m per k when m-contiguous and aligned: 512 contiguous bytes per warp), i.e. a
+    //           4 x 4 block transposed in registers.  Its four 16-byte stores go to rows 4 lane + ((j + rot) & 3),
+    //           rot = (lane >> 1) & 3, so that the eight lanes of a quarter warp hit eight different 16-byte columns
+    //           of the 128-byte core matrices (no bank conflicts).
     struct op_thread {
-      int kq;             // first k (inside the stage) of this thread's 4-k chunk
-      int row[4];         // row whose 4-k chunk is written by store step j
-      uint32_t st[4];     // byte offset of that chunk inside the K-major tile
-      int rot;            // m-fast fetch: rows are stored rotated by `rot` (see below)
+      const float *rp[4];   // address of (row j, k offset 0); m-fast contiguous: only rp[0] (rows are rp[0] + j)
+      unsigned rmask;       // bit j: row j exists
+      int kq;               // first k (inside the stage) of this thread's 4-k chunk
+      uint32_t st[4];       // byte offset inside the tile of the chunk written by store step j
+      int srow[4];          // ... and its row (B tile: rows beyond BN are not stored)
+      int rot;
     };
-    // Two fetch patterns, one shared-memory layout (K-major core matrices):
-    //   k-fast: lanes = 8 rows x 4 chunks per warp; a thread fetches the 4-k chunk of rows r0 + 32 j (one 128-bit
-    //           load each when the view is k-contiguous and aligned);
-    //   m-fast: lanes = 32 consecutive 4-row groups, the warp index is the chunk; a thread fetches a 4 x 4 block
-    //           (rows 4 lane .. 4 lane + 3; one 128-bit load along m per k when m-contiguous and aligned: 512
-    //           contiguous bytes per warp) and transposes it in registers.  Its four 16-byte stores go to rows
-    //           4 lane + ((j + rot) & 3), rot = (lane >> 1) & 3, so that the eight lanes of a quarter warp hit
-    //           eight different 16-byte columns of the 128-byte core matrices (no bank conflicts).
-    auto make_op = [&](int mn) {
+    auto make_op = [&](int which, const float *base, const int *offtab, int rows) {
       op_thread t;
-      if (!mn) {
+      t.rmask = 0;
+      if (!P.mn[which]) {
         const int kc = (lane >> 3) + 4 * (warp & 1), r0 = (warp >> 1) * 8 + (lane & 7);
         t.kq = kc * 4;
         t.rot = 0;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
           const int r = r0 + 32 * j;
-          t.row[j] = r;
+          t.srow[j] = r;
           t.st[j] = (uint32_t)((r >> 3) * SBO + kc * LBO + (r & 7) * 16);
+          t.rp[j] = base + (r < rows ? offtab[r] : 0);
+          if (r < rows) t.rmask |= 1u << j;
         }
       } else {
         t.kq = 4 * warp;
@@ -243,14 +238,17 @@ __global__ void __launch_bounds__(NBUILD + 32, 1)
 #pragma unroll
         for (int j = 0; j < 4; j++) {
           const int r = 4 * lane + ((j + t.rot) & 3);
-          t.row[j] = r;
+          t.srow[j] = r;
           t.st[j] = (uint32_t)((r >> 3) * SBO + warp * LBO + (r & 7) * 16);
+          const int rr = 4 * lane + j;
+          t.rp[j] = base + (rr < rows ? offtab[rr] : 0);
+          if (rr < rows) t.rmask |= 1u << j;
         }
       }
       return t;
     };
-    const op_thread ta = make_op(P.mn[0]), tb = make_op(P.mn[1]);
     const int rows_a = (int)min((int64_t)BM, P.Mtot - m0), rows_b = (int)min((int64_t)BN, P.Ntot - n0);
+    const op_thread ta = make_op(0, A, offAm, rows_a), tb = make_op(1, Bm, offBn, rows_b);
 
     // element offset of reduced index k in operand `which`
     auto koff = [&](int64_t k, int which) {
@@ -259,88 +257,105 @@ __global__ void __launch_bounds__(NBUILD + 32, 1)
       cg_off32(P.K, (uint32_t)k, oa, ob);
       return which ? ob : oa;
     };
-    // fetch this thread's 16 elements of one operand for k block kb: r[j][i] = (row j of the thread, k = chunk + i)
-    auto load_op = [&](const op_thread &t, int which, const float *__restrict__ base, const int *offtab, int rows,
-                       int kb, float (&r)[4][4]) {
+    // fetch this thread's 16 elements of one operand for k block kb
+    auto load_op = [&](const op_thread &t, int which, int kb, float (&r)[4][4]) {
       const int mn = P.mn[which], contig = P.contig4[which], vec = P.vec[which];
       const int64_t k0 = (int64_t)kb * BK + t.kq;
+      const bool fullk = (int64_t)(kb + 1) * BK <= P.Ktot;
       int ko[4];
-      bool kv[4];
+      unsigned kmask = 0;
       if (!mn) {
-        if (contig) {
-          const int o = k0 < P.Ktot ? koff(k0, which) : 0;
+        if (contig) {   // Ktot % 4 == 0 here: the chunk is inside or outside as a whole
+          const bool in = fullk || k0 < P.Ktot;
+          const int o = in ? koff(k0, which) : 0;
 #pragma unroll
-          for (int i = 0; i < 4; i++) { ko[i] = o + i; kv[i] = k0 < P.Ktot; }   // Ktot % 4 == 0 here
+          for (int i = 0; i < 4; i++) ko[i] = o + i;
+          kmask = in ? 15u : 0u;
         } else {
 #pragma unroll
-          for (int i = 0; i < 4; i++) { kv[i] = k0 + i < P.Ktot; ko[i] = kv[i] ? koff(k0 + i, which) : 0; }
-        }
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const bool rv = t.row[j] < rows;
-          const int ro = rv ? offtab[t.row[j]] : 0;
-          if (vec) {
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (rv && kv[0]) v = __ldg((const float4 *)(base + ro + ko[0]));
-            r[j][0] = v.x; r[j][1] = v.y; r[j][2] = v.z; r[j][3] = v.w;
-          } else {
-#pragma unroll
-            for (int i = 0; i < 4; i++) r[j][i] = (rv && kv[i]) ? __ldg(base + ro + ko[i]) : 0.f;
+          for (int i = 0; i < 4; i++) {
+            const bool in = fullk || k0 + i < P.Ktot;
+            ko[i] = in ? koff(k0 + i, which) : 0;
+            kmask |= (unsigned)in << i;
           }
+        }
+        if (vec) {
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (((t.rmask >> j) & 1u) && kmask) v = __ldg((const float4 *)(t.rp[j] + ko[0]));
+            r[j][0] = v.x; r[j][1] = v.y; r[j][2] = v.z; r[j][3] = v.w;
+          }
+        } else if (t.rmask == 15u && kmask == 15u) {
+#pragma unroll
+          for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int i = 0; i < 4; i++) r[j][i] = __ldg(t.rp[j] + ko[i]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+              r[j][i] = (((t.rmask >> j) & 1u) && ((kmask >> i) & 1u)) ? __ldg(t.rp[j] + ko[i]) : 0.f;
         }
       } else {
         // the chunk is warp-uniform: lanes 0..3 decompose one k each
         if (P.K.rank == 1) {
 #pragma unroll
-          for (int i = 0; i < 4; i++) { kv[i] = k0 + i < P.Ktot; ko[i] = kv[i] ? koff(k0 + i, which) : 0; }
+          for (int i = 0; i < 4; i++) {
+            const bool in = fullk || k0 + i < P.Ktot;
+            ko[i] = in ? koff(k0 + i, which) : 0;
+            kmask |= (unsigned)in << i;
+          }
         } else {
           int mine = 0;
-          const bool ok = lane < 4 && k0 + lane < P.Ktot;
+          const bool ok = lane < 4 && (fullk || k0 + lane < P.Ktot);
           if (ok) mine = koff(k0 + lane, which);
-          const unsigned m = __ballot_sync(0xffffffffu, ok);
+          kmask = __ballot_sync(0xffffffffu, ok) & 15u;
 #pragma unroll
-          for (int i = 0; i < 4; i++) { ko[i] = __shfl_sync(0xffffffffu, mine, i); kv[i] = (m >> i) & 1u; }
+          for (int i = 0; i < 4; i++) ko[i] = __shfl_sync(0xffffffffu, mine, i);
         }
-        const int r0 = 4 * lane;
-        if (contig) {
-          const bool rv = r0 < rows;     // tile extents are multiples of 4 here: all four rows or none
-          const int ro = rv ? offtab[r0] : 0;
+        if (contig && vec) {
 #pragma unroll
           for (int i = 0; i < 4; i++) {
-            if (vec) {
-              float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (rv && kv[i]) v = __ldg((const float4 *)(base + ro + ko[i]));
-              r[0][i] = v.x; r[1][i] = v.y; r[2][i] = v.z; r[3][i] = v.w;
-            } else {
-#pragma unroll
-              for (int j = 0; j < 4; j++) r[j][i] = (rv && kv[i]) ? __ldg(base + ro + j + ko[i]) : 0.f;
-            }
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if ((t.rmask & 1u) && ((kmask >> i) & 1u)) v = __ldg((const float4 *)(t.rp[0] + ko[i]));
+            r[0][i] = v.x; r[1][i] = v.y; r[2][i] = v.z; r[3][i] = v.w;
           }
+        } else if (t.rmask == 15u && kmask == 15u) {
+#pragma unroll
+          for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) r[j][i] = __ldg(t.rp[j] + ko[i]);
         } else {
-          const int4 ro = *(const int4 *)(offtab + r0);
 #pragma unroll
-          for (int i = 0; i < 4; i++) {
-            r[0][i] = (kv[i] && r0 + 0 < rows) ? __ldg(base + ro.x + ko[i]) : 0.f;
-            r[1][i] = (kv[i] && r0 + 1 < rows) ? __ldg(base + ro.y + ko[i]) : 0.f;
-            r[2][i] = (kv[i] && r0 + 2 < rows) ? __ldg(base + ro.z + ko[i]) : 0.f;
-            r[3][i] = (kv[i] && r0 + 3 < rows) ? __ldg(base + ro.w + ko[i]) : 0.f;
-          }
+          for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+              r[j][i] = (((t.rmask >> j) & 1u) && ((kmask >> i) & 1u)) ? __ldg(t.rp[j] + ko[i]) : 0.f;
         }
       }
     };
+    // x = hi + lo with hi = x rounded to TF32 (bit trick: add half an ulp of TF32, clear the 13 low bits) and
+    // lo = x - hi exactly; the tensor core reads the top 19 bits of lo.  Non-finite x: hi = x, lo = NaN.
     auto split_store = [&](uint8_t *tile_hi, uint32_t off, const float (&v)[4]) {
       float h[4], l[4];
 #pragma unroll
       for (int i = 0; i < 4; i++) {
-        h[i] = tf32_rn(v[i]);
-        float d = v[i] - h[i];
-        l[i] = (fabsf(h[i]) <= 3.0e38f) ? tf32_rn(d) : 0.f;   // Inf/NaN stay in the hi term only
+        h[i] = __uint_as_float((__float_as_uint(v[i]) + 0x1000u) & 0xffffe000u);
+        l[i] = v[i] - h[i];
       }
       *(float4 *)(tile_hi + off) = make_float4(h[0], h[1], h[2], h[3]);
       *(float4 *)(tile_hi + TILE_BYTES + off) = make_float4(l[0], l[1], l[2], l[3]);
     };
-    // store step j writes row (j + rot) & 3 of the thread's block: rotate the rows by rot with two select levels
-    auto store_op = [&](uint8_t *tile_hi, const op_thread &t, const float (&r)[4][4], int nrows) {
+    auto store_op = [&](uint8_t *tile_hi, const op_thread &t, int which, const float (&r)[4][4], int nrows) {
+      if (!P.mn[which]) {
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+          if (t.srow[j] < nrows) split_store(tile_hi, t.st[j], r[j]);
+        return;
+      }
+      // store step j writes row (j + rot) & 3 of the thread's block: rotate the rows by rot with two select levels
       float s1[4][4], s2[4][4];
 #pragma unroll
       for (int j = 0; j < 4; j++)
@@ -350,17 +365,18 @@ __global__ void __launch_bounds__(NBUILD + 32, 1)
       for (int j = 0; j < 4; j++)
 #pragma unroll
         for (int i = 0; i < 4; i++) s2[j][i] = (t.rot & 2) ? s1[(j + 2) & 3][i] : s1[j][i];
+      if (4 * lane < nrows) {
 #pragma unroll
-      for (int j = 0; j < 4; j++)
-        if (t.row[j] < nrows) split_store(tile_hi, t.st[j], s2[j]);
+        for (int j = 0; j < 4; j++) split_store(tile_hi, t.st[j], s2[j]);
+      }
     };
 
     auto build = [&](int i, const float (&ra)[4][4], const float (&rb)[4][4]) {
       const int s = i % STAGES;
       mbar_wait(empty_bar(s), (uint32_t)(((i / STAGES) & 1) ^ 1));
       uint8_t *st = smem + (size_t)s * STAGE_BYTES;
-      store_op(st, ta, ra, BM);
-      store_op(st + 2 * TILE_BYTES, tb, rb, BN);   // rows of the B tile beyond BN are never read by the MMA
+      store_op(st, ta, 0, ra, BM);
+      store_op(st + 2 * TILE_BYTES, tb, 1, rb, BN);   // rows of the B tile beyond BN are never read by the MMA
       // generic-proxy writes -> visible to the tensor core's async-proxy reads, then one arrival per warp
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
@@ -368,15 +384,16 @@ __global__ void __launch_bounds__(NBUILD + 32, 1)
     };
 
     // two k blocks of loads in flight per thread: registers of block i + 2 are requested before block i + 1 is split
+    // (three in flight measured slower: 68 vs 75 TFLOP/s on 4096^3 -- the loop is issue-bound, not latency-bound)
     float ra0[4][4], rb0[4][4], ra1[4][4], rb1[4][4];
-    if (nkb > 0) { load_op(ta, 0, A, offAm, rows_a, kb0, ra0); load_op(tb, 1, Bm, offBn, rows_b, kb0, rb0); }
-    if (nkb > 1) { load_op(ta, 0, A, offAm, rows_a, kb0 + 1, ra1); load_op(tb, 1, Bm, offBn, rows_b, kb0 + 1, rb1); }
+    if (nkb > 0) { load_op(ta, 0, kb0, ra0); load_op(tb, 1, kb0, rb0); }
+    if (nkb > 1) { load_op(ta, 0, kb0 + 1, ra1); load_op(tb, 1, kb0 + 1, rb1); }
     for (int i = 0; i < nkb; i += 2) {
       build(i, ra0, rb0);
-      if (i + 2 < nkb) { load_op(ta, 0, A, offAm, rows_a, kb0 + i + 2, ra0); load_op(tb, 1, Bm, offBn, rows_b, kb0 + i + 2, rb0); }
+      if (i + 2 < nkb) { load_op(ta, 0, kb0 + i + 2, ra0); load_op(tb, 1, kb0 + i + 2, rb0); }
       if (i + 1 < nkb) {
         build(i + 1, ra1, rb1);
-        if (i + 3 < nkb) { load_op(ta, 0, A, offAm, rows_a, kb0 + i + 3, ra1); load_op(tb, 1, Bm, offBn, rows_b, kb0 + i + 3, rb1); }
+        if (i + 3 < nkb) { load_op(ta, 0, kb0 + i + 3, ra1); load_op(tb, 1, kb0 + i + 3, rb1); }
       }
     }
 
