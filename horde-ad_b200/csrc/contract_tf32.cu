@@ -106,6 +106,7 @@ __device__ __forceinline__ void cg_off32(const hb_cgroup &g, uint32_t lin, int &
   }
 }
 
+template <int AMODE, int BMODE>
 __global__ void __launch_bounds__(NBUILD + 32, 1)
     hb_contract_tf32_kernel(const __grid_constant__ tf32_params P, const float *__restrict__ A,
                             const float *__restrict__ Bm, float *__restrict__ C) {
@@ -217,10 +218,10 @@ __global__ void __launch_bounds__(NBUILD + 32, 1)
       int srow[4];          // ... and its row (B tile: rows beyond BN are not stored)
       int rot;
     };
-    auto make_op = [&](int which, const float *base, const int *offtab, int rows) {
+    auto make_op = [&](int mode, const float *base, const int *offtab, int rows) {
       op_thread t;
       t.rmask = 0;
-      if (!P.mn[which]) {
+      if (!(mode & 1)) {
         const int kc = (lane >> 3) + 4 * (warp & 1), r0 = (warp >> 1) * 8 + (lane & 7);
         t.kq = kc * 4;
         t.rot = 0;
@@ -248,7 +249,7 @@ __global__ void __launch_bounds__(NBUILD + 32, 1)
       return t;
     };
     const int rows_a = (int)min((int64_t)BM, P.Mtot - m0), rows_b = (int)min((int64_t)BN, P.Ntot - n0);
-    const op_thread ta = make_op(0, A, offAm, rows_a), tb = make_op(1, Bm, offBn, rows_b);
+    const op_thread ta = make_op(AMODE, A, offAm, rows_a), tb = make_op(BMODE, Bm, offBn, rows_b);
 
     // element offset of reduced index k in operand `which`
     auto koff = [&](int64_t k, int which) {
@@ -258,14 +259,16 @@ __global__ void __launch_bounds__(NBUILD + 32, 1)
       return which ? ob : oa;
     };
     // fetch this thread's 16 elements of one operand for k block kb
-    auto load_op = [&](const op_thread &t, int which, int kb, float (&r)[4][4]) {
-      const int mn = P.mn[which], contig = P.contig4[which], vec = P.vec[which];
+    auto load_op = [&](const op_thread &t, auto which_c, int kb, float (&r)[4][4]) {
+      constexpr int which = decltype(which_c)::value;
+      constexpr int mode = which ? BMODE : AMODE;
+      constexpr bool mn = mode & 1, contig = mode & 2, vec = mode & 4;
       const int64_t k0 = (int64_t)kb * BK + t.kq;
       const bool fullk = (int64_t)(kb + 1) * BK <= P.Ktot;
       int ko[4];
       unsigned kmask = 0;
-      if (!mn) {
-        if (contig) {   // Ktot % 4 == 0 here: the chunk is inside or outside as a whole
+      if constexpr (!mn) {
+        if constexpr (contig) {   // Ktot % 4 == 0 here: the chunk is inside or outside as a whole
           const bool in = fullk || k0 < P.Ktot;
           const int o = in ? koff(k0, which) : 0;
 #pragma unroll
@@ -279,7 +282,7 @@ __global__ void __launch_bounds__(NBUILD + 32, 1)
             kmask |= (unsigned)in << i;
           }
         }
-        if (vec) {
+        if constexpr (vec) {
 #pragma unroll
           for (int j = 0; j < 4; j++) {
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -288,9 +291,16 @@ __global__ void __launch_bounds__(NBUILD + 32, 1)
           }
         } else if (t.rmask == 15u && kmask == 15u) {
 #pragma unroll
-          for (int j = 0; j < 4; j++)
+          for (int j = 0; j < 4; j++) {
+            if constexpr (contig) {   // one address per row, the four k at immediate offsets
+              const float *q = t.rp[j] + ko[0];
 #pragma unroll
-            for (int i = 0; i < 4; i++) r[j][i] = __ldg(t.rp[j] + ko[i]);
+              for (int i = 0; i < 4; i++) r[j][i] = __ldg(q + i);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 4; i++) r[j][i] = __ldg(t.rp[j] + ko[i]);
+            }
+          }
         } else {
 #pragma unroll
           for (int j = 0; j < 4; j++)
@@ -315,7 +325,7 @@ __global__ void __launch_bounds__(NBUILD + 32, 1)
 #pragma unroll
           for (int i = 0; i < 4; i++) ko[i] = __shfl_sync(0xffffffffu, mine, i);
         }
-        if (contig && vec) {
+        if constexpr (contig && vec) {
 #pragma unroll
           for (int i = 0; i < 4; i++) {
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -324,9 +334,16 @@ __global__ void __launch_bounds__(NBUILD + 32, 1)
           }
         } else if (t.rmask == 15u && kmask == 15u) {
 #pragma unroll
-          for (int i = 0; i < 4; i++)
+          for (int i = 0; i < 4; i++) {
+            if constexpr (contig) {   // one address per k, the four rows at immediate offsets
+              const float *q = t.rp[0] + ko[i];
 #pragma unroll
-            for (int j = 0; j < 4; j++) r[j][i] = __ldg(t.rp[j] + ko[i]);
+              for (int j = 0; j < 4; j++) r[j][i] = __ldg(q + j);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; j++) r[j][i] = __ldg(t.rp[j] + ko[i]);
+            }
+          }
         } else {
 #pragma unroll
           for (int i = 0; i < 4; i++)
@@ -348,13 +365,13 @@ __global__ void __launch_bounds__(NBUILD + 32, 1)
       *(float4 *)(tile_hi + off) = make_float4(h[0], h[1], h[2], h[3]);
       *(float4 *)(tile_hi + TILE_BYTES + off) = make_float4(l[0], l[1], l[2], l[3]);
     };
-    auto store_op = [&](uint8_t *tile_hi, const op_thread &t, int which, const float (&r)[4][4], int nrows) {
-      if (!P.mn[which]) {
+    auto store_op = [&](uint8_t *tile_hi, const op_thread &t, auto which_c, const float (&r)[4][4], int nrows) {
+      constexpr int mode = decltype(which_c)::value ? BMODE : AMODE;
+      if constexpr (!(mode & 1)) {
 #pragma unroll
         for (int j = 0; j < 4; j++)
           if (t.srow[j] < nrows) split_store(tile_hi, t.st[j], r[j]);
-        return;
-      }
+      } else {
       // store step j writes row (j + rot) & 3 of the thread's block: rotate the rows by rot with two select levels
       float s1[4][4], s2[4][4];
 #pragma unroll
@@ -369,14 +386,17 @@ __global__ void __launch_bounds__(NBUILD + 32, 1)
 #pragma unroll
         for (int j = 0; j < 4; j++) split_store(tile_hi, t.st[j], s2[j]);
       }
+      }
     };
+    constexpr std::integral_constant<int, 0> opA{};
+    constexpr std::integral_constant<int, 1> opB{};
 
     auto build = [&](int i, const float (&ra)[4][4], const float (&rb)[4][4]) {
       const int s = i % STAGES;
       mbar_wait(empty_bar(s), (uint32_t)(((i / STAGES) & 1) ^ 1));
       uint8_t *st = smem + (size_t)s * STAGE_BYTES;
-      store_op(st, ta, 0, ra, BM);
-      store_op(st + 2 * TILE_BYTES, tb, 1, rb, BN);   // rows of the B tile beyond BN are never read by the MMA
+      store_op(st, ta, opA, ra, BM);
+      store_op(st + 2 * TILE_BYTES, tb, opB, rb, BN);   // rows of the B tile beyond BN are never read by the MMA
       // generic-proxy writes -> visible to the tensor core's async-proxy reads, then one arrival per warp
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
@@ -386,14 +406,14 @@ __global__ void __launch_bounds__(NBUILD + 32, 1)
     // two k blocks of loads in flight per thread: registers of block i + 2 are requested before block i + 1 is split
     // (three in flight measured slower: 68 vs 75 TFLOP/s on 4096^3 -- the loop is issue-bound, not latency-bound)
     float ra0[4][4], rb0[4][4], ra1[4][4], rb1[4][4];
-    if (nkb > 0) { load_op(ta, 0, kb0, ra0); load_op(tb, 1, kb0, rb0); }
-    if (nkb > 1) { load_op(ta, 0, kb0 + 1, ra1); load_op(tb, 1, kb0 + 1, rb1); }
+    if (nkb > 0) { load_op(ta, opA, kb0, ra0); load_op(tb, opB, kb0, rb0); }
+    if (nkb > 1) { load_op(ta, opA, kb0 + 1, ra1); load_op(tb, opB, kb0 + 1, rb1); }
     for (int i = 0; i < nkb; i += 2) {
       build(i, ra0, rb0);
-      if (i + 2 < nkb) { load_op(ta, 0, kb0 + i + 2, ra0); load_op(tb, 1, kb0 + i + 2, rb0); }
+      if (i + 2 < nkb) { load_op(ta, opA, kb0 + i + 2, ra0); load_op(tb, opB, kb0 + i + 2, rb0); }
       if (i + 1 < nkb) {
         build(i + 1, ra1, rb1);
-        if (i + 3 < nkb) { load_op(ta, 0, kb0 + i + 3, ra1); load_op(tb, 1, kb0 + i + 3, rb1); }
+        if (i + 3 < nkb) { load_op(ta, opA, kb0 + i + 3, ra1); load_op(tb, opB, kb0 + i + 3, rb1); }
       }
     }
 
@@ -589,13 +609,29 @@ int hb_contract_tf32(const hb_contractp &Pin, const float *A, const float *B, fl
     P.partial = (float *)scratch;
   }
   const size_t smem_bytes = (size_t)STAGES * STAGE_BYTES + BM * 4 + 128 * 4 + BM * 8 + 128 * 8 + (2 * STAGES + 1) * 8 + 16;
-  static bool attr_set = false;
-  if (!attr_set) {
-    HB_CUDA(cudaFuncSetAttribute(hb_contract_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-    attr_set = true;
+  // one instantiation per pair of fetch modes (bit 0 = m-fast, bit 1 = 4-element runs, bit 2 = 128-bit loads);
+  // vec implies contig: modes 0, 1, 2, 3, 6, 7
+  typedef void (*kern_t)(const tf32_params, const float *, const float *, float *);
+  static kern_t table[8][8];
+  static bool table_set = false;
+  if (!table_set) {
+#define HB_TF_ROW(a)                                                                                           \
+  table[a][0] = hb_contract_tf32_kernel<a, 0>; table[a][1] = hb_contract_tf32_kernel<a, 1>;                    \
+  table[a][2] = hb_contract_tf32_kernel<a, 2>; table[a][3] = hb_contract_tf32_kernel<a, 3>;                    \
+  table[a][6] = hb_contract_tf32_kernel<a, 6>; table[a][7] = hb_contract_tf32_kernel<a, 7>;
+    HB_TF_ROW(0) HB_TF_ROW(1) HB_TF_ROW(2) HB_TF_ROW(3) HB_TF_ROW(6) HB_TF_ROW(7)
+#undef HB_TF_ROW
+    for (int a = 0; a < 8; a++)
+      for (int b = 0; b < 8; b++)
+        if (table[a][b])
+          HB_CUDA(cudaFuncSetAttribute(table[a][b], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    table_set = true;
   }
+  const int am = P.mn[0] | (P.contig4[0] << 1) | (P.vec[0] << 2), bm = P.mn[1] | (P.contig4[1] << 1) | (P.vec[1] << 2);
+  kern_t kern = table[am][bm];
+  HB_REQUIRE(kern, "tf32 contraction: no kernel for fetch modes %d, %d", am, bm);
   dim3 grid((unsigned)tm, (unsigned)tn, (unsigned)(nb * splits));
-  hb_contract_tf32_kernel<<<grid, NBUILD + 32, smem_bytes, g_hb.stream>>>(P, A, B, C);
+  kern<<<grid, NBUILD + 32, smem_bytes, g_hb.stream>>>(P, A, B, C);
   HB_LAUNCHED();
   if (splits > 1) {
     int64_t total = P.Mtot * P.Ntot * nb;
