@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "comm.cuh"
 #include "lazy.cuh"
 
 typedef struct ncclComm *ncclComm_t;
@@ -139,7 +140,10 @@ struct hb_fcomm {
   unsigned long long *ctl = nullptr;  // local: [0] = steps completed, [1] = CTAs done in the running step
   size_t cap = 0;
 };
+// scalar exchange area of every rank's block (global-objective mode, comm.cuh): [HB_SX_BYTES] after the control words
 static hb_fcomm g_fc;
+static hb_scalar_xchg g_sx;          // peer-mapped scalar slots (world > 1)
+static int g_global_objective = 0;
 static void *g_fc_block = nullptr;
 static void *g_fc_peer[8] = {};
 static bool g_fc_ready = false;
@@ -240,7 +244,7 @@ static int fcomm_setup(size_t cap_bytes) {
     return HB_OK;
   }
   HB_REQUIRE(g_nccl.world <= 8, "fused exchange: at most 8 ranks of one NVSwitch domain (have %d)", g_nccl.world);
-  const size_t total = flag_bytes + ctl_bytes + 2 * cap_bytes;
+  const size_t total = flag_bytes + ctl_bytes + HB_SX_BYTES + 2 * cap_bytes;
   HB_CUDA(cudaMalloc(&g_fc_block, total));
   HB_CUDA(cudaMemset(g_fc_block, 0, total));
   // the block is zero before its handle leaves this process: a peer can only raise a flag in it after the exchange
@@ -265,8 +269,14 @@ static int fcomm_setup(size_t cap_bytes) {
       g_fc_peer[r] = base;
     }
     g_fc.flags[r] = (unsigned long long *)base;
-    g_fc.buf[r] = (char *)base + flag_bytes + ctl_bytes;
+    g_fc.buf[r] = (char *)base + flag_bytes + ctl_bytes + HB_SX_BYTES;
+    char *sx = (char *)base + flag_bytes + ctl_bytes;
+    g_sx.flag[r] = (unsigned long long *)sx;                       // [2 kinds][8 ranks]
+    g_sx.val[r] = (double *)(sx + 2 * 8 * sizeof(unsigned long long));   // [2 parities][2 kinds][8 ranks]
   }
+  g_sx.rank = g_nccl.rank;
+  g_sx.world = g_nccl.world;
+  g_sx.ctl = (unsigned long long *)((char *)g_fc_block + flag_bytes + ctl_bytes + HB_SX_BYTES - 64);
   g_fc.ctl = (unsigned long long *)((char *)g_fc_block + flag_bytes);
   g_fc_ready = true;
   return HB_OK;
@@ -321,7 +331,25 @@ extern "C" int hb_allreduce_adam_step(hb_array *bucket, int64_t n_params, hb_arr
   return HB_OK;
 }
 
+// ---- global-objective mode: lossSoftMaxCrossEntropyS normalises over the WHOLE [10, batch]
+// tensor (CommonShapedOps.hs:89-111), so a batch sharded over G ranks equals the reference's one-device step only if
+// `minimum u` and `sum (exp (u - min))` are taken over all shards.  When switched on (and world > 1) hb_softmax_xent
+// exchanges the two scalars through peer-mapped slots inside its kernel, combined in rank order on every rank.
+extern "C" int hb_comm_set_global_objective(int on) {
+  HB_CHECK_INIT();
+  HB_REQUIRE(!on || g_nccl.world == 1 || g_fc_ready, "global objective: hb_comm_init has not been called");
+  g_global_objective = on ? 1 : 0;
+  return HB_OK;
+}
+
+bool hb_comm_scalar_xchg(hb_scalar_xchg *out) {
+  if (!g_global_objective || g_nccl.world <= 1 || !g_fc_ready) return false;
+  *out = g_sx;
+  return true;
+}
+
 extern "C" int hb_comm_destroy(void) {
+  g_global_objective = 0;
   fcomm_teardown();
   if (g_nccl.comm) {
     g_nccl.CommDestroy(g_nccl.comm);

@@ -5,6 +5,7 @@
 // softmax-cross-entropy loss (lossSoftMaxCrossEntropyS, :89-111).
 // All kernels are HBM-bound single passes.
 #include "common.cuh"
+#include "comm.cuh"
 #include "lazy.cuh"
 #include "iter.cuh"
 
@@ -487,17 +488,109 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// One CTA for the whole loss (small minibatches -- a 512-sample shard has 5120 logits -- and every global-objective
+// step): min, sum of exponentials, loss and dual in ONE launch instead of four, fixed reduction trees -> deterministic.
+// exp (u - min) is computed once (kept in the dual's buffer between the passes when the dual is wanted).
+// Global objective (comm.cuh): thread 0 exchanges the shard's minimum and exponential sum with the peer ranks
+// through NVLink-mapped slots, so that softMax is normalised over ALL shards as on one device.
+__device__ __forceinline__ double hb_sx_exchange(const hb_scalar_xchg &X, int kind, double mine, unsigned long long e,
+                                                 bool is_min) {
+  const int par = (int)(e & 1);
+  for (int p = 0; p < X.world; p++) *(volatile double *)&X.val[p][(par * 2 + kind) * 8 + X.rank] = mine;
+  __threadfence_system();
+  for (int p = 0; p < X.world; p++)
+    if (p != X.rank)
+      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(X.flag[p] + kind * 8 + X.rank), "l"(e) : "memory");
+  for (int q = 0; q < X.world; q++) {
+    if (q == X.rank) continue;
+    const unsigned long long *f = X.flag[X.rank] + kind * 8 + q;
+    unsigned long long v;
+    const long long t0 = clock64();
+    do {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+      if (v < e) {
+        __nanosleep(64);
+        if (clock64() - t0 > 20000000000ll) __trap();   // a peer that never arrives must not hang the GPU
+      }
+    } while (v < e);
+  }
+  const volatile double *mv = X.val[X.rank] + (par * 2 + kind) * 8;
+  double r = mv[0];
+  for (int q = 1; q < X.world; q++) r = is_min ? (mv[q] < r ? mv[q] : r) : r + mv[q];   // rank order on every rank
+  return r;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(1024)
+    hb_softmax_xent_one_kernel(const T *__restrict__ u, hb_dims ud, const T *__restrict__ ex, hb_dims ed, int64_t n,
+                               T scale, T *__restrict__ loss, T *__restrict__ dl, hb_scalar_xchg X) {
+  __shared__ T smem[32];
+  __shared__ double bcast;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  unsigned long long e = 0;
+  if (X.world > 1) e = *(volatile unsigned long long *)X.ctl + 1;
+  T mn = u[hb_offset_of(ud, tid < n ? tid : 0)];
+  for (int64_t i = tid; i < n; i += nt) {
+    T v = u[hb_offset_of(ud, i)];
+    mn = v < mn ? v : mn;
+  }
+  mn = hb_block_reduce<T>(mn, smem, true);
+  if (X.world > 1) {
+    if (tid == 0) bcast = hb_sx_exchange(X, 0, (double)mn, e, true);
+    __syncthreads();
+    mn = (T)bcast;
+  }
+  T s = T(0);
+  for (int64_t i = tid; i < n; i += nt) {
+    T ev = exp(u[hb_offset_of(ud, i)] - mn);
+    if (dl) dl[i] = ev;
+    s += ev;
+  }
+  s = hb_block_reduce<T>(s, smem, false);
+  if (X.world > 1) {
+    __syncthreads();
+    if (tid == 0) bcast = hb_sx_exchange(X, 1, (double)s, e, false);
+    __syncthreads();
+    s = (T)bcast;
+  }
+  const T rs = T(1) / s;
+  T l = T(0);
+  for (int64_t i = tid; i < n; i += nt) {
+    T sm = rs * (dl ? dl[i] : exp(u[hb_offset_of(ud, i)] - mn));
+    T t = ex[hb_offset_of(ed, i)];
+    l += log(sm) * t;
+    if (dl) dl[i] = scale * (sm - t);
+  }
+  l = hb_block_reduce<T>(l, smem, false);
+  if (tid == 0) {
+    *loss = scale * (-l);
+    if (X.world > 1) {
+      __threadfence();
+      *(volatile unsigned long long *)X.ctl = e;
+    }
+  }
+}
+
 template <typename T>
 static int softmax_xent_launch(const hb_array *logits, const hb_array *expected, const hb_dims &ud,
                                const hb_dims &ed, int64_t n, double scale, hb_array *loss, hb_array *dl) {
+  const T *u = (const T *)hb_data(logits), *ex = (const T *)hb_data(expected);
+  T *lp = (T *)hb_data(loss), *dp = dl ? (T *)hb_data(dl) : nullptr;
+  hb_scalar_xchg X;
+  memset(&X, 0, sizeof X);
+  X.world = 1;
+  const bool global = hb_comm_scalar_xchg(&X);
+  if (global || n <= 16384) {
+    hb_softmax_xent_one_kernel<T><<<1, 1024, 0, g_hb.stream>>>(u, ud, ex, ed, n, (T)scale, lp, dp, X);
+    HB_LAUNCHED();
+    return HB_OK;
+  }
   int nb = (int)((n + 511) / 512);
   if (nb > 128) nb = 128;
   if (nb < 1) nb = 1;
   void *scr;
   HB_TRY(hb_scratch((size_t)3 * 128 * sizeof(T), &scr));
   T *pmin = (T *)scr, *psum = pmin + 128, *ploss = psum + 128;
-  const T *u = (const T *)hb_data(logits), *ex = (const T *)hb_data(expected);
-  T *lp = (T *)hb_data(loss), *dp = dl ? (T *)hb_data(dl) : nullptr;
   hb_softmax_xent_phase<T, 0><<<nb, 256, 0, g_hb.stream>>>(u, ud, ex, ed, n, (T)scale, pmin, psum, ploss, lp, dp);
   HB_LAUNCHED();
   hb_softmax_xent_phase<T, 1><<<nb, 256, 0, g_hb.stream>>>(u, ud, ex, ed, n, (T)scale, pmin, psum, ploss, lp, dp);

@@ -111,7 +111,7 @@ PROTOTYPES = {
     "hb_prod_fold_grad": [P, C.c_double, PP, PP],
     "hb_graph_begin": [], "hb_graph_end": [PP], "hb_graph_launch": [P], "hb_graph_free": [P],
     "hb_comm_unique_id": [P], "hb_comm_init": [C.c_int, C.c_int, P],
-    "hb_allreduce_sum": [P, C.c_double], "hb_comm_destroy": [],
+    "hb_allreduce_sum": [P, C.c_double], "hb_comm_destroy": [], "hb_comm_set_global_objective": [C.c_int],
     "hb_allreduce_adam_step": [P, C.c_int64, P, P, P, P, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double],
     "hb_microbench": [C.c_int, C.POINTER(C.c_double)],
     "hb_lazy_begin": [], "hb_lazy_end": [C.c_int, PP, C.c_uint, PP], "hb_lazy_abort": [],

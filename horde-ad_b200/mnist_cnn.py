@@ -70,11 +70,13 @@ def convMnistTwoS(T, x, params, fused=True):
     return T.binary("add", T.smatmul2(wR, hidden), T.stranspose([1, 0], T.sreplicate(N, bR)))
 
 
-def convMnistLossFusedS(T, glyphs, labels, params, fused=True):
+def convMnistLossFusedS(T, glyphs, labels, params, fused=True, loss_scale=None):
     """convMnistLossFusedS (MnistCnnShaped2.hs:111-136): glyphs [batch, h, w],
-    labels [batch, 10] one-hot; returns the 0-d loss."""
+    labels [batch, 10] one-hot; returns the 0-d loss.  `loss_scale` replaces the
+    `recip batch` factor (:136) when the tensor at hand is one shard of a larger
+    batch whose objective is normalised globally (train.py, objective="global")."""
     N, H, W = T.shape(glyphs)
     x = T.sreshape([N, 1, H, W], glyphs)
     result = convMnistTwoS(T, x, params, fused)
     targets = T.stranspose([1, 0], labels)
-    return nn.lossSoftMaxCrossEntropyS(T, targets, result, scale=1.0 / N)
+    return nn.lossSoftMaxCrossEntropyS(T, targets, result, scale=(1.0 / N if loss_scale is None else loss_scale))

@@ -31,10 +31,11 @@ def shard_range(rank: int, world: int, batch: int) -> tuple[int, int]:
     return rank * per, (rank + 1) * per
 
 
-def exchange_scale(world: int) -> float:
-    """Factor applied to the all-reduce SUM: the mean of per-shard mean losses / gradients equals the global
-    mean for equal shards (MnistCnnShaped2.hs:136)."""
-    return 1.0 / world
+def exchange_scale(world: int, objective: str = "shard") -> float:
+    """Factor applied to the all-reduce SUM.  objective="shard": the mean of per-shard mean losses / gradients
+    (MnistCnnShaped2.hs:136 applied to every shard).  objective="global": every shard already carries the global
+    `recip batch` factor and the globally normalised softmax, so the buckets are summed."""
+    return 1.0 if objective == "global" else 1.0 / world
 
 
 class BucketLayout:
@@ -106,10 +107,19 @@ class CnnTrainer:
 
     def __init__(self, dev: DeviceBackend, local_batch: int, kh=4, kw=4, c_out=16, n_hidden=64,
                  dtype=np.float64, world=1, seed=44, use_graph=True, optimizer="adam", gamma=0.02,
-                 program="vectorised", exchange="fused"):
+                 program="vectorised", exchange="fused", objective="shard"):
         assert program in ("vectorised", "vectorised-eager", "fused")
         assert exchange in ("fused", "nccl")
+        assert objective in ("shard", "global")
         self.program = program
+        # "shard": every rank optimises the reference objective of ITS shard (softmax normalised over the shard) and
+        #          the gradients are averaged -- the decomposition SURVEY.md 8e prescribes;
+        # "global": the N-rank step IS the reference's step on the whole batch: `minimum u` and `sum expU` of
+        #          lossSoftMaxCrossEntropyS (CommonShapedOps.hs:89-111) are exchanged across the ranks inside the loss
+        #          kernel (hb_comm_set_global_objective), every shard uses 1 / global batch, the buckets are summed
+        self.objective = objective if world > 1 else "shard"
+        if self.objective == "global":
+            call("hb_comm_set_global_objective", 1)
         # "fused": gradient exchange + 1/world + Adam in ONE kernel over peer-mapped buffers (hb_allreduce_adam_step,
         # deterministic rank-order sum, step counter on the device, so the whole step is one graph launch);
         # "nccl": ncclAllReduce, then the scale kernel, then the Adam kernel (round 1's path, the comparison arm)
@@ -151,14 +161,16 @@ class CnnTrainer:
         dev = self.dev
         fused = self.program == "fused"
         loss, grads = ad.grad(
-            dev, lambda T, *ps: mnist_cnn.convMnistLossFusedS(T, self.glyphs, self.labels, list(ps), fused=fused),
+            dev, lambda T, *ps: mnist_cnn.convMnistLossFusedS(
+                T, self.glyphs, self.labels, list(ps), fused=fused,
+                loss_scale=(1.0 / (self.B * self.world) if self.objective == "global" else None)),
             self.params)
         bucket = dev.flatten_concat(list(grads) + [loss])
         if self.exchange == "fused":
             call("hb_allreduce_adam_step", bucket.h, self.n_params, self.flat_p.h, self.flat_m.h, self.flat_v.h,
-                 self.t_dev.h, 1e-3, 0.9, 0.999, 1e-7, exchange_scale(self.world))
+                 self.t_dev.h, 1e-3, 0.9, 0.999, 1e-7, exchange_scale(self.world, self.objective))
         else:
-            call("hb_allreduce_sum", bucket.h, exchange_scale(self.world))
+            call("hb_allreduce_sum", bucket.h, exchange_scale(self.world, self.objective))
         return bucket
 
     def _apply(self, bucket):
@@ -308,6 +320,9 @@ class CnnTrainer:
         if self.prog is not None:
             self.prog.close()
             self.prog = None
+        if self.objective == "global":
+            call("hb_comm_set_global_objective", 0)
+            self.objective = "shard"
 
 
 def comm_init(rank: int, world: int, broadcast_bytes) -> None:

@@ -574,6 +574,17 @@ int hb_allreduce_adam_step(hb_array *bucket, int64_t n_params, hb_array *p,
                            hb_array *m, hb_array *v, hb_array *t_counter,
                            double alpha, double beta1, double beta2,
                            double epsilon, double scale);
+/* Global-objective mode.  lossSoftMaxCrossEntropyS (CommonShapedOps.hs:89-111)
+ * normalises its softmax over the WHOLE [labels, batch] tensor, so a batch
+ * sharded over G ranks reproduces the reference's one-device step only if
+ * `minimum u` and `sum (exp (u - minimum u))` range over all shards.  With
+ * on != 0 (and world > 1) every hb_softmax_xent call exchanges these two
+ * scalars with the peer ranks inside its kernel (peer-mapped slots over NVLink,
+ * combined in rank order: identical on every rank); the caller then passes the
+ * GLOBAL 1/batch as `scale` and sums (scale 1.0) instead of averaging the
+ * gradient buckets.  Every rank must make the same sequence of hb_softmax_xent
+ * calls.  Off by default (each rank optimises its own shard's objective). */
+int hb_comm_set_global_objective(int on);
 int hb_comm_destroy(void);
 
 /* -------------------------------------------------------- micro-benchmarks

@@ -4,7 +4,10 @@ all-reduce + Adam kernel (hb_allreduce_adam_step) -- and check
   * the exchanged bucket == mean of the two shard buckets (rtol 1e-14) and == the NCCL + scale path bit for bit
     (two summands commute),
   * parameters bit-identical across ranks after 5 steps, and equal to the NCCL-path trainer's,
-  * Adam's device-side step counter advanced identically."""
+  * Adam's device-side step counter advanced identically,
+  * objective="global" (min u and sum expU of the loss exchanged across the ranks inside the loss kernel): the summed
+    bucket of the two shards == the ORACLE's gradient and loss of the unfused reference program on the WHOLE batch
+    (1e-12 normwise) -- the N-GPU step is the reference's one-device step on the same inputs."""
 import os
 import socket
 
@@ -92,6 +95,27 @@ def _worker(rank, world, port, q):
     dist.all_gather_object(locs, local)
     out["bucket_is_mean_of_shards"] = bool(np.allclose(exchanged, sum(locs) * exchange_scale(world), rtol=1e-13, atol=1e-300))
     tr0.close()
+    # (3) global objective: sharded step == the oracle's step on the concatenated batch
+    trg = CnnTrainer(dev, B, **hyper, world=world, exchange="nccl", objective="global", use_graph=False)
+    trg.upload(gl.ptr, lb.ptr)
+    p_init = [p.copy() for p in trg.get_params()]
+    gbucket = dev.to_numpy(trg._gradient_program())          # recorded program is not needed here: one eager step
+    trg.close()
+    glall, lball = [None] * world, [None] * world
+    dist.all_gather_object(glall, np.array(gl.array))
+    dist.all_gather_object(lball, np.array(lb.array))
+    if rank == 0:
+        from oracle.concrete import ConcreteBackend
+        orc = ConcreteBackend()
+        G, L = orc.sconcrete(np.concatenate(glall)), orc.sconcrete(np.concatenate(lball))
+        oval, ograds = ad.grad(orc, lambda T, *ps: mnist_cnn.convMnistLossFusedS(T, G, L, list(ps), fused=False),
+                               [orc.sconcrete(p) for p in p_init])
+        ref = np.concatenate([orc.to_numpy(g).reshape(-1) for g in ograds] + [np.array([float(orc.kfromS(oval))])])
+        out["global_objective_rel_err"] = float(np.max(np.abs(gbucket - ref)) / np.max(np.abs(ref)))
+        out["global_loss"] = (float(gbucket[-1]), float(ref[-1]))
+    gb = [None] * world
+    dist.all_gather_object(gb, gbucket)
+    out["global_bucket_identical_across_ranks"] = bool(all(np.array_equal(gb[0], b) for b in gb))
     if rank == 0:
         q.put(out)
     dist.barrier()
@@ -117,3 +141,6 @@ def test_two_rank_exchange_and_training_on_hardware():
     assert out["fused_vs_nccl_params_equal"] and out["params_identical_across_ranks"], out
     assert out["bucket_is_mean_of_shards"], out
     assert all(np.isfinite(out["losses"])), out
+    assert out["global_objective_rel_err"] <= 1e-12, out
+    assert abs(out["global_loss"][0] - out["global_loss"][1]) <= 1e-12 * abs(out["global_loss"][1]), out
+    assert out["global_bucket_identical_across_ranks"], out
