@@ -448,9 +448,9 @@ def main():
     pass_stats = tr.prog.stats if tr.prog is not None else None
 
     # ---- side measurements (every rank runs them: the step contains the all-reduce)
-    def time_program(program, steps, warm, batch=None, graph=True, exchange=None):
+    def time_program(program, steps, warm, batch=None, graph=True, exchange=None, objective="shard"):
         t2 = CnnTrainer(dev, batch or local_batch, **HYPER, world=world, use_graph=graph, program=program,
-                        exchange=exchange or args.exchange)
+                        exchange=exchange or args.exchange, objective=objective)
         g2, l2 = gl, lb
         if batch and batch != local_batch:
             g2 = PinnedBuffer((batch, 28, 28), np.float64)
@@ -490,6 +490,22 @@ def main():
             other = "nccl" if args.exchange == "fused" else "fused"
             extras["exchange_comparison"] = {"this_run": args.exchange, "other": other,
                                              "other_ms_per_step": time_program("vectorised", min(K, 20), 3, exchange=other)[0]}
+        if world > 1:
+            # the step whose result equals the reference's one-device step on the whole batch: min u / sum expU of
+            # the loss exchanged across the ranks inside the loss kernel (train.py objective="global")
+            gms, gl_ = time_program("vectorised", min(K, 20), 3, objective="global")
+            extras["global_objective"] = {"ms_per_step": gms, "value": global_batch / (gms * 1e-3), "unit": "samples/s",
+                                          "first_step_loss": gl_,
+                                          "what": "N-rank step == reference step on the whole batch (2-GPU test: 1e-12 vs oracle)"}
+        if world > 1:
+            import bench_configs
+            try:
+                extras["rnn_dp"] = bench_configs.rnn_dp(dev, world, rank, barrier, max_over_ranks)
+                sums = [None] * world
+                dist.all_gather_object(sums, extras["rnn_dp"]["param_sum"])
+                extras["rnn_dp"]["params_identical_across_ranks"] = len(set(sums)) == 1
+            except Exception as e:      # a side measurement must not take the headline line down with it
+                extras["rnn_dp"] = {"error": repr(e)[:300]}
         if world > 1 and args.scaling == "strong":
             wms, _ = time_program("vectorised", min(K, 20), 3, batch=PER_GPU_BATCH)
             extras["weak_scaling"] = {"per_gpu_batch": PER_GPU_BATCH, "ms_per_step": wms,

@@ -352,5 +352,56 @@ def run_configs(dev, quick=False, skip_families=False, only_families=False, emit
 
 
 
+def rnn_dp(dev, world, rank, barrier, max_over_ranks, width=512, batch=1024, steps=8):
+    """BASELINE config 5 data-parallel: MnistRnnShaped2 (width 512, 28 steps), `batch` samples PER GPU, the gradient
+    program + flat bucket + the fused peer-memory all-reduce + Adam kernel captured into one CUDA graph (the same
+    exchange as the CNN trainer).  Called by every rank; returns the record (max over ranks of the device time)."""
+    from horde_ad_b200.train import BucketLayout, exchange_scale
+    rng = np.random.Generator(np.random.Philox(4200 + rank))
+    host = mnist_rnn.init_params(width, rng_range=0.05)
+    lay = BucketLayout([p.shape for p in host])
+    flat = lay.flatten(host, 0.0)[:lay.n_params]
+    fp, fm, fv = dev.sconcrete(flat), dev.sconcrete(np.zeros_like(flat)), dev.sconcrete(np.zeros_like(flat))
+    t_dev = dev.sconcrete(np.zeros((), np.int64))
+    params = [dev.sreshape(list(sh), dev.sslice(off, n, fp)) for sh, n, off in zip(lay.shapes, lay.sizes, lay.offsets)]
+    glyphs = dev.sconcrete(rng.uniform(0, 1, (batch, 28, 28)))
+    labels = dev.sconcrete(np.eye(10)[rng.integers(0, 10, batch)])
+
+    def step():
+        val, grads = ad.grad(dev, lambda T, *ps: mnist_rnn.rnnMnistLossFusedS(T, glyphs, labels, list(ps), fused=RNN_FUSION), params)
+        bucket = dev.flatten_concat(list(grads) + [val])
+        ffi.call("hb_allreduce_adam_step", bucket.h, lay.n_params, fp.h, fm.h, fv.h, t_dev.h, 1e-3, 0.9, 0.999, 1e-7,
+                 exchange_scale(world))
+        return bucket
+    b = step()                      # allocations, scratch
+    dev.sync()
+    del b
+    barrier()
+    ffi.call("hb_graph_begin")
+    try:
+        bucket = step()
+    finally:
+        gph = C.c_void_p()
+        ffi.call("hb_graph_end", C.byref(gph))
+    for _ in range(2):
+        ffi.call("hb_graph_launch", gph)
+    barrier()
+    ms = C.c_float()
+    ffi.call("hb_event_record", 6)
+    for _ in range(steps):
+        ffi.call("hb_graph_launch", gph)
+    ffi.call("hb_event_record", 7)
+    ffi.call("hb_event_elapsed_ms", 6, 7, C.byref(ms))
+    barrier()
+    step_ms = max_over_ranks(float(ms.value)) / steps
+    digest = float(np.sum(dev.to_numpy(fp)))
+    fl = 28 * 3 * 2.0 * batch * (28 * width + 3 * width * width)
+    ffi.call("hb_graph_free", gph)
+    return {"config": "MnistRnnShaped2 data-parallel", "width": width, "seq": 28, "per_gpu_batch": batch,
+            "n_gpus": world, "scaling": "weak", "ms_per_step": step_ms, "samples_per_s": batch * world / (step_ms * 1e-3),
+            "tflops_per_gpu": fl / (step_ms * 1e-3) / 1e12, "param_sum": digest,
+            "exchange": "hb_allreduce_adam_step (fused peer-memory all-reduce + Adam) inside the step's CUDA graph"}
+
+
 if __name__ == "__main__":
     main()

@@ -79,9 +79,10 @@ extern "C" int hb_comm_init(int rank, int world, const void *id_bytes) {
   ncclUniqueId id;
   memcpy(&id, id_bytes, HB_UNIQUE_ID_BYTES);
   HB_NCCL(g_nccl.CommInitRank(&g_nccl.comm, world, id, rank));
-  // peer-mapped exchange buffers of the fused all-reduce + optimizer kernel (32 MB per parity: every model of the
-  // reference's examples fits -- MnistFcnnRanked2 at 1500|500 has 1.93 M parameters = 15.4 MB in Double)
-  return fcomm_setup((size_t)32 << 20);
+  // peer-mapped exchange buffers of the fused all-reduce + optimizer kernel: 2 parities x 8 source slots of 16 MB
+  // (every model of the reference's examples fits -- MnistFcnnRanked2 at 1500|500 has 1.93 M parameters = 15.4 MB in
+  // Double); 256 MB of the 180 GB
+  return fcomm_setup((size_t)16 << 20);
 }
 
 template <typename T>
@@ -121,22 +122,23 @@ extern "C" int hb_allreduce_sum(hb_array *bucket, double scale) {
 // ------------------------------------------------- fused exchange + optimizer
 // ONE kernel per training step does what ncclAllReduce + hb_scale_kernel + hb_adam_kernel did in three launches
 // (65 us + 2 launches for a 0.46 MB bucket at 8 GPUs, the top entry of the strong-scaling step in round 1):
-//   every rank publishes its gradient bucket in a peer-mapped buffer (cudaIpc over NVLink 5 / NVSwitch: every GPU
-//   reaches every peer at full bandwidth), raises a per-chunk flag in every peer's memory, waits for the peers'
-//   flags, then PULLS the G buckets with plain peer loads and adds them in rank order 0..G-1 -- the same order on
-//   every rank, so the reduced bucket (and therefore the replicated parameters) are bit-identical across ranks and
-//   across runs, independently of NCCL's algorithm choice -- scales by 1/G and applies the Adam update
-//   (OptimizerTools.hs:134-232) to its replica in the same pass.
-// Chunk c of rank A only ever waits for chunk c of the peers (no grid-wide barrier); buckets are double-buffered
+//   PUSH: every rank writes its chunk of the gradient bucket straight into a slot of EVERY peer's exchange buffer
+//   (cudaIpc-mapped over NVLink 5 / NVSwitch: posted remote stores, every GPU reaches every peer at full
+//   bandwidth), fences, and raises a per-chunk flag in the peer's memory; the receiver waits for its peers' flags
+//   and then reads only LOCAL memory: it adds the G contributions in rank order 0..G-1 -- the same order on every
+//   rank, so the reduced bucket (and therefore the replicated parameters) are bit-identical across ranks and
+//   across runs, independently of any library's algorithm choice -- scales by 1/G (or 1) and applies the Adam update
+//   (OptimizerTools.hs:134-232) to its replica in the same pass.  No remote LOAD is on the critical path.
+// Chunk c of rank A only ever waits for chunk c of the peers (no grid-wide barrier); slots are double-buffered
 // by step parity, so one flag round per step is the only synchronisation: a rank reaches step e+2 (which overwrites
-// the parity-e buffer) only after its step e+1 kernel saw every peer's e+1 flags, i.e. after every peer finished
-// its step-e kernel and with it all reads of the parity-e buffers.
+// the parity-e slots it owns in its peers' buffers) only after its step e+1 kernel saw every peer's e+1 flags, i.e.
+// after every peer finished its step-e kernel and with it all reads of the parity-e slots.
 // The step counter of Adam lives on the device (a CUDA graph replays the launch unchanged).
-#define HB_COMM_MAXCHUNKS 64
+#define HB_COMM_MAXCHUNKS 256
 struct hb_fcomm {
   int rank = 0, world = 1;
-  char *buf[8] = {};                  // peer-mapped: [2 parities][cap bytes]
-  unsigned long long *flags[8] = {};  // peer-mapped: [world][HB_COMM_MAXCHUNKS] step numbers
+  char *buf[8] = {};                  // peer-mapped: [2 parities][8 source ranks][cap bytes]
+  unsigned long long *flags[8] = {};  // peer-mapped: [8 source ranks][HB_COMM_MAXCHUNKS] step numbers
   unsigned long long *ctl = nullptr;  // local: [0] = steps completed, [1] = CTAs done in the running step
   size_t cap = 0;
 };
@@ -157,10 +159,6 @@ __device__ __forceinline__ unsigned long long hb_ld_acquire_sys(const unsigned l
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-template <typename T>
-__device__ __forceinline__ T hb_ld_peer(const T *p) {  // peer memory: never from a stale L1 line
-  return *(const volatile T *)p;
-}
 
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -173,9 +171,14 @@ __global__ void __launch_bounds__(256)
   const int64_t per = ((n + nchunks - 1) / nchunks + 1) & ~(int64_t)1;
   const int64_t lo = min((int64_t)c * per, n), hi = min(lo + per, n);
   const int par = (int)(e & 1);
+  const size_t slot = ((size_t)par * 8 + C.rank) * C.cap;   // where THIS rank's data lives in every peer's buffer
   if (C.world > 1) {
-    T *mine = (T *)(C.buf[C.rank] + (size_t)par * C.cap);
-    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) mine[i] = bucket[i];
+    // push: posted stores into the peers' memory
+    for (int q = 1; q < C.world; q++) {
+      const int peer = (C.rank + q) % C.world;
+      T *dst = (T *)(C.buf[peer] + slot);
+      for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) dst[i] = bucket[i];
+    }
     __syncthreads();
     if (threadIdx.x == 0) __threadfence_system();
     __syncthreads();
@@ -186,7 +189,7 @@ __global__ void __launch_bounds__(256)
       // a peer that never arrives (crashed rank) must not hang the GPU: give up after ~10 s and fault the launch
       const long long t0 = clock64();
       while (hb_ld_acquire_sys(f) < e) {
-        __nanosleep(64);
+        __nanosleep(32);
         if (clock64() - t0 > 20000000000ll) __trap();
       }
     }
@@ -195,12 +198,13 @@ __global__ void __launch_bounds__(256)
   const T one = (T)1;
   const double alphat_d = alpha * sqrt(1.0 - hb_powi_ghc(beta2, t)) / (1.0 - hb_powi_ghc(beta1, t));
   const T alphat = (T)alphat_d, b1 = (T)beta1, b2 = (T)beta2, eps = (T)epsilon;
+  const char *mine = C.world > 1 ? C.buf[C.rank] + (size_t)par * 8 * C.cap : nullptr;
   for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
     T acc;
     if (C.world > 1) {
       acc = (T)0;
-      for (int r = 0; r < C.world; r++)   // fixed rank order: bit-identical on every rank
-        acc = acc + (r == C.rank ? bucket[i] : hb_ld_peer((const T *)(C.buf[r] + (size_t)par * C.cap) + i));
+      for (int r = 0; r < C.world; r++)   // fixed rank order: bit-identical on every rank; L2 loads (peers wrote it)
+        acc = acc + (r == C.rank ? bucket[i] : __ldcg((const T *)(mine + (size_t)r * C.cap) + i));
     } else {
       acc = bucket[i];
     }
@@ -244,7 +248,7 @@ static int fcomm_setup(size_t cap_bytes) {
     return HB_OK;
   }
   HB_REQUIRE(g_nccl.world <= 8, "fused exchange: at most 8 ranks of one NVSwitch domain (have %d)", g_nccl.world);
-  const size_t total = flag_bytes + ctl_bytes + HB_SX_BYTES + 2 * cap_bytes;
+  const size_t total = flag_bytes + ctl_bytes + HB_SX_BYTES + 2 * 8 * cap_bytes;
   HB_CUDA(cudaMalloc(&g_fc_block, total));
   HB_CUDA(cudaMemset(g_fc_block, 0, total));
   // the block is zero before its handle leaves this process: a peer can only raise a flag in it after the exchange
@@ -317,8 +321,9 @@ extern "C" int hb_allreduce_adam_step(hb_array *bucket, int64_t n_params, hb_arr
   if (!g_fc_ready) HB_TRY(fcomm_setup(0));   // single process without hb_comm_init
   HB_REQUIRE(g_fc.world == 1 || (size_t)n * hb_dtype_size(bucket->dt) <= g_fc.cap,
              "allreduce_adam: bucket of %lld bytes exceeds the exchange buffer (%zu)", (long long)n * 8, g_fc.cap);
-  // chunks: enough CTAs to saturate the links on a MB-sized bucket, few enough that all are co-resident
-  int chunks = (int)std::min<int64_t>(HB_COMM_MAXCHUNKS, std::max<int64_t>(1, n / 2048));
+  // chunks: one or two elements per thread for the small buckets of the reference's models (latency is what counts),
+  // all CTAs co-resident
+  int chunks = (int)std::min<int64_t>(HB_COMM_MAXCHUNKS, std::max<int64_t>(1, (n + 511) / 512));
   if (bucket->dt == HB_F64)
     hb_allreduce_adam_kernel<double><<<chunks, 256, 0, g_hb.stream>>>(
         g_fc, (double *)hb_data(bucket), n, n_params, (double *)hb_data(p), (double *)hb_data(m), (double *)hb_data(v),
