@@ -520,19 +520,48 @@ __device__ __forceinline__ double hb_sx_exchange(const hb_scalar_xchg &X, int ki
   return r;
 }
 
-template <typename T>
+// linear index -> element offset with 32-bit arithmetic (n < 2^31 elements)
+__device__ __forceinline__ int hb_offset_of32(const hb_dims &d, uint32_t lin) {
+  int off = 0;
+#pragma unroll 1
+  for (int i = d.rank - 1; i >= 0; i--) {
+    const uint32_t s = (uint32_t)d.shape[i];
+    const uint32_t q = lin / s, r = lin - q * s;
+    off += (int)r * (int)d.stride[i];
+    lin = q;
+  }
+  return off;
+}
+
+// REG: the thread's (at most NE) logits stay in registers through the three passes (n <= NE * 1024): every logit and
+// label is read once, every exp evaluated once; otherwise the passes re-read memory (exp kept in the dual's buffer).
+template <typename T, bool REG>
 __global__ void __launch_bounds__(1024)
     hb_softmax_xent_one_kernel(const T *__restrict__ u, hb_dims ud, const T *__restrict__ ex, hb_dims ed, int64_t n,
                                T scale, T *__restrict__ loss, T *__restrict__ dl, hb_scalar_xchg X) {
+  constexpr int NE = 8;
   __shared__ T smem[32];
   __shared__ double bcast;
   const int tid = threadIdx.x, nt = blockDim.x;
   unsigned long long e = 0;
   if (X.world > 1) e = *(volatile unsigned long long *)X.ctl + 1;
-  T mn = u[hb_offset_of(ud, tid < n ? tid : 0)];
-  for (int64_t i = tid; i < n; i += nt) {
-    T v = u[hb_offset_of(ud, i)];
-    mn = v < mn ? v : mn;
+  T val[NE];
+  T mn;
+  if (REG) {
+#pragma unroll
+    for (int k = 0; k < NE; k++) {
+      const int64_t i = tid + (int64_t)k * nt;
+      val[k] = u[hb_offset_of32(ud, (uint32_t)(i < n ? i : 0))];   // out-of-range slots repeat element 0 (harmless for min)
+    }
+    mn = val[0];
+#pragma unroll
+    for (int k = 1; k < NE; k++) mn = val[k] < mn ? val[k] : mn;
+  } else {
+    mn = u[hb_offset_of(ud, tid < n ? tid : 0)];
+    for (int64_t i = tid; i < n; i += nt) {
+      T v = u[hb_offset_of(ud, i)];
+      mn = v < mn ? v : mn;
+    }
   }
   mn = hb_block_reduce<T>(mn, smem, true);
   if (X.world > 1) {
@@ -541,10 +570,19 @@ __global__ void __launch_bounds__(1024)
     mn = (T)bcast;
   }
   T s = T(0);
-  for (int64_t i = tid; i < n; i += nt) {
-    T ev = exp(u[hb_offset_of(ud, i)] - mn);
-    if (dl) dl[i] = ev;
-    s += ev;
+  if (REG) {
+#pragma unroll
+    for (int k = 0; k < NE; k++) {
+      const int64_t i = tid + (int64_t)k * nt;
+      val[k] = i < n ? exp(val[k] - mn) : T(0);
+      s += val[k];
+    }
+  } else {
+    for (int64_t i = tid; i < n; i += nt) {
+      T ev = exp(u[hb_offset_of(ud, i)] - mn);
+      if (dl) dl[i] = ev;
+      s += ev;
+    }
   }
   s = hb_block_reduce<T>(s, smem, false);
   if (X.world > 1) {
@@ -555,11 +593,24 @@ __global__ void __launch_bounds__(1024)
   }
   const T rs = T(1) / s;
   T l = T(0);
-  for (int64_t i = tid; i < n; i += nt) {
-    T sm = rs * (dl ? dl[i] : exp(u[hb_offset_of(ud, i)] - mn));
-    T t = ex[hb_offset_of(ed, i)];
-    l += log(sm) * t;
-    if (dl) dl[i] = scale * (sm - t);
+  if (REG) {
+#pragma unroll
+    for (int k = 0; k < NE; k++) {
+      const int64_t i = tid + (int64_t)k * nt;
+      if (i < n) {
+        T sm = rs * val[k];
+        T t = ex[hb_offset_of32(ed, (uint32_t)i)];
+        l += log(sm) * t;
+        if (dl) dl[i] = scale * (sm - t);
+      }
+    }
+  } else {
+    for (int64_t i = tid; i < n; i += nt) {
+      T sm = rs * (dl ? dl[i] : exp(u[hb_offset_of(ud, i)] - mn));
+      T t = ex[hb_offset_of(ed, i)];
+      l += log(sm) * t;
+      if (dl) dl[i] = scale * (sm - t);
+    }
   }
   l = hb_block_reduce<T>(l, smem, false);
   if (tid == 0) {
@@ -581,7 +632,8 @@ static int softmax_xent_launch(const hb_array *logits, const hb_array *expected,
   X.world = 1;
   const bool global = hb_comm_scalar_xchg(&X);
   if (global || n <= 16384) {
-    hb_softmax_xent_one_kernel<T><<<1, 1024, 0, g_hb.stream>>>(u, ud, ex, ed, n, (T)scale, lp, dp, X);
+    if (n <= 8 * 1024) hb_softmax_xent_one_kernel<T, true><<<1, 1024, 0, g_hb.stream>>>(u, ud, ex, ed, n, (T)scale, lp, dp, X);
+    else hb_softmax_xent_one_kernel<T, false><<<1, 1024, 0, g_hb.stream>>>(u, ud, ex, ed, n, (T)scale, lp, dp, X);
     HB_LAUNCHED();
     return HB_OK;
   }
