@@ -45,6 +45,7 @@ struct tf32_params {
   int mn[2];                  // fetch pattern: 0 = k-fast (4 consecutive k of one row), 1 = m-fast (4 rows of one k)
   int contig4[2];             // the 4 elements of a fetch are at consecutive addresses
   int vec[2];                 // ... and 16-byte aligned: one 128-bit load
+  int kdelta[4];              // BK written in the mixed radix of the K group (rank <= 4): incremental k decomposition
   int splits;                 // split-K factor; > 1: compact partial output
   int kb_per_split;           // k blocks (of BK) per split
   float *partial;             // [batch][split][n][m] when splits > 1
@@ -258,9 +259,47 @@ __global__ void __launch_bounds__(NBUILD + 32, 1)
       cg_off32(P.K, (uint32_t)k, oa, ob);
       return which ? ob : oa;
     };
+    // Incremental decomposition: a thread's k advances by exactly BK from one call of load_op to the next (per
+    // operand), so the multi-index over the K group is carried along with digit-wise adds (no division per stage).
+    // Tracked k: the first k of the thread's chunk (k-fast) / the chunk's k of lane & 3 (m-fast, lanes 0..3 are read).
+    struct kwalk { int idx[4]; };
+    const bool kinc = P.K.rank >= 2 && P.K.rank <= 4;
+    auto kwalk_init = [&](int kq, int mn) {
+      kwalk w;
+      uint32_t lin = (uint32_t)min((int64_t)kb0 * BK + kq + (mn ? (lane & 3) : 0), (int64_t)INT32_MAX);
+#pragma unroll
+      for (int d = 3; d >= 0; d--) {
+        w.idx[d] = 0;
+        if (d < P.K.rank) {
+          if (d == 0) { w.idx[0] = (int)lin; }
+          else { uint32_t s = (uint32_t)P.K.shape[d], q = lin / s; w.idx[d] = (int)(lin - q * s); lin = q; }
+        }
+      }
+      return w;
+    };
+    auto kwalk_off = [&](const kwalk &w, int which) {
+      int off = 0;
+#pragma unroll
+      for (int d = 0; d < 4; d++)
+        if (d < P.K.rank) off += w.idx[d] * (int)(which ? P.K.sb[d] : P.K.sa[d]);
+      return off;
+    };
+    auto kwalk_next = [&](kwalk &w) {
+      int carry = 0;
+#pragma unroll
+      for (int d = 3; d >= 0; d--)
+        if (d < P.K.rank) {
+          int v = w.idx[d] + P.kdelta[d] + carry;
+          carry = 0;
+          if (d > 0 && v >= (int)P.K.shape[d]) { v -= (int)P.K.shape[d]; carry = 1; }
+          w.idx[d] = v;
+        }
+    };
+    kwalk wa = kwalk_init(ta.kq, AMODE & 1), wb = kwalk_init(tb.kq, BMODE & 1);
     // fetch this thread's 16 elements of one operand for k block kb
     auto load_op = [&](const op_thread &t, auto which_c, int kb, float (&r)[4][4]) {
       constexpr int which = decltype(which_c)::value;
+      kwalk &kw = which ? wb : wa;
       constexpr int mode = which ? BMODE : AMODE;
       constexpr bool mn = mode & 1, contig = mode & 2, vec = mode & 4;
       const int64_t k0 = (int64_t)kb * BK + t.kq;
@@ -270,7 +309,9 @@ __global__ void __launch_bounds__(NBUILD + 32, 1)
       if constexpr (!mn) {
         if constexpr (contig) {   // Ktot % 4 == 0 here: the chunk is inside or outside as a whole
           const bool in = fullk || k0 < P.Ktot;
-          const int o = in ? koff(k0, which) : 0;
+          int o = 0;
+          if (kinc) { o = kwalk_off(kw, which); kwalk_next(kw); }
+          else if (in) o = koff(k0, which);
 #pragma unroll
           for (int i = 0; i < 4; i++) ko[i] = o + i;
           kmask = in ? 15u : 0u;
@@ -320,7 +361,8 @@ __global__ void __launch_bounds__(NBUILD + 32, 1)
         } else {
           int mine = 0;
           const bool ok = lane < 4 && (fullk || k0 + lane < P.Ktot);
-          if (ok) mine = koff(k0 + lane, which);
+          if (kinc) { mine = kwalk_off(kw, which); kwalk_next(kw); }
+          else if (ok) mine = koff(k0 + lane, which);
           kmask = __ballot_sync(0xffffffffu, ok) & 15u;
 #pragma unroll
           for (int i = 0; i < 4; i++) ko[i] = __shfl_sync(0xffffffffu, mine, i);
@@ -590,13 +632,18 @@ int hb_contract_tf32(const hb_contractp &Pin, const float *A, const float *B, fl
   };
   configure(0, P.M, A);
   configure(1, P.N, B);
+  if (P.K.rank >= 2 && P.K.rank <= 4) {
+    int64_t rem = BK;
+    for (int d = P.K.rank - 1; d >= 1; d--) { P.kdelta[d] = (int)(rem % P.K.shape[d]); rem /= P.K.shape[d]; }
+    P.kdelta[0] = (int)rem;
+  }
 
   const int64_t tm = (P.Mtot + BM - 1) / BM, tn = (P.Ntot + P.bn - 1) / P.bn;
   const int nkb = (int)((K + BK - 1) / BK);
   int splits = 1;
   const int64_t ctas = tm * tn * nb;
   if (ctas < g_hb.sm_count && nkb >= 16) {
-    splits = (int)std::min<int64_t>((g_hb.sm_count + ctas - 1) / ctas, nkb / 8);
+    splits = (int)std::min<int64_t>(g_hb.sm_count / ctas, nkb / 8);   // one wave: ctas * splits <= SMs (1 CTA per SM)
     if (splits < 1) splits = 1;
   }
   P.kb_per_split = (nkb + splits - 1) / splits;

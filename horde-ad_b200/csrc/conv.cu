@@ -86,6 +86,86 @@ static hb_array *view6(const hb_array *base, int64_t off, const int64_t *shape, 
   return v;
 }
 
+// ---- Float: channels-last staging for the tcgen05 engine (contract_tf32.cu) --------------------------------------
+// The strided-view engine fetches 16 bytes per load when a view is contiguous and 16-byte aligned along the reduced
+// axis (or along its rows).  In NCHW the im2col window moves by ONE float per tap, which breaks the alignment, and
+// the reduced axis (c, kh, kw) has no run of four.  So the Float path copies the activations once into a zero-padded
+// CHANNELS-LAST buffer [N, H + pad, W + pad, C] (one pass over the input, ~2 x its bytes) and the weights into
+// [Co, KH, KW, Ci]: the reduced axis then ends in the channel run, every window starts on a multiple of C floats,
+// and all three contractions run on 128-bit fetches.  Still no patch tensor.  Needs C % 4 == 0 (else: NCHW views).
+// x[N,C,H,W] (contiguous) -> the interior of dst[N,Hp,Wp,C]: 32 x 32 tiles through shared memory, reads coalesced
+// along the positions, writes coalesced along the channels
+template <typename T>
+__global__ void __launch_bounds__(256)
+    hb_nchw_to_nhwc_kernel(const T *__restrict__ src, T *__restrict__ dst, int C, int H, int W, int Wp, int64_t dimg,
+                           int lo_h, int lo_w) {
+  __shared__ T tile[32][33];
+  const int HW = H * W;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int64_t n = blockIdx.z;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  const T *s = src + n * (int64_t)C * HW;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const int c = c0 + ty + 8 * j, p = p0 + tx;
+    tile[ty + 8 * j][tx] = (c < C && p < HW) ? s[(int64_t)c * HW + p] : T(0);
+  }
+  __syncthreads();
+  T *d = dst + n * dimg;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const int p = p0 + ty + 8 * j, c = c0 + tx;
+    if (p < HW && c < C) {
+      const int h = p / W, w = p - h * W;
+      d[((int64_t)(h + lo_h) * Wp + (w + lo_w)) * C + c] = tile[tx][ty + 8 * j];
+    }
+  }
+}
+
+static int pad2d_nhwc(const hb_array *x, int64_t lo_h, int64_t hi_h, int64_t lo_w, int64_t hi_w, hb_array **out) {
+  int64_t N = x->shape[0], C = x->shape[1], H = x->shape[2], W = x->shape[3];
+  int64_t sh[4] = {N, H + lo_h + hi_h, W + lo_w + hi_w, C};
+  hb_array *p;
+  if (lo_h + hi_h + lo_w + hi_w == 0) HB_TRY(hb_new_array(x->dt, 4, sh, &p));
+  else HB_TRY(hb_zeros(x->dt, 4, sh, &p));
+  if (x->dt == HB_F32 && hb_contig(x) && N > 0 && N < 65536 && C > 0 && H * W > 0 && (C + 31) / 32 < 65536) {
+    dim3 grid((unsigned)((H * W + 31) / 32), (unsigned)((C + 31) / 32), (unsigned)N);
+    hb_nchw_to_nhwc_kernel<float><<<grid, 256, 0, g_hb.stream>>>((const float *)hb_data(x), (float *)hb_data(p), (int)C,
+                                                                (int)H, (int)W, (int)sh[2], p->strides[0], (int)lo_h,
+                                                                (int)lo_w);
+    HB_LAUNCHED();
+    *out = p;
+    return HB_OK;
+  }
+  hb_array *v = hb_new_view(p);   // the interior, indexed as [N, C, H, W]
+  v->shape[0] = N; v->strides[0] = p->strides[0];
+  v->shape[1] = C; v->strides[1] = 1;
+  v->shape[2] = H; v->strides[2] = p->strides[1];
+  v->shape[3] = W; v->strides[3] = p->strides[2];
+  v->offset += lo_h * p->strides[1] + lo_w * p->strides[2];
+  int st = hb_copy_into(v, x);
+  hb_release(v);
+  if (st != HB_OK) { hb_release(p); return st; }
+  *out = p;
+  return HB_OK;
+}
+// K[o,c,kh,kw] as a contiguous [d0, KH, KW, d3] array with (d0, d3) = (o, c) or (c, o)
+static int weights_last(const hb_array *K, bool out_first, hb_array **out) {
+  hb_array *v = hb_new_view(K);
+  int a0 = out_first ? 0 : 1, a3 = out_first ? 1 : 0;
+  v->shape[0] = K->shape[a0]; v->strides[0] = K->strides[a0];
+  v->shape[1] = K->shape[2];  v->strides[1] = K->strides[2];
+  v->shape[2] = K->shape[3];  v->strides[2] = K->strides[3];
+  v->shape[3] = K->shape[a3]; v->strides[3] = K->strides[a3];
+  int st = hb_contiguous(v, out);
+  hb_release(v);
+  return st;
+}
+static bool f32_channels_last(const hb_array *x, int64_t c_reduced) {
+  static const bool off = getenv("HB_CONV_F32_NCHW") != nullptr;   // measurement switch: the NCHW views
+  return !off && x->dt == HB_F32 && c_reduced >= 4 && c_reduced % 4 == 0;
+}
+
 extern "C" int hb_conv2d_preserving(const hb_array *K, const hb_array *A, hb_array **out) {
   hb_prof_scope prof_("conv2d_preserving", K, A);
   HB_CHECK_INIT_LAZY();
@@ -110,6 +190,21 @@ extern "C" int hb_conv2d_preserving(const hb_array *K, const hb_array *A, hb_arr
     int done = 0;
     HB_TRY(try_sp(K, A, osh, 0, out, &done));
     if (done) return HB_OK;
+  }
+  if (f32_channels_last(A, Ci)) {
+    hb_array *Ap, *Kp;
+    HB_TRY(pad2d_nhwc(A, 0, KH - 1, 0, KW - 1, &Ap));
+    int st = weights_last(K, true, &Kp);
+    if (st != HB_OK) { hb_release(Ap); return st; }
+    // leading reduced (kh, kw), kept (n, o, h, w), last reduced c
+    int64_t shp[7] = {KH, KW, N, Co, H, W, Ci};
+    int64_t sa[7] = {Ap->strides[1], Ap->strides[2], Ap->strides[0], 0, Ap->strides[1], Ap->strides[2], 1};
+    int64_t sk[7] = {Kp->strides[1], Kp->strides[2], 0, Kp->strides[0], 0, 0, 1};
+    hb_array *va = view6(Ap, 0, shp, sa, 7);
+    hb_array *vk = view6(Kp, 0, shp, sk, 7);
+    st = hb_dot_inner_sum_leading(va, vk, 2, out);
+    hb_release(va); hb_release(vk); hb_release(Ap); hb_release(Kp);
+    return st;
   }
   hb_array *Ap;
   HB_TRY(pad2d(A, 0, KH - 1, 0, KW - 1, &Ap));
@@ -155,6 +250,30 @@ extern "C" int hb_conv2d_preserving_dkrn(const hb_array *A, const hb_array *dB, 
     }
     hb_release(o);
     if (st != HB_OK) return st;
+  }
+  if (f32_channels_last(A, Ci) && Co % 4 == 0) {
+    hb_array *Ap, *Bt;
+    HB_TRY(pad2d_nhwc(A, 0, KH - 1, 0, KW - 1, &Ap));
+    int st = pad2d_nhwc(dB, 0, 0, 0, 0, &Bt);
+    if (st != HB_OK) { hb_release(Ap); return st; }
+    // leading reduced (n, h), kept (o, kh, kw, c), last reduced w; the engine splits K itself (fixed-order reduce)
+    int64_t shp[7] = {N, H, Co, KH, KW, Ci, W};
+    int64_t sb[7] = {Bt->strides[0], Bt->strides[1], 1, 0, 0, 0, Bt->strides[2]};
+    int64_t sa[7] = {Ap->strides[0], Ap->strides[1], 0, Ap->strides[1], Ap->strides[2], 1, Ap->strides[2]};
+    hb_array *vb = view6(Bt, 0, shp, sb, 7);
+    hb_array *va = view6(Ap, 0, shp, sa, 7);
+    hb_array *part = nullptr;
+    st = hb_dot_inner_sum_leading(vb, va, 2, &part);   // [Co, KH, KW, Ci]
+    hb_release(vb); hb_release(va); hb_release(Ap); hb_release(Bt);
+    if (st != HB_OK) return st;
+    hb_array *v = hb_new_view(part);                   // -> [Co, Ci, KH, KW]
+    v->shape[1] = Ci; v->strides[1] = part->strides[3];
+    v->shape[2] = KH; v->strides[2] = part->strides[1];
+    v->shape[3] = KW; v->strides[3] = part->strides[2];
+    st = hb_contiguous(v, out);
+    hb_release(v);
+    hb_release(part);
+    return st;
   }
   hb_array *Ap;
   HB_TRY(pad2d(A, 0, KH - 1, 0, KW - 1, &Ap));
@@ -205,6 +324,22 @@ extern "C" int hb_conv2d_preserving_dinp(const hb_array *K, const hb_array *dB, 
     int done = 0;
     HB_TRY(try_sp(K, dB, ash, 1, out, &done));
     if (done) return HB_OK;
+  }
+  if (f32_channels_last(dB, Co)) {
+    hb_array *Bp, *Kq;
+    HB_TRY(pad2d_nhwc(dB, KH - 1, 0, KW - 1, 0, &Bp));
+    int st = weights_last(K, false, &Kq);              // [Ci, KH, KW, Co]
+    if (st != HB_OK) { hb_release(Bp); return st; }
+    // dA[n,c,h,w] = sum_{kh,kw,o} Bp[n, h+(KH-1)-kh, w+(KW-1)-kw, o] Kq[c,kh,kw,o]
+    int64_t shp[7] = {KH, KW, N, Ci, H, W, Co};
+    int64_t sb[7] = {-Bp->strides[1], -Bp->strides[2], Bp->strides[0], 0, Bp->strides[1], Bp->strides[2], 1};
+    int64_t sk[7] = {Kq->strides[1], Kq->strides[2], 0, Kq->strides[0], 0, 0, 1};
+    int64_t off = (KH - 1) * Bp->strides[1] + (KW - 1) * Bp->strides[2];
+    hb_array *vb = view6(Bp, off, shp, sb, 7);
+    hb_array *vk = view6(Kq, 0, shp, sk, 7);
+    st = hb_dot_inner_sum_leading(vb, vk, 2, out);
+    hb_release(vb); hb_release(vk); hb_release(Bp); hb_release(Kq);
+    return st;
   }
   hb_array *Bp;
   HB_TRY(pad2d(dB, KH - 1, 0, KW - 1, 0, &Bp));
