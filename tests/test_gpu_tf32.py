@@ -147,3 +147,29 @@ def test_f32_engine_agrees_with_the_ffma_engine(dev):
     absref = np.abs(a).astype(np.float64) @ np.abs(b).astype(np.float64)
     for o in outs:
         check(o, ref, absref, 300)
+
+
+def test_f32_cnn_gradient_through_the_engine(dev, oracle):
+    """MnistCnnShaped2 in Float: loss and the 8 gradient leaves of the whole-layer program (Float conv nodes ->
+    channels-last views -> the tcgen05 engine for the 16 -> 16 channel layer, dense products) against the oracle's
+    UNFUSED program evaluated in Double on the same Float inputs.  Normwise per leaf: the whole model in f32 (every
+    elementwise op rounds to 24 bits on both sides of the reference's own Float runs) stays inside 2e-5."""
+    from horde_ad_b200 import ad, mnist_cnn
+    rng = np.random.Generator(np.random.Philox(7))
+    batch, kh, kw, c_out, n_hidden = 32, 2, 2, 16, 8
+    params = [p.astype(np.float32) for p in mnist_cnn.init_params(kh, kw, c_out, n_hidden)]
+    glyphs = rng.uniform(0, 1, (batch, 28, 28)).astype(np.float32)
+    labels = np.eye(10, dtype=np.float32)[rng.integers(0, 10, batch)]
+
+    def run(B, fused, dt):
+        ins = [B.sconcrete(p.astype(dt)) for p in params]
+        g, l = B.sconcrete(glyphs.astype(dt)), B.sconcrete(labels.astype(dt))
+        val, grads = ad.grad(B, lambda T, *ps: mnist_cnn.convMnistLossFusedS(T, g, l, list(ps), fused=fused), ins)
+        return float(B.kfromS(val)), [B.to_numpy(x) for x in grads]
+    (dl, dg), sites = launched_sites(lambda: run(dev, "nodes", np.float32))
+    assert any(s.startswith("hb_contract_tf32") for s in sites), sites
+    ol, og = run(oracle, False, np.float64)
+    assert abs(dl - ol) <= 2e-5 * abs(ol), (dl, ol)
+    for a, b in zip(dg, og):
+        assert a.dtype == np.float32
+        assert float(np.max(np.abs(a.astype(np.float64) - b))) <= 2e-5 * float(np.max(np.abs(b))), (a.shape,)

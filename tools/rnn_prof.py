@@ -1,0 +1,33 @@
+"""Per-launch-site times of one MnistRnnShaped2 gradient step (width 512, batch 1024, fused pair nodes)."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from horde_ad_b200 import ad, ffi, mnist_rnn
+from horde_ad_b200.device import DeviceBackend
+
+dev = DeviceBackend(0)
+rng = np.random.default_rng(0)
+width, batch = 512, 1024
+params = [dev.sconcrete(p) for p in mnist_rnn.init_params(width, rng_range=0.05)]
+glyphs = dev.sconcrete(rng.uniform(0, 1, (batch, 28, 28)))
+labels = dev.sconcrete(np.eye(10)[rng.integers(0, 10, batch)])
+f = lambda: ad.grad(dev, lambda T, *ps: mnist_rnn.rnnMnistLossFusedS(T, glyphs, labels, list(ps), fused="pair"), params)
+for _ in range(2):
+    f()
+dev.sync()
+ffi.call("hb_prof_begin")
+f()
+ffi.call("hb_prof_end")
+buf = C.create_string_buffer(1 << 16)
+ffi.call("hb_prof_report", buf, len(buf))
+rows = []
+for line in buf.value.decode().splitlines():
+    tag, site, cnt, tot = line.rsplit(" ", 3)
+    rows.append((float(tot), int(cnt), site, tag))
+print("total ms", sum(r[0] for r in rows), "launches", sum(r[1] for r in rows))
+for tot, cnt, site, tag in sorted(rows, reverse=True)[:24]:
+    print(f"{tot:8.3f} ms n={cnt:4d} {tot / cnt * 1e3:7.1f} us  {site}  {tag[:70]}")
