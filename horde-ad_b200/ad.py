@@ -436,6 +436,7 @@ class ADBackend:
 
 
 _NO_MATMUL_ACC = bool(os.environ.get("HB_AD_NO_MATMUL_ACC"))   # measurement switch: product + separate add
+_NO_MATMUL_LIST = bool(os.environ.get("HB_AD_NO_MATMUL_LIST"))  # measurement switch: accumulate weight cotangents per step
 
 
 class DeferredMatmul:
@@ -499,6 +500,11 @@ def grad(base, f: Callable, inputs: Sequence, dt=None):
         # cotangents that this sweep itself created by an accumulation: only those may be updated in
         # place (a pullback may hand the SAME array to several parents, e.g. `add` returns [c, c])
         owned = set()
+        # deferred products whose parent is an INPUT (a weight used at every step of an unrolled loop): kept as a list
+        # and evaluated ONCE, when the input is reached at the end of the sweep, as one product over the concatenated
+        # reduced axes (hb_matmul2_list) instead of one small accumulating product per step
+        pending = {}
+        use_list = hasattr(base, "smatmul2_list") and not _NO_MATMUL_LIST and not _NO_MATMUL_ACC
         heap = [-out.d.id]
         while heap:
             nid = -heapq.heappop(heap)
@@ -507,9 +513,28 @@ def grad(base, f: Callable, inputs: Sequence, dt=None):
             if isinstance(c, DeferredPad):
                 c = c.force(base)
             if nid in input_ix:
+                if nid in pending:
+                    lst = pending.pop(nid)
+                    if len(lst) == 1:                  # a single contribution: the plain product
+                        lst_val = base.smatmul2(*lst[0])
+                        c = lst_val if c is None else base.binary("add", c, lst_val)
+                    elif c is None or nid in owned:    # an accumulator this sweep created: may be updated in place
+                        c = base.smatmul2_list(lst, c)
+                    else:                              # an array other parents may hold too
+                        c = base.binary("add", c, base.smatmul2_list(lst, None))
                 grads[input_ix[nid]] = c
                 continue
             cs = list(node.pullback(c))
+            if use_list:
+                for i, pc in enumerate(cs):
+                    parent = node.parents[i]
+                    if isinstance(pc, DeferredMatmul) and parent is not None and parent.id in input_ix:
+                        pending.setdefault(parent.id, []).append((pc.a, pc.b))
+                        if parent.id not in cot:
+                            cot[parent.id] = None
+                            nodes[parent.id] = parent
+                            heapq.heappush(heap, -parent.id)
+                        cs[i] = None
             # two deferred products marked as partners whose cotangents both exist and are owned by the sweep:
             # both accumulations in one launch
             for i, pc in enumerate(cs):
@@ -525,6 +550,12 @@ def grad(base, f: Callable, inputs: Sequence, dt=None):
                 if parent is None or pc is None:
                     continue
                 deferred = isinstance(pc, DeferredMatmul)
+                if parent.id in cot and cot[parent.id] is None:    # placeholder of an input with pending products
+                    if deferred or isinstance(pc, DeferredPad):
+                        pc = pc.force(base)
+                        owned.add(parent.id)
+                    cot[parent.id] = pc
+                    continue
                 if isinstance(pc, DeferredPad):
                     old = cot.get(parent.id)
                     if old is None:                       # stays unevaluated until a second window arrives

@@ -238,6 +238,8 @@ int hb_gemm_dmma_pair(const double *A1, int64_t a1_sm, int64_t a1_sk, const doub
                       int64_t K1, const double *A2, int64_t a2_sm, int64_t a2_sk, const double *B2, int64_t b2_sk,
                       int64_t b2_sn, int64_t K2, double *C1, double *C2, int64_t M, int64_t N, int chain, int accum,
                       int *done);
+int hb_gemm_dmma_list(int n, const double *const *A, int64_t a_sm, int64_t a_sk, const double *const *B, int64_t b_sk,
+                      int64_t b_sn, double *C, int64_t M, int64_t N, int64_t K, int accum, int *done);
 int hb_reduce_generic(const hb_array *a, const hb_array *b, int nk, const int *kax, int nr,
                       const int *rax, hb_array *out);
 
@@ -573,6 +575,108 @@ extern "C" int hb_matmul2_acc_pair(hb_array *acc1, const hb_array *a1, const hb_
   int st = hb_matmul2_acc(acc2, a2, b2, out2);
   if (st != HB_OK) { hb_release(*out1); *out1 = nullptr; }
   return st;
+}
+
+// acc + sum_t a_t x b_t for a list of products of one shape: the cotangent of a weight that is used at every step
+// of an unrolled loop (taddTarget over the transposition rule of tsmatmul2 at every step, DeltaEval.hs:317-332),
+// evaluated at the END of the sweep as ONE product over the concatenated reduced axes instead of one small product
+// per step.  Deterministic (fixed slice order).  acc may be NULL.  Falls back to a chain of hb_matmul2_acc.
+extern "C" int hb_matmul2_list(int n, hb_array *const *as, hb_array *const *bs, hb_array *acc, hb_array **out) {
+  hb_prof_scope prof_("matmul2_list", n > 0 ? as[0] : nullptr, n > 0 ? bs[0] : nullptr);
+  HB_CHECK_INIT_LAZY();
+  HB_REQUIRE(n >= 1 && as && bs && out, "matmul2_list: empty list");
+  for (int t = 0; t < n; t++)
+    HB_REQUIRE(as[t] && bs[t] && as[t]->rank == 2 && bs[t]->rank == 2 && as[t]->shape[1] == bs[t]->shape[0] &&
+                   as[t]->dt == as[0]->dt && bs[t]->dt == as[0]->dt && hb_same_shape(as[t], as[0]) &&
+                   hb_same_shape(bs[t], bs[0]),
+               "matmul2_list: entry %d does not match the first product", t);
+  const int64_t M = as[0]->shape[0], K = as[0]->shape[1], N = bs[0]->shape[1];
+  HB_REQUIRE(!acc || (acc->rank == 2 && acc->shape[0] == M && acc->shape[1] == N && acc->dt == as[0]->dt),
+             "matmul2_list: accumulator does not match the products");
+  if (hb_lazy_on()) {
+    hb_lrec r(HB_L_GENERIC, "matmul2_list");
+    for (int t = 0; t < n; t++) r.in(as[t]);
+    for (int t = 0; t < n; t++) r.in(bs[t]);
+    if (acc) r.in(acc);
+    int64_t sh_[2] = {M, N};
+    return r.iarg(0, n).iarg(1, acc != nullptr).out(out, as[0]->dt, 2, sh_).commit(
+        [=](hb_lnode &nd, hb_array *const *in, hb_array **o) {
+          const int n_ = (int)nd.ia[0];
+          return hb_matmul2_list(n_, in, in + n_, nd.ia[1] ? in[2 * n_] : nullptr, &o[0]);
+        });
+  }
+  if (as[0]->dt == HB_F64 && M * N > 0 && n <= 32) {
+    // the entries that share the stride pattern of the FIRST one (else of the last one) go into the one launch; the
+    // odd ones (e.g. the broadcast zero state of time step 0, which arrives last) are accumulated one by one afterwards
+    // operands without a unit stride (rows of a transposed batch, e.g. the glyph rows of MnistRnnShaped2) are packed
+    // first: O(rows * K) each against the product
+    hb_array *tmp[64];
+    for (int t = 0; t < 2 * n; t++) tmp[t] = nullptr;
+    auto drop_tmp = [&]() { for (int t = 0; t < 2 * n; t++) hb_release(tmp[t]); };
+    Op2 OA[32], OB[32];
+    bool usable[32];
+    for (int t = 0; t < n; t++) {
+      const bool bcast_a = as[t]->strides[0] == 0 && as[t]->strides[1] == 0, bcast_b = bs[t]->strides[0] == 0 && bs[t]->strides[1] == 0;
+      usable[t] = !bcast_a && !bcast_b && op2_pack(as[t], &OA[t], &tmp[2 * t]) && op2_pack(bs[t], &OB[t], &tmp[2 * t + 1]);
+    }
+    int ref = -1;
+    for (int t = 0; t < n && ref < 0; t++) if (usable[t]) ref = t;
+    bool ok = ref >= 0;
+    Op2 A0 = OA[ok ? ref : 0], B0 = OB[ok ? ref : 0];
+    const double *pa[32], *pb[32];
+    int nl = 0;
+    bool in_list[32];
+    for (int t = 0; t < n && ok; t++) {
+      in_list[t] = usable[t] && OA[t].s0 == A0.s0 && OA[t].s1 == A0.s1 && OB[t].s0 == B0.s0 && OB[t].s1 == B0.s1;
+      if (in_list[t]) { pa[nl] = OA[t].p; pb[nl] = OB[t].p; nl++; }
+    }
+    const bool inplace = acc && acc_unique(acc, as[0], bs[0]);
+    if (!(ok && nl >= 2)) drop_tmp();
+    if (ok && nl >= 2) {
+      hb_array *o = nullptr;
+      if (inplace) { hb_retain(acc); o = acc; }
+      else {
+        int64_t sh[2] = {M, N};
+        HB_TRY(hb_new_array(HB_F64, 2, sh, &o));
+      }
+      int done = 0;
+      int st = hb_gemm_dmma_list(nl, pa, A0.s0, A0.s1, pb, B0.s0, B0.s1, (double *)hb_data(o), M, N, K, inplace ? 1 : 0, &done);
+      drop_tmp();   // stream-ordered: the packed copies are released behind the launch
+      if (st != HB_OK) { hb_release(o); return st; }
+      if (done) {
+        if (acc && !inplace) {
+          hb_array *sum = nullptr;
+          st = hb_add_inplace_or_new(o, acc, &sum);
+          hb_release(o);
+          if (st != HB_OK) return st;
+          o = sum;
+        }
+        for (int t = 0; t < n; t++) {
+          if (in_list[t]) continue;
+          hb_array *nx = nullptr;
+          st = hb_matmul2_acc(o, as[t], bs[t], &nx);
+          hb_release(o);
+          if (st != HB_OK) return st;
+          o = nx;
+        }
+        *out = o;
+        return HB_OK;
+      }
+      hb_release(o);
+    }
+  }
+  // generic: acc (+)= a_t x b_t one by one
+  hb_array *cur = acc;
+  if (cur) hb_retain(cur);
+  for (int t = 0; t < n; t++) {
+    hb_array *nx = nullptr;
+    int st = cur ? hb_matmul2_acc(cur, as[t], bs[t], &nx) : hb_matmul2(as[t], bs[t], &nx);
+    hb_release(cur);
+    if (st != HB_OK) return st;
+    cur = nx;
+  }
+  *out = cur;
+  return HB_OK;
 }
 
 // tsmatvecmul m v = sdot1In m (sreplicate v)  (OpsConcrete.hs:236)

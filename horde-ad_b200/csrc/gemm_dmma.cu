@@ -14,6 +14,8 @@
 // CTAs (grid.z) with partials reduced in a fixed order (deterministic).
 // Anything else (batch axes, non-unit strides) stays on the generic strided
 // engine in contract.cu.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace {
@@ -57,6 +59,11 @@ struct GemmP {
   int K2, kchunks2, a_vec2, b_vec2;
   int64_t a_sm2, a_sk2, b_sk2, b_sn2;
   int zsplit, chain;
+  // A LIST of products of one shape accumulated into one result (hb_gemm_dmma_list: the weight cotangents
+  // dW = sum_t d_t x_t^T of an unrolled loop): the K axis is the concatenation of the entries' K axes
+  // (K % BK8 == 0, so a chunk never straddles two entries); slices go to partial buffers + the fixed-order reduce.
+  int nlist;
+  const double *Al[32], *Bl[32];
 };
 
 // Stage one operand tile: `rows` x BK where the operand's (row, k) element is
@@ -252,7 +259,7 @@ __global__ void __launch_bounds__(256, 2) gemm8_dmma_kernel(const __grid_constan
   const int64_t a_sm = second ? p.a_sm2 : p.a_sm, a_sk = second ? p.a_sk2 : p.a_sk;
   const int64_t b_sk = second ? p.b_sk2 : p.b_sk, b_sn = second ? p.b_sn2 : p.b_sn;
   const int a_vec = second ? p.a_vec2 : p.a_vec, b_vec = second ? p.b_vec2 : p.b_vec;
-  const int Kp = second ? p.K2 : p.K, kch = second ? p.kchunks2 : p.kchunks;
+  const int Kp = p.nlist ? p.nlist * p.K : (second ? p.K2 : p.K), kch = second ? p.kchunks2 : p.kchunks;
   const int zl = second ? (int)blockIdx.z - p.zsplit : (int)blockIdx.z;
   const int kbeg = zl * kch * BK8;
   int kend = kbeg + kch * BK8;
@@ -261,8 +268,17 @@ __global__ void __launch_bounds__(256, 2) gemm8_dmma_kernel(const __grid_constan
 
   auto issue = [&](int c) {
     double *as = smem + (c % STAGES8) * 2 * TILE8, *bs = as + TILE8;
-    stage_tile8<A_KFAST>(as, gA, a_sm, a_sk, m0, p.M, kbeg + c * BK8, kend, a_vec, tid);
-    stage_tile8<B_KFAST>(bs, gB, b_sn, b_sk, n0, p.N, kbeg + c * BK8, kend, b_vec, tid);
+    const double *__restrict__ cA = gA, *__restrict__ cB = gB;
+    int k0 = kbeg + c * BK8, ke = kend;
+    if (p.nlist) {   // which entry of the list this chunk lies in
+      const int t = k0 / p.K;
+      k0 -= t * p.K;
+      ke = p.K;
+      cA = p.Al[t];
+      cB = p.Bl[t];
+    }
+    stage_tile8<A_KFAST>(as, cA, a_sm, a_sk, m0, p.M, k0, ke, a_vec, tid);
+    stage_tile8<B_KFAST>(bs, cB, b_sn, b_sk, n0, p.N, k0, ke, b_vec, tid);
     cp_commit();
   };
   double acc[4][2][2];
@@ -507,6 +523,74 @@ int hb_gemm_dmma(const double *A, int64_t a_sm, int64_t a_sk, const double *B, i
     gemm_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, g_hb.stream>>>(p.C, C, n, splits, accum);
     HB_LAUNCHED();
   }
+  *done = 1;
+  return HB_OK;
+}
+
+// C (contiguous [M,N] f64) = (accum ? C : 0) + sum_t A_t x B_t for n products of one shape and stride pattern, in ONE
+// launch of the eight-warp kernel + the fixed-order reduce: *done = 1 if handled.
+int hb_gemm_dmma_list(int n, const double *const *A, int64_t a_sm, int64_t a_sk, const double *const *B, int64_t b_sk,
+                      int64_t b_sn, double *C, int64_t M, int64_t N, int64_t K, int accum, int *done) {
+  *done = 0;
+  if (n < 1 || n > 32 || M <= 0 || N <= 0 || K <= 0 || K % BK8) return HB_OK;
+  if (M >= (1ll << 31) || N >= (1ll << 31) || (int64_t)n * K >= (1ll << 31)) return HB_OK;
+  const bool a_kfast = a_sk == 1, b_kfast = b_sk == 1;
+  if (!a_kfast && a_sm != 1) return HB_OK;
+  if (!b_kfast && b_sn != 1) return HB_OK;
+  GemmP p;
+  memset(&p, 0, sizeof p);
+  p.M = (int)M; p.N = (int)N; p.K = (int)K;
+  p.a_sm = a_sm; p.a_sk = a_sk; p.b_sk = b_sk; p.b_sn = b_sn;
+  p.c_sm = N;
+  p.accum = accum;
+  p.nlist = n;
+  p.a_vec = (a_kfast ? a_sm : a_sk) % 2 == 0;
+  p.b_vec = (b_kfast ? b_sn : b_sk) % 2 == 0;
+  for (int t = 0; t < n; t++) {
+    p.Al[t] = A[t]; p.Bl[t] = B[t];
+    if ((uintptr_t)A[t] & 15) p.a_vec = 0;
+    if ((uintptr_t)B[t] & 15) p.b_vec = 0;
+  }
+  p.A = A[0]; p.B = B[0];
+  const int gm = (int)((M + BM - 1) / BM), gn = (int)((N + BN - 1) / BN);
+  if (gn > 65535) return HB_OK;
+  const int64_t tiles = (int64_t)gm * gn, slots = 2 * (int64_t)g_hb.sm_count;
+  const int chunks = (int)((int64_t)n * K / BK8);
+  // K slices: the count (up to ~4 waves of two CTAs per SM, at least 8 chunks = 256 k per slice) that fills the
+  // last wave best
+  int splits = 1;
+  {
+    const int smax = (int)std::min<int64_t>(std::min<int64_t>(512, std::max(1, chunks / 8)), std::max<int64_t>(1, 4 * slots / tiles));
+    double best = 0.0;
+    for (int sp = 1; sp <= smax; sp++) {
+      const int64_t ctas = tiles * sp, waves = (ctas + slots - 1) / slots;
+      const double eff = (double)ctas / (double)(waves * slots) - 0.002 * sp;   // mild preference for fewer partials
+      if (eff > best) { best = eff; splits = sp; }
+    }
+  }
+  p.kchunks = (chunks + splits - 1) / splits;
+  splits = (chunks + p.kchunks - 1) / p.kchunks;
+  void *scr;
+  HB_TRY(hb_scratch((size_t)splits * M * N * 8, &scr));
+  p.C = (double *)scr;
+  p.flags = nullptr;
+  dim3 grid((unsigned)gm, (unsigned)gn, (unsigned)splits);
+  size_t smem = (size_t)STAGES8 * 2 * TILE8 * 8;
+#define GEMM8L_LAUNCH(AK, BKF)                                                                                 \
+  do {                                                                                                         \
+    HB_CUDA(cudaFuncSetAttribute(gemm8_dmma_kernel<AK, BKF>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                 (int)smem));                                                                  \
+    gemm8_dmma_kernel<AK, BKF><<<grid, 256, smem, g_hb.stream>>>(p);                                           \
+  } while (0)
+  if (a_kfast && b_kfast) GEMM8L_LAUNCH(true, true);
+  else if (a_kfast) GEMM8L_LAUNCH(true, false);
+  else if (b_kfast) GEMM8L_LAUNCH(false, true);
+  else GEMM8L_LAUNCH(false, false);
+#undef GEMM8L_LAUNCH
+  HB_LAUNCHED();
+  const int64_t nel = M * N;
+  gemm_reduce_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, g_hb.stream>>>(p.C, C, nel, splits, accum);
+  HB_LAUNCHED();
   *done = 1;
   return HB_OK;
 }

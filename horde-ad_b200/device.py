@@ -389,6 +389,19 @@ class DeviceBackend:
                 outs.append(_wrap(p))
         return outs[0], outs[1]
 
+    def smatmul2_list(self, pairs, acc=None):
+        """acc + sum_t a_t b_t as ONE product over the concatenated reduced axes (hb_matmul2_list); in place when
+        `acc` is uniquely referenced."""
+        n = len(pairs)
+        arr_a = (C.c_void_p * n)(*[a.h for a, _ in pairs])
+        arr_b = (C.c_void_p * n)(*[b.h for _, b in pairs])
+        p = _out()
+        call("hb_matmul2_list", n, arr_a, arr_b, acc.h if acc is not None else None, C.byref(p))
+        if acc is not None and p.value == acc.h.value:
+            ffi._lib.hb_release(p)
+            return acc
+        return _wrap(p)
+
     def smatvecmul(self, m, v):
         p = _out()
         call("hb_matvecmul", m.h, v.h, C.byref(p))

@@ -393,6 +393,15 @@ int hb_matmul2_acc_pair(hb_array *acc1, const hb_array *a1,
                         const hb_array *b1, hb_array *acc2,
                         const hb_array *a2, const hb_array *b2,
                         hb_array **out1, hb_array **out2);
+/* acc + sum_t a[t] x b[t] for n products of one shape (acc may be NULL): the
+ * cotangent of a weight used at every step of an unrolled loop (taddTarget
+ * over the transposition rule of tsmatmul2, DeltaEval.hs:317-332), evaluated
+ * once at the end of the sweep as ONE product over the concatenated reduced
+ * axes (f64, n <= 32, K % 32 == 0, one stride pattern; otherwise a chain of
+ * hb_matmul2_acc).  In place when `acc` is uniquely referenced.  Fixed
+ * reduction order: deterministic. */
+int hb_matmul2_list(int n, hb_array *const *a, hb_array *const *b, hb_array *acc,
+                    hb_array **out);
 /* tsargMax / tsargMin (OpsConcrete.hs:1712-1746): reduce the LAST axis,
  * result shape Init sh, dtype I64; first extremum wins. */
 int hb_argmax_last(const hb_array *a, hb_array **out);

@@ -267,6 +267,15 @@ class ConcreteBackend:
     def smatmul2_acc_pair(self, acc1, a1, b1, acc2, a2, b2):
         return acc1 + self.smatmul2(a1, b1), acc2 + self.smatmul2(a2, b2)
 
+    def smatmul2_list(self, pairs, acc=None):
+        """taddTarget folded over the contributions `tsmatmul2 a_t b_t` of one weight (DeltaEval.hs:317-332),
+        in arrival order."""
+        out = acc
+        for a, b in pairs:
+            prod = self.smatmul2(a, b)
+            out = prod if out is None else out + prod
+        return out
+
     # tsargMax / tsargMin reduce the LAST axis, Int result of shape Init sh
     # (OpsConcrete.hs:1712-1746); first extremum (unpinned in the reference)
     def sargMax(self, t):

@@ -1,5 +1,6 @@
 """Host-side logic of the reverse sweep (horde-ad_b200/ad.py) that the device path shares: deferred products
-accumulated by `smatmul2_acc` / `smatmul2_acc_pair`, zero-padded slice cotangents joined by one `sappend`.
+accumulated by `smatmul2_acc` / `smatmul2_acc_pair` (interior values) or kept as a list and evaluated once by
+`smatmul2_list` (inputs: weights of an unrolled loop), zero-padded slice cotangents joined by one `sappend`.
 Runs on the CPU oracle with a call-counting wrapper; values are checked against the plain rules."""
 import numpy as np
 import pytest
@@ -19,8 +20,8 @@ class Counting(ConcreteBackend):
         self.calls[name] = self.calls.get(name, 0) + 1
 
 
-for _name in ("smatmul2", "smatmul2_acc", "smatmul2_acc_pair", "smatmul2_pair", "smatmul2_sum", "sappend", "srepl",
-              "add_accumulate"):
+for _name in ("smatmul2", "smatmul2_acc", "smatmul2_acc_pair", "smatmul2_pair", "smatmul2_sum", "smatmul2_list",
+              "sappend", "srepl", "add_accumulate"):
     def _wrap(name):
         base = getattr(ConcreteBackend, name)
 
@@ -87,8 +88,14 @@ def test_weight_used_at_every_step_accumulates_in_the_product():
         return T.ssum0(h)
     B = Counting()
     _, (gw, gx) = ad.grad(B, f, [w, x])
-    # three uses of W: the first cotangent is a product, the other two are accumulated by smatmul2_acc
-    assert B.calls.get("smatmul2_acc") == 2
+    # W is an INPUT used three times: its three cotangent products are kept as a list and evaluated once, when the
+    # sweep reaches the input (one product over the concatenated reduced axes on the device)
+    assert B.calls.get("smatmul2_list") == 1 and B.calls.get("smatmul2_acc", 0) == 0
+    # an INTERIOR value used three times (W = 2 * V): the first cotangent is a product, the others accumulate into it
+    B2 = Counting()
+    _, (gv, _) = ad.grad(B2, lambda T, V, X: f(T, T.binary("mul", V, T.srepl([5, 5], 2.0)), X), [w / 2, x])
+    assert B2.calls.get("smatmul2_acc") == 2 and B2.calls.get("smatmul2_list", 0) == 0
+    np.testing.assert_allclose(gv, 2 * gw, rtol=1e-13)
 
     def val(W):
         h = x
@@ -112,7 +119,8 @@ def test_paired_layer_node_pairs_its_cotangents():
     B = Counting()
     v, grads = ad.grad(B, f, [wx, ws, x0, s0])
     assert B.calls.get("smatmul2_sum") == 3
-    assert B.calls.get("smatmul2_acc_pair") == 2             # second and third contribution to (dWX, dWS)
+    assert B.calls.get("smatmul2_list") == 2                 # dWX and dWS: one list product each at the end
+    assert B.calls.get("smatmul2_acc_pair", 0) == 0
     assert B.calls.get("smatmul2_pair", 0) >= 2              # (dX, dS) of a step share one launch
 
     def val(WX, WS, X, S):

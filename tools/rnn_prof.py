@@ -31,3 +31,22 @@ for line in buf.value.decode().splitlines():
 print("total ms", sum(r[0] for r in rows), "launches", sum(r[1] for r in rows))
 for tot, cnt, site, tag in sorted(rows, reverse=True)[:24]:
     print(f"{tot:8.3f} ms n={cnt:4d} {tot / cnt * 1e3:7.1f} us  {site}  {tag[:70]}")
+
+# the same step as one CUDA graph (what bench_configs.py times)
+ffi.call("hb_graph_begin")
+try:
+    val, grads = f()
+finally:
+    g = C.c_void_p()
+    ffi.call("hb_graph_end", C.byref(g))
+for _ in range(3):
+    ffi.call("hb_graph_launch", g)
+dev.sync()
+ms = C.c_float()
+ffi.call("hb_event_record", 2)
+for _ in range(10):
+    ffi.call("hb_graph_launch", g)
+ffi.call("hb_event_record", 3)
+ffi.call("hb_event_elapsed_ms", 2, 3, C.byref(ms))
+fl = 28 * 3 * 2.0 * batch * (28 * width + 3 * width * width)
+print(f"graph step {ms.value / 10:.3f} ms  {fl / (ms.value / 10) / 1e9:.2f} TFLOP/s")
