@@ -50,6 +50,39 @@ class ADVal:
         return tuple(self.p.shape)
 
 
+class LazyAppend(ADVal):
+    """`sappend a b` not yet evaluated.  A `sslice` that reads back exactly one operand returns that operand -- the
+    rule `astSlice` of an `AstAppend` that the reference's simplifier applies to the symbolic artifact
+    (AstSimplify.hs), here applied by the dual-number layer: the recurrent state `sappend vec1 vec2` of
+    MnistRnnShaped2.hs:73-99 is only ever read back as its two halves, so neither the append nor (in the reverse
+    sweep) the re-assembly of its cotangent is ever launched.  Any other use forces the append."""
+    __slots__ = ("T", "a", "b", "_forced")
+
+    def __init__(self, T, a, b):
+        self.T, self.a, self.b, self._forced = T, a, b, None
+
+    def _force(self):
+        if self._forced is None:
+            self._forced = self.T._sappend_now(self.a, self.b)
+        return self._forced
+
+    @property
+    def p(self):
+        return self._force().p
+
+    @property
+    def d(self):
+        return self._force().d
+
+    @property
+    def shape(self):
+        sa, sb = self.a.shape, self.b.shape
+        return (sa[0] + sb[0],) + tuple(sa[1:])
+
+
+_NO_LAZY_APPEND = bool(os.environ.get("HB_AD_NO_LAZY_APPEND"))   # measurement switch
+
+
 def _inv_perm(perm):
     inv = [0] * len(perm)
     for i, p in enumerate(perm):
@@ -230,6 +263,12 @@ class ADBackend:
     def sslice(self, i, n, t):
         B = self.B
         t = self.lift(t)
+        if isinstance(t, LazyAppend) and t._forced is None:
+            m = t.a.shape[0]
+            if i == 0 and n == m:
+                return t.a
+            if i == m and n == t.b.shape[0]:
+                return t.b
         sh = B.shape(t.p)
         total, rest, dt = sh[0], list(sh[1:]), B.dtype(t.p)
 
@@ -243,8 +282,13 @@ class ADBackend:
         return self._node(B.sslice(i, n, t.p), [t], pb)
 
     def sappend(self, a, b):
-        B = self.B
         a, b = self.lift(a), self.lift(b)
+        if _NO_LAZY_APPEND:
+            return self._sappend_now(a, b)
+        return LazyAppend(self, a, b)
+
+    def _sappend_now(self, a, b):
+        B = self.B
         m, n = B.shape(a.p)[0], B.shape(b.p)[0]
         return self._node(B.sappend(a.p, b.p), [a, b], lambda c: [B.sslice(0, m, c), B.sslice(m, n, c)])
 
@@ -252,6 +296,12 @@ class ADBackend:
         B = self.B
         t = self.lift(t)
         return self._node(B.sreverse(t.p), [t], lambda c: [B.sreverse(c)])
+
+    def scontiguous(self, t):
+        """Identity on values (a materialised copy of a view)."""
+        B = self.B
+        t = self.lift(t)
+        return self._node(B.scontiguous(t.p), [t], lambda c: [c])
 
     def sfromVector(self, ts):
         B = self.B
@@ -743,6 +793,7 @@ class FwdBackend:
     def ssum0(self, t): return self.ssumN(t, len(self.shape(t)))
     def sslice(self, i, n, t): return self._map(t, lambda x: self.B.sslice(i, n, x))
     def sreverse(self, t): return self._map(t, lambda x: self.B.sreverse(x))
+    def scontiguous(self, t): return self._map(t, lambda x: self.B.scontiguous(x))
     def sindex(self, t, ixs): return self._map(t, lambda x: self.B.sindex(x, [int(i) for i in ixs]))
     def sunravelToList(self, t): return [self.sindex(t, [i]) for i in range(self.shape(t)[0])]
 

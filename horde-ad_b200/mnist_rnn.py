@@ -65,5 +65,9 @@ def rnnMnistLossFusedS(T, glyphs, labels, params, fused=False):
     labels [batch, 10]."""
     batch = T.shape(glyphs)[0]
     xs = T.stranspose([2, 1, 0], glyphs)
+    if fused and hasattr(T, "scontiguous"):
+        # the transposed glyph batch is materialised ONCE (6 MB) instead of every per-step row `xs !! t` being packed
+        # inside the products that read it (twice per step: forward product and weight cotangent)
+        xs = T.scontiguous(xs)
     result = rnnMnistZeroS(T, xs, params, fused)
     return nn.lossSoftMaxCrossEntropyS(T, T.stranspose([1, 0], labels), result, scale=1.0 / batch)
