@@ -197,7 +197,7 @@ def _cpu_worker(args):
     return float(val)
 
 
-def cpu_oracle_rate(per_worker_batch: int, steps: int, workers: int):
+def cpu_oracle_rate(per_worker_batch: int, steps: int, workers: int, warm: int = 0):
     """samples/s of the oracle with `workers` processes, each owning a shard
     (the data-parallel decomposition of the GPU arm, on host cores); the
     reference's own interpreter is single-threaded, this is every core it
@@ -205,7 +205,9 @@ def cpu_oracle_rate(per_worker_batch: int, steps: int, workers: int):
     import multiprocessing as mp
     ctx = mp.get_context("spawn")
     with ctx.Pool(workers) as pool:
-        pool.map(_cpu_worker, [(100 + i, 8, 1) for i in range(workers)])          # start-up + warm-up
+        pool.map(_cpu_worker, [(100 + i, 8, 1) for i in range(workers)])          # start-up (imports, first touch)
+        if warm:
+            pool.map(_cpu_worker, [(42 + i, per_worker_batch, warm) for i in range(workers)])   # untimed warm-up steps
         t0 = time.perf_counter()
         pool.map(_cpu_worker, [(42 + i, per_worker_batch, steps) for i in range(workers)])
         dt = time.perf_counter() - t0
@@ -220,9 +222,11 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     workers = args.cpu_workers or (os.cpu_count() or 1)
-    per = max(8, args.cpu_sample // workers)
-    steps, warm = max(1, min(args.steps, 3)), 1
-    val, dt_total = cpu_oracle_rate(per, steps, workers)
+    # EXACTLY --steps timed and --warmup untimed steps; the per-step sample is bounded so that the whole run stays
+    # within a couple of minutes (~150 samples/s per core for this model on the boxes seen so far)
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    per = max(8, min(args.cpu_sample // workers, int(120 * 150 / (steps + warm))))
+    val, dt_total = cpu_oracle_rate(per, steps, workers, warm)
     dt = dt_total / steps
     sample = per * workers
     out = {
