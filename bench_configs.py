@@ -344,6 +344,8 @@ def run_configs(dev, quick=False, skip_families=False, only_families=False, emit
     tf = fl / (step_ms * 1e-3) / 1e12
     emit(({"config": "MnistRnnShaped2", "width": width, "seq": 28, "per_gpu_batch": batch, "ms_per_step": step_ms,
                       "ms_per_step_eager": eager_ms,
+                      "program": "rnnMnistLossFusedS with the paired-product / tanh_affine nodes selected ABOVE the C ABI "
+                                 "(fused='pair'; weight cotangents as hb_matmul2_list; not the contraction pass)",
                       "samples_per_s": batch / (step_ms * 1e-3), "loss": loss if np.isfinite(loss) else None,
                       "roofline": {"bound": "tensor", "achieved": tf, "peak": fp64.value, "unit": "TFLOP/s",
                                    "frac": tf / fp64.value, "peak_source": "hb_microbench FP64 DMMA, this run",
@@ -400,6 +402,7 @@ def rnn_dp(dev, world, rank, barrier, max_over_ranks, width=512, batch=1024, ste
     return {"config": "MnistRnnShaped2 data-parallel", "width": width, "seq": 28, "per_gpu_batch": batch,
             "n_gpus": world, "scaling": "weak", "ms_per_step": step_ms, "samples_per_s": batch * world / (step_ms * 1e-3),
             "tflops_per_gpu": fl / (step_ms * 1e-3) / 1e12, "param_sum": digest,
+            "program": "paired-product / tanh_affine nodes selected above the C ABI (fused='pair')",
             "exchange": "hb_allreduce_adam_step (fused peer-memory all-reduce + Adam) inside the step's CUDA graph"}
 
 
