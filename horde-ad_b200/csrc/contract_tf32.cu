@@ -30,6 +30,13 @@ namespace {
 constexpr int BM = 128;       // UMMA M (TMEM lanes)
 constexpr int BK = 32;        // k elements per stage (4 MMA k-steps of 8)
 constexpr int STAGES = 3;
+// Variants measured on 4096^3 (row-major operands / A^T view), TFLOP/s:  8 builder warps with the proxy fence in the
+// builders (this version) 119 / 144;  16 builder warps 117 / 122;  16 warps with the fence moved to the MMA thread
+// 124 / 127;  8 warps with the fence in the MMA thread 112 / 122;  three k blocks in flight 68 (spills).  More warps or
+// deeper prefetch do not help: with everything but the global loads switched off the loop still takes 0.79-0.92 ms of
+// the 0.96-1.16 -- every 128 x 128 tile re-reads its operands from L2 (32 KB per MFLOP, 4.3 GB in all), which caps
+// this one-CTA-per-tile design near 165 TFLOP/s; the MMAs alone reach 265 TFLOP/s = 0.68 of the TF32 rate (M = 128
+// SS-mode operand reads).  Past that: cta_group::2 / cluster multicast (operands shared by a CTA pair), N = 256 tiles.
 constexpr int NBUILD = 256;   // builder threads (8 warps)
 constexpr int TILE_BYTES = BM * BK * 4;   // one operand tile (hi or lo), BN <= 128 uses the same footprint
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;   // A_hi, A_lo, B_hi, B_lo
