@@ -392,6 +392,28 @@ class ADBackend:
             return [da1, db1, da2, db2]
         return self._node(B.smatmul2_sum(a1.p, b1.p, a2.p, b2.p), [a1, b1, a2, b2], pb)
 
+    def smatmul2_sum_tanh(self, a1, b1, a2, b2, bias):
+        """tanh (a1 b1 + a2 b2 + bias): `smatmul2_sum` and `tanh_affine` as ONE node (one launch forward: bias and
+        tanh ride in the epilogue of the paired product); the pullback is the composition of theirs."""
+        B = self.B
+        a1, b1, a2, b2, bias = self.lift(a1), self.lift(b1), self.lift(a2), self.lift(b2), self.lift(bias)
+        tr = lambda t: B.stranspose([1, 0], t)
+        y = B.smatmul2_sum_tanh(a1.p, b1.p, a2.p, b2.p, bias.p)
+
+        def pb(c0):
+            c, dbias = B.tanh_affine_bwd(y, c0, want_bias=bias.d is not None)
+            da1 = DeferredMatmul(c, tr(b1.p)) if a1.d is not None else None
+            da2 = DeferredMatmul(c, tr(b2.p)) if a2.d is not None else None
+            if da1 is not None and da2 is not None:
+                da1.partner, da2.partner = 2, 0
+            if b1.d is not None and b2.d is not None and B.shape(a1.p) == B.shape(a2.p):
+                db1, db2 = B.smatmul2_pair(tr(a1.p), c, tr(a2.p), c)
+            else:
+                db1 = DeferredMatmul(tr(a1.p), c) if b1.d is not None else None
+                db2 = DeferredMatmul(tr(a2.p), c) if b2.d is not None else None
+            return [da1, db1, da2, db2, dbias]
+        return self._node(y, [a1, b1, a2, b2, bias], pb)
+
     def smatvecmul(self, m, v):
         B = self.B
         m, v = self.lift(m), self.lift(v)
@@ -830,6 +852,9 @@ class FwdBackend:
 
     def smatmul2_sum(self, a1, b1, a2, b2):
         return self.binary("add", self.smatmul2(a1, b1), self.smatmul2(a2, b2))
+
+    def smatmul2_sum_tanh(self, a1, b1, a2, b2, bias):
+        return self.tanh_affine(self.smatmul2_sum(a1, b1, a2, b2), None, bias)
     def conv2dPreserving(self, K, A): return self._bilinear(self.B.conv2dPreserving, K, A)
 
     def sdot1InSumN(self, a, b, n):

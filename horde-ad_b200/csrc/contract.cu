@@ -237,7 +237,7 @@ int hb_gemm_dmma(const double *A, int64_t a_sm, int64_t a_sk, const double *B, i
 int hb_gemm_dmma_pair(const double *A1, int64_t a1_sm, int64_t a1_sk, const double *B1, int64_t b1_sk, int64_t b1_sn,
                       int64_t K1, const double *A2, int64_t a2_sm, int64_t a2_sk, const double *B2, int64_t b2_sk,
                       int64_t b2_sn, int64_t K2, double *C1, double *C2, int64_t M, int64_t N, int chain, int accum,
-                      int *done);
+                      int *done, const double *epi_bias = nullptr);
 int hb_gemm_dmma_list(int n, const double *const *A, int64_t a_sm, int64_t a_sk, const double *const *B, int64_t b_sk,
                       int64_t b_sn, double *C, int64_t M, int64_t N, int64_t K, int accum, int *done);
 int hb_reduce_generic(const hb_array *a, const hb_array *b, int nk, const int *kax, int nr,
@@ -506,6 +506,52 @@ extern "C" int hb_matmul2_sum(const hb_array *a1, const hb_array *b1, const hb_a
   HB_TRY(hb_matmul2(a1, b1, &t));
   int st = hb_matmul2_acc(t, a2, b2, out);
   hb_release(t);
+  return st;
+}
+
+extern "C" int hb_tanh_affine_fwd(const hb_array *u, const hb_array *v, const hb_array *bias, hb_array **y_out);
+
+// tanh (a1 x b1 + a2 x b2 + bias stretched over the columns): the whole rnnMnistLayerS (MnistRnnShaped2.hs:55-69) as
+// one launch -- the paired product with the bias + tanh in the epilogue of the last K slice of each tile's chain.
+// Bit-identical to hb_matmul2_sum followed by hb_tanh_affine_fwd (same sums, same tanh), which is also the fallback.
+extern "C" int hb_matmul2_sum_tanh(const hb_array *a1, const hb_array *b1, const hb_array *a2, const hb_array *b2,
+                                   const hb_array *bias, hb_array **out) {
+  hb_prof_scope prof_("matmul2_sum_tanh", a1, b1);
+  HB_CHECK_INIT_LAZY();
+  HB_REQUIRE(a1 && b1 && a2 && b2 && bias && out, "null argument");
+  HB_REQUIRE(pair_shapes_ok(a1, b1, a2, b2), "smatmul2 + smatmul2: %s x %s + %s x %s", hb_shape_str(a1).c_str(),
+             hb_shape_str(b1).c_str(), hb_shape_str(a2).c_str(), hb_shape_str(b2).c_str());
+  HB_REQUIRE(bias->rank == 1 && bias->shape[0] == a1->shape[0] && bias->dt == a1->dt,
+             "matmul2_sum_tanh: bias must be [%lld] of the operands' type", (long long)a1->shape[0]);
+  if (hb_lazy_on()) {
+    int64_t sh_[2] = {a1->shape[0], b1->shape[1]};
+    return hb_lrec(HB_L_GENERIC, "matmul2_sum_tanh").in(a1).in(b1).in(a2).in(b2).in(bias).out(out, a1->dt, 2, sh_).commit(
+        [=](hb_lnode &n, hb_array *const *in, hb_array **o) { return hb_matmul2_sum_tanh(in[0], in[1], in[2], in[3], in[4], &o[0]); });
+  }
+  Op2 A1, B1, A2, B2;
+  hb_array *tmp[4] = {nullptr, nullptr, nullptr, nullptr};
+  auto drop = [&]() { for (hb_array *t : tmp) hb_release(t); };
+  if (a1->dt == HB_F64 && hb_contig(bias) && op2_pack(a1, &A1, &tmp[0]) && op2_pack(b1, &B1, &tmp[1]) &&
+      op2_pack(a2, &A2, &tmp[2]) && op2_pack(b2, &B2, &tmp[3])) {
+    int64_t sh[2] = {a1->shape[0], b1->shape[1]};
+    hb_array *o;
+    int st = hb_new_array(HB_F64, 2, sh, &o);
+    if (st != HB_OK) { drop(); return st; }
+    int done = 0;
+    st = hb_gemm_dmma_pair(A1.p, A1.s0, A1.s1, B1.p, B1.s0, B1.s1, a1->shape[1], A2.p, A2.s0, A2.s1, B2.p, B2.s0,
+                           B2.s1, a2->shape[1], (double *)hb_data(o), nullptr, sh[0], sh[1], 1, 0, &done,
+                           (const double *)hb_data(bias));
+    drop();
+    if (st != HB_OK) { hb_release(o); return st; }
+    if (done) { *out = o; return HB_OK; }
+    hb_release(o);
+  } else {
+    drop();
+  }
+  hb_array *pre = nullptr;
+  HB_TRY(hb_matmul2_sum(a1, b1, a2, b2, &pre));
+  int st = hb_tanh_affine_fwd(pre, nullptr, bias, out);
+  hb_release(pre);
   return st;
 }
 

@@ -64,6 +64,9 @@ struct GemmP {
   // (K % BK8 == 0, so a chunk never straddles two entries); slices go to partial buffers + the fixed-order reduce.
   int nlist;
   const double *Al[32], *Bl[32];
+  // epilogue of the LAST slice of a serial chain (or of an unsplit product): C = tanh (C + bias[m]) -- the body of
+  // rnnMnistLayerS, tanh (wX x + wS s + b), without a separate elementwise pass
+  const double *epi_bias;
 };
 
 // Stage one operand tile: `rows` x BK where the operand's (row, k) element is
@@ -341,6 +344,7 @@ __global__ void __launch_bounds__(256, 2) gemm8_dmma_kernel(const __grid_constan
   }
   const bool addc = serial ? (z > 0 || p.accum) : (p.accum && gridDim.z == 1);
   const bool cvec = (p.c_sm & 1) == 0 && ((uintptr_t)C & 15) == 0;
+  const bool epi = p.epi_bias != nullptr && (serial ? z + 1 == zlen : gridDim.z == 1);
 #pragma unroll
   for (int i = 0; i < 4; i++)
 #pragma unroll
@@ -348,6 +352,7 @@ __global__ void __launch_bounds__(256, 2) gemm8_dmma_kernel(const __grid_constan
       int m = m0 + wm + i * 8 + fr, n = n0 + wn + j * 8 + fk * 2;
       if (m < p.M) {
         double *c = C + (int64_t)m * p.c_sm + n;
+        const double eb = epi ? p.epi_bias[m] : 0.0;
         if (n + 1 < p.N && cvec) {
           double2 o = make_double2(acc[i][j][0], acc[i][j][1]);
           if (addc) {
@@ -355,10 +360,17 @@ __global__ void __launch_bounds__(256, 2) gemm8_dmma_kernel(const __grid_constan
             o.x = t.x + o.x;
             o.y = t.y + o.y;
           }
+          if (epi) { o.x = tanh(o.x + eb); o.y = tanh(o.y + eb); }
           __stcg(reinterpret_cast<double2 *>(c), o);
         } else {
-          if (n < p.N) __stcg(c, addc ? __ldcg(c) + acc[i][j][0] : acc[i][j][0]);
-          if (n + 1 < p.N) __stcg(c + 1, addc ? __ldcg(c + 1) + acc[i][j][1] : acc[i][j][1]);
+          if (n < p.N) {
+            double v0 = addc ? __ldcg(c) + acc[i][j][0] : acc[i][j][0];
+            __stcg(c, epi ? tanh(v0 + eb) : v0);
+          }
+          if (n + 1 < p.N) {
+            double v1 = addc ? __ldcg(c + 1) + acc[i][j][1] : acc[i][j][1];
+            __stcg(c + 1, epi ? tanh(v1 + eb) : v1);
+          }
         }
       }
     }
@@ -606,8 +618,9 @@ int hb_gemm_dmma_list(int n, const double *const *A, int64_t a_sm, int64_t a_sk,
 int hb_gemm_dmma_pair(const double *A1, int64_t a1_sm, int64_t a1_sk, const double *B1, int64_t b1_sk, int64_t b1_sn,
                       int64_t K1, const double *A2, int64_t a2_sm, int64_t a2_sk, const double *B2, int64_t b2_sk,
                       int64_t b2_sn, int64_t K2, double *C1, double *C2, int64_t M, int64_t N, int chain, int accum,
-                      int *done) {
+                      int *done, const double *epi_bias) {
   *done = 0;
+  if (epi_bias && (!chain || accum)) return HB_OK;   // the epilogue belongs to the one chain of `A1 B1 + A2 B2`
   if (M <= 0 || N <= 0 || K1 <= 0 || K2 <= 0) return HB_OK;
   if (M >= (1ll << 31) || N >= (1ll << 31) || K1 >= (1ll << 31) || K2 >= (1ll << 31)) return HB_OK;
   const bool a_kfast = a1_sk == 1, b_kfast = b1_sk == 1;
@@ -624,6 +637,7 @@ int hb_gemm_dmma_pair(const double *A1, int64_t a1_sm, int64_t a1_sk, const doub
   p.c_sm = N;
   p.accum = accum;
   p.chain = chain;
+  p.epi_bias = epi_bias;
   p.a_vec = ((uintptr_t)A1 & 15) == 0 && ((a_kfast ? a1_sm : a1_sk) % 2 == 0);
   p.b_vec = ((uintptr_t)B1 & 15) == 0 && ((b_kfast ? b1_sn : b1_sk) % 2 == 0);
   p.a_vec2 = ((uintptr_t)A2 & 15) == 0 && ((a_kfast ? a2_sm : a2_sk) % 2 == 0);

@@ -389,6 +389,12 @@ class DeviceBackend:
                 outs.append(_wrap(p))
         return outs[0], outs[1]
 
+    def smatmul2_sum_tanh(self, a1, b1, a2, b2, bias):
+        """tanh (a1 b1 + a2 b2 + bias stretched over the columns): one launch (hb_matmul2_sum_tanh)."""
+        p = _out()
+        call("hb_matmul2_sum_tanh", a1.h, b1.h, a2.h, b2.h, bias.h, C.byref(p))
+        return _wrap(p)
+
     def smatmul2_list(self, pairs, acc=None):
         """acc + sum_t a_t b_t as ONE product over the concatenated reduced axes (hb_matmul2_list); in place when
         `acc` is uniquely referenced."""

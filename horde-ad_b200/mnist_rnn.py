@@ -28,7 +28,9 @@ def rnnMnistLayerS(T, s, x, wX, wS, b, fused=False):
     stretched bias and tanh as the one contraction-pass node `tanh_affine`; `fused == "pair"`: additionally
     `wX x + wS s` as the node `smatmul2_sum`."""
     batch = T.shape(x)[1]
-    if fused == "pair":   # the two products and their sum as one node as well (one paired GEMM launch)
+    if fused == "pair":   # the two products, their sum, the bias and tanh as ONE node (one paired GEMM launch)
+        if hasattr(T, "smatmul2_sum_tanh"):
+            return T.smatmul2_sum_tanh(wX, x, wS, s, b)
         return T.tanh_affine(T.smatmul2_sum(wX, x, wS, s), None, b)
     if fused:
         return T.tanh_affine(T.smatmul2(wX, x), T.smatmul2(wS, s), b)

@@ -393,6 +393,12 @@ int hb_matmul2_acc_pair(hb_array *acc1, const hb_array *a1,
                         const hb_array *b1, hb_array *acc2,
                         const hb_array *a2, const hb_array *b2,
                         hb_array **out1, hb_array **out2);
+/* tanh (a1 x b1 + a2 x b2 + bias[row]): the body of rnnMnistLayerS
+ * (MnistRnnShaped2.hs:55-69) in one launch (bias + tanh in the epilogue of the
+ * paired product); bit-identical to hb_matmul2_sum + hb_tanh_affine_fwd. */
+int hb_matmul2_sum_tanh(const hb_array *a1, const hb_array *b1,
+                        const hb_array *a2, const hb_array *b2,
+                        const hb_array *bias, hb_array **out);
 /* acc + sum_t a[t] x b[t] for n products of one shape (acc may be NULL): the
  * cotangent of a weight used at every step of an unrolled loop (taddTarget
  * over the transposition rule of tsmatmul2, DeltaEval.hs:317-332), evaluated

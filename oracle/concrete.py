@@ -267,6 +267,10 @@ class ConcreteBackend:
     def smatmul2_acc_pair(self, acc1, a1, b1, acc2, a2, b2):
         return acc1 + self.smatmul2(a1, b1), acc2 + self.smatmul2(a2, b2)
 
+    def smatmul2_sum_tanh(self, a1, b1, a2, b2, bias):
+        """rnnMnistLayerS (MnistRnnShaped2.hs:55-69): tanh (wX x + wS s + b stretched over the batch)."""
+        return np.tanh((self.smatmul2(a1, b1) + self.smatmul2(a2, b2)) + np.asarray(bias)[:, None])
+
     def smatmul2_list(self, pairs, acc=None):
         """taddTarget folded over the contributions `tsmatmul2 a_t b_t` of one weight (DeltaEval.hs:317-332),
         in arrival order."""

@@ -1013,6 +1013,27 @@ def test_tanh_affine_node(dev, dtype, shape):
     assert none is None and np.array_equal(dev.to_numpy(dz2), dev.to_numpy(dz))
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("shape", [(512, 28, 512, 1024), (512, 512, 512, 1024), (64, 40, 24, 130), (3, 2, 5, 4)])
+def test_matmul2_sum_tanh_is_the_unfused_pair_bit_for_bit(dev, oracle, dtype, shape):
+    """hb_matmul2_sum_tanh (bias + tanh in the epilogue of the paired product's last K slice) == hb_matmul2_sum
+    followed by hb_tanh_affine_fwd, bit for bit (same sums, same tanh); and both against the oracle."""
+    m, k1, k2, n = shape
+    rng = np.random.default_rng(23)
+    a1, b1 = rnd(rng, (m, k1), dtype), rnd(rng, (k1, n), dtype)
+    a2, b2 = rnd(rng, (m, k2), dtype), rnd(rng, (k2, n), dtype)
+    bias = rnd(rng, (m,), dtype)
+    d = [dev.sconcrete(x) for x in (a1, b1, a2, b2, bias)]
+    fused = dev.to_numpy(dev.smatmul2_sum_tanh(*d))
+    two = dev.to_numpy(dev.tanh_affine_fwd(dev.smatmul2_sum(*d[:4]), None, d[4]))
+    exact(fused, two)
+    ref = oracle.smatmul2_sum_tanh(*[x.astype(np.float64) for x in (a1, b1, a2, b2, bias)])
+    close(fused, ref.astype(dtype), dtype, scale=8 * (k1 + k2))
+    # operands as transposed views (the orientations the RNN's backward pass hands over)
+    dt = [dev.stranspose([1, 0], dev.sconcrete(np.ascontiguousarray(x.T))) for x in (a1, b1, a2, b2)]
+    exact(dev.to_numpy(dev.smatmul2_sum_tanh(*dt, d[4])), dev.to_numpy(dev.tanh_affine_fwd(dev.smatmul2_sum(*dt), None, d[4])))
+
+
 @pytest.mark.parametrize("name,mk,expected", P.VSTACK_GOLDEN, ids=[v[0] for v in P.VSTACK_GOLDEN])
 def test_vstack_known_answers_on_the_device(dev, name, mk, expected):
     """vstackABC / vstackBuild (TestAdaptorSimplified.hs:785-835, 949) through the C ABI, and the
