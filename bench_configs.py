@@ -301,42 +301,48 @@ def run_configs(dev, quick=False, skip_families=False, only_families=False, emit
     # --------------------------------------------------------------------- RNN
     sec.begin("MnistRnnShaped2")
     width, batch = 512, (256 if args.quick else 1024)
-    params = [dev.sconcrete(p) for p in mnist_rnn.init_params(width, rng_range=0.05)]
+    # parameters, moments and the gradient bucket as flat arrays (the trainer's layout, train.py): Adam with its
+    # device-side step counter then lives INSIDE the step's CUDA graph, as one launch
+    from horde_ad_b200.train import BucketLayout, exchange_scale
+    host = mnist_rnn.init_params(width, rng_range=0.05)
+    lay = BucketLayout([p.shape for p in host])
+    flat = lay.flatten(host, 0.0)[:lay.n_params]
+    fp, fm, fv = dev.sconcrete(flat), dev.sconcrete(np.zeros_like(flat)), dev.sconcrete(np.zeros_like(flat))
+    t_dev = dev.sconcrete(np.zeros((), np.int64))
+    params = [dev.sreshape(list(sh), dev.sslice(off, n, fp)) for sh, n, off in zip(lay.shapes, lay.sizes, lay.offsets)]
     glyphs = dev.sconcrete(rng.uniform(0, 1, (batch, 28, 28)))
     labels = dev.sconcrete(np.eye(10)[rng.integers(0, 10, batch)])
-    moms = [(dev.sconcrete(np.zeros(p.shape)), dev.sconcrete(np.zeros(p.shape))) for p in params]
-    tstep = [0]
 
     def rnn_grad():
         return ad.grad(dev, lambda T, *ps: mnist_rnn.rnnMnistLossFusedS(T, glyphs, labels, list(ps), fused=RNN_FUSION), params)
 
-    def rnn_apply(grads):
-        tstep[0] += 1
-        for p, (mm, vv), g in zip(params, moms, grads):
-            dev.adam_step(p, mm, vv, g, tstep[0])
+    def rnn_apply(val, grads):
+        bucket = dev.flatten_concat(list(grads) + [val])
+        ffi.call("hb_allreduce_adam_step", bucket.h, lay.n_params, fp.h, fm.h, fv.h, t_dev.h, 1e-3, 0.9, 0.999, 1e-7,
+                 exchange_scale(1))
+        return bucket
     # eager: one C-ABI call per op, as the interpreter would issue them
     val, grads = rnn_grad()
-    rnn_apply(grads)
+    rnn_apply(val, grads)
     dev.sync()
     t0 = time.perf_counter()
     for _ in range(3):
         val, grads = rnn_grad()
-        rnn_apply(grads)
+        rnn_apply(val, grads)
     dev.sync()
     eager_ms = (time.perf_counter() - t0) / 3 * 1e3
-    # the gradient program captured once into a CUDA graph; Adam stays
-    # outside (its bias-corrected step size depends on t)
+    # the whole step -- gradient program, bucket, Adam -- captured once into a CUDA graph
     del val, grads
     ffi.call("hb_graph_begin")
     try:
         val, grads = rnn_grad()
+        bucket = rnn_apply(val, grads)
     finally:
         gph = C.c_void_p()
         ffi.call("hb_graph_end", C.byref(gph))
 
     def rnn_step():
         ffi.call("hb_graph_launch", gph)
-        rnn_apply(grads)
     step_ms = timed(dev, rnn_step, 10)
     loss = float(dev.kfromS(val))
     # flops: per time step 2 layers x (W_x x + W_s s), fwd + 2x bwd
@@ -345,7 +351,8 @@ def run_configs(dev, quick=False, skip_families=False, only_families=False, emit
     emit(({"config": "MnistRnnShaped2", "width": width, "seq": 28, "per_gpu_batch": batch, "ms_per_step": step_ms,
                       "ms_per_step_eager": eager_ms,
                       "program": "rnnMnistLossFusedS with the paired-product / tanh_affine nodes selected ABOVE the C ABI "
-                                 "(fused='pair'; weight cotangents as hb_matmul2_list; not the contraction pass)",
+                                 "(fused='pair'; weight cotangents as hb_matmul2_list, bias cotangents accumulated by the tanh adjoint; not the "
+                                 "contraction pass); flat parameters + Adam (device step counter) inside the same CUDA graph",
                       "samples_per_s": batch / (step_ms * 1e-3), "loss": loss if np.isfinite(loss) else None,
                       "roofline": {"bound": "tensor", "achieved": tf, "peak": fp64.value, "unit": "TFLOP/s",
                                    "frac": tf / fp64.value, "peak_source": "hb_microbench FP64 DMMA, this run",

@@ -29,12 +29,23 @@ _ids = itertools.count(1)
 
 
 class Node:
-    __slots__ = ("id", "parents", "pullback")
+    __slots__ = ("id", "parents", "pullback", "acc")
 
-    def __init__(self, parents, pullback):
+    def __init__(self, parents, pullback, acc=None):
         self.id = next(_ids)
         self.parents = parents      # list[Node | None]
         self.pullback = pullback    # c -> list of cotangents (None = zero)
+        # (slot, fn): fn(c, acc) is the pullback with the cotangent of parents[slot] ACCUMULATED into `acc` by the
+        # pass that produces it (the sweep offers it only an accumulator it created itself)
+        self.acc = acc
+
+
+class Fresh:
+    """A cotangent contribution in an array nobody else holds: the sweep may later update it in place."""
+    __slots__ = ("x",)
+
+    def __init__(self, x):
+        self.x = x
 
 
 class ADVal:
@@ -104,11 +115,11 @@ class ADBackend:
     def primal(self, x):
         return x.p if isinstance(x, ADVal) else x
 
-    def _node(self, p, parents: Sequence[ADVal], pullback) -> ADVal:
+    def _node(self, p, parents: Sequence[ADVal], pullback, acc=None) -> ADVal:
         ds = [a.d for a in parents]
         if all(d is None for d in ds):
             return ADVal(p)
-        return ADVal(p, Node(ds, pullback))
+        return ADVal(p, Node(ds, pullback, acc))
 
     def shape(self, t): return tuple(self.primal(t).shape)
     def dtype(self, t): return self.B.dtype(self.primal(t))
@@ -400,8 +411,12 @@ class ADBackend:
         tr = lambda t: B.stranspose([1, 0], t)
         y = B.smatmul2_sum_tanh(a1.p, b1.p, a2.p, b2.p, bias.p)
 
-        def pb(c0):
-            c, dbias = B.tanh_affine_bwd(y, c0, want_bias=bias.d is not None)
+        def pb(c0, acc=None):
+            if acc is not None:
+                c, dbias = B.tanh_affine_bwd_acc(y, c0, acc)
+            else:
+                c, dbias = B.tanh_affine_bwd(y, c0, want_bias=bias.d is not None)
+                dbias = Fresh(dbias) if dbias is not None else None
             da1 = DeferredMatmul(c, tr(b1.p)) if a1.d is not None else None
             da2 = DeferredMatmul(c, tr(b2.p)) if a2.d is not None else None
             if da1 is not None and da2 is not None:
@@ -412,7 +427,8 @@ class ADBackend:
                 db1 = DeferredMatmul(tr(a1.p), c) if b1.d is not None else None
                 db2 = DeferredMatmul(tr(a2.p), c) if b2.d is not None else None
             return [da1, db1, da2, db2, dbias]
-        return self._node(y, [a1, b1, a2, b2, bias], pb)
+        use_acc = hasattr(B, "tanh_affine_bwd_acc") and not _NO_BIAS_ACC
+        return self._node(y, [a1, b1, a2, b2, bias], pb, acc=(4, pb) if use_acc else None)
 
     def smatvecmul(self, m, v):
         B = self.B
@@ -509,6 +525,7 @@ class ADBackend:
 
 _NO_MATMUL_ACC = bool(os.environ.get("HB_AD_NO_MATMUL_ACC"))   # measurement switch: product + separate add
 _NO_MATMUL_LIST = bool(os.environ.get("HB_AD_NO_MATMUL_LIST"))  # measurement switch: accumulate weight cotangents per step
+_NO_BIAS_ACC = bool(os.environ.get("HB_AD_NO_BIAS_ACC"))        # measurement switch: bias cotangents by a separate add
 
 
 class DeferredMatmul:
@@ -596,7 +613,22 @@ def grad(base, f: Callable, inputs: Sequence, dt=None):
                         c = base.binary("add", c, base.smatmul2_list(lst, None))
                 grads[input_ix[nid]] = c
                 continue
-            cs = list(node.pullback(c))
+            acc_slot = None
+            if node.acc is not None:
+                slot, fn = node.acc
+                parent = node.parents[slot]
+                if (parent is not None and parent.id in owned and cot.get(parent.id) is not None
+                        and not isinstance(cot[parent.id], DeferredPad)):
+                    acc_slot = slot
+            if acc_slot is not None:
+                pid = node.parents[acc_slot].id
+                held = cot.pop(pid)            # hand over the only reference: the update may then be in place
+                cs = list(fn(c, held))
+                del held
+                cot[pid] = cs[acc_slot]
+                cs[acc_slot] = None
+            else:
+                cs = list(node.pullback(c))
             if use_list:
                 for i, pc in enumerate(cs):
                     parent = node.parents[i]
@@ -621,6 +653,11 @@ def grad(base, f: Callable, inputs: Sequence, dt=None):
             for parent, pc in zip(node.parents, cs):
                 if parent is None or pc is None:
                     continue
+                fresh = isinstance(pc, Fresh)
+                if fresh:
+                    pc = pc.x
+                    if cot.get(parent.id) is None:     # first contribution: the sweep owns this array
+                        owned.add(parent.id)
                 deferred = isinstance(pc, DeferredMatmul)
                 if parent.id in cot and cot[parent.id] is None:    # placeholder of an input with pending products
                     if deferred or isinstance(pc, DeferredPad):

@@ -820,28 +820,51 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256)
+// One CTA of 128 threads per row: 16-byte loads when the row length allows, row sum by warp shuffles + one
+// shared-memory hop in a fixed order (deterministic).  ACC: dbias[row] += sum (the accumulator of an unrolled
+// loop's bias cotangent -- one CTA owns a row, so the update is race-free and ordered by the launches).
+template <typename T, bool ACC>
+__global__ void __launch_bounds__(128)
     hb_tanh_affine_bwd_kernel(const T *__restrict__ y, const T *__restrict__ c, int64_t cols, T *__restrict__ dz,
                               T *__restrict__ dbias) {
-  __shared__ T red[256];
+  constexpr int V = 16 / (int)sizeof(T);
+  __shared__ T red[4];
   const int64_t row = blockIdx.x;
   const T *yr = y + row * cols, *cr = c + row * cols;
   T *dr = dz + row * cols;
   T s = T(0);
-  for (int64_t j = threadIdx.x; j < cols; j += 256) {
-    T yy = yr[j];
-    T d = (T(1) - yy * yy) * cr[j];
-    dr[j] = d;
-    s += d;
+  const bool vec = cols % V == 0 && (((uintptr_t)y | (uintptr_t)c | (uintptr_t)dz) & 15) == 0;
+  if (vec) {
+    using VT = typename std::conditional<sizeof(T) == 8, double2, float4>::type;
+    const int64_t nv = cols / V;
+#pragma unroll 4
+    for (int64_t j = threadIdx.x; j < nv; j += 128) {
+      VT yy = __ldcg(reinterpret_cast<const VT *>(yr) + j), cc = __ldcg(reinterpret_cast<const VT *>(cr) + j), d;
+      T *yp = reinterpret_cast<T *>(&yy), *cp = reinterpret_cast<T *>(&cc), *dp = reinterpret_cast<T *>(&d);
+#pragma unroll
+      for (int k = 0; k < V; k++) {
+        dp[k] = (T(1) - yp[k] * yp[k]) * cp[k];
+        s += dp[k];
+      }
+      reinterpret_cast<VT *>(dr)[j] = d;
+    }
+  } else {
+    for (int64_t j = threadIdx.x; j < cols; j += 128) {
+      T yy = yr[j];
+      T d = (T(1) - yy * yy) * cr[j];
+      dr[j] = d;
+      s += d;
+    }
   }
-  red[threadIdx.x] = s;
+  if (!dbias) return;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
   __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
-    __syncthreads();
+  if (threadIdx.x == 0) {
+    T t = (red[0] + red[1]) + (red[2] + red[3]);
+    dbias[row] = ACC ? dbias[row] + t : t;
   }
-  if (threadIdx.x == 0 && dbias) dbias[row] = red[0];
 }
 
 extern "C" int hb_tanh_affine_fwd(const hb_array *u, const hb_array *v, const hb_array *bias, hb_array **y_out) {
@@ -888,6 +911,40 @@ extern "C" int hb_tanh_affine_fwd(const hb_array *u, const hb_array *v, const hb
   return HB_OK;
 }
 
+// dz = (1 - y^2) * c; the row sums go to a fresh [rows] array (*dbias_out) or, acc != NULL, are ADDED to acc in
+// place (acc is an accumulator the caller owns: hb_tanh_affine_bwd_acc)
+static int tanh_affine_bwd_impl(const hb_array *y, const hb_array *c, hb_array *acc, hb_array **dz_out, hb_array **dbias_out) {
+  const hb_array *yc = y, *cc = c;
+  hb_array *t1 = nullptr, *t2 = nullptr, *dz = nullptr, *db = nullptr;
+  int st = HB_OK;
+  if (!hb_contig(y)) { st = hb_contiguous(y, &t1); yc = t1; }
+  if (st == HB_OK && !hb_contig(c)) { st = hb_contiguous(c, &t2); cc = t2; }
+  if (st == HB_OK) st = hb_new_array(y->dt, 2, y->shape, &dz);
+  const int64_t rows = y->shape[0], cols = y->shape[1];
+  // every row's CTA writes its sum: zero fill only for the degenerate empty row
+  if (st == HB_OK && dbias_out) st = cols > 0 ? hb_new_array(y->dt, 1, y->shape, &db) : hb_zeros(y->dt, 1, y->shape, &db);
+  if (st == HB_OK && rows > 0 && cols > 0) {
+    void *bias = acc ? hb_data(acc) : db ? hb_data(db) : nullptr;
+#define HB_TAB_LAUNCH(T, ACC)                                                                                  \
+  hb_tanh_affine_bwd_kernel<T, ACC><<<(unsigned)rows, 128, 0, g_hb.stream>>>(                                  \
+      (const T *)hb_data(yc), (const T *)hb_data(cc), cols, (T *)hb_data(dz), (T *)bias)
+    if (y->dt == HB_F64) {
+      if (acc) HB_TAB_LAUNCH(double, true);
+      else HB_TAB_LAUNCH(double, false);
+    } else {
+      if (acc) HB_TAB_LAUNCH(float, true);
+      else HB_TAB_LAUNCH(float, false);
+    }
+#undef HB_TAB_LAUNCH
+    HB_LAUNCHED();
+  }
+  hb_release(t1); hb_release(t2);
+  if (st != HB_OK) { hb_release(dz); hb_release(db); return st; }
+  *dz_out = dz;
+  if (dbias_out) *dbias_out = db;
+  return HB_OK;
+}
+
 extern "C" int hb_tanh_affine_bwd(const hb_array *y, const hb_array *c, hb_array **dz_out, hb_array **dbias_out) {
   hb_prof_scope prof_("tanh_affine_bwd", y);
   HB_CHECK_INIT_LAZY();
@@ -898,28 +955,39 @@ extern "C" int hb_tanh_affine_bwd(const hb_array *y, const hb_array *c, hb_array
   if (hb_lazy_on())
     return hb_lrec(HB_L_GENERIC, "tanh_affine_bwd").in(y).in(c).out(dz_out, y->dt, 2, y->shape).out(dbias_out, y->dt, 1, y->shape)
         .commit([=](hb_lnode &n, hb_array *const *in, hb_array **o) { return hb_tanh_affine_bwd(in[0], in[1], &o[0], n.out[1] ? &o[1] : nullptr); });
-  const hb_array *yc = y, *cc = c;
-  hb_array *t1 = nullptr, *t2 = nullptr, *dz = nullptr, *db = nullptr;
-  int st = HB_OK;
-  if (!hb_contig(y)) { st = hb_contiguous(y, &t1); yc = t1; }
-  if (st == HB_OK && !hb_contig(c)) { st = hb_contiguous(c, &t2); cc = t2; }
-  if (st == HB_OK) st = hb_new_array(y->dt, 2, y->shape, &dz);
-  if (st == HB_OK && dbias_out) st = hb_zeros(y->dt, 1, y->shape, &db);
-  const int64_t rows = y->shape[0], cols = y->shape[1];
-  if (st == HB_OK && rows > 0 && cols > 0) {
-    if (y->dt == HB_F64)
-      hb_tanh_affine_bwd_kernel<double><<<(unsigned)rows, 256, 0, g_hb.stream>>>(
-          (const double *)hb_data(yc), (const double *)hb_data(cc), cols, (double *)hb_data(dz),
-          db ? (double *)hb_data(db) : nullptr);
-    else
-      hb_tanh_affine_bwd_kernel<float><<<(unsigned)rows, 256, 0, g_hb.stream>>>(
-          (const float *)hb_data(yc), (const float *)hb_data(cc), cols, (float *)hb_data(dz),
-          db ? (float *)hb_data(db) : nullptr);
-    HB_LAUNCHED();
+  return tanh_affine_bwd_impl(y, c, nullptr, dz_out, dbias_out);
+}
+
+// dz as above; *acc_out = dbias_acc + row sums.  Value semantics like hb_matmul2_acc: the accumulator's storage is
+// updated in place (and handed back retained) only when the caller holds the single reference to it.
+extern "C" int hb_tanh_affine_bwd_acc(const hb_array *y, const hb_array *c, hb_array *dbias_acc, hb_array **dz_out,
+                                      hb_array **acc_out) {
+  hb_prof_scope prof_("tanh_affine_bwd_acc", y);
+  HB_CHECK_INIT_LAZY();
+  HB_REQUIRE(y && c && dbias_acc && dz_out && acc_out, "null argument");
+  HB_REQUIRE(y->rank == 2 && hb_same_shape(y, c) && y->dt == c->dt && hb_is_float(y->dt),
+             "tanh_affine_bwd_acc: two floating [width, batch] operands of one shape required");
+  HB_REQUIRE(y->shape[0] < (1ll << 31), "tanh_affine_bwd_acc: too many rows");
+  HB_REQUIRE(dbias_acc->rank == 1 && dbias_acc->shape[0] == y->shape[0] && dbias_acc->dt == y->dt,
+             "tanh_affine_bwd_acc: the accumulator must be a [width] array of the operands' type");
+  if (hb_lazy_on())
+    return hb_lrec(HB_L_GENERIC, "tanh_affine_bwd_acc").in(y).in(c).in(dbias_acc).out(dz_out, y->dt, 2, y->shape)
+        .out(acc_out, y->dt, 1, y->shape)
+        .commit([=](hb_lnode &, hb_array *const *in, hb_array **o) {
+          return hb_tanh_affine_bwd_acc(in[0], in[1], in[2], &o[0], &o[1]);
+        });
+  const bool unique = dbias_acc->rc.load() == 1 && dbias_acc->st && dbias_acc->st->rc.load() == 1 && hb_contig(dbias_acc) &&
+                      dbias_acc->st != y->st && dbias_acc->st != c->st;
+  if (unique) {
+    HB_TRY(tanh_affine_bwd_impl(y, c, dbias_acc, dz_out, nullptr));
+    hb_retain(dbias_acc);
+    *acc_out = dbias_acc;
+    return HB_OK;
   }
-  hb_release(t1); hb_release(t2);
-  if (st != HB_OK) { hb_release(dz); hb_release(db); return st; }
-  *dz_out = dz;
-  if (dbias_out) *dbias_out = db;
-  return HB_OK;
+  hb_array *db = nullptr;
+  HB_TRY(tanh_affine_bwd_impl(y, c, nullptr, dz_out, &db));
+  int st = hb_binary(HB_ADD, dbias_acc, db, acc_out);
+  hb_release(db);
+  if (st != HB_OK) { hb_release(*dz_out); *dz_out = nullptr; }
+  return st;
 }

@@ -543,6 +543,16 @@ class DeviceBackend:
         call("hb_tanh_affine_bwd", y.h, c.h, C.byref(dz), C.byref(db) if want_bias else None)
         return _wrap(dz), (_wrap(db) if want_bias else None)
 
+    def tanh_affine_bwd_acc(self, y: DeviceArray, c: DeviceArray, acc: DeviceArray):
+        """(dz, acc + row sums of dz): the bias cotangent accumulated by the pass that produces the summand, in
+        place when `acc` is uniquely referenced (hb_tanh_affine_bwd_acc)."""
+        dz, p = _out(), _out()
+        call("hb_tanh_affine_bwd_acc", y.h, c.h, acc.h, C.byref(dz), C.byref(p))
+        if p.value == acc.h.value:  # same handle, retained once more
+            ffi._lib.hb_release(p)
+            return _wrap(dz), acc
+        return _wrap(dz), _wrap(p)
+
     def mnist_batch_into(self, pixels: DeviceArray, labels: DeviceArray, order, start: int,
                          glyphs_dst: DeviceArray, targets_dst: DeviceArray):
         """mkMnistDataBatchS on the device (MnistData.hs:134-171): glyph = pixel / 255, target = one-hot

@@ -103,6 +103,7 @@ PROTOTYPES = {
     "hb_mnist_batch_into": [P, P, P, C.c_int64, P, P],
     "hb_tanh_affine_fwd": [P, P, P, PP],
     "hb_tanh_affine_bwd": [P, P, PP, PP],
+    "hb_tanh_affine_bwd_acc": [P, P, P, PP, PP],
     "hb_relu_pool_bwd": [P, P, C.c_int, C.c_int64, C.c_int64, PP, PP],
     "hb_conv_relu_pool_fwd": [P, P, P, C.c_int, PP, PP],
     "hb_conv_relu_pool_bwd": [P, P, P, P, C.c_int, PP, PP, PP],

@@ -488,6 +488,14 @@ int hb_tanh_affine_fwd(const hb_array *u, const hb_array *v,
                        const hb_array *bias, hb_array **y_out);
 int hb_tanh_affine_bwd(const hb_array *y, const hb_array *c, hb_array **dz_out,
                        hb_array **dbias_out);
+/* The same adjoint with the bias cotangent ACCUMULATED (the taddTarget of an
+ * unrolled loop's shared bias, DeltaEval.hs:496-511, fused into the pass that
+ * produces the summand): *acc_out = dbias_acc + row sums.  Value semantics like
+ * hb_matmul2_acc: dbias_acc's storage is reused only when the caller holds the
+ * single reference to it. */
+int hb_tanh_affine_bwd_acc(const hb_array *y, const hb_array *c,
+                           hb_array *dbias_acc, hb_array **dz_out,
+                           hb_array **acc_out);
 
 /* Device twin of the MNIST input pipeline (example/MnistData.hs:134-171,
  * SURVEY.md 8f-3).  `pixels` [n,H,W] and `labels` [n] hold the raw IDX bytes

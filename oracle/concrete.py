@@ -472,6 +472,10 @@ class ConcreteBackend:
         dz, db = tanh_affine_bwd(y, c)
         return dz, (db if want_bias else None)
 
+    def tanh_affine_bwd_acc(self, y, c, acc):
+        dz, db = tanh_affine_bwd(y, c)
+        return dz, acc + db
+
     def conv_relu_pool_bwd(self, K, A, dy, code, ksize, want_bias=True, want_dA=True):
         dpre, db = self.relu_pool_bwd(dy, code, ksize, A.shape[2], A.shape[3], want_bias)
         return (self.conv2d_dkrn(A, dpre, K.shape[2], K.shape[3]), db,

@@ -1034,6 +1034,35 @@ def test_matmul2_sum_tanh_is_the_unfused_pair_bit_for_bit(dev, oracle, dtype, sh
     exact(dev.to_numpy(dev.smatmul2_sum_tanh(*dt, d[4])), dev.to_numpy(dev.tanh_affine_fwd(dev.smatmul2_sum(*dt), None, d[4])))
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("shape", [(512, 1024), (33, 257), (7, 1), (64, 130)])
+def test_tanh_affine_bwd_acc_is_the_adjoint_plus_add(dev, oracle, dtype, shape):
+    """hb_tanh_affine_bwd_acc (bias cotangent accumulated by the pass that produces the row sums) == hb_tanh_affine_bwd
+    followed by the addition, bit for bit; in place exactly when the accumulator is uniquely referenced."""
+    rng = np.random.default_rng(29)
+    y, c, acc = np.tanh(rnd(rng, shape, dtype)), rnd(rng, shape, dtype), rnd(rng, shape[:1], dtype)
+    dy, dc = dev.sconcrete(y), dev.sconcrete(c)
+    dz0, db0 = dev.tanh_affine_bwd(dy, dc)
+    want = dev.to_numpy(dev.binary("add", dev.sconcrete(acc), db0))
+    oz, ob = oracle.tanh_affine_bwd_acc(y.astype(np.float64), c.astype(np.float64), acc.astype(np.float64))
+    close(dev.to_numpy(dz0), oz.astype(dtype), dtype)
+    close(want, ob.astype(dtype), dtype, scale=shape[1])
+    # uniquely referenced accumulator: updated in place, the same handle comes back
+    a1 = dev.sconcrete(acc)
+    dz1, out1 = dev.tanh_affine_bwd_acc(dy, dc, a1)
+    assert out1 is a1
+    exact(dev.to_numpy(dz1), dev.to_numpy(dz0))
+    exact(dev.to_numpy(out1), want)
+    # an accumulator somebody else holds a view of is left alone
+    a2 = dev.sconcrete(acc)
+    view = dev.sreverse(a2)
+    dz2, out2 = dev.tanh_affine_bwd_acc(dy, dc, a2)
+    assert out2 is not a2
+    exact(dev.to_numpy(a2), acc)
+    exact(dev.to_numpy(view), acc[::-1])
+    exact(dev.to_numpy(out2), want)
+
+
 @pytest.mark.parametrize("name,mk,expected", P.VSTACK_GOLDEN, ids=[v[0] for v in P.VSTACK_GOLDEN])
 def test_vstack_known_answers_on_the_device(dev, name, mk, expected):
     """vstackABC / vstackBuild (TestAdaptorSimplified.hs:785-835, 949) through the C ABI, and the
