@@ -395,9 +395,9 @@ class ADBackend:
             da2 = DeferredMatmul(c, tr(b2.p)) if a2.d is not None else None
             if da1 is not None and da2 is not None:
                 da1.partner, da2.partner = 2, 0          # slot of the partner in this node's parent list
-            if b1.d is not None and b2.d is not None and B.shape(a1.p) == B.shape(a2.p):
+            if b1.d is not None and b2.d is not None and B.shape(a1.p) == B.shape(a2.p) and not _use_group(B):
                 db1, db2 = B.smatmul2_pair(tr(a1.p), c, tr(a2.p), c)
-            else:
+            else:       # deferred: the sweep launches them together with whatever else is waiting (smatmul2_group)
                 db1 = DeferredMatmul(tr(a1.p), c) if b1.d is not None else None
                 db2 = DeferredMatmul(tr(a2.p), c) if b2.d is not None else None
             return [da1, db1, da2, db2]
@@ -421,9 +421,9 @@ class ADBackend:
             da2 = DeferredMatmul(c, tr(b2.p)) if a2.d is not None else None
             if da1 is not None and da2 is not None:
                 da1.partner, da2.partner = 2, 0
-            if b1.d is not None and b2.d is not None and B.shape(a1.p) == B.shape(a2.p):
+            if b1.d is not None and b2.d is not None and B.shape(a1.p) == B.shape(a2.p) and not _use_group(B):
                 db1, db2 = B.smatmul2_pair(tr(a1.p), c, tr(a2.p), c)
-            else:
+            else:       # deferred: the sweep launches them together with whatever else is waiting (smatmul2_group)
                 db1 = DeferredMatmul(tr(a1.p), c) if b1.d is not None else None
                 db2 = DeferredMatmul(tr(a2.p), c) if b2.d is not None else None
             return [da1, db1, da2, db2, dbias]
@@ -526,6 +526,11 @@ class ADBackend:
 _NO_MATMUL_ACC = bool(os.environ.get("HB_AD_NO_MATMUL_ACC"))   # measurement switch: product + separate add
 _NO_MATMUL_LIST = bool(os.environ.get("HB_AD_NO_MATMUL_LIST"))  # measurement switch: accumulate weight cotangents per step
 _NO_BIAS_ACC = bool(os.environ.get("HB_AD_NO_BIAS_ACC"))        # measurement switch: bias cotangents by a separate add
+_NO_MATMUL_GROUP = bool(os.environ.get("HB_AD_NO_MATMUL_GROUP"))  # measurement switch: deferred products one by one
+
+
+def _use_group(base):
+    return hasattr(base, "smatmul2_group") and not _NO_MATMUL_GROUP and not _NO_MATMUL_ACC
 
 
 class DeferredMatmul:
@@ -594,10 +599,65 @@ def grad(base, f: Callable, inputs: Sequence, dt=None):
         # reduced axes (hb_matmul2_list) instead of one small accumulating product per step
         pending = {}
         use_list = hasattr(base, "smatmul2_list") and not _NO_MATMUL_LIST and not _NO_MATMUL_ACC
+        # deferred products whose parent is NOT an input stay unevaluated until one of them is needed (its parent is
+        # reached); then ALL that are waiting go out in groups of up to four products per launch (smatmul2_group: e.g.
+        # the three input cotangents of one time step of a two-layer recurrence), each accumulated into the cotangent
+        # it belongs to by the product's own epilogue
+        lazy = {}
+        use_group = _use_group(base)
+
+        def flush():
+            targets = list(lazy.items())
+            lazy.clear()
+            group, n_prod = [], 0
+
+            def launch():
+                results, products, post = [], [], []
+                for r, (pid, lst) in enumerate(group):
+                    old = cot.pop(pid, None)
+                    if isinstance(old, DeferredPad):
+                        old = old.force(base)
+                        owned.add(pid)
+                    if old is not None and pid in owned:
+                        results.append((old, None))
+                        post.append(None)
+                    else:                      # nothing yet, or an array other parents may hold too
+                        results.append((None, None))
+                        post.append(old)
+                    del old
+                    products += [(d.a, d.b, r) for d in lst]
+                if len(products) == 1:         # nothing to share a launch with: the plain (accumulating) product
+                    (acc, _), (a, b, _) = results[0], products[0]
+                    del results
+                    outs = [base.smatmul2(a, b) if acc is None else base.smatmul2_acc(acc, a, b)]
+                    del acc
+                else:
+                    outs = base.smatmul2_group(results, products)
+                    del results
+                for (pid, _), o, old in zip(group, outs, post):
+                    cot[pid] = o if old is None else base.binary("add", old, o)
+                    owned.add(pid)
+            for pid, lst in targets:
+                while lst:
+                    take = lst[:4 - n_prod] if len(group) < 4 else []
+                    if not take:
+                        launch()
+                        group, n_prod = [], 0
+                        continue
+                    group.append((pid, take))
+                    n_prod += len(take)
+                    lst = lst[len(take):]
+                    if n_prod == 4 and lst:        # the rest of this target in the next launch, on top of this one
+                        launch()
+                        group, n_prod = [], 0
+            if group:
+                launch()
         heap = [-out.d.id]
         while heap:
             nid = -heapq.heappop(heap)
             node = nodes.pop(nid)
+            if nid in lazy:
+                flush()
             c = cot.pop(nid)
             if isinstance(c, DeferredPad):
                 c = c.force(base)
@@ -652,6 +712,13 @@ def grad(base, f: Callable, inputs: Sequence, dt=None):
                     cs[i] = cs[j] = None
             for parent, pc in zip(node.parents, cs):
                 if parent is None or pc is None:
+                    continue
+                if use_group and isinstance(pc, DeferredMatmul):
+                    lazy.setdefault(parent.id, []).append(pc)
+                    if parent.id not in cot:
+                        cot[parent.id] = None          # placeholder: reached through the heap like any other
+                        nodes[parent.id] = parent
+                        heapq.heappush(heap, -parent.id)
                     continue
                 fresh = isinstance(pc, Fresh)
                 if fresh:

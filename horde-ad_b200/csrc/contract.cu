@@ -623,6 +623,123 @@ extern "C" int hb_matmul2_acc_pair(hb_array *acc1, const hb_array *a1, const hb_
   return st;
 }
 
+// A group of products of one [M, N] with named results, in one launch where the DMMA kernel takes them
+// (hb_gemm_dmma_group):  outs[r] = f_r ((acc[r] or 0) + sum over g with res_index[g] == r of a_g x b_g, in order of g),
+// f_r = tanh (. + bias[r] stretched over the columns) where bias[r] is given, else the identity.  This is what one
+// time step of an unrolled two-layer recurrence asks for, forward (two layers' wX x + wS s + b, tanh of independent
+// time steps: the wavefront of MnistRnnShaped2.hs:71-93) and backward (the transposition rules of tsmatmul2 of one
+// sweep step, DeltaEval.hs:317-332: three products, two cotangents).  Value semantics: acc[r] is updated in place
+// only when the caller holds its single reference.  acc / bias may be NULL (no accumulators / no epilogues).
+// Falls back to one product at a time (same sums, possibly another association between K slices).
+extern "C" int hb_matmul2_group(int n_res, hb_array *const *acc, const hb_array *const *bias, int n_prod,
+                                const hb_array *const *as, const hb_array *const *bs, const int *res_index,
+                                hb_array **outs) {
+  hb_prof_scope prof_("matmul2_group", n_prod > 0 && as ? as[0] : nullptr, n_prod > 0 && bs ? bs[0] : nullptr);
+  HB_CHECK_INIT_LAZY();
+  HB_REQUIRE(n_res >= 1 && n_res <= 16 && n_prod >= 1 && n_prod <= 32 && as && bs && res_index && outs,
+             "matmul2_group: %d products into %d results", n_prod, n_res);
+  const int64_t M = as[0] ? as[0]->shape[0] : 0, N = bs[0] ? bs[0]->shape[1] : 0;
+  int count[16] = {0};
+  for (int g = 0; g < n_prod; g++) {
+    HB_REQUIRE(as[g] && bs[g] && as[g]->rank == 2 && bs[g]->rank == 2 && as[g]->shape[1] == bs[g]->shape[0] &&
+                   as[g]->shape[0] == M && bs[g]->shape[1] == N && as[g]->dt == as[0]->dt && bs[g]->dt == as[0]->dt,
+               "matmul2_group: product %d does not match the first one", g);
+    HB_REQUIRE(res_index[g] >= 0 && res_index[g] < n_res, "matmul2_group: product %d names result %d of %d", g,
+               res_index[g], n_res);
+    count[res_index[g]]++;
+  }
+  for (int r = 0; r < n_res; r++) {
+    HB_REQUIRE(count[r] > 0, "matmul2_group: result %d has no product", r);
+    HB_REQUIRE(!acc || !acc[r] || (acc[r]->rank == 2 && acc[r]->shape[0] == M && acc[r]->shape[1] == N && acc[r]->dt == as[0]->dt),
+               "matmul2_group: accumulator %d does not match the products", r);
+    HB_REQUIRE(!bias || !bias[r] || (bias[r]->rank == 1 && bias[r]->shape[0] == M && bias[r]->dt == as[0]->dt),
+               "matmul2_group: bias %d must be [%lld] of the operands' type", r, (long long)M);
+    HB_REQUIRE(!(acc && acc[r] && bias && bias[r]), "matmul2_group: result %d has both an accumulator and an epilogue", r);
+  }
+  if (hb_lazy_on()) {
+    hb_lrec rec(HB_L_GENERIC, "matmul2_group");
+    for (int g = 0; g < n_prod; g++) rec.in(as[g]);
+    for (int g = 0; g < n_prod; g++) rec.in(bs[g]);
+    std::vector<int> idx(res_index, res_index + n_prod), has_acc(n_res, 0), has_bias(n_res, 0);
+    for (int r = 0; r < n_res; r++) if (acc && acc[r]) { rec.in(acc[r]); has_acc[r] = 1; }
+    for (int r = 0; r < n_res; r++) if (bias && bias[r]) { rec.in(bias[r]); has_bias[r] = 1; }
+    int64_t sh_[2] = {M, N};
+    for (int r = 0; r < n_res; r++) rec.out(&outs[r], as[0]->dt, 2, sh_);
+    return rec.commit([=](hb_lnode &, hb_array *const *in, hb_array **o) {
+      hb_array *ac[16];
+      const hb_array *bi[16];
+      int k = 2 * n_prod;
+      for (int r = 0; r < n_res; r++) ac[r] = has_acc[r] ? in[k++] : nullptr;
+      for (int r = 0; r < n_res; r++) bi[r] = has_bias[r] ? in[k++] : nullptr;
+      return hb_matmul2_group(n_res, ac, bi, n_prod, in, in + n_prod, idx.data(), o);
+    });
+  }
+  for (int r = 0; r < n_res; r++) outs[r] = nullptr;
+  if (as[0]->dt == HB_F64 && M * N > 0 && n_prod <= 4 && n_res <= 4) {
+    hb_array *tmp[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    auto drop = [&]() { for (hb_array *t : tmp) hb_release(t); };
+    hb_gemm_prod pr[4];
+    hb_gemm_res rs[4];
+    bool ok = true;
+    for (int g = 0; g < n_prod && ok; g++) {
+      Op2 A, B;
+      const bool bcast = (as[g]->strides[0] == 0 && as[g]->strides[1] == 0) || (bs[g]->strides[0] == 0 && bs[g]->strides[1] == 0);
+      ok = !bcast && as[g]->shape[1] > 0 && op2_pack(as[g], &A, &tmp[2 * g]) && op2_pack(bs[g], &B, &tmp[2 * g + 1]);
+      if (ok) pr[g] = hb_gemm_prod{A.p, A.s0, A.s1, B.p, B.s0, B.s1, as[g]->shape[1], res_index[g]};
+    }
+    hb_array *o[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (int r = 0; r < n_res && ok; r++) {
+      hb_array *a = acc ? acc[r] : nullptr;
+      if (a) {
+        bool unique = a->dt == HB_F64 && a->rc.load() == 1 && a->st && a->st->rc.load() == 1 && hb_contig(a);
+        for (int g = 0; g < n_prod && unique; g++) unique = a->st != as[g]->st && a->st != bs[g]->st;
+        for (int q = 0; q < r && unique; q++) unique = acc[q] != a;
+        if (!unique) { ok = false; break; }
+        hb_retain(a);
+        o[r] = a;
+      } else {
+        int64_t sh[2] = {M, N};
+        if (hb_new_array(HB_F64, 2, sh, &o[r]) != HB_OK) { ok = false; break; }
+      }
+      const hb_array *bi = bias ? bias[r] : nullptr;
+      if (bi && !hb_contig(bi)) { ok = false; break; }
+      rs[r] = hb_gemm_res{(double *)hb_data(o[r]), a ? 1 : 0, bi ? (const double *)hb_data(bi) : nullptr};
+    }
+    int done = 0, st = HB_OK;
+    if (ok) st = hb_gemm_dmma_group(n_prod, pr, n_res, rs, M, N, &done);
+    drop();   // stream-ordered: the packed copies are released behind the launch
+    if (st == HB_OK && done) {
+      for (int r = 0; r < n_res; r++) outs[r] = o[r];
+      return HB_OK;
+    }
+    for (int r = 0; r < n_res; r++) hb_release(o[r]);
+    if (st != HB_OK) return st;
+  }
+  // one product at a time
+  int st = HB_OK;
+  for (int r = 0; r < n_res && st == HB_OK; r++) {
+    hb_array *cur = acc ? acc[r] : nullptr;
+    if (cur) hb_retain(cur);
+    for (int g = 0; g < n_prod && st == HB_OK; g++) {
+      if (res_index[g] != r) continue;
+      hb_array *nx = nullptr;
+      st = cur ? hb_matmul2_acc(cur, as[g], bs[g], &nx) : hb_matmul2(as[g], bs[g], &nx);
+      hb_release(cur);
+      cur = nx;
+    }
+    if (st == HB_OK && bias && bias[r]) {
+      hb_array *y = nullptr;
+      st = hb_tanh_affine_fwd(cur, nullptr, bias[r], &y);
+      hb_release(cur);
+      cur = y;
+    }
+    outs[r] = st == HB_OK ? cur : nullptr;
+  }
+  if (st != HB_OK)
+    for (int r = 0; r < n_res; r++) { hb_release(outs[r]); outs[r] = nullptr; }
+  return st;
+}
+
 // acc + sum_t a_t x b_t for a list of products of one shape: the cotangent of a weight that is used at every step
 // of an unrolled loop (taddTarget over the transposition rule of tsmatmul2 at every step, DeltaEval.hs:317-332),
 // evaluated at the END of the sweep as ONE product over the concatenated reduced axes instead of one small product

@@ -33,3 +33,18 @@ __device__ __forceinline__ void hb_cg_offsets(const hb_cgroup &g, int64_t lin, i
 // contract_tf32.cu: Float contraction over the same strided views on the 5th-generation tensor cores
 // (tcgen05.mma kind::tf32, three-term split, TMEM accumulators).  *done = 0 when the shape is left to the caller.
 int hb_contract_tf32(const hb_contractp &P, const float *A, const float *B, float *C, int *done);
+
+// gemm_dmma.cu: a group of FP64 products of one [M, N] in one launch of the DMMA kernel (hb_gemm_dmma_group).
+struct hb_gemm_prod {
+  const double *A; int64_t a_sm, a_sk;   // A[m, k] strides
+  const double *B; int64_t b_sk, b_sn;   // B[k, n] strides
+  int64_t K;
+  int out;                               // index of the result the product is accumulated into
+};
+struct hb_gemm_res {
+  double *C;                  // contiguous [M, N]
+  int accum;                  // start the chain from the old contents of C
+  const double *epi_bias;     // C = tanh (C + bias[m]) after the last product (NULL: none)
+};
+int hb_gemm_dmma_group(int nprod, const hb_gemm_prod *pr, int nres, const hb_gemm_res *res, int64_t M, int64_t N,
+                       int *done);

@@ -17,6 +17,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "contract.cuh"
 
 namespace {
 
@@ -40,6 +41,8 @@ __device__ __forceinline__ void cp_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
+constexpr int GMAX = 4;   // products per launch (hb_gemm_dmma_group)
+
 struct GemmP {
   const double *A, *B;
   double *C;            // C or the split-K partial buffer [split][M][N]
@@ -51,21 +54,27 @@ struct GemmP {
   int a_vec, b_vec;     // 16-byte cp.async allowed
   int *flags;           // serial split-K: per output tile, the number of K slices already accumulated into C
   int accum;            // C += A x B (taddTarget fused into the product: cotangent accumulation of a weight)
-  // A second product of the same [M, N] in the same launch (hb_gemm_dmma_pair): K slices z >= zsplit work on it.
-  // chain = 1: both products are accumulated into ONE C in one serial chain (C = A x B + A2 x B2);
-  // chain = 0: two results, C and C2, each with its own serial chain (flags of the second at flags + tiles).
-  const double *A2, *B2;
-  double *C2;
-  int K2, kchunks2, a_vec2, b_vec2;
-  int64_t a_sm2, a_sk2, b_sk2, b_sn2;
-  int zsplit, chain;
+  // A GROUP of up to GMAX products of one [M, N] in one launch (hb_gemm_dmma_group; the pair of wX x + wS s, the
+  // three input cotangents of one time step of the unrolled recurrence, ...).  Product 0 is the fields above; product
+  // g >= 1 owns the K slices blockIdx.z in [zbeg[g], zbeg[g+1]).  Every product names the result it is accumulated
+  // into (gout[g]); the slices of all products of one result form ONE serial chain in product order: gzpos[g] is the
+  // chain position of product g's first slice, rzlen[r] the chain's length, rC[r] / raccum[r] / rbias[r] the result,
+  // whether the chain starts from the old contents, and the bias of the tanh epilogue of the chain's last slice
+  // (C = tanh (C + bias[m]): the body of rnnMnistLayerS without a separate elementwise pass).
+  int nprod;
+  const double *gA[GMAX], *gB[GMAX];
+  int64_t ga_sm[GMAX], ga_sk[GMAX], gb_sk[GMAX], gb_sn[GMAX];
+  int gK[GMAX], gkchunks[GMAX], ga_vec[GMAX], gb_vec[GMAX];
+  int zbeg[GMAX], gout[GMAX], gzpos[GMAX];
+  double *rC[GMAX];
+  int rzlen[GMAX], raccum[GMAX];
+  const double *rbias[GMAX];
   // A LIST of products of one shape accumulated into one result (hb_gemm_dmma_list: the weight cotangents
   // dW = sum_t d_t x_t^T of an unrolled loop): the K axis is the concatenation of the entries' K axes
   // (K % BK8 == 0, so a chunk never straddles two entries); slices go to partial buffers + the fixed-order reduce.
   int nlist;
   const double *Al[32], *Bl[32];
-  // epilogue of the LAST slice of a serial chain (or of an unsplit product): C = tanh (C + bias[m]) -- the body of
-  // rnnMnistLayerS, tanh (wX x + wS s + b), without a separate elementwise pass
+  // epilogue of an unsplit single product: C = tanh (C + bias[m])
   const double *epi_bias;
 };
 
@@ -257,13 +266,25 @@ __global__ void __launch_bounds__(256, 2) gemm8_dmma_kernel(const __grid_constan
   const int fr = lane >> 2, fk = lane & 3;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   // which product this K slice belongs to, and its slice index there
-  const bool second = p.zsplit > 0 && (int)blockIdx.z >= p.zsplit;
-  const double *__restrict__ gA = second ? p.A2 : p.A, *__restrict__ gB = second ? p.B2 : p.B;
-  const int64_t a_sm = second ? p.a_sm2 : p.a_sm, a_sk = second ? p.a_sk2 : p.a_sk;
-  const int64_t b_sk = second ? p.b_sk2 : p.b_sk, b_sn = second ? p.b_sn2 : p.b_sn;
-  const int a_vec = second ? p.a_vec2 : p.a_vec, b_vec = second ? p.b_vec2 : p.b_vec;
-  const int Kp = p.nlist ? p.nlist * p.K : (second ? p.K2 : p.K), kch = second ? p.kchunks2 : p.kchunks;
-  const int zl = second ? (int)blockIdx.z - p.zsplit : (int)blockIdx.z;
+  const double *__restrict__ gA = p.A, *__restrict__ gB = p.B;
+  int64_t a_sm = p.a_sm, a_sk = p.a_sk, b_sk = p.b_sk, b_sn = p.b_sn;
+  int a_vec = p.a_vec, b_vec = p.b_vec, Kp = p.nlist ? p.nlist * p.K : p.K, kch = p.kchunks;
+  int zl = (int)blockIdx.z, res = 0, zpos0 = 0;
+  if (p.nprod > 1) {
+    res = p.gout[0];
+    zpos0 = p.gzpos[0];
+#pragma unroll
+    for (int g = 1; g < GMAX; g++)
+      if (g < p.nprod && (int)blockIdx.z >= p.zbeg[g]) {
+        gA = p.gA[g]; gB = p.gB[g];
+        a_sm = p.ga_sm[g]; a_sk = p.ga_sk[g]; b_sk = p.gb_sk[g]; b_sn = p.gb_sn[g];
+        a_vec = p.ga_vec[g]; b_vec = p.gb_vec[g];
+        Kp = p.gK[g]; kch = p.gkchunks[g];
+        zl = (int)blockIdx.z - p.zbeg[g];
+        res = p.gout[g];
+        zpos0 = p.gzpos[g];
+      }
+  }
   const int kbeg = zl * kch * BK8;
   int kend = kbeg + kch * BK8;
   if (kend > Kp) kend = Kp;
@@ -327,13 +348,14 @@ __global__ void __launch_bounds__(256, 2) gemm8_dmma_kernel(const __grid_constan
   double *C = serial ? p.C : p.C + (int64_t)blockIdx.z * p.M * p.c_sm;
   int *flag = serial ? p.flags + blockIdx.y * gridDim.x + blockIdx.x : nullptr;
   int z = blockIdx.z, zlen = gridDim.z;   // position in / length of this tile's serial chain
-  if (p.zsplit > 0 && !p.chain) {          // two results: each product has its own chain
-    z = zl;
-    zlen = second ? (int)gridDim.z - p.zsplit : p.zsplit;
-    if (second) {
-      C = p.C2;
-      flag += gridDim.x * gridDim.y;
-    }
+  int accum = p.accum;
+  const double *bias = p.epi_bias;
+  if (p.nprod > 1) {                       // a group: the chain of the result this product belongs to
+    z = zpos0 + zl;
+#pragma unroll
+    for (int r = 0; r < GMAX; r++)
+      if (r == res) { C = p.rC[r]; zlen = p.rzlen[r]; accum = p.raccum[r]; bias = p.rbias[r]; }
+    flag += res * (int)(gridDim.x * gridDim.y);
   }
   if (serial && z > 0) {
     if (tid == 0) {
@@ -342,9 +364,9 @@ __global__ void __launch_bounds__(256, 2) gemm8_dmma_kernel(const __grid_constan
     }
     __syncthreads();
   }
-  const bool addc = serial ? (z > 0 || p.accum) : (p.accum && gridDim.z == 1);
+  const bool addc = serial ? (z > 0 || accum) : (accum && gridDim.z == 1);
   const bool cvec = (p.c_sm & 1) == 0 && ((uintptr_t)C & 15) == 0;
-  const bool epi = p.epi_bias != nullptr && (serial ? z + 1 == zlen : gridDim.z == 1);
+  const bool epi = bias != nullptr && (serial ? z + 1 == zlen : gridDim.z == 1);
 #pragma unroll
   for (int i = 0; i < 4; i++)
 #pragma unroll
@@ -352,7 +374,7 @@ __global__ void __launch_bounds__(256, 2) gemm8_dmma_kernel(const __grid_constan
       int m = m0 + wm + i * 8 + fr, n = n0 + wn + j * 8 + fk * 2;
       if (m < p.M) {
         double *c = C + (int64_t)m * p.c_sm + n;
-        const double eb = epi ? p.epi_bias[m] : 0.0;
+        const double eb = epi ? bias[m] : 0.0;
         if (n + 1 < p.N && cvec) {
           double2 o = make_double2(acc[i][j][0], acc[i][j][1]);
           if (addc) {
@@ -607,64 +629,89 @@ int hb_gemm_dmma_list(int n, const double *const *A, int64_t a_sm, int64_t a_sk,
   return HB_OK;
 }
 
-// Two products of the same [M, N] in ONE launch of the eight-warp kernel (the recurrent layer of
-// MnistRnnShaped2 runs ~one 64 x 64 tile per SM per product: pairing fills the second CTA slot of every SM
-// and halves launches and epilogues):
-//   chain = 1:  C  = (accum ? C : 0) + A1 x B1 + A2 x B2        (C2 ignored)   -- wX x + wS s
-//   chain = 0:  C  = (accum ? C  : 0) + A1 x B1,  C2 = (accum ? C2 : 0) + A2 x B2 -- the two input cotangents
-//               that share dY, or the two weight cotangents that share it on the other side
-// K may differ between the products; both must have the same operand orientations.  Slices of one tile are
-// combined in slice order through the per-tile flags (deterministic).  *done = 0: shapes not taken.
-int hb_gemm_dmma_pair(const double *A1, int64_t a1_sm, int64_t a1_sk, const double *B1, int64_t b1_sk, int64_t b1_sn,
-                      int64_t K1, const double *A2, int64_t a2_sm, int64_t a2_sk, const double *B2, int64_t b2_sk,
-                      int64_t b2_sn, int64_t K2, double *C1, double *C2, int64_t M, int64_t N, int chain, int accum,
-                      int *done, const double *epi_bias) {
+// A GROUP of up to GMAX products of the same [M, N] in ONE launch of the eight-warp kernel, each accumulated into the
+// result it names:  C_r = (accum_r ? C_r : 0) + sum over the products with out == r of A_g x B_g, in product order,
+// optionally followed by C_r = tanh (C_r + bias_r[m]).  The recurrent layers of MnistRnnShaped2 run ~one 64 x 64 tile
+// per SM per product, so one product alone leaves SMs idle and pays a launch + pipeline fill per 0.5 GFLOP:
+//   wX x + wS s (+ b, tanh)                      two products, one result                (forward layer)
+//   wX^T d, wS^T d                               two products, two results               (input cotangents)
+//   dW1 += d x^T, dW2 += d s^T                   two products, two accumulated results   (weight cotangents)
+//   wS1^T d1' + wX2^T d2 -> dh1, wS2^T d2 -> dh2 three products, two results             (one backward time step)
+// K may differ between the products; all must have the same operand orientations (one template instantiation).
+// Slices of one result's tile are combined in chain order through the per-tile flags (deterministic).
+// *done = 0: shapes not taken.
+int hb_gemm_dmma_group(int nprod, const hb_gemm_prod *pr, int nres, const hb_gemm_res *res, int64_t M, int64_t N,
+                       int *done) {
   *done = 0;
-  if (epi_bias && (!chain || accum)) return HB_OK;   // the epilogue belongs to the one chain of `A1 B1 + A2 B2`
-  if (M <= 0 || N <= 0 || K1 <= 0 || K2 <= 0) return HB_OK;
-  if (M >= (1ll << 31) || N >= (1ll << 31) || K1 >= (1ll << 31) || K2 >= (1ll << 31)) return HB_OK;
-  const bool a_kfast = a1_sk == 1, b_kfast = b1_sk == 1;
-  // one template instantiation serves both products: same operand orientations
-  if (a_kfast ? a2_sk != 1 : (a1_sm != 1 || a2_sm != 1)) return HB_OK;
-  if (b_kfast ? b2_sk != 1 : (b1_sn != 1 || b2_sn != 1)) return HB_OK;
+  if (nprod < 1 || nprod > GMAX || nres < 1 || nres > GMAX || M <= 0 || N <= 0) return HB_OK;
+  if (M >= (1ll << 31) || N >= (1ll << 31)) return HB_OK;
+  const bool a_kfast = pr[0].a_sk == 1, b_kfast = pr[0].b_sk == 1;
+  for (int g = 0; g < nprod; g++) {
+    if (pr[g].K <= 0 || pr[g].K >= (1ll << 31) || pr[g].out < 0 || pr[g].out >= nres) return HB_OK;
+    if (a_kfast ? pr[g].a_sk != 1 : pr[g].a_sm != 1) return HB_OK;
+    if (b_kfast ? pr[g].b_sk != 1 : pr[g].b_sn != 1) return HB_OK;
+  }
+  for (int r = 0; r < nres; r++)
+    if (res[r].epi_bias && res[r].accum) return HB_OK;   // the epilogue belongs to a chain that starts from zero
   GemmP p;
   memset(&p, 0, sizeof p);
-  p.A = A1; p.B = B1; p.C = C1;
-  p.A2 = A2; p.B2 = B2; p.C2 = chain ? C1 : C2;
-  p.M = (int)M; p.N = (int)N; p.K = (int)K1; p.K2 = (int)K2;
-  p.a_sm = a1_sm; p.a_sk = a1_sk; p.b_sk = b1_sk; p.b_sn = b1_sn;
-  p.a_sm2 = a2_sm; p.a_sk2 = a2_sk; p.b_sk2 = b2_sk; p.b_sn2 = b2_sn;
+  p.M = (int)M; p.N = (int)N;
   p.c_sm = N;
-  p.accum = accum;
-  p.chain = chain;
-  p.epi_bias = epi_bias;
-  p.a_vec = ((uintptr_t)A1 & 15) == 0 && ((a_kfast ? a1_sm : a1_sk) % 2 == 0);
-  p.b_vec = ((uintptr_t)B1 & 15) == 0 && ((b_kfast ? b1_sn : b1_sk) % 2 == 0);
-  p.a_vec2 = ((uintptr_t)A2 & 15) == 0 && ((a_kfast ? a2_sm : a2_sk) % 2 == 0);
-  p.b_vec2 = ((uintptr_t)B2 & 15) == 0 && ((b_kfast ? b2_sn : b2_sk) % 2 == 0);
   const int gm = (int)((M + BM - 1) / BM), gn = (int)((N + BN - 1) / BN);
   if (gn > 65535) return HB_OK;
   const int64_t tiles = (int64_t)gm * gn;
-  if (2 * tiles > kFlagTiles) return HB_OK;
-  // K slices: about two CTAs per SM over BOTH products, every slice about the same depth (a K = 28 product next
+  if (nres * tiles > kFlagTiles) return HB_OK;
+  // K slices: about two CTAs per SM over ALL products, every slice about the same depth (a K = 28 product next
   // to a K = 512 one gets one slice and the deep one two, so the real work is still 256 CTAs of K = 256), at
   // least 4 chunks (128 k) per slice, at most 3 slices per product
-  const int chunks1 = (int)((K1 + BK8 - 1) / BK8), chunks2 = (int)((K2 + BK8 - 1) / BK8);
+  int chunks[GMAX], total = 0;
+  for (int g = 0; g < nprod; g++) total += chunks[g] = (int)((pr[g].K + BK8 - 1) / BK8);
   int budget = (int)(2 * (int64_t)g_hb.sm_count / tiles);
   if (budget < 2) budget = 2;
-  int per = (chunks1 + chunks2 + budget - 1) / budget;
+  int per = (total + budget - 1) / budget;
   if (per < 4) per = 4;
-  auto slices = [&](int chunks, int *kchunks) {
-    int sp = (chunks + per - 1) / per;
-    if (sp > 3) sp = 3;
+  static const int per_forced = getenv("HB_GROUP_PER") ? atoi(getenv("HB_GROUP_PER")) : 0;
+  if (per_forced > 0 && nprod > 2) per = per_forced;
+  int z = 0, zlen[GMAX] = {0, 0, 0, 0};
+  p.nprod = nprod;
+  for (int g = 0; g < nprod; g++) {
+    int sp = (chunks[g] + per - 1) / per;
+    if (sp > 3 && per_forced <= 0) sp = 3;
     if (sp < 1) sp = 1;
-    *kchunks = (chunks + sp - 1) / sp;
-    return (chunks + *kchunks - 1) / *kchunks;
-  };
-  const int s1 = slices(chunks1, &p.kchunks), s2 = slices(chunks2, &p.kchunks2);
-  p.zsplit = s1;
+    const int kch = (chunks[g] + sp - 1) / sp;
+    sp = (chunks[g] + kch - 1) / kch;
+    p.gA[g] = pr[g].A; p.gB[g] = pr[g].B;
+    p.ga_sm[g] = pr[g].a_sm; p.ga_sk[g] = pr[g].a_sk; p.gb_sk[g] = pr[g].b_sk; p.gb_sn[g] = pr[g].b_sn;
+    p.gK[g] = (int)pr[g].K;
+    p.gkchunks[g] = kch;
+    p.ga_vec[g] = ((uintptr_t)pr[g].A & 15) == 0 && ((a_kfast ? pr[g].a_sm : pr[g].a_sk) % 2 == 0);
+    p.gb_vec[g] = ((uintptr_t)pr[g].B & 15) == 0 && ((b_kfast ? pr[g].b_sn : pr[g].b_sk) % 2 == 0);
+    p.zbeg[g] = z;
+    p.gout[g] = pr[g].out;
+    p.gzpos[g] = zlen[pr[g].out];
+    zlen[pr[g].out] += sp;
+    z += sp;
+  }
+  for (int r = 0; r < nres; r++) {
+    if (zlen[r] == 0) return HB_OK;                    // a result nobody writes
+    p.rC[r] = res[r].C;
+    p.rzlen[r] = zlen[r];
+    p.raccum[r] = res[r].accum;
+    p.rbias[r] = res[r].epi_bias;
+  }
+  // product 0 is also the kernel's default operand set
+  p.A = p.gA[0]; p.B = p.gB[0]; p.C = p.rC[p.gout[0]];
+  p.K = p.gK[0]; p.kchunks = p.gkchunks[0];
+  p.a_sm = p.ga_sm[0]; p.a_sk = p.ga_sk[0]; p.b_sk = p.gb_sk[0]; p.b_sn = p.gb_sn[0];
+  p.a_vec = p.ga_vec[0]; p.b_vec = p.gb_vec[0];
+  if (nprod == 1) {        // the kernel's single-product path: one chain over gridDim.z
+    p.nprod = 0;
+    p.accum = res[0].accum;
+    p.epi_bias = res[0].epi_bias;
+  }
+  if (z > 65535) return HB_OK;
   HB_TRY(gemm_flags(&p.flags));
-  dim3 grid((unsigned)gm, (unsigned)gn, (unsigned)(s1 + s2));
+  dim3 grid((unsigned)gm, (unsigned)gn, (unsigned)z);
   size_t smem = (size_t)STAGES8 * 2 * TILE8 * 8;
 #define GEMM8_LAUNCH(AK, BKF)                                                                                  \
   do {                                                                                                         \
@@ -682,3 +729,16 @@ int hb_gemm_dmma_pair(const double *A1, int64_t a1_sm, int64_t a1_sk, const doub
   return HB_OK;
 }
 
+// Two products of one [M, N] (see hb_gemm_dmma_group):
+//   chain = 1:  C1 = (accum ? C1 : 0) + A1 x B1 + A2 x B2   (C2 ignored), optionally tanh (. + epi_bias[m])
+//   chain = 0:  C1 = (accum ? C1 : 0) + A1 x B1,  C2 = (accum ? C2 : 0) + A2 x B2
+int hb_gemm_dmma_pair(const double *A1, int64_t a1_sm, int64_t a1_sk, const double *B1, int64_t b1_sk, int64_t b1_sn,
+                      int64_t K1, const double *A2, int64_t a2_sm, int64_t a2_sk, const double *B2, int64_t b2_sk,
+                      int64_t b2_sn, int64_t K2, double *C1, double *C2, int64_t M, int64_t N, int chain, int accum,
+                      int *done, const double *epi_bias) {
+  *done = 0;
+  if (epi_bias && (!chain || accum)) return HB_OK;   // the epilogue belongs to the one chain of `A1 B1 + A2 B2`
+  hb_gemm_prod pr[2] = {{A1, a1_sm, a1_sk, B1, b1_sk, b1_sn, K1, 0}, {A2, a2_sm, a2_sk, B2, b2_sk, b2_sn, K2, chain ? 0 : 1}};
+  hb_gemm_res res[2] = {{C1, accum, epi_bias}, {C2, accum, nullptr}};
+  return hb_gemm_dmma_group(2, pr, chain ? 1 : 2, res, M, N, done);
+}

@@ -408,6 +408,27 @@ class DeviceBackend:
             return acc
         return _wrap(p)
 
+    def smatmul2_group(self, results, products):
+        """results: [(acc or None, bias or None)]; products: [(a, b, result index)] -> [outs]: every result is its
+        accumulator plus its products (in order), then tanh (. + bias) if it has one; one launch where the DMMA
+        kernel takes the group (hb_matmul2_group).  Accumulators are updated in place when uniquely referenced."""
+        nr, npr = len(results), len(products)
+        accs = (C.c_void_p * nr)(*[a.h if a is not None else None for a, _ in results])
+        bias = (C.c_void_p * nr)(*[b.h if b is not None else None for _, b in results])
+        arr_a = (C.c_void_p * npr)(*[a.h for a, _, _ in products])
+        arr_b = (C.c_void_p * npr)(*[b.h for _, b, _ in products])
+        idx = (C.c_int * npr)(*[int(r) for _, _, r in products])
+        outs = (C.c_void_p * nr)()
+        call("hb_matmul2_group", nr, accs, bias, npr, arr_a, arr_b, idx, outs)
+        res = []
+        for (acc, _), h in zip(results, outs):
+            if acc is not None and h == acc.h.value:   # same handle, retained once more
+                ffi._lib.hb_release(C.c_void_p(h))
+                res.append(acc)
+            else:
+                res.append(_wrap(C.c_void_p(h)))
+        return res
+
     def smatvecmul(self, m, v):
         p = _out()
         call("hb_matvecmul", m.h, v.h, C.byref(p))

@@ -92,6 +92,7 @@ PROTOTYPES = {
     "hb_matmul2": [P, P, PP], "hb_matvecmul": [P, P, PP], "hb_matmul2_acc": [P, P, P, PP],
     "hb_matmul2_sum": [P, P, P, P, PP], "hb_matmul2_pair": [P, P, P, P, PP, PP],
     "hb_matmul2_acc_pair": [P, P, P, P, P, P, PP, PP], "hb_matmul2_list": [C.c_int, C.POINTER(P), C.POINTER(P), P, PP],
+    "hb_matmul2_group": [C.c_int, C.POINTER(P), C.POINTER(P), C.c_int, C.POINTER(P), C.POINTER(P), C.POINTER(C.c_int), C.POINTER(P)],
     "hb_matmul2_sum_tanh": [P, P, P, P, P, PP],
     "hb_argmax_last": [P, PP], "hb_argmin_last": [P, PP],
     "hb_conv2d_preserving": [P, P, PP],

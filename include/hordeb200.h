@@ -399,6 +399,23 @@ int hb_matmul2_acc_pair(hb_array *acc1, const hb_array *a1,
 int hb_matmul2_sum_tanh(const hb_array *a1, const hb_array *b1,
                         const hb_array *a2, const hb_array *b2,
                         const hb_array *bias, hb_array **out);
+/* A group of n_prod products of one [M, N] with named results:
+ *   outs[r] = f_r ((acc[r] or 0) + sum over g with res_index[g] == r of a[g] x b[g])
+ * (products in order of g), f_r = tanh (. + bias[r] stretched over the columns)
+ * where bias[r] is given, else the identity; acc and bias may be NULL or hold
+ * NULL entries; a result has an accumulator or an epilogue, not both.  One
+ * launch of the DMMA kernel when f64, n_prod <= 4, n_res <= 4 and the operands
+ * share an orientation: what one step of an unrolled two-layer recurrence
+ * needs, forward (the wavefront of rnnMnistTwoS, MnistRnnShaped2.hs:71-93: the
+ * two layers' tanh (wX x + wS s + b) of independent time steps) and backward
+ * (the transposition rules of tsmatmul2 of one sweep step, DeltaEval.hs:317-332:
+ * three products into two cotangents).  acc[r] is updated in place only when
+ * the caller holds its single reference.  Otherwise one product at a time.
+ * Deterministic (K slices of a result are combined in a fixed order). */
+int hb_matmul2_group(int n_res, hb_array *const *acc, const hb_array *const *bias,
+                     int n_prod, const hb_array *const *a,
+                     const hb_array *const *b, const int *res_index,
+                     hb_array **outs);
 /* acc + sum_t a[t] x b[t] for n products of one shape (acc may be NULL): the
  * cotangent of a weight used at every step of an unrolled loop (taddTarget
  * over the transposition rule of tsmatmul2, DeltaEval.hs:317-332), evaluated

@@ -280,6 +280,19 @@ class ConcreteBackend:
             out = prod if out is None else out + prod
         return out
 
+    def smatmul2_group(self, results, products):
+        """[acc_r + sum of the products naming r (in order), then tanh (. + bias_r) if given]: the transposition /
+        forward rules of tsmatmul2 applied one by one (OpsConcrete.hs:234-242, DeltaEval.hs:317-332)."""
+        outs = []
+        for r, (acc, bias) in enumerate(results):
+            out = acc
+            for a, b, ri in products:
+                if ri == r:
+                    prod = self.smatmul2(a, b)
+                    out = prod if out is None else out + prod
+            outs.append(tanh_affine_fwd(out, None, bias) if bias is not None else out)
+        return outs
+
     # tsargMax / tsargMin reduce the LAST axis, Int result of shape Init sh
     # (OpsConcrete.hs:1712-1746); first extremum (unpinned in the reference)
     def sargMax(self, t):

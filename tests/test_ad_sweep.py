@@ -15,9 +15,15 @@ class Counting(ConcreteBackend):
     def __init__(self):
         super().__init__()
         self.calls = {}
+        self.groups = []
 
     def _count(self, name):
         self.calls[name] = self.calls.get(name, 0) + 1
+
+    def smatmul2_group(self, results, products):
+        """Counted by its shape (results, products, accumulated results); the products inside are not counted."""
+        self.groups.append((len(results), len(products), sum(a is not None for a, _ in results)))
+        return ConcreteBackend.smatmul2_group(ConcreteBackend(), results, products)
 
 
 for _name in ("smatmul2", "smatmul2_acc", "smatmul2_acc_pair", "smatmul2_pair", "smatmul2_sum", "smatmul2_list",
@@ -91,10 +97,12 @@ def test_weight_used_at_every_step_accumulates_in_the_product():
     # W is an INPUT used three times: its three cotangent products are kept as a list and evaluated once, when the
     # sweep reaches the input (one product over the concatenated reduced axes on the device)
     assert B.calls.get("smatmul2_list") == 1 and B.calls.get("smatmul2_acc", 0) == 0
-    # an INTERIOR value used three times (W = 2 * V): the first cotangent is a product, the others accumulate into it
+    # an INTERIOR value used three times (W = 2 * V): its cotangent products wait until something needs a deferred
+    # product, then go out together with the state's (one launch for two results), accumulated from the second on
     B2 = Counting()
     _, (gv, _) = ad.grad(B2, lambda T, V, X: f(T, T.binary("mul", V, T.srepl([5, 5], 2.0)), X), [w / 2, x])
-    assert B2.calls.get("smatmul2_acc") == 2 and B2.calls.get("smatmul2_list", 0) == 0
+    assert B2.groups == [(2, 2, 0), (2, 2, 1)] and B2.calls.get("smatmul2_acc") == 1
+    assert B2.calls.get("smatmul2_list", 0) == 0
     np.testing.assert_allclose(gv, 2 * gw, rtol=1e-13)
 
     def val(W):
@@ -119,9 +127,10 @@ def test_paired_layer_node_pairs_its_cotangents():
     B = Counting()
     v, grads = ad.grad(B, f, [wx, ws, x0, s0])
     assert B.calls.get("smatmul2_sum") == 3
-    assert B.calls.get("smatmul2_list") == 2                 # dWX and dWS: one list product each at the end
+    # dWX, dWS and dS (s0 is x of the second step): one list product each at the end; dX: a single product
+    assert B.calls.get("smatmul2_list") == 3
     assert B.calls.get("smatmul2_acc_pair", 0) == 0
-    assert B.calls.get("smatmul2_pair", 0) >= 2              # (dX, dS) of a step share one launch
+    assert B.groups[0] == (2, 2, 0)                          # (dx, ds) of the last step share one launch
 
     def val(WX, WS, X, S):
         x, s = X, S
@@ -132,4 +141,38 @@ def test_paired_layer_node_pairs_its_cotangents():
     args = [wx, ws, x0, s0]
     for k in range(4):
         ref = fd_grad(lambda a: val(*[a if j == k else args[j] for j in range(4)]), args[k])
+        np.testing.assert_allclose(grads[k], ref, rtol=1e-7, atol=1e-9)
+
+
+def test_two_layer_recurrence_launches_three_products_per_step():
+    """rnnMnistTwoS's shape (MnistRnnShaped2.hs:71-93): at every step of the sweep the cotangent of the first layer's
+    state gets wS1^T d1' (recurrence) + wX2^T d2 (second layer), the second layer's state gets wS2^T d2 -- three
+    deferred products, two results, ONE group launch."""
+    rng = np.random.default_rng(5)
+    n, b, steps = 4, 3, 4
+    ws = [rng.uniform(-.3, .3, (n, n)) for _ in range(4)]
+    bs = [rng.uniform(-.1, .1, (n,)) for _ in range(2)]
+    xs = rng.uniform(-.5, .5, (steps, n, b))
+
+    def f(T, wx1, ws1, wx2, ws2, b1, b2):
+        h1 = h2 = T.srepl([n, b], 0.0)
+        for t in range(steps):
+            h1 = T.smatmul2_sum_tanh(wx1, T.sconcrete(xs[t]), ws1, h1, b1)
+            h2 = T.smatmul2_sum_tanh(wx2, h1, ws2, h2, b2)
+        return T.ssum0(h2)
+    B = Counting()
+    _, grads = ad.grad(B, f, ws + bs)
+    # last time step: no recurrence cotangent yet; first: the initial states are constants
+    assert B.groups == [(2, 2, 0)] + [(2, 3, 0)] * (steps - 2) + [(1, 2, 0)], B.groups
+    assert B.calls.get("smatmul2_list") == 4
+
+    def val(wx1, ws1, wx2, ws2, b1, b2):
+        h1 = h2 = np.zeros((n, b))
+        for t in range(steps):
+            h1 = np.tanh(wx1 @ xs[t] + ws1 @ h1 + b1[:, None])
+            h2 = np.tanh(wx2 @ h1 + ws2 @ h2 + b2[:, None])
+        return h2.sum()
+    args = ws + bs
+    for k in range(6):
+        ref = fd_grad(lambda a: val(*[a if j == k else args[j] for j in range(6)]), args[k])
         np.testing.assert_allclose(grads[k], ref, rtol=1e-7, atol=1e-9)

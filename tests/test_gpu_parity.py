@@ -1063,6 +1063,63 @@ def test_tanh_affine_bwd_acc_is_the_adjoint_plus_add(dev, oracle, dtype, shape):
     exact(dev.to_numpy(out2), want)
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("m,n,ks", [(512, 1024, (512, 512, 512)), (130, 70, (33, 64, 5)), (64, 64, (28, 512, 512, 512)),
+                                    (8, 3, (2, 1))])
+def test_matmul2_group_against_the_oracle(dev, oracle, dtype, m, n, ks):
+    """hb_matmul2_group: products of one [M, N] into named results in one launch -- accumulators (in place when
+    uniquely referenced), tanh epilogues, operands in either orientation -- against the rules applied one by one."""
+    rng = np.random.default_rng(31)
+    a = [rnd(rng, (m, k), dtype) for k in ks]
+    b = [rnd(rng, (k, n), dtype) for k in ks]
+    acc, bias = rnd(rng, (m, n), dtype), rnd(rng, (m,), dtype)
+    f64 = lambda x: x.astype(np.float64)
+    da, db = [dev.sconcrete(x) for x in a], [dev.sconcrete(x) for x in b]
+    # weights as transposed views (the backward pass hands over wS^T), cotangents as they are
+    dat = [dev.stranspose([1, 0], dev.sconcrete(np.ascontiguousarray(x.T))) for x in a]
+    scale = 8 * sum(ks)
+    for ops in (da, dat):
+        # (1) the backward step: the first two products into result 0, the rest into result 1; result 1 accumulated
+        idx = [0, 0] + [1] * (len(ks) - 2)
+        prods = [(ops[g], db[g], idx[g]) for g in range(len(ks))]
+        oprods = [(f64(a[g]), f64(b[g]), idx[g]) for g in range(len(ks))]
+        nres = 2 if len(ks) > 2 else 1
+        held = dev.sconcrete(acc)
+        res = [(None, None), (held, None)][:nres]
+        ores = [(None, None), (f64(acc), None)][:nres]
+        outs = dev.smatmul2_group(res, prods)
+        del res
+        refs = oracle.smatmul2_group(ores, oprods)
+        for o, r in zip(outs, refs):
+            close(dev.to_numpy(o), r.astype(dtype), dtype, scale=scale)
+        if nres == 2 and dtype == np.float64:
+            assert outs[1] is held                      # updated in place
+        # (2) the forward wavefront: two layers' tanh (wX x + wS s + b), every result with its epilogue
+        if len(ks) >= 3:
+            idx = [0, 0] + [1] * (len(ks) - 2)
+            b2 = dev.sconcrete(bias[::-1].copy())
+            outs = dev.smatmul2_group([(None, dev.sconcrete(bias)), (None, b2)], [(ops[g], db[g], idx[g]) for g in range(len(ks))])
+            refs = oracle.smatmul2_group([(None, f64(bias)), (None, f64(bias[::-1]))], oprods)
+            for o, r in zip(outs, refs):
+                close(dev.to_numpy(o), r.astype(dtype), dtype, scale=scale)
+            # the first result is exactly hb_matmul2_sum_tanh of its two products (same kernel, same chain)
+            if dtype == np.float64 and ks[0] >= 32:
+                one = dev.smatmul2_sum_tanh(ops[0], db[0], ops[1], db[1], dev.sconcrete(bias))
+                close(dev.to_numpy(outs[0]), dev.to_numpy(one), dtype, scale=scale)
+    # an accumulator somebody else holds is left alone
+    held = dev.sconcrete(acc)
+    view = dev.stranspose([1, 0], held)
+    out, = dev.smatmul2_group([(held, None)], [(da[0], db[0], 0), (da[1], db[1], 0)])
+    assert out is not held
+    exact(dev.to_numpy(view), acc.T)
+    close(dev.to_numpy(out), (f64(acc) + f64(a[0]) @ f64(b[0]) + f64(a[1]) @ f64(b[1])).astype(dtype), dtype, scale=scale)
+    # deterministic: the same launch twice (K slices of a tile are combined in chain order)
+    one, = dev.smatmul2_group([(dev.sconcrete(acc), None)], [(da[0], db[0], 0), (da[1], db[1], 0)])
+    two, = dev.smatmul2_group([(dev.sconcrete(acc), None)], [(da[0], db[0], 0), (da[1], db[1], 0)])
+    exact(dev.to_numpy(one), dev.to_numpy(two))
+    close(dev.to_numpy(one), dev.to_numpy(out), dtype, scale=scale)
+
+
 @pytest.mark.parametrize("name,mk,expected", P.VSTACK_GOLDEN, ids=[v[0] for v in P.VSTACK_GOLDEN])
 def test_vstack_known_answers_on_the_device(dev, name, mk, expected):
     """vstackABC / vstackBuild (TestAdaptorSimplified.hs:785-835, 949) through the C ABI, and the
