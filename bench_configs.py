@@ -34,8 +34,8 @@ from horde_ad_b200 import ad, ffi, mnist_fcnn, mnist_rnn  # noqa: E402
 from horde_ad_b200.device import DeviceBackend  # noqa: E402
 
 
-# fusion level of the RNN layer body: "pair" (smatmul2_sum + tanh_affine nodes), "1" (tanh_affine only), "0" (literal)
-RNN_FUSION = {"pair": "pair", "1": True, "0": False}[os.environ.get("HB_RNN_FUSION", "pair")]
+# fusion level of the RNN layer body: "wave" (pair nodes in wavefront order: two layer bodies per launch), "pair" (smatmul2_sum + tanh_affine nodes), "1" (tanh_affine only), "0" (literal)
+RNN_FUSION = {"wave": "wave", "pair": "pair", "1": True, "0": False}[os.environ.get("HB_RNN_FUSION", "wave")]
 
 
 def peaks():

@@ -408,8 +408,23 @@ class ADBackend:
         tanh ride in the epilogue of the paired product); the pullback is the composition of theirs."""
         B = self.B
         a1, b1, a2, b2, bias = self.lift(a1), self.lift(b1), self.lift(a2), self.lift(b2), self.lift(bias)
+        return self._sum_tanh_node(B.smatmul2_sum_tanh(a1.p, b1.p, a2.p, b2.p, bias.p), a1, b1, a2, b2, bias)
+
+    def smatmul2_sum_tanh_2(self, first, second):
+        """(smatmul2_sum_tanh first, smatmul2_sum_tanh second) for two layer bodies that do not depend on each other
+        (layer 1 at time t and layer 2 at time t - 1 of rnnMnistTwoS: the wavefront schedule of the unrolled loop):
+        ONE launch forward (smatmul2_group: four products, two results, two tanh epilogues); two ordinary nodes, each
+        with the pullback of smatmul2_sum_tanh."""
+        B = self.B
+        f = [self.lift(t) for t in first]
+        g = [self.lift(t) for t in second]
+        y1, y2 = B.smatmul2_group([(None, f[4].p), (None, g[4].p)],
+                                  [(f[0].p, f[1].p, 0), (f[2].p, f[3].p, 0), (g[0].p, g[1].p, 1), (g[2].p, g[3].p, 1)])
+        return self._sum_tanh_node(y1, *f), self._sum_tanh_node(y2, *g)
+
+    def _sum_tanh_node(self, y, a1, b1, a2, b2, bias):
+        B = self.B
         tr = lambda t: B.stranspose([1, 0], t)
-        y = B.smatmul2_sum_tanh(a1.p, b1.p, a2.p, b2.p, bias.p)
 
         def pb(c0, acc=None):
             if acc is not None:

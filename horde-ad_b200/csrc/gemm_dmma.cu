@@ -670,8 +670,10 @@ int hb_gemm_dmma_group(int nprod, const hb_gemm_prod *pr, int nres, const hb_gem
   if (budget < 2) budget = 2;
   int per = (total + budget - 1) / budget;
   if (per < 4) per = 4;
-  static const int per_forced = getenv("HB_GROUP_PER") ? atoi(getenv("HB_GROUP_PER")) : 0;
-  if (per_forced > 0 && nprod > 2) per = per_forced;
+  static const int per3 = getenv("HB_GROUP_PER") ? atoi(getenv("HB_GROUP_PER")) : 0;     // measurement switches
+  static const int per4 = getenv("HB_GROUP_PER4") ? atoi(getenv("HB_GROUP_PER4")) : 0;
+  const int per_forced = nprod == 3 ? per3 : nprod == 4 ? per4 : 0;
+  if (per_forced > 0) per = per_forced;
   int z = 0, zlen[GMAX] = {0, 0, 0, 0};
   p.nprod = nprod;
   for (int g = 0; g < nprod; g++) {

@@ -55,6 +55,21 @@ def rnnMnistZeroS(T, xs, params, fused=False):
     wX, wS, b, wX2, wS2, b2, w3, b3 = params
     out_width = T.shape(wS)[0]
     batch = T.shape(xs)[2]
+    if fused == "wave" and hasattr(T, "smatmul2_sum_tanh_2"):
+        # the same dataflow in WAVEFRONT order: layer 1 at row t and layer 2 at row t - 1 read only values of earlier
+        # waves (vec1 of row t - 1, vec2 of row t - 2), so the two layer bodies share one launch (four products, two
+        # tanh epilogues).  The state `sappend vec1 vec2` of rnnMnistTwoS is never materialised: each half is only
+        # ever sliced back out.  Every value is bit-identical to the row-by-row schedule's.
+        rows = T.sunravelToList(xs)
+        zero = T.srepl([out_width, batch], 0, T.dtype(wS))
+        vec1 = T.smatmul2_sum_tanh(wX, rows[0], wS, zero, b)
+        vec2 = zero
+        for x in rows[1:]:
+            vec1, vec2 = T.smatmul2_sum_tanh_2((wX, x, wS, vec1, b), (wX2, vec1, wS2, vec2, b2))
+        out = T.smatmul2_sum_tanh(wX2, vec1, wS2, vec2, b2)
+        return T.binary("add", T.smatmul2(w3, out), T.stranspose([1, 0], T.sreplicate(batch, b3)))
+    if fused == "wave":
+        fused = "pair"
     s = T.srepl([2 * out_width, batch], 0, T.dtype(wS))
     out = None
     for x in T.sunravelToList(xs):          # foldl' over the rows (:45-52)

@@ -176,3 +176,31 @@ def test_two_layer_recurrence_launches_three_products_per_step():
     for k in range(6):
         ref = fd_grad(lambda a: val(*[a if j == k else args[j] for j in range(6)]), args[k])
         np.testing.assert_allclose(grads[k], ref, rtol=1e-7, atol=1e-9)
+
+
+def test_wavefront_schedule_is_the_row_by_row_program():
+    """mnist_rnn's fused="wave" (layer 1 of row t and layer 2 of row t - 1 as one smatmul2_group forward) computes
+    the values and gradients of the row-by-row program of rnnMnistTwoS (MnistRnnShaped2.hs:71-117): on the oracle the
+    two schedules agree to the last bit forward and to rounding in the gradients (other summation order of the shared
+    cotangents)."""
+    from horde_ad_b200 import mnist_rnn
+    rng = np.random.Generator(np.random.Philox(3))
+    batch, width = 5, 12
+    glyphs, labels = rng.uniform(0, 1, (batch, 28, 28)), np.eye(10)[rng.integers(0, 10, batch)]
+    params = mnist_rnn.init_params(width, rng_range=0.2)
+
+    def run(fused):
+        B = Counting()
+        val, grads = ad.grad(B, lambda T, *ps: mnist_rnn.rnnMnistLossFusedS(T, glyphs, labels, list(ps), fused=fused), params)
+        return B, float(val), grads
+    Bw, vw, gw = run("wave")
+    Bp, vp, gp = run("pair")
+    _, v0, g0 = run(False)
+    assert vw == vp
+    np.testing.assert_allclose(vw, v0, rtol=1e-13)
+    for a, b, c in zip(gw, gp, g0):
+        np.testing.assert_allclose(a, b, rtol=1e-11, atol=1e-15)
+        np.testing.assert_allclose(a, c, rtol=1e-9, atol=1e-14)
+    # forward: 27 waves of (2 results, 4 products); backward: 26 sweep steps of (2 results, 3 products)
+    assert Bw.groups.count((2, 4, 0)) == 27 and Bw.groups.count((2, 3, 0)) == 26, Bw.groups
+    assert Bp.groups.count((2, 3, 0)) == 26 and Bp.groups.count((2, 4, 0)) == 0

@@ -968,13 +968,14 @@ def test_mnist_fcnn_gradient_vs_oracle(dev, oracle, q):
         np.testing.assert_allclose(a, b, rtol=tol * 100, atol=tol * 10)
 
 
-@pytest.mark.parametrize("fused,batch,width", [(False, 9, 24), (True, 9, 24), ("pair", 9, 24), ("pair", 200, 128)])
+@pytest.mark.parametrize("fused,batch,width", [(False, 9, 24), (True, 9, 24), ("pair", 9, 24), ("pair", 200, 128),
+                                               ("wave", 9, 24), ("wave", 200, 128), ("wave", 64, 512)])
 def test_mnist_rnn_gradient_vs_oracle(dev, oracle, fused, batch, width):
     """MnistRnnShaped2 (BASELINE config 5) at a small width: 28 unrolled steps of
     two tanh layers (smatmul2 on the DMMA GEMM), loss and the 8 gradient leaves;
     `fused`: the layer body as the tanh_affine node (`"pair"`: `wX x + wS s` as the smatmul2_sum node too:
-    paired GEMM launches forward and in both transposition rules), checked against the oracle's UNFUSED
-    program."""
+    paired GEMM launches forward and in both transposition rules; `"wave"`: the wavefront schedule, layer 1 of row t
+    and layer 2 of row t - 1 in one group launch), checked against the oracle's UNFUSED program."""
     from horde_ad_b200 import mnist_rnn
     rng = np.random.Generator(np.random.Philox(12))
     glyphs, labels = rng.uniform(0, 1, (batch, 28, 28)), np.eye(10)[rng.integers(0, 10, batch)]

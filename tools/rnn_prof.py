@@ -15,7 +15,7 @@ width, batch = 512, 1024
 params = [dev.sconcrete(p) for p in mnist_rnn.init_params(width, rng_range=0.05)]
 glyphs = dev.sconcrete(rng.uniform(0, 1, (batch, 28, 28)))
 labels = dev.sconcrete(np.eye(10)[rng.integers(0, 10, batch)])
-f = lambda: ad.grad(dev, lambda T, *ps: mnist_rnn.rnnMnistLossFusedS(T, glyphs, labels, list(ps), fused="pair"), params)
+f = lambda: ad.grad(dev, lambda T, *ps: mnist_rnn.rnnMnistLossFusedS(T, glyphs, labels, list(ps), fused=os.environ.get("RNN_FUSION", "wave")), params)
 for _ in range(2):
     f()
 dev.sync()
