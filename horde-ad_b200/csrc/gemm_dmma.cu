@@ -367,32 +367,51 @@ __global__ void __launch_bounds__(256, 2) gemm8_dmma_kernel(const __grid_constan
   const bool addc = serial ? (z > 0 || accum) : (accum && gridDim.z == 1);
   const bool cvec = (p.c_sm & 1) == 0 && ((uintptr_t)C & 15) == 0;
   const bool epi = bias != nullptr && (serial ? z + 1 == zlen : gridDim.z == 1);
+  // three phases so that the eight loads, the sixteen tanh evaluations and the eight stores of a thread each overlap
+  // among themselves (a load may not be hoisted over the previous store by the compiler)
+  if (addc) {
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int j = 0; j < 2; j++) {
+        const int m = m0 + wm + i * 8 + fr, n = n0 + wn + j * 8 + fk * 2;
+        if (m < p.M) {
+          const double *c = C + (int64_t)m * p.c_sm + n;
+          if (n + 1 < p.N && cvec) {
+            const double2 t = __ldcg(reinterpret_cast<const double2 *>(c));
+            acc[i][j][0] = t.x + acc[i][j][0];
+            acc[i][j][1] = t.y + acc[i][j][1];
+          } else {
+            if (n < p.N) acc[i][j][0] = __ldcg(c) + acc[i][j][0];
+            if (n + 1 < p.N) acc[i][j][1] = __ldcg(c + 1) + acc[i][j][1];
+          }
+        }
+      }
+  }
+  if (epi) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int m = m0 + wm + i * 8 + fr;
+      const double eb = m < p.M ? bias[m] : 0.0;
+#pragma unroll
+      for (int j = 0; j < 2; j++) {
+        acc[i][j][0] = hb_tanh_f64(acc[i][j][0] + eb);
+        acc[i][j][1] = hb_tanh_f64(acc[i][j][1] + eb);
+      }
+    }
+  }
 #pragma unroll
   for (int i = 0; i < 4; i++)
 #pragma unroll
     for (int j = 0; j < 2; j++) {
-      int m = m0 + wm + i * 8 + fr, n = n0 + wn + j * 8 + fk * 2;
+      const int m = m0 + wm + i * 8 + fr, n = n0 + wn + j * 8 + fk * 2;
       if (m < p.M) {
         double *c = C + (int64_t)m * p.c_sm + n;
-        const double eb = epi ? bias[m] : 0.0;
         if (n + 1 < p.N && cvec) {
-          double2 o = make_double2(acc[i][j][0], acc[i][j][1]);
-          if (addc) {
-            double2 t = __ldcg(reinterpret_cast<const double2 *>(c));
-            o.x = t.x + o.x;
-            o.y = t.y + o.y;
-          }
-          if (epi) { o.x = tanh(o.x + eb); o.y = tanh(o.y + eb); }
-          __stcg(reinterpret_cast<double2 *>(c), o);
+          __stcg(reinterpret_cast<double2 *>(c), make_double2(acc[i][j][0], acc[i][j][1]));
         } else {
-          if (n < p.N) {
-            double v0 = addc ? __ldcg(c) + acc[i][j][0] : acc[i][j][0];
-            __stcg(c, epi ? tanh(v0 + eb) : v0);
-          }
-          if (n + 1 < p.N) {
-            double v1 = addc ? __ldcg(c + 1) + acc[i][j][1] : acc[i][j][1];
-            __stcg(c + 1, epi ? tanh(v1 + eb) : v1);
-          }
+          if (n < p.N) __stcg(c, acc[i][j][0]);
+          if (n + 1 < p.N) __stcg(c + 1, acc[i][j][1]);
         }
       }
     }

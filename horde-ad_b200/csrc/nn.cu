@@ -815,8 +815,10 @@ __global__ void __launch_bounds__(256)
                               int64_t cols, T *__restrict__ y) {
   const int64_t n = rows * cols;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    T b = bias ? bias[i / cols] : T(0);
-    y[i] = tanh((v ? u[i] + v[i] : u[i]) + b);
+    T z = v ? u[i] + v[i] : u[i];
+    if (bias) z = z + bias[i / cols];
+    if constexpr (sizeof(T) == 8) y[i] = hb_tanh_f64(z);   // the same function as the grouped products' epilogue
+    else y[i] = tanh(z);
   }
 }
 

@@ -1014,6 +1014,27 @@ def test_tanh_affine_node(dev, dtype, shape):
     assert none is None and np.array_equal(dev.to_numpy(dz2), dev.to_numpy(dz))
 
 
+def test_layer_body_tanh_is_within_ulps_of_the_correctly_rounded_value(dev):
+    """hb_tanh_f64 (common.cuh: the branch-free tanh of hb_tanh_affine_fwd and of the grouped products' epilogue)
+    against numpy's over the whole range, in ulps; special values."""
+    rng = np.random.default_rng(41)
+    parts = [rng.uniform(-1, 1, 200000), rng.uniform(-25, 25, 200000), rng.uniform(-0.6, 0.6, 100000),
+             np.sign(rng.uniform(-1, 1, 100000)) * 10.0 ** rng.uniform(-300, 1.5, 100000),
+             np.linspace(0.3, 0.4, 24001), (np.arange(1, 60) * np.log(2) / 2)[:, None].repeat(3, 1).ravel() * (1 + np.array([-1e-15, 0, 1e-15]).repeat(59).reshape(3, 59).T.ravel())]
+    x = np.concatenate(parts)
+    x = x[: x.size // 8 * 8].reshape(8, -1)
+    got = dev.to_numpy(dev.tanh_affine_fwd(dev.sconcrete(x), None, None))
+    ref = np.tanh(x)
+    ulp = np.abs(got - ref) / np.spacing(np.abs(ref))
+    assert float(ulp.max()) <= 4.0, float(ulp.max())
+    assert np.all(np.abs(got) <= 1.0) and np.all(np.sign(got) == np.sign(x))
+    sp = np.array([[0.0, -0.0, np.inf, -np.inf, np.nan, 5e-324, -5e-324, 20.0, -20.0, 1e300, -1e300, 19.0]])
+    g = dev.to_numpy(dev.tanh_affine_fwd(dev.sconcrete(sp), None, None))[0]
+    assert g[0] == 0 and not np.signbit(g[0]) and g[1] == 0 and np.signbit(g[1])
+    assert g[2] == 1 and g[3] == -1 and np.isnan(g[4]) and g[5] == 5e-324 and g[6] == -5e-324
+    assert g[7] == 1 and g[8] == -1 and g[9] == 1 and g[10] == -1 and abs(g[11] - np.tanh(19.0)) <= 2 ** -52
+
+
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 @pytest.mark.parametrize("shape", [(512, 28, 512, 1024), (512, 512, 512, 1024), (64, 40, 24, 130), (3, 2, 5, 4)])
 def test_matmul2_sum_tanh_is_the_unfused_pair_bit_for_bit(dev, oracle, dtype, shape):
