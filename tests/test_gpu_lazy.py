@@ -42,6 +42,34 @@ def test_replay_without_the_pass_is_the_eager_program_bit_for_bit(dev):
     assert np.array_equal(dev.to_numpy(prog.outs[0]), eager)
 
 
+@pytest.mark.parametrize("fused,batch,width", [("wave", 40, 64), ("pair", 40, 64), ("wave", 7, 24)])
+def test_recorded_rnn_gradient_replays_to_the_eager_values(dev, oracle, fused, batch, width):
+    """MnistRnnShaped2's gradient with the grouped products (hb_matmul2_group), the list products (hb_matmul2_list)
+    and the accumulating tanh adjoint (hb_tanh_affine_bwd_acc) RECORDED through the C ABI and replayed: every one of
+    those entry points has a lazy form.  Replayed accumulators are never unique (the recorder holds them), so the
+    replay takes the value-semantics paths: equal to the eager run to rounding, and to the oracle's unfused program."""
+    from horde_ad_b200 import mnist_rnn
+    rng = np.random.Generator(np.random.Philox(17))
+    glyphs, labels = rng.uniform(0, 1, (batch, 28, 28)), np.eye(10)[rng.integers(0, 10, batch)]
+    params = mnist_rnn.init_params(width, rng_range=0.1)
+
+    def bucket(B, fused):
+        ins = [B.sconcrete(p) for p in params]
+        g, l = B.sconcrete(glyphs), B.sconcrete(labels)
+        val, grads = ad.grad(B, lambda T, *ps: mnist_rnn.rnnMnistLossFusedS(T, g, l, list(ps), fused=fused), ins)
+        return B.flatten_concat(list(grads) + [val])
+    eager = dev.to_numpy(bucket(dev, fused))
+    prog = dev.record(lambda: bucket(dev, fused))
+    prog.run()
+    got = dev.to_numpy(prog.outs[0])
+    np.testing.assert_allclose(got, eager, rtol=1e-10, atol=1e-14)
+    prog.run()
+    assert np.array_equal(dev.to_numpy(prog.outs[0]), got)          # deterministic
+    ov, og = ad.grad(oracle, lambda T, *ps: mnist_rnn.rnnMnistLossFusedS(T, glyphs, labels, list(ps), fused=False), params)
+    ref = np.concatenate([np.asarray(x).reshape(-1) for x in og] + [np.asarray(ov).reshape(1)])
+    np.testing.assert_allclose(got, ref, rtol=1e-9, atol=1e-13)
+
+
 @pytest.mark.parametrize("batch,hyper", [(6, (2, 2, 4, 8)), (33, (4, 4, 16, 16)), (8, (2, 3, 5, 7))])
 def test_contraction_pass_on_the_vectorised_cnn_gradient(dev, oracle, batch, hyper):
     params, glyphs, labels = _cnn_inputs(batch, hyper)
