@@ -427,7 +427,7 @@ def rnn_dp(dev, world, rank, barrier, max_over_ranks, width=512, batch=1024, ste
     return {"config": "MnistRnnShaped2 data-parallel", "width": width, "seq": 28, "per_gpu_batch": batch,
             "n_gpus": world, "scaling": "weak", "ms_per_step": step_ms, "samples_per_s": batch * world / (step_ms * 1e-3),
             "tflops_per_gpu": fl / (step_ms * 1e-3) / 1e12, "param_sum": digest,
-            "program": "paired-product / tanh_affine nodes selected above the C ABI (fused='pair')",
+            "program": "grouped products in wavefront order / accumulating tanh adjoint, selected above the C ABI (fused='wave')",
             "exchange": "hb_allreduce_adam_step (fused peer-memory all-reduce + Adam) inside the step's CUDA graph"}
 
 
