@@ -290,6 +290,14 @@ __global__ void __launch_bounds__(256, 2) gemm8_dmma_kernel(const __grid_constan
   if (kend > Kp) kend = Kp;
   const int nk = kend > kbeg ? (kend - kbeg + BK8 - 1) / BK8 : 0;
 
+  const bool fast = a_vec && b_vec && m0 + BM <= p.M && n0 + BN <= p.N;
+  const int64_t toff_a = A_KFAST ? (int64_t)(m0 + (tid >> 4)) * a_sm + (tid & 15) * 2 : (int64_t)(tid >> 5) * a_sk + m0 + (tid & 31) * 2;
+  const int64_t toff_b = B_KFAST ? (int64_t)(n0 + (tid >> 4)) * b_sn + (tid & 15) * 2 : (int64_t)(tid >> 5) * b_sk + n0 + (tid & 31) * 2;
+  const int64_t step_a = A_KFAST ? 16 * a_sm : 8 * a_sk, step_b = B_KFAST ? 16 * b_sn : 8 * b_sk;
+  const int64_t kmul_a = A_KFAST ? 1 : a_sk, kmul_b = B_KFAST ? 1 : b_sk;
+  const int da = A_KFAST ? (tid >> 4) * LDK8 + (tid & 15) * 2 : (tid >> 5) * LDM8 + (tid & 31) * 2;
+  const int db = B_KFAST ? (tid >> 4) * LDK8 + (tid & 15) * 2 : (tid >> 5) * LDM8 + (tid & 31) * 2;
+  constexpr int dstep_a = A_KFAST ? 16 * LDK8 : 8 * LDM8, dstep_b = B_KFAST ? 16 * LDK8 : 8 * LDM8;
   auto issue = [&](int c) {
     double *as = smem + (c % STAGES8) * 2 * TILE8, *bs = as + TILE8;
     const double *__restrict__ cA = gA, *__restrict__ cB = gB;
@@ -301,8 +309,19 @@ __global__ void __launch_bounds__(256, 2) gemm8_dmma_kernel(const __grid_constan
       cA = p.Al[t];
       cB = p.Bl[t];
     }
-    stage_tile8<A_KFAST>(as, cA, a_sm, a_sk, m0, p.M, k0, ke, a_vec, tid);
-    stage_tile8<B_KFAST>(bs, cB, b_sn, b_sk, n0, p.N, k0, ke, b_vec, tid);
+    if (fast && k0 + BK8 <= ke) {
+      // interior chunk of an interior tile with 16-byte aligned rows: this thread's four pieces per operand are
+      // base + thread offset + chunk offset + it * step -- eight cp.async and a few adds instead of the
+      // bounds-checked generic path
+      const double *ga = cA + toff_a + (int64_t)k0 * kmul_a, *gb = cB + toff_b + (int64_t)k0 * kmul_b;
+#pragma unroll
+      for (int it = 0; it < 4; it++) cp16(as + da + it * dstep_a, ga + it * step_a);
+#pragma unroll
+      for (int it = 0; it < 4; it++) cp16(bs + db + it * dstep_b, gb + it * step_b);
+    } else {
+      stage_tile8<A_KFAST>(as, cA, a_sm, a_sk, m0, p.M, k0, ke, a_vec, tid);
+      stage_tile8<B_KFAST>(bs, cB, b_sn, b_sk, n0, p.N, k0, ke, b_vec, tid);
+    }
     cp_commit();
   };
   double acc[4][2][2];
@@ -725,15 +744,15 @@ int hb_gemm_dmma_group(int nprod, const hb_gemm_prod *pr, int nres, const hb_gem
   p.K = p.gK[0]; p.kchunks = p.gkchunks[0];
   p.a_sm = p.ga_sm[0]; p.a_sk = p.ga_sk[0]; p.b_sk = p.gb_sk[0]; p.b_sn = p.gb_sn[0];
   p.a_vec = p.ga_vec[0]; p.b_vec = p.gb_vec[0];
+  HB_TRY(gemm_flags(&p.flags));
+  size_t smem = (size_t)STAGES8 * 2 * TILE8 * 8;
   if (nprod == 1) {        // the kernel's single-product path: one chain over gridDim.z
     p.nprod = 0;
     p.accum = res[0].accum;
     p.epi_bias = res[0].epi_bias;
   }
   if (z > 65535) return HB_OK;
-  HB_TRY(gemm_flags(&p.flags));
   dim3 grid((unsigned)gm, (unsigned)gn, (unsigned)z);
-  size_t smem = (size_t)STAGES8 * 2 * TILE8 * 8;
 #define GEMM8_LAUNCH(AK, BKF)                                                                                  \
   do {                                                                                                         \
     HB_CUDA(cudaFuncSetAttribute(gemm8_dmma_kernel<AK, BKF>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
