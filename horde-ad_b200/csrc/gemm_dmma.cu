@@ -54,20 +54,22 @@ struct GemmP {
   int a_vec, b_vec;     // 16-byte cp.async allowed
   int *flags;           // serial split-K: per output tile, the number of K slices already accumulated into C
   int accum;            // C += A x B (taddTarget fused into the product: cotangent accumulation of a weight)
-  // A GROUP of up to GMAX products of one [M, N] in one launch (hb_gemm_dmma_group; the pair of wX x + wS s, the
-  // three input cotangents of one time step of the unrolled recurrence, ...).  Product 0 is the fields above; product
-  // g >= 1 owns the K slices blockIdx.z in [zbeg[g], zbeg[g+1]).  Every product names the result it is accumulated
-  // into (gout[g]); the slices of all products of one result form ONE serial chain in product order: gzpos[g] is the
-  // chain position of product g's first slice, rzlen[r] the chain's length, rC[r] / raccum[r] / rbias[r] the result,
-  // whether the chain starts from the old contents, and the bias of the tanh epilogue of the chain's last slice
-  // (C = tanh (C + bias[m]): the body of rnnMnistLayerS without a separate elementwise pass).
-  int nprod;
+  // A GROUP of up to GMAX products of one [M, N] in one launch (hb_gemm_dmma_group / gemm8_group_kernel; the pair of
+  // wX x + wS s, the three input cotangents of one time step of the unrolled recurrence, ...).  Every product is
+  // accumulated into the result it names; the K chunks of all products of one result, in product order, are ONE
+  // sequence (its chain) that is cut into K slices: a CTA is one (tile, result, slice) and walks from one product
+  // into the next inside its slice.  gch[g] = chunks of product g, gnext[g] = the next product of the same result
+  // (-1: none), rfirst[r] = the chain's first product, rT[r] its chunks, rkch[r] chunks per slice, rzbeg[r] the
+  // first blockIdx.z of result r, rzlen[r] its slices; rC / raccum / rbias: the result, whether the chain starts
+  // from its old contents, the bias of the tanh epilogue of the last slice (C = tanh (C + bias[m]): the body of
+  // rnnMnistLayerS without a separate elementwise pass).
+  int nprod, nres;
   const double *gA[GMAX], *gB[GMAX];
   int64_t ga_sm[GMAX], ga_sk[GMAX], gb_sk[GMAX], gb_sn[GMAX];
-  int gK[GMAX], gkchunks[GMAX], ga_vec[GMAX], gb_vec[GMAX];
-  int zbeg[GMAX], gout[GMAX], gzpos[GMAX];
+  int gK[GMAX], ga_vec[GMAX], gb_vec[GMAX];
+  int gch[GMAX], gnext[GMAX];
+  int rfirst[GMAX], rT[GMAX], rkch[GMAX], rzbeg[GMAX], rzlen[GMAX], raccum[GMAX];
   double *rC[GMAX];
-  int rzlen[GMAX], raccum[GMAX];
   const double *rbias[GMAX];
   // A LIST of products of one shape accumulated into one result (hb_gemm_dmma_list: the weight cotangents
   // dW = sum_t d_t x_t^T of an unrolled loop): the K axis is the concatenation of the entries' K axes
@@ -269,22 +271,7 @@ __global__ void __launch_bounds__(256, 2) gemm8_dmma_kernel(const __grid_constan
   const double *__restrict__ gA = p.A, *__restrict__ gB = p.B;
   int64_t a_sm = p.a_sm, a_sk = p.a_sk, b_sk = p.b_sk, b_sn = p.b_sn;
   int a_vec = p.a_vec, b_vec = p.b_vec, Kp = p.nlist ? p.nlist * p.K : p.K, kch = p.kchunks;
-  int zl = (int)blockIdx.z, res = 0, zpos0 = 0;
-  if (p.nprod > 1) {
-    res = p.gout[0];
-    zpos0 = p.gzpos[0];
-#pragma unroll
-    for (int g = 1; g < GMAX; g++)
-      if (g < p.nprod && (int)blockIdx.z >= p.zbeg[g]) {
-        gA = p.gA[g]; gB = p.gB[g];
-        a_sm = p.ga_sm[g]; a_sk = p.ga_sk[g]; b_sk = p.gb_sk[g]; b_sn = p.gb_sn[g];
-        a_vec = p.ga_vec[g]; b_vec = p.gb_vec[g];
-        Kp = p.gK[g]; kch = p.gkchunks[g];
-        zl = (int)blockIdx.z - p.zbeg[g];
-        res = p.gout[g];
-        zpos0 = p.gzpos[g];
-      }
-  }
+  const int zl = (int)blockIdx.z;
   const int kbeg = zl * kch * BK8;
   int kend = kbeg + kch * BK8;
   if (kend > Kp) kend = Kp;
@@ -369,13 +356,6 @@ __global__ void __launch_bounds__(256, 2) gemm8_dmma_kernel(const __grid_constan
   int z = blockIdx.z, zlen = gridDim.z;   // position in / length of this tile's serial chain
   int accum = p.accum;
   const double *bias = p.epi_bias;
-  if (p.nprod > 1) {                       // a group: the chain of the result this product belongs to
-    z = zpos0 + zl;
-#pragma unroll
-    for (int r = 0; r < GMAX; r++)
-      if (r == res) { C = p.rC[r]; zlen = p.rzlen[r]; accum = p.raccum[r]; bias = p.rbias[r]; }
-    flag += res * (int)(gridDim.x * gridDim.y);
-  }
   if (serial && z > 0) {
     if (tid == 0) {
       while (*reinterpret_cast<volatile int *>(flag) != z) __nanosleep(64);
@@ -435,6 +415,187 @@ __global__ void __launch_bounds__(256, 2) gemm8_dmma_kernel(const __grid_constan
       }
     }
   if (serial && zlen > 1) {
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) *reinterpret_cast<volatile int *>(flag) = z + 1 == zlen ? 0 : z + 1;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// The group launch: one CTA per (tile, result, K slice of the result's chain).  Same tile, warp layout, pipeline and
+// epilogue as gemm8_dmma_kernel; the difference is that a slice is cut from the CONCATENATED chunks of all products
+// of the result, so a thin product (wX x with K = 28 next to wS s with K = 512) costs one more chunk of the CTA
+// that also multiplies its neighbour, not a CTA (and a link of the serial chain) of its own.
+template <bool A_KFAST, bool B_KFAST>
+__global__ void __launch_bounds__(256, 2) gemm8_group_kernel(const __grid_constant__ GemmP p) {
+  extern __shared__ __align__(16) double smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wm = (warp & 1) * 32, wn = (warp >> 1) * 16;
+  const int fr = lane >> 2, fk = lane & 3;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  // result, slice, chunk range inside the chain
+  int r = 0;
+#pragma unroll
+  for (int q = 1; q < GMAX; q++)
+    if (q < p.nres && (int)blockIdx.z >= p.rzbeg[q]) r = q;
+  int zbeg = p.rzbeg[0], kch = p.rkch[0], T = p.rT[0], zlen = p.rzlen[0], accum = p.raccum[0], g = p.rfirst[0];
+  double *C = p.rC[0];
+  const double *bias = p.rbias[0];
+#pragma unroll
+  for (int q = 1; q < GMAX; q++)
+    if (q == r) {
+      zbeg = p.rzbeg[q]; kch = p.rkch[q]; T = p.rT[q]; zlen = p.rzlen[q]; accum = p.raccum[q]; g = p.rfirst[q];
+      C = p.rC[q]; bias = p.rbias[q];
+    }
+  const int z = (int)blockIdx.z - zbeg;
+  const int cbeg = z * kch;
+  int cend = cbeg + kch;
+  if (cend > T) cend = T;
+  const int nk = cend > cbeg ? cend - cbeg : 0;
+  // the product the first chunk lies in, and the chunk's index there
+  int q0 = cbeg;
+#pragma unroll
+  for (int it = 0; it < GMAX - 1; it++) {
+    int gch = p.gch[0], gnext = p.gnext[0];
+#pragma unroll
+    for (int h = 1; h < GMAX; h++)
+      if (h == g) { gch = p.gch[h]; gnext = p.gnext[h]; }
+    if (q0 >= gch && gnext >= 0) { q0 -= gch; g = gnext; }
+  }
+  // staging state of the product the issue position is in (this thread's four 16-byte pieces per operand and
+  // chunk are base + it * step + the chunk's k offset; bounds-checked generic path for edges and unaligned rows)
+  int st_g = -1, st_K = 0, st_ch = 0, st_next = -1, a_vec = 0, b_vec = 0;
+  bool fast = false;
+  const double *gA = nullptr, *gB = nullptr, *pa = nullptr, *pb = nullptr;
+  int64_t a_sm = 0, a_sk = 0, b_sk = 0, b_sn = 0, step_a = 0, step_b = 0, kmul_a = 0, kmul_b = 0;
+  const int da = A_KFAST ? (tid >> 4) * LDK8 + (tid & 15) * 2 : (tid >> 5) * LDM8 + (tid & 31) * 2;
+  const int db = B_KFAST ? (tid >> 4) * LDK8 + (tid & 15) * 2 : (tid >> 5) * LDM8 + (tid & 31) * 2;
+  constexpr int dstep_a = A_KFAST ? 16 * LDK8 : 8 * LDM8, dstep_b = B_KFAST ? 16 * LDK8 : 8 * LDM8;
+  auto issue = [&](int c) {
+    double *as = smem + (c % STAGES8) * 2 * TILE8, *bs = as + TILE8;
+    if (g != st_g) {
+      st_g = g;
+      gA = p.gA[0]; gB = p.gB[0];
+      a_sm = p.ga_sm[0]; a_sk = p.ga_sk[0]; b_sk = p.gb_sk[0]; b_sn = p.gb_sn[0];
+      a_vec = p.ga_vec[0]; b_vec = p.gb_vec[0]; st_K = p.gK[0]; st_ch = p.gch[0]; st_next = p.gnext[0];
+#pragma unroll
+      for (int h = 1; h < GMAX; h++)
+        if (h == g) {
+          gA = p.gA[h]; gB = p.gB[h];
+          a_sm = p.ga_sm[h]; a_sk = p.ga_sk[h]; b_sk = p.gb_sk[h]; b_sn = p.gb_sn[h];
+          a_vec = p.ga_vec[h]; b_vec = p.gb_vec[h]; st_K = p.gK[h]; st_ch = p.gch[h]; st_next = p.gnext[h];
+        }
+      fast = a_vec && b_vec && m0 + BM <= p.M && n0 + BN <= p.N;
+      if (A_KFAST) { pa = gA + (int64_t)(m0 + (tid >> 4)) * a_sm + (tid & 15) * 2; step_a = 16 * a_sm; kmul_a = 1; }
+      else { pa = gA + (int64_t)(tid >> 5) * a_sk + m0 + (tid & 31) * 2; step_a = 8 * a_sk; kmul_a = a_sk; }
+      if (B_KFAST) { pb = gB + (int64_t)(n0 + (tid >> 4)) * b_sn + (tid & 15) * 2; step_b = 16 * b_sn; kmul_b = 1; }
+      else { pb = gB + (int64_t)(tid >> 5) * b_sk + n0 + (tid & 31) * 2; step_b = 8 * b_sk; kmul_b = b_sk; }
+    }
+    const int k0 = q0 * BK8;
+    if (fast && k0 + BK8 <= st_K) {
+      const double *ga = pa + (int64_t)k0 * kmul_a, *gb = pb + (int64_t)k0 * kmul_b;
+#pragma unroll
+      for (int it = 0; it < 4; it++) cp16(as + da + it * dstep_a, ga + it * step_a);
+#pragma unroll
+      for (int it = 0; it < 4; it++) cp16(bs + db + it * dstep_b, gb + it * step_b);
+    } else {
+      stage_tile8<A_KFAST>(as, gA, a_sm, a_sk, m0, p.M, k0, st_K, a_vec, tid);
+      stage_tile8<B_KFAST>(bs, gB, b_sn, b_sk, n0, p.N, k0, st_K, b_vec, tid);
+    }
+    cp_commit();
+    if (++q0 == st_ch && st_next >= 0) { q0 = 0; g = st_next; }   // on into the chain's next product
+  };
+  double acc[4][2][2];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 2; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+  for (int c = 0; c < STAGES8 - 1; c++) {
+    if (c < nk) issue(c);
+    else cp_commit();
+  }
+  const int aoff = A_KFAST ? (wm + fr) * LDK8 + fk : fk * LDM8 + wm + fr;
+  const int boff = B_KFAST ? (wn + fr) * LDK8 + fk : fk * LDM8 + wn + fr;
+  constexpr int a_i = A_KFAST ? 8 * LDK8 : 8, a_k = A_KFAST ? 4 : 4 * LDM8;
+  constexpr int b_j = B_KFAST ? 8 * LDK8 : 8, b_k = B_KFAST ? 4 : 4 * LDM8;
+  for (int c = 0; c < nk; c++) {
+    cp_wait<STAGES8 - 2>();
+    __syncthreads();
+    if (c + STAGES8 - 1 < nk) issue(c + STAGES8 - 1);
+    else cp_commit();
+    const double *as = smem + (c % STAGES8) * 2 * TILE8 + aoff, *bs = smem + (c % STAGES8) * 2 * TILE8 + TILE8 + boff;
+#pragma unroll
+    for (int k4 = 0; k4 < BK8 / 4; k4++) {
+      double a[4], b[2];
+#pragma unroll
+      for (int i = 0; i < 4; i++) a[i] = as[i * a_i + k4 * a_k];
+#pragma unroll
+      for (int j = 0; j < 2; j++) b[j] = bs[j * b_j + k4 * b_k];
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 2; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+  }
+  // serial chain over the result's slices (see gemm8_dmma_kernel)
+  int *flag = p.flags + r * (int)(gridDim.x * gridDim.y) + blockIdx.y * gridDim.x + blockIdx.x;
+  if (z > 0) {
+    if (tid == 0) {
+      while (*reinterpret_cast<volatile int *>(flag) != z) __nanosleep(64);
+      __threadfence();
+    }
+    __syncthreads();
+  }
+  const bool addc = z > 0 || accum;
+  const bool cvec = (p.c_sm & 1) == 0 && ((uintptr_t)C & 15) == 0;
+  const bool epi = bias != nullptr && z + 1 == zlen;
+  if (addc) {
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int j = 0; j < 2; j++) {
+        const int m = m0 + wm + i * 8 + fr, n = n0 + wn + j * 8 + fk * 2;
+        if (m < p.M) {
+          const double *c = C + (int64_t)m * p.c_sm + n;
+          if (n + 1 < p.N && cvec) {
+            const double2 t = __ldcg(reinterpret_cast<const double2 *>(c));
+            acc[i][j][0] = t.x + acc[i][j][0];
+            acc[i][j][1] = t.y + acc[i][j][1];
+          } else {
+            if (n < p.N) acc[i][j][0] = __ldcg(c) + acc[i][j][0];
+            if (n + 1 < p.N) acc[i][j][1] = __ldcg(c + 1) + acc[i][j][1];
+          }
+        }
+      }
+  }
+  if (epi) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int m = m0 + wm + i * 8 + fr;
+      const double eb = m < p.M ? bias[m] : 0.0;
+#pragma unroll
+      for (int j = 0; j < 2; j++) {
+        acc[i][j][0] = hb_tanh_f64(acc[i][j][0] + eb);
+        acc[i][j][1] = hb_tanh_f64(acc[i][j][1] + eb);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      const int m = m0 + wm + i * 8 + fr, n = n0 + wn + j * 8 + fk * 2;
+      if (m < p.M) {
+        double *c = C + (int64_t)m * p.c_sm + n;
+        if (n + 1 < p.N && cvec) {
+          __stcg(reinterpret_cast<double2 *>(c), make_double2(acc[i][j][0], acc[i][j][1]));
+        } else {
+          if (n < p.N) __stcg(c, acc[i][j][0]);
+          if (n + 1 < p.N) __stcg(c + 1, acc[i][j][1]);
+        }
+      }
+    }
+  if (zlen > 1) {
     __threadfence();
     __syncthreads();
     if (tid == 0) *reinterpret_cast<volatile int *>(flag) = z + 1 == zlen ? 0 : z + 1;
@@ -699,71 +860,67 @@ int hb_gemm_dmma_group(int nprod, const hb_gemm_prod *pr, int nres, const hb_gem
   if (gn > 65535) return HB_OK;
   const int64_t tiles = (int64_t)gm * gn;
   if (nres * tiles > kFlagTiles) return HB_OK;
-  // K slices: about two CTAs per SM over ALL products, every slice about the same depth (a K = 28 product next
-  // to a K = 512 one gets one slice and the deep one two, so the real work is still 256 CTAs of K = 256), at
-  // least 4 chunks (128 k) per slice, at most 3 slices per product
+  // K slices: about two CTAs per SM over ALL results, every slice about the same depth, cut from each result's
+  // concatenated chain (wX x with K = 28 rides in the slice of wS s); at least 4 chunks (128 k) per slice, at most
+  // 6 slices per result
   int chunks[GMAX], total = 0;
   for (int g = 0; g < nprod; g++) total += chunks[g] = (int)((pr[g].K + BK8 - 1) / BK8);
   int budget = (int)(2 * (int64_t)g_hb.sm_count / tiles);
-  if (budget < 2) budget = 2;
+  if (budget < nres) budget = nres;
   int per = (total + budget - 1) / budget;
   if (per < 4) per = 4;
   static const int per3 = getenv("HB_GROUP_PER") ? atoi(getenv("HB_GROUP_PER")) : 0;     // measurement switches
   static const int per4 = getenv("HB_GROUP_PER4") ? atoi(getenv("HB_GROUP_PER4")) : 0;
   const int per_forced = nprod == 3 ? per3 : nprod == 4 ? per4 : 0;
   if (per_forced > 0) per = per_forced;
-  int z = 0, zlen[GMAX] = {0, 0, 0, 0};
   p.nprod = nprod;
+  p.nres = nres;
+  int last[GMAX] = {-1, -1, -1, -1};
+  for (int r = 0; r < GMAX; r++) { p.rfirst[r] = -1; p.rT[r] = 0; }
   for (int g = 0; g < nprod; g++) {
-    int sp = (chunks[g] + per - 1) / per;
-    if (sp > 3 && per_forced <= 0) sp = 3;
-    if (sp < 1) sp = 1;
-    const int kch = (chunks[g] + sp - 1) / sp;
-    sp = (chunks[g] + kch - 1) / kch;
     p.gA[g] = pr[g].A; p.gB[g] = pr[g].B;
     p.ga_sm[g] = pr[g].a_sm; p.ga_sk[g] = pr[g].a_sk; p.gb_sk[g] = pr[g].b_sk; p.gb_sn[g] = pr[g].b_sn;
     p.gK[g] = (int)pr[g].K;
-    p.gkchunks[g] = kch;
     p.ga_vec[g] = ((uintptr_t)pr[g].A & 15) == 0 && ((a_kfast ? pr[g].a_sm : pr[g].a_sk) % 2 == 0);
     p.gb_vec[g] = ((uintptr_t)pr[g].B & 15) == 0 && ((b_kfast ? pr[g].b_sn : pr[g].b_sk) % 2 == 0);
-    p.zbeg[g] = z;
-    p.gout[g] = pr[g].out;
-    p.gzpos[g] = zlen[pr[g].out];
-    zlen[pr[g].out] += sp;
-    z += sp;
+    p.gch[g] = chunks[g];
+    p.gnext[g] = -1;
+    const int r = pr[g].out;
+    if (last[r] >= 0) p.gnext[last[r]] = g;
+    else p.rfirst[r] = g;
+    last[r] = g;
+    p.rT[r] += chunks[g];
   }
+  int z = 0;
   for (int r = 0; r < nres; r++) {
-    if (zlen[r] == 0) return HB_OK;                    // a result nobody writes
+    if (p.rT[r] == 0) return HB_OK;                    // a result nobody writes
+    int sp = (p.rT[r] + per - 1) / per;
+    if (sp > 6 && per_forced <= 0) sp = 6;
+    if (sp < 1) sp = 1;
+    p.rkch[r] = (p.rT[r] + sp - 1) / sp;
+    sp = (p.rT[r] + p.rkch[r] - 1) / p.rkch[r];
+    p.rzbeg[r] = z;
+    p.rzlen[r] = sp;
+    z += sp;
     p.rC[r] = res[r].C;
-    p.rzlen[r] = zlen[r];
     p.raccum[r] = res[r].accum;
     p.rbias[r] = res[r].epi_bias;
   }
-  // product 0 is also the kernel's default operand set
-  p.A = p.gA[0]; p.B = p.gB[0]; p.C = p.rC[p.gout[0]];
-  p.K = p.gK[0]; p.kchunks = p.gkchunks[0];
-  p.a_sm = p.ga_sm[0]; p.a_sk = p.ga_sk[0]; p.b_sk = p.gb_sk[0]; p.b_sn = p.gb_sn[0];
-  p.a_vec = p.ga_vec[0]; p.b_vec = p.gb_vec[0];
-  HB_TRY(gemm_flags(&p.flags));
-  size_t smem = (size_t)STAGES8 * 2 * TILE8 * 8;
-  if (nprod == 1) {        // the kernel's single-product path: one chain over gridDim.z
-    p.nprod = 0;
-    p.accum = res[0].accum;
-    p.epi_bias = res[0].epi_bias;
-  }
   if (z > 65535) return HB_OK;
+  HB_TRY(gemm_flags(&p.flags));
   dim3 grid((unsigned)gm, (unsigned)gn, (unsigned)z);
-#define GEMM8_LAUNCH(AK, BKF)                                                                                  \
+  size_t smem = (size_t)STAGES8 * 2 * TILE8 * 8;
+#define GEMM8G_LAUNCH(AK, BKF)                                                                                 \
   do {                                                                                                         \
-    HB_CUDA(cudaFuncSetAttribute(gemm8_dmma_kernel<AK, BKF>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+    HB_CUDA(cudaFuncSetAttribute(gemm8_group_kernel<AK, BKF>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
                                  (int)smem));                                                                  \
-    gemm8_dmma_kernel<AK, BKF><<<grid, 256, smem, g_hb.stream>>>(p);                                           \
+    gemm8_group_kernel<AK, BKF><<<grid, 256, smem, g_hb.stream>>>(p);                                          \
   } while (0)
-  if (a_kfast && b_kfast) GEMM8_LAUNCH(true, true);
-  else if (a_kfast) GEMM8_LAUNCH(true, false);
-  else if (b_kfast) GEMM8_LAUNCH(false, true);
-  else GEMM8_LAUNCH(false, false);
-#undef GEMM8_LAUNCH
+  if (a_kfast && b_kfast) GEMM8G_LAUNCH(true, true);
+  else if (a_kfast) GEMM8G_LAUNCH(true, false);
+  else if (b_kfast) GEMM8G_LAUNCH(false, true);
+  else GEMM8G_LAUNCH(false, false);
+#undef GEMM8G_LAUNCH
   HB_LAUNCHED();
   *done = 1;
   return HB_OK;
