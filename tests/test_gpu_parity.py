@@ -1014,6 +1014,52 @@ def test_tanh_affine_node(dev, dtype, shape):
     assert none is None and np.array_equal(dev.to_numpy(dz2), dev.to_numpy(dz))
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_matmul2_group_edge_cases(dev, oracle, dtype):
+    """Empty reduced axes, empty results, broadcast (stride-0) operands, more than four products, an accumulator
+    shared by two results, errors for inconsistent arguments."""
+    rng = np.random.default_rng(37)
+    f64 = lambda x: x.astype(np.float64)
+    # K = 0 next to K = 5; an empty result
+    for m, n, ks in [(4, 5, (0, 5)), (0, 5, (2, 2)), (3, 0, (2, 2))]:
+        a = [rnd(rng, (m, k), dtype) for k in ks]
+        b = [rnd(rng, (k, n), dtype) for k in ks]
+        outs = dev.smatmul2_group([(None, None), (None, None)], [(dev.sconcrete(a[0]), dev.sconcrete(b[0]), 0), (dev.sconcrete(a[1]), dev.sconcrete(b[1]), 1)])
+        for o, x, y in zip(outs, a, b):
+            close(dev.to_numpy(o), (f64(x) @ f64(y)).astype(dtype), dtype, scale=16)
+    # a broadcast zero state (the first time step of the recurrence) and a broadcast bias-like operand
+    m, n, k = 64, 96, 32
+    a, b = rnd(rng, (m, k), dtype), rnd(rng, (k, n), dtype)
+    zero = dev.srepl([k, n], 0.0, dtype)
+    ones = dev.srepl([k, n], 1.0, dtype)
+    o0, o1 = dev.smatmul2_group([(None, None), (None, None)], [(dev.sconcrete(a), dev.sconcrete(b), 0), (dev.sconcrete(a), zero, 0),
+                                                              (dev.sconcrete(a), ones, 1)])
+    close(dev.to_numpy(o0), (f64(a) @ f64(b)).astype(dtype), dtype, scale=8 * k)
+    close(dev.to_numpy(o1), (f64(a) @ np.ones((k, n))).astype(dtype), dtype, scale=8 * k)
+    # six products into two results (more than one launch's worth)
+    aa = [rnd(rng, (m, k), dtype) for _ in range(6)]
+    bb = [rnd(rng, (k, n), dtype) for _ in range(6)]
+    idx = [0, 1, 0, 1, 1, 0]
+    outs = dev.smatmul2_group([(None, None), (None, None)], [(dev.sconcrete(x), dev.sconcrete(y), i) for x, y, i in zip(aa, bb, idx)])
+    for r in range(2):
+        ref = sum(f64(x) @ f64(y) for x, y, i in zip(aa, bb, idx) if i == r)
+        close(dev.to_numpy(outs[r]), ref.astype(dtype), dtype, scale=8 * 6 * k)
+    # the same accumulator array named by two results: both results start from its value, it is left alone
+    acc = rnd(rng, (m, n), dtype)
+    held = dev.sconcrete(acc)
+    o0, o1 = dev.smatmul2_group([(held, None), (held, None)], [(dev.sconcrete(aa[0]), dev.sconcrete(bb[0]), 0), (dev.sconcrete(aa[1]), dev.sconcrete(bb[1]), 1)])
+    exact(dev.to_numpy(held), acc)
+    close(dev.to_numpy(o0), (f64(acc) + f64(aa[0]) @ f64(bb[0])).astype(dtype), dtype, scale=8 * k)
+    close(dev.to_numpy(o1), (f64(acc) + f64(aa[1]) @ f64(bb[1])).astype(dtype), dtype, scale=8 * k)
+    # errors: a result without a product, mismatched shapes, accumulator and epilogue together
+    with pytest.raises(Exception):
+        dev.smatmul2_group([(None, None), (None, None)], [(dev.sconcrete(aa[0]), dev.sconcrete(bb[0]), 0)])
+    with pytest.raises(Exception):
+        dev.smatmul2_group([(None, None)], [(dev.sconcrete(aa[0]), dev.sconcrete(bb[0]), 0), (dev.sconcrete(aa[0][:5]), dev.sconcrete(bb[0]), 0)])
+    with pytest.raises(Exception):
+        dev.smatmul2_group([(dev.sconcrete(acc), dev.sconcrete(acc[:, 0].copy()))], [(dev.sconcrete(aa[0]), dev.sconcrete(bb[0]), 0)])
+
+
 def test_layer_body_tanh_is_within_ulps_of_the_correctly_rounded_value(dev):
     """hb_tanh_f64 (common.cuh: the branch-free tanh of hb_tanh_affine_fwd and of the grouped products' epilogue)
     against numpy's over the whole range, in ulps; special values."""
