@@ -277,10 +277,12 @@ __device__ __forceinline__ T hb_block_range_prod(const T *__restrict__ tp, int64
   return smem[8];
 }
 
-// 58 registers: four CTAs per SM.  Forcing five or six (__launch_bounds__(256, 5 / 6): 48 / 40 registers) spills
-// and loses far more than the occupancy gains (0.43 -> 0.54 / 0.67 ms at 1e8).
+// Four CTAs per SM (64 registers, no spills; left alone the compiler takes 73 -> three CTAs: 0.428 ms at 1e8 against
+// 0.411).  Forcing five or six (48 / 40 registers) spills and loses far more than the occupancy gains (0.54 / 0.67 ms).
+// Measured without effect in this configuration: evict-first loads / streaming stores in phase B (0.412-0.417 ms), one
+// CTA barrier per tile instead of two (alternating scan scratch: 0.413 ms).
 template <typename T, bool VEC>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
     hb_prod_fused_kernel(const T *__restrict__ x, int64_t stride, int64_t n, int64_t nt, T dt, T *__restrict__ tp,
                          T *__restrict__ cp, unsigned *__restrict__ bar, T *__restrict__ total, T *__restrict__ grad,
                          int own_cap) {
