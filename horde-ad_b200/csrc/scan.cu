@@ -235,6 +235,8 @@ __global__ void __launch_bounds__(256)
 // A prefix AND a suffix are needed, so every tile's gradient depends on every other tile's product: x has to be
 // read twice unless it fits on chip -- 24 n bytes when n*8 >> L2 (126 MB), 16 n bytes of HBM traffic below that.
 // Same ordered in-tile scans as before -> deterministic; no division (exact when some x_j = 0).
+// bar[0] counts arrivals, bar[1] departures: the last CTA to LEAVE the spin puts both back to zero, so the two words
+// (allocated once, zero between launches) need no memset node in front of every launch
 __device__ __forceinline__ void hb_grid_barrier(unsigned *bar, unsigned expected) {
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -245,6 +247,11 @@ __device__ __forceinline__ void hb_grid_barrier(unsigned *bar, unsigned expected
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
       if (v < expected) __nanosleep(32);
     } while (v < expected);
+    if (atomicAdd(bar + 1, 1u) == expected - 1) {   // everybody has seen the full count
+      bar[1] = 0;
+      __threadfence();
+      bar[0] = 0;
+    }
   }
   __syncthreads();
 }
@@ -288,6 +295,7 @@ __global__ void __launch_bounds__(256, 4)
                          int own_cap) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   T *own_pre = reinterpret_cast<T *>(dyn_smem);   // [own_cap]: product of everything before own tile k
+  T *own_tp = own_pre + own_cap;                  // [own_cap]: products of the own tiles (never re-read from global)
   __shared__ T smem[16];
   __shared__ __align__(16) double stage[8 * 32 * 10];   // per warp: 32 lanes x (8 results + 2 pad)
   const int64_t G = gridDim.x, b = blockIdx.x;
@@ -307,7 +315,7 @@ __global__ void __launch_bounds__(256, 4)
     T before = hb_block_excl_prod<T>(p, false, smem);
     if (threadIdx.x == 255) {
       T tile = before * p;
-      tp[t] = tile;
+      own_tp[t - t0] = tile;
       own = own * tile;
     }
   }
@@ -319,11 +327,22 @@ __global__ void __launch_bounds__(256, 4)
   if (b == 0 && threadIdx.x == 0) *total = __ldcg(cp) * e1;   // prod x = (own range of CTA 0) * (everything after it)
   if (!grad) return;
   e1 = e1 * dt;
-  if (threadIdx.x == 0) {
-    T r = e0;
-    for (int64_t t = t0; t < t1; t++) {
-      own_pre[t - t0] = r;
-      r = r * __ldcg(tp + t);
+  if (threadIdx.x < 32) {   // exclusive prefix products of the own tiles, by one warp: a run per lane + a warp scan
+    const int cnt = (int)(t1 - t0), per = (cnt + 31) / 32, lane = threadIdx.x;
+    const int lo = lane * per < cnt ? lane * per : cnt, hi = lo + per < cnt ? lo + per : cnt;
+    T run = T(1);
+    for (int k = lo; k < hi; k++) run = run * own_tp[k];
+    T incl = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      T u = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl = u * incl;
+    }
+    T r = __shfl_up_sync(0xffffffffu, incl, 1);
+    r = lane == 0 ? e0 : e0 * r;
+    for (int k = lo; k < hi; k++) {
+      own_pre[k] = r;
+      r = r * own_tp[k];
     }
   }
   __syncthreads();
@@ -387,7 +406,7 @@ __global__ void __launch_bounds__(256, 4)
       for (int i = 0; i < 8; i++)
         if (base + i < n) grad[base + i] = out[i];
     }
-    suf = __ldcg(tp + t) * suf;   // tile t joins the suffix of the tiles before it
+    suf = own_tp[t - t0] * suf;   // tile t joins the suffix of the tiles before it
   }
 }
 
@@ -403,24 +422,28 @@ static int prod_launch_fused(const hb_array *x, int64_t n, int64_t nt, double dt
       vec ? hb_prod_fused_kernel<T, true> : hb_prod_fused_kernel<T, false>;
   int occ = 0;
   const int own_guess = 64;
-  HB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, own_guess * sizeof(T)));
+  HB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 2 * own_guess * sizeof(T)));
   if (occ < 1) return HB_OK;
   if (occ > 8) occ = 8;
   int64_t G = (int64_t)occ * g_hb.sm_count;
   if (G > nt) G = nt;
   int64_t own = (nt + G - 1) / G + 1;
-  size_t dyn = (size_t)own * sizeof(T);
+  size_t dyn = 2 * (size_t)own * sizeof(T);   // own_pre + own_tp
   if (dyn > 48 * 1024) return HB_OK;   // absurdly long vectors: the multi-launch pipeline takes them
   HB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, dyn));
   if ((int64_t)occ * g_hb.sm_count < G) {
     G = (int64_t)occ * g_hb.sm_count;
     if (G < 1) return HB_OK;
     own = (nt + G - 1) / G + 1;
-    if ((size_t)own * sizeof(T) > dyn) return HB_OK;
+    if (2 * (size_t)own * sizeof(T) > dyn) return HB_OK;
   }
   T *tp = (T *)scr, *cp = tp + nt;   // G <= nt per-CTA products in the round-1 pipeline's `pre` region
-  unsigned *bar = (unsigned *)((char *)scr + (size_t)(nt * 3 + GT) * sizeof(T));
-  HB_CUDA(cudaMemsetAsync(bar, 0, sizeof(unsigned), g_hb.stream));
+  static unsigned *bar = nullptr;   // arrival / departure counters of the grid barrier: zero between launches
+  if (!bar) {
+    HB_REQUIRE(!g_hb.capturing, "prod fold: first use inside a graph capture");
+    HB_CUDA(cudaMalloc(&bar, 2 * sizeof(unsigned)));
+    HB_CUDA(cudaMemsetAsync(bar, 0, 2 * sizeof(unsigned), g_hb.stream));
+  }
   int64_t stride = x->strides[0];
   T dtt = (T)dt;
   T *tot = (T *)hb_data(prod), *gp = grad ? (T *)hb_data(grad) : nullptr;
