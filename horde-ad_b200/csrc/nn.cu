@@ -321,13 +321,16 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// one warp per channel: lane l adds chunks l, l + 32, ... in order, the 32 lane sums are combined by a fixed shuffle
+// tree (deterministic; a single thread walking all chunks was a chain of dependent loads: 7 us for 74 chunks)
 template <typename T>
 __global__ void hb_bias_finish_kernel(const T *__restrict__ part, int C, int nchunks, T *__restrict__ out) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   if (c >= C) return;
   T s = T(0);
-  for (int k = 0; k < nchunks; k++) s += part[(int64_t)c * nchunks + k];
-  out[c] = s;
+  for (int k = lane; k < nchunks; k += 32) s += part[(int64_t)c * nchunks + k];
+  s = hb_warp_sum(s);
+  if (lane == 0) out[c] = s;
 }
 
 extern "C" int hb_relu_pool_bwd(const hb_array *dy, const hb_array *code, int ksize, int64_t H, int64_t W,
@@ -393,9 +396,9 @@ extern "C" int hb_relu_pool_bwd(const hb_array *dy, const hb_array *code, int ks
       g_hb.launches.fetch_add(1);
       if (g_hb.profiling) hb_prof_mark(__func__, __LINE__);
       if (dy->dt == HB_F64)
-        hb_bias_finish_kernel<double><<<(unsigned)((C + 127) / 128), 128, 0, g_hb.stream>>>((const double *)scr, (int)C, nchunks, (double *)hb_data(db));
+        hb_bias_finish_kernel<double><<<(unsigned)((C + 3) / 4), 128, 0, g_hb.stream>>>((const double *)scr, (int)C, nchunks, (double *)hb_data(db));
       else
-        hb_bias_finish_kernel<float><<<(unsigned)((C + 127) / 128), 128, 0, g_hb.stream>>>((const float *)scr, (int)C, nchunks, (float *)hb_data(db));
+        hb_bias_finish_kernel<float><<<(unsigned)((C + 3) / 4), 128, 0, g_hb.stream>>>((const float *)scr, (int)C, nchunks, (float *)hb_data(db));
       g_hb.launches.fetch_add(1);
       if (g_hb.profiling) hb_prof_mark(__func__, __LINE__);
       cudaError_t e = cudaPeekAtLastError();
