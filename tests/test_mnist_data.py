@@ -130,3 +130,37 @@ def test_training_from_resident_data_equals_training_from_host_batches(dev):
         assert np.array_equal(pa, pb)
     a.close()
     b.close()
+
+
+@pytest.mark.gpu
+def test_pipelined_train_step_equals_plain_uploads(dev):
+    """CnnTrainer.train_step(cur, next): the next minibatch is copied to the device during the step and moved into the
+    step's input arrays right behind it -- the same losses and parameters as uploading every batch in its own call;
+    an upload or another batch in between invalidates what was staged."""
+    from horde_ad_b200.train import CnnTrainer, PinnedBuffer
+    rng = np.random.default_rng(5)
+    B, nb = 16, 5
+    bufs = []
+    for _ in range(nb):
+        g, t = PinnedBuffer((B, 28, 28), np.float64), PinnedBuffer((B, 10), np.float64)
+        g.array[...] = rng.uniform(0, 1, (B, 28, 28))
+        t.array[...] = np.eye(10)[rng.integers(0, 10, B)]
+        bufs.append((g, t))
+    a = CnnTrainer(dev, B, kh=2, kw=2, c_out=4, n_hidden=8)
+    b = CnnTrainer(dev, B, kh=2, kw=2, c_out=4, n_hidden=8)
+    seq = [0, 1, 2, 3, 4, 0, 2]
+    la = [a.train_step(bufs[i][0].ptr, bufs[i][1].ptr) for i in seq]
+    lb = []
+    for k, i in enumerate(seq):
+        nxt = bufs[seq[k + 1]] if k + 1 < len(seq) else (None, None)
+        if k == 4:       # the caller changes its mind: batch 0 was announced, an explicit upload of batch 3 comes first
+            b.upload(bufs[3][0].ptr, bufs[3][1].ptr)
+        lb.append(b.train_step(bufs[i][0].ptr, bufs[i][1].ptr, *(x.ptr if x is not None else None for x in nxt)))
+    assert la == lb
+    for pa, pb in zip(a.get_params(), b.get_params()):
+        assert np.array_equal(pa, pb)
+    a.close()
+    b.close()
+    for g, t in bufs:
+        g.free()
+        t.free()
